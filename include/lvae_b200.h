@@ -1,0 +1,144 @@
+/* lvae_b200.h -- C ABI of liblvae_b200.so (hand-written sm_100a kernels for the Ladder VAE hot path).
+ *
+ * The reference (addtt/ladder-vae-pytorch) has no FFI: its "operators" are PyTorch nn.Modules
+ * whose kernels are ATen/cuDNN library calls.  Each entry point below names the reference code
+ * (file:line under the reference tree) whose GPU work it replaces; INTEGRATION.md shows the
+ * ctypes stub a reference maintainer would add at that spot.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless noted; the caller (PyTorch) owns all memory;
+ *   - activations are NHWC: (B, H, W, C) contiguous; `dtype` 0 = float32, 1 = bfloat16;
+ *     images handed in by the user (`x` of the likelihoods, pad source) are NCHW float32;
+ *   - `stream` is the cudaStream_t to launch on; kernels never allocate or synchronise, so
+ *     every call can be captured into a CUDA graph;
+ *   - return 0 on success, non-zero on error; lvae_last_error() gives the message
+ *     (bad arguments are rejected before any launch).
+ */
+#ifndef LVAE_B200_H
+#define LVAE_B200_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* lvae_stream_t; /* cudaStream_t */
+
+/* ---- plumbing ---- */
+const char* lvae_last_error(void);
+int lvae_abi_version(void);
+unsigned long long lvae_launch_count(void); /* kernels launched by this library so far */
+void lvae_reset_launch_count(void);
+int lvae_device_check(void); /* 0 iff the current device is sm_10x */
+
+/* ---- convolutions: nn.Conv2d / nn.ConvTranspose2d forward, dgrad, wgrad ----
+ * replaces cuDNN behind lib/nn.py:83-87 (3x3 residual convs), lib/nn.py:118 (1x1 gate conv),
+ * lib/stochastic.py:25-27 (conv_in_p / conv_in_q / conv_out), models/lvae_layers.py:263-276
+ * (strided / transposed resampling), models/lvae_layers.py:350,359 (1x1 merge over cat(x, x2)),
+ * models/lvae.py:75 (5x5 stem), lib/likelihoods.py:55,199 (heads).
+ *   y[b,oy,ox,n] = ( sum_{ky,kx,c} in[b,iy,ix,c] * wp[(ky*kw+kx)*(C1+C2)+c][n] + bias[n] ) * out_scale[b,n] + res
+ *   mode 0: iy = oy*stride - pad + ky          (Conv2d forward, ConvTranspose2d dgrad)
+ *   mode 1: iy = (oy + pad - ky) / stride      (Conv2d dgrad, ConvTranspose2d forward)
+ * `in` is the channel concatenation of x (C1) and x2 (C2, may be NULL/0); in_scale (B,C1+C2) and
+ * out_scale (B,N) are per-sample channel scales (Dropout2d, lib/nn.py:62,76,89) or NULL. */
+int lvae_conv2d_gather(const void* x, const void* x2, const void* wp, const float* bias, const float* in_scale,
+                       const float* out_scale, const void* res, void* y, int B, int Hi, int Wi, int C1, int C2,
+                       int Ho, int Wo, int N, int ldw, int kh, int kw, int stride, int pad, int mode, int dtype,
+                       lvae_stream_t stream);
+/* dw[o][i][ky][kx] += sum dz[b,oy,ox,o] * u[b,oy*stride-pad+ky,ox*stride-pad+kx,i]; dbias[o] += sum dz.
+ * dw is the torch parameter layout (O,I,kh,kw) fp32; for ConvTranspose2d pass (u=dy, dz=x). */
+int lvae_conv2d_wgrad(const void* u, const void* u2, const void* dz, const float* in_scale, const float* out_scale,
+                      float* dw, float* dbias, int B, int Hi, int Wi, int C1, int C2, int Ho, int Wo, int O, int kh,
+                      int kw, int stride, int pad, int dtype, lvae_stream_t stream);
+/* Re-layout torch (O,I,kh,kw) weights into GEMM rows; descs_dev = device array of n LvaePackDesc
+ * {const float* src; void* dst; int O, I, taps, mode, ld, dtype} (see csrc/conv_generic.cu). */
+int lvae_pack_weights(const void* descs_dev, int n, lvae_stream_t stream);
+int lvae_pack_desc_size(void);
+/* out[c] += sum_{b,hw} dy[b,hw,c] * scale[b,c]  (ConvTranspose2d bias gradient) */
+int lvae_colsum(const void* dy, const float* scale, float* out, int B, int HW, int C, int dtype, lvae_stream_t stream);
+
+/* ---- BatchNorm2d (+ nonlinearity) : lib/nn.py:60,67,81 + models/lvae.py:64-69 ----
+ * act: 0 none, 1 relu, 2 leaky_relu(0.01), 3 elu, 4 selu.  acc = 2*C doubles, zero on entry,
+ * left zero on exit.  Train mode: stats -> finalize (also updates running_mean/var and
+ * num_batches_tracked on the device) -> bn_act_fwd.  Eval mode: eval_prepare -> bn_act_fwd. */
+int lvae_bn_stats(const void* x, double* acc, long long P, int C, int dtype, lvae_stream_t stream);
+int lvae_bn_finalize(double* acc, float* save_mean, float* save_rstd, float* running_mean, float* running_var,
+                     long long* num_batches_tracked, long long P, int C, float momentum, float eps,
+                     lvae_stream_t stream);
+int lvae_bn_eval_prepare(const float* running_mean, const float* running_var, float* save_mean, float* save_rstd,
+                         int C, float eps, lvae_stream_t stream);
+/* y = act(((x-mean)*rstd)*gamma+beta); mean == NULL -> plain activation */
+int lvae_bn_act_fwd(const void* x, void* y, const float* mean, const float* rstd, const float* gamma,
+                    const float* beta, long long P, int C, int act, int dtype_in, int dtype_out,
+                    lvae_stream_t stream);
+/* dx, dgamma += , dbeta += ; training = 1 uses batch-statistics backward */
+int lvae_bn_act_bwd(const void* dy, const void* x, void* dx, const float* mean, const float* rstd,
+                    const float* gamma, const float* beta, double* acc, float* dgamma, float* dbeta, long long P,
+                    int C, int act, int training, int dtype, lvae_stream_t stream);
+
+/* ---- GateLayer2d product + residual: lib/nn.py:121-126 and :99 ----
+ * h (P,2C): out = act(h[:, :C]) * sigmoid(h[:, C:]) + res */
+int lvae_gate_fwd(const void* h, const void* res, void* out, long long P, int C, int act, int dtype,
+                  lvae_stream_t stream);
+int lvae_gate_bwd(const void* dout, const void* h, void* dh, long long P, int C, int act, int dtype,
+                  lvae_stream_t stream);
+
+/* ---- boilr helpers used inside the model: Interpolate(scale=2) (models/lvae.py:144),
+ *      pad_img_tensor / crop_img_tensor (models/lvae.py:176,185,324,357) ---- */
+int lvae_upsample2x_fwd(const void* x, void* y, int B, int H, int W, int C, int dtype, lvae_stream_t stream);
+int lvae_upsample2x_bwd(const void* dy, void* dx, int B, int H, int W, int C, int dtype, lvae_stream_t stream);
+int lvae_copy_window(const void* src, void* dst, int B, int C, int Hs, int Ws, int Hd, int Wd, int sy0, int sx0,
+                     int dy0, int dx0, int h, int w, int src_nchw, int dst_nchw, int src_dtype, int dst_dtype,
+                     lvae_stream_t stream);
+
+/* ---- randomness: device-resident Philox state {uint64 seed, uint64 offset} ---- */
+int lvae_dropout_masks(float* masks, long long n, float p, const void* rng_state, unsigned long long stream_id,
+                       lvae_stream_t stream); /* nn.Dropout2d masks for every site of a step, lib/nn.py:62,76,89 */
+int lvae_rng_advance(void* rng_state, unsigned long long inc, lvae_stream_t stream);
+int lvae_sum_batch(const float* x, float* out, int B, long long n, int accumulate, lvae_stream_t stream);
+
+/* ---- NormalStochasticBlock2d core: lib/stochastic.py:45-96 and kl_normal_mc :209-226 ----
+ * q, p: (B,hw,2Z) fp32 rows [mu | logvar]; p_broadcast = 1 when p has batch 1 (learned top prior,
+ * models/lvae_layers.py:131-136).  z = mu_q + exp(lv_q/2)*eps with eps given, or Philox when eps == NULL;
+ * forced != NULL -> z = forced; use_mode -> z = mu.  q == NULL -> sample from p (generation).
+ * Outputs: z (B,hw,Z) [+ optional bf16 copy], kl_sample (B) (MC log q - log p, or analytic),
+ * kl_spatial (B,hw) (always analytic), logp (B), logq (B). */
+int lvae_stoch_fwd(const float* q, const float* p, int p_broadcast, const float* eps, const float* forced,
+                   const void* rng_state, unsigned long long stream_id, float* z, void* z_bf16, float* kl_sample,
+                   float* kl_spatial, float* logp, float* logq, int B, int hw, int Z, int use_mode, int analytical,
+                   lvae_stream_t stream);
+/* z_kind: 1 reparameterised sample, 2 mode, 0 forced latent.  dq, dp: (B,hw,2Z). */
+int lvae_stoch_bwd(const float* q, const float* p, int p_broadcast, const float* z, const float* g_z,
+                   const float* g_kl, const float* g_logp, const float* g_logq, const float* g_kls, float* dq,
+                   float* dp, int B, int hw, int Z, int analytical, int z_kind, lvae_stream_t stream);
+
+/* ---- likelihoods: lib/likelihoods.py ----
+ * Bernoulli (:51-78, log_bernoulli :385-388): logits (B,hw,C) NHWC, x (B,C,hw) NCHW. */
+int lvae_bernoulli_fwd(const float* logits, const float* x, float* prob, float* ll, int B, int hw, int C,
+                       lvae_stream_t stream);
+int lvae_bernoulli_bwd(const float* prob, const float* x, const float* g_ll, const float* g_prob, float* dlogits,
+                       int B, int hw, int C, lvae_stream_t stream);
+int lvae_bernoulli_sample(const float* prob, float* out_nchw, int B, int hw, int C, const void* rng_state,
+                          unsigned long long stream_id, lvae_stream_t stream);
+/* 10-component discretized mixture of logistics (:183-230, discretized_mix_logistic_loss :291-382):
+ * l (B,hw,100) NHWC, x (B,3,hw) NCHW in [0,1]; ll (B) must be zero on entry (fwd accumulates). */
+int lvae_dmol_fwd(const float* l, const float* x, float* ll, int B, int hw, lvae_stream_t stream);
+int lvae_dmol_bwd(const float* l, const float* x, const float* g_ll, float* dl, int B, int hw, lvae_stream_t stream);
+/* sample_from_discretized_mix_logistic (lib/stochastic.py:141-206) + rescale/clamp (likelihoods.py:221-225) */
+int lvae_dmol_sample(const float* l, float* out_nchw, int B, int hw, const void* rng_state,
+                     unsigned long long stream_id, lvae_stream_t stream);
+
+/* ---- step glue: experiment/experiment_manager.py:78-80 (Adamax), :346-350 (L2 norm) ---- */
+int lvae_adamax_step(float* p, const float* g, float* exp_avg, float* exp_inf, long long n, float lr, float beta1,
+                     float beta2, float eps, float weight_decay, long long* step_count_dev, float grad_scale,
+                     lvae_stream_t stream);
+int lvae_l2_norm(const float* p, long long n, double* acc, float* out, lvae_stream_t stream);
+
+/* ---- importance-weighted bound (boilr test_procedure, call site evaluate.py:30) ----
+ * state (B,2) = running (max, sum exp) of elbo = ll - kl over samples; combine merges R ranks' states. */
+int lvae_iw_lse_update(const float* ll, const float* kl, float* state, int B, int first, lvae_stream_t stream);
+int lvae_iw_lse_combine(const float* states, float* out, int R, int B, int K_total, lvae_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LVAE_B200_H */

@@ -1,0 +1,495 @@
+// Generic implicit-GEMM convolution on CUDA cores (fp32 accumulate), NHWC activations.
+//
+// This is the exact-fp32 path (parity runs, odd shapes: 5x5 stem, 64->100 / 64->1 heads,
+// strided / transposed 3x3).  The bf16 tcgen05 kernels in conv_tcgen05.cu take over the
+// dominant 64-channel shapes.  Replaces the cuDNN calls behind nn.Conv2d / nn.ConvTranspose2d
+// at lib/nn.py:83-87,118, lib/stochastic.py:25-27, models/lvae_layers.py:263-276,350,
+// models/lvae.py:75 and lib/likelihoods.py:55,199 (forward, dgrad and wgrad).
+#include "common.cuh"
+
+struct ConvArgs {
+  const void* x;        // (B,Hi,Wi,C1)
+  const void* x2;       // optional (B,Hi,Wi,C2): channel-concatenated second input (MergeLayer)
+  const void* wp;       // packed weights [kh*kw*(C1+C2)][ldw]
+  const float* bias;    // [N] or null
+  const float* in_scale;   // (B, C1+C2) per-sample channel scale on the input, or null
+  const float* out_scale;  // (B, N) per-sample channel scale on the output (Dropout2d), or null
+  const void* res;      // optional residual (B,Ho,Wo,N) added after scaling
+  void* y;              // (B,Ho,Wo,N)
+  int B, Hi, Wi, C1, C2, Ho, Wo, N, ldw;
+  int kh, kw, stride, pad, mode;  // mode 0: iy = oy*stride - pad + ky ; mode 1: iy = (oy + pad - ky)/stride
+};
+
+constexpr int CG_BM = 128, CG_BN = 64, CG_BK = 32, CG_THREADS = 256;
+constexpr int CG_APITCH = CG_BK + 4;
+
+template <typename T, bool VEC>
+__global__ void __launch_bounds__(CG_THREADS) conv_gather_kernel(ConvArgs a) {
+  __shared__ __align__(16) float As[CG_BM][CG_APITCH];
+  __shared__ __align__(16) float Bs[CG_BK][CG_BN];
+  const int t = threadIdx.x;
+  const int Cin = a.C1 + a.C2;
+  const int K = a.kh * a.kw * Cin;
+  const long long M = (long long)a.B * a.Ho * a.Wo;
+  const long long m0 = (long long)blockIdx.x * CG_BM;
+  const int n0 = blockIdx.y * CG_BN;
+  const T* x = (const T*)a.x;
+  const T* x2 = (const T*)a.x2;
+  const T* wp = (const T*)a.wp;
+
+  // --- A-load bookkeeping: this thread loads rows (t/8 + 32 i), k-quad (t%8) ---
+  const int kq = t & 7;
+  int pb[4], py[4], px[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    long long m = m0 + (t >> 3) + 32 * i;
+    if (m < M) {
+      int hw = a.Ho * a.Wo;
+      pb[i] = (int)(m / hw);
+      int r = (int)(m - (long long)pb[i] * hw);
+      py[i] = r / a.Wo;
+      px[i] = r - py[i] * a.Wo;
+    } else {
+      pb[i] = -1; py[i] = 0; px[i] = 0;
+    }
+  }
+  // --- B-load bookkeeping: rows (t/16 + 16 i), col-quad (t%16) ---
+  const int bq = t & 15;
+
+  float acc[8][4];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+  const int tm = t >> 4, tn = t & 15;
+  float4 ra[4], rb[2];
+
+  auto load_tiles = [&](int k0) {
+    // A: gathered input patch
+    int k = k0 + kq * 4;
+    if (VEC) {
+      int tap = k / Cin, ci = k - tap * Cin;
+      int ky = tap / a.kw, kx = tap - ky * a.kw;
+      bool kvalid = k < K;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (kvalid && pb[i] >= 0) {
+          int iy, ix;
+          bool ok;
+          if (a.mode == 0) {
+            iy = py[i] * a.stride - a.pad + ky;
+            ix = px[i] * a.stride - a.pad + kx;
+            ok = iy >= 0 && iy < a.Hi && ix >= 0 && ix < a.Wi;
+          } else {
+            int ty = py[i] + a.pad - ky, tx = px[i] + a.pad - kx;
+            ok = ty >= 0 && tx >= 0 && (ty % a.stride) == 0 && (tx % a.stride) == 0;
+            iy = ty / a.stride;
+            ix = tx / a.stride;
+            ok = ok && iy < a.Hi && ix < a.Wi;
+          }
+          if (ok) {
+            long long pix = ((long long)pb[i] * a.Hi + iy) * a.Wi + ix;
+            v = ci < a.C1 ? ld4<T>(x + pix * a.C1 + ci) : ld4<T>(x2 + pix * a.C2 + (ci - a.C1));
+            if (a.in_scale) {
+              float4 s = *reinterpret_cast<const float4*>(a.in_scale + (long long)pb[i] * Cin + ci);
+              v.x *= s.x; v.y *= s.y; v.z *= s.z; v.w *= s.w;
+            }
+          }
+        }
+        ra[i] = v;
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        float vv[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          int kk = k + j;
+          float v = 0.f;
+          if (kk < K && pb[i] >= 0) {
+            int tap = kk / Cin, ci = kk - tap * Cin;
+            int ky = tap / a.kw, kx = tap - ky * a.kw;
+            int iy, ix;
+            bool ok;
+            if (a.mode == 0) {
+              iy = py[i] * a.stride - a.pad + ky;
+              ix = px[i] * a.stride - a.pad + kx;
+              ok = iy >= 0 && iy < a.Hi && ix >= 0 && ix < a.Wi;
+            } else {
+              int ty = py[i] + a.pad - ky, tx = px[i] + a.pad - kx;
+              ok = ty >= 0 && tx >= 0 && (ty % a.stride) == 0 && (tx % a.stride) == 0;
+              iy = ty / a.stride;
+              ix = tx / a.stride;
+              ok = ok && iy < a.Hi && ix < a.Wi;
+            }
+            if (ok) {
+              long long pix = ((long long)pb[i] * a.Hi + iy) * a.Wi + ix;
+              v = ci < a.C1 ? ld1<T>(x + pix * a.C1 + ci) : ld1<T>(x2 + pix * a.C2 + (ci - a.C1));
+              if (a.in_scale) v *= a.in_scale[(long long)pb[i] * Cin + ci];
+            }
+          }
+          vv[j] = v;
+        }
+        ra[i] = make_float4(vv[0], vv[1], vv[2], vv[3]);
+      }
+    }
+    // B: packed weights, rows k, ldw is a multiple of 4
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      int kr = k0 + (t >> 4) + 16 * i;
+      int n = n0 + bq * 4;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (kr < K && n < a.ldw) v = ld4<T>(wp + (long long)kr * a.ldw + n);
+      rb[i] = v;
+    }
+  };
+
+  load_tiles(0);
+  for (int k0 = 0; k0 < K; k0 += CG_BK) {
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < 4; ++i) *reinterpret_cast<float4*>(&As[(t >> 3) + 32 * i][kq * 4]) = ra[i];
+#pragma unroll
+    for (int i = 0; i < 2; ++i) *reinterpret_cast<float4*>(&Bs[(t >> 4) + 16 * i][bq * 4]) = rb[i];
+    __syncthreads();
+    if (k0 + CG_BK < K) load_tiles(k0 + CG_BK);
+#pragma unroll
+    for (int k4 = 0; k4 < CG_BK; k4 += 4) {
+      float4 b4[4];
+#pragma unroll
+      for (int kk = 0; kk < 4; ++kk) b4[kk] = *reinterpret_cast<const float4*>(&Bs[k4 + kk][tn * 4]);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        float4 a4 = *reinterpret_cast<const float4*>(&As[tm * 8 + i][k4]);
+        acc[i][0] += a4.x * b4[0].x; acc[i][1] += a4.x * b4[0].y; acc[i][2] += a4.x * b4[0].z; acc[i][3] += a4.x * b4[0].w;
+        acc[i][0] += a4.y * b4[1].x; acc[i][1] += a4.y * b4[1].y; acc[i][2] += a4.y * b4[1].z; acc[i][3] += a4.y * b4[1].w;
+        acc[i][0] += a4.z * b4[2].x; acc[i][1] += a4.z * b4[2].y; acc[i][2] += a4.z * b4[2].z; acc[i][3] += a4.z * b4[2].w;
+        acc[i][0] += a4.w * b4[3].x; acc[i][1] += a4.w * b4[3].y; acc[i][2] += a4.w * b4[3].z; acc[i][3] += a4.w * b4[3].w;
+      }
+    }
+  }
+
+  // --- epilogue: (acc + bias) * out_scale + res ---
+  T* y = (T*)a.y;
+  const T* res = (const T*)a.res;
+  const int n = n0 + tn * 4;
+  if (n >= a.N) return;
+  const int hw = a.Ho * a.Wo;
+  float bv[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) bv[j] = (a.bias && n + j < a.N) ? a.bias[n + j] : 0.f;
+  const bool vec_out = (a.N & 3) == 0;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    long long m = m0 + tm * 8 + i;
+    if (m >= M) break;
+    int b = (int)(m / hw);
+    float o[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      o[j] = acc[i][j] + bv[j];
+      if (a.out_scale && n + j < a.N) o[j] *= a.out_scale[(long long)b * a.N + n + j];
+    }
+    long long off = m * a.N + n;
+    if (vec_out) {
+      if (res) {
+        float4 r = ld4<T>(res + off);
+        o[0] += r.x; o[1] += r.y; o[2] += r.z; o[3] += r.w;
+      }
+      st4<T>(y + off, make_float4(o[0], o[1], o[2], o[3]));
+    } else {
+      for (int j = 0; j < 4 && n + j < a.N; ++j) {
+        float v = o[j];
+        if (res) v += ld1<T>(res + off + j);
+        st1<T>(y + off + j, v);
+      }
+    }
+  }
+}
+
+LVAE_API int lvae_conv2d_gather(const void* x, const void* x2, const void* wp, const float* bias,
+                                const float* in_scale, const float* out_scale, const void* res, void* y,
+                                int B, int Hi, int Wi, int C1, int C2, int Ho, int Wo, int N, int ldw,
+                                int kh, int kw, int stride, int pad, int mode, int dtype, cudaStream_t stream) {
+  LVAE_REQUIRE(x && wp && y, "conv2d_gather: null pointer");
+  LVAE_REQUIRE(B > 0 && Hi > 0 && Wi > 0 && C1 > 0 && C2 >= 0 && Ho > 0 && Wo > 0 && N > 0, "conv2d_gather: bad shape");
+  LVAE_REQUIRE((C2 == 0) == (x2 == nullptr), "conv2d_gather: x2/C2 mismatch");
+  LVAE_REQUIRE(ldw % 4 == 0 && ldw >= N, "conv2d_gather: ldw must be a multiple of 4 and >= N");
+  LVAE_REQUIRE(mode == 0 || mode == 1, "conv2d_gather: bad mode");
+  LVAE_REQUIRE(dtype == 0 || dtype == 1, "conv2d_gather: dtype must be 0 (f32) or 1 (bf16)");
+  ConvArgs a{x, x2, wp, bias, in_scale, out_scale, res, y, B, Hi, Wi, C1, C2, Ho, Wo, N, ldw, kh, kw, stride, pad, mode};
+  long long M = (long long)B * Ho * Wo;
+  dim3 grid(cdiv(M, CG_BM), cdiv(N, CG_BN));
+  bool vec = (C1 % 4 == 0) && (C2 % 4 == 0);
+  if (dtype == 0) {
+    if (vec) conv_gather_kernel<float, true><<<grid, CG_THREADS, 0, stream>>>(a);
+    else conv_gather_kernel<float, false><<<grid, CG_THREADS, 0, stream>>>(a);
+  } else {
+    if (vec) conv_gather_kernel<__nv_bfloat16, true><<<grid, CG_THREADS, 0, stream>>>(a);
+    else conv_gather_kernel<__nv_bfloat16, false><<<grid, CG_THREADS, 0, stream>>>(a);
+  }
+  LVAE_COUNT_LAUNCH();
+  LVAE_CHECK_LAUNCH("conv2d_gather");
+  return LVAE_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// wgrad: dW[o][i][ky][kx] += sum_{b,oy,ox} dz[b,oy,ox,o] * u[b, oy*stride-pad+ky, ox*stride-pad+kx, i]
+// (u may be the channel concat of u1,u2).  For ConvTranspose2d the caller swaps roles
+// (u = dy, dz = x), which yields the (Cin,Cout,kh,kw) layout directly.
+// dbias[o] += sum dz[...,o] (only when dbias != null).
+// ------------------------------------------------------------------------------------------
+struct WgradArgs {
+  const void* u; const void* u2; const void* dz;
+  const float* in_scale;   // (B, I) on u
+  const float* out_scale;  // (B, O) on dz
+  float* dw; float* dbias;
+  int B, Hi, Wi, C1, C2, Ho, Wo, O, kh, kw, stride, pad;
+  int m_per_cta;
+};
+
+constexpr int WG_BK = 64, WG_BN = 64, WG_BM = 32, WG_THREADS = 256;
+
+template <typename T, bool VEC>
+__global__ void __launch_bounds__(WG_THREADS) conv_wgrad_kernel(WgradArgs a) {
+  __shared__ __align__(16) float As[WG_BM][WG_BK + 4];
+  __shared__ __align__(16) float Ds[WG_BM][WG_BN + 4];
+  const int t = threadIdx.x;
+  const int I = a.C1 + a.C2;
+  const int K = a.kh * a.kw * I;
+  const long long M = (long long)a.B * a.Ho * a.Wo;
+  const int k0 = blockIdx.x * WG_BK, n0 = blockIdx.y * WG_BN;
+  const long long mbeg = (long long)blockIdx.z * a.m_per_cta;
+  const long long mend = min(M, mbeg + (long long)a.m_per_cta);
+  const T* u = (const T*)a.u;
+  const T* u2 = (const T*)a.u2;
+  const T* dz = (const T*)a.dz;
+  const int hw = a.Ho * a.Wo;
+
+  // load mapping: pixel rows (t/16 + 16 i), quad (t%16)
+  const int q = t & 15;
+  // k decode for this thread's A quad is fixed over the whole loop
+  int kk = k0 + q * 4;
+  int tapv = 0, civ = 0, kyv = 0, kxv = 0;
+  if (VEC) {
+    tapv = kk / I; civ = kk - tapv * I; kyv = tapv / a.kw; kxv = tapv - kyv * a.kw;
+  }
+  const int tk = t >> 4, tn = t & 15;
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  float bsum[4] = {0.f, 0.f, 0.f, 0.f};
+  const bool do_bias = a.dbias != nullptr && blockIdx.x == 0;
+
+  for (long long mc = mbeg; mc < mend; mc += WG_BM) {
+    float4 ra[2], rd[2];
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      long long m = mc + (t >> 4) + 16 * i;
+      float4 va = make_float4(0.f, 0.f, 0.f, 0.f), vd = va;
+      if (m < mend) {
+        int b = (int)(m / hw);
+        int r = (int)(m - (long long)b * hw);
+        int oy = r / a.Wo, ox = r - oy * a.Wo;
+        // dz quad
+        int n = n0 + q * 4;
+        if (n < a.O) {
+          if ((a.O & 3) == 0) {
+            vd = ld4<T>(dz + m * a.O + n);
+          } else {
+            float tmp[4] = {0.f, 0.f, 0.f, 0.f};
+            for (int j = 0; j < 4 && n + j < a.O; ++j) tmp[j] = ld1<T>(dz + m * a.O + n + j);
+            vd = make_float4(tmp[0], tmp[1], tmp[2], tmp[3]);
+          }
+          if (a.out_scale) {
+            float s[4] = {1.f, 1.f, 1.f, 1.f};
+            for (int j = 0; j < 4 && n + j < a.O; ++j) s[j] = a.out_scale[(long long)b * a.O + n + j];
+            vd.x *= s[0]; vd.y *= s[1]; vd.z *= s[2]; vd.w *= s[3];
+          }
+        }
+        // gathered u quad
+        if (VEC) {
+          if (kk < K) {
+            int iy = oy * a.stride - a.pad + kyv, ix = ox * a.stride - a.pad + kxv;
+            if (iy >= 0 && iy < a.Hi && ix >= 0 && ix < a.Wi) {
+              long long pix = ((long long)b * a.Hi + iy) * a.Wi + ix;
+              va = civ < a.C1 ? ld4<T>(u + pix * a.C1 + civ) : ld4<T>(u2 + pix * a.C2 + (civ - a.C1));
+              if (a.in_scale) {
+                float4 s = *reinterpret_cast<const float4*>(a.in_scale + (long long)b * I + civ);
+                va.x *= s.x; va.y *= s.y; va.z *= s.z; va.w *= s.w;
+              }
+            }
+          }
+        } else {
+          float tmp[4] = {0.f, 0.f, 0.f, 0.f};
+          for (int j = 0; j < 4; ++j) {
+            int k = kk + j;
+            if (k < K) {
+              int tap = k / I, ci = k - tap * I, ky = tap / a.kw, kx = tap - ky * a.kw;
+              int iy = oy * a.stride - a.pad + ky, ix = ox * a.stride - a.pad + kx;
+              if (iy >= 0 && iy < a.Hi && ix >= 0 && ix < a.Wi) {
+                long long pix = ((long long)b * a.Hi + iy) * a.Wi + ix;
+                float v = ci < a.C1 ? ld1<T>(u + pix * a.C1 + ci) : ld1<T>(u2 + pix * a.C2 + (ci - a.C1));
+                if (a.in_scale) v *= a.in_scale[(long long)b * I + ci];
+                tmp[j] = v;
+              }
+            }
+          }
+          va = make_float4(tmp[0], tmp[1], tmp[2], tmp[3]);
+        }
+      }
+      ra[i] = va;
+      rd[i] = vd;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      *reinterpret_cast<float4*>(&As[(t >> 4) + 16 * i][q * 4]) = ra[i];
+      *reinterpret_cast<float4*>(&Ds[(t >> 4) + 16 * i][q * 4]) = rd[i];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int p = 0; p < WG_BM; ++p) {
+      float4 a4 = *reinterpret_cast<const float4*>(&As[p][tk * 4]);
+      float4 d4 = *reinterpret_cast<const float4*>(&Ds[p][tn * 4]);
+      acc[0][0] += a4.x * d4.x; acc[0][1] += a4.x * d4.y; acc[0][2] += a4.x * d4.z; acc[0][3] += a4.x * d4.w;
+      acc[1][0] += a4.y * d4.x; acc[1][1] += a4.y * d4.y; acc[1][2] += a4.y * d4.z; acc[1][3] += a4.y * d4.w;
+      acc[2][0] += a4.z * d4.x; acc[2][1] += a4.z * d4.y; acc[2][2] += a4.z * d4.z; acc[2][3] += a4.z * d4.w;
+      acc[3][0] += a4.w * d4.x; acc[3][1] += a4.w * d4.y; acc[3][2] += a4.w * d4.z; acc[3][3] += a4.w * d4.w;
+    }
+    if (do_bias && tk == 0) {
+#pragma unroll
+      for (int p = 0; p < WG_BM; ++p) {
+        float4 d4 = *reinterpret_cast<const float4*>(&Ds[p][tn * 4]);
+        bsum[0] += d4.x; bsum[1] += d4.y; bsum[2] += d4.z; bsum[3] += d4.w;
+      }
+    }
+  }
+  // scatter-accumulate into (O, I, kh, kw)
+  const int taps = a.kh * a.kw;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    int k = k0 + tk * 4 + i;
+    if (k >= K) continue;
+    int tap = k / I, ci = k - tap * I;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      int o = n0 + tn * 4 + j;
+      if (o < a.O) atomicAdd(a.dw + ((long long)o * I + ci) * taps + tap, acc[i][j]);
+    }
+  }
+  if (do_bias && tk == 0) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      int o = n0 + tn * 4 + j;
+      if (o < a.O) atomicAdd(a.dbias + o, bsum[j]);
+    }
+  }
+}
+
+LVAE_API int lvae_conv2d_wgrad(const void* u, const void* u2, const void* dz, const float* in_scale,
+                               const float* out_scale, float* dw, float* dbias, int B, int Hi, int Wi,
+                               int C1, int C2, int Ho, int Wo, int O, int kh, int kw, int stride, int pad,
+                               int dtype, cudaStream_t stream) {
+  LVAE_REQUIRE(u && dz && dw, "conv2d_wgrad: null pointer");
+  LVAE_REQUIRE((C2 == 0) == (u2 == nullptr), "conv2d_wgrad: u2/C2 mismatch");
+  LVAE_REQUIRE(dtype == 0 || dtype == 1, "conv2d_wgrad: dtype must be 0 (f32) or 1 (bf16)");
+  int I = C1 + C2, K = kh * kw * I;
+  long long M = (long long)B * Ho * Wo;
+  int ktiles = cdiv(K, WG_BK), ntiles = cdiv(O, WG_BN);
+  // split the pixel reduction so that the grid is ~4 waves, chunks are multiples of WG_BM
+  long long target = 4LL * lvae_num_sms();
+  long long splits = target / ((long long)ktiles * ntiles);
+  if (splits < 1) splits = 1;
+  long long max_splits = (M + 4 * WG_BM - 1) / (4 * WG_BM);
+  if (splits > max_splits) splits = max_splits;
+  int m_per = (int)(((M + splits - 1) / splits + WG_BM - 1) / WG_BM * WG_BM);
+  splits = (M + m_per - 1) / m_per;
+  WgradArgs a{u, u2, dz, in_scale, out_scale, dw, dbias, B, Hi, Wi, C1, C2, Ho, Wo, O, kh, kw, stride, pad, m_per};
+  dim3 grid(ktiles, ntiles, (unsigned)splits);
+  bool vec = (C1 % 4 == 0) && (C2 % 4 == 0);
+  if (dtype == 0) {
+    if (vec) conv_wgrad_kernel<float, true><<<grid, WG_THREADS, 0, stream>>>(a);
+    else conv_wgrad_kernel<float, false><<<grid, WG_THREADS, 0, stream>>>(a);
+  } else {
+    if (vec) conv_wgrad_kernel<__nv_bfloat16, true><<<grid, WG_THREADS, 0, stream>>>(a);
+    else conv_wgrad_kernel<__nv_bfloat16, false><<<grid, WG_THREADS, 0, stream>>>(a);
+  }
+  LVAE_COUNT_LAUNCH();
+  LVAE_CHECK_LAUNCH("conv2d_wgrad");
+  return LVAE_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// Weight packing: torch (O,I,kh,kw) fp32 -> GEMM-ready [K][ld] rows (fp32 or bf16).
+//   mode 0: dst[(tap*I + i)*ld + o] = w[o][i][tap]   (conv forward / ConvTranspose dgrad)
+//   mode 1: dst[(tap*O + o)*ld + i] = w[o][i][tap]   (conv dgrad / ConvTranspose forward)
+// ------------------------------------------------------------------------------------------
+struct LvaePackDesc {
+  const float* src;
+  void* dst;
+  int O, I, taps, mode, ld, dtype;
+};
+
+__global__ void pack_weights_kernel(const LvaePackDesc* descs, int n) {
+  for (int d = blockIdx.y; d < n; d += gridDim.y) {
+    LvaePackDesc p = descs[d];
+    int rows = p.taps * (p.mode == 0 ? p.I : p.O);
+    int total = rows * p.ld;
+    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+      int r = idx / p.ld, c = idx - r * p.ld;
+      int tap, o, i;
+      if (p.mode == 0) { tap = r / p.I; i = r - tap * p.I; o = c; }
+      else { tap = r / p.O; o = r - tap * p.O; i = c; }
+      float v = 0.f;
+      if (o < p.O && i < p.I) v = p.src[((long long)o * p.I + i) * p.taps + tap];
+      if (p.dtype == 0) ((float*)p.dst)[idx] = v;
+      else ((__nv_bfloat16*)p.dst)[idx] = __float2bfloat16(v);
+    }
+  }
+}
+
+// descs: DEVICE array of n descriptors (built once by the host; weights are re-packed every step)
+LVAE_API int lvae_pack_weights(const void* descs_dev, int n, cudaStream_t stream) {
+  LVAE_REQUIRE(descs_dev && n > 0, "pack_weights: bad args");
+  dim3 grid(8, n < 65535 ? n : 65535);
+  pack_weights_kernel<<<grid, 256, 0, stream>>>((const LvaePackDesc*)descs_dev, n);
+  LVAE_COUNT_LAUNCH();
+  LVAE_CHECK_LAUNCH("pack_weights");
+  return LVAE_OK;
+}
+
+LVAE_API int lvae_pack_desc_size() { return (int)sizeof(LvaePackDesc); }
+
+// per-channel sum over (B,H,W) of dy * scale[b,c]  -> out[c] (+=); used for ConvTranspose dbias
+template <typename T>
+__global__ void colsum_kernel(const T* dy, const float* scale, float* out, long long M, int C, int hw) {
+  // grid.x strides over pixel rows, each thread owns channel (threadIdx.x % C) when blockDim % C == 0
+  int c = threadIdx.x % C, rpb = blockDim.x / C, r0 = threadIdx.x / C;
+  float s = 0.f;
+  for (long long m = (long long)blockIdx.x * rpb + r0; m < M; m += (long long)gridDim.x * rpb) {
+    float v = ld1<T>(dy + m * C + c);
+    if (scale) v *= scale[(m / hw) * C + c];
+    s += v;
+  }
+  atomicAdd(out + c, s);
+}
+
+LVAE_API int lvae_colsum(const void* dy, const float* scale, float* out, int B, int HW, int C, int dtype,
+                         cudaStream_t stream) {
+  LVAE_REQUIRE(dy && out && C > 0 && C <= 1024, "colsum: bad args");
+  int threads = (256 / C) * C;
+  if (threads == 0) threads = C;
+  long long M = (long long)B * HW;
+  int rpb = threads / C;
+  int grid = (int)min((long long)2 * lvae_num_sms(), (M + rpb - 1) / rpb);
+  if (dtype == 0) colsum_kernel<float><<<grid, threads, 0, stream>>>((const float*)dy, scale, out, M, C, HW);
+  else colsum_kernel<__nv_bfloat16><<<grid, threads, 0, stream>>>((const __nv_bfloat16*)dy, scale, out, M, C, HW);
+  LVAE_COUNT_LAUNCH();
+  LVAE_CHECK_LAUNCH("colsum");
+  return LVAE_OK;
+}

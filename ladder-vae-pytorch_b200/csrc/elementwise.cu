@@ -1,0 +1,540 @@
+// HBM-bound passes between the convolutions: BatchNorm (train/eval) fused with the
+// nonlinearity, the GateLayer2d product, bilinear x2 upsampling, pad/crop windows,
+// Dropout2d mask generation.  NHWC activations (fp32 or bf16), fp32 math.
+// Replaces the ATen elementwise / cuDNN BatchNorm kernels launched by lib/nn.py:50-99,121-126,
+// boilr Interpolate (models/lvae.py:144) and boilr pad/crop (models/lvae.py:176,185).
+#include "common.cuh"
+
+// =========================================================================================
+// BatchNorm2d statistics: per-channel sum / sum of squares over (B,H,W), accumulated in
+// double (fp32 partials per thread, double atomics per block).
+// =========================================================================================
+template <typename T>
+__global__ void bn_stats_kernel(const T* __restrict__ x, double* __restrict__ acc, long long P, int C) {
+  // thread -> channel quad (threadIdx.x % CV), row lane (threadIdx.x / CV)
+  extern __shared__ float sm[];  // [2][blockDim.x*4]
+  const int CV = C >> 2;
+  const int cq = threadIdx.x % CV, rl = threadIdx.x / CV, rpb = blockDim.x / CV;
+  float4 s = make_float4(0.f, 0.f, 0.f, 0.f), ss = s;
+  for (long long r = (long long)blockIdx.x * rpb + rl; r < P; r += (long long)gridDim.x * rpb) {
+    float4 v = ld4<T>(x + r * C + cq * 4);
+    s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+    ss.x += v.x * v.x; ss.y += v.y * v.y; ss.z += v.z * v.z; ss.w += v.w * v.w;
+  }
+  float* s_s = sm;
+  float* s_ss = sm + blockDim.x * 4;
+  reinterpret_cast<float4*>(s_s)[threadIdx.x] = s;
+  reinterpret_cast<float4*>(s_ss)[threadIdx.x] = ss;
+  __syncthreads();
+  // threads 0..C-1 reduce over row lanes
+  if (threadIdx.x < C) {
+    int c = threadIdx.x, q = c >> 2, e = c & 3;
+    double a = 0.0, b = 0.0;
+    for (int r = 0; r < rpb; ++r) {
+      a += (double)s_s[(r * CV + q) * 4 + e];
+      b += (double)s_ss[(r * CV + q) * 4 + e];
+    }
+    atomicAdd(acc + c, a);
+    atomicAdd(acc + C + c, b);
+  }
+}
+
+// finalize: mean / rstd for this batch, update running stats (momentum), clear the accumulators.
+__global__ void bn_finalize_kernel(double* acc, float* save_mean, float* save_rstd, float* running_mean,
+                                   float* running_var, long long* num_batches_tracked, long long P, int C,
+                                   float momentum, float eps) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c < C) {
+    double mean = acc[c] / (double)P;
+    double var = acc[C + c] / (double)P - mean * mean;
+    if (var < 0.0) var = 0.0;
+    save_mean[c] = (float)mean;
+    save_rstd[c] = (float)(1.0 / sqrt(var + (double)eps));
+    if (running_mean) {
+      double unb = P > 1 ? var * (double)P / (double)(P - 1) : var;
+      running_mean[c] = (float)((1.0 - momentum) * (double)running_mean[c] + momentum * mean);
+      running_var[c] = (float)((1.0 - momentum) * (double)running_var[c] + momentum * unb);
+    }
+    acc[c] = 0.0;
+    acc[C + c] = 0.0;
+  }
+  if (c == 0 && num_batches_tracked) *num_batches_tracked += 1;
+}
+
+// eval-mode: mean/rstd from running stats
+__global__ void bn_eval_prepare_kernel(const float* running_mean, const float* running_var, float* save_mean,
+                                       float* save_rstd, int C, float eps) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c < C) {
+    save_mean[c] = running_mean[c];
+    save_rstd[c] = 1.0f / sqrtf(running_var[c] + eps);
+  }
+}
+
+// y = act(((x - mean) * rstd) * gamma + beta); with mean == null this is a plain activation pass
+template <typename TI, typename TO>
+__global__ void bn_act_fwd_kernel(const TI* __restrict__ x, TO* __restrict__ y, const float* __restrict__ mean,
+                                  const float* __restrict__ rstd, const float* __restrict__ gamma,
+                                  const float* __restrict__ beta, long long nquads, int C, int act) {
+  const int CV = C >> 2;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nquads; i += (long long)gridDim.x * blockDim.x) {
+    int c = (int)(i % CV) * 4;
+    float4 v = ld4<TI>(x + i * 4);
+    float o[4] = {v.x, v.y, v.z, v.w};
+    if (mean) {
+      float4 m = *reinterpret_cast<const float4*>(mean + c), r = *reinterpret_cast<const float4*>(rstd + c);
+      float4 g = *reinterpret_cast<const float4*>(gamma + c), b = *reinterpret_cast<const float4*>(beta + c);
+      o[0] = (o[0] - m.x) * r.x * g.x + b.x;
+      o[1] = (o[1] - m.y) * r.y * g.y + b.y;
+      o[2] = (o[2] - m.z) * r.z * g.z + b.z;
+      o[3] = (o[3] - m.w) * r.w * g.w + b.w;
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) o[j] = act_fwd(o[j], act);
+    st4<TO>(y + i * 4, make_float4(o[0], o[1], o[2], o[3]));
+  }
+}
+
+// backward pass 1: g = dy * act'(pre); accumulate sum(g), sum(g*xhat) per channel (double)
+template <typename T>
+__global__ void bn_act_bwd_reduce_kernel(const T* __restrict__ dy, const T* __restrict__ x,
+                                         const float* __restrict__ mean, const float* __restrict__ rstd,
+                                         const float* __restrict__ gamma, const float* __restrict__ beta,
+                                         double* __restrict__ acc, long long P, int C, int act) {
+  extern __shared__ float sm[];
+  const int CV = C >> 2;
+  const int cq = threadIdx.x % CV, rl = threadIdx.x / CV, rpb = blockDim.x / CV;
+  const int c = cq * 4;
+  float4 m = *reinterpret_cast<const float4*>(mean + c), r = *reinterpret_cast<const float4*>(rstd + c);
+  float4 g = *reinterpret_cast<const float4*>(gamma + c), b = *reinterpret_cast<const float4*>(beta + c);
+  float mm[4] = {m.x, m.y, m.z, m.w}, rr[4] = {r.x, r.y, r.z, r.w}, gg[4] = {g.x, g.y, g.z, g.w}, bb[4] = {b.x, b.y, b.z, b.w};
+  float s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
+  for (long long row = (long long)blockIdx.x * rpb + rl; row < P; row += (long long)gridDim.x * rpb) {
+    float4 xv = ld4<T>(x + row * C + c), dv = ld4<T>(dy + row * C + c);
+    float xs[4] = {xv.x, xv.y, xv.z, xv.w}, ds[4] = {dv.x, dv.y, dv.z, dv.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float xh = (xs[j] - mm[j]) * rr[j];
+      float gpre = ds[j] * act_bwd(xh * gg[j] + bb[j], act);
+      s1[j] += gpre;
+      s2[j] += gpre * xh;
+    }
+  }
+  float* a1 = sm;
+  float* a2 = sm + blockDim.x * 4;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    a1[threadIdx.x * 4 + j] = s1[j];
+    a2[threadIdx.x * 4 + j] = s2[j];
+  }
+  __syncthreads();
+  if (threadIdx.x < C) {
+    int cc = threadIdx.x, q = cc >> 2, e = cc & 3;
+    double u = 0.0, v = 0.0;
+    for (int rrw = 0; rrw < rpb; ++rrw) {
+      u += (double)a1[(rrw * CV + q) * 4 + e];
+      v += (double)a2[(rrw * CV + q) * 4 + e];
+    }
+    atomicAdd(acc + cc, u);
+    atomicAdd(acc + C + cc, v);
+  }
+}
+
+// backward pass 2: dx = gamma*rstd*(g - sum_g/P - xhat*sum_gx/P) (train) or gamma*rstd*g (eval);
+// block 0 also emits dgamma (+=) / dbeta (+=) and clears the accumulators via a second tiny kernel.
+template <typename T>
+__global__ void bn_act_bwd_apply_kernel(const T* __restrict__ dy, const T* __restrict__ x, T* __restrict__ dx,
+                                        const float* __restrict__ mean, const float* __restrict__ rstd,
+                                        const float* __restrict__ gamma, const float* __restrict__ beta,
+                                        const double* __restrict__ acc, long long nquads, long long P, int C,
+                                        int act, int training) {
+  const int CV = C >> 2;
+  const double invP = 1.0 / (double)P;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nquads; i += (long long)gridDim.x * blockDim.x) {
+    int c = (int)(i % CV) * 4;
+    float4 xv = ld4<T>(x + i * 4), dv = ld4<T>(dy + i * 4);
+    float xs[4] = {xv.x, xv.y, xv.z, xv.w}, ds[4] = {dv.x, dv.y, dv.z, dv.w}, o[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float mj = mean[c + j], rj = rstd[c + j], gj = gamma[c + j], bj = beta[c + j];
+      float xh = (xs[j] - mj) * rj;
+      float gpre = ds[j] * act_bwd(xh * gj + bj, act);
+      if (training) {
+        float m1 = (float)(acc[c + j] * invP), m2 = (float)(acc[C + c + j] * invP);
+        o[j] = gj * rj * (gpre - m1 - xh * m2);
+      } else {
+        o[j] = gj * rj * gpre;
+      }
+    }
+    st4<T>(dx + i * 4, make_float4(o[0], o[1], o[2], o[3]));
+  }
+}
+
+__global__ void bn_bwd_params_kernel(double* acc, float* dgamma, float* dbeta, int C) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c < C) {
+    if (dbeta) dbeta[c] += (float)acc[c];
+    if (dgamma) dgamma[c] += (float)acc[C + c];
+    acc[c] = 0.0;
+    acc[C + c] = 0.0;
+  }
+}
+
+// plain activation backward (no BatchNorm): dx = dy * act'(x)
+template <typename T>
+__global__ void act_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ x, T* __restrict__ dx, long long nquads, int act) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nquads; i += (long long)gridDim.x * blockDim.x) {
+    float4 xv = ld4<T>(x + i * 4), dv = ld4<T>(dy + i * 4);
+    st4<T>(dx + i * 4, make_float4(dv.x * act_bwd(xv.x, act), dv.y * act_bwd(xv.y, act), dv.z * act_bwd(xv.z, act),
+                                   dv.w * act_bwd(xv.w, act)));
+  }
+}
+
+static inline int ew_grid(long long n, int threads) {
+  long long g = (n + threads - 1) / threads;
+  long long cap = 8LL * lvae_num_sms();
+  return (int)(g < cap ? (g > 0 ? g : 1) : cap);
+}
+
+static bool bn_c_ok(int C) { return C >= 4 && C % 4 == 0 && C <= 256; }
+static int bn_threads(int C) { return (256 / (C / 4)) * (C / 4); }
+
+LVAE_API int lvae_bn_stats(const void* x, double* acc, long long P, int C, int dtype, cudaStream_t stream) {
+  LVAE_REQUIRE(x && acc && P > 0, "bn_stats: bad args");
+  LVAE_REQUIRE(bn_c_ok(C), "bn_stats: channels must be a multiple of 4 and <= 256 (got %d)", C);
+  int threads = bn_threads(C), rpb = threads / (C / 4);
+  int grid = (int)min((long long)4 * lvae_num_sms(), (P + rpb - 1) / rpb);
+  size_t smem = (size_t)threads * 4 * 2 * sizeof(float);
+  if (dtype == 0) bn_stats_kernel<float><<<grid, threads, smem, stream>>>((const float*)x, acc, P, C);
+  else bn_stats_kernel<__nv_bfloat16><<<grid, threads, smem, stream>>>((const __nv_bfloat16*)x, acc, P, C);
+  LVAE_COUNT_LAUNCH();
+  LVAE_CHECK_LAUNCH("bn_stats");
+  return LVAE_OK;
+}
+
+LVAE_API int lvae_bn_finalize(double* acc, float* save_mean, float* save_rstd, float* running_mean,
+                              float* running_var, long long* num_batches_tracked, long long P, int C,
+                              float momentum, float eps, cudaStream_t stream) {
+  LVAE_REQUIRE(acc && save_mean && save_rstd, "bn_finalize: bad args");
+  bn_finalize_kernel<<<cdiv(C, 128), 128, 0, stream>>>(acc, save_mean, save_rstd, running_mean, running_var,
+                                                       num_batches_tracked, P, C, momentum, eps);
+  LVAE_COUNT_LAUNCH();
+  LVAE_CHECK_LAUNCH("bn_finalize");
+  return LVAE_OK;
+}
+
+LVAE_API int lvae_bn_eval_prepare(const float* running_mean, const float* running_var, float* save_mean,
+                                  float* save_rstd, int C, float eps, cudaStream_t stream) {
+  LVAE_REQUIRE(running_mean && running_var && save_mean && save_rstd, "bn_eval_prepare: bad args");
+  bn_eval_prepare_kernel<<<cdiv(C, 128), 128, 0, stream>>>(running_mean, running_var, save_mean, save_rstd, C, eps);
+  LVAE_COUNT_LAUNCH();
+  LVAE_CHECK_LAUNCH("bn_eval_prepare");
+  return LVAE_OK;
+}
+
+// dtype_in / dtype_out: 0 f32, 1 bf16 (the bf16 conv path stores bf16 activations)
+LVAE_API int lvae_bn_act_fwd(const void* x, void* y, const float* mean, const float* rstd, const float* gamma,
+                             const float* beta, long long P, int C, int act, int dtype_in, int dtype_out,
+                             cudaStream_t stream) {
+  LVAE_REQUIRE(x && y && P > 0 && C % 4 == 0, "bn_act_fwd: bad args (C must be a multiple of 4)");
+  long long nq = P * (C / 4);
+  int g = ew_grid(nq, 256);
+  if (dtype_in == 0 && dtype_out == 0)
+    bn_act_fwd_kernel<float, float><<<g, 256, 0, stream>>>((const float*)x, (float*)y, mean, rstd, gamma, beta, nq, C, act);
+  else if (dtype_in == 0 && dtype_out == 1)
+    bn_act_fwd_kernel<float, __nv_bfloat16><<<g, 256, 0, stream>>>((const float*)x, (__nv_bfloat16*)y, mean, rstd, gamma, beta, nq, C, act);
+  else if (dtype_in == 1 && dtype_out == 1)
+    bn_act_fwd_kernel<__nv_bfloat16, __nv_bfloat16><<<g, 256, 0, stream>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)y, mean, rstd, gamma, beta, nq, C, act);
+  else
+    bn_act_fwd_kernel<__nv_bfloat16, float><<<g, 256, 0, stream>>>((const __nv_bfloat16*)x, (float*)y, mean, rstd, gamma, beta, nq, C, act);
+  LVAE_COUNT_LAUNCH();
+  LVAE_CHECK_LAUNCH("bn_act_fwd");
+  return LVAE_OK;
+}
+
+LVAE_API int lvae_bn_act_bwd(const void* dy, const void* x, void* dx, const float* mean, const float* rstd,
+                             const float* gamma, const float* beta, double* acc, float* dgamma, float* dbeta,
+                             long long P, int C, int act, int training, int dtype, cudaStream_t stream) {
+  LVAE_REQUIRE(dy && x && dx && P > 0, "bn_act_bwd: bad args");
+  long long nq = P * (C / 4);
+  if (!mean) {  // plain activation
+    LVAE_REQUIRE(C % 4 == 0, "act_bwd: C must be a multiple of 4");
+    int g = ew_grid(nq, 256);
+    if (dtype == 0) act_bwd_kernel<float><<<g, 256, 0, stream>>>((const float*)dy, (const float*)x, (float*)dx, nq, act);
+    else act_bwd_kernel<__nv_bfloat16><<<g, 256, 0, stream>>>((const __nv_bfloat16*)dy, (const __nv_bfloat16*)x, (__nv_bfloat16*)dx, nq, act);
+    LVAE_COUNT_LAUNCH();
+    LVAE_CHECK_LAUNCH("act_bwd");
+    return LVAE_OK;
+  }
+  LVAE_REQUIRE(bn_c_ok(C) && acc, "bn_act_bwd: channels must be a multiple of 4, <= 256, and acc non-null");
+  int threads = bn_threads(C), rpb = threads / (C / 4);
+  int grid = (int)min((long long)4 * lvae_num_sms(), (P + rpb - 1) / rpb);
+  size_t smem = (size_t)threads * 4 * 2 * sizeof(float);
+  if (dtype == 0)
+    bn_act_bwd_reduce_kernel<float><<<grid, threads, smem, stream>>>((const float*)dy, (const float*)x, mean, rstd, gamma, beta, acc, P, C, act);
+  else
+    bn_act_bwd_reduce_kernel<__nv_bfloat16><<<grid, threads, smem, stream>>>((const __nv_bfloat16*)dy, (const __nv_bfloat16*)x, mean, rstd, gamma, beta, acc, P, C, act);
+  LVAE_COUNT_LAUNCH();
+  LVAE_CHECK_LAUNCH("bn_act_bwd_reduce");
+  int g = ew_grid(nq, 256);
+  if (dtype == 0)
+    bn_act_bwd_apply_kernel<float><<<g, 256, 0, stream>>>((const float*)dy, (const float*)x, (float*)dx, mean, rstd, gamma, beta, acc, nq, P, C, act, training);
+  else
+    bn_act_bwd_apply_kernel<__nv_bfloat16><<<g, 256, 0, stream>>>((const __nv_bfloat16*)dy, (const __nv_bfloat16*)x, (__nv_bfloat16*)dx, mean, rstd, gamma, beta, acc, nq, P, C, act, training);
+  LVAE_COUNT_LAUNCH();
+  LVAE_CHECK_LAUNCH("bn_act_bwd_apply");
+  bn_bwd_params_kernel<<<cdiv(C, 128), 128, 0, stream>>>(acc, dgamma, dbeta, C);
+  LVAE_COUNT_LAUNCH();
+  LVAE_CHECK_LAUNCH("bn_bwd_params");
+  return LVAE_OK;
+}
+
+// =========================================================================================
+// GateLayer2d (lib/nn.py:121-126) + residual (lib/nn.py:99): h is (P, 2C); out = act(h[:, :C]) * sigmoid(h[:, C:]) + res
+// =========================================================================================
+template <typename T>
+__global__ void gate_fwd_kernel(const T* __restrict__ h, const T* __restrict__ res, T* __restrict__ out,
+                                long long nquads, int C, int act) {
+  const int CV = C >> 2;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nquads; i += (long long)gridDim.x * blockDim.x) {
+    long long row = i / CV;
+    int c = (int)(i - row * CV) * 4;
+    float4 a = ld4<T>(h + row * 2 * C + c), g = ld4<T>(h + row * 2 * C + C + c);
+    float4 o = make_float4(act_fwd(a.x, act) * sigmoidf_(g.x), act_fwd(a.y, act) * sigmoidf_(g.y),
+                           act_fwd(a.z, act) * sigmoidf_(g.z), act_fwd(a.w, act) * sigmoidf_(g.w));
+    if (res) {
+      float4 r = ld4<T>(res + i * 4);
+      o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
+    }
+    st4<T>(out + i * 4, o);
+  }
+}
+
+template <typename T>
+__global__ void gate_bwd_kernel(const T* __restrict__ dout, const T* __restrict__ h, T* __restrict__ dh,
+                                long long nquads, int C, int act) {
+  const int CV = C >> 2;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nquads; i += (long long)gridDim.x * blockDim.x) {
+    long long row = i / CV;
+    int c = (int)(i - row * CV) * 4;
+    float4 a = ld4<T>(h + row * 2 * C + c), g = ld4<T>(h + row * 2 * C + C + c), d = ld4<T>(dout + i * 4);
+    float av[4] = {a.x, a.y, a.z, a.w}, gv[4] = {g.x, g.y, g.z, g.w}, dv[4] = {d.x, d.y, d.z, d.w}, da[4], dg[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float s = sigmoidf_(gv[j]);
+      da[j] = dv[j] * s * act_bwd(av[j], act);
+      dg[j] = dv[j] * act_fwd(av[j], act) * s * (1.f - s);
+    }
+    st4<T>(dh + row * 2 * C + c, make_float4(da[0], da[1], da[2], da[3]));
+    st4<T>(dh + row * 2 * C + C + c, make_float4(dg[0], dg[1], dg[2], dg[3]));
+  }
+}
+
+LVAE_API int lvae_gate_fwd(const void* h, const void* res, void* out, long long P, int C, int act, int dtype, cudaStream_t stream) {
+  LVAE_REQUIRE(h && out && P > 0 && C % 4 == 0, "gate_fwd: bad args");
+  long long nq = P * (C / 4);
+  int g = ew_grid(nq, 256);
+  if (dtype == 0) gate_fwd_kernel<float><<<g, 256, 0, stream>>>((const float*)h, (const float*)res, (float*)out, nq, C, act);
+  else gate_fwd_kernel<__nv_bfloat16><<<g, 256, 0, stream>>>((const __nv_bfloat16*)h, (const __nv_bfloat16*)res, (__nv_bfloat16*)out, nq, C, act);
+  LVAE_COUNT_LAUNCH();
+  LVAE_CHECK_LAUNCH("gate_fwd");
+  return LVAE_OK;
+}
+
+LVAE_API int lvae_gate_bwd(const void* dout, const void* h, void* dh, long long P, int C, int act, int dtype, cudaStream_t stream) {
+  LVAE_REQUIRE(dout && h && dh && P > 0 && C % 4 == 0, "gate_bwd: bad args");
+  long long nq = P * (C / 4);
+  int g = ew_grid(nq, 256);
+  if (dtype == 0) gate_bwd_kernel<float><<<g, 256, 0, stream>>>((const float*)dout, (const float*)h, (float*)dh, nq, C, act);
+  else gate_bwd_kernel<__nv_bfloat16><<<g, 256, 0, stream>>>((const __nv_bfloat16*)dout, (const __nv_bfloat16*)h, (__nv_bfloat16*)dh, nq, C, act);
+  LVAE_COUNT_LAUNCH();
+  LVAE_CHECK_LAUNCH("gate_bwd");
+  return LVAE_OK;
+}
+
+// =========================================================================================
+// Bilinear x2 upsampling, align_corners=False (boilr Interpolate(scale=2), models/lvae.py:144)
+// =========================================================================================
+__device__ __forceinline__ void up2_src(int o, int n_in, int& i0, int& i1, float& l) {
+  float s = (o + 0.5f) * 0.5f - 0.5f;
+  if (s < 0.f) s = 0.f;
+  i0 = (int)s;
+  i1 = i0 + (i0 < n_in - 1 ? 1 : 0);
+  l = s - (float)i0;
+}
+
+template <typename T>
+__global__ void upsample2x_fwd_kernel(const T* __restrict__ x, T* __restrict__ y, int B, int H, int W, int C) {
+  const int CV = C >> 2;
+  long long total = (long long)B * 2 * H * 2 * W * CV;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    int c = (int)(i % CV) * 4;
+    long long p = i / CV;
+    int ox = (int)(p % (2 * W));
+    long long q = p / (2 * W);
+    int oy = (int)(q % (2 * H));
+    int b = (int)(q / (2 * H));
+    int y0, y1, x0, x1;
+    float ly, lx;
+    up2_src(oy, H, y0, y1, ly);
+    up2_src(ox, W, x0, x1, lx);
+    const T* base = x + (long long)b * H * W * C + c;
+    float4 v00 = ld4<T>(base + ((long long)y0 * W + x0) * C), v01 = ld4<T>(base + ((long long)y0 * W + x1) * C);
+    float4 v10 = ld4<T>(base + ((long long)y1 * W + x0) * C), v11 = ld4<T>(base + ((long long)y1 * W + x1) * C);
+    float w00 = (1.f - ly) * (1.f - lx), w01 = (1.f - ly) * lx, w10 = ly * (1.f - lx), w11 = ly * lx;
+    float4 o = make_float4(w00 * v00.x + w01 * v01.x + w10 * v10.x + w11 * v11.x,
+                           w00 * v00.y + w01 * v01.y + w10 * v10.y + w11 * v11.y,
+                           w00 * v00.z + w01 * v01.z + w10 * v10.z + w11 * v11.z,
+                           w00 * v00.w + w01 * v01.w + w10 * v10.w + w11 * v11.w);
+    st4<T>(y + i * 4, o);
+  }
+}
+
+// backward as a gather: every input pixel collects from the <= 3x3 output pixels that read it
+template <typename T>
+__global__ void upsample2x_bwd_kernel(const T* __restrict__ dy, T* __restrict__ dx, int B, int H, int W, int C) {
+  const int CV = C >> 2;
+  long long total = (long long)B * H * W * CV;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    int c = (int)(i % CV) * 4;
+    long long p = i / CV;
+    int ix = (int)(p % W);
+    long long q = p / W;
+    int iy = (int)(q % H);
+    int b = (int)(q / H);
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int oy = max(0, 2 * iy - 2); oy <= min(2 * H - 1, 2 * iy + 2); ++oy) {
+      int y0, y1;
+      float ly;
+      up2_src(oy, H, y0, y1, ly);
+      float wy = (y0 == iy ? 1.f - ly : 0.f) + (y1 == iy ? ly : 0.f);
+      if (wy == 0.f) continue;
+      for (int ox = max(0, 2 * ix - 2); ox <= min(2 * W - 1, 2 * ix + 2); ++ox) {
+        int x0, x1;
+        float lx;
+        up2_src(ox, W, x0, x1, lx);
+        float wx = (x0 == ix ? 1.f - lx : 0.f) + (x1 == ix ? lx : 0.f);
+        if (wx == 0.f) continue;
+        float4 d = ld4<T>(dy + (((long long)b * 2 * H + oy) * 2 * W + ox) * C + c);
+        float w = wy * wx;
+        acc.x += w * d.x; acc.y += w * d.y; acc.z += w * d.z; acc.w += w * d.w;
+      }
+    }
+    st4<T>(dx + i * 4, acc);
+  }
+}
+
+LVAE_API int lvae_upsample2x_fwd(const void* x, void* y, int B, int H, int W, int C, int dtype, cudaStream_t stream) {
+  LVAE_REQUIRE(x && y && C % 4 == 0, "upsample2x_fwd: bad args");
+  long long n = (long long)B * 4 * H * W * (C / 4);
+  if (dtype == 0) upsample2x_fwd_kernel<float><<<ew_grid(n, 256), 256, 0, stream>>>((const float*)x, (float*)y, B, H, W, C);
+  else upsample2x_fwd_kernel<__nv_bfloat16><<<ew_grid(n, 256), 256, 0, stream>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)y, B, H, W, C);
+  LVAE_COUNT_LAUNCH();
+  LVAE_CHECK_LAUNCH("upsample2x_fwd");
+  return LVAE_OK;
+}
+
+LVAE_API int lvae_upsample2x_bwd(const void* dy, void* dx, int B, int H, int W, int C, int dtype, cudaStream_t stream) {
+  LVAE_REQUIRE(dy && dx && C % 4 == 0, "upsample2x_bwd: bad args");
+  long long n = (long long)B * H * W * (C / 4);
+  if (dtype == 0) upsample2x_bwd_kernel<float><<<ew_grid(n, 256), 256, 0, stream>>>((const float*)dy, (float*)dx, B, H, W, C);
+  else upsample2x_bwd_kernel<__nv_bfloat16><<<ew_grid(n, 256), 256, 0, stream>>>((const __nv_bfloat16*)dy, (__nv_bfloat16*)dx, B, H, W, C);
+  LVAE_COUNT_LAUNCH();
+  LVAE_CHECK_LAUNCH("upsample2x_bwd");
+  return LVAE_OK;
+}
+
+// =========================================================================================
+// Window copy between layouts: dst[b, y+dy0, x+dx0, c] = src[b, y+sy0, x+sx0, c] for a (h,w) window.
+// Used for boilr pad_img_tensor (NCHW image -> zero-padded NHWC) and crop_img_tensor (and their
+// backward).  src_nchw / dst_nchw select the physical layout of either side.
+// =========================================================================================
+template <typename TS, typename TD>
+__global__ void copy_window_kernel(const TS* __restrict__ src, TD* __restrict__ dst, int B, int C, int Hs, int Ws,
+                                   int Hd, int Wd, int sy0, int sx0, int dy0, int dx0, int h, int w,
+                                   int src_nchw, int dst_nchw) {
+  long long total = (long long)B * h * w * C;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    int c = (int)(i % C);
+    long long p = i / C;
+    int x = (int)(p % w);
+    long long q = p / w;
+    int y = (int)(q % h);
+    int b = (int)(q / h);
+    long long si = src_nchw ? (((long long)b * C + c) * Hs + (y + sy0)) * Ws + (x + sx0)
+                            : (((long long)b * Hs + (y + sy0)) * Ws + (x + sx0)) * C + c;
+    long long di = dst_nchw ? (((long long)b * C + c) * Hd + (y + dy0)) * Wd + (x + dx0)
+                            : (((long long)b * Hd + (y + dy0)) * Wd + (x + dx0)) * C + c;
+    st1<TD>(dst + di, ld1<TS>(src + si));
+  }
+}
+
+LVAE_API int lvae_copy_window(const void* src, void* dst, int B, int C, int Hs, int Ws, int Hd, int Wd, int sy0,
+                              int sx0, int dy0, int dx0, int h, int w, int src_nchw, int dst_nchw,
+                              int src_dtype, int dst_dtype, cudaStream_t stream) {
+  LVAE_REQUIRE(src && dst && B > 0 && C > 0 && h > 0 && w > 0, "copy_window: bad args");
+  LVAE_REQUIRE(sy0 >= 0 && sx0 >= 0 && sy0 + h <= Hs && sx0 + w <= Ws && dy0 >= 0 && dx0 >= 0 && dy0 + h <= Hd && dx0 + w <= Wd,
+               "copy_window: window out of range");
+  long long n = (long long)B * h * w * C;
+  int g = ew_grid(n, 256);
+#define CW(TS, TD) copy_window_kernel<TS, TD><<<g, 256, 0, stream>>>((const TS*)src, (TD*)dst, B, C, Hs, Ws, Hd, Wd, sy0, sx0, dy0, dx0, h, w, src_nchw, dst_nchw)
+  if (src_dtype == 0 && dst_dtype == 0) CW(float, float);
+  else if (src_dtype == 0 && dst_dtype == 1) CW(float, __nv_bfloat16);
+  else if (src_dtype == 1 && dst_dtype == 0) CW(__nv_bfloat16, float);
+  else CW(__nv_bfloat16, __nv_bfloat16);
+#undef CW
+  LVAE_COUNT_LAUNCH();
+  LVAE_CHECK_LAUNCH("copy_window");
+  return LVAE_OK;
+}
+
+// =========================================================================================
+// Dropout2d keep masks for every dropout site of one step in ONE launch:
+// masks[i] = (u_i >= p) / (1-p), i over (site, sample, channel).  RNG state lives on the device.
+// =========================================================================================
+__global__ void dropout_masks_kernel(float* masks, long long n, float p, const PhiloxState* st, unsigned long long stream_id) {
+  PhiloxState s = *st;
+  float inv = 1.f / (1.f - p);
+  for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q * 4 < n; q += (long long)gridDim.x * blockDim.x) {
+    float4 u = philox_uniform4(s, stream_id, (unsigned long long)q);
+    float v[4] = {u.x, u.y, u.z, u.w};
+    for (int j = 0; j < 4 && q * 4 + j < n; ++j) masks[q * 4 + j] = v[j] > p ? inv : 0.f;
+  }
+}
+
+LVAE_API int lvae_dropout_masks(float* masks, long long n, float p, const void* rng_state, unsigned long long stream_id,
+                                cudaStream_t stream) {
+  LVAE_REQUIRE(masks && n > 0 && p >= 0.f && p < 1.f && rng_state, "dropout_masks: bad args");
+  dropout_masks_kernel<<<ew_grid((n + 3) / 4, 256), 256, 0, stream>>>(masks, n, p, (const PhiloxState*)rng_state, stream_id);
+  LVAE_COUNT_LAUNCH();
+  LVAE_CHECK_LAUNCH("dropout_masks");
+  return LVAE_OK;
+}
+
+__global__ void rng_advance_kernel(PhiloxState* st, unsigned long long inc) { st->offset += inc; }
+
+// rng_state: device uint64[2] = {seed, offset}; advance once per step (graph-replay safe)
+LVAE_API int lvae_rng_advance(void* rng_state, unsigned long long inc, cudaStream_t stream) {
+  LVAE_REQUIRE(rng_state, "rng_advance: null state");
+  rng_advance_kernel<<<1, 1, 0, stream>>>((PhiloxState*)rng_state, inc);
+  LVAE_COUNT_LAUNCH();
+  LVAE_CHECK_LAUNCH("rng_advance");
+  return LVAE_OK;
+}
+
+// out[i] (+)= sum_b x[b, i]  (top-layer prior gradient: the prior is a batch-1 parameter, lvae_layers.py:131-136)
+__global__ void sum_batch_kernel(const float* x, float* out, int B, long long n, int accumulate) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    float s = 0.f;
+    for (int b = 0; b < B; ++b) s += x[(long long)b * n + i];
+    out[i] = accumulate ? out[i] + s : s;
+  }
+}
+
+LVAE_API int lvae_sum_batch(const float* x, float* out, int B, long long n, int accumulate, cudaStream_t stream) {
+  LVAE_REQUIRE(x && out && B > 0 && n > 0, "sum_batch: bad args");
+  sum_batch_kernel<<<ew_grid(n, 256), 256, 0, stream>>>(x, out, B, n, accumulate);
+  LVAE_COUNT_LAUNCH();
+  LVAE_CHECK_LAUNCH("sum_batch");
+  return LVAE_OK;
+}

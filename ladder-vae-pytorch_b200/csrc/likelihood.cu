@@ -1,0 +1,328 @@
+// Fused output log-likelihoods (forward + backward) and their samplers.
+//   * Bernoulli on probabilities with BCE's -100 log clamp (lib/likelihoods.py:62,385-388)
+//   * 10-component discretized mixture of logistics (lib/likelihoods.py:226-230,291-382),
+//     per-pixel logsumexp kept in registers, parameters staged through shared memory so the
+//     (B,H,W,100) NHWC rows are read/written fully coalesced.
+//   * samplers: Bernoulli (likelihoods.py:73-75), DMoL (lib/stochastic.py:141-206, likelihoods.py:221-225)
+// x is the user's image tensor: (B,C,H,W) NCHW fp32 in [0,1].  params are NHWC fp32.
+#include "common.cuh"
+
+// =========================================================================================
+// Bernoulli
+// =========================================================================================
+__global__ void __launch_bounds__(256) bernoulli_fwd_kernel(const float* __restrict__ logits, const float* __restrict__ x,
+                                                            float* __restrict__ prob, float* __restrict__ ll,
+                                                            int hw, int C) {
+  __shared__ float red[32];
+  const int b = blockIdx.x, n = hw * C;
+  float s = 0.f;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    int pix = i / C, c = i - pix * C;
+    float p = sigmoidf_(logits[(long long)b * n + i]);
+    prob[(long long)b * n + i] = p;
+    if (x) {
+      float xv = x[((long long)b * C + c) * hw + pix];
+      float lp = fmaxf(logf(p), -100.f), l1p = fmaxf(logf(1.f - p), -100.f);
+      s += xv * lp + (1.f - xv) * l1p;
+    }
+  }
+  s = block_sum(s, red);
+  if (threadIdx.x == 0 && ll) ll[b] = s;
+}
+
+// dlogit = g_ll[b] * (x - p) * p(1-p) / max(p(1-p), 1e-12)   (ATen BCE backward times sigmoid')
+__global__ void bernoulli_bwd_kernel(const float* __restrict__ prob, const float* __restrict__ x,
+                                     const float* __restrict__ g_ll, const float* __restrict__ g_prob,
+                                     float* __restrict__ dlogits, int B, int hw, int C) {
+  long long total = (long long)B * hw * C;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    int c = (int)(i % C);
+    long long t = i / C;
+    int pix = (int)(t % hw);
+    int b = (int)(t / hw);
+    float p = prob[i], xv = x[((long long)b * C + c) * hw + pix];
+    float pq = p * (1.f - p);
+    float d = g_ll[b] * (xv - p) / fmaxf(pq, 1e-12f) * pq;
+    if (g_prob) d += g_prob[i] * pq;
+    dlogits[i] = d;
+  }
+}
+
+LVAE_API int lvae_bernoulli_fwd(const float* logits, const float* x, float* prob, float* ll, int B, int hw, int C,
+                                cudaStream_t stream) {
+  LVAE_REQUIRE(logits && prob && B > 0 && hw > 0 && C > 0, "bernoulli_fwd: bad args");
+  LVAE_REQUIRE((x == nullptr) == (ll == nullptr), "bernoulli_fwd: x and ll go together");
+  bernoulli_fwd_kernel<<<B, 256, 0, stream>>>(logits, x, prob, ll, hw, C);
+  LVAE_COUNT_LAUNCH();
+  LVAE_CHECK_LAUNCH("bernoulli_fwd");
+  return LVAE_OK;
+}
+
+LVAE_API int lvae_bernoulli_bwd(const float* prob, const float* x, const float* g_ll, const float* g_prob,
+                                float* dlogits, int B, int hw, int C, cudaStream_t stream) {
+  LVAE_REQUIRE(prob && x && g_ll && dlogits, "bernoulli_bwd: bad args");
+  long long n = (long long)B * hw * C;
+  int grid = (int)min((long long)4 * lvae_num_sms(), (n + 255) / 256);
+  bernoulli_bwd_kernel<<<grid, 256, 0, stream>>>(prob, x, g_ll, g_prob, dlogits, B, hw, C);
+  LVAE_COUNT_LAUNCH();
+  LVAE_CHECK_LAUNCH("bernoulli_bwd");
+  return LVAE_OK;
+}
+
+__global__ void bernoulli_sample_kernel(const float* prob, float* out, long long n, int hw, int C,
+                                        const PhiloxState* rng, unsigned long long stream_id) {
+  // out is NCHW like every image the module API hands back
+  PhiloxState st = *rng;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    float4 u = philox_uniform4(st, stream_id, (unsigned long long)i);
+    int c = (int)(i % C);
+    long long t = i / C;
+    int pix = (int)(t % hw);
+    long long b = t / hw;
+    out[(b * C + c) * hw + pix] = (u.x - 5.9e-8f) < prob[i] ? 1.f : 0.f;
+  }
+}
+
+LVAE_API int lvae_bernoulli_sample(const float* prob, float* out_nchw, int B, int hw, int C, const void* rng_state,
+                                   unsigned long long stream_id, cudaStream_t stream) {
+  LVAE_REQUIRE(prob && out_nchw && rng_state, "bernoulli_sample: bad args");
+  long long n = (long long)B * hw * C;
+  int grid = (int)min((long long)4 * lvae_num_sms(), (n + 255) / 256);
+  bernoulli_sample_kernel<<<grid, 256, 0, stream>>>(prob, out_nchw, n, hw, C, (const PhiloxState*)rng_state, stream_id);
+  LVAE_COUNT_LAUNCH();
+  LVAE_CHECK_LAUNCH("bernoulli_sample");
+  return LVAE_OK;
+}
+
+// =========================================================================================
+// Discretized mixture of logistics, 10 components, 3 colour channels
+// =========================================================================================
+constexpr int DM_M = 10, DM_P = 100, DM_PITCH = 101, DM_TILE = 128;
+#define LOG_127_5 4.8481163519437300f
+
+// log-prob of one sub-pixel under one logistic; optionally its derivatives wrt the centred value
+// and the (clamped) log-scale.  Mirrors likelihoods.py:331-375.
+__device__ __forceinline__ float dmol_term(float x, float cen, float ls, float& d_cen, float& d_ls, bool want_grad) {
+  float inv = expf(-ls);
+  float plus_in = inv * (cen + (1.f / 255.f));
+  float min_in = inv * (cen - (1.f / 255.f));
+  if (x < -0.999f) {
+    if (want_grad) { float om = 1.f - sigmoidf_(plus_in); d_cen = inv * om; d_ls = -plus_in * om; }
+    return plus_in - softplusf_(plus_in);
+  }
+  if (x > 0.999f) {
+    if (want_grad) { float s = sigmoidf_(min_in); d_cen = -inv * s; d_ls = min_in * s; }
+    return -softplusf_(min_in);
+  }
+  float cp = sigmoidf_(plus_in), cm = sigmoidf_(min_in);
+  float delta = cp - cm;
+  if (delta > 1e-5f) {
+    if (want_grad) {
+      float dpv = cp * (1.f - cp), dmv = cm * (1.f - cm);
+      float dd = fmaxf(delta, 1e-12f);
+      d_cen = inv * (dpv - dmv) / dd;
+      d_ls = -(plus_in * dpv - min_in * dmv) / dd;
+    }
+    return logf(fmaxf(delta, 1e-12f));
+  }
+  float mid = inv * cen;
+  if (want_grad) { float w = 1.f - 2.f * sigmoidf_(mid); d_cen = inv * w; d_ls = -mid * w - 1.f; }
+  return mid - ls - 2.f * softplusf_(mid) - LOG_127_5;
+}
+
+// BWD = false: ll[b] += sum over this CTA's pixels.  BWD = true: dl = g_ll[b] * d ll / d l.
+template <bool BWD>
+__global__ void __launch_bounds__(DM_TILE) dmol_kernel(const float* __restrict__ l, const float* __restrict__ x,
+                                                       float* __restrict__ ll, const float* __restrict__ g_ll,
+                                                       float* __restrict__ dl, int hw) {
+  extern __shared__ float sm[];  // DM_TILE * DM_PITCH (+32 for the reduction)
+  float* red = sm + DM_TILE * DM_PITCH;
+  const int b = blockIdx.y;
+  const int pix0 = blockIdx.x * DM_TILE;
+  const int npix = min(DM_TILE, hw - pix0);
+  const long long base = ((long long)b * hw + pix0) * DM_P;
+  // coalesced stage-in (rows are contiguous in NHWC); base is a multiple of 4 floats
+  {
+    const float4* src = reinterpret_cast<const float4*>(l + base);
+    int nq = npix * DM_P / 4;
+    for (int i = threadIdx.x; i < nq; i += DM_TILE) {
+      float4 v = src[i];
+      int e = i * 4;
+      float vv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        int r = (e + j) / DM_P, cidx = (e + j) - r * DM_P;
+        sm[r * DM_PITCH + cidx] = vv[j];
+      }
+    }
+  }
+  __syncthreads();
+  const int r = threadIdx.x;
+  float pix_ll = 0.f;
+  if (r < npix) {
+    float* L = sm + r * DM_PITCH;
+    const int pix = pix0 + r;
+    float xc[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) xc[c] = x[((long long)b * 3 + c) * hw + pix] * 2.f - 1.f;
+    // log_softmax of the mixture logits
+    float mx = L[0];
+#pragma unroll
+    for (int m = 1; m < DM_M; ++m) mx = fmaxf(mx, L[m]);
+    float se = 0.f;
+#pragma unroll
+    for (int m = 0; m < DM_M; ++m) se += expf(L[m] - mx);
+    const float lse0 = mx + logf(se);
+    float v[DM_M];
+    float vmax = -INFINITY;
+#pragma unroll
+    for (int m = 0; m < DM_M; ++m) {
+      float S = 0.f, dc, dls;
+      float k0 = tanhf(L[10 + 20 + m]), k1 = tanhf(L[40 + 20 + m]), k2 = tanhf(L[70 + 20 + m]);
+      float mu[3] = {L[10 + m], L[40 + m] + k0 * xc[0], L[70 + m] + k1 * xc[0] + k2 * xc[1]};
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        float ls = fmaxf(L[10 + 30 * c + 10 + m], -7.f);
+        S += dmol_term(xc[c], xc[c] - mu[c], ls, dc, dls, false);
+      }
+      v[m] = S + (L[m] - lse0);
+      vmax = fmaxf(vmax, v[m]);
+    }
+    float sv = 0.f;
+#pragma unroll
+    for (int m = 0; m < DM_M; ++m) sv += expf(v[m] - vmax);
+    const float lse = vmax + logf(sv);
+    pix_ll = lse;
+    if (BWD) {
+      const float g = g_ll[b];
+      // overwrite the staged parameters with their gradients, component by component
+#pragma unroll
+      for (int m = 0; m < DM_M; ++m) {
+        float rm = expf(v[m] - lse);           // responsibility
+        float gS = g * rm;
+        float dlogit = g * (rm - expf(L[m] - lse0));
+        float c0r = L[10 + 20 + m], c1r = L[40 + 20 + m], c2r = L[70 + 20 + m];
+        float k0 = tanhf(c0r), k1 = tanhf(c1r), k2 = tanhf(c2r);
+        float mu[3] = {L[10 + m], L[40 + m] + k0 * xc[0], L[70 + m] + k1 * xc[0] + k2 * xc[1]};
+        float dmu[3];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          float lsr = L[10 + 30 * c + 10 + m];
+          float ls = fmaxf(lsr, -7.f), dc, dls;
+          dmol_term(xc[c], xc[c] - mu[c], ls, dc, dls, true);
+          dmu[c] = -gS * dc;                                     // cen = x - mu
+          L[10 + 30 * c + 10 + m] = lsr >= -7.f ? gS * dls : 0.f;   // clamp(min=-7) backward
+        }
+        L[m] = dlogit;
+        L[10 + m] = dmu[0];
+        L[40 + m] = dmu[1];
+        L[70 + m] = dmu[2];
+        L[10 + 20 + m] = dmu[1] * xc[0] * (1.f - k0 * k0);
+        L[40 + 20 + m] = dmu[2] * xc[0] * (1.f - k1 * k1);
+        L[70 + 20 + m] = dmu[2] * xc[1] * (1.f - k2 * k2);
+      }
+    }
+  }
+  if (!BWD) {
+    float s = block_sum(pix_ll, red);
+    if (threadIdx.x == 0) atomicAdd(ll + b, s);
+  } else {
+    __syncthreads();
+    float4* dst = reinterpret_cast<float4*>(dl + base);
+    int nq = npix * DM_P / 4;
+    for (int i = threadIdx.x; i < nq; i += DM_TILE) {
+      int e = i * 4;
+      float vv[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        int rr = (e + j) / DM_P, cidx = (e + j) - rr * DM_P;
+        vv[j] = sm[rr * DM_PITCH + cidx];
+      }
+      dst[i] = make_float4(vv[0], vv[1], vv[2], vv[3]);
+    }
+  }
+}
+
+static const size_t DMOL_SMEM = (DM_TILE * DM_PITCH + 32) * sizeof(float);
+
+// ll must be zeroed by the caller (partial sums are accumulated with atomics, 8 per image at 32x32)
+LVAE_API int lvae_dmol_fwd(const float* l, const float* x, float* ll, int B, int hw, cudaStream_t stream) {
+  LVAE_REQUIRE(l && x && ll && B > 0 && hw > 0, "dmol_fwd: bad args");
+  static bool attr = false;
+  if (!attr) {
+    cudaFuncSetAttribute(dmol_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DMOL_SMEM);
+    cudaFuncSetAttribute(dmol_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DMOL_SMEM);
+    attr = true;
+  }
+  dim3 grid(cdiv(hw, DM_TILE), B);
+  dmol_kernel<false><<<grid, DM_TILE, DMOL_SMEM, stream>>>(l, x, ll, nullptr, nullptr, hw);
+  LVAE_COUNT_LAUNCH();
+  LVAE_CHECK_LAUNCH("dmol_fwd");
+  return LVAE_OK;
+}
+
+LVAE_API int lvae_dmol_bwd(const float* l, const float* x, const float* g_ll, float* dl, int B, int hw, cudaStream_t stream) {
+  LVAE_REQUIRE(l && x && g_ll && dl && B > 0 && hw > 0, "dmol_bwd: bad args");
+  static bool attr = false;
+  if (!attr) {
+    cudaFuncSetAttribute(dmol_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DMOL_SMEM);
+    cudaFuncSetAttribute(dmol_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DMOL_SMEM);
+    attr = true;
+  }
+  dim3 grid(cdiv(hw, DM_TILE), B);
+  dmol_kernel<true><<<grid, DM_TILE, DMOL_SMEM, stream>>>(l, x, nullptr, g_ll, dl, hw);
+  LVAE_COUNT_LAUNCH();
+  LVAE_CHECK_LAUNCH("dmol_bwd");
+  return LVAE_OK;
+}
+
+// DMoL sampler: Gumbel-max over the mixture logits, logistic draw per colour, autoregressive means,
+// clamp to [-1,1], rescale to [0,1].  One thread per pixel; out is (B,3,H,W) NCHW.
+__global__ void dmol_sample_kernel(const float* __restrict__ l, float* __restrict__ out, long long npix, int hw,
+                                   const PhiloxState* rng, unsigned long long stream_id) {
+  PhiloxState st = *rng;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < npix; i += (long long)gridDim.x * blockDim.x) {
+    const float* L = l + i * DM_P;
+    float u[16];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      float4 t = philox_uniform4(st, stream_id, (unsigned long long)(i * 4 + q));
+      u[q * 4] = t.x; u[q * 4 + 1] = t.y; u[q * 4 + 2] = t.z; u[q * 4 + 3] = t.w;
+    }
+    int sel = 0;
+    float best = -INFINITY;
+#pragma unroll
+    for (int m = 0; m < DM_M; ++m) {
+      float uu = 1e-5f + u[m] * (1.f - 2e-5f);
+      float s = L[m] - logf(-logf(uu));
+      if (s > best) { best = s; sel = m; }
+    }
+    float xs[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      float uu = 1e-5f + u[10 + c] * (1.f - 2e-5f);
+      float mean = L[10 + 30 * c + sel], ls = fmaxf(L[10 + 30 * c + 10 + sel], -7.f);
+      xs[c] = mean + expf(ls) * (logf(uu) - logf(1.f - uu));
+    }
+    float k0 = tanhf(L[10 + 20 + sel]), k1 = tanhf(L[40 + 20 + sel]), k2 = tanhf(L[70 + 20 + sel]);
+    float x0 = fminf(fmaxf(xs[0], -1.f), 1.f);
+    float x1 = fminf(fmaxf(xs[1] + k0 * x0, -1.f), 1.f);
+    float x2 = fminf(fmaxf(xs[2] + k1 * x0 + k2 * x1, -1.f), 1.f);
+    long long b = i / hw;
+    int pix = (int)(i - b * hw);
+    out[(b * 3 + 0) * hw + pix] = fminf(fmaxf((x0 + 1.f) * 0.5f, 0.f), 1.f);
+    out[(b * 3 + 1) * hw + pix] = fminf(fmaxf((x1 + 1.f) * 0.5f, 0.f), 1.f);
+    out[(b * 3 + 2) * hw + pix] = fminf(fmaxf((x2 + 1.f) * 0.5f, 0.f), 1.f);
+  }
+}
+
+LVAE_API int lvae_dmol_sample(const float* l, float* out_nchw, int B, int hw, const void* rng_state,
+                              unsigned long long stream_id, cudaStream_t stream) {
+  LVAE_REQUIRE(l && out_nchw && rng_state, "dmol_sample: bad args");
+  long long n = (long long)B * hw;
+  int grid = (int)min((long long)4 * lvae_num_sms(), (n + 127) / 128);
+  dmol_sample_kernel<<<grid, 128, 0, stream>>>(l, out_nchw, n, hw, (const PhiloxState*)rng_state, stream_id);
+  LVAE_COUNT_LAUNCH();
+  LVAE_CHECK_LAUNCH("dmol_sample");
+  return LVAE_OK;
+}

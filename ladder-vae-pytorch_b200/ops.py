@@ -1,0 +1,655 @@
+"""torch.autograd glue over the C-ABI kernels.
+
+Tensors that cross this layer are *logical* NCHW (what the reference's modules exchange) but
+*physically* NHWC: ``nhwc(x)`` returns the contiguous (B,H,W,C) view the kernels consume and
+``as_nchw(y)`` re-labels a kernel output without copying.  Nothing here computes on the CPU
+and nothing falls back to ATen for the hot ops; a missing library raises.
+"""
+from __future__ import annotations
+
+import struct
+import threading
+from contextlib import contextmanager
+from typing import List, Optional
+
+import torch
+from torch.autograd import Function
+
+from . import _capi
+
+call = _capi.call
+
+ACT_IDS = {None: 0, "none": 0, "relu": 1, "leakyrelu": 2, "elu": 3, "selu": 4}
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _p(t):
+    return None if t is None else t.data_ptr()
+
+
+def _dt(t) -> int:
+    if t.dtype == torch.float32:
+        return 0
+    if t.dtype == torch.bfloat16:
+        return 1
+    raise TypeError("lvae_b200 kernels take float32 or bfloat16 activations, got %s" % t.dtype)
+
+
+def _require_cuda(t):
+    if not t.is_cuda:
+        raise RuntimeError("lvae_b200 has no CPU path: tensors must live on a CUDA (sm_100a) device")
+
+
+def nhwc(x: torch.Tensor) -> torch.Tensor:
+    """logical NCHW -> contiguous (B,H,W,C) (zero-copy when x is already NHWC-physical)."""
+    y = x.permute(0, 2, 3, 1)
+    return y if y.is_contiguous() else y.contiguous()
+
+
+def as_nchw(y: torch.Tensor) -> torch.Tensor:
+    """(B,H,W,C) contiguous kernel output -> logical NCHW view."""
+    return y.permute(0, 3, 1, 2)
+
+
+# --------------------------------------------------------------------------- RNG + injection
+class _Rng(threading.local):
+    def __init__(self):
+        self.state = {}        # device index -> int64[2] tensor (seed, offset)
+        self.seed = None
+        self.stream_id = 0
+
+
+_rng = _Rng()
+
+
+def manual_seed(seed: int) -> None:
+    _rng.seed = int(seed)
+    _rng.state = {}
+    _rng.stream_id = 0
+
+
+def rng_state(device) -> torch.Tensor:
+    idx = device.index if device.index is not None else torch.cuda.current_device()
+    st = _rng.state.get(idx)
+    if st is None:
+        seed = _rng.seed if _rng.seed is not None else (torch.initial_seed() & 0x7FFFFFFFFFFFFFFF)
+        st = torch.tensor([seed, 0], dtype=torch.int64, device=torch.device("cuda", idx))
+        _rng.state[idx] = st
+    return st
+
+
+def next_stream_id() -> int:
+    _rng.stream_id += 1
+    return _rng.stream_id
+
+
+def set_stream_id(v: int) -> None:
+    _rng.stream_id = int(v)
+
+
+def rng_advance(device, inc: int = 1 << 36) -> None:
+    call("lvae_rng_advance", rng_state(device).data_ptr(), inc, _stream())
+
+
+class StepContext(threading.local):
+    """Per-forward side inputs: injected eps / dropout masks (parity tests) or one pre-drawn
+    mask arena for all Dropout2d sites of a forward (one launch instead of ~300)."""
+
+    def __init__(self):
+        self.eps: Optional[List[torch.Tensor]] = None
+        self.masks: Optional[List[torch.Tensor]] = None
+        self.mask_arena: Optional[torch.Tensor] = None
+        self.mask_cursor = 0
+
+
+_ctx = StepContext()
+
+
+@contextmanager
+def inject(eps=None, masks=None):
+    """Feed fixed noise to the next forward: ``eps`` = list of (B,Z,h,w) tensors in execution
+    (top-down) order, ``masks`` = list of (B,C,1,1) or (B,C) keep masks already scaled by 1/(1-p)."""
+    old = (_ctx.eps, _ctx.masks)
+    _ctx.eps = list(eps) if eps is not None else None
+    _ctx.masks = list(masks) if masks is not None else None
+    try:
+        yield
+    finally:
+        _ctx.eps, _ctx.masks = old
+
+
+def pop_eps():
+    if _ctx.eps is None:
+        return None
+    if not _ctx.eps:
+        raise RuntimeError("injected eps list exhausted")
+    return _ctx.eps.pop(0)
+
+
+def prepare_masks(n_sites: int, batch: int, channels: int, p: float, device) -> None:
+    """Draw all Dropout2d masks of one forward in a single launch."""
+    if _ctx.masks is not None or n_sites == 0 or not p:
+        _ctx.mask_arena = None
+        return
+    arena = torch.empty((n_sites, batch, channels), dtype=torch.float32, device=device)
+    call("lvae_dropout_masks", arena.data_ptr(), arena.numel(), float(p), rng_state(device).data_ptr(),
+         next_stream_id(), _stream())
+    _ctx.mask_arena, _ctx.mask_cursor = arena, 0
+
+
+def clear_masks() -> None:
+    _ctx.mask_arena = None
+    _ctx.mask_cursor = 0
+
+
+def next_mask(batch: int, channels: int, p: float, device) -> Optional[torch.Tensor]:
+    """(B,C) fp32 keep mask scaled by 1/(1-p) for one Dropout2d site (None when p == 0)."""
+    if _ctx.masks is not None:
+        if not _ctx.masks:
+            raise RuntimeError("injected dropout mask list exhausted")
+        m = _ctx.masks.pop(0)
+        return m.reshape(batch, channels).to(device=device, dtype=torch.float32).contiguous()
+    if not p:
+        return None
+    a = _ctx.mask_arena
+    if a is not None and _ctx.mask_cursor < a.shape[0] and a.shape[1] == batch and a.shape[2] == channels:
+        m = a[_ctx.mask_cursor]
+        _ctx.mask_cursor += 1
+        return m
+    m = torch.empty((batch, channels), dtype=torch.float32, device=device)
+    call("lvae_dropout_masks", m.data_ptr(), m.numel(), float(p), rng_state(device).data_ptr(),
+         next_stream_id(), _stream())
+    return m
+
+
+# --------------------------------------------------------------------------- gradient sinks
+def grad_sink(param) -> Optional[torch.Tensor]:
+    """Engine-owned flat gradient arena slice for this parameter (kernels accumulate into it
+    directly, autograd is bypassed for parameter gradients); None -> return grads normally."""
+    return getattr(param, "_lvae_grad_sink", None)
+
+
+def _param_grad_buffer(param):
+    sink = grad_sink(param)
+    if sink is not None:
+        return sink, True
+    return torch.zeros_like(param, dtype=torch.float32, memory_format=torch.contiguous_format), False
+
+
+# --------------------------------------------------------------------------- packed weights
+_PACK_FMT = "<QQiiiiii"   # must match LvaePackDesc in csrc/conv_generic.cu
+
+
+class WeightPack:
+    """GEMM-ready copy of one conv weight (see lvae_pack_weights).  Re-packed when the
+    parameter's version counter or storage changes (i.e. after every optimizer step)."""
+
+    def __init__(self, O: int, I: int, taps: int, mode: int):
+        self.O, self.I, self.taps, self.mode = O, I, taps, mode
+        n = O if mode == 0 else I
+        self.ld = (n + 3) // 4 * 4
+        self.rows = taps * (I if mode == 0 else O)
+        self.buf = None
+        self.desc = None
+        self.key = None
+
+    def get(self, weight: torch.Tensor, dtype: torch.dtype) -> torch.Tensor:
+        key = (weight.data_ptr(), weight._version, dtype, weight.device)
+        if self.key == key:
+            return self.buf
+        if self.buf is None or self.buf.dtype != dtype or self.buf.device != weight.device or \
+                self.desc_src != weight.data_ptr():
+            self.buf = torch.empty((self.rows, self.ld), dtype=dtype, device=weight.device)
+            raw = struct.pack(_PACK_FMT, weight.data_ptr(), self.buf.data_ptr(), self.O, self.I, self.taps,
+                              self.mode, self.ld, 0 if dtype == torch.float32 else 1)
+            assert len(raw) == _capi.lib().lvae_pack_desc_size()
+            self.desc = torch.frombuffer(bytearray(raw), dtype=torch.uint8).to(weight.device)
+            self.desc_src = weight.data_ptr()
+        call("lvae_pack_weights", self.desc.data_ptr(), 1, _stream())
+        self.key = key
+        return self.buf
+
+    def mark_fresh(self, weight, dtype):
+        """The engine packed every weight in one batched launch; record that this one is current."""
+        self.key = (weight.data_ptr(), weight._version, dtype, weight.device)
+
+
+class ConvSpec:
+    """Static geometry + packed-weight caches of one conv module (Conv2d or ConvTranspose2d)."""
+
+    def __init__(self, cout, cin, k, stride, pad, transposed=False, output_padding=0):
+        self.cout, self.cin, self.k, self.stride, self.pad = cout, cin, k, stride, pad
+        self.transposed, self.output_padding = transposed, output_padding
+        taps = k * k
+        if not transposed:            # weight (Cout, Cin, k, k)
+            self.pack_fwd = WeightPack(cout, cin, taps, 0)    # rows (tap, ci) -> cols co
+            self.pack_bwd = WeightPack(cout, cin, taps, 1)    # rows (tap, co) -> cols ci
+        else:                         # weight (Cin, Cout, k, k): O' = Cin, I' = Cout
+            self.pack_fwd = WeightPack(cin, cout, taps, 1)    # rows (tap, ci) -> cols co
+            self.pack_bwd = WeightPack(cin, cout, taps, 0)    # rows (tap, co) -> cols ci
+
+    def out_hw(self, h, w):
+        if not self.transposed:
+            return ((h + 2 * self.pad - self.k) // self.stride + 1, (w + 2 * self.pad - self.k) // self.stride + 1)
+        return ((h - 1) * self.stride - 2 * self.pad + self.k + self.output_padding,
+                (w - 1) * self.stride - 2 * self.pad + self.k + self.output_padding)
+
+
+def _gather(x, x2, wp, ld, bias, in_scale, out_scale, res, B, Hi, Wi, C1, C2, Ho, Wo, N, k, stride, pad, mode, out_dtype):
+    y = torch.empty((B, Ho, Wo, N), dtype=out_dtype, device=x.device)
+    call("lvae_conv2d_gather", x.data_ptr(), _p(x2), wp.data_ptr(), _p(bias), _p(in_scale), _p(out_scale), _p(res),
+         y.data_ptr(), B, Hi, Wi, C1, C2, Ho, Wo, N, ld, k, k, stride, pad, mode, _dt(x), _stream())
+    return y
+
+
+class Conv2dFn(Function):
+    """y = (conv(cat(x, x2)) + bias) * out_scale[b, c] + res   (Conv2d or ConvTranspose2d)."""
+
+    @staticmethod
+    def forward(ctx, x, x2, weight, bias, out_scale, res, spec: ConvSpec):
+        _require_cuda(x)
+        xn = nhwc(x)
+        x2n = nhwc(x2) if x2 is not None else None
+        resn = nhwc(res) if res is not None else None
+        B, Hi, Wi, C1 = xn.shape
+        C2 = x2n.shape[3] if x2n is not None else 0
+        assert C1 + C2 == spec.cin, "conv input channels %d+%d != %d" % (C1, C2, spec.cin)
+        Ho, Wo = spec.out_hw(Hi, Wi)
+        wp = spec.pack_fwd.get(weight, xn.dtype)
+        if out_scale is not None:
+            out_scale = out_scale.reshape(B, spec.cout)
+        y = _gather(xn, x2n, wp, spec.pack_fwd.ld, bias, None, out_scale, resn, B, Hi, Wi, C1, C2, Ho, Wo,
+                    spec.cout, spec.k, spec.stride, spec.pad, 1 if spec.transposed else 0, xn.dtype)
+        ctx.spec = spec
+        ctx.save_for_backward(xn, x2n, weight, bias, out_scale)
+        ctx.has_res = res is not None
+        return as_nchw(y)
+
+    @staticmethod
+    def backward(ctx, gy):
+        spec = ctx.spec
+        xn, x2n, weight, bias, out_scale = ctx.saved_tensors
+        gyn = nhwc(gy)
+        B, Hi, Wi, C1 = xn.shape
+        C2 = x2n.shape[3] if x2n is not None else 0
+        _, Ho, Wo, N = gyn.shape
+        gx = gx2 = gw = gb = None
+        need_x = ctx.needs_input_grad[0] or (x2n is not None and ctx.needs_input_grad[1])
+        if need_x:
+            wpb = spec.pack_bwd.get(weight, gyn.dtype)
+            gcat = _gather(gyn, None, wpb, spec.pack_bwd.ld, None, out_scale, None, None, B, Ho, Wo, N, 0, Hi, Wi,
+                           spec.cin, spec.k, spec.stride, spec.pad, 0 if spec.transposed else 1, gyn.dtype)
+            if x2n is None:
+                gx = as_nchw(gcat)
+            else:
+                gx = as_nchw(gcat[..., :C1])
+                gx2 = as_nchw(gcat[..., C1:])
+        if ctx.needs_input_grad[2]:
+            gwbuf, sunk = _param_grad_buffer(weight)
+            gbbuf, bsunk = (None, True)
+            if bias is not None and ctx.needs_input_grad[3]:
+                gbbuf, bsunk = _param_grad_buffer(bias)
+            if not spec.transposed:
+                call("lvae_conv2d_wgrad", xn.data_ptr(), _p(x2n), gyn.data_ptr(), None, _p(out_scale),
+                     gwbuf.data_ptr(), _p(gbbuf), B, Hi, Wi, C1, C2, Ho, Wo, N, spec.k, spec.k, spec.stride,
+                     spec.pad, _dt(xn), _stream())
+            else:
+                # roles swap: "input" = dy (scaled), "output grad" = x; result is (Cin, Cout, k, k)
+                call("lvae_conv2d_wgrad", gyn.data_ptr(), None, xn.data_ptr(), _p(out_scale), None,
+                     gwbuf.data_ptr(), None, B, Ho, Wo, N, 0, Hi, Wi, C1, spec.k, spec.k, spec.stride, spec.pad,
+                     _dt(xn), _stream())
+                if gbbuf is not None:
+                    call("lvae_colsum", gyn.data_ptr(), _p(out_scale), gbbuf.data_ptr(), B, Ho * Wo, N, _dt(gyn), _stream())
+            gw = None if sunk else gwbuf
+            gb = None if (bsunk or gbbuf is None) else gbbuf
+        gos = None
+        if out_scale is not None and ctx.needs_input_grad[4]:
+            raise RuntimeError("gradient wrt the dropout mask is not supported")
+        gres = gy if ctx.has_res and ctx.needs_input_grad[5] else None
+        return gx, gx2, gw, gb, gos, gres, None
+
+
+def conv2d(x, weight, bias, spec: ConvSpec, x2=None, out_scale=None, res=None):
+    return Conv2dFn.apply(x, x2, weight, bias, out_scale, res, spec)
+
+
+# --------------------------------------------------------------------------- BatchNorm (+ nonlinearity)
+class BnActFn(Function):
+    """y = act(batch_norm(x)); bn may be absent (plain activation).  Running statistics and
+    num_batches_tracked are updated on the device in train mode."""
+
+    @staticmethod
+    def forward(ctx, x, gamma, beta, running_mean, running_var, nbt, acc, training, momentum, eps, act, out_dtype):
+        _require_cuda(x)
+        xn = nhwc(x)
+        B, H, W, C = xn.shape
+        Pn = B * H * W
+        y = torch.empty((B, H, W, C), dtype=out_dtype or xn.dtype, device=xn.device)
+        mean = rstd = None
+        if gamma is not None:
+            stats = torch.empty((2, C), dtype=torch.float32, device=xn.device)
+            mean, rstd = stats[0], stats[1]
+            if training:
+                call("lvae_bn_stats", xn.data_ptr(), acc.data_ptr(), Pn, C, _dt(xn), _stream())
+                call("lvae_bn_finalize", acc.data_ptr(), mean.data_ptr(), rstd.data_ptr(), _p(running_mean),
+                     _p(running_var), _p(nbt), Pn, C, float(momentum), float(eps), _stream())
+            else:
+                call("lvae_bn_eval_prepare", running_mean.data_ptr(), running_var.data_ptr(), mean.data_ptr(),
+                     rstd.data_ptr(), C, float(eps), _stream())
+        call("lvae_bn_act_fwd", xn.data_ptr(), y.data_ptr(), _p(mean), _p(rstd), _p(gamma), _p(beta), Pn, C, act,
+             _dt(xn), _dt(y), _stream())
+        ctx.save_for_backward(xn, mean, rstd, gamma, beta)
+        ctx.acc, ctx.training, ctx.act = acc, training, act
+        return as_nchw(y)
+
+    @staticmethod
+    def backward(ctx, gy):
+        xn, mean, rstd, gamma, beta = ctx.saved_tensors
+        gyn = nhwc(gy)
+        if gyn.dtype != xn.dtype:
+            gyn = gyn.to(xn.dtype)
+        B, H, W, C = xn.shape
+        Pn = B * H * W
+        gx = torch.empty_like(xn)
+        gg = gb = None
+        gsunk = bsunk = True
+        if gamma is not None:
+            gg, gsunk = _param_grad_buffer(gamma)
+            gb, bsunk = _param_grad_buffer(beta)
+        call("lvae_bn_act_bwd", gyn.data_ptr(), xn.data_ptr(), gx.data_ptr(), _p(mean), _p(rstd), _p(gamma), _p(beta),
+             _p(ctx.acc), _p(gg), _p(gb), Pn, C, ctx.act, 1 if ctx.training else 0, _dt(xn), _stream())
+        return (as_nchw(gx), None if gsunk else gg, None if bsunk else gb, None, None, None, None, None, None, None,
+                None, None)
+
+
+def bn_act(x, bn, act_id: int, out_dtype=None):
+    """bn: our BatchNorm2d module or None."""
+    if bn is None:
+        return BnActFn.apply(x, None, None, None, None, None, None, False, 0.0, 0.0, act_id, out_dtype)
+    training = bn.training or (bn.running_mean is None)
+    return BnActFn.apply(x, bn.weight, bn.bias, bn.running_mean, bn.running_var,
+                         bn.num_batches_tracked if training else None, bn.stat_acc(x.device), training,
+                         bn.momentum if bn.momentum is not None else 0.1, bn.eps, act_id, out_dtype)
+
+
+# --------------------------------------------------------------------------- gate (+ residual)
+class GateFn(Function):
+    @staticmethod
+    def forward(ctx, h, res, act):
+        hn = nhwc(h)
+        B, H, W, C2 = hn.shape
+        C = C2 // 2
+        resn = nhwc(res) if res is not None else None
+        out = torch.empty((B, H, W, C), dtype=hn.dtype, device=hn.device)
+        call("lvae_gate_fwd", hn.data_ptr(), _p(resn), out.data_ptr(), B * H * W, C, act, _dt(hn), _stream())
+        ctx.save_for_backward(hn)
+        ctx.act, ctx.has_res = act, res is not None
+        return as_nchw(out)
+
+    @staticmethod
+    def backward(ctx, g):
+        (hn,) = ctx.saved_tensors
+        gn = nhwc(g)
+        B, H, W, C2 = hn.shape
+        dh = torch.empty_like(hn)
+        call("lvae_gate_bwd", gn.data_ptr(), hn.data_ptr(), dh.data_ptr(), B * H * W, C2 // 2, ctx.act, _dt(hn), _stream())
+        return as_nchw(dh), (g if ctx.has_res else None), None
+
+
+def gate(h, res, act_id):
+    return GateFn.apply(h, res, act_id)
+
+
+# --------------------------------------------------------------------------- resampling helpers
+class Upsample2xFn(Function):
+    @staticmethod
+    def forward(ctx, x):
+        xn = nhwc(x)
+        B, H, W, C = xn.shape
+        y = torch.empty((B, 2 * H, 2 * W, C), dtype=xn.dtype, device=xn.device)
+        call("lvae_upsample2x_fwd", xn.data_ptr(), y.data_ptr(), B, H, W, C, _dt(xn), _stream())
+        ctx.shape = (B, H, W, C)
+        return as_nchw(y)
+
+    @staticmethod
+    def backward(ctx, g):
+        gn = nhwc(g)
+        B, H, W, C = ctx.shape
+        dx = torch.empty((B, H, W, C), dtype=gn.dtype, device=gn.device)
+        call("lvae_upsample2x_bwd", gn.data_ptr(), dx.data_ptr(), B, H, W, C, _dt(gn), _stream())
+        return as_nchw(dx)
+
+
+def upsample2x(x):
+    return Upsample2xFn.apply(x)
+
+
+def _copy_window(src, dst, B, C, Hs, Ws, Hd, Wd, sy0, sx0, dy0, dx0, h, w, src_nchw, dst_nchw):
+    call("lvae_copy_window", src.data_ptr(), dst.data_ptr(), B, C, Hs, Ws, Hd, Wd, sy0, sx0, dy0, dx0, h, w,
+         1 if src_nchw else 0, 1 if dst_nchw else 0, _dt(src), _dt(dst), _stream())
+
+
+def pad_image(x: torch.Tensor, size, out_dtype=torch.float32) -> torch.Tensor:
+    """boilr pad_img_tensor on the *input image* (no gradient needed): NCHW user tensor ->
+    zero-padded NHWC-physical activation (logical NCHW)."""
+    _require_cuda(x)
+    x = x.contiguous()
+    if x.dtype != torch.float32:
+        x = x.float()
+    B, C, H, W = x.shape
+    Hp, Wp = int(size[0]), int(size[1])
+    dr, dc = Hp - H, Wp - W
+    if dr < 0 or dc < 0:
+        raise ValueError("trying to pad to a smaller size")
+    if dr == 0 and dc == 0:
+        y = torch.empty((B, Hp, Wp, C), dtype=out_dtype, device=x.device)
+    else:
+        y = torch.zeros((B, Hp, Wp, C), dtype=out_dtype, device=x.device)
+    _copy_window(x, y, B, C, H, W, Hp, Wp, 0, 0, dr // 2, dc // 2, H, W, True, False)
+    return as_nchw(y)
+
+
+class CropFn(Function):
+    """boilr crop_img_tensor (centred) on an NHWC-physical activation."""
+
+    @staticmethod
+    def forward(ctx, x, size):
+        xn = nhwc(x)
+        B, H, W, C = xn.shape
+        h, w = int(size[0]), int(size[1])
+        dr, dc = H - h, W - w
+        if dr < 0 or dc < 0:
+            raise ValueError("trying to crop to a larger size")
+        y = torch.empty((B, h, w, C), dtype=xn.dtype, device=xn.device)
+        _copy_window(xn, y, B, C, H, W, h, w, dr // 2, dc // 2, 0, 0, h, w, False, False)
+        ctx.geom = (B, H, W, C, h, w, dr // 2, dc // 2)
+        return as_nchw(y)
+
+    @staticmethod
+    def backward(ctx, g):
+        B, H, W, C, h, w, y0, x0 = ctx.geom
+        gn = nhwc(g)
+        dx = torch.zeros((B, H, W, C), dtype=gn.dtype, device=gn.device)
+        _copy_window(gn, dx, B, C, h, w, H, W, 0, 0, y0, x0, h, w, False, False)
+        return as_nchw(dx), None
+
+
+def crop(x, size):
+    if tuple(x.shape[2:]) == tuple(int(s) for s in size):
+        return x
+    return CropFn.apply(x, size)
+
+
+# --------------------------------------------------------------------------- stochastic block core
+class StochasticFn(Function):
+    """Everything between conv_in_* and conv_out of NormalStochasticBlock2d (lib/stochastic.py:45-96)."""
+
+    @staticmethod
+    def forward(ctx, q_params, p_params, eps, forced, use_mode, analytical, lowp_copy):
+        _require_cuda(p_params)
+        pn = nhwc(p_params).float()
+        qn = nhwc(q_params).float() if q_params is not None else None
+        ref = qn if qn is not None else pn
+        p_broadcast = pn.shape[0] == 1 and ref.shape[0] != 1
+        B, H, W, Z2 = ref.shape
+        Z, hw = Z2 // 2, H * W
+        dev = ref.device
+        epsn = nhwc(eps).float() if eps is not None else None
+        forcedn = nhwc(forced).float() if forced is not None else None
+        z = torch.empty((B, H, W, Z), dtype=torch.float32, device=dev)
+        z_lp = torch.empty((B, H, W, Z), dtype=torch.bfloat16, device=dev) if lowp_copy else None
+        logp = torch.empty((B,), dtype=torch.float32, device=dev)
+        if qn is not None:
+            kl = torch.empty((B,), dtype=torch.float32, device=dev)
+            logq = torch.empty((B,), dtype=torch.float32, device=dev)
+            kls = torch.empty((B, H, W), dtype=torch.float32, device=dev)
+        else:
+            kl = logq = kls = None
+        need_rng = epsn is None and forcedn is None and not use_mode
+        call("lvae_stoch_fwd", _p(qn), pn.data_ptr(), 1 if p_broadcast else 0, _p(epsn), _p(forcedn),
+             rng_state(dev).data_ptr() if need_rng else None, next_stream_id() if need_rng else 0,
+             z.data_ptr(), _p(z_lp), _p(kl), _p(kls), logp.data_ptr(), _p(logq), B, hw, Z,
+             1 if use_mode else 0, 1 if analytical else 0, _stream())
+        ctx.save_for_backward(qn, pn, z)
+        ctx.meta = (B, hw, Z, p_broadcast, analytical, 0 if forced is not None else (2 if use_mode else 1))
+        ctx.q_dtype = q_params.dtype if q_params is not None else None
+        ctx.p_dtype = p_params.dtype
+        zo = as_nchw(z)
+        zlo = as_nchw(z_lp) if z_lp is not None else None
+        ctx.mark_non_differentiable(*([zlo] if zlo is not None else []))
+        return zo, zlo, kl, kls, logp, logq
+
+    @staticmethod
+    def backward(ctx, g_z, g_zlp, g_kl, g_kls, g_logp, g_logq):
+        qn, pn, z = ctx.saved_tensors
+        if qn is None:
+            raise RuntimeError("backward through prior sampling is not supported")
+        B, hw, Z, p_broadcast, analytical, z_kind = ctx.meta
+        gz = nhwc(g_z).float() if g_z is not None else None
+        cg = lambda t: t.contiguous().float() if t is not None else None
+        g_kl, g_kls, g_logp, g_logq = cg(g_kl), cg(g_kls), cg(g_logp), cg(g_logq)
+        dq = torch.empty_like(qn)
+        dp = torch.empty((B,) + tuple(qn.shape[1:]), dtype=torch.float32, device=qn.device)
+        call("lvae_stoch_bwd", qn.data_ptr(), pn.data_ptr(), 1 if p_broadcast else 0, z.data_ptr(), _p(gz), _p(g_kl),
+             _p(g_logp), _p(g_logq), _p(g_kls), dq.data_ptr(), dp.data_ptr(), B, hw, Z, 1 if analytical else 0,
+             z_kind, _stream())
+        if p_broadcast:
+            dps = torch.empty_like(pn)
+            call("lvae_sum_batch", dp.data_ptr(), dps.data_ptr(), B, dps.numel(), 0, _stream())
+            dp = dps
+        dq, dp = as_nchw(dq), as_nchw(dp)
+        if ctx.q_dtype != torch.float32:
+            dq = dq.to(ctx.q_dtype)
+        if ctx.p_dtype != torch.float32:
+            dp = dp.to(ctx.p_dtype)
+        return dq, dp, None, None, None, None, None
+
+
+def stochastic_core(q_params, p_params, eps=None, forced=None, use_mode=False, analytical=False, lowp_copy=False):
+    return StochasticFn.apply(q_params, p_params, eps, forced, use_mode, analytical, lowp_copy)
+
+
+# --------------------------------------------------------------------------- likelihoods
+class BernoulliFn(Function):
+    """sigmoid + Bernoulli log-likelihood (lib/likelihoods.py:61-62,385-388). Returns (prob, ll)."""
+
+    @staticmethod
+    def forward(ctx, logits, x):
+        ln = nhwc(logits).float()
+        B, H, W, C = ln.shape
+        prob = torch.empty_like(ln)
+        ll = None
+        xc = None
+        if x is not None:
+            xc = x.contiguous().float()
+            assert tuple(xc.shape) == (B, C, H, W), "image shape %s vs params %s" % (tuple(xc.shape), (B, C, H, W))
+            ll = torch.empty((B,), dtype=torch.float32, device=ln.device)
+        call("lvae_bernoulli_fwd", ln.data_ptr(), _p(xc), prob.data_ptr(), _p(ll), B, H * W, C, _stream())
+        ctx.save_for_backward(prob, xc)
+        ctx.in_dtype = logits.dtype
+        return as_nchw(prob), ll
+
+    @staticmethod
+    def backward(ctx, g_prob, g_ll):
+        prob, xc = ctx.saved_tensors
+        B, H, W, C = prob.shape
+        if xc is None or g_ll is None:
+            if g_prob is None:
+                return None, None
+            gp = nhwc(g_prob).float()
+            return as_nchw(gp * prob * (1 - prob)).to(ctx.in_dtype), None
+        gp = nhwc(g_prob).float() if g_prob is not None else None
+        dl = torch.empty_like(prob)
+        call("lvae_bernoulli_bwd", prob.data_ptr(), xc.data_ptr(), g_ll.contiguous().float().data_ptr(), _p(gp),
+             dl.data_ptr(), B, H * W, C, _stream())
+        out = as_nchw(dl)
+        return (out if ctx.in_dtype == torch.float32 else out.to(ctx.in_dtype)), None
+
+
+def bernoulli_loglik(logits, x):
+    return BernoulliFn.apply(logits, x)
+
+
+def bernoulli_sample(prob):
+    pn = nhwc(prob).float()
+    B, H, W, C = pn.shape
+    out = torch.empty((B, C, H, W), dtype=torch.float32, device=pn.device)
+    call("lvae_bernoulli_sample", pn.data_ptr(), out.data_ptr(), B, H * W, C, rng_state(pn.device).data_ptr(),
+         next_stream_id(), _stream())
+    return out
+
+
+class DmolFn(Function):
+    """-discretized_mix_logistic_loss(2x-1, l) (lib/likelihoods.py:226-230,291-382) -> ll (B,)."""
+
+    @staticmethod
+    def forward(ctx, l, x):
+        ln = nhwc(l).float()
+        B, H, W, C = ln.shape
+        if C != 100:
+            raise RuntimeError("discretized logistic mixture expects 100 parameter channels, got %d" % C)
+        xc = x.contiguous().float()
+        assert tuple(xc.shape) == (B, 3, H, W), "image shape %s vs params %s" % (tuple(xc.shape), (B, 3, H, W))
+        ll = torch.zeros((B,), dtype=torch.float32, device=ln.device)
+        call("lvae_dmol_fwd", ln.data_ptr(), xc.data_ptr(), ll.data_ptr(), B, H * W, _stream())
+        ctx.save_for_backward(ln, xc)
+        ctx.in_dtype = l.dtype
+        return ll
+
+    @staticmethod
+    def backward(ctx, g_ll):
+        ln, xc = ctx.saved_tensors
+        B, H, W, C = ln.shape
+        dl = torch.empty_like(ln)
+        call("lvae_dmol_bwd", ln.data_ptr(), xc.data_ptr(), g_ll.contiguous().float().data_ptr(), dl.data_ptr(), B,
+             H * W, _stream())
+        out = as_nchw(dl)
+        return (out if ctx.in_dtype == torch.float32 else out.to(ctx.in_dtype)), None
+
+
+def dmol_loglik(l, x):
+    return DmolFn.apply(l, x)
+
+
+def dmol_sample(l):
+    ln = nhwc(l).float()
+    B, H, W, C = ln.shape
+    out = torch.empty((B, 3, H, W), dtype=torch.float32, device=ln.device)
+    call("lvae_dmol_sample", ln.data_ptr(), out.data_ptr(), B, H * W, rng_state(ln.device).data_ptr(), next_stream_id(),
+         _stream())
+    return out
+
+
+# --------------------------------------------------------------------------- IW bound
+def iw_lse_update(ll, kl_sep, state, first: bool):
+    call("lvae_iw_lse_update", ll.data_ptr(), kl_sep.data_ptr(), state.data_ptr(), ll.numel(), 1 if first else 0, _stream())
+
+
+def iw_lse_combine(states, k_total: int):
+    R, B, _ = states.shape
+    out = torch.empty((B,), dtype=torch.float32, device=states.device)
+    call("lvae_iw_lse_combine", states.data_ptr(), out.data_ptr(), R, B, int(k_total), _stream())
+    return out

@@ -1,0 +1,75 @@
+"""CPU: the C-ABI library builds, loads and exports every symbol include/lvae_b200.h declares
+(no compute calls without a GPU), and the package mirrors the reference's state_dict layout."""
+import ctypes
+import os
+import re
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def libpath():
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("lvae_build", os.path.join(ROOT, "ladder-vae-pytorch_b200", "build.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod.build()
+
+
+def header_symbols():
+    text = open(os.path.join(ROOT, "include", "lvae_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(lvae_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_header_symbols_exported(libpath):
+    lib = ctypes.CDLL(libpath)
+    syms = header_symbols()
+    assert len(syms) >= 30
+    for s in syms:
+        assert hasattr(lib, s), "missing export %s" % s
+    lib.lvae_abi_version.restype = ctypes.c_int
+    assert lib.lvae_abi_version() == 1
+
+
+def test_binding_covers_header(libpath):
+    import lvae_b200
+    assert sorted(lvae_b200._capi.exported_symbols()) == header_symbols()
+    lvae_b200._capi.lib()       # loads and resolves every bound symbol
+
+
+def test_no_cpu_fallback(libpath):
+    import lvae_b200
+    from oracle import lvae_oracle as O
+    cfg = O.LVAEConfig(color_ch=1, z_dims=[4], img_shape=(8, 8), blocks_per_layer=1, n_filters=8, dropout=0.0,
+                       likelihood_form="bernoulli", res_block_type="bacdbacd", merge_type="residual", gated=True)
+    m = lvae_b200.LadderVAE(**cfg.kwargs())
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        m(torch.zeros(2, 1, 8, 8))
+
+
+@pytest.mark.parametrize("name", ["mnist3", "mnist12", "cifar15", "celeba20"])
+def test_state_dict_layout_matches_reference(name, libpath):
+    import lvae_b200
+    from oracle import lvae_oracle as O
+    cfg = O.baseline_config(name)
+    m = lvae_b200.LadderVAE(**cfg.kwargs())
+    sd, shapes = m.state_dict(), O.param_shapes(cfg)
+    assert list(sd.keys()) == list(shapes.keys())
+    for k in sd:
+        assert tuple(sd[k].shape) == tuple(shapes[k]), k
+    m.load_state_dict(O.make_params(cfg, 1), strict=True)
+
+
+def test_error_conventions(libpath):
+    import lvae_b200
+    from lvae_b200.lib.nn import ResidualBlock, ELU
+    with pytest.raises(ValueError):
+        ResidualBlock(8, ELU, block_type="nope")
+    with pytest.raises(TypeError):
+        ResidualBlock(8, ELU, block_type="bacdbacd", dropout=None)
+    with pytest.raises(RuntimeError, match="Unrecognized likelihood"):
+        lvae_b200.LadderVAE(1, [4], img_shape=(8, 8), likelihood_form="x", res_block_type="bacdbac", merge_type="residual")

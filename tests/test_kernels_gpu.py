@@ -1,0 +1,358 @@
+"""GPU parity, kernel by kernel: every C-ABI op against a float64 CPU restatement
+(torch functional ops / oracle functions) on the same seeded inputs.  Tolerances are for fp32
+kernels: 2e-5 relative on outputs, 1e-4 on gradients (north_star asks 1e-4 / 1e-3)."""
+import math
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from lvae_test_helpers import rel_err
+
+pytestmark = pytest.mark.gpu
+
+TOL, GTOL = 2e-5, 1e-4
+
+
+@pytest.fixture(scope="module")
+def L():
+    import lvae_b200
+    lvae_b200._capi.device_check()
+    return lvae_b200
+
+
+def dev(t, requires_grad=False):
+    return t.float().cuda().requires_grad_(requires_grad)
+
+
+def to_nhwc_phys(t):
+    """NCHW tensor whose memory is NHWC (what our modules exchange)."""
+    return t.permute(0, 2, 3, 1).contiguous().permute(0, 3, 1, 2)
+
+
+CONV_CASES = [
+    # cin, cout, k, stride, pad, transposed, H, W, B, cin2
+    (64, 64, 3, 1, 1, False, 8, 8, 3, 0),
+    (64, 64, 3, 2, 1, False, 8, 8, 2, 0),
+    (64, 64, 3, 2, 1, True, 4, 4, 2, 0),
+    (64, 128, 1, 1, 0, False, 4, 4, 2, 0),
+    (64, 64, 1, 1, 0, False, 4, 6, 2, 64),
+    (1, 64, 5, 2, 2, False, 32, 32, 2, 0),
+    (3, 16, 5, 1, 2, False, 9, 7, 2, 0),
+    (32, 64, 3, 1, 1, False, 2, 2, 5, 0),
+    (64, 100, 3, 1, 1, False, 6, 6, 2, 0),
+    (64, 1, 3, 1, 1, False, 28, 28, 2, 0),
+    (16, 16, 3, 1, 1, False, 5, 5, 3, 0),
+    (6, 8, 3, 1, 1, False, 5, 5, 3, 0),
+    (8, 8, 3, 2, 1, True, 3, 5, 2, 0),
+]
+
+
+@pytest.mark.parametrize("case", CONV_CASES)
+def test_conv_fwd_bwd(L, case):
+    cin, cout, k, stride, pad, transposed, H, W, B, cin2 = case
+    from lvae_b200.lib.nn import Conv2d, ConvTranspose2d
+    g = torch.Generator().manual_seed(hash(case) % 1000)
+    x = torch.randn(B, cin, H, W, generator=g, dtype=torch.float64)
+    x2 = torch.randn(B, cin2, H, W, generator=g, dtype=torch.float64) if cin2 else None
+    if transposed:
+        mod = ConvTranspose2d(cin, cout, k, stride=stride, padding=pad, output_padding=1)
+    else:
+        mod = Conv2d(cin + cin2, cout, k, stride=stride, padding=pad)
+    w = torch.randn(mod.weight.shape, generator=g, dtype=torch.float64) / math.sqrt(cin * k * k)
+    b = torch.randn(cout, generator=g, dtype=torch.float64)
+    scale = (torch.rand(B, cout, generator=g, dtype=torch.float64) > 0.3).double() / 0.7
+    # float64 reference
+    xr = x.clone().requires_grad_(True)
+    x2r = x2.clone().requires_grad_(True) if cin2 else None
+    wr, br = w.clone().requires_grad_(True), b.clone().requires_grad_(True)
+    inp = torch.cat([xr, x2r], 1) if cin2 else xr
+    if transposed:
+        yr = F.conv_transpose2d(inp, wr, br, stride=stride, padding=pad, output_padding=1)
+    else:
+        yr = F.conv2d(inp, wr, br, stride=stride, padding=pad)
+    res = torch.randn(yr.shape, generator=g, dtype=torch.float64)
+    resr = res.clone().requires_grad_(True)
+    outr = yr * scale.view(B, cout, 1, 1) + resr
+    gy = torch.randn(outr.shape, generator=g, dtype=torch.float64)
+    outr.backward(gy)
+    # ours
+    mod = mod.cuda()
+    with torch.no_grad():
+        mod.weight.copy_(w.float())
+        mod.bias.copy_(b.float())
+    xd, resd = dev(x, True), dev(res, True)
+    x2d = dev(x2, True) if cin2 else None
+    kw = dict(out_scale=dev(scale), res=resd)
+    if cin2:
+        kw["x2"] = x2d
+    out = mod(xd, **kw)
+    assert tuple(out.shape) == tuple(outr.shape)
+    assert rel_err(out, outr) < TOL
+    out.backward(dev(gy))
+    assert rel_err(xd.grad, xr.grad) < GTOL
+    if cin2:
+        assert rel_err(x2d.grad, x2r.grad) < GTOL
+    assert rel_err(mod.weight.grad, wr.grad) < GTOL
+    assert rel_err(mod.bias.grad, br.grad) < GTOL
+    assert rel_err(resd.grad, resr.grad) < 1e-6
+
+
+@pytest.mark.parametrize("C,act,training", [(64, "elu", True), (64, "elu", False), (16, "relu", True),
+                                            (8, "selu", True), (24, "leakyrelu", True), (64, None, True)])
+def test_bn_act(L, C, act, training):
+    from lvae_b200.lib.nn import BatchNorm2d
+    from lvae_b200 import ops
+    g = torch.Generator().manual_seed(C)
+    B, H, W = 5, 6, 7
+    x = torch.randn(B, C, H, W, generator=g, dtype=torch.float64) * 2 + 0.5
+    gamma = 1 + 0.2 * torch.randn(C, generator=g, dtype=torch.float64)
+    beta = 0.3 * torch.randn(C, generator=g, dtype=torch.float64)
+    rm = 0.1 * torch.randn(C, generator=g, dtype=torch.float64)
+    rv = 1 + 0.3 * torch.rand(C, generator=g, dtype=torch.float64)
+    fn = {None: lambda t: t, "elu": F.elu, "relu": F.relu, "selu": F.selu, "leakyrelu": F.leaky_relu}[act]
+    xr, gr, br = x.clone().requires_grad_(True), gamma.clone().requires_grad_(True), beta.clone().requires_grad_(True)
+    rmr, rvr = rm.clone(), rv.clone()
+    yr = fn(F.batch_norm(xr, rmr, rvr, gr, br, training, 0.1, 1e-5))
+    gy = torch.randn(yr.shape, generator=g, dtype=torch.float64)
+    yr.backward(gy)
+    bn = BatchNorm2d(C).cuda()
+    with torch.no_grad():
+        bn.weight.copy_(gamma.float()); bn.bias.copy_(beta.float())
+        bn.running_mean.copy_(rm.float()); bn.running_var.copy_(rv.float())
+    bn.train(training)
+    xd = dev(x, True)
+    y = ops.bn_act(xd, bn, ops.ACT_IDS[act])
+    assert rel_err(y, yr) < TOL
+    y.backward(dev(gy))
+    assert rel_err(xd.grad, xr.grad) < GTOL
+    assert rel_err(bn.weight.grad, gr.grad) < GTOL
+    assert rel_err(bn.bias.grad, br.grad) < GTOL
+    assert rel_err(bn.running_mean, rmr) < TOL and rel_err(bn.running_var, rvr) < TOL
+    assert int(bn.num_batches_tracked) == (1 if training else 0)
+    # second call: the self-cleaning accumulators must be back to zero
+    y2 = ops.bn_act(dev(x), bn, ops.ACT_IDS[act])
+    assert rel_err(y2, yr) < (TOL if training else TOL)
+
+
+def test_plain_activation_and_gate(L):
+    from lvae_b200 import ops
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(3, 16, 5, 4, generator=g, dtype=torch.float64)
+    xr = x.clone().requires_grad_(True)
+    yr = F.elu(xr)
+    gy = torch.randn(yr.shape, generator=g, dtype=torch.float64)
+    yr.backward(gy)
+    xd = dev(x, True)
+    y = ops.bn_act(xd, None, 3)
+    y.backward(dev(gy))
+    assert rel_err(y, yr) < TOL and rel_err(xd.grad, xr.grad) < GTOL
+    h = torch.randn(3, 32, 5, 4, generator=g, dtype=torch.float64)
+    r = torch.randn(3, 16, 5, 4, generator=g, dtype=torch.float64)
+    hr, rr = h.clone().requires_grad_(True), r.clone().requires_grad_(True)
+    a, b = hr.chunk(2, 1)
+    outr = F.elu(a) * torch.sigmoid(b) + rr
+    outr.backward(gy)
+    hd, rd = dev(h, True), dev(r, True)
+    out = ops.gate(hd, rd, 3)
+    out.backward(dev(gy))
+    assert rel_err(out, outr) < TOL and rel_err(hd.grad, hr.grad) < GTOL and rel_err(rd.grad, rr.grad) < 1e-6
+
+
+def test_upsample_crop_pad(L):
+    from lvae_b200 import ops
+    g = torch.Generator().manual_seed(4)
+    x = torch.randn(2, 8, 5, 3, generator=g, dtype=torch.float64)
+    xr = x.clone().requires_grad_(True)
+    yr = F.interpolate(xr, scale_factor=2, mode="bilinear", align_corners=False)
+    gy = torch.randn(yr.shape, generator=g, dtype=torch.float64)
+    yr.backward(gy)
+    xd = dev(x, True)
+    y = ops.upsample2x(xd)
+    y.backward(dev(gy))
+    assert rel_err(y, yr) < TOL and rel_err(xd.grad, xr.grad) < GTOL
+    img = torch.rand(2, 3, 28, 26, generator=g)
+    p = ops.pad_image(img.cuda(), (32, 32))
+    assert rel_err(p, F.pad(img, [3, 3, 2, 2])) == 0
+    act = torch.randn(2, 8, 32, 32, generator=g, dtype=torch.float64)
+    ar = act.clone().requires_grad_(True)
+    cr = ar[:, :, 2:30, 3:29]
+    gc = torch.randn(cr.shape, generator=g, dtype=torch.float64)
+    cr.backward(gc)
+    ad = dev(act, True)
+    c = ops.crop(ad, (28, 26))
+    c.backward(dev(gc))
+    assert rel_err(c, cr) == 0 and rel_err(ad.grad, ar.grad) == 0
+
+
+@pytest.mark.parametrize("Z,hw,analytical,broadcast", [(32, (8, 8), False, False), (32, (2, 2), False, True),
+                                                       (32, (4, 4), True, False), (6, (3, 5), False, False),
+                                                       (8, (4, 4), False, True), (64, (4, 4), False, False)])
+def test_stochastic_core(L, Z, hw, analytical, broadcast):
+    from oracle import lvae_oracle as O
+    from lvae_b200 import ops
+    g = torch.Generator().manual_seed(Z + hw[0])
+    B = 5
+    q = torch.randn(B, 2 * Z, *hw, generator=g, dtype=torch.float64)
+    p = torch.randn(1 if broadcast else B, 2 * Z, *hw, generator=g, dtype=torch.float64)
+    eps = torch.randn(B, Z, *hw, generator=g, dtype=torch.float64)
+    qr, pr = q.clone().requires_grad_(True), p.clone().requires_grad_(True)
+    qm, ql = qr.chunk(2, 1)
+    pm, pl = pr.chunk(2, 1)
+    z = qm + (ql / 2).exp() * eps
+    logp = O.normal_log_prob(z, pm, pl).sum((1, 2, 3))
+    logq = O.normal_log_prob(z, qm, ql).sum((1, 2, 3))
+    kl_an = O.normal_kl(qm, ql, pm, pl)
+    kl = kl_an.sum((1, 2, 3)) if analytical else logq - logp
+    kls = kl_an.sum(1)
+    w = [torch.randn(t.shape, generator=g, dtype=torch.float64) for t in (z, kl, kls, logp, logq)]
+    (z * w[0]).sum().add((kl * w[1]).sum()).add((kls * w[2]).sum()).add((logp * w[3]).sum()).add((logq * w[4]).sum()).backward()
+    qd, pd = dev(q, True), dev(p, True)
+    zz, _, klo, klso, lpo, lqo = ops.stochastic_core(qd, pd, eps=dev(eps), analytical=analytical)
+    assert rel_err(zz, z) < TOL and rel_err(klo, kl) < TOL and rel_err(klso, kls) < TOL
+    assert rel_err(lpo, logp) < TOL and rel_err(lqo, logq) < TOL
+    ((zz * dev(w[0])).sum() + (klo * dev(w[1])).sum() + (klso * dev(w[2])).sum() + (lpo * dev(w[3])).sum()
+     + (lqo * dev(w[4])).sum()).backward()
+    assert rel_err(qd.grad, qr.grad) < GTOL
+    assert rel_err(pd.grad, pr.grad) < GTOL
+
+
+def test_stochastic_philox_statistics(L):
+    from lvae_b200 import ops
+    L.manual_seed(7)
+    q = torch.zeros(64, 64, 16, 16, device="cuda")
+    p = torch.zeros(64, 64, 16, 16, device="cuda")
+    z1 = ops.stochastic_core(q, p)[0]
+    z2 = ops.stochastic_core(q, p)[0]
+    assert abs(float(z1.mean())) < 5e-3 and abs(float(z1.std()) - 1) < 5e-3
+    assert float((z1 - z2).abs().max()) > 1          # fresh draws per call
+    k = float((z1 ** 4).mean())
+    assert abs(k - 3) < 0.1                           # normal kurtosis
+    L.manual_seed(7)
+    z3 = ops.stochastic_core(q, p)[0]
+    assert torch.equal(z1, z3)                        # reproducible from the seed
+
+
+def test_bernoulli(L):
+    from oracle import lvae_oracle as O
+    from lvae_b200 import ops
+    g = torch.Generator().manual_seed(5)
+    B, C, H, W = 4, 1, 28, 28
+    logits = torch.randn(B, C, H, W, generator=g, dtype=torch.float64) * 8
+    logits[0, 0, 0, :4] = torch.tensor([20.0, -20.0, 30.0, -120.0])          # saturation (SURVEY trap 2)
+    x = (torch.rand(B, C, H, W, generator=g) < 0.3).double()
+    lr = logits.float().requires_grad_(True)                                   # fp32: saturation is dtype-specific
+    llr = O.bernoulli_log_lik(x.float(), torch.sigmoid(lr))
+    gll = torch.randn(B, generator=g)
+    llr.backward(gll)
+    ld = dev(logits, True)
+    prob, ll = ops.bernoulli_loglik(ld, x.float().cuda())
+    assert rel_err(ll, llr) < TOL
+    assert rel_err(prob, torch.sigmoid(lr)) < TOL
+    ll.backward(gll.cuda())
+    assert rel_err(ld.grad, lr.grad) < GTOL
+    s = ops.bernoulli_sample(torch.full((8, 1, 64, 64), 0.3, device="cuda"))
+    assert abs(float(s.mean()) - 0.3) < 0.01
+    # 3 colour channels: NHWC params vs NCHW image indexing
+    logits3 = torch.randn(2, 3, 5, 4, generator=g, dtype=torch.float64)
+    x3 = (torch.rand(2, 3, 5, 4, generator=g) < 0.5).double()
+    ll3 = ops.bernoulli_loglik(dev(logits3), x3.float().cuda())[1]
+    assert rel_err(ll3, O.bernoulli_log_lik(x3, torch.sigmoid(logits3))) < TOL
+
+
+@pytest.mark.parametrize("H,W,B", [(32, 32, 3), (16, 16, 2), (5, 7, 2)])
+def test_dmol(L, H, W, B):
+    from oracle import lvae_oracle as O
+    from lvae_b200 import ops
+    g = torch.Generator().manual_seed(H)
+    l = torch.randn(B, 100, H, W, generator=g, dtype=torch.float64)
+    l[:, 20:30] -= 4            # some log-scales below the -7 clamp / narrow logistics
+    l[:, 50:60] *= 3
+    x = torch.randint(0, 256, (B, 3, H, W), generator=g).double() / 255
+    x[0, :, 0, 0] = 0.0
+    x[0, :, 0, 1] = 1.0
+    lr = l.clone().requires_grad_(True)
+    llr = O.dmol_log_lik(x, lr)
+    gll = torch.randn(B, generator=g, dtype=torch.float64)
+    llr.backward(gll)
+    ld = dev(l, True)
+    ll = ops.dmol_loglik(ld, x.float().cuda())
+    assert rel_err(ll, llr) < TOL
+    ll.backward(dev(gll))
+    assert rel_err(ld.grad, lr.grad) < GTOL
+    s = ops.dmol_sample(dev(l))
+    assert tuple(s.shape) == (B, 3, H, W) and float(s.min()) >= 0 and float(s.max()) <= 1
+
+
+def test_dmol_sampler_distribution(L):
+    from lvae_b200 import ops
+    # one dominant component with a tight scale: samples must concentrate at its mean
+    l = torch.zeros(4, 100, 8, 8)
+    l[:, 3] = 20.0
+    for c in range(3):
+        l[:, 10 + 30 * c + 3] = (-0.5, 0.0, 0.5)[c]
+        l[:, 10 + 30 * c + 10 + 3] = -6.0
+    s = ops.dmol_sample(l.cuda()) * 2 - 1
+    m = s.mean((0, 2, 3)).cpu()
+    assert torch.allclose(m, torch.tensor([-0.5, 0.0, 0.5]), atol=0.01)
+
+
+def test_adamax_l2_iw(L):
+    from oracle import lvae_oracle as O
+    from lvae_b200 import ops, _capi
+    g = torch.Generator().manual_seed(9)
+    n = 100003
+    p = torch.randn(n, generator=g, dtype=torch.float64)
+    pr = p.clone()
+    ea, ei = torch.zeros(n, dtype=torch.float64), torch.zeros(n, dtype=torch.float64)
+    pd = dev(p)
+    m, u = torch.zeros(n, device="cuda"), torch.zeros(n, device="cuda")
+    step = torch.zeros((), dtype=torch.int64, device="cuda")
+    s = torch.cuda.current_stream().cuda_stream
+    for t in range(1, 4):
+        gr = torch.randn(n, generator=g, dtype=torch.float64)
+        O.adamax_step(pr, gr, ea, ei, t)
+        gd = dev(gr)
+        _capi.call("lvae_adamax_step", pd.data_ptr(), gd.data_ptr(), m.data_ptr(), u.data_ptr(), n, 3e-4, 0.9, 0.999,
+                   1e-8, 0.0, step.data_ptr(), 1.0, s)
+    assert int(step) == 3
+    assert rel_err(pd, pr) < 1e-6
+    acc = torch.zeros((), dtype=torch.float64, device="cuda")
+    out = torch.zeros((), device="cuda")
+    _capi.call("lvae_l2_norm", pd.data_ptr(), n, acc.data_ptr(), out.data_ptr(), s)
+    assert rel_err(out, pr.pow(2).sum().sqrt()) < 1e-6 and float(acc) == 0.0
+    # IW bound: streaming logsumexp over K samples split over R "ranks"
+    B, K, R = 37, 12, 3
+    ll = torch.randn(K, B, generator=g, dtype=torch.float64) * 50 - 800
+    kl = torch.rand(K, B, generator=g, dtype=torch.float64) * 40
+    ref = O.iw_bound((ll - kl).t())
+    states = torch.zeros(R, B, 2, device="cuda")
+    for r in range(R):
+        for j, k in enumerate(range(r, K, R)):
+            ops.iw_lse_update(dev(ll[k]), dev(kl[k]), states[r], j == 0)
+    out = ops.iw_lse_combine(states, K)
+    assert rel_err(out, ref) < 1e-5
+
+
+def test_dropout_masks(L):
+    from lvae_b200 import ops
+    L.manual_seed(1)
+    ops.prepare_masks(10, 64, 64, 0.2, torch.device("cuda", 0))
+    m = [ops.next_mask(64, 64, 0.2, torch.device("cuda", 0)) for _ in range(10)]
+    ops.clear_masks()
+    allm = torch.stack(m)
+    vals = set(np.round(allm.unique().cpu().numpy(), 5).tolist())
+    assert vals == {0.0, 1.25}
+    assert abs(float((allm > 0).float().mean()) - 0.8) < 0.01
+    assert not torch.equal(m[0], m[1])
+
+
+def test_bad_arguments_raise(L):
+    from lvae_b200 import _capi
+    with pytest.raises(RuntimeError, match="bn_stats"):
+        _capi.call("lvae_bn_stats", None, None, 0, 64, 0, None)
+    with pytest.raises(RuntimeError, match="ldw"):
+        t = torch.zeros(16, device="cuda")
+        _capi.call("lvae_conv2d_gather", t.data_ptr(), None, t.data_ptr(), None, None, None, None, t.data_ptr(),
+                   1, 1, 1, 4, 0, 1, 1, 3, 3, 1, 1, 1, 0, 0, 0, None)

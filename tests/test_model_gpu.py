@@ -1,0 +1,137 @@
+"""GPU parity of the whole model: our LadderVAE against (a) the golden vectors written from the
+unmodified reference and (b) the CPU oracle run on the same weights / inputs / eps / dropout masks.
+Tolerances (north_star): per-layer KL, reconstruction ll and ELBO within 1e-4 relative in fp32,
+gradients within 1e-3 (relative to the largest gradient entry of the tensor group)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import lvae_oracle as O
+from lvae_test_helpers import load_golden, make_inputs, rel_err
+
+pytestmark = pytest.mark.gpu
+
+CASES = ["mnist3_train_b4", "mnist3_eval_b4", "small_dmol_train_b4", "small_dmol_eval_b4", "small_bern_bacdbac",
+         "small_bern_cabdcabd_linear", "small_dmol_nobn_selu", "mnist12_eval_b2", "mnist12_train_b2",
+         "cifar15_train_b2", "celeba20_train_b1"]
+
+
+def build(cfg, meta):
+    import lvae_b200
+    model = lvae_b200.LadderVAE(**cfg.kwargs())
+    model.load_state_dict(O.make_params(cfg, meta["weight_seed"]), strict=True)
+    return model.cuda().train(meta["training"])
+
+
+def run_ours(model, cfg, meta, k=0):
+    import lvae_b200
+    x, eps, masks = make_inputs(cfg, meta["batch"], meta["input_seed"], meta["training"], meta["n_iw"])
+    xs = x.float().cuda()
+    with lvae_b200.inject(eps=[e.float().cuda() for e in eps[k]],
+                          masks=[m.float().cuda() for m in masks] if masks else None):
+        out = model(xs)
+    return out
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_model_matches_golden(name):
+    cfg, meta, g = load_golden(name)
+    model = build(cfg, meta)
+    with torch.set_grad_enabled(meta["training"]):
+        out = run_ours(model, cfg, meta)
+        loss = (-out["ll"]).mean() + out["kl_loss"]
+    assert rel_err(out["ll"], g["f64_ll"]) < 1e-4
+    assert rel_err(out["kl_sep"], g["f64_kl_sep"]) < 1e-4
+    assert rel_err(out["kl_avg_layerwise"], g["f64_kl_avg_layerwise"]) < 1e-4
+    assert rel_err(out["kl_loss"], g["f64_kl_loss"]) < 1e-4
+    assert rel_err(out["kl"], g["f64_kl"]) < 1e-4
+    assert rel_err(loss, g["f64_loss"]) < 1e-4
+    assert rel_err(out["logp"], g["f64_logp"]) < 1e-4
+    assert rel_err([k.sum().item() for k in out["kl_spatial"]], g["f64_kl_spatial_sum"]) < 1e-4
+    assert rel_err([z.abs().sum().item() for z in out["z"]], g["f64_z_abs"]) < 1e-4
+    lp = out["likelihood_params"]
+    lp = lp["all_params"] if isinstance(lp, dict) else lp
+    assert rel_err(lp.abs().sum().item(), g["f64_lik_params_abs"]) < 1e-4
+    for i, z in enumerate(out["z"]):
+        assert tuple(z.shape) == tuple(O.latent_shapes(cfg, meta["batch"])[i])
+    if meta["training"]:
+        loss.backward()
+        names = [str(n) for n in g["f64_grad_names"]]
+        params = dict(model.named_parameters())
+        ours = np.array([float(params[n].grad.double().pow(2).sum().sqrt()) if params[n].grad is not None else 0.0
+                         for n in names])
+        ref = g["f64_grad_l2"]
+        assert np.abs(ours - ref).max() < 1e-3 * ref.max(), names[int(np.abs(ours - ref).argmax())]
+        osum = np.array([float(params[n].grad.double().sum()) if params[n].grad is not None else 0.0 for n in names])
+        assert np.abs(osum - g["f64_grad_sum"]).max() < 1e-3 * max(np.abs(g["f64_grad_sum"]).max(), ref.max())
+        sd = model.state_dict()
+        rn = [str(n) for n in g["f64_running_names"]]
+        if rn:
+            rs = np.array([float(sd[n].double().sum()) for n in rn])
+            assert np.abs(rs - g["f64_running_sum"]).max() < 1e-4 * np.abs(g["f64_running_sum"]).max()
+    if meta["n_iw"]:
+        from lvae_b200 import ops
+        state = torch.zeros(meta["batch"], 2, device="cuda")
+        with torch.no_grad():
+            for k in range(meta["n_iw"]):
+                o = run_ours(model, cfg, meta, k)
+                assert rel_err(o["ll"] - o["kl_sep"], g["f64_elbo_sep_samples"][:, k]) < 1e-4
+                ops.iw_lse_update(o["ll"], o["kl_sep"], state, k == 0)
+        iw = ops.iw_lse_combine(state[None], meta["n_iw"])
+        assert rel_err(iw, g["f64_iw_bound"]) < 1e-4
+
+
+@pytest.mark.parametrize("name", ["small_dmol_train_b4", "mnist3_train_b4"])
+def test_every_gradient_tensor_matches_oracle(name):
+    """Element-wise gradient check of every parameter against the float64 oracle."""
+    cfg, meta, g = load_golden(name)
+    model = build(cfg, meta)
+    out = run_ours(model, cfg, meta)
+    ((-out["ll"]).mean() + out["kl_loss"]).backward()
+    x, eps, masks = make_inputs(cfg, meta["batch"], meta["input_seed"], True)
+    st = O.TrainState(cfg, O.make_params(cfg, meta["weight_seed"], torch.float64))
+    o2, t2 = st.step(x, eps[0], masks, update=False)
+    gmax = max(float(st.P[n].grad.abs().max()) for n in st.names if st.P[n].grad is not None)
+    for n, p in model.named_parameters():
+        gr = st.P[n].grad
+        if gr is None:
+            continue
+        err = float((p.grad.double().cpu() - gr).abs().max())
+        assert err < 1e-3 * max(float(gr.abs().max()), 1e-3 * gmax), (n, err, float(gr.abs().max()))
+    for a, b in zip(out["z"], o2["z"]):
+        assert rel_err(a, b) < 1e-4
+    for a, b in zip(out["kl_spatial"], o2["kl_spatial"]):
+        assert rel_err(a, b) < 1e-4
+
+
+def test_hooked_path_matches_fused_path():
+    """A forward hook anywhere in a block (boilr data-dependent init) switches that block to the
+    module-by-module path; results must not change."""
+    cfg, meta, g = load_golden("small_dmol_eval_b4")
+    model = build(cfg, meta)
+    with torch.no_grad():
+        a = run_ours(model, cfg, meta)
+        calls = []
+        hs = [m.register_forward_hook(lambda mod, i, o: calls.append(1)) for m in model.modules()
+              if isinstance(m, torch.nn.Conv2d)]
+        b = run_ours(model, cfg, meta)
+        for h in hs:
+            h.remove()
+    assert len(calls) > 10
+    assert rel_err(b["ll"], a["ll"]) < 1e-5 and rel_err(b["kl_sep"], a["kl_sep"]) < 1e-5
+
+
+def test_sample_prior_and_modes():
+    cfg, meta, g = load_golden("small_dmol_eval_b4")
+    model = build(cfg, meta)
+    with torch.no_grad():
+        s = model.sample_prior(6)
+        assert tuple(s.shape) == (6, 3) + tuple(cfg.img_shape)
+        assert float(s.min()) >= 0 and float(s.max()) <= 1
+        s2 = model.sample_prior(4, mode_layers=[0, 1, 2])
+        s3 = model.sample_prior(4, constant_layers=[2])
+        assert tuple(s2.shape) == tuple(s3.shape) == (4, 3) + tuple(cfg.img_shape)
+    with pytest.raises(RuntimeError):
+        model.topdown_pass(bu_values=None, n_img_prior=None)
+    with pytest.raises(ValueError):
+        model.top_down_layers[-1](torch.zeros(1, 16, 2, 2, device="cuda"))
