@@ -1,0 +1,270 @@
+"""Step engines: the training step and the importance-weighted evaluation as replayable CUDA
+graphs over flat parameter / gradient arenas, data-parallel across one process per GPU.
+
+What the reference does per step in Python (experiment/experiment_manager.py:322-367 forward_pass,
+:78-80 Adamax over ~1700 tensors, :346-350 L2 loop, boilr's train loop) is here one captured
+graph: rng advance -> grad arena memset -> batched weight re-pack -> LadderVAE forward -> loss ->
+backward (kernels accumulate parameter gradients straight into the arena) -> [NCCL all-reduce of
+the arena in buckets, outside the graph] -> fused Adamax + L2 norm.
+"""
+from __future__ import annotations
+
+import math
+import os
+import struct
+from typing import Dict, List, Optional
+
+import torch
+import torch.distributed as dist
+
+from . import _capi, ops
+from .lib.nn import Conv2d, ConvTranspose2d
+
+call = _capi.call
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def shard_samples(k_total: int, rank: int, world: int):
+    """Contiguous split of K importance samples over ranks (first ranks take the remainder)."""
+    base, rem = divmod(k_total, world)
+    n = base + (1 if rank < rem else 0)
+    start = rank * base + min(rank, rem)
+    return start, n
+
+
+def bucket_ranges(numel: int, bucket_bytes: int = 25 << 20, elem_bytes: int = 4):
+    """[start, end) element ranges of the gradient arena, one NCCL call each."""
+    per = max(1, bucket_bytes // elem_bytes)
+    return [(s, min(numel, s + per)) for s in range(0, numel, per)]
+
+
+class ParamArena:
+    """All trainable parameters of a model as views into one flat fp32 buffer, with a parallel
+    gradient buffer that the wgrad / BatchNorm / prior kernels accumulate into directly."""
+
+    def __init__(self, model: torch.nn.Module):
+        params = [p for p in model.parameters() if p.requires_grad]
+        if not params:
+            raise RuntimeError("model has no trainable parameters")
+        dev = params[0].device
+        if dev.type != "cuda":
+            raise RuntimeError("lvae_b200 has no CPU path: move the model to a CUDA device first")
+        sizes = [((p.numel() + 3) // 4) * 4 for p in params]          # keep every view 16-byte aligned
+        self.numel = sum(sizes)
+        self.flat = torch.zeros(self.numel, dtype=torch.float32, device=dev)
+        self.grad = torch.zeros(self.numel, dtype=torch.float32, device=dev)
+        self.params, off = params, 0
+        for p, n in zip(params, sizes):
+            view = self.flat[off:off + p.numel()].view(p.shape)
+            view.copy_(p.data)
+            p.data = view
+            sink = self.grad[off:off + p.numel()].view(p.shape)
+            p._lvae_grad_sink = sink
+            p.grad = sink
+            off += n
+
+    def detach_sinks(self):
+        for p in self.params:
+            if hasattr(p, "_lvae_grad_sink"):
+                del p._lvae_grad_sink
+
+
+class PackTable:
+    """One device table of LvaePackDesc for every conv weight (both GEMM layouts): the whole
+    model is re-packed by ONE launch per step."""
+
+    def __init__(self, model: torch.nn.Module, dtype: torch.dtype):
+        self.entries = []
+        raws = []
+        for m in model.modules():
+            if isinstance(m, (Conv2d, ConvTranspose2d)):
+                for pack in (m.spec.pack_fwd, m.spec.pack_bwd):
+                    w = m.weight
+                    pack.buf = torch.empty((pack.rows, pack.ld), dtype=dtype, device=w.device)
+                    raw = struct.pack(ops._PACK_FMT, w.data_ptr(), pack.buf.data_ptr(), pack.O, pack.I, pack.taps,
+                                      pack.mode, pack.ld, 0 if dtype == torch.float32 else 1)
+                    pack.desc = torch.frombuffer(bytearray(raw), dtype=torch.uint8).to(w.device)
+                    pack.desc_src = w.data_ptr()
+                    raws.append(raw)
+                    self.entries.append((pack, w))
+        self.dtype = dtype
+        self.table = torch.frombuffer(bytearray(b"".join(raws)), dtype=torch.uint8).cuda()
+        self.n = len(raws)
+
+    def repack(self):
+        call("lvae_pack_weights", self.table.data_ptr(), self.n, _stream())
+        for pack, w in self.entries:
+            pack.mark_fresh(w, self.dtype)
+
+
+class TrainEngine:
+    """ELBO training step for a lvae_b200.LadderVAE on one GPU of a data-parallel job."""
+
+    def __init__(self, model, batch_size: int, lr: float = 3e-4, weight_decay: float = 0.0, betas=(0.9, 0.999),
+                 eps: float = 1e-8, beta_kl: float = 1.0, use_graph: bool = True, process_group=None,
+                 bucket_bytes: int = 25 << 20, compute_l2: bool = True):
+        _capi.device_check()
+        self.model = model.train()
+        self.batch_size = batch_size
+        self.lr, self.wd, self.betas, self.eps, self.beta_kl = lr, weight_decay, betas, eps, beta_kl
+        self.pg = process_group
+        self.world = dist.get_world_size(process_group) if (process_group is not None or dist.is_initialized()) else 1
+        self.arena = ParamArena(model)
+        dev = self.arena.flat.device
+        self.device = dev
+        self.exp_avg = torch.zeros_like(self.arena.flat)
+        self.exp_inf = torch.zeros_like(self.arena.flat)
+        self.step_count = torch.zeros((), dtype=torch.int64, device=dev)
+        self.l2_acc = torch.zeros((), dtype=torch.float64, device=dev)
+        self.l2 = torch.zeros((), dtype=torch.float32, device=dev)
+        self.compute_l2 = compute_l2
+        self.packs = PackTable(model, torch.float32)
+        self.buckets = bucket_ranges(self.arena.numel, bucket_bytes)
+        self.x = torch.zeros((batch_size, model.color_ch) + tuple(model.img_shape), dtype=torch.float32, device=dev)
+        self.use_graph = use_graph
+        self.graph_fb: Optional[torch.cuda.CUDAGraph] = None
+        self.graph_opt: Optional[torch.cuda.CUDAGraph] = None
+        self.out: Dict[str, torch.Tensor] = {}
+        self.launches_per_step = 0
+        if self.world > 1:                      # all replicas start from rank 0's weights
+            dist.broadcast(self.arena.flat, 0, group=self.pg)
+            for b in model.buffers():
+                dist.broadcast(b, 0, group=self.pg)
+
+    # -- pieces ---------------------------------------------------------------------------
+    def _forward_backward(self):
+        ops.rng_advance(self.device)
+        self.arena.grad.zero_()
+        self.packs.repack()
+        out = self.model(self.x)
+        recons = (-out["ll"]).mean()
+        loss = recons + out["kl_loss"] * self.beta_kl
+        loss.backward()
+        elbo = (out["ll"] - out["kl_sep"]).mean()
+        self.out = {"loss": loss.detach(), "elbo": elbo.detach(), "recons": recons.detach(), "kl": out["kl"].detach(),
+                    "kl_avg_layerwise": out["kl_avg_layerwise"].detach()}
+
+    def _all_reduce(self):
+        if self.world > 1:
+            for s, e in self.buckets:
+                dist.all_reduce(self.arena.grad[s:e], op=dist.ReduceOp.SUM, group=self.pg)
+
+    def _optimizer(self):
+        a = self.arena
+        call("lvae_adamax_step", a.flat.data_ptr(), a.grad.data_ptr(), self.exp_avg.data_ptr(), self.exp_inf.data_ptr(),
+             a.numel, self.lr, self.betas[0], self.betas[1], self.eps, self.wd, self.step_count.data_ptr(),
+             1.0 / self.world, _stream())
+        if self.compute_l2:
+            call("lvae_l2_norm", a.flat.data_ptr(), a.numel, self.l2_acc.data_ptr(), self.l2.data_ptr(), _stream())
+        self.out["l2"] = self.l2
+
+    def _eager_step(self):
+        self._forward_backward()
+        self._all_reduce()
+        self._optimizer()
+
+    def _capture(self):
+        # warm-up on a side stream (allocates pack buffers, BatchNorm scratch, cuBLAS-free)
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            for _ in range(2):
+                self._eager_step()
+        torch.cuda.current_stream().wait_stream(s)
+        torch.cuda.synchronize()
+        sid = ops._rng.stream_id
+        n0 = _capi.launch_count()
+        self.graph_fb = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph_fb):
+            self._forward_backward()
+        self.graph_opt = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph_opt, pool=self.graph_fb.pool()):
+            self._optimizer()
+        self.launches_per_step = _capi.launch_count() - n0
+        ops.set_stream_id(sid + 100000)
+
+    # -- public ---------------------------------------------------------------------------
+    def step(self, x: Optional[torch.Tensor] = None) -> Dict[str, torch.Tensor]:
+        """One optimisation step.  ``x``: (B,C,H,W) in [0,1], host (ideally pinned) or device;
+        None re-uses the resident batch.  Returns device scalars (no host sync)."""
+        if x is not None:
+            self.x.copy_(x, non_blocking=True)
+        if not self.use_graph:
+            n0 = _capi.launch_count()
+            self._eager_step()
+            self.launches_per_step = _capi.launch_count() - n0
+        else:
+            if self.graph_fb is None:
+                self._capture()
+            self.graph_fb.replay()
+            self._all_reduce()
+            self.graph_opt.replay()
+        ops.bump_pack_epoch()          # parameters changed behind torch's version counters
+        self.model.global_step = getattr(self.model, "global_step", 0) + 1
+        return self.out
+
+
+class IWEvaluator:
+    """Importance-weighted bound log p(x) >= logsumexp_k(ll_k - kl_k) - log K, with the
+    K samples sharded over ranks and one (B,2) all-gather + combine per image batch."""
+
+    def __init__(self, model, batch_size: int, use_graph: bool = True, process_group=None):
+        _capi.device_check()
+        self.model = model.eval()
+        self.pg = process_group
+        inited = process_group is not None or dist.is_initialized()
+        self.world = dist.get_world_size(process_group) if inited else 1
+        self.rank = dist.get_rank(process_group) if inited else 0
+        dev = next(model.parameters()).device
+        self.device = dev
+        self.x = torch.zeros((batch_size, model.color_ch) + tuple(model.img_shape), dtype=torch.float32, device=dev)
+        self.state = torch.zeros((batch_size, 2), dtype=torch.float32, device=dev)
+        self.use_graph = use_graph
+        self.graph = None
+        self.launches_per_sample = 0
+
+    def _one_sample(self):
+        ops.rng_advance(self.device)
+        out = self.model(self.x)
+        ops.iw_lse_update(out["ll"], out["kl_sep"], self.state, False)
+
+    def _reset(self):
+        self.state[:, 0].fill_(-math.inf)
+        self.state[:, 1].zero_()
+
+    def bound(self, x: torch.Tensor, k_total: int) -> torch.Tensor:
+        """Per-image IW bound (B,) for this image batch with k_total samples over all ranks."""
+        _, k_local = shard_samples(k_total, self.rank, self.world)
+        with torch.no_grad():
+            self.x.copy_(x, non_blocking=True)
+            self._reset()
+            if self.use_graph and self.graph is None:
+                s = torch.cuda.Stream()
+                s.wait_stream(torch.cuda.current_stream())
+                with torch.cuda.stream(s):
+                    self._one_sample()
+                torch.cuda.current_stream().wait_stream(s)
+                torch.cuda.synchronize()
+                self._reset()
+                n0 = _capi.launch_count()
+                self.graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(self.graph):
+                    self._one_sample()
+                self.launches_per_sample = _capi.launch_count() - n0
+                self._reset()
+            for _ in range(k_local):
+                if self.use_graph:
+                    self.graph.replay()
+                else:
+                    n0 = _capi.launch_count()
+                    self._one_sample()
+                    self.launches_per_sample = _capi.launch_count() - n0
+            if self.world > 1:
+                states = torch.empty((self.world,) + tuple(self.state.shape), dtype=torch.float32, device=self.device)
+                dist.all_gather_into_tensor(states, self.state, group=self.pg)
+            else:
+                states = self.state[None]
+            return ops.iw_lse_combine(states.contiguous(), k_total)

@@ -181,6 +181,14 @@ def _param_grad_buffer(param):
 
 # --------------------------------------------------------------------------- packed weights
 _PACK_FMT = "<QQiiiiii"   # must match LvaePackDesc in csrc/conv_generic.cu
+_pack_epoch = [0]         # bumped whenever weights were updated behind torch's version counters
+
+
+def bump_pack_epoch() -> None:
+    """Our fused optimizer writes parameters through raw pointers; this invalidates every
+    cached GEMM-layout copy so the next forward re-packs."""
+    _pack_epoch[0] += 1
+
 
 
 class WeightPack:
@@ -197,7 +205,7 @@ class WeightPack:
         self.key = None
 
     def get(self, weight: torch.Tensor, dtype: torch.dtype) -> torch.Tensor:
-        key = (weight.data_ptr(), weight._version, dtype, weight.device)
+        key = (weight.data_ptr(), weight._version, dtype, weight.device, _pack_epoch[0])
         if self.key == key:
             return self.buf
         if self.buf is None or self.buf.dtype != dtype or self.buf.device != weight.device or \
@@ -214,7 +222,7 @@ class WeightPack:
 
     def mark_fresh(self, weight, dtype):
         """The engine packed every weight in one batched launch; record that this one is current."""
-        self.key = (weight.data_ptr(), weight._version, dtype, weight.device)
+        self.key = (weight.data_ptr(), weight._version, dtype, weight.device, _pack_epoch[0])
 
 
 class ConvSpec:

@@ -515,9 +515,9 @@ def topdown_pass(r: _Run, bu_values=None, n_img_prior=None, mode_layers=(), cons
 # --------------------------------------------------------------------------- likelihoods
 def bernoulli_log_lik(x, prob):
     """log_bernoulli (likelihoods.py:385-388): -BCE on probabilities; BCE clamps each log at -100."""
-    lp = torch.clamp(torch.log(prob), min=-100.0)
-    l1p = torch.clamp(torch.log(1.0 - prob), min=-100.0)
-    return (x * lp + (1.0 - x) * l1p).sum((1, 2, 3))
+    # F.binary_cross_entropy is the very call the reference makes; its backward is the
+    # (p - x) / max(p (1 - p), 1e-12) form, finite even where p saturates to 0 or 1.
+    return -F.binary_cross_entropy(prob, x, reduction="none").sum((1, 2, 3))
 
 
 def dmol_log_lik(x01, l, nr_mix=10):
