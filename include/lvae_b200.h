@@ -49,6 +49,16 @@ int lvae_conv2d_gather(const void* x, const void* x2, const void* wp, const floa
 int lvae_conv2d_wgrad(const void* u, const void* u2, const void* dz, const float* in_scale, const float* out_scale,
                       float* dw, float* dbias, int B, int Hi, int Wi, int C1, int C2, int Ho, int Wo, int O, int kh,
                       int kw, int stride, int pad, int dtype, lvae_stream_t stream);
+/* bf16 tensor-core path (TMA -> tcgen05.mma -> TMEM) for the stride-1 "same" convs with 64 channels per
+ * input tensor: x, x2 (B,H,W,64) bf16; wp = lvae_pack_weights mode 2 (forward) / 3 (dgrad, flip = 1);
+ * y (B,H,W,N) bf16 or fp32 (out_f32); y2 != NULL splits the N output columns at nsplit (dgrad of the
+ * two-input merge conv).  H, W powers of two, W <= 128, N <= 256, ksize 1 or 3. */
+int lvae_conv2d_tc(const void* x, const void* x2, const void* wp, const float* bias, const float* out_scale,
+                   const void* res, void* y, void* y2, int nsplit, int B, int H, int W, int Cin, int N, int ksize,
+                   int flip, int out_f32, lvae_stream_t stream);
+/* y = x * scale[b,c] (Dropout2d mask on a gradient tensor ahead of the TMA-fed dgrad) */
+int lvae_channel_scale(const void* x, const float* scale, void* y, int B, int HW, int C, int dtype,
+                       lvae_stream_t stream);
 /* Re-layout torch (O,I,kh,kw) weights into GEMM rows; descs_dev = device array of n LvaePackDesc
  * {const float* src; void* dst; int O, I, taps, mode, ld, dtype} (see csrc/conv_generic.cu). */
 int lvae_pack_weights(const void* descs_dev, int n, lvae_stream_t stream);

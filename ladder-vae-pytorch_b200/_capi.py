@@ -21,6 +21,8 @@ _SIGNATURES = {
     "lvae_conv2d_gather": [P, P, P, P, P, P, P, P, I, I, I, I, I, I, I, I, I, I, I, I, I, I, I, P],
     "lvae_conv2d_wgrad": [P, P, P, P, P, P, P, I, I, I, I, I, I, I, I, I, I, I, I, I, P],
     "lvae_pack_weights": [P, I, P],
+    "lvae_conv2d_tc": [P, P, P, P, P, P, P, P, I, I, I, I, I, I, I, I, I, P],
+    "lvae_channel_scale": [P, P, P, I, I, I, I, P],
     "lvae_colsum": [P, P, P, I, I, I, I, P],
     "lvae_bn_stats": [P, P, L, I, I, P],
     "lvae_bn_finalize": [P, P, P, P, P, P, L, I, F, F, P],

@@ -428,6 +428,7 @@ LVAE_API int lvae_conv2d_wgrad(const void* u, const void* u2, const void* dz, co
 // Weight packing: torch (O,I,kh,kw) fp32 -> GEMM-ready [K][ld] rows (fp32 or bf16).
 //   mode 0: dst[(tap*I + i)*ld + o] = w[o][i][tap]   (conv forward / ConvTranspose dgrad)
 //   mode 1: dst[(tap*O + o)*ld + i] = w[o][i][tap]   (conv dgrad / ConvTranspose forward)
+//   mode 2/3: bf16 K-major operand tiles for the tcgen05 kernel (forward / dgrad), see below
 // ------------------------------------------------------------------------------------------
 struct LvaePackDesc {
   const float* src;
@@ -438,6 +439,27 @@ struct LvaePackDesc {
 __global__ void pack_weights_kernel(const LvaePackDesc* descs, int n) {
   for (int d = blockIdx.y; d < n; d += gridDim.y) {
     LvaePackDesc p = descs[d];
+    if (p.mode >= 2) {
+      // tcgen05 operand layout: [tap][k-block of 64][Npad rows][64] bf16, K-major rows of 128 bytes
+      //   mode 2 (forward):  row n = output channel o, k = input channel i   -> w[o][i][tap]
+      //   mode 3 (dgrad):    row n = input channel i,  k = output channel o  -> w[o][i][tap]
+      const int nreal = p.mode == 2 ? p.O : p.I, kreal = p.mode == 2 ? p.I : p.O;
+      const int KB = (kreal + 63) / 64, Npad = (nreal + 15) / 16 * 16;
+      const int total = p.taps * KB * Npad * 64;
+      for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+        int c = idx & 63, r = idx >> 6;
+        int nn = r % Npad, t2 = r / Npad;
+        int kb = t2 % KB, tap = t2 / KB;
+        int kk = kb * 64 + c;
+        float v = 0.f;
+        if (nn < nreal && kk < kreal) {
+          int o = p.mode == 2 ? nn : kk, i = p.mode == 2 ? kk : nn;
+          v = p.src[((long long)o * p.I + i) * p.taps + tap];
+        }
+        ((__nv_bfloat16*)p.dst)[idx] = __float2bfloat16(v);
+      }
+      continue;
+    }
     int rows = p.taps * (p.mode == 0 ? p.I : p.O);
     int total = rows * p.ld;
     for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {

@@ -1,0 +1,414 @@
+// bf16 implicit-GEMM convolution on the 5th-generation tensor cores (sm_100a only):
+// TMA (cp.async.bulk.tensor) -> 128B-swizzled shared memory -> tcgen05.mma with the fp32
+// accumulator in TMEM -> tcgen05.ld epilogue (bias, Dropout2d channel scale, residual).
+//
+// Covers the stride-1 "same" convolutions that carry ~97% of the model's FLOPs
+// (lib/nn.py:83-87 3x3 64->64, lib/nn.py:118 1x1 64->128 gate, models/lvae_layers.py:350 1x1
+// merge over two 64-channel inputs, lib/stochastic.py:25-26 3x3 64->64, lib/likelihoods.py:199
+// 3x3 64->100) and, with flipped taps and transposed weights, their data gradients.
+//
+// GEMM view: D[128 pixels, N] += A_tap[128 pixels, 64 ch] * W_tap[N, 64 ch]^T, one k-block of 64
+// channels per filter tap (or per input tensor for the merge).  A tile of 128 consecutive NHWC
+// pixels is ONE 4-D TMA box {64 ch, bw, bh, bn}; shifting the box origin by the tap offset
+// implements im2col, and TMA's out-of-bounds zero fill implements the zero padding (the batch is
+// its own tensor dimension, so a shifted box never bleeds into the neighbouring image).
+// All taps' weights stay resident in shared memory for the lifetime of a persistent CTA.
+//
+// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + single-thread MMA
+// issuer, warps 2..5 = epilogue (TMEM lane quadrant = warp_id % 4).  The accumulator is double
+// buffered in TMEM so the epilogue of tile i overlaps the MMAs of tile i+1.
+#include "common.cuh"
+#include <cuda.h>
+
+namespace {
+
+constexpr int TC_THREADS = 192;
+constexpr int TC_BM = 128;             // pixels per tile
+constexpr int TC_BK = 64;              // channels per k-block (= one 128-byte swizzle row of bf16)
+constexpr int TC_STAGE_BYTES = TC_BM * TC_BK * 2;   // 16 KB
+constexpr int TC_MAX_KB = 36;          // k-blocks per tile: taps x input k-blocks
+
+struct TcParams {
+  const float* bias;        // [N] or null
+  const float* out_scale;   // (B, N) or null
+  const void* res;          // residual (M, N) same dtype as y, or null
+  void* y;                  // (M, nsplit) when y2 != null else (M, N)
+  void* y2;                 // optional second output for columns >= nsplit: (M, N - nsplit)
+  int M_total, H, W, N, Npad, nsplit;
+  int n_kb;                 // number of k-blocks (taps * inputs)
+  int n_stages;
+  int bw, bh, bn;           // TMA box (pixels) : bw*bh*bn == 128
+  int out_f32;              // 1: y is fp32, 0: bf16
+  int tmem_cols;
+  int8_t dx[TC_MAX_KB], dy[TC_MAX_KB], src[TC_MAX_KB], coff[TC_MAX_KB];   // coff: channel offset / 64 inside the tensor
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+  return ok;
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  while (!mbar_try_wait(bar, parity)) {}
+}
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(dst), "l"(tm), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(tm), "r"(bar), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* tm) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(tm) : "memory");
+}
+// K-major, 128B-swizzled operand tile: rows of 128 B, 8-row groups 1024 B apart (SBO), version 1
+__device__ __forceinline__ uint64_t umma_desc_k_sw128(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);          // start address
+  d |= (uint64_t)1 << 16;                            // LBO (unused for swizzled K-major)
+  d |= (uint64_t)(1024 >> 4) << 32;                  // SBO
+  d |= (uint64_t)1 << 46;                            // descriptor version (Blackwell)
+  d |= (uint64_t)2 << 61;                            // SWIZZLE_128B
+  return d;
+}
+__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+__global__ void __launch_bounds__(TC_THREADS, 1)
+conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
+               const __grid_constant__ CUtensorMap tmW, const TcParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  // 1024-byte alignment for the 128B swizzle atoms
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  const int wbytes_kb = p.Npad * 128;                        // one k-block of weights
+  uint8_t* sW = smem;                                        // n_kb * Npad * 128
+  uint8_t* sA = sW + ((p.n_kb * wbytes_kb + 1023) & ~1023);  // n_stages * 16 KB
+  uint64_t* bars = (uint64_t*)(sA + p.n_stages * TC_STAGE_BYTES);
+  // barrier layout: [0..S) full, [S..2S) empty, 2S: weights, 2S+1..2S+2: tmem_full[2], 2S+3..2S+4: tmem_empty[2]
+  const int S = p.n_stages;
+  uint32_t* tmem_slot = (uint32_t*)(bars + 2 * S + 5);
+  const uint32_t bar0 = smem_u32(bars);
+  auto BAR = [&](int i) { return bar0 + 8u * (uint32_t)i; };
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_tiles = (p.M_total + TC_BM - 1) / TC_BM;
+
+  if (threadIdx.x == 0) {
+    prefetch_tmap(&tmA0);
+    prefetch_tmap(&tmA1);
+    prefetch_tmap(&tmW);
+    for (int i = 0; i < S; ++i) {
+      mbar_init(BAR(i), 1);
+      mbar_init(BAR(S + i), 1);
+    }
+    mbar_init(BAR(2 * S), 1);
+    mbar_init(BAR(2 * S + 1), 1);
+    mbar_init(BAR(2 * S + 2), 1);
+    mbar_init(BAR(2 * S + 3), 4);      // one arrive per epilogue warp
+    mbar_init(BAR(2 * S + 4), 4);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(p.tmem_cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      mbar_expect_tx(BAR(2 * S), (uint32_t)(p.n_kb * wbytes_kb));
+      for (int kb = 0; kb < p.n_kb; ++kb) tma_load_2d(smem_u32(sW + kb * wbytes_kb), &tmW, BAR(2 * S), 0, kb * p.Npad);
+      int stage = 0;
+      uint32_t phase = 0;
+      const int hw = p.H * p.W;
+      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        int p0 = tile * TC_BM;
+        int n0 = p0 / hw;
+        int rem = p0 - n0 * hw;
+        int h0 = rem / p.W;
+        int w0 = rem - h0 * p.W;
+        for (int kb = 0; kb < p.n_kb; ++kb) {
+          mbar_wait(BAR(S + stage), phase ^ 1);
+          mbar_expect_tx(BAR(stage), TC_STAGE_BYTES);
+          tma_load_4d(smem_u32(sA + stage * TC_STAGE_BYTES), p.src[kb] ? &tmA1 : &tmA0, BAR(stage), 64 * p.coff[kb],
+                      w0 + p.dx[kb], h0 + p.dy[kb], n0);
+          if (++stage == S) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      // instruction descriptor: D fp32, A/B bf16, both K-major, M = 128, N = Npad
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.Npad >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+      mbar_wait(BAR(2 * S), 0);
+      tc_fence_after();
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+        const int buf = it & 1;
+        const uint32_t use = (uint32_t)(it >> 1);
+        mbar_wait(BAR(2 * S + 3 + buf), (use & 1) ^ 1);      // epilogue drained this accumulator
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(buf * p.Npad);
+        for (int kb = 0; kb < p.n_kb; ++kb) {
+          mbar_wait(BAR(stage), phase);
+          tc_fence_after();
+          const uint64_t adesc = umma_desc_k_sw128(smem_u32(sA + stage * TC_STAGE_BYTES));
+          const uint64_t bdesc = umma_desc_k_sw128(smem_u32(sW + kb * wbytes_kb));
+#pragma unroll
+          for (int k = 0; k < TC_BK / 16; ++k) {
+            // advance 16 bf16 = 32 bytes along K inside the swizzle atom: +2 in the (addr >> 4) field
+            umma_bf16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (uint32_t)((kb | k) != 0));
+          }
+          umma_commit(BAR(S + stage));                         // frees the smem stage when these MMAs retire
+          if (++stage == S) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(BAR(2 * S + 1 + buf));                     // accumulator ready for the epilogue
+      }
+    }
+  } else {
+    // ===================== epilogue (4 warps) =====================
+    const int quad = warp & 3;                                 // TMEM lane quadrant this warp may read
+    const int row = quad * 32 + lane;
+    const int hw = p.H * p.W;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+      const int buf = it & 1;
+      const uint32_t use = (uint32_t)(it >> 1);
+      mbar_wait(BAR(2 * S + 1 + buf), use & 1);
+      tc_fence_after();
+      const long long m = (long long)tile * TC_BM + row;
+      const bool valid = m < p.M_total;
+      const int b = valid ? (int)(m / hw) : 0;
+      const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * p.Npad);
+      for (int c0 = 0; c0 < p.Npad; c0 += 16) {
+        float v[16];
+        tmem_ld16(taddr + (uint32_t)c0, v);                    // warp-collective: all lanes participate
+        if (!valid || c0 >= p.N) continue;
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          int n = c0 + j;
+          if (n < p.N) {
+            if (p.bias) v[j] += p.bias[n];
+            if (p.out_scale) v[j] *= p.out_scale[(long long)b * p.N + n];
+          }
+        }
+        // destination: y (columns < nsplit) or y2
+        const bool second = p.y2 != nullptr && c0 >= p.nsplit;
+        const int ncols = p.y2 ? (second ? p.N - p.nsplit : p.nsplit) : p.N;
+        const int cc = second ? c0 - p.nsplit : c0;
+        void* base = second ? p.y2 : p.y;
+        const long long off = m * ncols + cc;
+        const int nvalid = min(16, ncols - cc);
+        if (p.res && !p.y2) {
+          if (p.out_f32) {
+            const float* r = (const float*)p.res + off;
+            for (int j = 0; j < nvalid; ++j) v[j] += r[j];
+          } else {
+            const __nv_bfloat16* r = (const __nv_bfloat16*)p.res + off;
+            if (nvalid == 16) {
+              uint4 r0 = *reinterpret_cast<const uint4*>(r), r1 = *reinterpret_cast<const uint4*>(r + 8);
+              const __nv_bfloat162* h0 = reinterpret_cast<const __nv_bfloat162*>(&r0);
+              const __nv_bfloat162* h1 = reinterpret_cast<const __nv_bfloat162*>(&r1);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                float2 f0 = __bfloat1622float2(h0[j]), f1 = __bfloat1622float2(h1[j]);
+                v[2 * j] += f0.x; v[2 * j + 1] += f0.y; v[8 + 2 * j] += f1.x; v[8 + 2 * j + 1] += f1.y;
+              }
+            } else {
+              for (int j = 0; j < nvalid; ++j) v[j] += __bfloat162float(r[j]);
+            }
+          }
+        }
+        if (p.out_f32) {
+          float* o = (float*)base + off;
+          if (nvalid == 16 && (ncols & 3) == 0) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) reinterpret_cast<float4*>(o)[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+          } else {
+            for (int j = 0; j < nvalid; ++j) o[j] = v[j];
+          }
+        } else {
+          __nv_bfloat16* o = (__nv_bfloat16*)base + off;
+          if (nvalid == 16 && (ncols & 7) == 0) {
+            uint4 w0, w1;
+            __nv_bfloat162* h0 = reinterpret_cast<__nv_bfloat162*>(&w0);
+            __nv_bfloat162* h1 = reinterpret_cast<__nv_bfloat162*>(&w1);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              h0[j] = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
+              h1[j] = __floats2bfloat162_rn(v[8 + 2 * j], v[8 + 2 * j + 1]);
+            }
+            reinterpret_cast<uint4*>(o)[0] = w0;
+            reinterpret_cast<uint4*>(o)[1] = w1;
+          } else {
+            for (int j = 0; j < nvalid; ++j) o[j] = __float2bfloat16(v[j]);
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(BAR(2 * S + 3 + buf));
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(p.tmem_cols) : "memory");
+  }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)ptr;
+  }
+  return fn;
+}
+
+int pow2_floor_le(int v, int cap) {
+  int r = 1;
+  while (r * 2 <= v && r * 2 <= cap) r *= 2;
+  return r;
+}
+
+}  // namespace
+
+// x, x2: (B,H,W,Cin) bf16 NHWC, Cin a multiple of 64 (x2 optional: second input of a merge conv).
+// wp: bf16 [n_kb][Npad][64] (k-block = tap-major, then input): see lvae_pack_weights modes 2/3.
+// taps: ksize*ksize offsets; flip = 1 negates them (data gradient).  y: (B,H,W,N) bf16 or fp32;
+// y2 != NULL splits the output columns at nsplit into two tensors (dgrad of a merge conv).
+LVAE_API int lvae_conv2d_tc(const void* x, const void* x2, const void* wp, const float* bias, const float* out_scale,
+                            const void* res, void* y, void* y2, int nsplit, int B, int H, int W, int Cin, int N,
+                            int ksize, int flip, int out_f32, cudaStream_t stream) {
+  LVAE_REQUIRE(x && wp && y, "conv2d_tc: null pointer");
+  LVAE_REQUIRE(Cin % 64 == 0 && Cin >= 64 && Cin <= 256 && (ksize == 1 || ksize == 3),
+               "conv2d_tc: needs a multiple of 64 input channels per tensor and a 1x1 or 3x3 kernel");
+  LVAE_REQUIRE(N >= 1 && N <= 256, "conv2d_tc: 1 <= N <= 256");
+  LVAE_REQUIRE((W & (W - 1)) == 0 && (H & (H - 1)) == 0 && W <= 128, "conv2d_tc: H and W must be powers of two (W <= 128)");
+  LVAE_REQUIRE(!(y2 && res), "conv2d_tc: residual and split output are exclusive");
+  LVAE_REQUIRE(!y2 || (nsplit % 16 == 0 && nsplit > 0 && nsplit < N), "conv2d_tc: nsplit must be a multiple of 16 inside (0, N)");
+  EncodeTiledFn enc = get_encode();
+  if (!enc) {
+    lvae_set_error("conv2d_tc: cuTensorMapEncodeTiled unavailable");
+    return LVAE_ERR_CUDA;
+  }
+  TcParams p{};
+  p.bias = bias; p.out_scale = out_scale; p.res = res; p.y = y; p.y2 = y2; p.nsplit = nsplit;
+  p.M_total = B * H * W; p.H = H; p.W = W; p.N = N; p.Npad = (N + 15) / 16 * 16;
+  p.out_f32 = out_f32;
+  const int inputs = x2 ? 2 : 1;
+  const int taps = ksize * ksize;
+  const int cblocks = Cin / 64;
+  p.n_kb = taps * inputs * cblocks;
+  LVAE_REQUIRE(p.n_kb <= TC_MAX_KB, "conv2d_tc: too many k-blocks");
+  int kb = 0;
+  for (int t = 0; t < taps; ++t) {
+    int ky = t / ksize, kx = t % ksize;
+    int oy = ky - ksize / 2, ox = kx - ksize / 2;
+    if (flip) { oy = -oy; ox = -ox; }
+    for (int s = 0; s < inputs; ++s)
+      for (int c = 0; c < cblocks; ++c, ++kb) {
+        p.dy[kb] = (int8_t)oy; p.dx[kb] = (int8_t)ox; p.src[kb] = (int8_t)s; p.coff[kb] = (int8_t)c;
+      }
+  }
+  p.bw = W;                                  // full image rows (W <= 128)
+  p.bh = pow2_floor_le(H, TC_BM / p.bw);
+  p.bn = TC_BM / (p.bw * p.bh);
+  p.tmem_cols = 32;
+  while (p.tmem_cols < 2 * p.Npad) p.tmem_cols *= 2;
+  LVAE_REQUIRE(p.tmem_cols <= 512, "conv2d_tc: accumulator does not fit TMEM");
+  const int wbytes = ((p.n_kb * p.Npad * 128) + 1023) & ~1023;
+  const int max_smem = 227 * 1024 - 1024 /*align*/ - 512 /*barriers*/;
+  int stages = (max_smem - wbytes) / TC_STAGE_BYTES;
+  if (stages > 8) stages = 8;
+  LVAE_REQUIRE(stages >= 2, "conv2d_tc: weights leave no room for the activation pipeline");
+  p.n_stages = stages;
+  const size_t smem = 1024 + (size_t)wbytes + (size_t)stages * TC_STAGE_BYTES + 512;
+
+  CUtensorMap tmA0, tmA1, tmW;
+  {
+    cuuint64_t gdim[4] = {(cuuint64_t)Cin, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+    cuuint64_t gstr[3] = {(cuuint64_t)Cin * 2, (cuuint64_t)W * Cin * 2, (cuuint64_t)H * W * Cin * 2};
+    cuuint32_t box[4] = {64, (cuuint32_t)p.bw, (cuuint32_t)p.bh, (cuuint32_t)p.bn};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = enc(&tmA0, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, (void*)x, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { lvae_set_error("conv2d_tc: tensor map (x) encode failed: %d", (int)r); return LVAE_ERR_CUDA; }
+    r = enc(&tmA1, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, (void*)(x2 ? x2 : x), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { lvae_set_error("conv2d_tc: tensor map (x2) encode failed: %d", (int)r); return LVAE_ERR_CUDA; }
+    cuuint64_t wdim[2] = {64, (cuuint64_t)p.n_kb * p.Npad};
+    cuuint64_t wstr[1] = {128};
+    cuuint32_t wbox[2] = {64, (cuuint32_t)p.Npad};
+    cuuint32_t westr[2] = {1, 1};
+    r = enc(&tmW, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (void*)wp, wdim, wstr, wbox, westr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { lvae_set_error("conv2d_tc: tensor map (w) encode failed: %d", (int)r); return LVAE_ERR_CUDA; }
+  }
+  static size_t attr_smem = 0;
+  if (smem > attr_smem) {
+    cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024));
+    if (e != cudaSuccess) { lvae_set_error("conv2d_tc: cannot raise dynamic smem: %s", cudaGetErrorString(e)); return LVAE_ERR_CUDA; }
+    attr_smem = 227 * 1024;
+  }
+  const int n_tiles = (p.M_total + TC_BM - 1) / TC_BM;
+  const int grid = n_tiles < lvae_num_sms() ? n_tiles : lvae_num_sms();
+  conv_tc_kernel<<<grid, TC_THREADS, smem, stream>>>(tmA0, tmA1, tmW, p);
+  LVAE_COUNT_LAUNCH();
+  LVAE_CHECK_LAUNCH("conv2d_tc");
+  return LVAE_OK;
+}

@@ -538,3 +538,30 @@ LVAE_API int lvae_sum_batch(const float* x, float* out, int B, long long n, int 
   LVAE_CHECK_LAUNCH("sum_batch");
   return LVAE_OK;
 }
+
+// y[b,hw,c] = x[b,hw,c] * scale[b,c]   (Dropout2d mask applied to a gradient before the bf16 tensor-core dgrad,
+// whose TMA-fed operands never pass through registers)
+template <typename T>
+__global__ void channel_scale_kernel(const T* __restrict__ x, const float* __restrict__ scale, T* __restrict__ y,
+                                     long long nquads, int hw, int C) {
+  const int CV = C >> 2;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nquads; i += (long long)gridDim.x * blockDim.x) {
+    long long row = i / CV;
+    int c = (int)(i - row * CV) * 4;
+    long long b = row / hw;
+    float4 v = ld4<T>(x + i * 4);
+    float4 s = *reinterpret_cast<const float4*>(scale + b * C + c);
+    st4<T>(y + i * 4, make_float4(v.x * s.x, v.y * s.y, v.z * s.z, v.w * s.w));
+  }
+}
+
+LVAE_API int lvae_channel_scale(const void* x, const float* scale, void* y, int B, int HW, int C, int dtype_in,
+                                cudaStream_t stream) {
+  LVAE_REQUIRE(x && scale && y && C % 4 == 0, "channel_scale: bad args");
+  long long nq = (long long)B * HW * (C / 4);
+  if (dtype_in == 0) channel_scale_kernel<float><<<ew_grid(nq, 256), 256, 0, stream>>>((const float*)x, scale, (float*)y, nq, HW, C);
+  else channel_scale_kernel<__nv_bfloat16><<<ew_grid(nq, 256), 256, 0, stream>>>((const __nv_bfloat16*)x, scale, (__nv_bfloat16*)y, nq, HW, C);
+  LVAE_COUNT_LAUNCH();
+  LVAE_CHECK_LAUNCH("channel_scale");
+  return LVAE_OK;
+}

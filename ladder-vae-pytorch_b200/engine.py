@@ -81,15 +81,9 @@ class PackTable:
         raws = []
         for m in model.modules():
             if isinstance(m, (Conv2d, ConvTranspose2d)):
-                for pack in (m.spec.pack_fwd, m.spec.pack_bwd):
-                    w = m.weight
-                    pack.buf = torch.empty((pack.rows, pack.ld), dtype=dtype, device=w.device)
-                    raw = struct.pack(ops._PACK_FMT, w.data_ptr(), pack.buf.data_ptr(), pack.O, pack.I, pack.taps,
-                                      pack.mode, pack.ld, 0 if dtype == torch.float32 else 1)
-                    pack.desc = torch.frombuffer(bytearray(raw), dtype=torch.uint8).to(w.device)
-                    pack.desc_src = w.data_ptr()
-                    raws.append(raw)
-                    self.entries.append((pack, w))
+                for pack in m.spec.packs(dtype == torch.bfloat16):
+                    raws.append(pack.alloc(m.weight, dtype))
+                    self.entries.append((pack, m.weight))
         self.dtype = dtype
         self.table = torch.frombuffer(bytearray(b"".join(raws)), dtype=torch.uint8).cuda()
         self.n = len(raws)

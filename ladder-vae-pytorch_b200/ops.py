@@ -193,36 +193,67 @@ def bump_pack_epoch() -> None:
 
 class WeightPack:
     """GEMM-ready copy of one conv weight (see lvae_pack_weights).  Re-packed when the
-    parameter's version counter or storage changes (i.e. after every optimizer step)."""
+    parameter's version counter or storage changes (i.e. after every optimizer step).
+    modes 0/1: [K][ld] rows for the CUDA-core kernel; modes 2/3: bf16 K-major operand tiles
+    [tap][k-block][Npad][64] for the tcgen05 kernel (forward / dgrad)."""
 
     def __init__(self, O: int, I: int, taps: int, mode: int):
         self.O, self.I, self.taps, self.mode = O, I, taps, mode
-        n = O if mode == 0 else I
-        self.ld = (n + 3) // 4 * 4
-        self.rows = taps * (I if mode == 0 else O)
+        if mode >= 2:
+            nreal, kreal = (O, I) if mode == 2 else (I, O)
+            self.ld = 64
+            self.rows = taps * ((kreal + 63) // 64) * ((nreal + 15) // 16 * 16)
+        else:
+            n = O if mode == 0 else I
+            self.ld = (n + 3) // 4 * 4
+            self.rows = taps * (I if mode == 0 else O)
         self.buf = None
         self.desc = None
+        self.desc_src = None
         self.key = None
 
+    def alloc(self, weight: torch.Tensor, dtype: torch.dtype) -> bytes:
+        """(Re)allocate the packed buffer and return the raw LvaePackDesc for it."""
+        if self.mode >= 2:
+            dtype = torch.bfloat16
+        self.buf = torch.empty((self.rows, self.ld), dtype=dtype, device=weight.device)
+        raw = struct.pack(_PACK_FMT, weight.data_ptr(), self.buf.data_ptr(), self.O, self.I, self.taps,
+                          self.mode, self.ld, 0 if dtype == torch.float32 else 1)
+        assert len(raw) == _capi.lib().lvae_pack_desc_size()
+        self.desc = torch.frombuffer(bytearray(raw), dtype=torch.uint8).to(weight.device)
+        self.desc_src = weight.data_ptr()
+        return raw
+
     def get(self, weight: torch.Tensor, dtype: torch.dtype) -> torch.Tensor:
+        if self.mode >= 2:
+            dtype = torch.bfloat16
         key = (weight.data_ptr(), weight._version, dtype, weight.device, _pack_epoch[0])
         if self.key == key:
             return self.buf
         if self.buf is None or self.buf.dtype != dtype or self.buf.device != weight.device or \
                 self.desc_src != weight.data_ptr():
-            self.buf = torch.empty((self.rows, self.ld), dtype=dtype, device=weight.device)
-            raw = struct.pack(_PACK_FMT, weight.data_ptr(), self.buf.data_ptr(), self.O, self.I, self.taps,
-                              self.mode, self.ld, 0 if dtype == torch.float32 else 1)
-            assert len(raw) == _capi.lib().lvae_pack_desc_size()
-            self.desc = torch.frombuffer(bytearray(raw), dtype=torch.uint8).to(weight.device)
-            self.desc_src = weight.data_ptr()
+            self.alloc(weight, dtype)
         call("lvae_pack_weights", self.desc.data_ptr(), 1, _stream())
         self.key = key
         return self.buf
 
     def mark_fresh(self, weight, dtype):
         """The engine packed every weight in one batched launch; record that this one is current."""
+        if self.mode >= 2:
+            dtype = torch.bfloat16
         self.key = (weight.data_ptr(), weight._version, dtype, weight.device, _pack_epoch[0])
+
+
+_tc_enabled = [True]
+
+
+def set_tensor_cores(flag: bool) -> None:
+    """Route eligible bf16 convolutions to the tcgen05 kernel (default) or keep them on the CUDA-core one."""
+    _tc_enabled[0] = bool(flag)
+
+
+def _pow2(v: int) -> bool:
+    return v > 0 and (v & (v - 1)) == 0
 
 
 class ConvSpec:
@@ -231,6 +262,7 @@ class ConvSpec:
     def __init__(self, cout, cin, k, stride, pad, transposed=False, output_padding=0):
         self.cout, self.cin, self.k, self.stride, self.pad = cout, cin, k, stride, pad
         self.transposed, self.output_padding = transposed, output_padding
+        self.out_fp32 = False         # bf16 pipeline: keep this conv's output in fp32 (stochastic / likelihood inputs)
         taps = k * k
         if not transposed:            # weight (Cout, Cin, k, k)
             self.pack_fwd = WeightPack(cout, cin, taps, 0)    # rows (tap, ci) -> cols co
@@ -238,12 +270,51 @@ class ConvSpec:
         else:                         # weight (Cin, Cout, k, k): O' = Cin, I' = Cout
             self.pack_fwd = WeightPack(cin, cout, taps, 1)    # rows (tap, ci) -> cols co
             self.pack_bwd = WeightPack(cin, cout, taps, 0)    # rows (tap, co) -> cols ci
+        self.tc_shape = (not transposed) and stride == 1 and k in (1, 3) and pad == k // 2
+        self.pack_tc_fwd = WeightPack(cout, cin, taps, 2) if self.tc_shape else None
+        self.pack_tc_bwd = WeightPack(cout, cin, taps, 3) if self.tc_shape else None
+
+    def packs(self, bf16: bool):
+        out = [self.pack_fwd, self.pack_bwd]
+        if bf16 and self.tc_shape:
+            out += [self.pack_tc_fwd, self.pack_tc_bwd]
+        return out
 
     def out_hw(self, h, w):
         if not self.transposed:
             return ((h + 2 * self.pad - self.k) // self.stride + 1, (w + 2 * self.pad - self.k) // self.stride + 1)
         return ((h - 1) * self.stride - 2 * self.pad + self.k + self.output_padding,
                 (w - 1) * self.stride - 2 * self.pad + self.k + self.output_padding)
+
+    def tc_forward_ok(self, xn, x2n) -> bool:
+        if not (_tc_enabled[0] and self.tc_shape and xn.dtype == torch.bfloat16 and self.cout <= 256):
+            return False
+        B, H, W, C = xn.shape
+        if not (_pow2(H) and _pow2(W) and W <= 128):
+            return False
+        if x2n is None:
+            return C % 64 == 0 and C <= 256
+        return C == 64 and x2n.shape[3] == 64
+
+    def tc_dgrad_ok(self, gyn) -> bool:
+        if not (_tc_enabled[0] and self.tc_shape and self.cin <= 256):
+            return False
+        B, H, W, N = gyn.shape
+        return _pow2(H) and _pow2(W) and W <= 128 and N % 64 == 0 and N <= 256
+
+
+def _conv_tc(x, x2, wp, bias, out_scale, res, N, ksize, flip, out_f32, nsplit=0):
+    """Launch the tcgen05 kernel.  Returns y, or (y, y2) when nsplit splits the output columns."""
+    B, H, W, C = x.shape
+    odt = torch.float32 if out_f32 else torch.bfloat16
+    if nsplit:
+        y = torch.empty((B, H, W, nsplit), dtype=odt, device=x.device)
+        y2 = torch.empty((B, H, W, N - nsplit), dtype=odt, device=x.device)
+    else:
+        y, y2 = torch.empty((B, H, W, N), dtype=odt, device=x.device), None
+    call("lvae_conv2d_tc", x.data_ptr(), _p(x2), wp.data_ptr(), _p(bias), _p(out_scale), _p(res), y.data_ptr(), _p(y2),
+         nsplit, B, H, W, C, N, ksize, 1 if flip else 0, 1 if out_f32 else 0, _stream())
+    return (y, y2) if nsplit else y
 
 
 def _gather(x, x2, wp, ld, bias, in_scale, out_scale, res, B, Hi, Wi, C1, C2, Ho, Wo, N, k, stride, pad, mode, out_dtype):
@@ -254,7 +325,9 @@ def _gather(x, x2, wp, ld, bias, in_scale, out_scale, res, B, Hi, Wi, C1, C2, Ho
 
 
 class Conv2dFn(Function):
-    """y = (conv(cat(x, x2)) + bias) * out_scale[b, c] + res   (Conv2d or ConvTranspose2d)."""
+    """y = (conv(cat(x, x2)) + bias) * out_scale[b, c] + res   (Conv2d or ConvTranspose2d).
+    bf16 activations on eligible shapes run on the tensor cores (lvae_conv2d_tc), everything
+    else on the CUDA-core implicit GEMM (lvae_conv2d_gather)."""
 
     @staticmethod
     def forward(ctx, x, x2, weight, bias, out_scale, res, spec: ConvSpec):
@@ -266,11 +339,20 @@ class Conv2dFn(Function):
         C2 = x2n.shape[3] if x2n is not None else 0
         assert C1 + C2 == spec.cin, "conv input channels %d+%d != %d" % (C1, C2, spec.cin)
         Ho, Wo = spec.out_hw(Hi, Wi)
-        wp = spec.pack_fwd.get(weight, xn.dtype)
         if out_scale is not None:
             out_scale = out_scale.reshape(B, spec.cout)
-        y = _gather(xn, x2n, wp, spec.pack_fwd.ld, bias, None, out_scale, resn, B, Hi, Wi, C1, C2, Ho, Wo,
-                    spec.cout, spec.k, spec.stride, spec.pad, 1 if spec.transposed else 0, xn.dtype)
+        want_f32 = spec.out_fp32 and xn.dtype == torch.bfloat16
+        if spec.tc_forward_ok(xn, x2n) and (resn is None or resn.dtype == (torch.float32 if want_f32 else torch.bfloat16)):
+            wp = spec.pack_tc_fwd.get(weight, torch.bfloat16)
+            y = _conv_tc(xn, x2n, wp, bias, out_scale, resn, spec.cout, spec.k, False, want_f32)
+        else:
+            wp = spec.pack_fwd.get(weight, xn.dtype)
+            if resn is not None and resn.dtype != xn.dtype:
+                resn = resn.to(xn.dtype)
+            y = _gather(xn, x2n, wp, spec.pack_fwd.ld, bias, None, out_scale, resn, B, Hi, Wi, C1, C2, Ho, Wo,
+                        spec.cout, spec.k, spec.stride, spec.pad, 1 if spec.transposed else 0, xn.dtype)
+            if want_f32:
+                y = y.float()
         ctx.spec = spec
         ctx.save_for_backward(xn, x2n, weight, bias, out_scale)
         ctx.has_res = res is not None
@@ -281,20 +363,36 @@ class Conv2dFn(Function):
         spec = ctx.spec
         xn, x2n, weight, bias, out_scale = ctx.saved_tensors
         gyn = nhwc(gy)
+        if gyn.dtype != xn.dtype:
+            gyn = gyn.to(xn.dtype)
         B, Hi, Wi, C1 = xn.shape
         C2 = x2n.shape[3] if x2n is not None else 0
         _, Ho, Wo, N = gyn.shape
         gx = gx2 = gw = gb = None
         need_x = ctx.needs_input_grad[0] or (x2n is not None and ctx.needs_input_grad[1])
+        use_tc = xn.dtype == torch.bfloat16 and spec.tc_dgrad_ok(gyn)
+        if use_tc and out_scale is not None:
+            # TMA-fed operands never pass through registers: apply the Dropout2d mask in a separate pass
+            gys = torch.empty_like(gyn)
+            call("lvae_channel_scale", gyn.data_ptr(), out_scale.data_ptr(), gys.data_ptr(), B, Ho * Wo, N, _dt(gyn), _stream())
+            gyn, out_scale = gys, None
         if need_x:
-            wpb = spec.pack_bwd.get(weight, gyn.dtype)
-            gcat = _gather(gyn, None, wpb, spec.pack_bwd.ld, None, out_scale, None, None, B, Ho, Wo, N, 0, Hi, Wi,
-                           spec.cin, spec.k, spec.stride, spec.pad, 0 if spec.transposed else 1, gyn.dtype)
-            if x2n is None:
-                gx = as_nchw(gcat)
+            if use_tc:
+                wpb = spec.pack_tc_bwd.get(weight, torch.bfloat16)
+                if x2n is None:
+                    gx = as_nchw(_conv_tc(gyn, None, wpb, None, None, None, spec.cin, spec.k, True, False))
+                else:
+                    g1, g2 = _conv_tc(gyn, None, wpb, None, None, None, spec.cin, spec.k, True, False, nsplit=C1)
+                    gx, gx2 = as_nchw(g1), as_nchw(g2)
             else:
-                gx = as_nchw(gcat[..., :C1])
-                gx2 = as_nchw(gcat[..., C1:])
+                wpb = spec.pack_bwd.get(weight, gyn.dtype)
+                gcat = _gather(gyn, None, wpb, spec.pack_bwd.ld, None, out_scale, None, None, B, Ho, Wo, N, 0, Hi, Wi,
+                               spec.cin, spec.k, spec.stride, spec.pad, 0 if spec.transposed else 1, gyn.dtype)
+                if x2n is None:
+                    gx = as_nchw(gcat)
+                else:
+                    gx = as_nchw(gcat[..., :C1])
+                    gx2 = as_nchw(gcat[..., C1:])
         if ctx.needs_input_grad[2]:
             gwbuf, sunk = _param_grad_buffer(weight)
             gbbuf, bsunk = (None, True)
@@ -313,11 +411,8 @@ class Conv2dFn(Function):
                     call("lvae_colsum", gyn.data_ptr(), _p(out_scale), gbbuf.data_ptr(), B, Ho * Wo, N, _dt(gyn), _stream())
             gw = None if sunk else gwbuf
             gb = None if (bsunk or gbbuf is None) else gbbuf
-        gos = None
-        if out_scale is not None and ctx.needs_input_grad[4]:
-            raise RuntimeError("gradient wrt the dropout mask is not supported")
         gres = gy if ctx.has_res and ctx.needs_input_grad[5] else None
-        return gx, gx2, gw, gb, gos, gres, None
+        return gx, gx2, gw, gb, None, gres, None
 
 
 def conv2d(x, weight, bias, spec: ConvSpec, x2=None, out_scale=None, res=None):

@@ -1,0 +1,103 @@
+"""GPU parity of the tcgen05 / TMA / TMEM convolution kernel against a float64 convolution of the
+same bf16-rounded operands.  With fp32 output the only error left is fp32 accumulation order
+(tolerance 2e-5 relative); with bf16 output add one bf16 rounding (4e-3)."""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+from lvae_test_helpers import rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+def phys_nhwc(t):
+    return t.permute(0, 2, 3, 1).contiguous().permute(0, 3, 1, 2)
+
+
+CASES = [
+    # cin, cout, k, H, W, B, cin2, out_fp32
+    (64, 64, 3, 16, 16, 2, 0, True),
+    (64, 64, 3, 16, 16, 2, 0, False),
+    (64, 64, 3, 32, 32, 3, 0, True),
+    (64, 64, 3, 8, 8, 5, 0, True),
+    (64, 64, 3, 4, 4, 3, 0, True),       # 48 pixels: partial tile, batch dimension out of bounds in the box
+    (64, 64, 3, 2, 2, 40, 0, True),      # 160 pixels: two tiles, second partial
+    (64, 64, 3, 64, 64, 1, 0, True),
+    (64, 128, 1, 16, 16, 2, 0, True),    # gate conv
+    (64, 64, 1, 8, 8, 4, 64, True),      # merge conv over two inputs
+    (64, 100, 3, 32, 32, 2, 0, True),    # DMoL head (N padded to 112)
+    (64, 32, 3, 8, 8, 4, 0, True),
+    (128, 64, 3, 8, 8, 4, 0, True),      # two k-blocks from one tensor
+]
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_tc_conv_forward_backward(case):
+    import lvae_b200
+    from lvae_b200.lib.nn import Conv2d
+    from lvae_b200 import ops
+    cin, cout, k, H, W, B, cin2, out_fp32 = case
+    g = torch.Generator().manual_seed(sum(case))
+    bf = lambda t: t.to(torch.bfloat16)
+    x = bf(torch.randn(B, cin, H, W, generator=g))
+    x2 = bf(torch.randn(B, cin2, H, W, generator=g)) if cin2 else None
+    mod = Conv2d(cin + cin2, cout, k, padding=k // 2).cuda()
+    mod.spec.out_fp32 = out_fp32
+    w = bf(torch.randn(mod.weight.shape, generator=g) / math.sqrt((cin + cin2) * k * k))
+    b = torch.randn(cout, generator=g)
+    scale = ((torch.rand(B, cout, generator=g) > 0.3).float() / 0.7)
+    with torch.no_grad():
+        mod.weight.copy_(w.float())
+        mod.bias.copy_(b)
+    # float64 reference on the same bf16-rounded operands
+    xr = x.double().requires_grad_(True)
+    x2r = x2.double().requires_grad_(True) if cin2 else None
+    wr, br = w.double().requires_grad_(True), b.double().requires_grad_(True)
+    inp = torch.cat([xr, x2r], 1) if cin2 else xr
+    yr = F.conv2d(inp, wr, br, padding=k // 2) * scale.double().view(B, cout, 1, 1)
+    use_res = cout == 64 and not out_fp32
+    res = bf(torch.randn(B, cout, H, W, generator=g)) if use_res else None
+    if use_res:
+        yr = yr + res.double()
+    gy = bf(torch.randn(yr.shape, generator=g))
+    yr.backward(gy.double())
+
+    xd = phys_nhwc(x.cuda()).requires_grad_(True)
+    x2d = phys_nhwc(x2.cuda()).requires_grad_(True) if cin2 else None
+    kw = dict(out_scale=scale.cuda())
+    if cin2:
+        kw["x2"] = x2d
+    if use_res:
+        kw["res"] = phys_nhwc(res.cuda())
+    n0 = lvae_b200._capi.launch_count()
+    y = mod(xd, **kw)
+    assert y.dtype == (torch.float32 if out_fp32 else torch.bfloat16)
+    assert rel_err(y.float(), yr) < (2e-5 if out_fp32 else 6e-3)
+    y.backward(gy.cuda().to(y.dtype))
+    torch.cuda.synchronize()
+    # dgrad output is bf16: one rounding
+    assert rel_err(xd.grad.float(), xr.grad) < 6e-3
+    if cin2:
+        assert rel_err(x2d.grad.float(), x2r.grad) < 6e-3
+    # the Dropout2d-masked gradient is re-rounded to bf16 ahead of the TMA-fed dgrad / wgrad
+    assert rel_err(mod.weight.grad, wr.grad) < 5e-3
+    assert rel_err(mod.bias.grad, br.grad) < 5e-3
+
+
+def test_tc_path_is_taken_and_matches_cuda_core_path():
+    import lvae_b200
+    from lvae_b200.lib.nn import Conv2d
+    from lvae_b200 import ops
+    g = torch.Generator().manual_seed(0)
+    mod = Conv2d(64, 64, 3, padding=1).cuda()
+    x = phys_nhwc(torch.randn(4, 64, 16, 16, generator=g).to(torch.bfloat16).cuda())
+    y_tc = mod(x)
+    ops.set_tensor_cores(False)
+    try:
+        y_cc = mod(x)
+    finally:
+        ops.set_tensor_cores(True)
+    assert rel_err(y_tc.float(), y_cc.float()) < 1e-2
+    assert not torch.equal(y_tc, torch.zeros_like(y_tc))
