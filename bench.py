@@ -165,26 +165,39 @@ def run_reference(args, rank):
     print(json.dumps(line), flush=True)
 
 
-def conv_roofline(torch, pk, dtype_flag=0):
+def conv_roofline(torch, pk, dtype="bf16"):
     """Dominant kernel: 3x3 64->64 stride-1 conv (335 of 538 forward convs) at the most
     common CIFAR-15 shape (B=256, 16x16).  Timed alone with CUDA events on the launch stream over
     rotating buffers larger than L2."""
-    from lvae_b200 import _capi
+    from lvae_b200 import _capi, ops
     B, H, W, C, k = 256, 16, 16, 64, 3
-    nbuf = 6                                         # 6 x (16.8 + 16.8) MB > 126 MB L2
-    xs = [torch.randn(B, H, W, C, device="cuda") for _ in range(nbuf)]
-    ys = [torch.empty(B, H, W, C, device="cuda") for _ in range(nbuf)]
-    wp = torch.randn(k * k * C, C, device="cuda")
+    tdt = torch.bfloat16 if dtype == "bf16" else torch.float32
+    nbuf = 12 if dtype == "bf16" else 6             # (in + out) x nbuf > 126 MB L2
+    xs = [torch.randn(B, H, W, C, device="cuda").to(tdt) for _ in range(nbuf)]
+    ys = [torch.empty(B, H, W, C, device="cuda", dtype=tdt) for _ in range(nbuf)]
     bias = torch.zeros(C, device="cuda")
     s = torch.cuda.current_stream().cuda_stream
+    w = torch.randn(C, C, k, k, device="cuda") / 24.0
+    if dtype == "bf16":
+        pack = ops.WeightPack(C, C, k * k, 2)
+        wp = pack.get(w, torch.bfloat16)
+        name = "conv_tc_kernel 3x3 64->64 B=256 16x16 (TMA + tcgen05.mma + TMEM, bf16 in / fp32 accumulate)"
 
-    def launch(i):
-        _capi.call("lvae_conv2d_gather", xs[i % nbuf].data_ptr(), None, wp.data_ptr(), bias.data_ptr(), None, None, None,
-                   ys[i % nbuf].data_ptr(), B, H, W, C, 0, H, W, C, C, k, k, 1, 1, 0, dtype_flag, s)
+        def launch(i):
+            _capi.call("lvae_conv2d_tc", xs[i % nbuf].data_ptr(), None, wp.data_ptr(), bias.data_ptr(), None, None,
+                       ys[i % nbuf].data_ptr(), None, 0, B, H, W, C, C, k, 0, 0, s)
+    else:
+        pack = ops.WeightPack(C, C, k * k, 0)
+        wp = pack.get(w, torch.float32)
+        name = "conv_gather_kernel<float> 3x3 64->64 B=256 16x16 (fp32 CUDA-core implicit GEMM)"
+
+        def launch(i):
+            _capi.call("lvae_conv2d_gather", xs[i % nbuf].data_ptr(), None, wp.data_ptr(), bias.data_ptr(), None, None, None,
+                       ys[i % nbuf].data_ptr(), B, H, W, C, 0, H, W, C, C, k, k, 1, 1, 0, 0, s)
     for i in range(5):
         launch(i)
     torch.cuda.synchronize()
-    n = 30
+    n = 48
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for i in range(n):
@@ -194,9 +207,10 @@ def conv_roofline(torch, pk, dtype_flag=0):
     us = e0.elapsed_time(e1) * 1e3 / n
     flops = 2.0 * B * H * W * C * C * k * k
     achieved = flops / (us * 1e-6) / 1e12
-    return {"bound": "tensor", "kernel": "conv_gather_kernel<float> 3x3 64->64 B=256 16x16 (fp32 CUDA-core implicit GEMM)",
-            "achieved": achieved, "peak": pk["tf_burst"], "unit": "TFLOP/s", "frac": achieved / pk["tf_burst"],
-            "traffic": None, "us_per_launch": us, "flops_per_launch": flops,
+    bytes_alg = 2.0 * B * H * W * C * (2 if dtype == "bf16" else 4)
+    return {"bound": "tensor", "kernel": name, "achieved": achieved, "peak": pk["tf_burst"], "unit": "TFLOP/s",
+            "frac": achieved / pk["tf_burst"], "traffic": None, "us_per_launch": us, "flops_per_launch": flops,
+            "algorithmic_bytes_per_launch": bytes_alg, "hbm_gbs_at_this_rate": bytes_alg / (us * 1e-6) / 1e9,
             "peak_source": "%s bf16 burst (kernel timed alone)" % pk["src"]}
 
 
@@ -209,6 +223,8 @@ def main():
     ap.add_argument("--workload", default="train", choices=sorted(CONFIGS))
     ap.add_argument("--batch", type=int, default=0, help="per-GPU batch (default: the BASELINE config's)")
     ap.add_argument("--iw-samples", type=int, default=1000)
+    ap.add_argument("--dtype", default="bf16", choices=["bf16", "f32"],
+                    help="bf16: bf16 activations, tcgen05 convs, fp32 accumulation (default); f32: exact fp32 CUDA-core path")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
@@ -240,6 +256,8 @@ def main():
     torch.manual_seed(42)
     lvae_b200.manual_seed(1234 + rank)
     model = lvae_b200.LadderVAE(**cfg.kwargs()).cuda()
+    if args.dtype == "bf16":
+        model.set_compute_dtype(torch.bfloat16)
     x_host = synthetic_batch(cfg, batch, rank).pin_memory()
 
     def barrier():
@@ -286,7 +304,7 @@ def main():
         launches = ev.launches_per_sample * k_local * args.steps
         line = {"metric": "IW-%d evals/s (MNIST 12-layer LVAE)" % K, "value": value, "unit": "images/s with a %d-sample bound" % K,
                 "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
-                "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "scaling": "strong", "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
                 "config": {"workload": "importance-weighted bound, K=%d samples sharded over %d GPU(s), test batch %d, "
                                        "binarized-MNIST-shaped 12-layer LVAE, eval mode" % (K, world, batch),
                            "l2_policy": "per-sample working set exceeds L2"},
@@ -336,7 +354,7 @@ def main():
     gflop = CONV_GFLOP[cfg_name][1]
     line = {"metric": "train images/s (%s LVAE)" % {"cifar15": "CIFAR10 15-layer"}.get(cfg_name, cfg_name),
             "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": args.dtype,
             "data": "synthetic",
             "config": {"workload": "ELBO training step (zero grad, forward, loss, backward, gradient all-reduce, Adamax), "
                                    "%s, 10-component DMoL, dropout 0.2, train-mode BatchNorm" % cfg_name,
@@ -352,7 +370,7 @@ def main():
             "whole_step_frac_of_bf16_sustained": value / world * gflop / 1e3 / pk["tf_sustained"],
             "peak_mem_gb": mem_gb, "loss": final_loss}
     if rank == 0:
-        line["roofline"] = conv_roofline(torch, pk)
+        line["roofline"] = conv_roofline(torch, pk, args.dtype)
         if not args.no_cpu_baseline:
             cb = cpu_baseline_train(cfg_name, 16, 2)
             line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}

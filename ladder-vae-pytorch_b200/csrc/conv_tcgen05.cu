@@ -114,6 +114,92 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
   for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+__device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+      "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// Epilogue for 16 accumulator columns [c0, c0+16) of one output row: bias (shared memory), Dropout2d scale,
+// residual, conversion, vectorised store.  All global reads go through the read-only path so that the
+// compiler can batch them instead of ordering them against the stores.
+template <bool OUT_F32>
+__device__ __forceinline__ void epilogue16(const uint32_t* __restrict__ r, const float* __restrict__ sbias,
+                                           const float* __restrict__ scale_row, const void* __restrict__ res_row,
+                                           void* __restrict__ out_row, int c0, int cc, int nvalid, int ncols, int N) {
+  float v[16];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]) + sbias[c0 + j];
+  if (scale_row) {
+    if (c0 + 16 <= N && (N & 3) == 0) {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        float4 s4 = __ldg(reinterpret_cast<const float4*>(scale_row + c0) + q);
+        v[4 * q] *= s4.x; v[4 * q + 1] *= s4.y; v[4 * q + 2] *= s4.z; v[4 * q + 3] *= s4.w;
+      }
+    } else {
+      for (int j = 0; j < 16 && c0 + j < N; ++j) v[j] *= __ldg(scale_row + c0 + j);
+    }
+  }
+  if (OUT_F32) {
+    float* o = (float*)out_row + cc;
+    const float* rr = res_row ? (const float*)res_row + cc : nullptr;
+    if (nvalid == 16 && (ncols & 3) == 0) {
+      if (rr) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          float4 t = __ldg(reinterpret_cast<const float4*>(rr) + q);
+          v[4 * q] += t.x; v[4 * q + 1] += t.y; v[4 * q + 2] += t.z; v[4 * q + 3] += t.w;
+        }
+      }
+#pragma unroll
+      for (int q = 0; q < 4; ++q) reinterpret_cast<float4*>(o)[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+    } else {
+      for (int j = 0; j < nvalid; ++j) o[j] = v[j] + (rr ? __ldg(rr + j) : 0.f);
+    }
+  } else {
+    __nv_bfloat16* o = (__nv_bfloat16*)out_row + cc;
+    const __nv_bfloat16* rr = res_row ? (const __nv_bfloat16*)res_row + cc : nullptr;
+    if (nvalid == 16 && (ncols & 7) == 0) {
+      if (rr) {
+        uint4 r0 = __ldg(reinterpret_cast<const uint4*>(rr)), r1 = __ldg(reinterpret_cast<const uint4*>(rr) + 1);
+        const __nv_bfloat162* h0 = reinterpret_cast<const __nv_bfloat162*>(&r0);
+        const __nv_bfloat162* h1 = reinterpret_cast<const __nv_bfloat162*>(&r1);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          float2 f0 = __bfloat1622float2(h0[j]), f1 = __bfloat1622float2(h1[j]);
+          v[2 * j] += f0.x; v[2 * j + 1] += f0.y; v[8 + 2 * j] += f1.x; v[8 + 2 * j + 1] += f1.y;
+        }
+      }
+      uint4 w0, w1;
+      __nv_bfloat162* g0 = reinterpret_cast<__nv_bfloat162*>(&w0);
+      __nv_bfloat162* g1 = reinterpret_cast<__nv_bfloat162*>(&w1);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        g0[j] = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
+        g1[j] = __floats2bfloat162_rn(v[8 + 2 * j], v[8 + 2 * j + 1]);
+      }
+      reinterpret_cast<uint4*>(o)[0] = w0;
+      reinterpret_cast<uint4*>(o)[1] = w1;
+    } else {
+      for (int j = 0; j < nvalid; ++j) o[j] = __float2bfloat16(v[j] + (rr ? __bfloat162float(rr[j]) : 0.f));
+    }
+  }
+}
+
 __global__ void __launch_bounds__(TC_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                const __grid_constant__ CUtensorMap tmW, const TcParams p) {
@@ -127,6 +213,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
   // barrier layout: [0..S) full, [S..2S) empty, 2S: weights, 2S+1..2S+2: tmem_full[2], 2S+3..2S+4: tmem_empty[2]
   const int S = p.n_stages;
   uint32_t* tmem_slot = (uint32_t*)(bars + 2 * S + 5);
+  float* sbias = (float*)(bars + 32);                         // Npad floats (<= 256), zero beyond N / when bias == null
   const uint32_t bar0 = smem_u32(bars);
   auto BAR = [&](int i) { return bar0 + 8u * (uint32_t)i; };
 
@@ -148,6 +235,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     mbar_init(BAR(2 * S + 4), 4);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
+  for (int i = threadIdx.x; i < p.Npad; i += TC_THREADS) sbias[i] = (p.bias && i < p.N) ? p.bias[i] : 0.f;
   if (warp == 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(p.tmem_cols) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -227,69 +315,28 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
       const bool valid = m < p.M_total;
       const int b = valid ? (int)(m / hw) : 0;
       const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * p.Npad);
-      for (int c0 = 0; c0 < p.Npad; c0 += 16) {
-        float v[16];
-        tmem_ld16(taddr + (uint32_t)c0, v);                    // warp-collective: all lanes participate
-        if (!valid || c0 >= p.N) continue;
+      const float* scale_row = p.out_scale ? p.out_scale + (long long)b * p.N : nullptr;
+      for (int c0 = 0; c0 < p.Npad; c0 += 32) {
+        uint32_t r[32];
+        const bool two = c0 + 32 <= p.Npad;
+        if (two) tmem_ld32_nowait(taddr + (uint32_t)c0, r);      // warp-collective: all lanes participate
+        else tmem_ld16_nowait(taddr + (uint32_t)c0, r);
+        tmem_wait_ld();
+        if (!valid) continue;
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          int n = c0 + j;
-          if (n < p.N) {
-            if (p.bias) v[j] += p.bias[n];
-            if (p.out_scale) v[j] *= p.out_scale[(long long)b * p.N + n];
-          }
-        }
-        // destination: y (columns < nsplit) or y2
-        const bool second = p.y2 != nullptr && c0 >= p.nsplit;
-        const int ncols = p.y2 ? (second ? p.N - p.nsplit : p.nsplit) : p.N;
-        const int cc = second ? c0 - p.nsplit : c0;
-        void* base = second ? p.y2 : p.y;
-        const long long off = m * ncols + cc;
-        const int nvalid = min(16, ncols - cc);
-        if (p.res && !p.y2) {
-          if (p.out_f32) {
-            const float* r = (const float*)p.res + off;
-            for (int j = 0; j < nvalid; ++j) v[j] += r[j];
-          } else {
-            const __nv_bfloat16* r = (const __nv_bfloat16*)p.res + off;
-            if (nvalid == 16) {
-              uint4 r0 = *reinterpret_cast<const uint4*>(r), r1 = *reinterpret_cast<const uint4*>(r + 8);
-              const __nv_bfloat162* h0 = reinterpret_cast<const __nv_bfloat162*>(&r0);
-              const __nv_bfloat162* h1 = reinterpret_cast<const __nv_bfloat162*>(&r1);
-#pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                float2 f0 = __bfloat1622float2(h0[j]), f1 = __bfloat1622float2(h1[j]);
-                v[2 * j] += f0.x; v[2 * j + 1] += f0.y; v[8 + 2 * j] += f1.x; v[8 + 2 * j + 1] += f1.y;
-              }
-            } else {
-              for (int j = 0; j < nvalid; ++j) v[j] += __bfloat162float(r[j]);
-            }
-          }
-        }
-        if (p.out_f32) {
-          float* o = (float*)base + off;
-          if (nvalid == 16 && (ncols & 3) == 0) {
-#pragma unroll
-            for (int j = 0; j < 4; ++j) reinterpret_cast<float4*>(o)[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-          } else {
-            for (int j = 0; j < nvalid; ++j) o[j] = v[j];
-          }
-        } else {
-          __nv_bfloat16* o = (__nv_bfloat16*)base + off;
-          if (nvalid == 16 && (ncols & 7) == 0) {
-            uint4 w0, w1;
-            __nv_bfloat162* h0 = reinterpret_cast<__nv_bfloat162*>(&w0);
-            __nv_bfloat162* h1 = reinterpret_cast<__nv_bfloat162*>(&w1);
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              h0[j] = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
-              h1[j] = __floats2bfloat162_rn(v[8 + 2 * j], v[8 + 2 * j + 1]);
-            }
-            reinterpret_cast<uint4*>(o)[0] = w0;
-            reinterpret_cast<uint4*>(o)[1] = w1;
-          } else {
-            for (int j = 0; j < nvalid; ++j) o[j] = __float2bfloat16(v[j]);
-          }
+        for (int h = 0; h < 2; ++h) {
+          const int c = c0 + 16 * h;
+          if ((h == 1 && !two) || c >= p.N) break;
+          const bool second = p.y2 != nullptr && c >= p.nsplit;
+          const int ncols = p.y2 ? (second ? p.N - p.nsplit : p.nsplit) : p.N;
+          const int cc = second ? c - p.nsplit : c;
+          char* base = (char*)(second ? p.y2 : p.y);
+          const int esz = p.out_f32 ? 4 : 2;
+          void* out_row = base + (size_t)m * ncols * esz;
+          const void* res_row = (p.res && !p.y2) ? (const char*)p.res + (size_t)m * ncols * esz : nullptr;
+          const int nvalid = min(16, ncols - cc);
+          if (p.out_f32) epilogue16<true>(r + 16 * h, sbias, scale_row, res_row, out_row, c, cc, nvalid, ncols, p.N);
+          else epilogue16<false>(r + 16 * h, sbias, scale_row, res_row, out_row, c, cc, nvalid, ncols, p.N);
         }
       }
       tc_fence_before();
@@ -372,12 +419,12 @@ LVAE_API int lvae_conv2d_tc(const void* x, const void* x2, const void* wp, const
   while (p.tmem_cols < 2 * p.Npad) p.tmem_cols *= 2;
   LVAE_REQUIRE(p.tmem_cols <= 512, "conv2d_tc: accumulator does not fit TMEM");
   const int wbytes = ((p.n_kb * p.Npad * 128) + 1023) & ~1023;
-  const int max_smem = 227 * 1024 - 1024 /*align*/ - 512 /*barriers*/;
+  const int max_smem = 227 * 1024 - 1024 /*align*/ - 2048 /*barriers + bias*/;
   int stages = (max_smem - wbytes) / TC_STAGE_BYTES;
   if (stages > 8) stages = 8;
   LVAE_REQUIRE(stages >= 2, "conv2d_tc: weights leave no room for the activation pipeline");
   p.n_stages = stages;
-  const size_t smem = 1024 + (size_t)wbytes + (size_t)stages * TC_STAGE_BYTES + 512;
+  const size_t smem = 1024 + (size_t)wbytes + (size_t)stages * TC_STAGE_BYTES + 2048;
 
   CUtensorMap tmA0, tmA1, tmW;
   {

@@ -115,7 +115,7 @@ class TrainEngine:
         self.l2_acc = torch.zeros((), dtype=torch.float64, device=dev)
         self.l2 = torch.zeros((), dtype=torch.float32, device=dev)
         self.compute_l2 = compute_l2
-        self.packs = PackTable(model, torch.float32)
+        self.packs = PackTable(model, getattr(model, "compute_dtype", torch.float32))
         self.buckets = bucket_ranges(self.arena.numel, bucket_bytes)
         self.x = torch.zeros((batch_size, model.color_ch) + tuple(model.img_shape), dtype=torch.float32, device=dev)
         self.use_graph = use_graph

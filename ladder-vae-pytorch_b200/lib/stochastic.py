@@ -40,16 +40,18 @@ class NormalStochasticBlock2d(nn.Module):
         eps = None
         if forced_latent is None and not use_mode:
             eps = ops.pop_eps()      # only set by parity tests (ops.inject)
-        z, _, kl_samplewise, kl_spatial, logprob_p, logprob_q = ops.stochastic_core(
-            q_params, p_params, eps=eps, forced=forced_latent, use_mode=use_mode, analytical=analytical_kl)
+        lowp = self.conv_out.weight.is_cuda and getattr(self, "compute_dtype", torch.float32) == torch.bfloat16
+        z, z_lp, kl_samplewise, kl_spatial, logprob_p, logprob_q = ops.stochastic_core(
+            q_params, p_params, eps=eps, forced=forced_latent, use_mode=use_mode, analytical=analytical_kl,
+            lowp_copy=lowp)
         if force_constant_output:
             # prior experiment (lib/stochastic.py:71-73): one sample shared by the whole batch;
             # log p(z) is still evaluated under each row's own p
             z = z[0:1].expand_as(z).contiguous()
             p_shared = p_params[0:1].expand_as(p_params).contiguous()
-            z, _, _, _, logprob_p, _ = ops.stochastic_core(None, p_params, forced=z)
+            z, z_lp, _, _, logprob_p, _ = ops.stochastic_core(None, p_params, forced=z, lowp_copy=lowp)
             p_params = p_shared
-        out = self.conv_out(z)
+        out = self.conv_out(z_lp if z_lp is not None else z)
         data = {
             "z": z,
             "p_params": p_params,

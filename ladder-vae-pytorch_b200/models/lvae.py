@@ -84,6 +84,24 @@ class LadderVAE(BaseGenerativeModel):
             raise RuntimeError("Unrecognized likelihood '{}'".format(likelihood_form))
 
         self._n_dropout_sites = sum(1 for m in self.modules() if isinstance(m, Dropout2d))
+        self.compute_dtype = torch.float32
+
+    def set_compute_dtype(self, dtype):
+        """torch.float32: exact-fp32 CUDA-core convolutions (parity mode).  torch.bfloat16: activations
+        are stored in bf16 and the 64-channel convolutions run on the tensor cores with fp32
+        accumulation; the stochastic-block parameters and the likelihood parameters stay fp32."""
+        if dtype not in (torch.float32, torch.bfloat16):
+            raise ValueError("compute dtype must be torch.float32 or torch.bfloat16")
+        self.compute_dtype = dtype
+        from lvae_b200.lib.stochastic import NormalStochasticBlock2d
+        for m in self.modules():
+            if isinstance(m, NormalStochasticBlock2d):
+                m.compute_dtype = dtype
+                m.conv_in_q.spec.out_fp32 = True
+                if m.transform_p_params:
+                    m.conv_in_p.spec.out_fp32 = True
+        self.likelihood.parameter_net.spec.out_fp32 = True
+        return self
 
     # ------------------------------------------------------------------ forward pieces
     def _begin(self, batch, device):
@@ -160,7 +178,7 @@ class LadderVAE(BaseGenerativeModel):
     def pad_input(self, x):
         """Zero-pad (centred) to the next multiple of the overall downscale factor and hand the
         image to the kernels as an NHWC activation."""
-        return ops.pad_image(x, self.get_padded_size(x.size()))
+        return ops.pad_image(x, self.get_padded_size(x.size()), out_dtype=self.compute_dtype)
 
     def get_padded_size(self, size):
         dwnsc = self.overall_downscale_factor

@@ -622,7 +622,6 @@ class StochasticFn(Function):
         ctx.p_dtype = p_params.dtype
         zo = as_nchw(z)
         zlo = as_nchw(z_lp) if z_lp is not None else None
-        ctx.mark_non_differentiable(*([zlo] if zlo is not None else []))
         return zo, zlo, kl, kls, logp, logq
 
     @staticmethod
@@ -632,6 +631,9 @@ class StochasticFn(Function):
             raise RuntimeError("backward through prior sampling is not supported")
         B, hw, Z, p_broadcast, analytical, z_kind = ctx.meta
         gz = nhwc(g_z).float() if g_z is not None else None
+        if g_zlp is not None:       # gradient that arrived through the bf16 copy of z (input of conv_out)
+            gl = nhwc(g_zlp).float()
+            gz = gl if gz is None else gz + gl
         cg = lambda t: t.contiguous().float() if t is not None else None
         g_kl, g_kls, g_logp, g_logq = cg(g_kl), cg(g_kls), cg(g_logp), cg(g_logq)
         dq = torch.empty_like(qn)

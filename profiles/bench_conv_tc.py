@@ -1,0 +1,52 @@
+"""Device-time microbenchmark of the tcgen05 conv kernel per shape (CUDA-graph replay, so no host
+launch or tensor-map encode cost is inside the timed region; rotating buffers > L2)."""
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch  # noqa: E402
+
+import lvae_b200  # noqa: E402
+from lvae_b200 import _capi, ops  # noqa: E402
+
+B, C = 256, 64
+one = len(sys.argv) > 1 and sys.argv[1] == "--one"
+shapes = [(16, 3, 64)] if one else [(32, 3, 64), (16, 3, 64), (8, 3, 64), (4, 3, 64), (2, 3, 64), (16, 1, 128), (32, 3, 100)]
+s = torch.cuda.current_stream()
+for HW, k, N in shapes:
+    per = B * HW * HW * (C + N) * 2
+    nbuf = max(2, int(300e6 // per) + 1)
+    xs = [torch.randn(B, HW, HW, C, device="cuda").to(torch.bfloat16) for _ in range(nbuf)]
+    ys = [torch.empty(B, HW, HW, N, device="cuda", dtype=torch.bfloat16) for _ in range(nbuf)]
+    w = torch.randn(N, C, k, k, device="cuda") / 24
+    wp = ops.WeightPack(N, C, k * k, 2).get(w, torch.bfloat16)
+    bias = torch.zeros(N, device="cuda")
+
+    def launch(i):
+        _capi.call("lvae_conv2d_tc", xs[i % nbuf].data_ptr(), None, wp.data_ptr(), bias.data_ptr(), None, None,
+                   ys[i % nbuf].data_ptr(), None, 0, B, HW, HW, C, N, k, 0, 0, torch.cuda.current_stream().cuda_stream)
+    launch(0)
+    torch.cuda.synchronize()
+    if one:
+        torch.cuda.profiler.start()
+        for i in range(3):
+            launch(i)
+        torch.cuda.synchronize()
+        torch.cuda.profiler.stop()
+        continue
+    n = 40
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        for i in range(n):
+            launch(i)
+    g.replay()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    g.replay()
+    e1.record()
+    torch.cuda.synchronize()
+    us = e0.elapsed_time(e1) * 1e3 / n
+    fl = 2.0 * B * HW * HW * C * N * k * k
+    print("H=W=%2d k=%d N=%3d: %7.2f us/launch  %7.1f TFLOP/s  %6.0f GB/s (in+out)  tiles/CTA %.2f" % (
+        HW, k, N, us, fl / us / 1e6, per / us / 1e3, B * HW * HW / 128 / 148))

@@ -135,3 +135,30 @@ def test_sample_prior_and_modes():
         model.topdown_pass(bu_values=None, n_img_prior=None)
     with pytest.raises(ValueError):
         model.top_down_layers[-1](torch.zeros(1, 16, 2, 2, device="cuda"))
+
+
+@pytest.mark.parametrize("name", ["mnist3_train_b4", "cifar15_train_b2", "mnist12_eval_b2"])
+def test_bf16_tensor_core_pipeline_close_to_golden(name):
+    """bf16 activations + tcgen05 convolutions (fp32 accumulation; stochastic and likelihood
+    parameters in fp32).  Stated separately from the fp32 parity runs: tolerance 2e-2 relative on
+    ll / KL / loss (bf16 has 8 mantissa bits and the residual stream is ~150 blocks deep)."""
+    cfg, meta, g = load_golden(name)
+    model = build(cfg, meta)
+    model.set_compute_dtype(torch.bfloat16)
+    import lvae_b200
+    n0 = lvae_b200._capi.launch_count()
+    with torch.set_grad_enabled(meta["training"]):
+        out = run_ours(model, cfg, meta)
+        loss = (-out["ll"]).mean() + out["kl_loss"]
+    assert out["ll"].dtype == torch.float32
+    assert rel_err(out["ll"], g["f64_ll"]) < 2e-2
+    assert rel_err(out["kl_sep"], g["f64_kl_sep"]) < 2e-2
+    assert rel_err(loss, g["f64_loss"]) < 2e-2
+    if meta["training"]:
+        loss.backward()
+        names = [str(n) for n in g["f64_grad_names"]]
+        params = dict(model.named_parameters())
+        ours = np.array([float(params[n].grad.double().pow(2).sum().sqrt()) if params[n].grad is not None else 0.0
+                         for n in names])
+        ref = g["f64_grad_l2"]
+        assert np.abs(ours - ref).max() < 5e-2 * ref.max(), names[int(np.abs(ours - ref).argmax())]
