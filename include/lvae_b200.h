@@ -56,6 +56,13 @@ int lvae_conv2d_wgrad(const void* u, const void* u2, const void* dz, const float
 int lvae_conv2d_tc(const void* x, const void* x2, const void* wp, const float* bias, const float* out_scale,
                    const void* res, void* y, void* y2, int nsplit, int B, int H, int W, int Cin, int N, int ksize,
                    int flip, int out_f32, lvae_stream_t stream);
+/* bf16 tensor-core weight gradient for the same convolutions (reduction over pixels, MN-major operands,
+ * two filter taps per M = 128 MMA, bias gradient from an all-ones operand block): x, x2 (B,H,W,64) bf16,
+ * dy (B,H,W,N) bf16 with N in {64,128} (already multiplied by the Dropout2d mask); dw (N,I,k,k) fp32 +=,
+ * dbias [N] += or NULL; ws = lvae_wgrad_tc_workspace(...) floats of scratch for the per-CTA partials. */
+int lvae_conv2d_wgrad_tc(const void* x, const void* x2, const void* dy, float* dw, float* dbias, float* ws, int B,
+                         int H, int W, int N, int ksize, lvae_stream_t stream);
+long long lvae_wgrad_tc_workspace(int B, int H, int W, int N, int ksize, int two_inputs);
 /* y = x * scale[b,c] (Dropout2d mask on a gradient tensor ahead of the TMA-fed dgrad) */
 int lvae_channel_scale(const void* x, const float* scale, void* y, int B, int HW, int C, int dtype,
                        lvae_stream_t stream);

@@ -23,6 +23,7 @@ _SIGNATURES = {
     "lvae_pack_weights": [P, I, P],
     "lvae_conv2d_tc": [P, P, P, P, P, P, P, P, I, I, I, I, I, I, I, I, I, P],
     "lvae_channel_scale": [P, P, P, I, I, I, I, P],
+    "lvae_conv2d_wgrad_tc": [P, P, P, P, P, P, I, I, I, I, I, P],
     "lvae_colsum": [P, P, P, I, I, I, I, P],
     "lvae_bn_stats": [P, P, L, I, I, P],
     "lvae_bn_finalize": [P, P, P, P, P, P, L, I, F, F, P],
@@ -57,6 +58,7 @@ _SPECIAL = {
     "lvae_reset_launch_count": ([], None),
     "lvae_device_check": ([], c_int),
     "lvae_pack_desc_size": ([], c_int),
+    "lvae_wgrad_tc_workspace": ([I, I, I, I, I, I], c_longlong),
 }
 
 

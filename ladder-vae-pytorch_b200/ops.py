@@ -303,6 +303,20 @@ class ConvSpec:
         return _pow2(H) and _pow2(W) and W <= 128 and N % 64 == 0 and N <= 256
 
 
+_wgrad_ws = {}
+stats = {"tc_fwd": 0, "tc_dgrad": 0, "tc_wgrad": 0, "cc_fwd": 0, "cc_dgrad": 0, "cc_wgrad": 0}   # path counters (tests)
+
+
+def _wgrad_workspace(device) -> torch.Tensor:
+    """Scratch for the per-CTA partials of lvae_conv2d_wgrad_tc (stream-ordered reuse)."""
+    ws = _wgrad_ws.get(device)
+    if ws is None:
+        sms = torch.cuda.get_device_properties(device).multi_processor_count
+        ws = torch.empty(sms * 512 * 128, dtype=torch.float32, device=device)
+        _wgrad_ws[device] = ws
+    return ws
+
+
 def _conv_tc(x, x2, wp, bias, out_scale, res, N, ksize, flip, out_f32, nsplit=0):
     """Launch the tcgen05 kernel.  Returns y, or (y, y2) when nsplit splits the output columns."""
     B, H, W, C = x.shape
@@ -344,6 +358,7 @@ class Conv2dFn(Function):
         want_f32 = spec.out_fp32 and xn.dtype == torch.bfloat16
         if spec.tc_forward_ok(xn, x2n) and (resn is None or resn.dtype == (torch.float32 if want_f32 else torch.bfloat16)):
             wp = spec.pack_tc_fwd.get(weight, torch.bfloat16)
+            stats["tc_fwd"] += 1
             y = _conv_tc(xn, x2n, wp, bias, out_scale, resn, spec.cout, spec.k, False, want_f32)
         else:
             wp = spec.pack_fwd.get(weight, xn.dtype)
@@ -379,6 +394,7 @@ class Conv2dFn(Function):
         if need_x:
             if use_tc:
                 wpb = spec.pack_tc_bwd.get(weight, torch.bfloat16)
+                stats["tc_dgrad"] += 1
                 if x2n is None:
                     gx = as_nchw(_conv_tc(gyn, None, wpb, None, None, None, spec.cin, spec.k, True, False))
                 else:
@@ -398,7 +414,13 @@ class Conv2dFn(Function):
             gbbuf, bsunk = (None, True)
             if bias is not None and ctx.needs_input_grad[3]:
                 gbbuf, bsunk = _param_grad_buffer(bias)
-            if not spec.transposed:
+            if use_tc and out_scale is None and C1 == 64 and C2 in (0, 64) and N in (64, 128) and gyn.dtype == torch.bfloat16 \
+                    and spec.k * spec.k * (2 if C2 else 1) <= 9:
+                stats["tc_wgrad"] += 1
+                call("lvae_conv2d_wgrad_tc", xn.data_ptr(), _p(x2n), gyn.data_ptr(), gwbuf.data_ptr(), _p(gbbuf),
+                     _wgrad_workspace(xn.device).data_ptr(), B, Hi, Wi, N, spec.k, _stream())
+            elif not spec.transposed:
+                stats["cc_wgrad"] += 1
                 call("lvae_conv2d_wgrad", xn.data_ptr(), _p(x2n), gyn.data_ptr(), None, _p(out_scale),
                      gwbuf.data_ptr(), _p(gbbuf), B, Hi, Wi, C1, C2, Ho, Wo, N, spec.k, spec.k, spec.stride,
                      spec.pad, _dt(xn), _stream())

@@ -44,7 +44,7 @@ with torch.profiler.profile(activities=[torch.profiler.ProfilerActivity.CUDA]) a
 agg = collections.defaultdict(lambda: [0, 0.0])
 for ev in prof.events():
     if ev.device_type == torch.autograd.DeviceType.CUDA:
-        name = ev.name.split("(")[0]
+        name = ev.name.replace("(anonymous namespace)::", "").replace("<unnamed>::", "").split("(")[0]
         agg[name][0] += 1
         agg[name][1] += ev.device_time
 tot = sum(v[1] for v in agg.values())

@@ -71,12 +71,17 @@ def test_tc_conv_forward_backward(case):
         kw["x2"] = x2d
     if use_res:
         kw["res"] = phys_nhwc(res.cuda())
-    n0 = lvae_b200._capi.launch_count()
+    before = dict(ops.stats)
     y = mod(xd, **kw)
     assert y.dtype == (torch.float32 if out_fp32 else torch.bfloat16)
     assert rel_err(y.float(), yr) < (2e-5 if out_fp32 else 6e-3)
     y.backward(gy.cuda().to(y.dtype))
     torch.cuda.synchronize()
+    assert ops.stats["tc_fwd"] == before["tc_fwd"] + 1
+    if cout % 64 == 0:
+        assert ops.stats["tc_dgrad"] == before["tc_dgrad"] + 1
+    if cin == 64 and cout in (64, 128):
+        assert ops.stats["tc_wgrad"] == before["tc_wgrad"] + 1     # tensor-core weight gradient taken
     # dgrad output is bf16: one rounding
     assert rel_err(xd.grad.float(), xr.grad) < 6e-3
     if cin2:
