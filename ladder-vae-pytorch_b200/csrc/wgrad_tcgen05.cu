@@ -236,19 +236,34 @@ struct RedParams {
 };
 
 __global__ void wgrad_reduce_kernel(RedParams p) {
+  // grid.y splits the partials: each thread sums its slice of CTAs (independent loads, 4 in flight), then adds
   const int per = p.n_pairs * 128 * p.N;
-  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < per; idx += gridDim.x * blockDim.x) {
-    int co = idx % p.N;
-    int row = (idx / p.N) % 128;
-    int pr = idx / (p.N * 128);
-    int blk = pr * 2 + (row >> 6);
-    int kind = p.kind[blk];
-    if (kind == 2 || (kind == 1 && (row & 63) != 0) || (kind == 1 && !p.dbias)) continue;
-    float s = 0.f;
-    for (int c = 0; c < p.n_cta; ++c) s += p.ws[(size_t)c * per + idx];
-    if (kind == 1) p.dbias[co] += s;
-    else p.dw[((size_t)co * p.I + p.ci0_blk[blk] * 64 + (row & 63)) * p.taps + p.tap[blk]] += s;
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= per) return;
+  const int co = idx % p.N;
+  const int row = (idx / p.N) % 128;
+  const int pr = idx / (p.N * 128);
+  const int blk = pr * 2 + (row >> 6);
+  const int kind = p.kind[blk];
+  if (kind == 2 || (kind == 1 && ((row & 63) != 0 || !p.dbias))) return;
+  const int chunk = (p.n_cta + gridDim.y - 1) / gridDim.y;
+  const int c_beg = blockIdx.y * chunk, c_end = min(p.n_cta, c_beg + chunk);
+  if (c_beg >= c_end) return;
+  const float* src = p.ws + idx;
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+  int c = c_beg;
+  for (; c + 4 <= c_end; c += 4) {
+    s0 += __ldg(src + (size_t)c * per);
+    s1 += __ldg(src + (size_t)(c + 1) * per);
+    s2 += __ldg(src + (size_t)(c + 2) * per);
+    s3 += __ldg(src + (size_t)(c + 3) * per);
   }
+  for (; c < c_end; ++c) s0 += __ldg(src + (size_t)c * per);
+  const float s = (s0 + s1) + (s2 + s3);
+  float* dst = kind == 1 ? p.dbias + co
+                         : p.dw + ((size_t)co * p.I + p.ci0_blk[blk] * 64 + (row & 63)) * p.taps + p.tap[blk];
+  if (gridDim.y == 1) *dst += s;
+  else atomicAdd(dst, s);
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
@@ -345,7 +360,8 @@ LVAE_API int lvae_conv2d_wgrad_tc(const void* x, const void* x2, const void* dy,
   LVAE_CHECK_LAUNCH("conv2d_wgrad_tc");
   rp.ws = ws; rp.dw = dw; rp.dbias = dbias; rp.n_cta = grid; rp.n_pairs = p.n_pairs; rp.N = N; rp.I = 64 * inputs; rp.taps = taps;
   const int per = p.n_pairs * 128 * N;
-  wgrad_reduce_kernel<<<(per + 255) / 256, 256, 0, stream>>>(rp);
+  const int ysplit = grid >= 64 ? 8 : (grid >= 16 ? 4 : 1);
+  wgrad_reduce_kernel<<<dim3((per + 255) / 256, ysplit), 256, 0, stream>>>(rp);
   LVAE_COUNT_LAUNCH();
   LVAE_CHECK_LAUNCH("wgrad_reduce");
   return LVAE_OK;

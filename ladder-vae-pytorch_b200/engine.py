@@ -41,6 +41,20 @@ def bucket_ranges(numel: int, bucket_bytes: int = 25 << 20, elem_bytes: int = 4)
     return [(s, min(numel, s + per)) for s in range(0, numel, per)]
 
 
+def all_reduce_buckets(flat: torch.Tensor, buckets, group=None) -> None:
+    """Sum-all-reduce a flat gradient arena bucket by bucket (NCCL on GPUs; device agnostic)."""
+    for s, e in buckets:
+        dist.all_reduce(flat[s:e], op=dist.ReduceOp.SUM, group=group)
+
+
+def gather_states(state: torch.Tensor, group=None) -> torch.Tensor:
+    """All-gather the per-rank (B,2) running (max, sum-exp) states into (R,B,2)."""
+    world = dist.get_world_size(group)
+    out = torch.empty((world * state.shape[0],) + tuple(state.shape[1:]), dtype=state.dtype, device=state.device)
+    dist.all_gather_into_tensor(out, state.contiguous(), group=group)
+    return out.view((world,) + tuple(state.shape))
+
+
 class ParamArena:
     """All trainable parameters of a model as views into one flat fp32 buffer, with a parallel
     gradient buffer that the wgrad / BatchNorm / prior kernels accumulate into directly."""
@@ -143,8 +157,7 @@ class TrainEngine:
 
     def _all_reduce(self):
         if self.world > 1:
-            for s, e in self.buckets:
-                dist.all_reduce(self.arena.grad[s:e], op=dist.ReduceOp.SUM, group=self.pg)
+            all_reduce_buckets(self.arena.grad, self.buckets, self.pg)
 
     def _optimizer(self):
         a = self.arena
@@ -205,9 +218,11 @@ class IWEvaluator:
     """Importance-weighted bound log p(x) >= logsumexp_k(ll_k - kl_k) - log K, with the
     K samples sharded over ranks and one (B,2) all-gather + combine per image batch."""
 
-    def __init__(self, model, batch_size: int, use_graph: bool = True, process_group=None):
+    def __init__(self, model, batch_size: int, use_graph: bool = True, process_group=None, reuse_bottomup: bool = True):
         _capi.device_check()
         self.model = model.eval()
+        self.reuse_bottomup = reuse_bottomup      # False: full forward per sample, like the reference's loop
+        self.bu = None
         self.pg = process_group
         inited = process_group is not None or dist.is_initialized()
         self.world = dist.get_world_size(process_group) if inited else 1
@@ -218,11 +233,16 @@ class IWEvaluator:
         self.state = torch.zeros((batch_size, 2), dtype=torch.float32, device=dev)
         self.use_graph = use_graph
         self.graph = None
+        self.graph_bu = None
         self.launches_per_sample = 0
+        self.launches_bottomup = 0
+
+    def _bottomup(self):
+        self.bu = self.model.bottomup_pass(self.model.pad_input(self.x)) if self.reuse_bottomup else None
 
     def _one_sample(self):
         ops.rng_advance(self.device)
-        out = self.model(self.x)
+        out = self.model.forward_from_bottomup(self.x, self.bu) if self.reuse_bottomup else self.model(self.x)
         ops.iw_lse_update(out["ll"], out["kl_sep"], self.state, False)
 
     def _reset(self):
@@ -239,16 +259,26 @@ class IWEvaluator:
                 s = torch.cuda.Stream()
                 s.wait_stream(torch.cuda.current_stream())
                 with torch.cuda.stream(s):
+                    self._bottomup()
                     self._one_sample()
                 torch.cuda.current_stream().wait_stream(s)
                 torch.cuda.synchronize()
                 self._reset()
                 n0 = _capi.launch_count()
+                self.graph_bu = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(self.graph_bu):
+                    self._bottomup()
+                self.launches_bottomup = _capi.launch_count() - n0
+                n0 = _capi.launch_count()
                 self.graph = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(self.graph):
+                with torch.cuda.graph(self.graph, pool=self.graph_bu.pool()):
                     self._one_sample()
                 self.launches_per_sample = _capi.launch_count() - n0
                 self._reset()
+            if self.use_graph:
+                self.graph_bu.replay()
+            else:
+                self._bottomup()
             for _ in range(k_local):
                 if self.use_graph:
                     self.graph.replay()
@@ -257,8 +287,7 @@ class IWEvaluator:
                     self._one_sample()
                     self.launches_per_sample = _capi.launch_count() - n0
             if self.world > 1:
-                states = torch.empty((self.world,) + tuple(self.state.shape), dtype=torch.float32, device=self.device)
-                dist.all_gather_into_tensor(states, self.state, group=self.pg)
+                states = gather_states(self.state, self.pg)
             else:
                 states = self.state[None]
             return ops.iw_lse_combine(states.contiguous(), k_total)

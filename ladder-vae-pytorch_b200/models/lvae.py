@@ -112,10 +112,15 @@ class LadderVAE(BaseGenerativeModel):
             ops.clear_masks()
 
     def forward(self, x):
-        img_size = x.size()[2:]
         self._begin(x.shape[0], x.device)
-        x_pad = self.pad_input(x)
-        bu_values = self.bottomup_pass(x_pad)
+        bu_values = self.bottomup_pass(self.pad_input(x))
+        return self.forward_from_bottomup(x, bu_values)
+
+    def forward_from_bottomup(self, x, bu_values):
+        """Top-down pass, likelihood and KL bookkeeping given the bottom-up activations.  In eval()
+        the bottom-up pass is deterministic, so the importance-weighted evaluator computes it once
+        per image batch and calls this once per sample (the reference recomputes it K times)."""
+        img_size = x.size()[2:]
         out, td = self.topdown_pass(bu_values)
         out = ops.crop(out, img_size)
         ll, lik = self.likelihood(out, x)

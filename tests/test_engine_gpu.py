@@ -101,3 +101,7 @@ def test_iw_evaluator():
     assert tuple(b64.shape) == (16,) and torch.isfinite(b64).all()
     assert float(b64.mean()) > float(b1.mean()) - 1.0        # the bound tightens with K (up to noise)
     assert abs(float(b64.mean()) - float(c64.mean())) < 0.05 * abs(float(c64.mean()))
+    # reference-style loop (bottom-up pass recomputed per sample) agrees statistically
+    ev3 = IWEvaluator(model, 16, use_graph=False, reuse_bottomup=False)
+    d64 = ev3.bound(xd, 64)
+    assert abs(float(b64.mean()) - float(d64.mean())) < 0.05 * abs(float(d64.mean()))
