@@ -92,10 +92,27 @@ int lvae_bn_act_bwd(const void* dy, const void* x, void* dx, const float* mean, 
                     const float* gamma, const float* beta, double* acc, float* dgamma, float* dbeta, long long P,
                     int C, int act, int training, int dtype, lvae_stream_t stream);
 
+/* Fused variants for the whole-residual-block schedule: forward derives mean / rstd in-kernel from the
+ * statistics accumulator (training) or the running statistics (eval), writes save = [mean | rstd] and
+ * updates the running statistics; backward = reduce + apply, the apply pass also emitting dgamma / dbeta,
+ * an optional Dropout2d mask on dx (post_scale (B,C)) and an optional residual add.  Accumulators are
+ * not cleared (the caller zeroes its BatchNorm scratch arena once per forward). */
+int lvae_bn_act_fwd2(const void* x, void* y, const double* acc, const float* gamma, const float* beta, float* save,
+                     float* running_mean, float* running_var, long long* num_batches_tracked, long long P, int C,
+                     int act, int training, float momentum, float eps, int dtype_in, int dtype_out,
+                     lvae_stream_t stream);
+int lvae_bn_act_bwd2(const void* dy, const void* x, void* dx, const float* save, const float* gamma,
+                     const float* beta, double* acc, float* dgamma, float* dbeta, const float* post_scale,
+                     const void* add, long long P, int hw, int C, int act, int training, int dtype,
+                     lvae_stream_t stream);
+
 /* ---- GateLayer2d product + residual: lib/nn.py:121-126 and :99 ----
  * h (P,2C): out = act(h[:, :C]) * sigmoid(h[:, C:]) + res */
 int lvae_gate_fwd(const void* h, const void* res, void* out, long long P, int C, int act, int dtype,
                   lvae_stream_t stream);
+/* same, also accumulating per-channel sum / sum-of-squares of `out` into acc (2C doubles) */
+int lvae_gate_fwd_stats(const void* h, const void* res, void* out, double* acc, long long P, int C, int act,
+                        int dtype, lvae_stream_t stream);
 int lvae_gate_bwd(const void* dout, const void* h, void* dh, long long P, int C, int act, int dtype,
                   lvae_stream_t stream);
 

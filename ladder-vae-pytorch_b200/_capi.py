@@ -30,6 +30,9 @@ _SIGNATURES = {
     "lvae_bn_eval_prepare": [P, P, P, P, I, F, P],
     "lvae_bn_act_fwd": [P, P, P, P, P, P, L, I, I, I, I, P],
     "lvae_bn_act_bwd": [P, P, P, P, P, P, P, P, P, P, L, I, I, I, I, P],
+    "lvae_bn_act_fwd2": [P, P, P, P, P, P, P, P, P, L, I, I, I, F, F, I, I, P],
+    "lvae_bn_act_bwd2": [P, P, P, P, P, P, P, P, P, P, P, L, I, I, I, I, I, P],
+    "lvae_gate_fwd_stats": [P, P, P, P, L, I, I, I, P],
     "lvae_gate_fwd": [P, P, P, L, I, I, I, P],
     "lvae_gate_bwd": [P, P, P, L, I, I, I, P],
     "lvae_upsample2x_fwd": [P, P, I, I, I, I, I, P],

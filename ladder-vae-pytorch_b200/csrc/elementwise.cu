@@ -565,3 +565,223 @@ LVAE_API int lvae_channel_scale(const void* x, const float* scale, void* y, int 
   LVAE_CHECK_LAUNCH("channel_scale");
   return LVAE_OK;
 }
+
+// =========================================================================================
+// Fused variants used by the block-level schedule (no finalize / params / mask kernels):
+//   bn_act_fwd2: mean / rstd derived in-kernel from the statistics accumulator (train) or the running
+//                statistics (eval); block 0 also writes the saved statistics and updates the running ones.
+//   bn_act_bwd2: apply pass that also emits dgamma / dbeta, an optional Dropout2d mask on dx
+//                (post_scale, the mask of the conv that produced x) and an optional residual add.
+// The accumulators are NOT cleared here: the model zeroes its whole BatchNorm scratch arena once per forward.
+// =========================================================================================
+template <typename TI, typename TO>
+__global__ void bn_act_fwd2_kernel(const TI* __restrict__ x, TO* __restrict__ y, const double* __restrict__ acc,
+                                   const float* __restrict__ gamma, const float* __restrict__ beta,
+                                   float* __restrict__ save, float* running_mean, float* running_var,
+                                   long long* nbt, long long nquads, long long P, int C, int act, int training,
+                                   float momentum, float eps) {
+  const int CV = C >> 2;
+  const long long stride = (long long)gridDim.x * blockDim.x;      // multiple of CV by construction
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int c = (int)(i % CV) * 4;
+  float m[4], r[4], g[4], b[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    if (training) {
+      double mean = acc[c + j] / (double)P;
+      double var = acc[C + c + j] / (double)P - mean * mean;
+      if (var < 0.0) var = 0.0;
+      m[j] = (float)mean;
+      r[j] = (float)(1.0 / sqrt(var + (double)eps));
+    } else {
+      m[j] = running_mean[c + j];
+      r[j] = 1.0f / sqrtf(running_var[c + j] + eps);
+    }
+    g[j] = gamma[c + j];
+    b[j] = beta[c + j];
+  }
+  if (blockIdx.x == 0 && threadIdx.x < CV) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      save[c + j] = m[j];
+      save[C + c + j] = r[j];
+      if (training && running_mean) {
+        double mean = acc[c + j] / (double)P;
+        double var = acc[C + c + j] / (double)P - mean * mean;
+        if (var < 0.0) var = 0.0;
+        double unb = P > 1 ? var * (double)P / (double)(P - 1) : var;
+        running_mean[c + j] = (float)((1.0 - momentum) * (double)running_mean[c + j] + momentum * mean);
+        running_var[c + j] = (float)((1.0 - momentum) * (double)running_var[c + j] + momentum * unb);
+      }
+    }
+    if (threadIdx.x == 0 && training && nbt) *nbt += 1;
+  }
+  for (; i < nquads; i += stride) {
+    float4 v = ld4<TI>(x + i * 4);
+    float o[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) o[j] = act_fwd((o[j] - m[j]) * r[j] * g[j] + b[j], act);
+    st4<TO>(y + i * 4, make_float4(o[0], o[1], o[2], o[3]));
+  }
+}
+
+template <typename T>
+__global__ void bn_act_bwd2_kernel(const T* __restrict__ dy, const T* __restrict__ x, T* __restrict__ dx,
+                                   const float* __restrict__ save, const float* __restrict__ gamma,
+                                   const float* __restrict__ beta, const double* __restrict__ acc,
+                                   float* dgamma, float* dbeta, const float* __restrict__ post_scale,
+                                   const T* __restrict__ add, long long nquads, long long P, int hw, int C, int act,
+                                   int training) {
+  const int CV = C >> 2;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int c = (int)(i % CV) * 4;
+  const double invP = 1.0 / (double)P;
+  float m[4], r[4], g[4], b[4], m1[4], m2[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    m[j] = save[c + j]; r[j] = save[C + c + j]; g[j] = gamma[c + j]; b[j] = beta[c + j];
+    m1[j] = (float)(acc[c + j] * invP);
+    m2[j] = (float)(acc[C + c + j] * invP);
+  }
+  if (blockIdx.x == 0 && threadIdx.x < CV) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      if (dbeta) dbeta[c + j] += (float)acc[c + j];
+      if (dgamma) dgamma[c + j] += (float)acc[C + c + j];
+    }
+  }
+  for (; i < nquads; i += stride) {
+    float4 xv = ld4<T>(x + i * 4), dv = ld4<T>(dy + i * 4);
+    float xs[4] = {xv.x, xv.y, xv.z, xv.w}, ds[4] = {dv.x, dv.y, dv.z, dv.w}, o[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float xh = (xs[j] - m[j]) * r[j];
+      float gpre = ds[j] * act_bwd(xh * g[j] + b[j], act);
+      o[j] = training ? g[j] * r[j] * (gpre - m1[j] - xh * m2[j]) : g[j] * r[j] * gpre;
+    }
+    if (post_scale) {
+      long long bidx = (i / CV) / hw;
+      float4 s = *reinterpret_cast<const float4*>(post_scale + bidx * C + c);
+      o[0] *= s.x; o[1] *= s.y; o[2] *= s.z; o[3] *= s.w;
+    }
+    if (add) {
+      float4 a = ld4<T>(add + i * 4);
+      o[0] += a.x; o[1] += a.y; o[2] += a.z; o[3] += a.w;
+    }
+    st4<T>(dx + i * 4, make_float4(o[0], o[1], o[2], o[3]));
+  }
+}
+
+// grid whose total thread count is a multiple of C/4, so that every thread keeps the same channel quad
+static inline int ew_grid_aligned(long long n, int threads, int CV) {
+  int g = ew_grid(n, threads);
+  while (((long long)g * threads) % CV != 0) ++g;
+  return g;
+}
+
+LVAE_API int lvae_bn_act_fwd2(const void* x, void* y, const double* acc, const float* gamma, const float* beta,
+                              float* save, float* running_mean, float* running_var, long long* nbt, long long P, int C,
+                              int act, int training, float momentum, float eps, int dtype_in, int dtype_out,
+                              cudaStream_t stream) {
+  LVAE_REQUIRE(x && y && gamma && beta && save && P > 0 && bn_c_ok(C), "bn_act_fwd2: bad args");
+  LVAE_REQUIRE(training ? acc != nullptr : (running_mean && running_var), "bn_act_fwd2: statistics source missing");
+  long long nq = P * (C / 4);
+  int g = ew_grid_aligned(nq, 256, C / 4);
+#define FW2(TI, TO) bn_act_fwd2_kernel<TI, TO><<<g, 256, 0, stream>>>((const TI*)x, (TO*)y, acc, gamma, beta, save, running_mean, running_var, nbt, nq, P, C, act, training, momentum, eps)
+  if (dtype_in == 0 && dtype_out == 0) FW2(float, float);
+  else if (dtype_in == 0 && dtype_out == 1) FW2(float, __nv_bfloat16);
+  else if (dtype_in == 1 && dtype_out == 1) FW2(__nv_bfloat16, __nv_bfloat16);
+  else FW2(__nv_bfloat16, float);
+#undef FW2
+  LVAE_COUNT_LAUNCH();
+  LVAE_CHECK_LAUNCH("bn_act_fwd2");
+  return LVAE_OK;
+}
+
+// reduce pass (shared with lvae_bn_act_bwd) + fused apply
+LVAE_API int lvae_bn_act_bwd2(const void* dy, const void* x, void* dx, const float* save, const float* gamma,
+                              const float* beta, double* acc, float* dgamma, float* dbeta, const float* post_scale,
+                              const void* add, long long P, int hw, int C, int act, int training, int dtype,
+                              cudaStream_t stream) {
+  LVAE_REQUIRE(dy && x && dx && save && gamma && beta && acc && P > 0 && bn_c_ok(C), "bn_act_bwd2: bad args");
+  long long nq = P * (C / 4);
+  int threads = bn_threads(C), rpb = threads / (C / 4);
+  int grid = (int)min((long long)4 * lvae_num_sms(), (P + rpb - 1) / rpb);
+  size_t smem = (size_t)threads * 4 * 2 * sizeof(float);
+  if (dtype == 0)
+    bn_act_bwd_reduce_kernel<float><<<grid, threads, smem, stream>>>((const float*)dy, (const float*)x, save, save + C, gamma, beta, acc, P, C, act);
+  else
+    bn_act_bwd_reduce_kernel<__nv_bfloat16><<<grid, threads, smem, stream>>>((const __nv_bfloat16*)dy, (const __nv_bfloat16*)x, save, save + C, gamma, beta, acc, P, C, act);
+  LVAE_COUNT_LAUNCH();
+  LVAE_CHECK_LAUNCH("bn_act_bwd_reduce");
+  int g = ew_grid_aligned(nq, 256, C / 4);
+  if (dtype == 0)
+    bn_act_bwd2_kernel<float><<<g, 256, 0, stream>>>((const float*)dy, (const float*)x, (float*)dx, save, gamma, beta, acc, dgamma, dbeta, post_scale, (const float*)add, nq, P, hw, C, act, training);
+  else
+    bn_act_bwd2_kernel<__nv_bfloat16><<<g, 256, 0, stream>>>((const __nv_bfloat16*)dy, (const __nv_bfloat16*)x, (__nv_bfloat16*)dx, save, gamma, beta, acc, dgamma, dbeta, post_scale, (const __nv_bfloat16*)add, nq, P, hw, C, act, training);
+  LVAE_COUNT_LAUNCH();
+  LVAE_CHECK_LAUNCH("bn_act_bwd2");
+  return LVAE_OK;
+}
+
+// gate forward that also accumulates the per-channel sum / sum of squares of its OUTPUT (the next
+// residual block's first BatchNorm then needs no statistics pass of its own)
+template <typename T>
+__global__ void gate_fwd_stats_kernel(const T* __restrict__ h, const T* __restrict__ res, T* __restrict__ out,
+                                      double* __restrict__ acc, long long nquads, int C, int act) {
+  extern __shared__ float sm[];
+  const int CV = C >> 2;
+  const long long stride = (long long)gridDim.x * blockDim.x;      // multiple of CV
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int cq = (int)(i % CV);
+  float4 s = make_float4(0.f, 0.f, 0.f, 0.f), ss = s;
+  for (; i < nquads; i += stride) {
+    long long row = i / CV;
+    int c = cq * 4;
+    float4 a = ld4<T>(h + row * 2 * C + c), g = ld4<T>(h + row * 2 * C + C + c);
+    float4 o = make_float4(act_fwd(a.x, act) * sigmoidf_(g.x), act_fwd(a.y, act) * sigmoidf_(g.y),
+                           act_fwd(a.z, act) * sigmoidf_(g.z), act_fwd(a.w, act) * sigmoidf_(g.w));
+    if (res) {
+      float4 r = ld4<T>(res + i * 4);
+      o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
+    }
+    st4<T>(out + i * 4, o);
+    float4 q = ld4<T>(out + i * 4);        // statistics of the value as stored (bf16-rounded on the bf16 path)
+    s.x += q.x; s.y += q.y; s.z += q.z; s.w += q.w;
+    ss.x += q.x * q.x; ss.y += q.y * q.y; ss.z += q.z * q.z; ss.w += q.w * q.w;
+  }
+  // block reduction: threads with the same channel quad are blockDim/CV apart
+  float* s_s = sm;
+  float* s_ss = sm + blockDim.x * 4;
+  reinterpret_cast<float4*>(s_s)[threadIdx.x] = s;
+  reinterpret_cast<float4*>(s_ss)[threadIdx.x] = ss;
+  __syncthreads();
+  if (threadIdx.x < C) {
+    // thread t of the block has quad (blockIdx.x*blockDim.x + t) % CV; blockDim % CV == 0 -> quad = (base + t) % CV
+    const int base = (int)(((long long)blockIdx.x * blockDim.x) % CV);
+    int cch = threadIdx.x, q = cch >> 2, e = cch & 3;
+    double a = 0.0, b = 0.0;
+    for (int t = (q - base + CV) % CV; t < blockDim.x; t += CV) {
+      a += (double)s_s[t * 4 + e];
+      b += (double)s_ss[t * 4 + e];
+    }
+    atomicAdd(acc + cch, a);
+    atomicAdd(acc + C + cch, b);
+  }
+}
+
+LVAE_API int lvae_gate_fwd_stats(const void* h, const void* res, void* out, double* acc, long long P, int C, int act,
+                                 int dtype, cudaStream_t stream) {
+  LVAE_REQUIRE(h && out && acc && P > 0 && bn_c_ok(C) && 256 % (C / 4) == 0, "gate_fwd_stats: bad args");
+  long long nq = P * (C / 4);
+  long long cap = 4LL * lvae_num_sms();
+  long long want = (nq + 255) / 256;
+  int g = (int)(want < cap ? (want > 0 ? want : 1) : cap);
+  size_t smem = (size_t)256 * 4 * 2 * sizeof(float);
+  if (dtype == 0) gate_fwd_stats_kernel<float><<<g, 256, smem, stream>>>((const float*)h, (const float*)res, (float*)out, acc, nq, C, act);
+  else gate_fwd_stats_kernel<__nv_bfloat16><<<g, 256, smem, stream>>>((const __nv_bfloat16*)h, (const __nv_bfloat16*)res, (__nv_bfloat16*)out, acc, nq, C, act);
+  LVAE_COUNT_LAUNCH();
+  LVAE_CHECK_LAUNCH("gate_fwd_stats");
+  return LVAE_OK;
+}

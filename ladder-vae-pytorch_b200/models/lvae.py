@@ -104,8 +104,26 @@ class LadderVAE(BaseGenerativeModel):
         return self
 
     # ------------------------------------------------------------------ forward pieces
+    def _bn_arena(self, device):
+        """One float64 scratch arena for the statistics accumulators of every BatchNorm2d (zeroed once per forward)."""
+        arena = getattr(self, "_lvae_bn_arena", None)
+        if arena is None or arena.device != device:
+            from lvae_b200.lib.nn import BatchNorm2d
+            bns = [m for m in self.modules() if isinstance(m, BatchNorm2d)]
+            arena = torch.zeros((max(1, len(bns)), 6, self.n_filters), dtype=torch.float64, device=device)
+            for i, bn in enumerate(bns):
+                if bn.num_features == self.n_filters:
+                    bn._lvae_scratch = arena[i]
+                    bn._lvae_scratch_owned = False
+                    bn._lvae_epoch_fwd = bn._lvae_epoch_bwd = bn._lvae_epoch_out = -1
+            self._lvae_bn_arena = arena
+        return arena
+
     def _begin(self, batch, device):
-        """Draw every Dropout2d mask of this pass in one launch."""
+        """Zero the BatchNorm scratch arena and draw every Dropout2d mask of this pass (one launch each)."""
+        if self.training:
+            self._bn_arena(device).zero_()
+            ops.new_forward_epoch()
         if self.training and self.dropout:
             ops.prepare_masks(self._n_dropout_sites, batch, self.n_filters, self.dropout, device)
         else:

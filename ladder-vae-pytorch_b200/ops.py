@@ -338,10 +338,94 @@ def _gather(x, x2, wp, ld, bias, in_scale, out_scale, res, B, Hi, Wi, C1, C2, Ho
     return y
 
 
+def conv_forward_raw(spec: ConvSpec, xn, x2n, weight, bias, out_scale, resn):
+    """(conv(cat(xn, x2n)) + bias) * out_scale + resn on NHWC tensors.  bf16 activations on eligible shapes run on
+    the tensor cores (lvae_conv2d_tc), everything else on the CUDA-core implicit GEMM (lvae_conv2d_gather)."""
+    B, Hi, Wi, C1 = xn.shape
+    C2 = x2n.shape[3] if x2n is not None else 0
+    assert C1 + C2 == spec.cin, "conv input channels %d+%d != %d" % (C1, C2, spec.cin)
+    Ho, Wo = spec.out_hw(Hi, Wi)
+    want_f32 = spec.out_fp32 and xn.dtype == torch.bfloat16
+    if spec.tc_forward_ok(xn, x2n) and (resn is None or resn.dtype == (torch.float32 if want_f32 else torch.bfloat16)):
+        wp = spec.pack_tc_fwd.get(weight, torch.bfloat16)
+        stats["tc_fwd"] += 1
+        return _conv_tc(xn, x2n, wp, bias, out_scale, resn, spec.cout, spec.k, False, want_f32)
+    wp = spec.pack_fwd.get(weight, xn.dtype)
+    if resn is not None and resn.dtype != xn.dtype:
+        resn = resn.to(xn.dtype)
+    stats["cc_fwd"] += 1
+    y = _gather(xn, x2n, wp, spec.pack_fwd.ld, bias, None, out_scale, resn, B, Hi, Wi, C1, C2, Ho, Wo,
+                spec.cout, spec.k, spec.stride, spec.pad, 1 if spec.transposed else 0, xn.dtype)
+    return y.float() if want_f32 else y
+
+
+def conv_backward_raw(spec: ConvSpec, xn, x2n, weight, bias, out_scale, gyn, need_x=True, need_w=True, need_b=True,
+                      dx_scale=None):
+    """Data and parameter gradients of conv_forward_raw.  ``out_scale`` is the forward's Dropout2d mask (gyn is the
+    gradient wrt the masked output; pass None when gyn is already the gradient wrt the raw conv output).
+    ``dx_scale`` (B, Cin) is folded into the dgrad epilogue: the returned dx is multiplied by it (the mask of the
+    conv that produced xn).  Returns (gx, gx2, gw, gb); gw / gb are None when accumulated into a gradient sink."""
+    if gyn.dtype != xn.dtype:
+        gyn = gyn.to(xn.dtype)
+    B, Hi, Wi, C1 = xn.shape
+    C2 = x2n.shape[3] if x2n is not None else 0
+    _, Ho, Wo, N = gyn.shape
+    gx = gx2 = gw = gb = None
+    use_tc = xn.dtype == torch.bfloat16 and spec.tc_dgrad_ok(gyn)
+    if use_tc and out_scale is not None:
+        # TMA-fed operands never pass through registers: apply the Dropout2d mask in a separate pass
+        gys = torch.empty_like(gyn)
+        call("lvae_channel_scale", gyn.data_ptr(), out_scale.data_ptr(), gys.data_ptr(), B, Ho * Wo, N, _dt(gyn), _stream())
+        gyn, out_scale = gys, None
+    if need_x:
+        if use_tc:
+            wpb = spec.pack_tc_bwd.get(weight, torch.bfloat16)
+            stats["tc_dgrad"] += 1
+            if x2n is None:
+                gx = _conv_tc(gyn, None, wpb, None, dx_scale, None, spec.cin, spec.k, True, False)
+            else:
+                assert dx_scale is None
+                gx, gx2 = _conv_tc(gyn, None, wpb, None, None, None, spec.cin, spec.k, True, False, nsplit=C1)
+        else:
+            wpb = spec.pack_bwd.get(weight, gyn.dtype)
+            stats["cc_dgrad"] += 1
+            gcat = _gather(gyn, None, wpb, spec.pack_bwd.ld, None, out_scale, dx_scale, None, B, Ho, Wo, N, 0, Hi, Wi,
+                           spec.cin, spec.k, spec.stride, spec.pad, 0 if spec.transposed else 1, gyn.dtype)
+            if x2n is None:
+                gx = gcat
+            else:
+                assert dx_scale is None
+                gx, gx2 = gcat[..., :C1], gcat[..., C1:]
+    if need_w:
+        gwbuf, sunk = _param_grad_buffer(weight)
+        gbbuf, bsunk = (None, True)
+        if bias is not None and need_b:
+            gbbuf, bsunk = _param_grad_buffer(bias)
+        if use_tc and out_scale is None and C1 == 64 and C2 in (0, 64) and N in (64, 128) and gyn.dtype == torch.bfloat16 \
+                and spec.k * spec.k * (2 if C2 else 1) <= 9:
+            stats["tc_wgrad"] += 1
+            call("lvae_conv2d_wgrad_tc", xn.data_ptr(), _p(x2n), gyn.data_ptr(), gwbuf.data_ptr(), _p(gbbuf),
+                 _wgrad_workspace(xn.device).data_ptr(), B, Hi, Wi, N, spec.k, _stream())
+        elif not spec.transposed:
+            stats["cc_wgrad"] += 1
+            call("lvae_conv2d_wgrad", xn.data_ptr(), _p(x2n), gyn.data_ptr(), None, _p(out_scale),
+                 gwbuf.data_ptr(), _p(gbbuf), B, Hi, Wi, C1, C2, Ho, Wo, N, spec.k, spec.k, spec.stride,
+                 spec.pad, _dt(xn), _stream())
+        else:
+            # roles swap: "input" = dy (scaled), "output grad" = x; result is (Cin, Cout, k, k)
+            stats["cc_wgrad"] += 1
+            call("lvae_conv2d_wgrad", gyn.data_ptr(), None, xn.data_ptr(), _p(out_scale), None,
+                 gwbuf.data_ptr(), None, B, Ho, Wo, N, 0, Hi, Wi, C1, spec.k, spec.k, spec.stride, spec.pad,
+                 _dt(xn), _stream())
+            if gbbuf is not None:
+                call("lvae_colsum", gyn.data_ptr(), _p(out_scale), gbbuf.data_ptr(), B, Ho * Wo, N, _dt(gyn), _stream())
+        gw = None if sunk else gwbuf
+        gb = None if (bsunk or gbbuf is None) else gbbuf
+    return gx, gx2, gw, gb
+
+
 class Conv2dFn(Function):
-    """y = (conv(cat(x, x2)) + bias) * out_scale[b, c] + res   (Conv2d or ConvTranspose2d).
-    bf16 activations on eligible shapes run on the tensor cores (lvae_conv2d_tc), everything
-    else on the CUDA-core implicit GEMM (lvae_conv2d_gather)."""
+    """y = (conv(cat(x, x2)) + bias) * out_scale[b, c] + res   (Conv2d or ConvTranspose2d)."""
 
     @staticmethod
     def forward(ctx, x, x2, weight, bias, out_scale, res, spec: ConvSpec):
@@ -349,25 +433,9 @@ class Conv2dFn(Function):
         xn = nhwc(x)
         x2n = nhwc(x2) if x2 is not None else None
         resn = nhwc(res) if res is not None else None
-        B, Hi, Wi, C1 = xn.shape
-        C2 = x2n.shape[3] if x2n is not None else 0
-        assert C1 + C2 == spec.cin, "conv input channels %d+%d != %d" % (C1, C2, spec.cin)
-        Ho, Wo = spec.out_hw(Hi, Wi)
         if out_scale is not None:
-            out_scale = out_scale.reshape(B, spec.cout)
-        want_f32 = spec.out_fp32 and xn.dtype == torch.bfloat16
-        if spec.tc_forward_ok(xn, x2n) and (resn is None or resn.dtype == (torch.float32 if want_f32 else torch.bfloat16)):
-            wp = spec.pack_tc_fwd.get(weight, torch.bfloat16)
-            stats["tc_fwd"] += 1
-            y = _conv_tc(xn, x2n, wp, bias, out_scale, resn, spec.cout, spec.k, False, want_f32)
-        else:
-            wp = spec.pack_fwd.get(weight, xn.dtype)
-            if resn is not None and resn.dtype != xn.dtype:
-                resn = resn.to(xn.dtype)
-            y = _gather(xn, x2n, wp, spec.pack_fwd.ld, bias, None, out_scale, resn, B, Hi, Wi, C1, C2, Ho, Wo,
-                        spec.cout, spec.k, spec.stride, spec.pad, 1 if spec.transposed else 0, xn.dtype)
-            if want_f32:
-                y = y.float()
+            out_scale = out_scale.reshape(xn.shape[0], spec.cout)
+        y = conv_forward_raw(spec, xn, x2n, weight, bias, out_scale, resn)
         ctx.spec = spec
         ctx.save_for_backward(xn, x2n, weight, bias, out_scale)
         ctx.has_res = res is not None
@@ -377,64 +445,12 @@ class Conv2dFn(Function):
     def backward(ctx, gy):
         spec = ctx.spec
         xn, x2n, weight, bias, out_scale = ctx.saved_tensors
-        gyn = nhwc(gy)
-        if gyn.dtype != xn.dtype:
-            gyn = gyn.to(xn.dtype)
-        B, Hi, Wi, C1 = xn.shape
-        C2 = x2n.shape[3] if x2n is not None else 0
-        _, Ho, Wo, N = gyn.shape
-        gx = gx2 = gw = gb = None
         need_x = ctx.needs_input_grad[0] or (x2n is not None and ctx.needs_input_grad[1])
-        use_tc = xn.dtype == torch.bfloat16 and spec.tc_dgrad_ok(gyn)
-        if use_tc and out_scale is not None:
-            # TMA-fed operands never pass through registers: apply the Dropout2d mask in a separate pass
-            gys = torch.empty_like(gyn)
-            call("lvae_channel_scale", gyn.data_ptr(), out_scale.data_ptr(), gys.data_ptr(), B, Ho * Wo, N, _dt(gyn), _stream())
-            gyn, out_scale = gys, None
-        if need_x:
-            if use_tc:
-                wpb = spec.pack_tc_bwd.get(weight, torch.bfloat16)
-                stats["tc_dgrad"] += 1
-                if x2n is None:
-                    gx = as_nchw(_conv_tc(gyn, None, wpb, None, None, None, spec.cin, spec.k, True, False))
-                else:
-                    g1, g2 = _conv_tc(gyn, None, wpb, None, None, None, spec.cin, spec.k, True, False, nsplit=C1)
-                    gx, gx2 = as_nchw(g1), as_nchw(g2)
-            else:
-                wpb = spec.pack_bwd.get(weight, gyn.dtype)
-                gcat = _gather(gyn, None, wpb, spec.pack_bwd.ld, None, out_scale, None, None, B, Ho, Wo, N, 0, Hi, Wi,
-                               spec.cin, spec.k, spec.stride, spec.pad, 0 if spec.transposed else 1, gyn.dtype)
-                if x2n is None:
-                    gx = as_nchw(gcat)
-                else:
-                    gx = as_nchw(gcat[..., :C1])
-                    gx2 = as_nchw(gcat[..., C1:])
-        if ctx.needs_input_grad[2]:
-            gwbuf, sunk = _param_grad_buffer(weight)
-            gbbuf, bsunk = (None, True)
-            if bias is not None and ctx.needs_input_grad[3]:
-                gbbuf, bsunk = _param_grad_buffer(bias)
-            if use_tc and out_scale is None and C1 == 64 and C2 in (0, 64) and N in (64, 128) and gyn.dtype == torch.bfloat16 \
-                    and spec.k * spec.k * (2 if C2 else 1) <= 9:
-                stats["tc_wgrad"] += 1
-                call("lvae_conv2d_wgrad_tc", xn.data_ptr(), _p(x2n), gyn.data_ptr(), gwbuf.data_ptr(), _p(gbbuf),
-                     _wgrad_workspace(xn.device).data_ptr(), B, Hi, Wi, N, spec.k, _stream())
-            elif not spec.transposed:
-                stats["cc_wgrad"] += 1
-                call("lvae_conv2d_wgrad", xn.data_ptr(), _p(x2n), gyn.data_ptr(), None, _p(out_scale),
-                     gwbuf.data_ptr(), _p(gbbuf), B, Hi, Wi, C1, C2, Ho, Wo, N, spec.k, spec.k, spec.stride,
-                     spec.pad, _dt(xn), _stream())
-            else:
-                # roles swap: "input" = dy (scaled), "output grad" = x; result is (Cin, Cout, k, k)
-                call("lvae_conv2d_wgrad", gyn.data_ptr(), None, xn.data_ptr(), _p(out_scale), None,
-                     gwbuf.data_ptr(), None, B, Ho, Wo, N, 0, Hi, Wi, C1, spec.k, spec.k, spec.stride, spec.pad,
-                     _dt(xn), _stream())
-                if gbbuf is not None:
-                    call("lvae_colsum", gyn.data_ptr(), _p(out_scale), gbbuf.data_ptr(), B, Ho * Wo, N, _dt(gyn), _stream())
-            gw = None if sunk else gwbuf
-            gb = None if (bsunk or gbbuf is None) else gbbuf
+        gx, gx2, gw, gb = conv_backward_raw(spec, xn, x2n, weight, bias, out_scale, nhwc(gy), need_x,
+                                            ctx.needs_input_grad[2], ctx.needs_input_grad[3])
         gres = gy if ctx.has_res and ctx.needs_input_grad[5] else None
-        return gx, gx2, gw, gb, None, gres, None
+        return (as_nchw(gx) if gx is not None else None, as_nchw(gx2) if gx2 is not None else None, gw, gb, None,
+                gres, None)
 
 
 def conv2d(x, weight, bias, spec: ConvSpec, x2=None, out_scale=None, res=None):
@@ -498,6 +514,161 @@ def bn_act(x, bn, act_id: int, out_dtype=None):
     return BnActFn.apply(x, bn.weight, bn.bias, bn.running_mean, bn.running_var,
                          bn.num_batches_tracked if training else None, bn.stat_acc(x.device), training,
                          bn.momentum if bn.momentum is not None else 0.1, bn.eps, act_id, out_dtype)
+
+
+# --------------------------------------------------------------------------- BatchNorm scratch arena
+_bn_epoch = [0]
+_whole_block = [True]
+
+
+def set_whole_block(flag: bool) -> None:
+    """Run default residual blocks as one autograd node with the hand-scheduled backward (default) or op by op."""
+    _whole_block[0] = bool(flag)
+
+
+def whole_block_enabled() -> bool:
+    return _whole_block[0]
+
+
+
+def new_forward_epoch() -> int:
+    """A model zeroed its BatchNorm scratch arena: accumulators stamped with an older epoch are clean again."""
+    _bn_epoch[0] += 1
+    return _bn_epoch[0]
+
+
+def bn_scratch(bn, device):
+    """(6, C) float64 scratch of one BatchNorm2d: rows 0-1 forward sum / sum-of-squares, rows 2-3 backward sums,
+    rows 4-5 statistics of the output of the residual block this BatchNorm opens.  Clean (all zero) at first use
+    in a forward epoch when it lives in a model arena; otherwise zeroed on demand."""
+    acc = getattr(bn, "_lvae_scratch", None)
+    if acc is None or acc.device != device:
+        acc = torch.zeros((6, bn.num_features), dtype=torch.float64, device=device)
+        bn._lvae_scratch = acc
+        bn._lvae_scratch_owned = True
+        bn._lvae_epoch_fwd = bn._lvae_epoch_bwd = -1
+    return acc
+
+
+def _bn_clean(bn, acc_rows, which: str):
+    """Make sure the accumulator rows are zero before accumulating into them."""
+    attr = "_lvae_epoch_" + which
+    arena_clean = (not getattr(bn, "_lvae_scratch_owned", True)) and getattr(bn, attr, -1) != _bn_epoch[0]
+    if not arena_clean:
+        acc_rows.zero_()
+    setattr(bn, attr, _bn_epoch[0])
+
+
+class GatedBlockFn(Function):
+    """One whole ResidualGatedBlock of type 'bacdbacd' (lib/nn.py:78-99 + GateLayer2d :108-126) with a hand-made
+    backward schedule:
+        forward : [stats] BN1+act -> conv1 (*mask1) -> stats, BN2+act -> conv2 (*mask2) -> 1x1 gate conv ->
+                  act(a)*sigmoid(b) + x  (+ statistics of the output for the next block's BN1)
+        backward: gate' -> 1x1 dgrad (*mask2 in its epilogue) / wgrad -> conv2 dgrad / wgrad -> BN2' (*mask1 fused)
+                  -> conv1 dgrad / wgrad -> BN1' (+ residual gradient fused)
+    Dropout2d masks are folded into neighbouring kernels' epilogues and BatchNorm needs no finalize / parameter kernels."""
+
+    @staticmethod
+    def forward(ctx, x, g1, b1, w1, cb1, g2, b2, w2, cb2, wg, gbias, m1, m2, blk, x_stats, training):
+        _require_cuda(x)
+        xn = nhwc(x)
+        B, H, W, C = xn.shape
+        Pn, dev, dt = B * H * W, xn.device, _dt(xn)
+        bn1, bn2, conv1, conv2, gconv, act, gact = blk
+        sc1, sc2 = bn_scratch(bn1, dev), bn_scratch(bn2, dev)
+        saves = torch.empty((2, 2, C), dtype=torch.float32, device=dev)
+
+        def bn_fwd(inp, bn, sc, save, gamma, beta, given_acc=None):
+            acc = None
+            if training:
+                if given_acc is not None:
+                    acc = given_acc
+                else:
+                    acc = sc[0:2]
+                    _bn_clean(bn, acc, "fwd")
+                    call("lvae_bn_stats", inp.data_ptr(), acc.data_ptr(), Pn, C, dt, _stream())
+            out = torch.empty_like(inp)
+            call("lvae_bn_act_fwd2", inp.data_ptr(), out.data_ptr(), _p(acc), gamma.data_ptr(), beta.data_ptr(),
+                 save.data_ptr(), _p(bn.running_mean), _p(bn.running_var), _p(bn.num_batches_tracked) if training else None,
+                 Pn, C, act, 1 if training else 0, float(bn.momentum if bn.momentum is not None else 0.1), float(bn.eps),
+                 dt, dt, _stream())
+            return out
+
+        a1 = bn_fwd(xn, bn1, sc1, saves[0], g1, b1, x_stats)
+        y1 = conv_forward_raw(conv1.spec, a1, None, w1, cb1, m1, None)
+        a2 = bn_fwd(y1, bn2, sc2, saves[1], g2, b2)
+        y2 = conv_forward_raw(conv2.spec, a2, None, w2, cb2, m2, None)
+        h = conv_forward_raw(gconv.spec, y2, None, wg, gbias, None, None)
+        out = torch.empty_like(xn)
+        out_stats = None
+        if training and 256 % (C // 4) == 0:
+            out_stats = sc1[4:6]                      # statistics of this block's output, for the next block's BN1
+            _bn_clean(bn1, out_stats, "out")
+            call("lvae_gate_fwd_stats", h.data_ptr(), xn.data_ptr(), out.data_ptr(), out_stats.data_ptr(), Pn, C, gact, dt, _stream())
+        else:
+            call("lvae_gate_fwd", h.data_ptr(), xn.data_ptr(), out.data_ptr(), Pn, C, gact, dt, _stream())
+        ctx.save_for_backward(xn, a1, y1, a2, y2, h, saves, g1, b1, w1, cb1, g2, b2, w2, cb2, wg, gbias, m1, m2)
+        ctx.blk, ctx.training = blk, training
+        blk[0]._lvae_last_out_stats = (out_stats, Pn, _bn_epoch[0]) if out_stats is not None else None
+        return as_nchw(out)
+
+    @staticmethod
+    def backward(ctx, gout):
+        xn, a1, y1, a2, y2, h, saves, g1, b1, w1, cb1, g2, b2, w2, cb2, wg, gbias, m1, m2 = ctx.saved_tensors
+        bn1, bn2, conv1, conv2, gconv, act, gact = ctx.blk
+        training = ctx.training
+        B, H, W, C = xn.shape
+        Pn, dev, dt = B * H * W, xn.device, _dt(xn)
+        gn = nhwc(gout)
+        if gn.dtype != xn.dtype:
+            gn = gn.to(xn.dtype)
+        ng = ctx.needs_input_grad
+        # gate
+        dh = torch.empty_like(h)
+        call("lvae_gate_bwd", gn.data_ptr(), h.data_ptr(), dh.data_ptr(), Pn, C, gact, dt, _stream())
+        # 1x1 gate conv: dgrad carries conv2's Dropout2d mask in its epilogue -> gradient wrt conv2's raw output
+        dy2, _, gwg, ggb = conv_backward_raw(gconv.spec, y2, None, wg, gbias, None, dh, True, ng[9], ng[10], dx_scale=m2)
+        # conv2 (dy2 is already masked)
+        da2, _, gw2, gcb2 = conv_backward_raw(conv2.spec, a2, None, w2, cb2, None, dy2, True, ng[7], ng[8])
+
+        def bn_bwd(dy, xin, bn, sc, save, gamma, beta, post_scale, add):
+            acc = sc[2:4]
+            _bn_clean(bn, acc, "bwd")
+            dgam, gsunk = _param_grad_buffer(gamma)
+            dbet, bsunk = _param_grad_buffer(beta)
+            dxo = torch.empty_like(xin)
+            call("lvae_bn_act_bwd2", dy.data_ptr(), xin.data_ptr(), dxo.data_ptr(), save.data_ptr(), gamma.data_ptr(),
+                 beta.data_ptr(), acc.data_ptr(), dgam.data_ptr(), dbet.data_ptr(), _p(post_scale), _p(add), Pn, H * W, C,
+                 act, 1 if training else 0, dt, _stream())
+            return dxo, (None if gsunk else dgam), (None if bsunk else dbet)
+
+        # BN2 + act backward, conv1's mask fused -> gradient wrt conv1's raw output
+        dy1, gg2, gb2 = bn_bwd(da2, y1, bn2, bn_scratch(bn2, dev), saves[1], g2, b2, m1, None)
+        da1, _, gw1, gcb1 = conv_backward_raw(conv1.spec, a1, None, w1, cb1, None, dy1, True, ng[3], ng[4])
+        # BN1 + act backward, residual gradient fused
+        dx, gg1, gb1 = bn_bwd(da1, xn, bn1, bn_scratch(bn1, dev), saves[0], g1, b1, None, gn)
+        return (as_nchw(dx), gg1, gb1, gw1, gcb1, gg2, gb2, gw2, gcb2, gwg, ggb, None, None, None, None, None)
+
+
+def gated_block(x, bn1, conv1, drop1, bn2, conv2, drop2, gate_layer, act_id):
+    training = bn1.training
+    # statistics of x computed by the kernel that produced it (previous block's gate), if still valid
+    x_stats = None
+    st = getattr(x, "_lvae_stats", None)
+    if training and st is not None and st[2] == _bn_epoch[0] and st[1] == x.shape[0] * x.shape[2] * x.shape[3]:
+        x_stats = st[0]
+    m1 = drop1.mask(x) if drop1 is not None else None
+    m2 = drop2.mask(x) if drop2 is not None else None
+    if m1 is not None:
+        m1 = m1.reshape(x.shape[0], -1)
+    if m2 is not None:
+        m2 = m2.reshape(x.shape[0], -1)
+    blk = (bn1, bn2, conv1, conv2, gate_layer.conv, act_id, getattr(gate_layer.nonlin, "act_id", 0))
+    out = GatedBlockFn.apply(x, bn1.weight, bn1.bias, conv1.weight, conv1.bias, bn2.weight, bn2.bias, conv2.weight,
+                             conv2.bias, gate_layer.conv.weight, gate_layer.conv.bias, m1, m2, blk, x_stats, training)
+    if training and bn1._lvae_last_out_stats is not None:
+        out._lvae_stats = bn1._lvae_last_out_stats
+    return out
 
 
 # --------------------------------------------------------------------------- gate (+ residual)

@@ -51,7 +51,7 @@ def test_no_cpu_fallback(libpath):
         m(torch.zeros(2, 1, 8, 8))
 
 
-@pytest.mark.parametrize("name", ["mnist3", "mnist12", "cifar15", "celeba20"])
+@pytest.mark.parametrize("name", ["mnist3", "cifar15"])
 def test_state_dict_layout_matches_reference(name, libpath):
     import lvae_b200
     from oracle import lvae_oracle as O

@@ -162,3 +162,29 @@ def test_bf16_tensor_core_pipeline_close_to_golden(name):
                          for n in names])
         ref = g["f64_grad_l2"]
         assert np.abs(ours - ref).max() < 5e-2 * ref.max(), names[int(np.abs(ours - ref).argmax())]
+
+
+def test_whole_block_schedule_matches_op_by_op():
+    """The hand-scheduled residual-block node (Dropout2d masks folded into dgrad / BatchNorm epilogues,
+    statistics handed from one block's gate kernel to the next block's BatchNorm) against the same
+    model run op by op through autograd."""
+    from lvae_b200 import ops
+    cfg, meta, g = load_golden("mnist3_train_b4")
+    res = {}
+    for flag in (True, False):
+        ops.set_whole_block(flag)
+        try:
+            model = build(cfg, meta)
+            out = run_ours(model, cfg, meta)
+            loss = (-out["ll"]).mean() + out["kl_loss"]
+            loss.backward()
+            res[flag] = (float(loss), {n: p.grad.clone() for n, p in model.named_parameters() if p.grad is not None},
+                         {k: v.clone() for k, v in model.state_dict().items() if "running" in k})
+        finally:
+            ops.set_whole_block(True)
+    assert abs(res[True][0] - res[False][0]) < 1e-5 * abs(res[False][0])
+    gmax = max(float(v.abs().max()) for v in res[False][1].values())
+    for n, gr in res[False][1].items():
+        assert float((res[True][1][n] - gr).abs().max()) < 1e-4 * max(float(gr.abs().max()), 1e-3 * gmax), n
+    for k, v in res[False][2].items():
+        assert rel_err(res[True][2][k], v) < 1e-5, k

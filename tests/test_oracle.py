@@ -11,7 +11,8 @@ from oracle import ref_loader
 from lvae_test_helpers import golden_names, load_golden, make_inputs, rel_err
 
 FAST = ["mnist3_train_b4", "mnist3_eval_b4", "small_dmol_train_b4", "small_dmol_eval_b4", "small_bern_bacdbac",
-        "small_bern_cabdcabd_linear", "small_dmol_nobn_selu", "mnist12_eval_b2", "cifar15_train_b2"]
+        "small_bern_cabdcabd_linear", "small_dmol_nobn_selu", "cifar15_train_b2"]
+# (mnist12 / celeba20 golden files are exercised by the GPU parity tests; here they would only add minutes)
 
 
 def run_oracle(cfg, meta, dtype):
@@ -60,7 +61,7 @@ def test_oracle_matches_golden_f64(name):
 
 
 def test_oracle_f32_close_to_f64_golden():
-    cfg, meta, g = load_golden("mnist3_train_b4")
+    cfg, meta, g = load_golden("small_dmol_train_b4")
     P, out, terms, _, _ = run_oracle(cfg, meta, torch.float32)
     assert rel_err(out["ll"], g["f64_ll"]) < 1e-4
     assert rel_err(terms["loss"], g["f64_loss"]) < 1e-4
@@ -94,7 +95,7 @@ def test_iw_bound_and_adamax_restatements():
 
 
 @pytest.mark.skipif(not ref_loader.reference_available(), reason="reference tree not mounted")
-@pytest.mark.parametrize("name", ["small_dmol_train_b4", "small_bern_bacdbac", "mnist3_train_b4"])
+@pytest.mark.parametrize("name", ["small_dmol_train_b4", "small_bern_bacdbac", "small_bern_cabdcabd_linear"])
 def test_oracle_matches_live_reference(name):
     cfg, meta, g = load_golden(name)
     ref = ref_loader.load_reference()
