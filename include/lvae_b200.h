@@ -61,7 +61,7 @@ int lvae_conv2d_tc(const void* x, const void* x2, const void* wp, const float* b
  * dy (B,H,W,N) bf16 with N in {64,128} (already multiplied by the Dropout2d mask); dw (N,I,k,k) fp32 +=,
  * dbias [N] += or NULL; ws = lvae_wgrad_tc_workspace(...) floats of scratch for the per-CTA partials. */
 int lvae_conv2d_wgrad_tc(const void* x, const void* x2, const void* dy, float* dw, float* dbias, float* ws, int B,
-                         int H, int W, int N, int ksize, lvae_stream_t stream);
+                         int H, int W, int N, int ksize, int I_real, lvae_stream_t stream);
 long long lvae_wgrad_tc_workspace(int B, int H, int W, int N, int ksize, int two_inputs);
 /* y = x * scale[b,c] (Dropout2d mask on a gradient tensor ahead of the TMA-fed dgrad) */
 int lvae_channel_scale(const void* x, const float* scale, void* y, int B, int HW, int C, int dtype,
@@ -134,10 +134,10 @@ int lvae_sum_batch(const float* x, float* out, int B, long long n, int accumulat
  * q, p: (B,hw,2Z) fp32 rows [mu | logvar]; p_broadcast = 1 when p has batch 1 (learned top prior,
  * models/lvae_layers.py:131-136).  z = mu_q + exp(lv_q/2)*eps with eps given, or Philox when eps == NULL;
  * forced != NULL -> z = forced; use_mode -> z = mu.  q == NULL -> sample from p (generation).
- * Outputs: z (B,hw,Z) [+ optional bf16 copy], kl_sample (B) (MC log q - log p, or analytic),
+ * Outputs: z (B,hw,Z) [+ optional bf16 copy with row pitch z_bf16_pitch >= Z, zero padded], kl_sample (B) (MC log q - log p, or analytic),
  * kl_spatial (B,hw) (always analytic), logp (B), logq (B). */
 int lvae_stoch_fwd(const float* q, const float* p, int p_broadcast, const float* eps, const float* forced,
-                   const void* rng_state, unsigned long long stream_id, float* z, void* z_bf16, float* kl_sample,
+                   const void* rng_state, unsigned long long stream_id, float* z, void* z_bf16, int z_bf16_pitch, float* kl_sample,
                    float* kl_spatial, float* logp, float* logq, int B, int hw, int Z, int use_mode, int analytical,
                    lvae_stream_t stream);
 /* z_kind: 1 reparameterised sample, 2 mode, 0 forced latent.  dq, dp: (B,hw,2Z). */

@@ -23,7 +23,7 @@ _SIGNATURES = {
     "lvae_pack_weights": [P, I, P],
     "lvae_conv2d_tc": [P, P, P, P, P, P, P, P, I, I, I, I, I, I, I, I, I, P],
     "lvae_channel_scale": [P, P, P, I, I, I, I, P],
-    "lvae_conv2d_wgrad_tc": [P, P, P, P, P, P, I, I, I, I, I, P],
+    "lvae_conv2d_wgrad_tc": [P, P, P, P, P, P, I, I, I, I, I, I, P],
     "lvae_colsum": [P, P, P, I, I, I, I, P],
     "lvae_bn_stats": [P, P, L, I, I, P],
     "lvae_bn_finalize": [P, P, P, P, P, P, L, I, F, F, P],
@@ -41,7 +41,7 @@ _SIGNATURES = {
     "lvae_dropout_masks": [P, L, F, P, U, P],
     "lvae_rng_advance": [P, U, P],
     "lvae_sum_batch": [P, P, I, L, I, P],
-    "lvae_stoch_fwd": [P, P, I, P, P, P, U, P, P, P, P, P, P, I, I, I, I, I, P],
+    "lvae_stoch_fwd": [P, P, I, P, P, P, U, P, P, I, P, P, P, P, I, I, I, I, I, P],
     "lvae_stoch_bwd": [P, P, I, P, P, P, P, P, P, P, P, I, I, I, I, I, P],
     "lvae_bernoulli_fwd": [P, P, P, P, I, I, I, P],
     "lvae_bernoulli_bwd": [P, P, P, P, P, I, I, I, P],

@@ -580,48 +580,44 @@ __global__ void bn_act_fwd2_kernel(const TI* __restrict__ x, TO* __restrict__ y,
                                    float* __restrict__ save, float* running_mean, float* running_var,
                                    long long* nbt, long long nquads, long long P, int C, int act, int training,
                                    float momentum, float eps) {
+  __shared__ float s_scale[256], s_shift[256];       // y = act(x * scale + shift), C <= 256
   const int CV = C >> 2;
+  // one thread per channel derives the statistics (the only double-precision math in the kernel)
+  for (int ch = threadIdx.x; ch < C; ch += blockDim.x) {
+    float mean, rstd;
+    if (training) {
+      double m = acc[ch] / (double)P;
+      double var = acc[C + ch] / (double)P - m * m;
+      if (var < 0.0) var = 0.0;
+      mean = (float)m;
+      rstd = rsqrtf((float)var + eps);
+      if (blockIdx.x == 0 && running_mean) {
+        double unb = P > 1 ? var * (double)P / (double)(P - 1) : var;
+        running_mean[ch] = (float)((1.0 - momentum) * (double)running_mean[ch] + momentum * m);
+        running_var[ch] = (float)((1.0 - momentum) * (double)running_var[ch] + momentum * unb);
+      }
+    } else {
+      mean = running_mean[ch];
+      rstd = rsqrtf(running_var[ch] + eps);
+    }
+    if (blockIdx.x == 0) {
+      save[ch] = mean;
+      save[C + ch] = rstd;
+    }
+    float sc = rstd * gamma[ch];
+    s_scale[ch] = sc;
+    s_shift[ch] = beta[ch] - mean * sc;
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0 && training && nbt) *nbt += 1;
+  __syncthreads();
   const long long stride = (long long)gridDim.x * blockDim.x;      // multiple of CV by construction
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const int c = (int)(i % CV) * 4;
-  float m[4], r[4], g[4], b[4];
-#pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    if (training) {
-      double mean = acc[c + j] / (double)P;
-      double var = acc[C + c + j] / (double)P - mean * mean;
-      if (var < 0.0) var = 0.0;
-      m[j] = (float)mean;
-      r[j] = (float)(1.0 / sqrt(var + (double)eps));
-    } else {
-      m[j] = running_mean[c + j];
-      r[j] = 1.0f / sqrtf(running_var[c + j] + eps);
-    }
-    g[j] = gamma[c + j];
-    b[j] = beta[c + j];
-  }
-  if (blockIdx.x == 0 && threadIdx.x < CV) {
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      save[c + j] = m[j];
-      save[C + c + j] = r[j];
-      if (training && running_mean) {
-        double mean = acc[c + j] / (double)P;
-        double var = acc[C + c + j] / (double)P - mean * mean;
-        if (var < 0.0) var = 0.0;
-        double unb = P > 1 ? var * (double)P / (double)(P - 1) : var;
-        running_mean[c + j] = (float)((1.0 - momentum) * (double)running_mean[c + j] + momentum * mean);
-        running_var[c + j] = (float)((1.0 - momentum) * (double)running_var[c + j] + momentum * unb);
-      }
-    }
-    if (threadIdx.x == 0 && training && nbt) *nbt += 1;
-  }
+  const float4 sc4 = *reinterpret_cast<const float4*>(s_scale + c), sh4 = *reinterpret_cast<const float4*>(s_shift + c);
   for (; i < nquads; i += stride) {
     float4 v = ld4<TI>(x + i * 4);
-    float o[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-    for (int j = 0; j < 4; ++j) o[j] = act_fwd((o[j] - m[j]) * r[j] * g[j] + b[j], act);
-    st4<TO>(y + i * 4, make_float4(o[0], o[1], o[2], o[3]));
+    st4<TO>(y + i * 4, make_float4(act_fwd(v.x * sc4.x + sh4.x, act), act_fwd(v.y * sc4.y + sh4.y, act),
+                                   act_fwd(v.z * sc4.z + sh4.z, act), act_fwd(v.w * sc4.w + sh4.w, act)));
   }
 }
 
@@ -725,6 +721,13 @@ LVAE_API int lvae_bn_act_bwd2(const void* dy, const void* x, void* dx, const flo
   return LVAE_OK;
 }
 
+template <typename T> __device__ __forceinline__ float4 round_as(float4 v);
+template <> __device__ __forceinline__ float4 round_as<float>(float4 v) { return v; }
+template <> __device__ __forceinline__ float4 round_as<__nv_bfloat16>(float4 v) {
+  return make_float4(__bfloat162float(__float2bfloat16(v.x)), __bfloat162float(__float2bfloat16(v.y)),
+                     __bfloat162float(__float2bfloat16(v.z)), __bfloat162float(__float2bfloat16(v.w)));
+}
+
 // gate forward that also accumulates the per-channel sum / sum of squares of its OUTPUT (the next
 // residual block's first BatchNorm then needs no statistics pass of its own)
 template <typename T>
@@ -747,7 +750,7 @@ __global__ void gate_fwd_stats_kernel(const T* __restrict__ h, const T* __restri
       o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
     }
     st4<T>(out + i * 4, o);
-    float4 q = ld4<T>(out + i * 4);        // statistics of the value as stored (bf16-rounded on the bf16 path)
+    float4 q = round_as<T>(o);             // statistics of the value as stored (bf16-rounded on the bf16 path)
     s.x += q.x; s.y += q.y; s.z += q.z; s.w += q.w;
     ss.x += q.x * q.x; ss.y += q.y * q.y; ss.z += q.z * q.z; ss.w += q.w * q.w;
   }

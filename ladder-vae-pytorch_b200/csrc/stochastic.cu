@@ -20,7 +20,8 @@ struct StochArgs {
   const PhiloxState* rng;
   unsigned long long stream_id;
   float* z;             // (B,hw,Z)
-  void* z_lp;           // optional bf16 copy of z (input of conv_out on the bf16 path)
+  void* z_lp;           // optional bf16 copy of z (input of conv_out on the bf16 path), row pitch z_lp_pitch >= Z, zero padded
+  int z_lp_pitch;
   float* kl_sample;     // (B) or null when q == null
   float* kl_spatial;    // (B,hw) or null
   float* logp;          // (B)
@@ -103,12 +104,17 @@ __global__ void __launch_bounds__(256) stoch_fwd_kernel(StochArgs a) {
         }
         if (VEC == 4) {
           *reinterpret_cast<float4*>(a.z + zi) = make_float4(zz[0], zz[1], zz[2], zz[3]);
-          if (a.z_lp) st4<__nv_bfloat16>((__nv_bfloat16*)a.z_lp + zi, make_float4(zz[0], zz[1], zz[2], zz[3]));
+          if (a.z_lp) st4<__nv_bfloat16>((__nv_bfloat16*)a.z_lp + ((long long)b * a.hw + pix) * a.z_lp_pitch + c, make_float4(zz[0], zz[1], zz[2], zz[3]));
         } else {
           a.z[zi] = zz[0];
-          if (a.z_lp) ((__nv_bfloat16*)a.z_lp)[zi] = __float2bfloat16(zz[0]);
+          if (a.z_lp) ((__nv_bfloat16*)a.z_lp)[((long long)b * a.hw + pix) * a.z_lp_pitch + c] = __float2bfloat16(zz[0]);
         }
       }
+    }
+    // zero padding of the low-precision copy (channels Z .. pitch)
+    if (pvalid && a.z_lp) {
+      __nv_bfloat16* zr = (__nv_bfloat16*)a.z_lp + ((long long)b * a.hw + pix) * a.z_lp_pitch;
+      for (int cz = a.Z + gl; cz < a.z_lp_pitch; cz += G) zr[cz] = __float2bfloat16(0.f);
     }
     // per-pixel channel reduction inside the lane group
     for (int o = G >> 1; o > 0; o >>= 1) kls += __shfl_xor_sync(0xffffffffu, kls, o);
@@ -126,13 +132,14 @@ __global__ void __launch_bounds__(256) stoch_fwd_kernel(StochArgs a) {
 }
 
 LVAE_API int lvae_stoch_fwd(const float* q, const float* p, int p_broadcast, const float* eps, const float* forced,
-                            const void* rng_state, unsigned long long stream_id, float* z, void* z_bf16,
+                            const void* rng_state, unsigned long long stream_id, float* z, void* z_bf16, int z_bf16_pitch,
                             float* kl_sample, float* kl_spatial, float* logp, float* logq, int B, int hw, int Z,
                             int use_mode, int analytical, cudaStream_t stream) {
   LVAE_REQUIRE(p && z && logp && B > 0 && hw > 0 && Z > 0, "stoch_fwd: bad args");
   LVAE_REQUIRE(eps || forced || use_mode || rng_state, "stoch_fwd: need eps, forced latent, mode, or an RNG state");
+  LVAE_REQUIRE(!z_bf16 || (z_bf16_pitch >= Z && z_bf16_pitch % 4 == 0), "stoch_fwd: bad low-precision pitch");
   StochArgs a{q, p, p_broadcast ? 0LL : (long long)hw * 2 * Z, eps, forced, (const PhiloxState*)rng_state, stream_id,
-              z, z_bf16, kl_sample, kl_spatial, logp, logq, B, hw, Z, use_mode, analytical};
+              z, z_bf16, z_bf16_pitch, kl_sample, kl_spatial, logp, logq, B, hw, Z, use_mode, analytical};
   if (Z % 4 == 0) stoch_fwd_kernel<4><<<B, 256, 0, stream>>>(a);
   else stoch_fwd_kernel<1><<<B, 256, 0, stream>>>(a);
   LVAE_COUNT_LAUNCH();

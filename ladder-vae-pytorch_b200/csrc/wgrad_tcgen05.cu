@@ -230,7 +230,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
 //   ones:                              dbias[co] += sum (row 0 of the block only)
 struct RedParams {
   const float* ws; float* dw; float* dbias;
-  int n_cta, n_pairs, N, I, taps;
+  int n_cta, n_pairs, N, I, taps, I_real;
   int8_t kind[2 * WG_MAX_PAIRS];     // 0 tap block, 1 ones, 2 unused
   int8_t tap[2 * WG_MAX_PAIRS], ci0_blk[2 * WG_MAX_PAIRS];
 };
@@ -246,6 +246,7 @@ __global__ void wgrad_reduce_kernel(RedParams p) {
   const int blk = pr * 2 + (row >> 6);
   const int kind = p.kind[blk];
   if (kind == 2 || (kind == 1 && ((row & 63) != 0 || !p.dbias))) return;
+  if (kind == 0 && p.ci0_blk[blk] * 64 + (row & 63) >= p.I_real) return;      // zero-padded input channels
   const int chunk = (p.n_cta + gridDim.y - 1) / gridDim.y;
   const int c_beg = blockIdx.y * chunk, c_end = min(p.n_cta, c_beg + chunk);
   if (c_beg >= c_end) return;
@@ -261,7 +262,7 @@ __global__ void wgrad_reduce_kernel(RedParams p) {
   for (; c < c_end; ++c) s0 += __ldg(src + (size_t)c * per);
   const float s = (s0 + s1) + (s2 + s3);
   float* dst = kind == 1 ? p.dbias + co
-                         : p.dw + ((size_t)co * p.I + p.ci0_blk[blk] * 64 + (row & 63)) * p.taps + p.tap[blk];
+                         : p.dw + ((size_t)co * p.I_real + p.ci0_blk[blk] * 64 + (row & 63)) * p.taps + p.tap[blk];
   if (gridDim.y == 1) *dst += s;
   else atomicAdd(dst, s);
 }
@@ -301,9 +302,10 @@ LVAE_API long long lvae_wgrad_tc_workspace(int B, int H, int W, int N, int ksize
 }
 
 // x, x2: (B,H,W,64) bf16 (x2 optional); dy: (B,H,W,N) bf16, N in {64,128}, already multiplied by any Dropout2d mask.
-// dw: (N, I, k, k) fp32 (+=), I = 64 or 128 (two inputs); dbias: [N] fp32 (+=) or NULL.  ws: workspace (see above).
+// dw: (N, I_real, k, k) fp32 (+=); I_real <= 64 * inputs (x may carry zero-padded channels beyond I_real, 0 = no padding);
+// dbias: [N] fp32 (+=) or NULL.  ws: workspace (see above).
 LVAE_API int lvae_conv2d_wgrad_tc(const void* x, const void* x2, const void* dy, float* dw, float* dbias, float* ws,
-                                  int B, int H, int W, int N, int ksize, cudaStream_t stream) {
+                                  int B, int H, int W, int N, int ksize, int I_real, cudaStream_t stream) {
   LVAE_REQUIRE(x && dy && dw && ws, "conv2d_wgrad_tc: null pointer");
   LVAE_REQUIRE((N == 64 || N == 128) && (ksize == 1 || ksize == 3), "conv2d_wgrad_tc: N must be 64 or 128, ksize 1 or 3");
   LVAE_REQUIRE((W & (W - 1)) == 0 && (H & (H - 1)) == 0 && W <= 128, "conv2d_wgrad_tc: H and W must be powers of two (W <= 128)");
@@ -358,7 +360,7 @@ LVAE_API int lvae_conv2d_wgrad_tc(const void* x, const void* x2, const void* dy,
   wgrad_tc_kernel<<<grid, WG_THREADS_TC, smem, stream>>>(tmX, tmX2, tmDY, p);
   LVAE_COUNT_LAUNCH();
   LVAE_CHECK_LAUNCH("conv2d_wgrad_tc");
-  rp.ws = ws; rp.dw = dw; rp.dbias = dbias; rp.n_cta = grid; rp.n_pairs = p.n_pairs; rp.N = N; rp.I = 64 * inputs; rp.taps = taps;
+  rp.ws = ws; rp.dw = dw; rp.dbias = dbias; rp.n_cta = grid; rp.n_pairs = p.n_pairs; rp.N = N; rp.I = 64 * inputs; rp.taps = taps; rp.I_real = I_real > 0 ? I_real : 64 * inputs;
   const int per = p.n_pairs * 128 * N;
   const int ysplit = grid >= 64 ? 8 : (grid >= 16 ? 4 : 1);
   wgrad_reduce_kernel<<<dim3((per + 255) / 256, ysplit), 256, 0, stream>>>(rp);

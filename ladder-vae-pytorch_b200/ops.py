@@ -343,9 +343,12 @@ def conv_forward_raw(spec: ConvSpec, xn, x2n, weight, bias, out_scale, resn):
     the tensor cores (lvae_conv2d_tc), everything else on the CUDA-core implicit GEMM (lvae_conv2d_gather)."""
     B, Hi, Wi, C1 = xn.shape
     C2 = x2n.shape[3] if x2n is not None else 0
-    assert C1 + C2 == spec.cin, "conv input channels %d+%d != %d" % (C1, C2, spec.cin)
+    padded = x2n is None and C1 > spec.cin          # zero-padded input channels (bf16 copy of z): tensor-core path only
+    assert padded or C1 + C2 == spec.cin, "conv input channels %d+%d != %d" % (C1, C2, spec.cin)
     Ho, Wo = spec.out_hw(Hi, Wi)
     want_f32 = spec.out_fp32 and xn.dtype == torch.bfloat16
+    if padded and not spec.tc_forward_ok(xn, x2n):
+        xn, C1 = xn[..., :spec.cin].contiguous(), spec.cin
     if spec.tc_forward_ok(xn, x2n) and (resn is None or resn.dtype == (torch.float32 if want_f32 else torch.bfloat16)):
         wp = spec.pack_tc_fwd.get(weight, torch.bfloat16)
         stats["tc_fwd"] += 1
@@ -372,6 +375,9 @@ def conv_backward_raw(spec: ConvSpec, xn, x2n, weight, bias, out_scale, gyn, nee
     _, Ho, Wo, N = gyn.shape
     gx = gx2 = gw = gb = None
     use_tc = xn.dtype == torch.bfloat16 and spec.tc_dgrad_ok(gyn)
+    padded = x2n is None and C1 > spec.cin
+    if padded and not use_tc:
+        xn, C1, padded = xn[..., :spec.cin].contiguous(), spec.cin, False
     if use_tc and out_scale is not None:
         # TMA-fed operands never pass through registers: apply the Dropout2d mask in a separate pass
         gys = torch.empty_like(gyn)
@@ -383,6 +389,8 @@ def conv_backward_raw(spec: ConvSpec, xn, x2n, weight, bias, out_scale, gyn, nee
             stats["tc_dgrad"] += 1
             if x2n is None:
                 gx = _conv_tc(gyn, None, wpb, None, dx_scale, None, spec.cin, spec.k, True, False)
+                if padded:          # gradient wrt the zero-padded input: the padding channels get zeros
+                    gx = torch.nn.functional.pad(gx, (0, C1 - spec.cin))
             else:
                 assert dx_scale is None
                 gx, gx2 = _conv_tc(gyn, None, wpb, None, None, None, spec.cin, spec.k, True, False, nsplit=C1)
@@ -405,7 +413,7 @@ def conv_backward_raw(spec: ConvSpec, xn, x2n, weight, bias, out_scale, gyn, nee
                 and spec.k * spec.k * (2 if C2 else 1) <= 9:
             stats["tc_wgrad"] += 1
             call("lvae_conv2d_wgrad_tc", xn.data_ptr(), _p(x2n), gyn.data_ptr(), gwbuf.data_ptr(), _p(gbbuf),
-                 _wgrad_workspace(xn.device).data_ptr(), B, Hi, Wi, N, spec.k, _stream())
+                 _wgrad_workspace(xn.device).data_ptr(), B, Hi, Wi, N, spec.k, spec.cin if padded else 0, _stream())
         elif not spec.transposed:
             stats["cc_wgrad"] += 1
             call("lvae_conv2d_wgrad", xn.data_ptr(), _p(x2n), gyn.data_ptr(), None, _p(out_scale),
@@ -796,7 +804,9 @@ class StochasticFn(Function):
         epsn = nhwc(eps).float() if eps is not None else None
         forcedn = nhwc(forced).float() if forced is not None else None
         z = torch.empty((B, H, W, Z), dtype=torch.float32, device=dev)
-        z_lp = torch.empty((B, H, W, Z), dtype=torch.bfloat16, device=dev) if lowp_copy else None
+        # bf16 copy of z for conv_out, zero-padded to 64 channels so that the conv runs on the tensor cores
+        zp = 64 if (lowp_copy and Z < 64) else Z
+        z_lp = torch.empty((B, H, W, zp), dtype=torch.bfloat16, device=dev) if lowp_copy else None
         logp = torch.empty((B,), dtype=torch.float32, device=dev)
         if qn is not None:
             kl = torch.empty((B,), dtype=torch.float32, device=dev)
@@ -807,7 +817,7 @@ class StochasticFn(Function):
         need_rng = epsn is None and forcedn is None and not use_mode
         call("lvae_stoch_fwd", _p(qn), pn.data_ptr(), 1 if p_broadcast else 0, _p(epsn), _p(forcedn),
              rng_state(dev).data_ptr() if need_rng else None, next_stream_id() if need_rng else 0,
-             z.data_ptr(), _p(z_lp), _p(kl), _p(kls), logp.data_ptr(), _p(logq), B, hw, Z,
+             z.data_ptr(), _p(z_lp), zp, _p(kl), _p(kls), logp.data_ptr(), _p(logq), B, hw, Z,
              1 if use_mode else 0, 1 if analytical else 0, _stream())
         ctx.save_for_backward(qn, pn, z)
         ctx.meta = (B, hw, Z, p_broadcast, analytical, 0 if forced is not None else (2 if use_mode else 1))
@@ -825,7 +835,7 @@ class StochasticFn(Function):
         B, hw, Z, p_broadcast, analytical, z_kind = ctx.meta
         gz = nhwc(g_z).float() if g_z is not None else None
         if g_zlp is not None:       # gradient that arrived through the bf16 copy of z (input of conv_out)
-            gl = nhwc(g_zlp).float()
+            gl = nhwc(g_zlp)[..., :Z].float()
             gz = gl if gz is None else gz + gl
         cg = lambda t: t.contiguous().float() if t is not None else None
         g_kl, g_kls, g_logp, g_logq = cg(g_kl), cg(g_kls), cg(g_logp), cg(g_logq)
