@@ -227,6 +227,7 @@ def main():
                     help="bf16: bf16 activations, tcgen05 convs, fp32 accumulation (default); f32: exact fp32 CUDA-core path")
     ap.add_argument("--iw-full-forward", action="store_true",
                     help="IW: recompute the bottom-up pass for every sample like the reference's loop (default: once per batch)")
+    ap.add_argument("--no-side-stream", action="store_true", help="keep weight-gradient kernels on the main stream")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
@@ -250,6 +251,7 @@ def main():
     torch.cuda.set_device(local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ["NCCL_DEBUG"] = "WARN"          # keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     pk = peaks()
     cfg_name, batch = CONFIGS[args.workload]
@@ -323,7 +325,7 @@ def main():
             dist.destroy_process_group()
         return
 
-    engine = TrainEngine(model, batch, use_graph=not args.no_graph)
+    engine = TrainEngine(model, batch, use_graph=not args.no_graph, wgrad_side_stream=not args.no_side_stream)
     for _ in range(args.warmup):
         engine.step(x_host)
     torch.cuda.synchronize()

@@ -5,34 +5,74 @@
 // boilr Interpolate (models/lvae.py:144) and boilr pad/crop (models/lvae.py:176,185).
 #include "common.cuh"
 
+// V-wide (4 or 8 element) typed vector IO: 16-byte transactions for bf16 when V = 8
+template <typename T, int V> __device__ __forceinline__ void ldv(const T* p, float* f);
+template <> __device__ __forceinline__ void ldv<float, 4>(const float* p, float* f) {
+  float4 v = *reinterpret_cast<const float4*>(p);
+  f[0] = v.x; f[1] = v.y; f[2] = v.z; f[3] = v.w;
+}
+template <> __device__ __forceinline__ void ldv<__nv_bfloat16, 4>(const __nv_bfloat16* p, float* f) {
+  float4 v = ld4<__nv_bfloat16>(p);
+  f[0] = v.x; f[1] = v.y; f[2] = v.z; f[3] = v.w;
+}
+template <> __device__ __forceinline__ void ldv<__nv_bfloat16, 8>(const __nv_bfloat16* p, float* f) {
+  uint4 u = *reinterpret_cast<const uint4*>(p);
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    float2 t = __bfloat1622float2(h[j]);
+    f[2 * j] = t.x; f[2 * j + 1] = t.y;
+  }
+}
+template <typename T, int V> __device__ __forceinline__ void stv(T* p, const float* f);
+template <> __device__ __forceinline__ void stv<float, 4>(float* p, const float* f) {
+  *reinterpret_cast<float4*>(p) = make_float4(f[0], f[1], f[2], f[3]);
+}
+template <> __device__ __forceinline__ void stv<__nv_bfloat16, 4>(__nv_bfloat16* p, const float* f) {
+  st4<__nv_bfloat16>(p, make_float4(f[0], f[1], f[2], f[3]));
+}
+template <> __device__ __forceinline__ void stv<__nv_bfloat16, 8>(__nv_bfloat16* p, const float* f) {
+  uint4 u;
+  __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) h[j] = __floats2bfloat162_rn(f[2 * j], f[2 * j + 1]);
+  *reinterpret_cast<uint4*>(p) = u;
+}
+template <typename T> __device__ __forceinline__ float round_to(float v);
+template <> __device__ __forceinline__ float round_to<float>(float v) { return v; }
+template <> __device__ __forceinline__ float round_to<__nv_bfloat16>(float v) { return __bfloat162float(__float2bfloat16(v)); }
+
 // =========================================================================================
 // BatchNorm2d statistics: per-channel sum / sum of squares over (B,H,W), accumulated in
 // double (fp32 partials per thread, double atomics per block).
 // =========================================================================================
-template <typename T>
+template <typename T, int V>
 __global__ void bn_stats_kernel(const T* __restrict__ x, double* __restrict__ acc, long long P, int C) {
-  // thread -> channel quad (threadIdx.x % CV), row lane (threadIdx.x / CV)
-  extern __shared__ float sm[];  // [2][blockDim.x*4]
-  const int CV = C >> 2;
+  // thread -> channel group (threadIdx.x % CV), row lane (threadIdx.x / CV)
+  extern __shared__ float sm[];  // [2][blockDim.x*V]
+  const int CV = C / V;
   const int cq = threadIdx.x % CV, rl = threadIdx.x / CV, rpb = blockDim.x / CV;
-  float4 s = make_float4(0.f, 0.f, 0.f, 0.f), ss = s;
+  float s[V], ss[V];
+#pragma unroll
+  for (int j = 0; j < V; ++j) s[j] = ss[j] = 0.f;
   for (long long r = (long long)blockIdx.x * rpb + rl; r < P; r += (long long)gridDim.x * rpb) {
-    float4 v = ld4<T>(x + r * C + cq * 4);
-    s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
-    ss.x += v.x * v.x; ss.y += v.y * v.y; ss.z += v.z * v.z; ss.w += v.w * v.w;
+    float v[V];
+    ldv<T, V>(x + r * C + cq * V, v);
+#pragma unroll
+    for (int j = 0; j < V; ++j) { s[j] += v[j]; ss[j] += v[j] * v[j]; }
   }
   float* s_s = sm;
-  float* s_ss = sm + blockDim.x * 4;
-  reinterpret_cast<float4*>(s_s)[threadIdx.x] = s;
-  reinterpret_cast<float4*>(s_ss)[threadIdx.x] = ss;
+  float* s_ss = sm + blockDim.x * V;
+#pragma unroll
+  for (int j = 0; j < V; ++j) { s_s[threadIdx.x * V + j] = s[j]; s_ss[threadIdx.x * V + j] = ss[j]; }
   __syncthreads();
   // threads 0..C-1 reduce over row lanes
   if (threadIdx.x < C) {
-    int c = threadIdx.x, q = c >> 2, e = c & 3;
+    int c = threadIdx.x, q = c / V, e = c % V;
     double a = 0.0, b = 0.0;
     for (int r = 0; r < rpb; ++r) {
-      a += (double)s_s[(r * CV + q) * 4 + e];
-      b += (double)s_ss[(r * CV + q) * 4 + e];
+      a += (double)s_s[(r * CV + q) * V + e];
+      b += (double)s_ss[(r * CV + q) * V + e];
     }
     atomicAdd(acc + c, a);
     atomicAdd(acc + C + c, b);
@@ -96,24 +136,27 @@ __global__ void bn_act_fwd_kernel(const TI* __restrict__ x, TO* __restrict__ y, 
 }
 
 // backward pass 1: g = dy * act'(pre); accumulate sum(g), sum(g*xhat) per channel (double)
-template <typename T>
+template <typename T, int V>
 __global__ void bn_act_bwd_reduce_kernel(const T* __restrict__ dy, const T* __restrict__ x,
                                          const float* __restrict__ mean, const float* __restrict__ rstd,
                                          const float* __restrict__ gamma, const float* __restrict__ beta,
                                          double* __restrict__ acc, long long P, int C, int act) {
   extern __shared__ float sm[];
-  const int CV = C >> 2;
+  const int CV = C / V;
   const int cq = threadIdx.x % CV, rl = threadIdx.x / CV, rpb = blockDim.x / CV;
-  const int c = cq * 4;
-  float4 m = *reinterpret_cast<const float4*>(mean + c), r = *reinterpret_cast<const float4*>(rstd + c);
-  float4 g = *reinterpret_cast<const float4*>(gamma + c), b = *reinterpret_cast<const float4*>(beta + c);
-  float mm[4] = {m.x, m.y, m.z, m.w}, rr[4] = {r.x, r.y, r.z, r.w}, gg[4] = {g.x, g.y, g.z, g.w}, bb[4] = {b.x, b.y, b.z, b.w};
-  float s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
-  for (long long row = (long long)blockIdx.x * rpb + rl; row < P; row += (long long)gridDim.x * rpb) {
-    float4 xv = ld4<T>(x + row * C + c), dv = ld4<T>(dy + row * C + c);
-    float xs[4] = {xv.x, xv.y, xv.z, xv.w}, ds[4] = {dv.x, dv.y, dv.z, dv.w};
+  const int c = cq * V;
+  float mm[V], rr[V], gg[V], bb[V], s1[V], s2[V];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
+  for (int j = 0; j < V; ++j) {
+    mm[j] = mean[c + j]; rr[j] = rstd[c + j]; gg[j] = gamma[c + j]; bb[j] = beta[c + j];
+    s1[j] = s2[j] = 0.f;
+  }
+  for (long long row = (long long)blockIdx.x * rpb + rl; row < P; row += (long long)gridDim.x * rpb) {
+    float xs[V], ds[V];
+    ldv<T, V>(x + row * C + c, xs);
+    ldv<T, V>(dy + row * C + c, ds);
+#pragma unroll
+    for (int j = 0; j < V; ++j) {
       float xh = (xs[j] - mm[j]) * rr[j];
       float gpre = ds[j] * act_bwd(xh * gg[j] + bb[j], act);
       s1[j] += gpre;
@@ -121,19 +164,19 @@ __global__ void bn_act_bwd_reduce_kernel(const T* __restrict__ dy, const T* __re
     }
   }
   float* a1 = sm;
-  float* a2 = sm + blockDim.x * 4;
+  float* a2 = sm + blockDim.x * V;
 #pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    a1[threadIdx.x * 4 + j] = s1[j];
-    a2[threadIdx.x * 4 + j] = s2[j];
+  for (int j = 0; j < V; ++j) {
+    a1[threadIdx.x * V + j] = s1[j];
+    a2[threadIdx.x * V + j] = s2[j];
   }
   __syncthreads();
   if (threadIdx.x < C) {
-    int cc = threadIdx.x, q = cc >> 2, e = cc & 3;
+    int cc = threadIdx.x, q = cc / V, e = cc % V;
     double u = 0.0, v = 0.0;
     for (int rrw = 0; rrw < rpb; ++rrw) {
-      u += (double)a1[(rrw * CV + q) * 4 + e];
-      v += (double)a2[(rrw * CV + q) * 4 + e];
+      u += (double)a1[(rrw * CV + q) * V + e];
+      v += (double)a2[(rrw * CV + q) * V + e];
     }
     atomicAdd(acc + cc, u);
     atomicAdd(acc + C + cc, v);
@@ -198,15 +241,47 @@ static inline int ew_grid(long long n, int threads) {
 
 static bool bn_c_ok(int C) { return C >= 4 && C % 4 == 0 && C <= 256; }
 static int bn_threads(int C) { return (256 / (C / 4)) * (C / 4); }
+// 8-wide bf16 path: 16-byte transactions; needs C % 8 == 0 and 256 % (C/8) == 0 (C = 64: 8 threads per pixel)
+static bool use_v8(int dtype, int C) { return dtype == 1 && C % 8 == 0 && C >= 8 && 256 % (C / 8) == 0 && C <= 256; }
+
+static int launch_bn_stats(const void* x, double* acc, long long P, int C, int dtype, cudaStream_t stream) {
+  if (use_v8(dtype, C)) {
+    int threads = 256, rpb = threads / (C / 8);
+    int grid = (int)min((long long)4 * lvae_num_sms(), (P + rpb - 1) / rpb);
+    bn_stats_kernel<__nv_bfloat16, 8><<<grid, threads, (size_t)threads * 8 * 2 * sizeof(float), stream>>>((const __nv_bfloat16*)x, acc, P, C);
+    return 0;
+  }
+  int threads = bn_threads(C), rpb = threads / (C / 4);
+  int grid = (int)min((long long)4 * lvae_num_sms(), (P + rpb - 1) / rpb);
+  size_t smem = (size_t)threads * 4 * 2 * sizeof(float);
+  if (dtype == 0) bn_stats_kernel<float, 4><<<grid, threads, smem, stream>>>((const float*)x, acc, P, C);
+  else bn_stats_kernel<__nv_bfloat16, 4><<<grid, threads, smem, stream>>>((const __nv_bfloat16*)x, acc, P, C);
+  return 0;
+}
+
+static int launch_bwd_reduce(const void* dy, const void* x, const float* mean, const float* rstd, const float* gamma,
+                             const float* beta, double* acc, long long P, int C, int act, int dtype, cudaStream_t stream) {
+  if (use_v8(dtype, C)) {
+    int threads = 256, rpb = threads / (C / 8);
+    int grid = (int)min((long long)4 * lvae_num_sms(), (P + rpb - 1) / rpb);
+    bn_act_bwd_reduce_kernel<__nv_bfloat16, 8><<<grid, threads, (size_t)threads * 8 * 2 * sizeof(float), stream>>>(
+        (const __nv_bfloat16*)dy, (const __nv_bfloat16*)x, mean, rstd, gamma, beta, acc, P, C, act);
+    return 0;
+  }
+  int threads = bn_threads(C), rpb = threads / (C / 4);
+  int grid = (int)min((long long)4 * lvae_num_sms(), (P + rpb - 1) / rpb);
+  size_t smem = (size_t)threads * 4 * 2 * sizeof(float);
+  if (dtype == 0)
+    bn_act_bwd_reduce_kernel<float, 4><<<grid, threads, smem, stream>>>((const float*)dy, (const float*)x, mean, rstd, gamma, beta, acc, P, C, act);
+  else
+    bn_act_bwd_reduce_kernel<__nv_bfloat16, 4><<<grid, threads, smem, stream>>>((const __nv_bfloat16*)dy, (const __nv_bfloat16*)x, mean, rstd, gamma, beta, acc, P, C, act);
+  return 0;
+}
 
 LVAE_API int lvae_bn_stats(const void* x, double* acc, long long P, int C, int dtype, cudaStream_t stream) {
   LVAE_REQUIRE(x && acc && P > 0, "bn_stats: bad args");
   LVAE_REQUIRE(bn_c_ok(C), "bn_stats: channels must be a multiple of 4 and <= 256 (got %d)", C);
-  int threads = bn_threads(C), rpb = threads / (C / 4);
-  int grid = (int)min((long long)4 * lvae_num_sms(), (P + rpb - 1) / rpb);
-  size_t smem = (size_t)threads * 4 * 2 * sizeof(float);
-  if (dtype == 0) bn_stats_kernel<float><<<grid, threads, smem, stream>>>((const float*)x, acc, P, C);
-  else bn_stats_kernel<__nv_bfloat16><<<grid, threads, smem, stream>>>((const __nv_bfloat16*)x, acc, P, C);
+  launch_bn_stats(x, acc, P, C, dtype, stream);
   LVAE_COUNT_LAUNCH();
   LVAE_CHECK_LAUNCH("bn_stats");
   return LVAE_OK;
@@ -267,13 +342,7 @@ LVAE_API int lvae_bn_act_bwd(const void* dy, const void* x, void* dx, const floa
     return LVAE_OK;
   }
   LVAE_REQUIRE(bn_c_ok(C) && acc, "bn_act_bwd: channels must be a multiple of 4, <= 256, and acc non-null");
-  int threads = bn_threads(C), rpb = threads / (C / 4);
-  int grid = (int)min((long long)4 * lvae_num_sms(), (P + rpb - 1) / rpb);
-  size_t smem = (size_t)threads * 4 * 2 * sizeof(float);
-  if (dtype == 0)
-    bn_act_bwd_reduce_kernel<float><<<grid, threads, smem, stream>>>((const float*)dy, (const float*)x, mean, rstd, gamma, beta, acc, P, C, act);
-  else
-    bn_act_bwd_reduce_kernel<__nv_bfloat16><<<grid, threads, smem, stream>>>((const __nv_bfloat16*)dy, (const __nv_bfloat16*)x, mean, rstd, gamma, beta, acc, P, C, act);
+  launch_bwd_reduce(dy, x, mean, rstd, gamma, beta, acc, P, C, act, dtype, stream);
   LVAE_COUNT_LAUNCH();
   LVAE_CHECK_LAUNCH("bn_act_bwd_reduce");
   int g = ew_grid(nq, 256);
@@ -310,23 +379,25 @@ __global__ void gate_fwd_kernel(const T* __restrict__ h, const T* __restrict__ r
   }
 }
 
-template <typename T>
+template <typename T, int V>
 __global__ void gate_bwd_kernel(const T* __restrict__ dout, const T* __restrict__ h, T* __restrict__ dh,
-                                long long nquads, int C, int act) {
-  const int CV = C >> 2;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nquads; i += (long long)gridDim.x * blockDim.x) {
+                                long long nvec, int C, int act) {
+  const int CV = C / V;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (long long)gridDim.x * blockDim.x) {
     long long row = i / CV;
-    int c = (int)(i - row * CV) * 4;
-    float4 a = ld4<T>(h + row * 2 * C + c), g = ld4<T>(h + row * 2 * C + C + c), d = ld4<T>(dout + i * 4);
-    float av[4] = {a.x, a.y, a.z, a.w}, gv[4] = {g.x, g.y, g.z, g.w}, dv[4] = {d.x, d.y, d.z, d.w}, da[4], dg[4];
+    int c = (int)(i - row * CV) * V;
+    float av[V], gv[V], dv[V], da[V], dg[V];
+    ldv<T, V>(h + row * 2 * C + c, av);
+    ldv<T, V>(h + row * 2 * C + C + c, gv);
+    ldv<T, V>(dout + i * V, dv);
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
+    for (int j = 0; j < V; ++j) {
       float s = sigmoidf_(gv[j]);
       da[j] = dv[j] * s * act_bwd(av[j], act);
       dg[j] = dv[j] * act_fwd(av[j], act) * s * (1.f - s);
     }
-    st4<T>(dh + row * 2 * C + c, make_float4(da[0], da[1], da[2], da[3]));
-    st4<T>(dh + row * 2 * C + C + c, make_float4(dg[0], dg[1], dg[2], dg[3]));
+    stv<T, V>(dh + row * 2 * C + c, da);
+    stv<T, V>(dh + row * 2 * C + C + c, dg);
   }
 }
 
@@ -343,10 +414,15 @@ LVAE_API int lvae_gate_fwd(const void* h, const void* res, void* out, long long 
 
 LVAE_API int lvae_gate_bwd(const void* dout, const void* h, void* dh, long long P, int C, int act, int dtype, cudaStream_t stream) {
   LVAE_REQUIRE(dout && h && dh && P > 0 && C % 4 == 0, "gate_bwd: bad args");
-  long long nq = P * (C / 4);
-  int g = ew_grid(nq, 256);
-  if (dtype == 0) gate_bwd_kernel<float><<<g, 256, 0, stream>>>((const float*)dout, (const float*)h, (float*)dh, nq, C, act);
-  else gate_bwd_kernel<__nv_bfloat16><<<g, 256, 0, stream>>>((const __nv_bfloat16*)dout, (const __nv_bfloat16*)h, (__nv_bfloat16*)dh, nq, C, act);
+  if (dtype == 1 && C % 8 == 0) {
+    long long nv = P * (C / 8);
+    gate_bwd_kernel<__nv_bfloat16, 8><<<ew_grid(nv, 256), 256, 0, stream>>>((const __nv_bfloat16*)dout, (const __nv_bfloat16*)h, (__nv_bfloat16*)dh, nv, C, act);
+  } else {
+    long long nq = P * (C / 4);
+    int g = ew_grid(nq, 256);
+    if (dtype == 0) gate_bwd_kernel<float, 4><<<g, 256, 0, stream>>>((const float*)dout, (const float*)h, (float*)dh, nq, C, act);
+    else gate_bwd_kernel<__nv_bfloat16, 4><<<g, 256, 0, stream>>>((const __nv_bfloat16*)dout, (const __nv_bfloat16*)h, (__nv_bfloat16*)dh, nq, C, act);
+  }
   LVAE_COUNT_LAUNCH();
   LVAE_CHECK_LAUNCH("gate_bwd");
   return LVAE_OK;
@@ -574,14 +650,14 @@ LVAE_API int lvae_channel_scale(const void* x, const float* scale, void* y, int 
 //                (post_scale, the mask of the conv that produced x) and an optional residual add.
 // The accumulators are NOT cleared here: the model zeroes its whole BatchNorm scratch arena once per forward.
 // =========================================================================================
-template <typename TI, typename TO>
+template <typename TI, typename TO, int V>
 __global__ void bn_act_fwd2_kernel(const TI* __restrict__ x, TO* __restrict__ y, const double* __restrict__ acc,
                                    const float* __restrict__ gamma, const float* __restrict__ beta,
                                    float* __restrict__ save, float* running_mean, float* running_var,
-                                   long long* nbt, long long nquads, long long P, int C, int act, int training,
+                                   long long* nbt, long long nvec, long long P, int C, int act, int training,
                                    float momentum, float eps) {
-  __shared__ float s_scale[256], s_shift[256];       // y = act(x * scale + shift), C <= 256
-  const int CV = C >> 2;
+  __shared__ __align__(16) float s_scale[256], s_shift[256];       // y = act(x * scale + shift), C <= 256
+  const int CV = C / V;
   // one thread per channel derives the statistics (the only double-precision math in the kernel)
   for (int ch = threadIdx.x; ch < C; ch += blockDim.x) {
     float mean, rstd;
@@ -612,60 +688,68 @@ __global__ void bn_act_fwd2_kernel(const TI* __restrict__ x, TO* __restrict__ y,
   __syncthreads();
   const long long stride = (long long)gridDim.x * blockDim.x;      // multiple of CV by construction
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  const int c = (int)(i % CV) * 4;
-  const float4 sc4 = *reinterpret_cast<const float4*>(s_scale + c), sh4 = *reinterpret_cast<const float4*>(s_shift + c);
-  for (; i < nquads; i += stride) {
-    float4 v = ld4<TI>(x + i * 4);
-    st4<TO>(y + i * 4, make_float4(act_fwd(v.x * sc4.x + sh4.x, act), act_fwd(v.y * sc4.y + sh4.y, act),
-                                   act_fwd(v.z * sc4.z + sh4.z, act), act_fwd(v.w * sc4.w + sh4.w, act)));
+  const int c = (int)(i % CV) * V;
+  float sc[V], sh[V];
+#pragma unroll
+  for (int j = 0; j < V; ++j) { sc[j] = s_scale[c + j]; sh[j] = s_shift[c + j]; }
+  for (; i < nvec; i += stride) {
+    float v[V];
+    ldv<TI, V>(x + i * V, v);
+#pragma unroll
+    for (int j = 0; j < V; ++j) v[j] = act_fwd(v[j] * sc[j] + sh[j], act);
+    stv<TO, V>(y + i * V, v);
   }
 }
 
-template <typename T>
+template <typename T, int V>
 __global__ void bn_act_bwd2_kernel(const T* __restrict__ dy, const T* __restrict__ x, T* __restrict__ dx,
                                    const float* __restrict__ save, const float* __restrict__ gamma,
                                    const float* __restrict__ beta, const double* __restrict__ acc,
                                    float* dgamma, float* dbeta, const float* __restrict__ post_scale,
-                                   const T* __restrict__ add, long long nquads, long long P, int hw, int C, int act,
+                                   const T* __restrict__ add, long long nvec, long long P, int hw, int C, int act,
                                    int training) {
-  const int CV = C >> 2;
+  const int CV = C / V;
   const long long stride = (long long)gridDim.x * blockDim.x;
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  const int c = (int)(i % CV) * 4;
+  const int c = (int)(i % CV) * V;
   const double invP = 1.0 / (double)P;
-  float m[4], r[4], g[4], b[4], m1[4], m2[4];
+  float m[V], r[V], g[V], b[V], m1[V], m2[V];
 #pragma unroll
-  for (int j = 0; j < 4; ++j) {
+  for (int j = 0; j < V; ++j) {
     m[j] = save[c + j]; r[j] = save[C + c + j]; g[j] = gamma[c + j]; b[j] = beta[c + j];
     m1[j] = (float)(acc[c + j] * invP);
     m2[j] = (float)(acc[C + c + j] * invP);
   }
   if (blockIdx.x == 0 && threadIdx.x < CV) {
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
+    for (int j = 0; j < V; ++j) {
       if (dbeta) dbeta[c + j] += (float)acc[c + j];
       if (dgamma) dgamma[c + j] += (float)acc[C + c + j];
     }
   }
-  for (; i < nquads; i += stride) {
-    float4 xv = ld4<T>(x + i * 4), dv = ld4<T>(dy + i * 4);
-    float xs[4] = {xv.x, xv.y, xv.z, xv.w}, ds[4] = {dv.x, dv.y, dv.z, dv.w}, o[4];
+  for (; i < nvec; i += stride) {
+    float xs[V], ds[V], o[V];
+    ldv<T, V>(x + i * V, xs);
+    ldv<T, V>(dy + i * V, ds);
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
+    for (int j = 0; j < V; ++j) {
       float xh = (xs[j] - m[j]) * r[j];
       float gpre = ds[j] * act_bwd(xh * g[j] + b[j], act);
       o[j] = training ? g[j] * r[j] * (gpre - m1[j] - xh * m2[j]) : g[j] * r[j] * gpre;
     }
     if (post_scale) {
       long long bidx = (i / CV) / hw;
-      float4 s = *reinterpret_cast<const float4*>(post_scale + bidx * C + c);
-      o[0] *= s.x; o[1] *= s.y; o[2] *= s.z; o[3] *= s.w;
+      const float* ps = post_scale + bidx * C + c;
+#pragma unroll
+      for (int j = 0; j < V; ++j) o[j] *= ps[j];
     }
     if (add) {
-      float4 a = ld4<T>(add + i * 4);
-      o[0] += a.x; o[1] += a.y; o[2] += a.z; o[3] += a.w;
+      float a[V];
+      ldv<T, V>(add + i * V, a);
+#pragma unroll
+      for (int j = 0; j < V; ++j) o[j] += a[j];
     }
-    st4<T>(dx + i * 4, make_float4(o[0], o[1], o[2], o[3]));
+    stv<T, V>(dx + i * V, o);
   }
 }
 
@@ -682,14 +766,21 @@ LVAE_API int lvae_bn_act_fwd2(const void* x, void* y, const double* acc, const f
                               cudaStream_t stream) {
   LVAE_REQUIRE(x && y && gamma && beta && save && P > 0 && bn_c_ok(C), "bn_act_fwd2: bad args");
   LVAE_REQUIRE(training ? acc != nullptr : (running_mean && running_var), "bn_act_fwd2: statistics source missing");
-  long long nq = P * (C / 4);
-  int g = ew_grid_aligned(nq, 256, C / 4);
-#define FW2(TI, TO) bn_act_fwd2_kernel<TI, TO><<<g, 256, 0, stream>>>((const TI*)x, (TO*)y, acc, gamma, beta, save, running_mean, running_var, nbt, nq, P, C, act, training, momentum, eps)
-  if (dtype_in == 0 && dtype_out == 0) FW2(float, float);
-  else if (dtype_in == 0 && dtype_out == 1) FW2(float, __nv_bfloat16);
-  else if (dtype_in == 1 && dtype_out == 1) FW2(__nv_bfloat16, __nv_bfloat16);
-  else FW2(__nv_bfloat16, float);
+  if (dtype_in == 1 && dtype_out == 1 && use_v8(1, C)) {
+    long long nv = P * (C / 8);
+    int g = ew_grid_aligned(nv, 256, C / 8);
+    bn_act_fwd2_kernel<__nv_bfloat16, __nv_bfloat16, 8><<<g, 256, 0, stream>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)y, acc, gamma,
+        beta, save, running_mean, running_var, nbt, nv, P, C, act, training, momentum, eps);
+  } else {
+    long long nq = P * (C / 4);
+    int g = ew_grid_aligned(nq, 256, C / 4);
+#define FW2(TI, TO) bn_act_fwd2_kernel<TI, TO, 4><<<g, 256, 0, stream>>>((const TI*)x, (TO*)y, acc, gamma, beta, save, running_mean, running_var, nbt, nq, P, C, act, training, momentum, eps)
+    if (dtype_in == 0 && dtype_out == 0) FW2(float, float);
+    else if (dtype_in == 0 && dtype_out == 1) FW2(float, __nv_bfloat16);
+    else if (dtype_in == 1 && dtype_out == 1) FW2(__nv_bfloat16, __nv_bfloat16);
+    else FW2(__nv_bfloat16, float);
 #undef FW2
+  }
   LVAE_COUNT_LAUNCH();
   LVAE_CHECK_LAUNCH("bn_act_fwd2");
   return LVAE_OK;
@@ -702,20 +793,21 @@ LVAE_API int lvae_bn_act_bwd2(const void* dy, const void* x, void* dx, const flo
                               cudaStream_t stream) {
   LVAE_REQUIRE(dy && x && dx && save && gamma && beta && acc && P > 0 && bn_c_ok(C), "bn_act_bwd2: bad args");
   long long nq = P * (C / 4);
-  int threads = bn_threads(C), rpb = threads / (C / 4);
-  int grid = (int)min((long long)4 * lvae_num_sms(), (P + rpb - 1) / rpb);
-  size_t smem = (size_t)threads * 4 * 2 * sizeof(float);
-  if (dtype == 0)
-    bn_act_bwd_reduce_kernel<float><<<grid, threads, smem, stream>>>((const float*)dy, (const float*)x, save, save + C, gamma, beta, acc, P, C, act);
-  else
-    bn_act_bwd_reduce_kernel<__nv_bfloat16><<<grid, threads, smem, stream>>>((const __nv_bfloat16*)dy, (const __nv_bfloat16*)x, save, save + C, gamma, beta, acc, P, C, act);
+  launch_bwd_reduce(dy, x, save, save + C, gamma, beta, acc, P, C, act, dtype, stream);
   LVAE_COUNT_LAUNCH();
   LVAE_CHECK_LAUNCH("bn_act_bwd_reduce");
-  int g = ew_grid_aligned(nq, 256, C / 4);
-  if (dtype == 0)
-    bn_act_bwd2_kernel<float><<<g, 256, 0, stream>>>((const float*)dy, (const float*)x, (float*)dx, save, gamma, beta, acc, dgamma, dbeta, post_scale, (const float*)add, nq, P, hw, C, act, training);
-  else
-    bn_act_bwd2_kernel<__nv_bfloat16><<<g, 256, 0, stream>>>((const __nv_bfloat16*)dy, (const __nv_bfloat16*)x, (__nv_bfloat16*)dx, save, gamma, beta, acc, dgamma, dbeta, post_scale, (const __nv_bfloat16*)add, nq, P, hw, C, act, training);
+  if (use_v8(dtype, C)) {
+    long long nv = P * (C / 8);
+    int g = ew_grid_aligned(nv, 256, C / 8);
+    bn_act_bwd2_kernel<__nv_bfloat16, 8><<<g, 256, 0, stream>>>((const __nv_bfloat16*)dy, (const __nv_bfloat16*)x, (__nv_bfloat16*)dx, save,
+        gamma, beta, acc, dgamma, dbeta, post_scale, (const __nv_bfloat16*)add, nv, P, hw, C, act, training);
+  } else {
+    int g = ew_grid_aligned(nq, 256, C / 4);
+    if (dtype == 0)
+      bn_act_bwd2_kernel<float, 4><<<g, 256, 0, stream>>>((const float*)dy, (const float*)x, (float*)dx, save, gamma, beta, acc, dgamma, dbeta, post_scale, (const float*)add, nq, P, hw, C, act, training);
+    else
+      bn_act_bwd2_kernel<__nv_bfloat16, 4><<<g, 256, 0, stream>>>((const __nv_bfloat16*)dy, (const __nv_bfloat16*)x, (__nv_bfloat16*)dx, save, gamma, beta, acc, dgamma, dbeta, post_scale, (const __nv_bfloat16*)add, nq, P, hw, C, act, training);
+  }
   LVAE_COUNT_LAUNCH();
   LVAE_CHECK_LAUNCH("bn_act_bwd2");
   return LVAE_OK;
@@ -730,44 +822,51 @@ template <> __device__ __forceinline__ float4 round_as<__nv_bfloat16>(float4 v) 
 
 // gate forward that also accumulates the per-channel sum / sum of squares of its OUTPUT (the next
 // residual block's first BatchNorm then needs no statistics pass of its own)
-template <typename T>
+template <typename T, int V>
 __global__ void gate_fwd_stats_kernel(const T* __restrict__ h, const T* __restrict__ res, T* __restrict__ out,
-                                      double* __restrict__ acc, long long nquads, int C, int act) {
+                                      double* __restrict__ acc, long long nvec, int C, int act) {
   extern __shared__ float sm[];
-  const int CV = C >> 2;
-  const long long stride = (long long)gridDim.x * blockDim.x;      // multiple of CV
+  const int CV = C / V;
+  const long long stride = (long long)gridDim.x * blockDim.x;      // multiple of CV (256 % CV == 0)
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const int cq = (int)(i % CV);
-  float4 s = make_float4(0.f, 0.f, 0.f, 0.f), ss = s;
-  for (; i < nquads; i += stride) {
+  float s[V], ss[V];
+#pragma unroll
+  for (int j = 0; j < V; ++j) s[j] = ss[j] = 0.f;
+  for (; i < nvec; i += stride) {
     long long row = i / CV;
-    int c = cq * 4;
-    float4 a = ld4<T>(h + row * 2 * C + c), g = ld4<T>(h + row * 2 * C + C + c);
-    float4 o = make_float4(act_fwd(a.x, act) * sigmoidf_(g.x), act_fwd(a.y, act) * sigmoidf_(g.y),
-                           act_fwd(a.z, act) * sigmoidf_(g.z), act_fwd(a.w, act) * sigmoidf_(g.w));
+    int c = cq * V;
+    float a[V], g[V], o[V];
+    ldv<T, V>(h + row * 2 * C + c, a);
+    ldv<T, V>(h + row * 2 * C + C + c, g);
+#pragma unroll
+    for (int j = 0; j < V; ++j) o[j] = act_fwd(a[j], act) * sigmoidf_(g[j]);
     if (res) {
-      float4 r = ld4<T>(res + i * 4);
-      o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
+      float r[V];
+      ldv<T, V>(res + i * V, r);
+#pragma unroll
+      for (int j = 0; j < V; ++j) o[j] += r[j];
     }
-    st4<T>(out + i * 4, o);
-    float4 q = round_as<T>(o);             // statistics of the value as stored (bf16-rounded on the bf16 path)
-    s.x += q.x; s.y += q.y; s.z += q.z; s.w += q.w;
-    ss.x += q.x * q.x; ss.y += q.y * q.y; ss.z += q.z * q.z; ss.w += q.w * q.w;
+    stv<T, V>(out + i * V, o);
+#pragma unroll
+    for (int j = 0; j < V; ++j) {
+      float q = round_to<T>(o[j]);           // statistics of the value as stored (bf16-rounded on the bf16 path)
+      s[j] += q;
+      ss[j] += q * q;
+    }
   }
-  // block reduction: threads with the same channel quad are blockDim/CV apart
   float* s_s = sm;
-  float* s_ss = sm + blockDim.x * 4;
-  reinterpret_cast<float4*>(s_s)[threadIdx.x] = s;
-  reinterpret_cast<float4*>(s_ss)[threadIdx.x] = ss;
+  float* s_ss = sm + blockDim.x * V;
+#pragma unroll
+  for (int j = 0; j < V; ++j) { s_s[threadIdx.x * V + j] = s[j]; s_ss[threadIdx.x * V + j] = ss[j]; }
   __syncthreads();
   if (threadIdx.x < C) {
-    // thread t of the block has quad (blockIdx.x*blockDim.x + t) % CV; blockDim % CV == 0 -> quad = (base + t) % CV
-    const int base = (int)(((long long)blockIdx.x * blockDim.x) % CV);
-    int cch = threadIdx.x, q = cch >> 2, e = cch & 3;
+    // blockDim % CV == 0, so thread t of any block owns channel group t % CV
+    int cch = threadIdx.x, q = cch / V, e = cch % V;
     double a = 0.0, b = 0.0;
-    for (int t = (q - base + CV) % CV; t < blockDim.x; t += CV) {
-      a += (double)s_s[t * 4 + e];
-      b += (double)s_ss[t * 4 + e];
+    for (int t = q; t < blockDim.x; t += CV) {
+      a += (double)s_s[t * V + e];
+      b += (double)s_ss[t * V + e];
     }
     atomicAdd(acc + cch, a);
     atomicAdd(acc + C + cch, b);
@@ -777,13 +876,15 @@ __global__ void gate_fwd_stats_kernel(const T* __restrict__ h, const T* __restri
 LVAE_API int lvae_gate_fwd_stats(const void* h, const void* res, void* out, double* acc, long long P, int C, int act,
                                  int dtype, cudaStream_t stream) {
   LVAE_REQUIRE(h && out && acc && P > 0 && bn_c_ok(C) && 256 % (C / 4) == 0, "gate_fwd_stats: bad args");
-  long long nq = P * (C / 4);
+  const int V = use_v8(dtype, C) ? 8 : 4;
+  long long nv = P * (C / V);
   long long cap = 4LL * lvae_num_sms();
-  long long want = (nq + 255) / 256;
+  long long want = (nv + 255) / 256;
   int g = (int)(want < cap ? (want > 0 ? want : 1) : cap);
-  size_t smem = (size_t)256 * 4 * 2 * sizeof(float);
-  if (dtype == 0) gate_fwd_stats_kernel<float><<<g, 256, smem, stream>>>((const float*)h, (const float*)res, (float*)out, acc, nq, C, act);
-  else gate_fwd_stats_kernel<__nv_bfloat16><<<g, 256, smem, stream>>>((const __nv_bfloat16*)h, (const __nv_bfloat16*)res, (__nv_bfloat16*)out, acc, nq, C, act);
+  size_t smem = (size_t)256 * V * 2 * sizeof(float);
+  if (V == 8) gate_fwd_stats_kernel<__nv_bfloat16, 8><<<g, 256, smem, stream>>>((const __nv_bfloat16*)h, (const __nv_bfloat16*)res, (__nv_bfloat16*)out, acc, nv, C, act);
+  else if (dtype == 0) gate_fwd_stats_kernel<float, 4><<<g, 256, smem, stream>>>((const float*)h, (const float*)res, (float*)out, acc, nv, C, act);
+  else gate_fwd_stats_kernel<__nv_bfloat16, 4><<<g, 256, smem, stream>>>((const __nv_bfloat16*)h, (const __nv_bfloat16*)res, (__nv_bfloat16*)out, acc, nv, C, act);
   LVAE_COUNT_LAUNCH();
   LVAE_CHECK_LAUNCH("gate_fwd_stats");
   return LVAE_OK;

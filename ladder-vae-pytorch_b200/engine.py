@@ -113,7 +113,7 @@ class TrainEngine:
 
     def __init__(self, model, batch_size: int, lr: float = 3e-4, weight_decay: float = 0.0, betas=(0.9, 0.999),
                  eps: float = 1e-8, beta_kl: float = 1.0, use_graph: bool = True, process_group=None,
-                 bucket_bytes: int = 25 << 20, compute_l2: bool = True):
+                 bucket_bytes: int = 25 << 20, compute_l2: bool = True, wgrad_side_stream: bool = True):
         _capi.device_check()
         self.model = model.train()
         self.batch_size = batch_size
@@ -133,6 +133,7 @@ class TrainEngine:
         self.buckets = bucket_ranges(self.arena.numel, bucket_bytes)
         self.x = torch.zeros((batch_size, model.color_ch) + tuple(model.img_shape), dtype=torch.float32, device=dev)
         self.use_graph = use_graph
+        self.side_stream = torch.cuda.Stream(device=dev) if wgrad_side_stream else None
         self.graph_fb: Optional[torch.cuda.CUDAGraph] = None
         self.graph_opt: Optional[torch.cuda.CUDAGraph] = None
         self.out: Dict[str, torch.Tensor] = {}
@@ -150,7 +151,13 @@ class TrainEngine:
         out = self.model(self.x)
         recons = (-out["ll"]).mean()
         loss = recons + out["kl_loss"] * self.beta_kl
-        loss.backward()
+        if self.side_stream is not None:
+            ops.set_side_stream(self.side_stream)
+        try:
+            loss.backward()
+        finally:
+            ops.join_side_stream()
+            ops.set_side_stream(None)
         elbo = (out["ll"] - out["kl_sep"]).mean()
         self.out = {"loss": loss.detach(), "elbo": elbo.detach(), "recons": recons.detach(), "kl": out["kl"].detach(),
                     "kl_avg_layerwise": out["kl_avg_layerwise"].detach()}

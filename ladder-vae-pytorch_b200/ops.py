@@ -303,6 +303,24 @@ class ConvSpec:
         return _pow2(H) and _pow2(W) and W <= 128 and N % 64 == 0 and N <= 256
 
 
+# Weight gradients depend only on saved activations and the output gradient, and nothing reads them before the
+# optimizer: the engine lets them run on a side stream (a parallel branch of the captured graph) so that the
+# small, latency-bound wgrad kernels overlap the dgrad / BatchNorm chain.
+_side = {"stream": None, "keep": []}
+
+
+def set_side_stream(stream) -> None:
+    _side["stream"] = stream
+    _side["keep"] = []
+
+
+def join_side_stream() -> None:
+    st = _side["stream"]
+    if st is not None:
+        torch.cuda.current_stream().wait_stream(st)
+    _side["keep"] = []
+
+
 _wgrad_ws = {}
 stats = {"tc_fwd": 0, "tc_dgrad": 0, "tc_wgrad": 0, "cc_fwd": 0, "cc_dgrad": 0, "cc_wgrad": 0}   # path counters (tests)
 
@@ -409,6 +427,12 @@ def conv_backward_raw(spec: ConvSpec, xn, x2n, weight, bias, out_scale, gyn, nee
         gbbuf, bsunk = (None, True)
         if bias is not None and need_b:
             gbbuf, bsunk = _param_grad_buffer(bias)
+        side = _side["stream"] if (sunk and bsunk) else None
+        if side is not None:
+            side.wait_event(torch.cuda.current_stream().record_event())     # gyn is ready
+            _side["keep"].append((xn, x2n, gyn, out_scale))                  # keep operands alive until the join
+            ctx_mgr = torch.cuda.stream(side)
+            ctx_mgr.__enter__()
         if use_tc and out_scale is None and C1 == 64 and C2 in (0, 64) and N in (64, 128) and gyn.dtype == torch.bfloat16 \
                 and spec.k * spec.k * (2 if C2 else 1) <= 9:
             stats["tc_wgrad"] += 1
@@ -427,6 +451,8 @@ def conv_backward_raw(spec: ConvSpec, xn, x2n, weight, bias, out_scale, gyn, nee
                  _dt(xn), _stream())
             if gbbuf is not None:
                 call("lvae_colsum", gyn.data_ptr(), _p(out_scale), gbbuf.data_ptr(), B, Ho * Wo, N, _dt(gyn), _stream())
+        if side is not None:
+            ctx_mgr.__exit__(None, None, None)
         gw = None if sunk else gwbuf
         gb = None if (bsunk or gbbuf is None) else gbbuf
     return gx, gx2, gw, gb
