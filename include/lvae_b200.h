@@ -29,6 +29,10 @@ int lvae_abi_version(void);
 unsigned long long lvae_launch_count(void); /* kernels launched by this library so far */
 void lvae_reset_launch_count(void);
 int lvae_device_check(void); /* 0 iff the current device is sm_10x */
+/* programmatic dependent launch for every kernel of the library (default on): a kernel's prologue overlaps
+ * the tail of its predecessor; all kernels call griddepcontrol.wait before touching upstream results */
+void lvae_set_pdl(int enabled);
+int lvae_get_pdl(void);
 
 /* ---- convolutions: nn.Conv2d / nn.ConvTranspose2d forward, dgrad, wgrad ----
  * replaces cuDNN behind lib/nn.py:83-87 (3x3 residual convs), lib/nn.py:118 (1x1 gate conv),

@@ -61,6 +61,8 @@ _SPECIAL = {
     "lvae_reset_launch_count": ([], None),
     "lvae_device_check": ([], c_int),
     "lvae_pack_desc_size": ([], c_int),
+    "lvae_set_pdl": ([c_int], None),
+    "lvae_get_pdl": ([], c_int),
     "lvae_wgrad_tc_workspace": ([I, I, I, I, I, I], c_longlong),
 }
 
@@ -86,6 +88,8 @@ def lib():
             fn = getattr(l, name)
             fn.argtypes = argtypes
             fn.restype = restype
+        if os.environ.get("LVAE_PDL", "1") == "0":
+            l.lvae_set_pdl(0)
         _lib = l
     return _lib
 

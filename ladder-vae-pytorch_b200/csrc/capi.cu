@@ -5,6 +5,7 @@
 
 static thread_local char g_err[512] = "";
 unsigned long long g_lvae_launches = 0;
+int g_lvae_pdl = 1;
 
 void lvae_set_error(const char* fmt, ...) {
   va_list ap;
@@ -15,6 +16,9 @@ void lvae_set_error(const char* fmt, ...) {
 
 LVAE_API const char* lvae_last_error(void) { return g_err; }
 LVAE_API int lvae_abi_version(void) { return 1; }
+// 1 (default): launch every kernel with programmatic dependent launch allowed; 0: plain stream order
+LVAE_API void lvae_set_pdl(int enabled) { g_lvae_pdl = enabled ? 1 : 0; }
+LVAE_API int lvae_get_pdl(void) { return g_lvae_pdl; }
 LVAE_API unsigned long long lvae_launch_count(void) { return g_lvae_launches; }
 LVAE_API void lvae_reset_launch_count(void) { g_lvae_launches = 0; }
 

@@ -32,6 +32,32 @@ void lvae_set_error(const char* fmt, ...);
     }                                                                         \
   } while (0)
 
+// ---- programmatic dependent launch (PDL) ----
+// Every kernel of this library is launched with programmaticStreamSerializationAllowed: its CTAs may be
+// scheduled while the previous kernel in the stream is still draining.  A kernel must not touch memory
+// written by its predecessor before pdl_wait(); it calls pdl_launch() right after, so the NEXT kernel can
+// only start once this one has seen its predecessor complete (anything two or more kernels upstream is
+// therefore safe to read in a prologue: packed weights, parameters, tensor maps).
+extern int g_lvae_pdl;
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+template <typename... KArgs, typename... Args>
+static inline cudaError_t lvae_launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                                      Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = g_lvae_pdl ? 1 : 0;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 // launch counter (bench.py reports gpu_launches from it)
 extern unsigned long long g_lvae_launches;
 #define LVAE_COUNT_LAUNCH() (++g_lvae_launches)

@@ -25,6 +25,8 @@ constexpr int CG_APITCH = CG_BK + 4;
 
 template <typename T, bool VEC>
 __global__ void __launch_bounds__(CG_THREADS) conv_gather_kernel(ConvArgs a) {
+  pdl_wait();
+  pdl_launch();
   __shared__ __align__(16) float As[CG_BM][CG_APITCH];
   __shared__ __align__(16) float Bs[CG_BK][CG_BN];
   const int t = threadIdx.x;
@@ -224,11 +226,11 @@ LVAE_API int lvae_conv2d_gather(const void* x, const void* x2, const void* wp, c
   dim3 grid(cdiv(M, CG_BM), cdiv(N, CG_BN));
   bool vec = (C1 % 4 == 0) && (C2 % 4 == 0);
   if (dtype == 0) {
-    if (vec) conv_gather_kernel<float, true><<<grid, CG_THREADS, 0, stream>>>(a);
-    else conv_gather_kernel<float, false><<<grid, CG_THREADS, 0, stream>>>(a);
+    if (vec) lvae_launch(conv_gather_kernel<float, true>, grid, CG_THREADS, 0, stream, a);
+    else lvae_launch(conv_gather_kernel<float, false>, grid, CG_THREADS, 0, stream, a);
   } else {
-    if (vec) conv_gather_kernel<__nv_bfloat16, true><<<grid, CG_THREADS, 0, stream>>>(a);
-    else conv_gather_kernel<__nv_bfloat16, false><<<grid, CG_THREADS, 0, stream>>>(a);
+    if (vec) lvae_launch(conv_gather_kernel<__nv_bfloat16, true>, grid, CG_THREADS, 0, stream, a);
+    else lvae_launch(conv_gather_kernel<__nv_bfloat16, false>, grid, CG_THREADS, 0, stream, a);
   }
   LVAE_COUNT_LAUNCH();
   LVAE_CHECK_LAUNCH("conv2d_gather");
@@ -254,6 +256,8 @@ constexpr int WG_BK = 64, WG_BN = 64, WG_BM = 32, WG_THREADS = 256;
 
 template <typename T, bool VEC>
 __global__ void __launch_bounds__(WG_THREADS) conv_wgrad_kernel(WgradArgs a) {
+  pdl_wait();
+  pdl_launch();
   __shared__ __align__(16) float As[WG_BM][WG_BK + 4];
   __shared__ __align__(16) float Ds[WG_BM][WG_BN + 4];
   const int t = threadIdx.x;
@@ -413,11 +417,11 @@ LVAE_API int lvae_conv2d_wgrad(const void* u, const void* u2, const void* dz, co
   dim3 grid(ktiles, ntiles, (unsigned)splits);
   bool vec = (C1 % 4 == 0) && (C2 % 4 == 0);
   if (dtype == 0) {
-    if (vec) conv_wgrad_kernel<float, true><<<grid, WG_THREADS, 0, stream>>>(a);
-    else conv_wgrad_kernel<float, false><<<grid, WG_THREADS, 0, stream>>>(a);
+    if (vec) lvae_launch(conv_wgrad_kernel<float, true>, grid, WG_THREADS, 0, stream, a);
+    else lvae_launch(conv_wgrad_kernel<float, false>, grid, WG_THREADS, 0, stream, a);
   } else {
-    if (vec) conv_wgrad_kernel<__nv_bfloat16, true><<<grid, WG_THREADS, 0, stream>>>(a);
-    else conv_wgrad_kernel<__nv_bfloat16, false><<<grid, WG_THREADS, 0, stream>>>(a);
+    if (vec) lvae_launch(conv_wgrad_kernel<__nv_bfloat16, true>, grid, WG_THREADS, 0, stream, a);
+    else lvae_launch(conv_wgrad_kernel<__nv_bfloat16, false>, grid, WG_THREADS, 0, stream, a);
   }
   LVAE_COUNT_LAUNCH();
   LVAE_CHECK_LAUNCH("conv2d_wgrad");
@@ -437,6 +441,8 @@ struct LvaePackDesc {
 };
 
 __global__ void pack_weights_kernel(const LvaePackDesc* descs, int n) {
+  pdl_wait();
+  pdl_launch();
   for (int d = blockIdx.y; d < n; d += gridDim.y) {
     LvaePackDesc p = descs[d];
     if (p.mode >= 2) {
@@ -479,7 +485,7 @@ __global__ void pack_weights_kernel(const LvaePackDesc* descs, int n) {
 LVAE_API int lvae_pack_weights(const void* descs_dev, int n, cudaStream_t stream) {
   LVAE_REQUIRE(descs_dev && n > 0, "pack_weights: bad args");
   dim3 grid(8, n < 65535 ? n : 65535);
-  pack_weights_kernel<<<grid, 256, 0, stream>>>((const LvaePackDesc*)descs_dev, n);
+  lvae_launch(pack_weights_kernel, grid, 256, 0, stream, (const LvaePackDesc*)descs_dev, n);
   LVAE_COUNT_LAUNCH();
   LVAE_CHECK_LAUNCH("pack_weights");
   return LVAE_OK;
@@ -490,6 +496,8 @@ LVAE_API int lvae_pack_desc_size() { return (int)sizeof(LvaePackDesc); }
 // per-channel sum over (B,H,W) of dy * scale[b,c]  -> out[c] (+=); used for ConvTranspose dbias
 template <typename T>
 __global__ void colsum_kernel(const T* dy, const float* scale, float* out, long long M, int C, int hw) {
+  pdl_wait();
+  pdl_launch();
   // grid.x strides over pixel rows, each thread owns channel (threadIdx.x % C) when blockDim % C == 0
   int c = threadIdx.x % C, rpb = blockDim.x / C, r0 = threadIdx.x / C;
   float s = 0.f;
@@ -509,8 +517,8 @@ LVAE_API int lvae_colsum(const void* dy, const float* scale, float* out, int B, 
   long long M = (long long)B * HW;
   int rpb = threads / C;
   int grid = (int)min((long long)2 * lvae_num_sms(), (M + rpb - 1) / rpb);
-  if (dtype == 0) colsum_kernel<float><<<grid, threads, 0, stream>>>((const float*)dy, scale, out, M, C, HW);
-  else colsum_kernel<__nv_bfloat16><<<grid, threads, 0, stream>>>((const __nv_bfloat16*)dy, scale, out, M, C, HW);
+  if (dtype == 0) lvae_launch(colsum_kernel<float>, grid, threads, 0, stream, (const float*)dy, scale, out, M, C, HW);
+  else lvae_launch(colsum_kernel<__nv_bfloat16>, grid, threads, 0, stream, (const __nv_bfloat16*)dy, scale, out, M, C, HW);
   LVAE_COUNT_LAUNCH();
   LVAE_CHECK_LAUNCH("colsum");
   return LVAE_OK;

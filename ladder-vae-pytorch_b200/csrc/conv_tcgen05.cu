@@ -234,6 +234,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     mbar_init(BAR(2 * S + 3), 4);      // one arrive per epilogue warp
     mbar_init(BAR(2 * S + 4), 4);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    // weights were packed many kernels ago: fetch them before waiting on the previous kernel (PDL prologue)
+    mbar_expect_tx(BAR(2 * S), (uint32_t)(p.n_kb * wbytes_kb));
+    for (int kb = 0; kb < p.n_kb; ++kb) tma_load_2d(smem_u32(sW + kb * wbytes_kb), &tmW, BAR(2 * S), 0, kb * p.Npad);
   }
   for (int i = threadIdx.x; i < p.Npad; i += TC_THREADS) sbias[i] = (p.bias && i < p.N) ? p.bias[i] : 0.f;
   if (warp == 1) {
@@ -244,12 +247,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();          // activations / residual / dropout mask come from the previous kernels
+  pdl_launch();
 
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
-      mbar_expect_tx(BAR(2 * S), (uint32_t)(p.n_kb * wbytes_kb));
-      for (int kb = 0; kb < p.n_kb; ++kb) tma_load_2d(smem_u32(sW + kb * wbytes_kb), &tmW, BAR(2 * S), 0, kb * p.Npad);
       int stage = 0;
       uint32_t phase = 0;
       const int hw = p.H * p.W;
@@ -454,7 +457,7 @@ LVAE_API int lvae_conv2d_tc(const void* x, const void* x2, const void* wp, const
   }
   const int n_tiles = (p.M_total + TC_BM - 1) / TC_BM;
   const int grid = n_tiles < lvae_num_sms() ? n_tiles : lvae_num_sms();
-  conv_tc_kernel<<<grid, TC_THREADS, smem, stream>>>(tmA0, tmA1, tmW, p);
+  lvae_launch(conv_tc_kernel, grid, TC_THREADS, smem, stream, tmA0, tmA1, tmW, p);
   LVAE_COUNT_LAUNCH();
   LVAE_CHECK_LAUNCH("conv2d_tc");
   return LVAE_OK;

@@ -48,6 +48,8 @@ template <> __device__ __forceinline__ float round_to<__nv_bfloat16>(float v) { 
 // =========================================================================================
 template <typename T, int V>
 __global__ void bn_stats_kernel(const T* __restrict__ x, double* __restrict__ acc, long long P, int C) {
+  pdl_wait();
+  pdl_launch();
   // thread -> channel group (threadIdx.x % CV), row lane (threadIdx.x / CV)
   extern __shared__ float sm[];  // [2][blockDim.x*V]
   const int CV = C / V;
@@ -83,6 +85,8 @@ __global__ void bn_stats_kernel(const T* __restrict__ x, double* __restrict__ ac
 __global__ void bn_finalize_kernel(double* acc, float* save_mean, float* save_rstd, float* running_mean,
                                    float* running_var, long long* num_batches_tracked, long long P, int C,
                                    float momentum, float eps) {
+  pdl_wait();
+  pdl_launch();
   int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c < C) {
     double mean = acc[c] / (double)P;
@@ -104,6 +108,8 @@ __global__ void bn_finalize_kernel(double* acc, float* save_mean, float* save_rs
 // eval-mode: mean/rstd from running stats
 __global__ void bn_eval_prepare_kernel(const float* running_mean, const float* running_var, float* save_mean,
                                        float* save_rstd, int C, float eps) {
+  pdl_wait();
+  pdl_launch();
   int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c < C) {
     save_mean[c] = running_mean[c];
@@ -116,6 +122,8 @@ template <typename TI, typename TO>
 __global__ void bn_act_fwd_kernel(const TI* __restrict__ x, TO* __restrict__ y, const float* __restrict__ mean,
                                   const float* __restrict__ rstd, const float* __restrict__ gamma,
                                   const float* __restrict__ beta, long long nquads, int C, int act) {
+  pdl_wait();
+  pdl_launch();
   const int CV = C >> 2;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nquads; i += (long long)gridDim.x * blockDim.x) {
     int c = (int)(i % CV) * 4;
@@ -141,6 +149,8 @@ __global__ void bn_act_bwd_reduce_kernel(const T* __restrict__ dy, const T* __re
                                          const float* __restrict__ mean, const float* __restrict__ rstd,
                                          const float* __restrict__ gamma, const float* __restrict__ beta,
                                          double* __restrict__ acc, long long P, int C, int act) {
+  pdl_wait();
+  pdl_launch();
   extern __shared__ float sm[];
   const int CV = C / V;
   const int cq = threadIdx.x % CV, rl = threadIdx.x / CV, rpb = blockDim.x / CV;
@@ -191,6 +201,8 @@ __global__ void bn_act_bwd_apply_kernel(const T* __restrict__ dy, const T* __res
                                         const float* __restrict__ gamma, const float* __restrict__ beta,
                                         const double* __restrict__ acc, long long nquads, long long P, int C,
                                         int act, int training) {
+  pdl_wait();
+  pdl_launch();
   const int CV = C >> 2;
   const double invP = 1.0 / (double)P;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nquads; i += (long long)gridDim.x * blockDim.x) {
@@ -214,6 +226,8 @@ __global__ void bn_act_bwd_apply_kernel(const T* __restrict__ dy, const T* __res
 }
 
 __global__ void bn_bwd_params_kernel(double* acc, float* dgamma, float* dbeta, int C) {
+  pdl_wait();
+  pdl_launch();
   int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c < C) {
     if (dbeta) dbeta[c] += (float)acc[c];
@@ -226,6 +240,8 @@ __global__ void bn_bwd_params_kernel(double* acc, float* dgamma, float* dbeta, i
 // plain activation backward (no BatchNorm): dx = dy * act'(x)
 template <typename T>
 __global__ void act_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ x, T* __restrict__ dx, long long nquads, int act) {
+  pdl_wait();
+  pdl_launch();
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nquads; i += (long long)gridDim.x * blockDim.x) {
     float4 xv = ld4<T>(x + i * 4), dv = ld4<T>(dy + i * 4);
     st4<T>(dx + i * 4, make_float4(dv.x * act_bwd(xv.x, act), dv.y * act_bwd(xv.y, act), dv.z * act_bwd(xv.z, act),
@@ -248,14 +264,14 @@ static int launch_bn_stats(const void* x, double* acc, long long P, int C, int d
   if (use_v8(dtype, C)) {
     int threads = 256, rpb = threads / (C / 8);
     int grid = (int)min((long long)4 * lvae_num_sms(), (P + rpb - 1) / rpb);
-    bn_stats_kernel<__nv_bfloat16, 8><<<grid, threads, (size_t)threads * 8 * 2 * sizeof(float), stream>>>((const __nv_bfloat16*)x, acc, P, C);
+    lvae_launch(bn_stats_kernel<__nv_bfloat16, 8>, grid, threads, (size_t)threads * 8 * 2 * sizeof(float), stream, (const __nv_bfloat16*)x, acc, P, C);
     return 0;
   }
   int threads = bn_threads(C), rpb = threads / (C / 4);
   int grid = (int)min((long long)4 * lvae_num_sms(), (P + rpb - 1) / rpb);
   size_t smem = (size_t)threads * 4 * 2 * sizeof(float);
-  if (dtype == 0) bn_stats_kernel<float, 4><<<grid, threads, smem, stream>>>((const float*)x, acc, P, C);
-  else bn_stats_kernel<__nv_bfloat16, 4><<<grid, threads, smem, stream>>>((const __nv_bfloat16*)x, acc, P, C);
+  if (dtype == 0) lvae_launch(bn_stats_kernel<float, 4>, grid, threads, smem, stream, (const float*)x, acc, P, C);
+  else lvae_launch(bn_stats_kernel<__nv_bfloat16, 4>, grid, threads, smem, stream, (const __nv_bfloat16*)x, acc, P, C);
   return 0;
 }
 
@@ -264,17 +280,16 @@ static int launch_bwd_reduce(const void* dy, const void* x, const float* mean, c
   if (use_v8(dtype, C)) {
     int threads = 256, rpb = threads / (C / 8);
     int grid = (int)min((long long)4 * lvae_num_sms(), (P + rpb - 1) / rpb);
-    bn_act_bwd_reduce_kernel<__nv_bfloat16, 8><<<grid, threads, (size_t)threads * 8 * 2 * sizeof(float), stream>>>(
-        (const __nv_bfloat16*)dy, (const __nv_bfloat16*)x, mean, rstd, gamma, beta, acc, P, C, act);
+    lvae_launch(bn_act_bwd_reduce_kernel<__nv_bfloat16, 8>, grid, threads, (size_t)threads * 8 * 2 * sizeof(float), stream, (const __nv_bfloat16*)dy, (const __nv_bfloat16*)x, mean, rstd, gamma, beta, acc, P, C, act);
     return 0;
   }
   int threads = bn_threads(C), rpb = threads / (C / 4);
   int grid = (int)min((long long)4 * lvae_num_sms(), (P + rpb - 1) / rpb);
   size_t smem = (size_t)threads * 4 * 2 * sizeof(float);
   if (dtype == 0)
-    bn_act_bwd_reduce_kernel<float, 4><<<grid, threads, smem, stream>>>((const float*)dy, (const float*)x, mean, rstd, gamma, beta, acc, P, C, act);
+    lvae_launch(bn_act_bwd_reduce_kernel<float, 4>, grid, threads, smem, stream, (const float*)dy, (const float*)x, mean, rstd, gamma, beta, acc, P, C, act);
   else
-    bn_act_bwd_reduce_kernel<__nv_bfloat16, 4><<<grid, threads, smem, stream>>>((const __nv_bfloat16*)dy, (const __nv_bfloat16*)x, mean, rstd, gamma, beta, acc, P, C, act);
+    lvae_launch(bn_act_bwd_reduce_kernel<__nv_bfloat16, 4>, grid, threads, smem, stream, (const __nv_bfloat16*)dy, (const __nv_bfloat16*)x, mean, rstd, gamma, beta, acc, P, C, act);
   return 0;
 }
 
@@ -291,7 +306,7 @@ LVAE_API int lvae_bn_finalize(double* acc, float* save_mean, float* save_rstd, f
                               float* running_var, long long* num_batches_tracked, long long P, int C,
                               float momentum, float eps, cudaStream_t stream) {
   LVAE_REQUIRE(acc && save_mean && save_rstd, "bn_finalize: bad args");
-  bn_finalize_kernel<<<cdiv(C, 128), 128, 0, stream>>>(acc, save_mean, save_rstd, running_mean, running_var,
+  lvae_launch(bn_finalize_kernel, cdiv(C, 128), 128, 0, stream, acc, save_mean, save_rstd, running_mean, running_var,
                                                        num_batches_tracked, P, C, momentum, eps);
   LVAE_COUNT_LAUNCH();
   LVAE_CHECK_LAUNCH("bn_finalize");
@@ -301,7 +316,7 @@ LVAE_API int lvae_bn_finalize(double* acc, float* save_mean, float* save_rstd, f
 LVAE_API int lvae_bn_eval_prepare(const float* running_mean, const float* running_var, float* save_mean,
                                   float* save_rstd, int C, float eps, cudaStream_t stream) {
   LVAE_REQUIRE(running_mean && running_var && save_mean && save_rstd, "bn_eval_prepare: bad args");
-  bn_eval_prepare_kernel<<<cdiv(C, 128), 128, 0, stream>>>(running_mean, running_var, save_mean, save_rstd, C, eps);
+  lvae_launch(bn_eval_prepare_kernel, cdiv(C, 128), 128, 0, stream, running_mean, running_var, save_mean, save_rstd, C, eps);
   LVAE_COUNT_LAUNCH();
   LVAE_CHECK_LAUNCH("bn_eval_prepare");
   return LVAE_OK;
@@ -315,13 +330,13 @@ LVAE_API int lvae_bn_act_fwd(const void* x, void* y, const float* mean, const fl
   long long nq = P * (C / 4);
   int g = ew_grid(nq, 256);
   if (dtype_in == 0 && dtype_out == 0)
-    bn_act_fwd_kernel<float, float><<<g, 256, 0, stream>>>((const float*)x, (float*)y, mean, rstd, gamma, beta, nq, C, act);
+    lvae_launch(bn_act_fwd_kernel<float, float>, g, 256, 0, stream, (const float*)x, (float*)y, mean, rstd, gamma, beta, nq, C, act);
   else if (dtype_in == 0 && dtype_out == 1)
-    bn_act_fwd_kernel<float, __nv_bfloat16><<<g, 256, 0, stream>>>((const float*)x, (__nv_bfloat16*)y, mean, rstd, gamma, beta, nq, C, act);
+    lvae_launch(bn_act_fwd_kernel<float, __nv_bfloat16>, g, 256, 0, stream, (const float*)x, (__nv_bfloat16*)y, mean, rstd, gamma, beta, nq, C, act);
   else if (dtype_in == 1 && dtype_out == 1)
-    bn_act_fwd_kernel<__nv_bfloat16, __nv_bfloat16><<<g, 256, 0, stream>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)y, mean, rstd, gamma, beta, nq, C, act);
+    lvae_launch(bn_act_fwd_kernel<__nv_bfloat16, __nv_bfloat16>, g, 256, 0, stream, (const __nv_bfloat16*)x, (__nv_bfloat16*)y, mean, rstd, gamma, beta, nq, C, act);
   else
-    bn_act_fwd_kernel<__nv_bfloat16, float><<<g, 256, 0, stream>>>((const __nv_bfloat16*)x, (float*)y, mean, rstd, gamma, beta, nq, C, act);
+    lvae_launch(bn_act_fwd_kernel<__nv_bfloat16, float>, g, 256, 0, stream, (const __nv_bfloat16*)x, (float*)y, mean, rstd, gamma, beta, nq, C, act);
   LVAE_COUNT_LAUNCH();
   LVAE_CHECK_LAUNCH("bn_act_fwd");
   return LVAE_OK;
@@ -335,8 +350,8 @@ LVAE_API int lvae_bn_act_bwd(const void* dy, const void* x, void* dx, const floa
   if (!mean) {  // plain activation
     LVAE_REQUIRE(C % 4 == 0, "act_bwd: C must be a multiple of 4");
     int g = ew_grid(nq, 256);
-    if (dtype == 0) act_bwd_kernel<float><<<g, 256, 0, stream>>>((const float*)dy, (const float*)x, (float*)dx, nq, act);
-    else act_bwd_kernel<__nv_bfloat16><<<g, 256, 0, stream>>>((const __nv_bfloat16*)dy, (const __nv_bfloat16*)x, (__nv_bfloat16*)dx, nq, act);
+    if (dtype == 0) lvae_launch(act_bwd_kernel<float>, g, 256, 0, stream, (const float*)dy, (const float*)x, (float*)dx, nq, act);
+    else lvae_launch(act_bwd_kernel<__nv_bfloat16>, g, 256, 0, stream, (const __nv_bfloat16*)dy, (const __nv_bfloat16*)x, (__nv_bfloat16*)dx, nq, act);
     LVAE_COUNT_LAUNCH();
     LVAE_CHECK_LAUNCH("act_bwd");
     return LVAE_OK;
@@ -347,12 +362,12 @@ LVAE_API int lvae_bn_act_bwd(const void* dy, const void* x, void* dx, const floa
   LVAE_CHECK_LAUNCH("bn_act_bwd_reduce");
   int g = ew_grid(nq, 256);
   if (dtype == 0)
-    bn_act_bwd_apply_kernel<float><<<g, 256, 0, stream>>>((const float*)dy, (const float*)x, (float*)dx, mean, rstd, gamma, beta, acc, nq, P, C, act, training);
+    lvae_launch(bn_act_bwd_apply_kernel<float>, g, 256, 0, stream, (const float*)dy, (const float*)x, (float*)dx, mean, rstd, gamma, beta, acc, nq, P, C, act, training);
   else
-    bn_act_bwd_apply_kernel<__nv_bfloat16><<<g, 256, 0, stream>>>((const __nv_bfloat16*)dy, (const __nv_bfloat16*)x, (__nv_bfloat16*)dx, mean, rstd, gamma, beta, acc, nq, P, C, act, training);
+    lvae_launch(bn_act_bwd_apply_kernel<__nv_bfloat16>, g, 256, 0, stream, (const __nv_bfloat16*)dy, (const __nv_bfloat16*)x, (__nv_bfloat16*)dx, mean, rstd, gamma, beta, acc, nq, P, C, act, training);
   LVAE_COUNT_LAUNCH();
   LVAE_CHECK_LAUNCH("bn_act_bwd_apply");
-  bn_bwd_params_kernel<<<cdiv(C, 128), 128, 0, stream>>>(acc, dgamma, dbeta, C);
+  lvae_launch(bn_bwd_params_kernel, cdiv(C, 128), 128, 0, stream, acc, dgamma, dbeta, C);
   LVAE_COUNT_LAUNCH();
   LVAE_CHECK_LAUNCH("bn_bwd_params");
   return LVAE_OK;
@@ -364,6 +379,8 @@ LVAE_API int lvae_bn_act_bwd(const void* dy, const void* x, void* dx, const floa
 template <typename T>
 __global__ void gate_fwd_kernel(const T* __restrict__ h, const T* __restrict__ res, T* __restrict__ out,
                                 long long nquads, int C, int act) {
+  pdl_wait();
+  pdl_launch();
   const int CV = C >> 2;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nquads; i += (long long)gridDim.x * blockDim.x) {
     long long row = i / CV;
@@ -382,6 +399,8 @@ __global__ void gate_fwd_kernel(const T* __restrict__ h, const T* __restrict__ r
 template <typename T, int V>
 __global__ void gate_bwd_kernel(const T* __restrict__ dout, const T* __restrict__ h, T* __restrict__ dh,
                                 long long nvec, int C, int act) {
+  pdl_wait();
+  pdl_launch();
   const int CV = C / V;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (long long)gridDim.x * blockDim.x) {
     long long row = i / CV;
@@ -405,8 +424,8 @@ LVAE_API int lvae_gate_fwd(const void* h, const void* res, void* out, long long 
   LVAE_REQUIRE(h && out && P > 0 && C % 4 == 0, "gate_fwd: bad args");
   long long nq = P * (C / 4);
   int g = ew_grid(nq, 256);
-  if (dtype == 0) gate_fwd_kernel<float><<<g, 256, 0, stream>>>((const float*)h, (const float*)res, (float*)out, nq, C, act);
-  else gate_fwd_kernel<__nv_bfloat16><<<g, 256, 0, stream>>>((const __nv_bfloat16*)h, (const __nv_bfloat16*)res, (__nv_bfloat16*)out, nq, C, act);
+  if (dtype == 0) lvae_launch(gate_fwd_kernel<float>, g, 256, 0, stream, (const float*)h, (const float*)res, (float*)out, nq, C, act);
+  else lvae_launch(gate_fwd_kernel<__nv_bfloat16>, g, 256, 0, stream, (const __nv_bfloat16*)h, (const __nv_bfloat16*)res, (__nv_bfloat16*)out, nq, C, act);
   LVAE_COUNT_LAUNCH();
   LVAE_CHECK_LAUNCH("gate_fwd");
   return LVAE_OK;
@@ -416,12 +435,12 @@ LVAE_API int lvae_gate_bwd(const void* dout, const void* h, void* dh, long long 
   LVAE_REQUIRE(dout && h && dh && P > 0 && C % 4 == 0, "gate_bwd: bad args");
   if (dtype == 1 && C % 8 == 0) {
     long long nv = P * (C / 8);
-    gate_bwd_kernel<__nv_bfloat16, 8><<<ew_grid(nv, 256), 256, 0, stream>>>((const __nv_bfloat16*)dout, (const __nv_bfloat16*)h, (__nv_bfloat16*)dh, nv, C, act);
+    lvae_launch(gate_bwd_kernel<__nv_bfloat16, 8>, ew_grid(nv, 256), 256, 0, stream, (const __nv_bfloat16*)dout, (const __nv_bfloat16*)h, (__nv_bfloat16*)dh, nv, C, act);
   } else {
     long long nq = P * (C / 4);
     int g = ew_grid(nq, 256);
-    if (dtype == 0) gate_bwd_kernel<float, 4><<<g, 256, 0, stream>>>((const float*)dout, (const float*)h, (float*)dh, nq, C, act);
-    else gate_bwd_kernel<__nv_bfloat16, 4><<<g, 256, 0, stream>>>((const __nv_bfloat16*)dout, (const __nv_bfloat16*)h, (__nv_bfloat16*)dh, nq, C, act);
+    if (dtype == 0) lvae_launch(gate_bwd_kernel<float, 4>, g, 256, 0, stream, (const float*)dout, (const float*)h, (float*)dh, nq, C, act);
+    else lvae_launch(gate_bwd_kernel<__nv_bfloat16, 4>, g, 256, 0, stream, (const __nv_bfloat16*)dout, (const __nv_bfloat16*)h, (__nv_bfloat16*)dh, nq, C, act);
   }
   LVAE_COUNT_LAUNCH();
   LVAE_CHECK_LAUNCH("gate_bwd");
@@ -441,6 +460,8 @@ __device__ __forceinline__ void up2_src(int o, int n_in, int& i0, int& i1, float
 
 template <typename T>
 __global__ void upsample2x_fwd_kernel(const T* __restrict__ x, T* __restrict__ y, int B, int H, int W, int C) {
+  pdl_wait();
+  pdl_launch();
   const int CV = C >> 2;
   long long total = (long long)B * 2 * H * 2 * W * CV;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -469,6 +490,8 @@ __global__ void upsample2x_fwd_kernel(const T* __restrict__ x, T* __restrict__ y
 // backward as a gather: every input pixel collects from the <= 3x3 output pixels that read it
 template <typename T>
 __global__ void upsample2x_bwd_kernel(const T* __restrict__ dy, T* __restrict__ dx, int B, int H, int W, int C) {
+  pdl_wait();
+  pdl_launch();
   const int CV = C >> 2;
   long long total = (long long)B * H * W * CV;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -503,8 +526,8 @@ __global__ void upsample2x_bwd_kernel(const T* __restrict__ dy, T* __restrict__ 
 LVAE_API int lvae_upsample2x_fwd(const void* x, void* y, int B, int H, int W, int C, int dtype, cudaStream_t stream) {
   LVAE_REQUIRE(x && y && C % 4 == 0, "upsample2x_fwd: bad args");
   long long n = (long long)B * 4 * H * W * (C / 4);
-  if (dtype == 0) upsample2x_fwd_kernel<float><<<ew_grid(n, 256), 256, 0, stream>>>((const float*)x, (float*)y, B, H, W, C);
-  else upsample2x_fwd_kernel<__nv_bfloat16><<<ew_grid(n, 256), 256, 0, stream>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)y, B, H, W, C);
+  if (dtype == 0) lvae_launch(upsample2x_fwd_kernel<float>, ew_grid(n, 256), 256, 0, stream, (const float*)x, (float*)y, B, H, W, C);
+  else lvae_launch(upsample2x_fwd_kernel<__nv_bfloat16>, ew_grid(n, 256), 256, 0, stream, (const __nv_bfloat16*)x, (__nv_bfloat16*)y, B, H, W, C);
   LVAE_COUNT_LAUNCH();
   LVAE_CHECK_LAUNCH("upsample2x_fwd");
   return LVAE_OK;
@@ -513,8 +536,8 @@ LVAE_API int lvae_upsample2x_fwd(const void* x, void* y, int B, int H, int W, in
 LVAE_API int lvae_upsample2x_bwd(const void* dy, void* dx, int B, int H, int W, int C, int dtype, cudaStream_t stream) {
   LVAE_REQUIRE(dy && dx && C % 4 == 0, "upsample2x_bwd: bad args");
   long long n = (long long)B * H * W * (C / 4);
-  if (dtype == 0) upsample2x_bwd_kernel<float><<<ew_grid(n, 256), 256, 0, stream>>>((const float*)dy, (float*)dx, B, H, W, C);
-  else upsample2x_bwd_kernel<__nv_bfloat16><<<ew_grid(n, 256), 256, 0, stream>>>((const __nv_bfloat16*)dy, (__nv_bfloat16*)dx, B, H, W, C);
+  if (dtype == 0) lvae_launch(upsample2x_bwd_kernel<float>, ew_grid(n, 256), 256, 0, stream, (const float*)dy, (float*)dx, B, H, W, C);
+  else lvae_launch(upsample2x_bwd_kernel<__nv_bfloat16>, ew_grid(n, 256), 256, 0, stream, (const __nv_bfloat16*)dy, (__nv_bfloat16*)dx, B, H, W, C);
   LVAE_COUNT_LAUNCH();
   LVAE_CHECK_LAUNCH("upsample2x_bwd");
   return LVAE_OK;
@@ -529,6 +552,8 @@ template <typename TS, typename TD>
 __global__ void copy_window_kernel(const TS* __restrict__ src, TD* __restrict__ dst, int B, int C, int Hs, int Ws,
                                    int Hd, int Wd, int sy0, int sx0, int dy0, int dx0, int h, int w,
                                    int src_nchw, int dst_nchw) {
+  pdl_wait();
+  pdl_launch();
   long long total = (long long)B * h * w * C;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     int c = (int)(i % C);
@@ -553,7 +578,7 @@ LVAE_API int lvae_copy_window(const void* src, void* dst, int B, int C, int Hs, 
                "copy_window: window out of range");
   long long n = (long long)B * h * w * C;
   int g = ew_grid(n, 256);
-#define CW(TS, TD) copy_window_kernel<TS, TD><<<g, 256, 0, stream>>>((const TS*)src, (TD*)dst, B, C, Hs, Ws, Hd, Wd, sy0, sx0, dy0, dx0, h, w, src_nchw, dst_nchw)
+#define CW(TS, TD) lvae_launch(copy_window_kernel<TS, TD>, g, 256, 0, stream, (const TS*)src, (TD*)dst, B, C, Hs, Ws, Hd, Wd, sy0, sx0, dy0, dx0, h, w, src_nchw, dst_nchw)
   if (src_dtype == 0 && dst_dtype == 0) CW(float, float);
   else if (src_dtype == 0 && dst_dtype == 1) CW(float, __nv_bfloat16);
   else if (src_dtype == 1 && dst_dtype == 0) CW(__nv_bfloat16, float);
@@ -569,6 +594,8 @@ LVAE_API int lvae_copy_window(const void* src, void* dst, int B, int C, int Hs, 
 // masks[i] = (u_i >= p) / (1-p), i over (site, sample, channel).  RNG state lives on the device.
 // =========================================================================================
 __global__ void dropout_masks_kernel(float* masks, long long n, float p, const PhiloxState* st, unsigned long long stream_id) {
+  pdl_wait();
+  pdl_launch();
   PhiloxState s = *st;
   float inv = 1.f / (1.f - p);
   for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q * 4 < n; q += (long long)gridDim.x * blockDim.x) {
@@ -581,18 +608,20 @@ __global__ void dropout_masks_kernel(float* masks, long long n, float p, const P
 LVAE_API int lvae_dropout_masks(float* masks, long long n, float p, const void* rng_state, unsigned long long stream_id,
                                 cudaStream_t stream) {
   LVAE_REQUIRE(masks && n > 0 && p >= 0.f && p < 1.f && rng_state, "dropout_masks: bad args");
-  dropout_masks_kernel<<<ew_grid((n + 3) / 4, 256), 256, 0, stream>>>(masks, n, p, (const PhiloxState*)rng_state, stream_id);
+  lvae_launch(dropout_masks_kernel, ew_grid((n + 3) / 4, 256), 256, 0, stream, masks, n, p, (const PhiloxState*)rng_state, stream_id);
   LVAE_COUNT_LAUNCH();
   LVAE_CHECK_LAUNCH("dropout_masks");
   return LVAE_OK;
 }
 
-__global__ void rng_advance_kernel(PhiloxState* st, unsigned long long inc) { st->offset += inc; }
+__global__ void rng_advance_kernel(PhiloxState* st, unsigned long long inc) {
+  pdl_wait();
+  pdl_launch(); st->offset += inc; }
 
 // rng_state: device uint64[2] = {seed, offset}; advance once per step (graph-replay safe)
 LVAE_API int lvae_rng_advance(void* rng_state, unsigned long long inc, cudaStream_t stream) {
   LVAE_REQUIRE(rng_state, "rng_advance: null state");
-  rng_advance_kernel<<<1, 1, 0, stream>>>((PhiloxState*)rng_state, inc);
+  lvae_launch(rng_advance_kernel, 1, 1, 0, stream, (PhiloxState*)rng_state, inc);
   LVAE_COUNT_LAUNCH();
   LVAE_CHECK_LAUNCH("rng_advance");
   return LVAE_OK;
@@ -600,6 +629,8 @@ LVAE_API int lvae_rng_advance(void* rng_state, unsigned long long inc, cudaStrea
 
 // out[i] (+)= sum_b x[b, i]  (top-layer prior gradient: the prior is a batch-1 parameter, lvae_layers.py:131-136)
 __global__ void sum_batch_kernel(const float* x, float* out, int B, long long n, int accumulate) {
+  pdl_wait();
+  pdl_launch();
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     float s = 0.f;
     for (int b = 0; b < B; ++b) s += x[(long long)b * n + i];
@@ -609,7 +640,7 @@ __global__ void sum_batch_kernel(const float* x, float* out, int B, long long n,
 
 LVAE_API int lvae_sum_batch(const float* x, float* out, int B, long long n, int accumulate, cudaStream_t stream) {
   LVAE_REQUIRE(x && out && B > 0 && n > 0, "sum_batch: bad args");
-  sum_batch_kernel<<<ew_grid(n, 256), 256, 0, stream>>>(x, out, B, n, accumulate);
+  lvae_launch(sum_batch_kernel, ew_grid(n, 256), 256, 0, stream, x, out, B, n, accumulate);
   LVAE_COUNT_LAUNCH();
   LVAE_CHECK_LAUNCH("sum_batch");
   return LVAE_OK;
@@ -620,6 +651,8 @@ LVAE_API int lvae_sum_batch(const float* x, float* out, int B, long long n, int 
 template <typename T>
 __global__ void channel_scale_kernel(const T* __restrict__ x, const float* __restrict__ scale, T* __restrict__ y,
                                      long long nquads, int hw, int C) {
+  pdl_wait();
+  pdl_launch();
   const int CV = C >> 2;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nquads; i += (long long)gridDim.x * blockDim.x) {
     long long row = i / CV;
@@ -635,8 +668,8 @@ LVAE_API int lvae_channel_scale(const void* x, const float* scale, void* y, int 
                                 cudaStream_t stream) {
   LVAE_REQUIRE(x && scale && y && C % 4 == 0, "channel_scale: bad args");
   long long nq = (long long)B * HW * (C / 4);
-  if (dtype_in == 0) channel_scale_kernel<float><<<ew_grid(nq, 256), 256, 0, stream>>>((const float*)x, scale, (float*)y, nq, HW, C);
-  else channel_scale_kernel<__nv_bfloat16><<<ew_grid(nq, 256), 256, 0, stream>>>((const __nv_bfloat16*)x, scale, (__nv_bfloat16*)y, nq, HW, C);
+  if (dtype_in == 0) lvae_launch(channel_scale_kernel<float>, ew_grid(nq, 256), 256, 0, stream, (const float*)x, scale, (float*)y, nq, HW, C);
+  else lvae_launch(channel_scale_kernel<__nv_bfloat16>, ew_grid(nq, 256), 256, 0, stream, (const __nv_bfloat16*)x, scale, (__nv_bfloat16*)y, nq, HW, C);
   LVAE_COUNT_LAUNCH();
   LVAE_CHECK_LAUNCH("channel_scale");
   return LVAE_OK;
@@ -656,6 +689,8 @@ __global__ void bn_act_fwd2_kernel(const TI* __restrict__ x, TO* __restrict__ y,
                                    float* __restrict__ save, float* running_mean, float* running_var,
                                    long long* nbt, long long nvec, long long P, int C, int act, int training,
                                    float momentum, float eps) {
+  pdl_wait();
+  pdl_launch();
   __shared__ __align__(16) float s_scale[256], s_shift[256];       // y = act(x * scale + shift), C <= 256
   const int CV = C / V;
   // one thread per channel derives the statistics (the only double-precision math in the kernel)
@@ -708,6 +743,8 @@ __global__ void bn_act_bwd2_kernel(const T* __restrict__ dy, const T* __restrict
                                    float* dgamma, float* dbeta, const float* __restrict__ post_scale,
                                    const T* __restrict__ add, long long nvec, long long P, int hw, int C, int act,
                                    int training) {
+  pdl_wait();
+  pdl_launch();
   const int CV = C / V;
   const long long stride = (long long)gridDim.x * blockDim.x;
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -769,12 +806,12 @@ LVAE_API int lvae_bn_act_fwd2(const void* x, void* y, const double* acc, const f
   if (dtype_in == 1 && dtype_out == 1 && use_v8(1, C)) {
     long long nv = P * (C / 8);
     int g = ew_grid_aligned(nv, 256, C / 8);
-    bn_act_fwd2_kernel<__nv_bfloat16, __nv_bfloat16, 8><<<g, 256, 0, stream>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)y, acc, gamma,
+    lvae_launch(bn_act_fwd2_kernel<__nv_bfloat16, __nv_bfloat16, 8>, g, 256, 0, stream, (const __nv_bfloat16*)x, (__nv_bfloat16*)y, acc, gamma,
         beta, save, running_mean, running_var, nbt, nv, P, C, act, training, momentum, eps);
   } else {
     long long nq = P * (C / 4);
     int g = ew_grid_aligned(nq, 256, C / 4);
-#define FW2(TI, TO) bn_act_fwd2_kernel<TI, TO, 4><<<g, 256, 0, stream>>>((const TI*)x, (TO*)y, acc, gamma, beta, save, running_mean, running_var, nbt, nq, P, C, act, training, momentum, eps)
+#define FW2(TI, TO) lvae_launch(bn_act_fwd2_kernel<TI, TO, 4>, g, 256, 0, stream, (const TI*)x, (TO*)y, acc, gamma, beta, save, running_mean, running_var, nbt, nq, P, C, act, training, momentum, eps)
     if (dtype_in == 0 && dtype_out == 0) FW2(float, float);
     else if (dtype_in == 0 && dtype_out == 1) FW2(float, __nv_bfloat16);
     else if (dtype_in == 1 && dtype_out == 1) FW2(__nv_bfloat16, __nv_bfloat16);
@@ -799,14 +836,14 @@ LVAE_API int lvae_bn_act_bwd2(const void* dy, const void* x, void* dx, const flo
   if (use_v8(dtype, C)) {
     long long nv = P * (C / 8);
     int g = ew_grid_aligned(nv, 256, C / 8);
-    bn_act_bwd2_kernel<__nv_bfloat16, 8><<<g, 256, 0, stream>>>((const __nv_bfloat16*)dy, (const __nv_bfloat16*)x, (__nv_bfloat16*)dx, save,
+    lvae_launch(bn_act_bwd2_kernel<__nv_bfloat16, 8>, g, 256, 0, stream, (const __nv_bfloat16*)dy, (const __nv_bfloat16*)x, (__nv_bfloat16*)dx, save,
         gamma, beta, acc, dgamma, dbeta, post_scale, (const __nv_bfloat16*)add, nv, P, hw, C, act, training);
   } else {
     int g = ew_grid_aligned(nq, 256, C / 4);
     if (dtype == 0)
-      bn_act_bwd2_kernel<float, 4><<<g, 256, 0, stream>>>((const float*)dy, (const float*)x, (float*)dx, save, gamma, beta, acc, dgamma, dbeta, post_scale, (const float*)add, nq, P, hw, C, act, training);
+      lvae_launch(bn_act_bwd2_kernel<float, 4>, g, 256, 0, stream, (const float*)dy, (const float*)x, (float*)dx, save, gamma, beta, acc, dgamma, dbeta, post_scale, (const float*)add, nq, P, hw, C, act, training);
     else
-      bn_act_bwd2_kernel<__nv_bfloat16, 4><<<g, 256, 0, stream>>>((const __nv_bfloat16*)dy, (const __nv_bfloat16*)x, (__nv_bfloat16*)dx, save, gamma, beta, acc, dgamma, dbeta, post_scale, (const __nv_bfloat16*)add, nq, P, hw, C, act, training);
+      lvae_launch(bn_act_bwd2_kernel<__nv_bfloat16, 4>, g, 256, 0, stream, (const __nv_bfloat16*)dy, (const __nv_bfloat16*)x, (__nv_bfloat16*)dx, save, gamma, beta, acc, dgamma, dbeta, post_scale, (const __nv_bfloat16*)add, nq, P, hw, C, act, training);
   }
   LVAE_COUNT_LAUNCH();
   LVAE_CHECK_LAUNCH("bn_act_bwd2");
@@ -825,6 +862,8 @@ template <> __device__ __forceinline__ float4 round_as<__nv_bfloat16>(float4 v) 
 template <typename T, int V>
 __global__ void gate_fwd_stats_kernel(const T* __restrict__ h, const T* __restrict__ res, T* __restrict__ out,
                                       double* __restrict__ acc, long long nvec, int C, int act) {
+  pdl_wait();
+  pdl_launch();
   extern __shared__ float sm[];
   const int CV = C / V;
   const long long stride = (long long)gridDim.x * blockDim.x;      // multiple of CV (256 % CV == 0)
@@ -882,9 +921,9 @@ LVAE_API int lvae_gate_fwd_stats(const void* h, const void* res, void* out, doub
   long long want = (nv + 255) / 256;
   int g = (int)(want < cap ? (want > 0 ? want : 1) : cap);
   size_t smem = (size_t)256 * V * 2 * sizeof(float);
-  if (V == 8) gate_fwd_stats_kernel<__nv_bfloat16, 8><<<g, 256, smem, stream>>>((const __nv_bfloat16*)h, (const __nv_bfloat16*)res, (__nv_bfloat16*)out, acc, nv, C, act);
-  else if (dtype == 0) gate_fwd_stats_kernel<float, 4><<<g, 256, smem, stream>>>((const float*)h, (const float*)res, (float*)out, acc, nv, C, act);
-  else gate_fwd_stats_kernel<__nv_bfloat16, 4><<<g, 256, smem, stream>>>((const __nv_bfloat16*)h, (const __nv_bfloat16*)res, (__nv_bfloat16*)out, acc, nv, C, act);
+  if (V == 8) lvae_launch(gate_fwd_stats_kernel<__nv_bfloat16, 8>, g, 256, smem, stream, (const __nv_bfloat16*)h, (const __nv_bfloat16*)res, (__nv_bfloat16*)out, acc, nv, C, act);
+  else if (dtype == 0) lvae_launch(gate_fwd_stats_kernel<float, 4>, g, 256, smem, stream, (const float*)h, (const float*)res, (float*)out, acc, nv, C, act);
+  else lvae_launch(gate_fwd_stats_kernel<__nv_bfloat16, 4>, g, 256, smem, stream, (const __nv_bfloat16*)h, (const __nv_bfloat16*)res, (__nv_bfloat16*)out, acc, nv, C, act);
   LVAE_COUNT_LAUNCH();
   LVAE_CHECK_LAUNCH("gate_fwd_stats");
   return LVAE_OK;

@@ -13,6 +13,8 @@
 __global__ void __launch_bounds__(256) bernoulli_fwd_kernel(const float* __restrict__ logits, const float* __restrict__ x,
                                                             float* __restrict__ prob, float* __restrict__ ll,
                                                             int hw, int C) {
+  pdl_wait();
+  pdl_launch();
   __shared__ float red[32];
   const int b = blockIdx.x, n = hw * C;
   float s = 0.f;
@@ -34,6 +36,8 @@ __global__ void __launch_bounds__(256) bernoulli_fwd_kernel(const float* __restr
 __global__ void bernoulli_bwd_kernel(const float* __restrict__ prob, const float* __restrict__ x,
                                      const float* __restrict__ g_ll, const float* __restrict__ g_prob,
                                      float* __restrict__ dlogits, int B, int hw, int C) {
+  pdl_wait();
+  pdl_launch();
   long long total = (long long)B * hw * C;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     int c = (int)(i % C);
@@ -52,7 +56,7 @@ LVAE_API int lvae_bernoulli_fwd(const float* logits, const float* x, float* prob
                                 cudaStream_t stream) {
   LVAE_REQUIRE(logits && prob && B > 0 && hw > 0 && C > 0, "bernoulli_fwd: bad args");
   LVAE_REQUIRE((x == nullptr) == (ll == nullptr), "bernoulli_fwd: x and ll go together");
-  bernoulli_fwd_kernel<<<B, 256, 0, stream>>>(logits, x, prob, ll, hw, C);
+  lvae_launch(bernoulli_fwd_kernel, B, 256, 0, stream, logits, x, prob, ll, hw, C);
   LVAE_COUNT_LAUNCH();
   LVAE_CHECK_LAUNCH("bernoulli_fwd");
   return LVAE_OK;
@@ -63,7 +67,7 @@ LVAE_API int lvae_bernoulli_bwd(const float* prob, const float* x, const float* 
   LVAE_REQUIRE(prob && x && g_ll && dlogits, "bernoulli_bwd: bad args");
   long long n = (long long)B * hw * C;
   int grid = (int)min((long long)4 * lvae_num_sms(), (n + 255) / 256);
-  bernoulli_bwd_kernel<<<grid, 256, 0, stream>>>(prob, x, g_ll, g_prob, dlogits, B, hw, C);
+  lvae_launch(bernoulli_bwd_kernel, grid, 256, 0, stream, prob, x, g_ll, g_prob, dlogits, B, hw, C);
   LVAE_COUNT_LAUNCH();
   LVAE_CHECK_LAUNCH("bernoulli_bwd");
   return LVAE_OK;
@@ -71,6 +75,8 @@ LVAE_API int lvae_bernoulli_bwd(const float* prob, const float* x, const float* 
 
 __global__ void bernoulli_sample_kernel(const float* prob, float* out, long long n, int hw, int C,
                                         const PhiloxState* rng, unsigned long long stream_id) {
+  pdl_wait();
+  pdl_launch();
   // out is NCHW like every image the module API hands back
   PhiloxState st = *rng;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
@@ -88,7 +94,7 @@ LVAE_API int lvae_bernoulli_sample(const float* prob, float* out_nchw, int B, in
   LVAE_REQUIRE(prob && out_nchw && rng_state, "bernoulli_sample: bad args");
   long long n = (long long)B * hw * C;
   int grid = (int)min((long long)4 * lvae_num_sms(), (n + 255) / 256);
-  bernoulli_sample_kernel<<<grid, 256, 0, stream>>>(prob, out_nchw, n, hw, C, (const PhiloxState*)rng_state, stream_id);
+  lvae_launch(bernoulli_sample_kernel, grid, 256, 0, stream, prob, out_nchw, n, hw, C, (const PhiloxState*)rng_state, stream_id);
   LVAE_COUNT_LAUNCH();
   LVAE_CHECK_LAUNCH("bernoulli_sample");
   return LVAE_OK;
@@ -135,6 +141,8 @@ template <bool BWD>
 __global__ void __launch_bounds__(DM_TILE) dmol_kernel(const float* __restrict__ l, const float* __restrict__ x,
                                                        float* __restrict__ ll, const float* __restrict__ g_ll,
                                                        float* __restrict__ dl, int hw) {
+  pdl_wait();
+  pdl_launch();
   extern __shared__ float sm[];  // DM_TILE * DM_PITCH (+32 for the reduction)
   float* red = sm + DM_TILE * DM_PITCH;
   const int b = blockIdx.y;
@@ -255,7 +263,7 @@ LVAE_API int lvae_dmol_fwd(const float* l, const float* x, float* ll, int B, int
     attr = true;
   }
   dim3 grid(cdiv(hw, DM_TILE), B);
-  dmol_kernel<false><<<grid, DM_TILE, DMOL_SMEM, stream>>>(l, x, ll, nullptr, nullptr, hw);
+  lvae_launch(dmol_kernel<false>, grid, DM_TILE, DMOL_SMEM, stream, l, x, ll, nullptr, nullptr, hw);
   LVAE_COUNT_LAUNCH();
   LVAE_CHECK_LAUNCH("dmol_fwd");
   return LVAE_OK;
@@ -270,7 +278,7 @@ LVAE_API int lvae_dmol_bwd(const float* l, const float* x, const float* g_ll, fl
     attr = true;
   }
   dim3 grid(cdiv(hw, DM_TILE), B);
-  dmol_kernel<true><<<grid, DM_TILE, DMOL_SMEM, stream>>>(l, x, nullptr, g_ll, dl, hw);
+  lvae_launch(dmol_kernel<true>, grid, DM_TILE, DMOL_SMEM, stream, l, x, nullptr, g_ll, dl, hw);
   LVAE_COUNT_LAUNCH();
   LVAE_CHECK_LAUNCH("dmol_bwd");
   return LVAE_OK;
@@ -280,6 +288,8 @@ LVAE_API int lvae_dmol_bwd(const float* l, const float* x, const float* g_ll, fl
 // clamp to [-1,1], rescale to [0,1].  One thread per pixel; out is (B,3,H,W) NCHW.
 __global__ void dmol_sample_kernel(const float* __restrict__ l, float* __restrict__ out, long long npix, int hw,
                                    const PhiloxState* rng, unsigned long long stream_id) {
+  pdl_wait();
+  pdl_launch();
   PhiloxState st = *rng;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < npix; i += (long long)gridDim.x * blockDim.x) {
     const float* L = l + i * DM_P;
@@ -321,7 +331,7 @@ LVAE_API int lvae_dmol_sample(const float* l, float* out_nchw, int B, int hw, co
   LVAE_REQUIRE(l && out_nchw && rng_state, "dmol_sample: bad args");
   long long n = (long long)B * hw;
   int grid = (int)min((long long)4 * lvae_num_sms(), (n + 127) / 128);
-  dmol_sample_kernel<<<grid, 128, 0, stream>>>(l, out_nchw, n, hw, (const PhiloxState*)rng_state, stream_id);
+  lvae_launch(dmol_sample_kernel, grid, 128, 0, stream, l, out_nchw, n, hw, (const PhiloxState*)rng_state, stream_id);
   LVAE_COUNT_LAUNCH();
   LVAE_CHECK_LAUNCH("dmol_sample");
   return LVAE_OK;

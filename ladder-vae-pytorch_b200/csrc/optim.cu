@@ -8,6 +8,8 @@
 __global__ void adamax_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                               float* __restrict__ u, long long n, float lr, float b1, float b2, float eps, float wd,
                               const long long* __restrict__ step_count, float grad_scale) {
+  pdl_wait();
+  pdl_launch();
   const double t = (double)(*step_count);
   const float clr = lr / (float)(1.0 - pow((double)b1, t));
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
@@ -21,16 +23,18 @@ __global__ void adamax_kernel(float* __restrict__ p, const float* __restrict__ g
     p[i] = pi - clr * (mi / ui);
   }
 }
-__global__ void step_inc_kernel(long long* s) { *s += 1; }
+__global__ void step_inc_kernel(long long* s) {
+  pdl_wait();
+  pdl_launch(); *s += 1; }
 
 LVAE_API int lvae_adamax_step(float* p, const float* g, float* exp_avg, float* exp_inf, long long n, float lr,
                               float beta1, float beta2, float eps, float weight_decay, long long* step_count_dev,
                               float grad_scale, cudaStream_t stream) {
   LVAE_REQUIRE(p && g && exp_avg && exp_inf && step_count_dev && n > 0, "adamax_step: bad args");
-  step_inc_kernel<<<1, 1, 0, stream>>>(step_count_dev);
+  lvae_launch(step_inc_kernel, 1, 1, 0, stream, step_count_dev);
   LVAE_COUNT_LAUNCH();
   int grid = (int)min((long long)8 * lvae_num_sms(), (n + 255) / 256);
-  adamax_kernel<<<grid, 256, 0, stream>>>(p, g, exp_avg, exp_inf, n, lr, beta1, beta2, eps, weight_decay,
+  lvae_launch(adamax_kernel, grid, 256, 0, stream, p, g, exp_avg, exp_inf, n, lr, beta1, beta2, eps, weight_decay,
                                           step_count_dev, grad_scale);
   LVAE_COUNT_LAUNCH();
   LVAE_CHECK_LAUNCH("adamax_step");
@@ -39,6 +43,8 @@ LVAE_API int lvae_adamax_step(float* p, const float* g, float* exp_avg, float* e
 
 // ---- global L2 norm of a flat arena: out[0] = sqrt(sum p^2) ----
 __global__ void sumsq_kernel(const float* __restrict__ p, long long n, double* __restrict__ acc) {
+  pdl_wait();
+  pdl_launch();
   __shared__ float red[32];
   float s = 0.f;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
@@ -49,6 +55,8 @@ __global__ void sumsq_kernel(const float* __restrict__ p, long long n, double* _
   if (threadIdx.x == 0) atomicAdd(acc, (double)s);
 }
 __global__ void sqrt_finalize_kernel(double* acc, float* out) {
+  pdl_wait();
+  pdl_launch();
   *out = (float)sqrt(*acc);
   *acc = 0.0;
 }
@@ -57,9 +65,9 @@ __global__ void sqrt_finalize_kernel(double* acc, float* out) {
 LVAE_API int lvae_l2_norm(const float* p, long long n, double* acc, float* out, cudaStream_t stream) {
   LVAE_REQUIRE(p && acc && out && n > 0, "l2_norm: bad args");
   int grid = (int)min((long long)4 * lvae_num_sms(), (n + 255) / 256);
-  sumsq_kernel<<<grid, 256, 0, stream>>>(p, n, acc);
+  lvae_launch(sumsq_kernel, grid, 256, 0, stream, p, n, acc);
   LVAE_COUNT_LAUNCH();
-  sqrt_finalize_kernel<<<1, 1, 0, stream>>>(acc, out);
+  lvae_launch(sqrt_finalize_kernel, 1, 1, 0, stream, acc, out);
   LVAE_COUNT_LAUNCH();
   LVAE_CHECK_LAUNCH("l2_norm");
   return LVAE_OK;
@@ -69,6 +77,8 @@ LVAE_API int lvae_l2_norm(const float* p, long long n, double* acc, float* out, 
 // state (B,2) = (running max m, running sum s of exp(elbo - m)); elbo = ll - kl per image.
 __global__ void iw_update_kernel(const float* __restrict__ ll, const float* __restrict__ kl, float* __restrict__ state,
                                  int B, int first) {
+  pdl_wait();
+  pdl_launch();
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= B) return;
   float e = ll[i] - kl[i];
@@ -85,7 +95,7 @@ __global__ void iw_update_kernel(const float* __restrict__ ll, const float* __re
 
 LVAE_API int lvae_iw_lse_update(const float* ll, const float* kl, float* state, int B, int first, cudaStream_t stream) {
   LVAE_REQUIRE(ll && kl && state && B > 0, "iw_lse_update: bad args");
-  iw_update_kernel<<<cdiv(B, 256), 256, 0, stream>>>(ll, kl, state, B, first);
+  lvae_launch(iw_update_kernel, cdiv(B, 256), 256, 0, stream, ll, kl, state, B, first);
   LVAE_COUNT_LAUNCH();
   LVAE_CHECK_LAUNCH("iw_lse_update");
   return LVAE_OK;
@@ -93,6 +103,8 @@ LVAE_API int lvae_iw_lse_update(const float* ll, const float* kl, float* state, 
 
 // states: (R,B,2) gathered from R ranks (R = 1 on one GPU); out[b] = logsumexp over all K samples - log K
 __global__ void iw_combine_kernel(const float* __restrict__ states, float* __restrict__ out, int R, int B, float logK) {
+  pdl_wait();
+  pdl_launch();
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= B) return;
   float m = -INFINITY;
@@ -104,7 +116,7 @@ __global__ void iw_combine_kernel(const float* __restrict__ states, float* __res
 
 LVAE_API int lvae_iw_lse_combine(const float* states, float* out, int R, int B, int K_total, cudaStream_t stream) {
   LVAE_REQUIRE(states && out && R > 0 && B > 0 && K_total > 0, "iw_lse_combine: bad args");
-  iw_combine_kernel<<<cdiv(B, 256), 256, 0, stream>>>(states, out, R, B, logf((float)K_total));
+  lvae_launch(iw_combine_kernel, cdiv(B, 256), 256, 0, stream, states, out, R, B, logf((float)K_total));
   LVAE_COUNT_LAUNCH();
   LVAE_CHECK_LAUNCH("iw_lse_combine");
   return LVAE_OK;

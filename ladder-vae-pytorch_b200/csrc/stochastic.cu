@@ -32,6 +32,8 @@ struct StochArgs {
 
 template <int VEC>
 __global__ void __launch_bounds__(256) stoch_fwd_kernel(StochArgs a) {
+  pdl_wait();
+  pdl_launch();
   __shared__ float red[32];
   const int b = blockIdx.x;
   const int ZV = a.Z / VEC;
@@ -140,8 +142,8 @@ LVAE_API int lvae_stoch_fwd(const float* q, const float* p, int p_broadcast, con
   LVAE_REQUIRE(!z_bf16 || (z_bf16_pitch >= Z && z_bf16_pitch % 4 == 0), "stoch_fwd: bad low-precision pitch");
   StochArgs a{q, p, p_broadcast ? 0LL : (long long)hw * 2 * Z, eps, forced, (const PhiloxState*)rng_state, stream_id,
               z, z_bf16, z_bf16_pitch, kl_sample, kl_spatial, logp, logq, B, hw, Z, use_mode, analytical};
-  if (Z % 4 == 0) stoch_fwd_kernel<4><<<B, 256, 0, stream>>>(a);
-  else stoch_fwd_kernel<1><<<B, 256, 0, stream>>>(a);
+  if (Z % 4 == 0) lvae_launch(stoch_fwd_kernel<4>, B, 256, 0, stream, a);
+  else lvae_launch(stoch_fwd_kernel<1>, B, 256, 0, stream, a);
   LVAE_COUNT_LAUNCH();
   LVAE_CHECK_LAUNCH("stoch_fwd");
   return LVAE_OK;
@@ -160,6 +162,8 @@ struct StochBwdArgs {
 };
 
 __global__ void __launch_bounds__(256) stoch_bwd_kernel(StochBwdArgs a) {
+  pdl_wait();
+  pdl_launch();
   const int b = blockIdx.x;
   const float gkl = a.g_kl ? a.g_kl[b] : 0.f, glp = a.g_logp ? a.g_logp[b] : 0.f, glq = a.g_logq ? a.g_logq[b] : 0.f;
   const float* qb = a.q + (long long)b * a.hw * 2 * a.Z;
@@ -208,7 +212,7 @@ LVAE_API int lvae_stoch_bwd(const float* q, const float* p, int p_broadcast, con
   LVAE_REQUIRE(q && p && z && dq && dp && B > 0, "stoch_bwd: bad args");
   StochBwdArgs a{q, p, p_broadcast ? 0LL : (long long)hw * 2 * Z, z, g_z, g_kl, g_logp, g_logq, g_kls, dq, dp,
                  B, hw, Z, analytical, z_kind};
-  stoch_bwd_kernel<<<B, 256, 0, stream>>>(a);
+  lvae_launch(stoch_bwd_kernel, B, 256, 0, stream, a);
   LVAE_COUNT_LAUNCH();
   LVAE_CHECK_LAUNCH("stoch_bwd");
   return LVAE_OK;

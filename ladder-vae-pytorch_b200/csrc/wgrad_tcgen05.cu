@@ -126,6 +126,8 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();
+  pdl_launch();
 
   if (warp == 0) {
     if (lane == 0) {
@@ -236,6 +238,8 @@ struct RedParams {
 };
 
 __global__ void wgrad_reduce_kernel(RedParams p) {
+  pdl_wait();
+  pdl_launch();
   // grid.y splits the partials: each thread sums its slice of CTAs (independent loads, 4 in flight), then adds
   const int per = p.n_pairs * 128 * p.N;
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
@@ -357,13 +361,13 @@ LVAE_API int lvae_conv2d_wgrad_tc(const void* x, const void* x2, const void* dy,
     if (e != cudaSuccess) { lvae_set_error("conv2d_wgrad_tc: cannot raise dynamic smem: %s", cudaGetErrorString(e)); return LVAE_ERR_CUDA; }
     attr = true;
   }
-  wgrad_tc_kernel<<<grid, WG_THREADS_TC, smem, stream>>>(tmX, tmX2, tmDY, p);
+  lvae_launch(wgrad_tc_kernel, grid, WG_THREADS_TC, smem, stream, tmX, tmX2, tmDY, p);
   LVAE_COUNT_LAUNCH();
   LVAE_CHECK_LAUNCH("conv2d_wgrad_tc");
   rp.ws = ws; rp.dw = dw; rp.dbias = dbias; rp.n_cta = grid; rp.n_pairs = p.n_pairs; rp.N = N; rp.I = 64 * inputs; rp.taps = taps; rp.I_real = I_real > 0 ? I_real : 64 * inputs;
   const int per = p.n_pairs * 128 * N;
   const int ysplit = grid >= 64 ? 8 : (grid >= 16 ? 4 : 1);
-  wgrad_reduce_kernel<<<dim3((per + 255) / 256, ysplit), 256, 0, stream>>>(rp);
+  lvae_launch(wgrad_reduce_kernel, dim3((per + 255) / 256, ysplit), 256, 0, stream, rp);
   LVAE_COUNT_LAUNCH();
   LVAE_CHECK_LAUNCH("wgrad_reduce");
   return LVAE_OK;
