@@ -67,6 +67,8 @@ int lvae_conv2d_tc(const void* x, const void* x2, const void* wp, const float* b
 int lvae_conv2d_wgrad_tc(const void* x, const void* x2, const void* dy, float* dw, float* dbias, float* ws, int B,
                          int H, int W, int N, int ksize, int I_real, lvae_stream_t stream);
 long long lvae_wgrad_tc_workspace(int B, int H, int W, int N, int ksize, int two_inputs);
+/* profiling aid: CTA 0 of subsequent lvae_conv2d_tc launches records clock64 stamps per tile into dev_buf (NULL = off) */
+void lvae_conv2d_tc_debug(long long* dev_buf);
 /* y = x * scale[b,c] (Dropout2d mask on a gradient tensor ahead of the TMA-fed dgrad) */
 int lvae_channel_scale(const void* x, const float* scale, void* y, int B, int HW, int C, int dtype,
                        lvae_stream_t stream);

@@ -14,15 +14,16 @@
 // its own tensor dimension, so a shifted box never bleeds into the neighbouring image).
 // All taps' weights stay resident in shared memory for the lifetime of a persistent CTA.
 //
-// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + single-thread MMA
-// issuer, warps 2..5 = epilogue (TMEM lane quadrant = warp_id % 4).  The accumulator is double
+// Warp roles (320 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + single-thread MMA
+// issuer, warps 2..9 = epilogue (TMEM lane quadrant = warp_id % 4, two warps per quadrant split the columns).  The accumulator is double
 // buffered in TMEM so the epilogue of tile i overlaps the MMAs of tile i+1.
 #include "common.cuh"
 #include <cuda.h>
+#include <stdlib.h>
 
 namespace {
 
-constexpr int TC_THREADS = 192;
+constexpr int TC_THREADS = 320;        // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue (two per TMEM lane quadrant)
 constexpr int TC_BM = 128;             // pixels per tile
 constexpr int TC_BK = 64;              // channels per k-block (= one 128-byte swizzle row of bf16)
 constexpr int TC_STAGE_BYTES = TC_BM * TC_BK * 2;   // 16 KB
@@ -40,6 +41,10 @@ struct TcParams {
   int bw, bh, bn;           // TMA box (pixels) : bw*bh*bn == 128
   int out_f32;              // 1: y is fp32, 0: bf16
   int tmem_cols;
+  // halo mode (3x3, W % 8 == 0, H % 16 == 0): ONE TMA box of 18 rows x 16 columns per 16x8-pixel tile; the nine
+  // tap operands are the same shared-memory tile read through shifted UMMA descriptors (no per-tap re-fetch)
+  int halo, stage_bytes, tiles_x, tiles_per_img, bo_mode;
+  long long* dbg;           // optional per-tile clock64 trace of CTA 0 (profiling aid, normally null)
   int8_t dx[TC_MAX_KB], dy[TC_MAX_KB], src[TC_MAX_KB], coff[TC_MAX_KB];   // coff: channel offset / 64 inside the tensor
 };
 
@@ -89,12 +94,35 @@ __device__ __forceinline__ uint64_t umma_desc_k_sw128(uint32_t saddr) {
   d |= (uint64_t)2 << 61;                            // SWIZZLE_128B
   return d;
 }
+// same, with the 8-row groups sbo bytes apart and a start address that is only 128-byte aligned: the swizzle phase
+// of the first row goes into the base-offset field
+__device__ __forceinline__ uint64_t umma_desc_k_sw128_shifted(uint32_t saddr, uint32_t sbo_bytes, int bo_mode) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(sbo_bytes >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  if (bo_mode) d |= (uint64_t)((saddr >> 7) & 7) << 49;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
 __device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
       "setp.ne.b32 p, %4, 0;\n\t"
       "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
       ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// one elected lane of a fully converged warp (lets ptxas keep the MMA operands in uniform registers instead of
+// wrapping every tcgen05.mma in a per-lane broadcast loop)
+__device__ __forceinline__ uint32_t elect_one() {
+  uint32_t pred = 0;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred;
 }
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
@@ -151,7 +179,9 @@ __device__ __forceinline__ void epilogue16(const uint32_t* __restrict__ r, const
         v[4 * q] *= s4.x; v[4 * q + 1] *= s4.y; v[4 * q + 2] *= s4.z; v[4 * q + 3] *= s4.w;
       }
     } else {
-      for (int j = 0; j < 16 && c0 + j < N; ++j) v[j] *= __ldg(scale_row + c0 + j);
+#pragma unroll
+      for (int j = 0; j < 16; ++j)                  // static indexing keeps v[] in registers
+        if (c0 + j < N) v[j] *= __ldg(scale_row + c0 + j);
     }
   }
   if (OUT_F32) {
@@ -168,7 +198,9 @@ __device__ __forceinline__ void epilogue16(const uint32_t* __restrict__ r, const
 #pragma unroll
       for (int q = 0; q < 4; ++q) reinterpret_cast<float4*>(o)[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
     } else {
-      for (int j = 0; j < nvalid; ++j) o[j] = v[j] + (rr ? __ldg(rr + j) : 0.f);
+#pragma unroll
+      for (int j = 0; j < 16; ++j)
+        if (j < nvalid) o[j] = v[j] + (rr ? __ldg(rr + j) : 0.f);
     }
   } else {
     __nv_bfloat16* o = (__nv_bfloat16*)out_row + cc;
@@ -195,7 +227,9 @@ __device__ __forceinline__ void epilogue16(const uint32_t* __restrict__ r, const
       reinterpret_cast<uint4*>(o)[0] = w0;
       reinterpret_cast<uint4*>(o)[1] = w1;
     } else {
-      for (int j = 0; j < nvalid; ++j) o[j] = __float2bfloat16(v[j] + (rr ? __bfloat162float(rr[j]) : 0.f));
+#pragma unroll
+      for (int j = 0; j < 16; ++j)
+        if (j < nvalid) o[j] = __float2bfloat16(v[j] + (rr ? __bfloat162float(rr[j]) : 0.f));
     }
   }
 }
@@ -209,7 +243,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
   const int wbytes_kb = p.Npad * 128;                        // one k-block of weights
   uint8_t* sW = smem;                                        // n_kb * Npad * 128
   uint8_t* sA = sW + ((p.n_kb * wbytes_kb + 1023) & ~1023);  // n_stages * 16 KB
-  uint64_t* bars = (uint64_t*)(sA + p.n_stages * TC_STAGE_BYTES);
+  const int stage_bytes = p.halo ? p.stage_bytes : TC_STAGE_BYTES;
+  uint64_t* bars = (uint64_t*)(sA + p.n_stages * stage_bytes);
   // barrier layout: [0..S) full, [S..2S) empty, 2S: weights, 2S+1..2S+2: tmem_full[2], 2S+3..2S+4: tmem_empty[2]
   const int S = p.n_stages;
   uint32_t* tmem_slot = (uint32_t*)(bars + 2 * S + 5);
@@ -218,7 +253,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
   auto BAR = [&](int i) { return bar0 + 8u * (uint32_t)i; };
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int n_tiles = (p.M_total + TC_BM - 1) / TC_BM;
+  const int n_tiles = p.halo ? (p.M_total / (p.H * p.W)) * p.tiles_per_img : (p.M_total + TC_BM - 1) / TC_BM;
 
   if (threadIdx.x == 0) {
     prefetch_tmap(&tmA0);
@@ -231,12 +266,18 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     mbar_init(BAR(2 * S), 1);
     mbar_init(BAR(2 * S + 1), 1);
     mbar_init(BAR(2 * S + 2), 1);
-    mbar_init(BAR(2 * S + 3), 4);      // one arrive per epilogue warp
-    mbar_init(BAR(2 * S + 4), 4);
+    mbar_init(BAR(2 * S + 3), 8);      // one arrive per epilogue warp
+    mbar_init(BAR(2 * S + 4), 8);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) {
+    __syncwarp();
     // weights were packed many kernels ago: fetch them before waiting on the previous kernel (PDL prologue)
-    mbar_expect_tx(BAR(2 * S), (uint32_t)(p.n_kb * wbytes_kb));
-    for (int kb = 0; kb < p.n_kb; ++kb) tma_load_2d(smem_u32(sW + kb * wbytes_kb), &tmW, BAR(2 * S), 0, kb * p.Npad);
+    if (elect_one()) {
+      mbar_expect_tx(BAR(2 * S), (uint32_t)(p.n_kb * wbytes_kb));
+      for (int kb = 0; kb < p.n_kb; ++kb) tma_load_2d(smem_u32(sW + kb * wbytes_kb), &tmW, BAR(2 * S), 0, kb * p.Npad);
+    }
+    __syncwarp();
   }
   for (int i = threadIdx.x; i < p.Npad; i += TC_THREADS) sbias[i] = (p.bias && i < p.N) ? p.bias[i] : 0.f;
   if (warp == 1) {
@@ -251,12 +292,26 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
   pdl_launch();
 
   if (warp == 0) {
-    // ===================== TMA producer =====================
-    if (lane == 0) {
+    // ===================== TMA producer (whole warp loops, one elected lane issues) =====================
+    {
       int stage = 0;
       uint32_t phase = 0;
       const int hw = p.H * p.W;
       for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        if (p.halo) {
+          int n0 = tile / p.tiles_per_img;
+          int r = tile - n0 * p.tiles_per_img;
+          int ty = r / p.tiles_x, tx = r - ty * p.tiles_x;
+          mbar_wait(BAR(S + stage), phase ^ 1);
+          if (p.dbg && blockIdx.x == 0 && lane == 0) p.dbg[(tile / gridDim.x) * 8 + 6] = clock64();
+          if (elect_one()) {
+            mbar_expect_tx(BAR(stage), (uint32_t)stage_bytes);
+            tma_load_4d(smem_u32(sA + stage * stage_bytes), &tmA0, BAR(stage), 0, tx * 8 - 1, ty * 16 - 1, n0);
+          }
+          __syncwarp();
+          if (++stage == S) { stage = 0; phase ^= 1; }
+          continue;
+        }
         int p0 = tile * TC_BM;
         int n0 = p0 / hw;
         int rem = p0 - n0 * hw;
@@ -264,18 +319,24 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         int w0 = rem - h0 * p.W;
         for (int kb = 0; kb < p.n_kb; ++kb) {
           mbar_wait(BAR(S + stage), phase ^ 1);
-          mbar_expect_tx(BAR(stage), TC_STAGE_BYTES);
-          tma_load_4d(smem_u32(sA + stage * TC_STAGE_BYTES), p.src[kb] ? &tmA1 : &tmA0, BAR(stage), 64 * p.coff[kb],
-                      w0 + p.dx[kb], h0 + p.dy[kb], n0);
+          if (elect_one()) {
+            mbar_expect_tx(BAR(stage), TC_STAGE_BYTES);
+            tma_load_4d(smem_u32(sA + stage * TC_STAGE_BYTES), p.src[kb] ? &tmA1 : &tmA0, BAR(stage), 64 * p.coff[kb],
+                        w0 + p.dx[kb], h0 + p.dy[kb], n0);
+          }
+          __syncwarp();
           if (++stage == S) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
+    // The whole warp runs the loop (converged); one elected lane issues tcgen05.mma / tcgen05.commit, so ptxas keeps
+    // descriptors and the TMEM address in uniform registers.
+    {
       // instruction descriptor: D fp32, A/B bf16, both K-major, M = 128, N = Npad
       const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.Npad >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+      const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
       mbar_wait(BAR(2 * S), 0);
       tc_fence_after();
       int stage = 0;
@@ -286,40 +347,77 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         const uint32_t use = (uint32_t)(it >> 1);
         mbar_wait(BAR(2 * S + 3 + buf), (use & 1) ^ 1);      // epilogue drained this accumulator
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + (uint32_t)(buf * p.Npad);
+        const uint32_t d_tmem = tmem_u + (uint32_t)(buf * p.Npad);
+        if (p.halo) {
+          if (p.dbg && blockIdx.x == 0 && lane == 0) p.dbg[it * 8 + 0] = clock64();
+          mbar_wait(BAR(stage), phase);
+          tc_fence_after();
+          if (p.dbg && blockIdx.x == 0 && lane == 0) p.dbg[it * 8 + 1] = clock64();
+          const uint32_t a_base = smem_u32(sA + stage * stage_bytes);
+          if (elect_one()) {
+            for (int kb = 0; kb < p.n_kb; ++kb) {
+              // tap (dy,dx): the tile's first pixel sits at halo row 1+dy, halo column 1+dx; rows are 16 pixels (2048 B)
+              const uint32_t a_start = a_base + (uint32_t)(((1 + p.dy[kb]) * 16 + (1 + p.dx[kb])) * 128);
+              const uint64_t adesc = umma_desc_k_sw128_shifted(a_start, 2048, p.bo_mode);
+              const uint64_t bdesc = umma_desc_k_sw128(smem_u32(sW + kb * wbytes_kb));
+#pragma unroll
+              for (int k = 0; k < TC_BK / 16; ++k)
+                umma_bf16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (uint32_t)((kb | k) != 0));
+            }
+            umma_commit(BAR(S + stage));
+            umma_commit(BAR(2 * S + 1 + buf));
+          }
+          __syncwarp();
+          if (++stage == S) { stage = 0; phase ^= 1; }
+          if (p.dbg && blockIdx.x == 0 && lane == 0) p.dbg[it * 8 + 2] = clock64();
+          continue;
+        }
         for (int kb = 0; kb < p.n_kb; ++kb) {
           mbar_wait(BAR(stage), phase);
           tc_fence_after();
-          const uint64_t adesc = umma_desc_k_sw128(smem_u32(sA + stage * TC_STAGE_BYTES));
-          const uint64_t bdesc = umma_desc_k_sw128(smem_u32(sW + kb * wbytes_kb));
+          if (elect_one()) {
+            const uint64_t adesc = umma_desc_k_sw128(smem_u32(sA + stage * TC_STAGE_BYTES));
+            const uint64_t bdesc = umma_desc_k_sw128(smem_u32(sW + kb * wbytes_kb));
 #pragma unroll
-          for (int k = 0; k < TC_BK / 16; ++k) {
-            // advance 16 bf16 = 32 bytes along K inside the swizzle atom: +2 in the (addr >> 4) field
-            umma_bf16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (uint32_t)((kb | k) != 0));
+            for (int k = 0; k < TC_BK / 16; ++k) {
+              // advance 16 bf16 = 32 bytes along K inside the swizzle atom: +2 in the (addr >> 4) field
+              umma_bf16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (uint32_t)((kb | k) != 0));
+            }
+            umma_commit(BAR(S + stage));                       // frees the smem stage when these MMAs retire
           }
-          umma_commit(BAR(S + stage));                         // frees the smem stage when these MMAs retire
+          __syncwarp();
           if (++stage == S) { stage = 0; phase ^= 1; }
         }
-        umma_commit(BAR(2 * S + 1 + buf));                     // accumulator ready for the epilogue
+        if (elect_one()) umma_commit(BAR(2 * S + 1 + buf));    // accumulator ready for the epilogue
+        __syncwarp();
       }
     }
   } else {
-    // ===================== epilogue (4 warps) =====================
+    // ===================== epilogue (8 warps: quadrant x column half) =====================
     const int quad = warp & 3;                                 // TMEM lane quadrant this warp may read
+    const int half = (warp - 2) >> 2;                          // which 32-column chunks (even / odd) this warp drains
     const int row = quad * 32 + lane;
     const int hw = p.H * p.W;
     int it = 0;
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
       const int buf = it & 1;
       const uint32_t use = (uint32_t)(it >> 1);
+      if (p.dbg && blockIdx.x == 0 && warp == 2 && lane == 0) p.dbg[it * 8 + 3] = clock64();
       mbar_wait(BAR(2 * S + 1 + buf), use & 1);
       tc_fence_after();
-      const long long m = (long long)tile * TC_BM + row;
+      if (p.dbg && blockIdx.x == 0 && warp == 2 && lane == 0) p.dbg[it * 8 + 4] = clock64();
+      long long m = (long long)tile * TC_BM + row;
+      if (p.halo) {
+        int n0 = tile / p.tiles_per_img;
+        int r = tile - n0 * p.tiles_per_img;
+        int ty = r / p.tiles_x, tx = r - ty * p.tiles_x;
+        m = ((long long)n0 * p.H + ty * 16 + (row >> 3)) * p.W + tx * 8 + (row & 7);
+      }
       const bool valid = m < p.M_total;
       const int b = valid ? (int)(m / hw) : 0;
       const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * p.Npad);
       const float* scale_row = p.out_scale ? p.out_scale + (long long)b * p.N : nullptr;
-      for (int c0 = 0; c0 < p.Npad; c0 += 32) {
+      for (int c0 = 32 * half; c0 < p.Npad; c0 += 64) {
         uint32_t r[32];
         const bool two = c0 + 32 <= p.Npad;
         if (two) tmem_ld32_nowait(taddr + (uint32_t)c0, r);      // warp-collective: all lanes participate
@@ -344,6 +442,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
       }
       tc_fence_before();
       __syncwarp();
+      if (p.dbg && blockIdx.x == 0 && warp == 2 && lane == 0) p.dbg[it * 8 + 5] = clock64();
       if (lane == 0) mbar_arrive(BAR(2 * S + 3 + buf));
     }
   }
@@ -368,6 +467,8 @@ EncodeTiledFn get_encode() {
   }
   return fn;
 }
+
+long long* g_tc_dbg = nullptr;
 
 int pow2_floor_le(int v, int cap) {
   int r = 1;
@@ -400,6 +501,7 @@ LVAE_API int lvae_conv2d_tc(const void* x, const void* x2, const void* wp, const
   p.bias = bias; p.out_scale = out_scale; p.res = res; p.y = y; p.y2 = y2; p.nsplit = nsplit;
   p.M_total = B * H * W; p.H = H; p.W = W; p.N = N; p.Npad = (N + 15) / 16 * 16;
   p.out_f32 = out_f32;
+  p.dbg = g_tc_dbg;
   const int inputs = x2 ? 2 : 1;
   const int taps = ksize * ksize;
   const int cblocks = Cin / 64;
@@ -423,17 +525,31 @@ LVAE_API int lvae_conv2d_tc(const void* x, const void* x2, const void* wp, const
   LVAE_REQUIRE(p.tmem_cols <= 512, "conv2d_tc: accumulator does not fit TMEM");
   const int wbytes = ((p.n_kb * p.Npad * 128) + 1023) & ~1023;
   const int max_smem = 227 * 1024 - 1024 /*align*/ - 2048 /*barriers + bias*/;
-  int stages = (max_smem - wbytes) / TC_STAGE_BYTES;
+  static int halo_env = -1, bo_env = 0;
+  if (halo_env < 0) {
+    const char* e = getenv("LVAE_CONV_HALO");
+    halo_env = e ? atoi(e) : 1;
+    const char* b = getenv("LVAE_HALO_BO");
+    bo_env = b ? atoi(b) : 0;   // the hardware swizzle is a function of the absolute shared-memory address: no base offset
+  }
+  p.halo = (halo_env && ksize == 3 && !x2 && Cin == 64 && W % 8 == 0 && H % 16 == 0 &&
+            (max_smem - wbytes) / (18 * 16 * 128) >= 2) ? 1 : 0;
+  p.stage_bytes = 18 * 16 * 128;
+  p.tiles_x = W / 8;
+  p.tiles_per_img = (W / 8) * (H / 16);
+  p.bo_mode = bo_env;
+  int stages = (max_smem - wbytes) / (p.halo ? p.stage_bytes : TC_STAGE_BYTES);
   if (stages > 8) stages = 8;
   LVAE_REQUIRE(stages >= 2, "conv2d_tc: weights leave no room for the activation pipeline");
   p.n_stages = stages;
-  const size_t smem = 1024 + (size_t)wbytes + (size_t)stages * TC_STAGE_BYTES + 2048;
+  const size_t smem = 1024 + (size_t)wbytes + (size_t)stages * (p.halo ? p.stage_bytes : TC_STAGE_BYTES) + 2048;
 
   CUtensorMap tmA0, tmA1, tmW;
   {
     cuuint64_t gdim[4] = {(cuuint64_t)Cin, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
     cuuint64_t gstr[3] = {(cuuint64_t)Cin * 2, (cuuint64_t)W * Cin * 2, (cuuint64_t)H * W * Cin * 2};
     cuuint32_t box[4] = {64, (cuuint32_t)p.bw, (cuuint32_t)p.bh, (cuuint32_t)p.bn};
+    if (p.halo) { box[1] = 16; box[2] = 18; box[3] = 1; }
     cuuint32_t estr[4] = {1, 1, 1, 1};
     CUresult r = enc(&tmA0, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, (void*)x, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                      CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -455,10 +571,15 @@ LVAE_API int lvae_conv2d_tc(const void* x, const void* x2, const void* wp, const
     if (e != cudaSuccess) { lvae_set_error("conv2d_tc: cannot raise dynamic smem: %s", cudaGetErrorString(e)); return LVAE_ERR_CUDA; }
     attr_smem = 227 * 1024;
   }
-  const int n_tiles = (p.M_total + TC_BM - 1) / TC_BM;
+  const int n_tiles = p.halo ? B * p.tiles_per_img : (p.M_total + TC_BM - 1) / TC_BM;
   const int grid = n_tiles < lvae_num_sms() ? n_tiles : lvae_num_sms();
   lvae_launch(conv_tc_kernel, grid, TC_THREADS, smem, stream, tmA0, tmA1, tmW, p);
   LVAE_COUNT_LAUNCH();
   LVAE_CHECK_LAUNCH("conv2d_tc");
   return LVAE_OK;
 }
+
+// profiling aid: device buffer (>= 8 * tiles-per-CTA int64) that CTA 0 of the following conv2d_tc launches fills with
+// clock64 stamps per tile: [0] MMA thread ready, [1] operands landed, [2] MMAs issued, [3] epilogue waiting,
+// [4] accumulator ready, [5] epilogue done, [6] producer got a free stage.  NULL switches it off.
+LVAE_API void lvae_conv2d_tc_debug(long long* dev_buf) { g_tc_dbg = dev_buf; }

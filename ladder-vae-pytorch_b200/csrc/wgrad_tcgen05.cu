@@ -75,6 +75,15 @@ __device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t adesc, uint6
       "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
       ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
 }
+__device__ __forceinline__ uint32_t elect_one() {
+  uint32_t pred = 0;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred;
+}
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
@@ -130,8 +139,8 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
   pdl_launch();
 
   if (warp == 0) {
-    if (lane == 0) {
-      // ===================== TMA producer =====================
+    {
+      // ===================== TMA producer (whole warp loops, one elected lane issues) =====================
       const int hw = p.H * p.W;
       int ps = 0, bs = 0;
       uint32_t pph = 0, bph = 0;
@@ -142,28 +151,35 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
         int h0 = rem / p.W;
         int w0 = rem - h0 * p.W;
         mbar_wait(BAR(10 + bs), bph ^ 1);
-        mbar_expect_tx(BAR(8 + bs), (uint32_t)(p.n_bblk * WG_BLK_BYTES));
-        for (int j = 0; j < p.n_bblk; ++j)
-          tma_load_4d(smem_u32(sB + (bs * p.n_bblk + j) * WG_BLK_BYTES), &tmDY, BAR(8 + bs), 64 * j, w0, h0, n0);
+        if (elect_one()) {
+          mbar_expect_tx(BAR(8 + bs), (uint32_t)(p.n_bblk * WG_BLK_BYTES));
+          for (int j = 0; j < p.n_bblk; ++j)
+            tma_load_4d(smem_u32(sB + (bs * p.n_bblk + j) * WG_BLK_BYTES), &tmDY, BAR(8 + bs), 64 * j, w0, h0, n0);
+        }
+        __syncwarp();
         if (++bs == WG_B_SLOTS) { bs = 0; bph ^= 1; }
         for (int pr = 0; pr < p.n_pairs; ++pr) {
           mbar_wait(BAR(4 + ps), pph ^ 1);
-          int nload = 0;
-          for (int h = 0; h < 2; ++h) nload += p.a_src[2 * pr + h] < 2 ? 1 : 0;
-          mbar_expect_tx(BAR(ps), (uint32_t)(nload * WG_BLK_BYTES));
-          for (int h = 0; h < 2; ++h) {
-            int src = p.a_src[2 * pr + h];
-            if (src < 2)
-              tma_load_4d(smem_u32(sPair + (ps * 2 + h) * WG_BLK_BYTES), src ? &tmX2 : &tmX, BAR(ps), 0,
-                          w0 + p.a_dx[2 * pr + h], h0 + p.a_dy[2 * pr + h], n0);
+          if (elect_one()) {
+            int nload = 0;
+            for (int h = 0; h < 2; ++h) nload += p.a_src[2 * pr + h] < 2 ? 1 : 0;
+            mbar_expect_tx(BAR(ps), (uint32_t)(nload * WG_BLK_BYTES));
+            for (int h = 0; h < 2; ++h) {
+              int src = p.a_src[2 * pr + h];
+              if (src < 2)
+                tma_load_4d(smem_u32(sPair + (ps * 2 + h) * WG_BLK_BYTES), src ? &tmX2 : &tmX, BAR(ps), 0,
+                            w0 + p.a_dx[2 * pr + h], h0 + p.a_dy[2 * pr + h], n0);
+            }
           }
+          __syncwarp();
           if (++ps == WG_PAIR_SLOTS) { ps = 0; pph ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      // ===================== MMA issuer =====================
+    {
+      // ===================== MMA issuer (whole warp loops, one elected lane issues) =====================
+      const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
       // D fp32, A/B bf16, both MN-major, M = 128, N = 64 * n_bblk
       const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) |
                              ((uint32_t)(N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
@@ -180,21 +196,26 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
           // second 64-row block: the slot's own second half, or the constant ones tile
           const uint32_t a2 = p.a_src[2 * pr + 1] == 2 ? smem_u32(sOnes) : a_addr + WG_BLK_BYTES;
           const uint32_t lbo_a = a2 - a_addr;
-          const uint32_t d_tmem = tmem_base + (uint32_t)(pr * N);
+          const uint32_t d_tmem = tmem_u + (uint32_t)(pr * N);
+          if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < WG_TILE / 16; ++k) {
-            // 16 pixels = two 8-row swizzle atoms = 2048 bytes along K; the ones tile is constant, so the
-            // same LBO works for it at every k (a_k + LBO stays inside its 16 KB)
-            umma_bf16(d_tmem, umma_desc_mn_sw128(a_addr + k * 2048, lbo_a), umma_desc_mn_sw128(b_addr + k * 2048, WG_BLK_BYTES),
-                      idesc, (uint32_t)((tile != tile_beg) || k != 0));
+            for (int k = 0; k < WG_TILE / 16; ++k) {
+              // 16 pixels = two 8-row swizzle atoms = 2048 bytes along K; the ones tile is constant, so the
+              // same LBO works for it at every k (a_k + LBO stays inside its 16 KB)
+              umma_bf16(d_tmem, umma_desc_mn_sw128(a_addr + k * 2048, lbo_a), umma_desc_mn_sw128(b_addr + k * 2048, WG_BLK_BYTES),
+                        idesc, (uint32_t)((tile != tile_beg) || k != 0));
+            }
+            umma_commit(BAR(4 + ps));
           }
-          umma_commit(BAR(4 + ps));
+          __syncwarp();
           if (++ps == WG_PAIR_SLOTS) { ps = 0; pph ^= 1; }
         }
-        umma_commit(BAR(10 + bs));
+        if (elect_one()) umma_commit(BAR(10 + bs));
+        __syncwarp();
         if (++bs == WG_B_SLOTS) { bs = 0; bph ^= 1; }
       }
-      umma_commit(BAR(12));
+      if (elect_one()) umma_commit(BAR(12));
+      __syncwarp();
     }
   } else {
     // ===================== epilogue: TMEM -> fp32 partial in the workspace =====================

@@ -11,7 +11,7 @@ from lvae_b200 import _capi, ops  # noqa: E402
 
 B, C = 256, 64
 one = len(sys.argv) > 1 and sys.argv[1] == "--one"
-shapes = [(16, 3, 64)] if one else [(32, 3, 64), (16, 3, 64), (8, 3, 64), (4, 3, 64), (2, 3, 64), (16, 1, 128), (32, 3, 100)]
+shapes = [(int(os.environ.get("HW", "16")), 3, 64)] if one else [(32, 3, 64), (16, 3, 64), (8, 3, 64), (4, 3, 64), (2, 3, 64), (16, 1, 128), (32, 3, 100)]
 s = torch.cuda.current_stream()
 for HW, k, N in shapes:
     per = B * HW * HW * (C + N) * 2
