@@ -20,6 +20,7 @@
 #include "common.cuh"
 #include <cuda.h>
 #include <stdlib.h>
+#include <string.h>
 
 namespace {
 
@@ -44,6 +45,7 @@ struct TcParams {
   // halo mode (3x3, W % 8 == 0, H % 16 == 0): ONE TMA box of 18 rows x 16 columns per 16x8-pixel tile; the nine
   // tap operands are the same shared-memory tile read through shifted UMMA descriptors (no per-tap re-fetch)
   int halo, stage_bytes, tiles_x, tiles_per_img, bo_mode;
+  int tma_store;            // bf16 output, N % 64 == 0, no residual: epilogue stages the tile in smem and stores it with TMA
   long long* dbg;           // optional per-tile clock64 trace of CTA 0 (profiling aid, normally null)
   int8_t dx[TC_MAX_KB], dy[TC_MAX_KB], src[TC_MAX_KB], coff[TC_MAX_KB];   // coff: channel offset / 64 inside the tensor
 };
@@ -80,6 +82,10 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* tm,
   asm volatile(
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
       ::"r"(dst), "l"(tm), "r"(bar), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* tm, uint32_t src, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+               ::"l"(tm), "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
 }
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* tm) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(tm) : "memory");
@@ -236,7 +242,8 @@ __device__ __forceinline__ void epilogue16(const uint32_t* __restrict__ r, const
 
 __global__ void __launch_bounds__(TC_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
-               const __grid_constant__ CUtensorMap tmW, const TcParams p) {
+               const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmY,
+               const __grid_constant__ CUtensorMap tmY2, const TcParams p) {
   extern __shared__ uint8_t smem_raw[];
   // 1024-byte alignment for the 128B swizzle atoms
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -244,7 +251,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
   uint8_t* sW = smem;                                        // n_kb * Npad * 128
   uint8_t* sA = sW + ((p.n_kb * wbytes_kb + 1023) & ~1023);  // n_stages * 16 KB
   const int stage_bytes = p.halo ? p.stage_bytes : TC_STAGE_BYTES;
-  uint64_t* bars = (uint64_t*)(sA + p.n_stages * stage_bytes);
+  uint8_t* sOut = sA + p.n_stages * stage_bytes;             // (N/64) x 16 KB output staging (TMA-store epilogue only)
+  uint64_t* bars = (uint64_t*)(sOut + (p.tma_store ? (p.Npad / 64) * TC_STAGE_BYTES : 0));
   // barrier layout: [0..S) full, [S..2S) empty, 2S: weights, 2S+1..2S+2: tmem_full[2], 2S+3..2S+4: tmem_empty[2]
   const int S = p.n_stages;
   uint32_t* tmem_slot = (uint32_t*)(bars + 2 * S + 5);
@@ -417,6 +425,74 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
       const int b = valid ? (int)(m / hw) : 0;
       const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * p.Npad);
       const float* scale_row = p.out_scale ? p.out_scale + (long long)b * p.N : nullptr;
+      if (p.tma_store) {
+        // ---- TMEM -> registers (bias, Dropout2d scale, bf16 pack), release the accumulator, stage in smem, TMA store ----
+        uint4 packed[2][4];
+#pragma unroll
+        for (int nch = 0; nch < 2; ++nch) {                      // N <= 128 on this path: at most two chunks per thread
+          const int c0 = 32 * half + 64 * nch;
+          if (c0 >= p.Npad) break;
+          uint32_t r[32];
+          tmem_ld32_nowait(taddr + (uint32_t)c0, r);
+          tmem_wait_ld();
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            float v[8];
+            const float4 b0 = *reinterpret_cast<const float4*>(sbias + c0 + 8 * q), b1 = *reinterpret_cast<const float4*>(sbias + c0 + 8 * q + 4);
+            v[0] = __uint_as_float(r[8 * q]) + b0.x; v[1] = __uint_as_float(r[8 * q + 1]) + b0.y;
+            v[2] = __uint_as_float(r[8 * q + 2]) + b0.z; v[3] = __uint_as_float(r[8 * q + 3]) + b0.w;
+            v[4] = __uint_as_float(r[8 * q + 4]) + b1.x; v[5] = __uint_as_float(r[8 * q + 5]) + b1.y;
+            v[6] = __uint_as_float(r[8 * q + 6]) + b1.z; v[7] = __uint_as_float(r[8 * q + 7]) + b1.w;
+            if (scale_row) {
+              const float4 s0 = __ldg(reinterpret_cast<const float4*>(scale_row + c0 + 8 * q));
+              const float4 s1 = __ldg(reinterpret_cast<const float4*>(scale_row + c0 + 8 * q + 4));
+              v[0] *= s0.x; v[1] *= s0.y; v[2] *= s0.z; v[3] *= s0.w; v[4] *= s1.x; v[5] *= s1.y; v[6] *= s1.z; v[7] *= s1.w;
+            }
+            __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&packed[nch][q]);
+            h2[0] = __floats2bfloat162_rn(v[0], v[1]); h2[1] = __floats2bfloat162_rn(v[2], v[3]);
+            h2[2] = __floats2bfloat162_rn(v[4], v[5]); h2[3] = __floats2bfloat162_rn(v[6], v[7]);
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(BAR(2 * S + 3 + buf));          // accumulator free again: next-but-one tile may start
+        // the previous tile's TMA store must have finished reading the staging buffer
+        if (threadIdx.x == 64) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+#pragma unroll
+        for (int nch = 0; nch < 2; ++nch) {
+          const int c0 = 32 * half + 64 * nch;
+          if (c0 >= p.Npad) break;
+          uint8_t* blk = sOut + (c0 >> 6) * TC_STAGE_BYTES + row * 128;
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const int chunk = ((c0 & 63) >> 3) + q;
+            *reinterpret_cast<uint4*>(blk + ((chunk ^ (row & 7)) << 4)) = packed[nch][q];
+          }
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        if (threadIdx.x == 64) {
+          int c1, c2, c3;
+          if (p.halo) {
+            int n0 = tile / p.tiles_per_img;
+            int r2 = tile - n0 * p.tiles_per_img;
+            c3 = n0; c2 = (r2 / p.tiles_x) * 16; c1 = (r2 % p.tiles_x) * 8;
+          } else {
+            int p0 = tile * TC_BM;
+            c3 = p0 / hw;
+            int rem = p0 - c3 * hw;
+            c2 = rem / p.W; c1 = rem - c2 * p.W;
+          }
+          for (int j = 0; j < p.Npad / 64; ++j) {
+            const bool second = p.y2 != nullptr && j * 64 >= p.nsplit;
+            tma_store_4d(second ? &tmY2 : &tmY, smem_u32(sOut + j * TC_STAGE_BYTES), second ? j * 64 - p.nsplit : j * 64, c1, c2, c3);
+          }
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
+        if (p.dbg && blockIdx.x == 0 && warp == 2 && lane == 0) p.dbg[it * 8 + 5] = clock64();
+        continue;
+      }
       for (int c0 = 32 * half; c0 < p.Npad; c0 += 64) {
         uint32_t r[32];
         const bool two = c0 + 32 <= p.Npad;
@@ -446,6 +522,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
       if (lane == 0) mbar_arrive(BAR(2 * S + 3 + buf));
     }
   }
+  if (p.tma_store && threadIdx.x == 64) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   tc_fence_before();
   __syncthreads();
   if (warp == 1) {
@@ -532,19 +609,40 @@ LVAE_API int lvae_conv2d_tc(const void* x, const void* x2, const void* wp, const
     const char* b = getenv("LVAE_HALO_BO");
     bo_env = b ? atoi(b) : 0;   // the hardware swizzle is a function of the absolute shared-memory address: no base offset
   }
+  static int tst_env = -1;
+  if (tst_env < 0) { const char* e = getenv("LVAE_CONV_TMA_STORE"); tst_env = e ? atoi(e) : 1; }
+  p.tma_store = (tst_env && !out_f32 && N % 64 == 0 && N <= 128 && !res && (!y2 || nsplit % 64 == 0)) ? 1 : 0;
+  const int out_stage = p.tma_store ? (p.Npad / 64) * TC_STAGE_BYTES : 0;
   p.halo = (halo_env && ksize == 3 && !x2 && Cin == 64 && W % 8 == 0 && H % 16 == 0 &&
-            (max_smem - wbytes) / (18 * 16 * 128) >= 2) ? 1 : 0;
+            (max_smem - wbytes - out_stage) / (18 * 16 * 128) >= 2) ? 1 : 0;
   p.stage_bytes = 18 * 16 * 128;
   p.tiles_x = W / 8;
   p.tiles_per_img = (W / 8) * (H / 16);
   p.bo_mode = bo_env;
-  int stages = (max_smem - wbytes) / (p.halo ? p.stage_bytes : TC_STAGE_BYTES);
+  int stages = (max_smem - wbytes - out_stage) / (p.halo ? p.stage_bytes : TC_STAGE_BYTES);
   if (stages > 8) stages = 8;
   LVAE_REQUIRE(stages >= 2, "conv2d_tc: weights leave no room for the activation pipeline");
   p.n_stages = stages;
-  const size_t smem = 1024 + (size_t)wbytes + (size_t)stages * (p.halo ? p.stage_bytes : TC_STAGE_BYTES) + 2048;
+  const size_t smem = 1024 + (size_t)wbytes + (size_t)stages * (p.halo ? p.stage_bytes : TC_STAGE_BYTES) + out_stage + 2048;
 
-  CUtensorMap tmA0, tmA1, tmW;
+  CUtensorMap tmA0, tmA1, tmW, tmY, tmY2;
+  memset(&tmY, 0, sizeof(tmY));
+  memset(&tmY2, 0, sizeof(tmY2));
+  if (p.tma_store) {
+    // output maps: same pixel box as the activation tiles (8 x 16 pixels in halo mode), 64 channels per box
+    for (int which = 0; which < (y2 ? 2 : 1); ++which) {
+      const int ncols = y2 ? (which ? N - nsplit : nsplit) : N;
+      cuuint64_t gdim[4] = {(cuuint64_t)ncols, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+      cuuint64_t gstr[3] = {(cuuint64_t)ncols * 2, (cuuint64_t)W * ncols * 2, (cuuint64_t)H * W * ncols * 2};
+      cuuint32_t box[4] = {64, (cuuint32_t)p.bw, (cuuint32_t)p.bh, (cuuint32_t)p.bn};
+      if (p.halo) { box[1] = 8; box[2] = 16; box[3] = 1; }
+      cuuint32_t estr[4] = {1, 1, 1, 1};
+      CUresult r = enc(which ? &tmY2 : &tmY, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, which ? y2 : y, gdim, gstr, box, estr,
+                       CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                       CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (r != CUDA_SUCCESS) { lvae_set_error("conv2d_tc: tensor map (y) encode failed: %d", (int)r); return LVAE_ERR_CUDA; }
+    }
+  }
   {
     cuuint64_t gdim[4] = {(cuuint64_t)Cin, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
     cuuint64_t gstr[3] = {(cuuint64_t)Cin * 2, (cuuint64_t)W * Cin * 2, (cuuint64_t)H * W * Cin * 2};
@@ -573,7 +671,7 @@ LVAE_API int lvae_conv2d_tc(const void* x, const void* x2, const void* wp, const
   }
   const int n_tiles = p.halo ? B * p.tiles_per_img : (p.M_total + TC_BM - 1) / TC_BM;
   const int grid = n_tiles < lvae_num_sms() ? n_tiles : lvae_num_sms();
-  lvae_launch(conv_tc_kernel, grid, TC_THREADS, smem, stream, tmA0, tmA1, tmW, p);
+  lvae_launch(conv_tc_kernel, grid, TC_THREADS, smem, stream, tmA0, tmA1, tmW, tmY, tmY2, p);
   LVAE_COUNT_LAUNCH();
   LVAE_CHECK_LAUNCH("conv2d_tc");
   return LVAE_OK;
