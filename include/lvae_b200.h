@@ -67,6 +67,22 @@ int lvae_conv2d_tc(const void* x, const void* x2, const void* wp, const float* b
 int lvae_conv2d_wgrad_tc(const void* x, const void* x2, const void* dy, float* dw, float* dbias, float* ws, int B,
                          int H, int W, int N, int ksize, int I_real, lvae_stream_t stream);
 long long lvae_wgrad_tc_workspace(int B, int H, int W, int N, int ksize, int two_inputs);
+/* Same with per-channel reductions fused into the epilogue (bf16 output, N == 64, no residual / split):
+ *   stats_acc  [2*64] += sum / sum-of-squares of the output as stored (the next BatchNorm's statistics),
+ *   bnb_*      BatchNorm-backward sums over this data-gradient output dy: bnb_acc [2*64] += sum(g), sum(g*xhat) with
+ *              xhat = (bnb_x - mean)*rstd, g = dy * act'(xhat*gamma + beta); bnb_save = [mean | rstd]. */
+typedef struct {
+  double* stats_acc;
+  const void* bnb_x;
+  const float* bnb_save;
+  const float* bnb_gamma;
+  const float* bnb_beta;
+  double* bnb_acc;
+  int bnb_act;
+} LvaeConvFuse;
+int lvae_conv2d_tc_ex(const void* x, const void* x2, const void* wp, const float* bias, const float* out_scale,
+                      const void* res, void* y, void* y2, int nsplit, int B, int H, int W, int Cin, int N, int ksize,
+                      int flip, int out_f32, const LvaeConvFuse* fuse, lvae_stream_t stream);
 /* profiling aid: CTA 0 of subsequent lvae_conv2d_tc launches records clock64 stamps per tile into dev_buf (NULL = off) */
 void lvae_conv2d_tc_debug(long long* dev_buf);
 /* y = x * scale[b,c] (Dropout2d mask on a gradient tensor ahead of the TMA-fed dgrad) */
@@ -110,7 +126,7 @@ int lvae_bn_act_fwd2(const void* x, void* y, const double* acc, const float* gam
 int lvae_bn_act_bwd2(const void* dy, const void* x, void* dx, const float* save, const float* gamma,
                      const float* beta, double* acc, float* dgamma, float* dbeta, const float* post_scale,
                      const void* add, long long P, int hw, int C, int act, int training, int dtype,
-                     lvae_stream_t stream);
+                     int skip_reduce, lvae_stream_t stream);
 
 /* ---- GateLayer2d product + residual: lib/nn.py:121-126 and :99 ----
  * h (P,2C): out = act(h[:, :C]) * sigmoid(h[:, C:]) + res */

@@ -22,6 +22,7 @@ _SIGNATURES = {
     "lvae_conv2d_wgrad": [P, P, P, P, P, P, P, I, I, I, I, I, I, I, I, I, I, I, I, I, P],
     "lvae_pack_weights": [P, I, P],
     "lvae_conv2d_tc": [P, P, P, P, P, P, P, P, I, I, I, I, I, I, I, I, I, P],
+    "lvae_conv2d_tc_ex": [P, P, P, P, P, P, P, P, I, I, I, I, I, I, I, I, I, P, P],
     "lvae_channel_scale": [P, P, P, I, I, I, I, P],
     "lvae_conv2d_wgrad_tc": [P, P, P, P, P, P, I, I, I, I, I, I, P],
     "lvae_colsum": [P, P, P, I, I, I, I, P],
@@ -31,7 +32,7 @@ _SIGNATURES = {
     "lvae_bn_act_fwd": [P, P, P, P, P, P, L, I, I, I, I, P],
     "lvae_bn_act_bwd": [P, P, P, P, P, P, P, P, P, P, L, I, I, I, I, P],
     "lvae_bn_act_fwd2": [P, P, P, P, P, P, P, P, P, L, I, I, I, F, F, I, I, P],
-    "lvae_bn_act_bwd2": [P, P, P, P, P, P, P, P, P, P, P, L, I, I, I, I, I, P],
+    "lvae_bn_act_bwd2": [P, P, P, P, P, P, P, P, P, P, P, L, I, I, I, I, I, I, P],
     "lvae_gate_fwd_stats": [P, P, P, P, L, I, I, I, P],
     "lvae_gate_fwd": [P, P, P, L, I, I, I, P],
     "lvae_gate_bwd": [P, P, P, L, I, I, I, P],
@@ -66,6 +67,12 @@ _SPECIAL = {
     "lvae_get_pdl": ([], c_int),
     "lvae_wgrad_tc_workspace": ([I, I, I, I, I, I], c_longlong),
 }
+
+
+class ConvFuse(ctypes.Structure):
+    """LvaeConvFuse of include/lvae_b200.h."""
+    _fields_ = [("stats_acc", c_void_p), ("bnb_x", c_void_p), ("bnb_save", c_void_p), ("bnb_gamma", c_void_p),
+                ("bnb_beta", c_void_p), ("bnb_acc", c_void_p), ("bnb_act", c_int)]
 
 
 def exported_symbols():

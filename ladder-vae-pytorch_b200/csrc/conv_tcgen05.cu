@@ -45,6 +45,12 @@ struct TcParams {
   // halo mode (3x3, W % 8 == 0, H % 16 == 0): ONE TMA box of 18 rows x 16 columns per 16x8-pixel tile; the nine
   // tap operands are the same shared-memory tile read through shifted UMMA descriptors (no per-tap re-fetch)
   int halo, stage_bytes, tiles_x, tiles_per_img, bo_mode;
+  // reductions fused into the TMA-store epilogue (N == 64 only)
+  double* stats_acc;        // += per-channel sum / sum of squares of the output as stored (next BatchNorm's statistics)
+  const __nv_bfloat16* bnb_x;   // BatchNorm-backward reduction over this dgrad's output: BN input x (M,64)
+  const float* bnb_save; const float* bnb_gamma; const float* bnb_beta;
+  double* bnb_acc;          // += sum(g), sum(g * xhat), g = dy * act'(xhat*gamma+beta)
+  int bnb_act;
   int tma_store;            // bf16 output, N % 64 == 0, no residual: epilogue stages the tile in smem and stores it with TMA
   long long* dbg;           // optional per-tile clock64 trace of CTA 0 (profiling aid, normally null)
   int8_t dx[TC_MAX_KB], dy[TC_MAX_KB], src[TC_MAX_KB], coff[TC_MAX_KB];   // coff: channel offset / 64 inside the tensor
@@ -167,6 +173,21 @@ __device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, uint32_t* r) {
 }
 __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
+// v[j] (j = 0..31) holds this lane's (row's) value for channel j.  Returns in v[0] the sum over the 32 lanes (rows)
+// of channel `lane`: a transposing butterfly, 31 shuffles instead of 32 x 5.
+__device__ __forceinline__ void warp_transpose_sum32(float* v, int lane) {
+#pragma unroll
+  for (int s = 16; s >= 1; s >>= 1) {
+    const bool up = (lane & s) != 0;
+#pragma unroll
+    for (int j = 0; j < s; ++j) {
+      const float send = up ? v[j] : v[j + s];
+      const float keep = up ? v[j + s] : v[j];
+      v[j] = keep + __shfl_xor_sync(0xffffffffu, send, s);
+    }
+  }
+}
+
 // Epilogue for 16 accumulator columns [c0, c0+16) of one output row: bias (shared memory), Dropout2d scale,
 // residual, conversion, vectorised store.  All global reads go through the read-only path so that the
 // compiler can batch them instead of ordering them against the stores.
@@ -257,6 +278,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
   const int S = p.n_stages;
   uint32_t* tmem_slot = (uint32_t*)(bars + 2 * S + 5);
   float* sbias = (float*)(bars + 32);                         // Npad floats (<= 256), zero beyond N / when bias == null
+  float* sbn = sbias + 256;                                   // [mean | rstd | gamma | beta] x 64 (fused BatchNorm-backward reduction)
+  float* sred = sbn + 256;                                    // 4 x 8 warps x 32 lanes reduction scratch
   const uint32_t bar0 = smem_u32(bars);
   auto BAR = [&](int i) { return bar0 + 8u * (uint32_t)i; };
 
@@ -288,6 +311,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     __syncwarp();
   }
   for (int i = threadIdx.x; i < p.Npad; i += TC_THREADS) sbias[i] = (p.bias && i < p.N) ? p.bias[i] : 0.f;
+  if (p.bnb_acc && threadIdx.x < 64) {                          // parameters / saved statistics: written long before this kernel
+    sbn[threadIdx.x] = p.bnb_save[threadIdx.x];
+    sbn[64 + threadIdx.x] = p.bnb_save[64 + threadIdx.x];
+    sbn[128 + threadIdx.x] = p.bnb_gamma[threadIdx.x];
+    sbn[192 + threadIdx.x] = p.bnb_beta[threadIdx.x];
+  }
   if (warp == 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(p.tmem_cols) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -406,6 +435,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     const int half = (warp - 2) >> 2;                          // which 32-column chunks (even / odd) this warp drains
     const int row = quad * 32 + lane;
     const int hw = p.H * p.W;
+    float red0 = 0.f, red1 = 0.f, red2 = 0.f, red3 = 0.f;      // per-lane (= channel 32*half + lane) running sums
     int it = 0;
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
       const int buf = it & 1;
@@ -435,22 +465,71 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
           uint32_t r[32];
           tmem_ld32_nowait(taddr + (uint32_t)c0, r);
           tmem_wait_ld();
+          float f[32];
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            const float4 b4 = *reinterpret_cast<const float4*>(sbias + c0 + 4 * q);
+            f[4 * q] = __uint_as_float(r[4 * q]) + b4.x; f[4 * q + 1] = __uint_as_float(r[4 * q + 1]) + b4.y;
+            f[4 * q + 2] = __uint_as_float(r[4 * q + 2]) + b4.z; f[4 * q + 3] = __uint_as_float(r[4 * q + 3]) + b4.w;
+            if (scale_row) {
+              const float4 s4 = __ldg(reinterpret_cast<const float4*>(scale_row + c0 + 4 * q));
+              f[4 * q] *= s4.x; f[4 * q + 1] *= s4.y; f[4 * q + 2] *= s4.z; f[4 * q + 3] *= s4.w;
+            }
+          }
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
-            float v[8];
-            const float4 b0 = *reinterpret_cast<const float4*>(sbias + c0 + 8 * q), b1 = *reinterpret_cast<const float4*>(sbias + c0 + 8 * q + 4);
-            v[0] = __uint_as_float(r[8 * q]) + b0.x; v[1] = __uint_as_float(r[8 * q + 1]) + b0.y;
-            v[2] = __uint_as_float(r[8 * q + 2]) + b0.z; v[3] = __uint_as_float(r[8 * q + 3]) + b0.w;
-            v[4] = __uint_as_float(r[8 * q + 4]) + b1.x; v[5] = __uint_as_float(r[8 * q + 5]) + b1.y;
-            v[6] = __uint_as_float(r[8 * q + 6]) + b1.z; v[7] = __uint_as_float(r[8 * q + 7]) + b1.w;
-            if (scale_row) {
-              const float4 s0 = __ldg(reinterpret_cast<const float4*>(scale_row + c0 + 8 * q));
-              const float4 s1 = __ldg(reinterpret_cast<const float4*>(scale_row + c0 + 8 * q + 4));
-              v[0] *= s0.x; v[1] *= s0.y; v[2] *= s0.z; v[3] *= s0.w; v[4] *= s1.x; v[5] *= s1.y; v[6] *= s1.z; v[7] *= s1.w;
-            }
             __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&packed[nch][q]);
-            h2[0] = __floats2bfloat162_rn(v[0], v[1]); h2[1] = __floats2bfloat162_rn(v[2], v[3]);
-            h2[2] = __floats2bfloat162_rn(v[4], v[5]); h2[3] = __floats2bfloat162_rn(v[6], v[7]);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) h2[e] = __floats2bfloat162_rn(f[8 * q + 2 * e], f[8 * q + 2 * e + 1]);
+          }
+          if (nch == 0 && (p.stats_acc || p.bnb_acc)) {
+            // values as stored (bf16-rounded); rows past the end of the tensor contribute nothing
+#pragma unroll
+            for (int j = 0; j < 32; ++j) f[j] = valid ? __bfloat162float(__float2bfloat16(f[j])) : 0.f;
+            if (p.stats_acc) {
+              float sq[32];
+#pragma unroll
+              for (int j = 0; j < 32; ++j) sq[j] = f[j] * f[j];
+              if (!p.bnb_acc) {
+                warp_transpose_sum32(f, lane);
+                red0 += f[0];
+              } else {
+                float cp[32];
+#pragma unroll
+                for (int j = 0; j < 32; ++j) cp[j] = f[j];
+                warp_transpose_sum32(cp, lane);
+                red0 += cp[0];
+              }
+              warp_transpose_sum32(sq, lane);
+              red1 += sq[0];
+            }
+            if (p.bnb_acc) {
+              // g = dy * act'(xhat*gamma + beta), accumulate sum(g) and sum(g*xhat) per channel
+              float xh[32];
+              const __nv_bfloat16* xr = p.bnb_x + (valid ? m : 0) * 64 + c0;
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                const uint4 u = __ldg(reinterpret_cast<const uint4*>(xr) + q);
+                const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  const float2 t = __bfloat1622float2(h2[e]);
+                  xh[8 * q + 2 * e] = t.x; xh[8 * q + 2 * e + 1] = t.y;
+                }
+              }
+#pragma unroll
+              for (int j = 0; j < 32; ++j) {
+                const int c = c0 + j;
+                const float xhat = (xh[j] - sbn[c]) * sbn[64 + c];
+                const float g = f[j] * act_bwd(xhat * sbn[128 + c] + sbn[192 + c], p.bnb_act);
+                f[j] = g;
+                xh[j] = g * xhat;
+              }
+              warp_transpose_sum32(f, lane);
+              warp_transpose_sum32(xh, lane);
+              red2 += f[0];
+              red3 += xh[0];
+            }
           }
         }
         tc_fence_before();
@@ -521,6 +600,22 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
       if (p.dbg && blockIdx.x == 0 && warp == 2 && lane == 0) p.dbg[it * 8 + 5] = clock64();
       if (lane == 0) mbar_arrive(BAR(2 * S + 3 + buf));
     }
+    if (p.stats_acc || p.bnb_acc) {
+      // combine the four lane quadrants (rows) per channel, one double atomic per channel and statistic per CTA
+      const int e = warp - 2;                                      // 0..7 = half * 4 + quad-order
+      sred[(0 * 8 + e) * 32 + lane] = red0;
+      sred[(1 * 8 + e) * 32 + lane] = red1;
+      sred[(2 * 8 + e) * 32 + lane] = red2;
+      sred[(3 * 8 + e) * 32 + lane] = red3;
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      const int t = threadIdx.x - 64;                              // 0..255 -> (statistic, channel)
+      const int st = t >> 6, c = t & 63, hf = c >> 5, l = c & 31;
+      float sum = 0.f;
+#pragma unroll
+      for (int qd = 0; qd < 4; ++qd) sum += sred[(st * 8 + hf * 4 + qd) * 32 + l];
+      if (st < 2) { if (p.stats_acc) atomicAdd(p.stats_acc + (st == 0 ? c : 64 + c), (double)sum); }
+      else if (p.bnb_acc) atomicAdd(p.bnb_acc + (st == 2 ? c : 64 + c), (double)sum);
+    }
   }
   if (p.tma_store && threadIdx.x == 64) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   tc_fence_before();
@@ -559,9 +654,31 @@ int pow2_floor_le(int v, int cap) {
 // wp: bf16 [n_kb][Npad][64] (k-block = tap-major, then input): see lvae_pack_weights modes 2/3.
 // taps: ksize*ksize offsets; flip = 1 negates them (data gradient).  y: (B,H,W,N) bf16 or fp32;
 // y2 != NULL splits the output columns at nsplit into two tensors (dgrad of a merge conv).
+struct LvaeConvFuse {
+  double* stats_acc;
+  const void* bnb_x;
+  const float* bnb_save;
+  const float* bnb_gamma;
+  const float* bnb_beta;
+  double* bnb_acc;
+  int bnb_act;
+};
+
+LVAE_API int lvae_conv2d_tc_ex(const void* x, const void* x2, const void* wp, const float* bias, const float* out_scale,
+                               const void* res, void* y, void* y2, int nsplit, int B, int H, int W, int Cin, int N,
+                               int ksize, int flip, int out_f32, const LvaeConvFuse* fuse, cudaStream_t stream);
+
 LVAE_API int lvae_conv2d_tc(const void* x, const void* x2, const void* wp, const float* bias, const float* out_scale,
                             const void* res, void* y, void* y2, int nsplit, int B, int H, int W, int Cin, int N,
                             int ksize, int flip, int out_f32, cudaStream_t stream) {
+  return lvae_conv2d_tc_ex(x, x2, wp, bias, out_scale, res, y, y2, nsplit, B, H, W, Cin, N, ksize, flip, out_f32, nullptr, stream);
+}
+
+// fuse (host struct, may be NULL): per-channel reductions computed in the epilogue, see LvaeConvFuse in include/lvae_b200.h.
+// Only on the TMA-store path (bf16 output, N == 64, no residual); anything else is rejected.
+LVAE_API int lvae_conv2d_tc_ex(const void* x, const void* x2, const void* wp, const float* bias, const float* out_scale,
+                               const void* res, void* y, void* y2, int nsplit, int B, int H, int W, int Cin, int N,
+                               int ksize, int flip, int out_f32, const LvaeConvFuse* fuse, cudaStream_t stream) {
   LVAE_REQUIRE(x && wp && y, "conv2d_tc: null pointer");
   LVAE_REQUIRE(Cin % 64 == 0 && Cin >= 64 && Cin <= 256 && (ksize == 1 || ksize == 3),
                "conv2d_tc: needs a multiple of 64 input channels per tensor and a 1x1 or 3x3 kernel");
@@ -579,6 +696,12 @@ LVAE_API int lvae_conv2d_tc(const void* x, const void* x2, const void* wp, const
   p.M_total = B * H * W; p.H = H; p.W = W; p.N = N; p.Npad = (N + 15) / 16 * 16;
   p.out_f32 = out_f32;
   p.dbg = g_tc_dbg;
+  if (fuse) {
+    p.stats_acc = fuse->stats_acc;
+    p.bnb_x = (const __nv_bfloat16*)fuse->bnb_x; p.bnb_save = fuse->bnb_save; p.bnb_gamma = fuse->bnb_gamma;
+    p.bnb_beta = fuse->bnb_beta; p.bnb_acc = fuse->bnb_acc; p.bnb_act = fuse->bnb_act;
+    LVAE_REQUIRE(!p.bnb_acc || (p.bnb_x && p.bnb_save && p.bnb_gamma && p.bnb_beta), "conv2d_tc: incomplete BatchNorm-backward fusion arguments");
+  }
   const int inputs = x2 ? 2 : 1;
   const int taps = ksize * ksize;
   const int cblocks = Cin / 64;
@@ -601,7 +724,7 @@ LVAE_API int lvae_conv2d_tc(const void* x, const void* x2, const void* wp, const
   while (p.tmem_cols < 2 * p.Npad) p.tmem_cols *= 2;
   LVAE_REQUIRE(p.tmem_cols <= 512, "conv2d_tc: accumulator does not fit TMEM");
   const int wbytes = ((p.n_kb * p.Npad * 128) + 1023) & ~1023;
-  const int max_smem = 227 * 1024 - 1024 /*align*/ - 2048 /*barriers + bias*/;
+  const int max_smem = 227 * 1024 - 1024 /*align*/ - 8192 /*barriers, bias, BatchNorm table, reduction scratch*/;
   static int halo_env = -1, bo_env = 0;
   if (halo_env < 0) {
     const char* e = getenv("LVAE_CONV_HALO");
@@ -613,6 +736,8 @@ LVAE_API int lvae_conv2d_tc(const void* x, const void* x2, const void* wp, const
   if (tst_env < 0) { const char* e = getenv("LVAE_CONV_TMA_STORE"); tst_env = e ? atoi(e) : 1; }
   p.tma_store = (tst_env && !out_f32 && N % 64 == 0 && N <= 128 && !res && (!y2 || nsplit % 64 == 0)) ? 1 : 0;
   const int out_stage = p.tma_store ? (p.Npad / 64) * TC_STAGE_BYTES : 0;
+  LVAE_REQUIRE(!(p.stats_acc || p.bnb_acc) || (p.tma_store && N == 64 && !y2),
+               "conv2d_tc: fused reductions need the TMA-store path (bf16 output, N == 64, no residual, no split)");
   p.halo = (halo_env && ksize == 3 && !x2 && Cin == 64 && W % 8 == 0 && H % 16 == 0 &&
             (max_smem - wbytes - out_stage) / (18 * 16 * 128) >= 2) ? 1 : 0;
   p.stage_bytes = 18 * 16 * 128;
@@ -623,7 +748,7 @@ LVAE_API int lvae_conv2d_tc(const void* x, const void* x2, const void* wp, const
   if (stages > 8) stages = 8;
   LVAE_REQUIRE(stages >= 2, "conv2d_tc: weights leave no room for the activation pipeline");
   p.n_stages = stages;
-  const size_t smem = 1024 + (size_t)wbytes + (size_t)stages * (p.halo ? p.stage_bytes : TC_STAGE_BYTES) + out_stage + 2048;
+  const size_t smem = 1024 + (size_t)wbytes + (size_t)stages * (p.halo ? p.stage_bytes : TC_STAGE_BYTES) + out_stage + 8192;
 
   CUtensorMap tmA0, tmA1, tmW, tmY, tmY2;
   memset(&tmY, 0, sizeof(tmY));

@@ -827,12 +827,14 @@ LVAE_API int lvae_bn_act_fwd2(const void* x, void* y, const double* acc, const f
 LVAE_API int lvae_bn_act_bwd2(const void* dy, const void* x, void* dx, const float* save, const float* gamma,
                               const float* beta, double* acc, float* dgamma, float* dbeta, const float* post_scale,
                               const void* add, long long P, int hw, int C, int act, int training, int dtype,
-                              cudaStream_t stream) {
+                              int skip_reduce, cudaStream_t stream) {
   LVAE_REQUIRE(dy && x && dx && save && gamma && beta && acc && P > 0 && bn_c_ok(C), "bn_act_bwd2: bad args");
   long long nq = P * (C / 4);
-  launch_bwd_reduce(dy, x, save, save + C, gamma, beta, acc, P, C, act, dtype, stream);
-  LVAE_COUNT_LAUNCH();
-  LVAE_CHECK_LAUNCH("bn_act_bwd_reduce");
+  if (!skip_reduce) {            // the producer of dy (tcgen05 dgrad epilogue) may already have accumulated the sums
+    launch_bwd_reduce(dy, x, save, save + C, gamma, beta, acc, P, C, act, dtype, stream);
+    LVAE_COUNT_LAUNCH();
+    LVAE_CHECK_LAUNCH("bn_act_bwd_reduce");
+  }
   if (use_v8(dtype, C)) {
     long long nv = P * (C / 8);
     int g = ew_grid_aligned(nv, 256, C / 8);

@@ -7,6 +7,7 @@ and nothing falls back to ATen for the hot ops; a missing library raises.
 """
 from __future__ import annotations
 
+import ctypes
 import struct
 import threading
 from contextlib import contextmanager
@@ -335,8 +336,15 @@ def _wgrad_workspace(device) -> torch.Tensor:
     return ws
 
 
-def _conv_tc(x, x2, wp, bias, out_scale, res, N, ksize, flip, out_f32, nsplit=0):
-    """Launch the tcgen05 kernel.  Returns y, or (y, y2) when nsplit splits the output columns."""
+def _tc_fusable(N, out_f32, res, nsplit=0) -> bool:
+    """Can the conv's epilogue carry a fused per-channel reduction (TMA-store path of lvae_conv2d_tc)?"""
+    return N == 64 and not out_f32 and res is None and not nsplit
+
+
+def _conv_tc(x, x2, wp, bias, out_scale, res, N, ksize, flip, out_f32, nsplit=0, stats_acc=None, bnb=None):
+    """Launch the tcgen05 kernel.  Returns y, or (y, y2) when nsplit splits the output columns.
+    stats_acc: (2,64) float64 accumulator for the output's per-channel statistics; bnb = (x, save, gamma, beta, acc, act):
+    BatchNorm-backward sums over the output (both fused into the epilogue)."""
     B, H, W, C = x.shape
     odt = torch.float32 if out_f32 else torch.bfloat16
     if nsplit:
@@ -344,8 +352,17 @@ def _conv_tc(x, x2, wp, bias, out_scale, res, N, ksize, flip, out_f32, nsplit=0)
         y2 = torch.empty((B, H, W, N - nsplit), dtype=odt, device=x.device)
     else:
         y, y2 = torch.empty((B, H, W, N), dtype=odt, device=x.device), None
-    call("lvae_conv2d_tc", x.data_ptr(), _p(x2), wp.data_ptr(), _p(bias), _p(out_scale), _p(res), y.data_ptr(), _p(y2),
-         nsplit, B, H, W, C, N, ksize, 1 if flip else 0, 1 if out_f32 else 0, _stream())
+    fuse = None
+    if stats_acc is not None or bnb is not None:
+        f = _capi.ConvFuse()
+        f.stats_acc = _p(stats_acc)
+        if bnb is not None:
+            bx, bsave, bgamma, bbeta, bacc, bact = bnb
+            f.bnb_x, f.bnb_save, f.bnb_gamma, f.bnb_beta = bx.data_ptr(), bsave.data_ptr(), bgamma.data_ptr(), bbeta.data_ptr()
+            f.bnb_acc, f.bnb_act = bacc.data_ptr(), int(bact)
+        fuse = ctypes.addressof(f)
+    call("lvae_conv2d_tc_ex", x.data_ptr(), _p(x2), wp.data_ptr(), _p(bias), _p(out_scale), _p(res), y.data_ptr(), _p(y2),
+         nsplit, B, H, W, C, N, ksize, 1 if flip else 0, 1 if out_f32 else 0, fuse, _stream())
     return (y, y2) if nsplit else y
 
 
@@ -356,7 +373,7 @@ def _gather(x, x2, wp, ld, bias, in_scale, out_scale, res, B, Hi, Wi, C1, C2, Ho
     return y
 
 
-def conv_forward_raw(spec: ConvSpec, xn, x2n, weight, bias, out_scale, resn):
+def conv_forward_raw(spec: ConvSpec, xn, x2n, weight, bias, out_scale, resn, stats_acc=None):
     """(conv(cat(xn, x2n)) + bias) * out_scale + resn on NHWC tensors.  bf16 activations on eligible shapes run on
     the tensor cores (lvae_conv2d_tc), everything else on the CUDA-core implicit GEMM (lvae_conv2d_gather)."""
     B, Hi, Wi, C1 = xn.shape
@@ -370,18 +387,22 @@ def conv_forward_raw(spec: ConvSpec, xn, x2n, weight, bias, out_scale, resn):
     if spec.tc_forward_ok(xn, x2n) and (resn is None or resn.dtype == (torch.float32 if want_f32 else torch.bfloat16)):
         wp = spec.pack_tc_fwd.get(weight, torch.bfloat16)
         stats["tc_fwd"] += 1
-        return _conv_tc(xn, x2n, wp, bias, out_scale, resn, spec.cout, spec.k, False, want_f32)
+        fused = stats_acc is not None and _tc_fusable(spec.cout, want_f32, resn)
+        y = _conv_tc(xn, x2n, wp, bias, out_scale, resn, spec.cout, spec.k, False, want_f32,
+                     stats_acc=stats_acc if fused else None)
+        return (y, fused) if stats_acc is not None else y
     wp = spec.pack_fwd.get(weight, xn.dtype)
     if resn is not None and resn.dtype != xn.dtype:
         resn = resn.to(xn.dtype)
     stats["cc_fwd"] += 1
     y = _gather(xn, x2n, wp, spec.pack_fwd.ld, bias, None, out_scale, resn, B, Hi, Wi, C1, C2, Ho, Wo,
                 spec.cout, spec.k, spec.stride, spec.pad, 1 if spec.transposed else 0, xn.dtype)
-    return y.float() if want_f32 else y
+    y = y.float() if want_f32 else y
+    return (y, False) if stats_acc is not None else y
 
 
 def conv_backward_raw(spec: ConvSpec, xn, x2n, weight, bias, out_scale, gyn, need_x=True, need_w=True, need_b=True,
-                      dx_scale=None):
+                      dx_scale=None, bnb=None):
     """Data and parameter gradients of conv_forward_raw.  ``out_scale`` is the forward's Dropout2d mask (gyn is the
     gradient wrt the masked output; pass None when gyn is already the gradient wrt the raw conv output).
     ``dx_scale`` (B, Cin) is folded into the dgrad epilogue: the returned dx is multiplied by it (the mask of the
@@ -392,6 +413,7 @@ def conv_backward_raw(spec: ConvSpec, xn, x2n, weight, bias, out_scale, gyn, nee
     C2 = x2n.shape[3] if x2n is not None else 0
     _, Ho, Wo, N = gyn.shape
     gx = gx2 = gw = gb = None
+    conv_backward_raw.last_fused = False
     use_tc = xn.dtype == torch.bfloat16 and spec.tc_dgrad_ok(gyn)
     padded = x2n is None and C1 > spec.cin
     if padded and not use_tc:
@@ -406,7 +428,12 @@ def conv_backward_raw(spec: ConvSpec, xn, x2n, weight, bias, out_scale, gyn, nee
             wpb = spec.pack_tc_bwd.get(weight, torch.bfloat16)
             stats["tc_dgrad"] += 1
             if x2n is None:
-                gx = _conv_tc(gyn, None, wpb, None, dx_scale, None, spec.cin, spec.k, True, False)
+                fuse_bnb = bnb is not None and not padded and _tc_fusable(spec.cin, False, None)
+                gx = _conv_tc(gyn, None, wpb, None, dx_scale, None, spec.cin, spec.k, True, False,
+                              bnb=bnb if fuse_bnb else None)
+                if fuse_bnb:
+                    stats["bnb_fused"] = stats.get("bnb_fused", 0) + 1
+                    conv_backward_raw.last_fused = True
                 if padded:          # gradient wrt the zero-padded input: the padding channels get zeros
                     gx = torch.nn.functional.pad(gx, (0, C1 - spec.cin))
             else:
@@ -629,8 +656,16 @@ class GatedBlockFn(Function):
             return out
 
         a1 = bn_fwd(xn, bn1, sc1, saves[0], g1, b1, x_stats)
-        y1 = conv_forward_raw(conv1.spec, a1, None, w1, cb1, m1, None)
-        a2 = bn_fwd(y1, bn2, sc2, saves[1], g2, b2)
+        acc2 = None
+        if training and C == 64:
+            acc2 = sc2[0:2]
+            _bn_clean(bn2, acc2, "fwd")
+            y1, fused = conv_forward_raw(conv1.spec, a1, None, w1, cb1, m1, None, stats_acc=acc2)   # BN2 statistics in the epilogue
+            if not fused:
+                call("lvae_bn_stats", y1.data_ptr(), acc2.data_ptr(), Pn, C, dt, _stream())
+        else:
+            y1 = conv_forward_raw(conv1.spec, a1, None, w1, cb1, m1, None)
+        a2 = bn_fwd(y1, bn2, sc2, saves[1], g2, b2, acc2)
         y2 = conv_forward_raw(conv2.spec, a2, None, w2, cb2, m2, None)
         h = conv_forward_raw(gconv.spec, y2, None, wg, gbias, None, None)
         out = torch.empty_like(xn)
@@ -662,25 +697,31 @@ class GatedBlockFn(Function):
         call("lvae_gate_bwd", gn.data_ptr(), h.data_ptr(), dh.data_ptr(), Pn, C, gact, dt, _stream())
         # 1x1 gate conv: dgrad carries conv2's Dropout2d mask in its epilogue -> gradient wrt conv2's raw output
         dy2, _, gwg, ggb = conv_backward_raw(gconv.spec, y2, None, wg, gbias, None, dh, True, ng[9], ng[10], dx_scale=m2)
-        # conv2 (dy2 is already masked)
-        da2, _, gw2, gcb2 = conv_backward_raw(conv2.spec, a2, None, w2, cb2, None, dy2, True, ng[7], ng[8])
+        sc1b, sc2b = bn_scratch(bn1, dev), bn_scratch(bn2, dev)
+        acc1b, acc2b = sc1b[2:4], sc2b[2:4]
+        _bn_clean(bn1, acc1b, "bwd")
+        _bn_clean(bn2, acc2b, "bwd")
+        # conv2 (dy2 is already masked); its dgrad epilogue also accumulates BN2's backward sums
+        da2, _, gw2, gcb2 = conv_backward_raw(conv2.spec, a2, None, w2, cb2, None, dy2, True, ng[7], ng[8],
+                                              bnb=(y1, saves[1], g2, b2, acc2b, act) if C == 64 else None)
+        fused2 = conv_backward_raw.last_fused
 
-        def bn_bwd(dy, xin, bn, sc, save, gamma, beta, post_scale, add):
-            acc = sc[2:4]
-            _bn_clean(bn, acc, "bwd")
+        def bn_bwd(dy, xin, bn, acc, save, gamma, beta, post_scale, add, skip_reduce):
             dgam, gsunk = _param_grad_buffer(gamma)
             dbet, bsunk = _param_grad_buffer(beta)
             dxo = torch.empty_like(xin)
             call("lvae_bn_act_bwd2", dy.data_ptr(), xin.data_ptr(), dxo.data_ptr(), save.data_ptr(), gamma.data_ptr(),
                  beta.data_ptr(), acc.data_ptr(), dgam.data_ptr(), dbet.data_ptr(), _p(post_scale), _p(add), Pn, H * W, C,
-                 act, 1 if training else 0, dt, _stream())
+                 act, 1 if training else 0, dt, 1 if skip_reduce else 0, _stream())
             return dxo, (None if gsunk else dgam), (None if bsunk else dbet)
 
         # BN2 + act backward, conv1's mask fused -> gradient wrt conv1's raw output
-        dy1, gg2, gb2 = bn_bwd(da2, y1, bn2, bn_scratch(bn2, dev), saves[1], g2, b2, m1, None)
-        da1, _, gw1, gcb1 = conv_backward_raw(conv1.spec, a1, None, w1, cb1, None, dy1, True, ng[3], ng[4])
+        dy1, gg2, gb2 = bn_bwd(da2, y1, bn2, acc2b, saves[1], g2, b2, m1, None, fused2)
+        da1, _, gw1, gcb1 = conv_backward_raw(conv1.spec, a1, None, w1, cb1, None, dy1, True, ng[3], ng[4],
+                                              bnb=(xn, saves[0], g1, b1, acc1b, act) if C == 64 else None)
+        fused1 = conv_backward_raw.last_fused
         # BN1 + act backward, residual gradient fused
-        dx, gg1, gb1 = bn_bwd(da1, xn, bn1, bn_scratch(bn1, dev), saves[0], g1, b1, None, gn)
+        dx, gg1, gb1 = bn_bwd(da1, xn, bn1, acc1b, saves[0], g1, b1, None, gn, fused1)
         return (as_nchw(dx), gg1, gb1, gw1, gcb1, gg2, gb2, gw2, gcb2, gwg, ggb, None, None, None, None, None)
 
 

@@ -19,6 +19,7 @@ ap.add_argument("--dtype", default="bf16")
 ap.add_argument("--config", default="cifar15")
 ap.add_argument("--batch", type=int, default=256)
 ap.add_argument("--ncu", action="store_true")
+ap.add_argument("--no-side-stream", action="store_true")
 ap.add_argument("--top", type=int, default=30)
 args = ap.parse_args()
 
@@ -27,7 +28,7 @@ torch.manual_seed(42)
 model = lvae_b200.LadderVAE(**cfg.kwargs()).cuda()
 if args.dtype == "bf16":
     model.set_compute_dtype(torch.bfloat16)
-eng = TrainEngine(model, args.batch, use_graph=False)
+eng = TrainEngine(model, args.batch, use_graph=False, wgrad_side_stream=not args.no_side_stream)
 x = synthetic_batch(cfg, args.batch, 0).cuda()
 for _ in range(2):
     eng.step(x)
