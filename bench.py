@@ -228,6 +228,7 @@ def main():
     ap.add_argument("--iw-full-forward", action="store_true",
                     help="IW: recompute the bottom-up pass for every sample like the reference's loop (default: once per batch)")
     ap.add_argument("--no-side-stream", action="store_true", help="keep weight-gradient kernels on the main stream")
+    ap.add_argument("--side-streams", type=int, default=2, help="number of side streams the weight-gradient kernels rotate over")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
@@ -325,7 +326,7 @@ def main():
             dist.destroy_process_group()
         return
 
-    engine = TrainEngine(model, batch, use_graph=not args.no_graph, wgrad_side_stream=not args.no_side_stream)
+    engine = TrainEngine(model, batch, use_graph=not args.no_graph, wgrad_side_stream=0 if args.no_side_stream else args.side_streams)
     for _ in range(args.warmup):
         engine.step(x_host)
     torch.cuda.synchronize()

@@ -133,7 +133,8 @@ class TrainEngine:
         self.buckets = bucket_ranges(self.arena.numel, bucket_bytes)
         self.x = torch.zeros((batch_size, model.color_ch) + tuple(model.img_shape), dtype=torch.float32, device=dev)
         self.use_graph = use_graph
-        self.side_stream = torch.cuda.Stream(device=dev) if wgrad_side_stream else None
+        n_side = int(wgrad_side_stream) if not isinstance(wgrad_side_stream, bool) else (2 if wgrad_side_stream else 0)
+        self.side_stream = [torch.cuda.Stream(device=dev) for _ in range(n_side)] if n_side else None
         self.graph_fb: Optional[torch.cuda.CUDAGraph] = None
         self.graph_opt: Optional[torch.cuda.CUDAGraph] = None
         self.out: Dict[str, torch.Tensor] = {}

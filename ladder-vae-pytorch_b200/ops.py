@@ -307,18 +307,23 @@ class ConvSpec:
 # Weight gradients depend only on saved activations and the output gradient, and nothing reads them before the
 # optimizer: the engine lets them run on a side stream (a parallel branch of the captured graph) so that the
 # small, latency-bound wgrad kernels overlap the dgrad / BatchNorm chain.
-_side = {"stream": None, "keep": []}
+_side = {"streams": None, "keep": [], "next": 0}
 
 
-def set_side_stream(stream) -> None:
-    _side["stream"] = stream
+def set_side_stream(streams) -> None:
+    """streams: list of side streams (weight-gradient launches rotate over them) or None."""
+    if streams is not None and not isinstance(streams, (list, tuple)):
+        streams = [streams]
+    _side["streams"] = list(streams) if streams else None
     _side["keep"] = []
+    _side["next"] = 0
 
 
 def join_side_stream() -> None:
-    st = _side["stream"]
-    if st is not None:
-        torch.cuda.current_stream().wait_stream(st)
+    sts = _side["streams"]
+    if sts:
+        for st in sts:
+            torch.cuda.current_stream().wait_stream(st)
     _side["keep"] = []
 
 
@@ -327,12 +332,13 @@ stats = {"tc_fwd": 0, "tc_dgrad": 0, "tc_wgrad": 0, "cc_fwd": 0, "cc_dgrad": 0, 
 
 
 def _wgrad_workspace(device) -> torch.Tensor:
-    """Scratch for the per-CTA partials of lvae_conv2d_wgrad_tc (stream-ordered reuse)."""
-    ws = _wgrad_ws.get(device)
+    """Scratch for the per-CTA partials of lvae_conv2d_wgrad_tc (stream-ordered reuse: one per stream)."""
+    key = (device, torch.cuda.current_stream().cuda_stream)
+    ws = _wgrad_ws.get(key)
     if ws is None:
         sms = torch.cuda.get_device_properties(device).multi_processor_count
         ws = torch.empty(sms * 512 * 128, dtype=torch.float32, device=device)
-        _wgrad_ws[device] = ws
+        _wgrad_ws[key] = ws
     return ws
 
 
@@ -454,7 +460,10 @@ def conv_backward_raw(spec: ConvSpec, xn, x2n, weight, bias, out_scale, gyn, nee
         gbbuf, bsunk = (None, True)
         if bias is not None and need_b:
             gbbuf, bsunk = _param_grad_buffer(bias)
-        side = _side["stream"] if (sunk and bsunk) else None
+        side = None
+        if _side["streams"] and sunk and bsunk:
+            side = _side["streams"][_side["next"] % len(_side["streams"])]
+            _side["next"] += 1
         if side is not None:
             side.wait_event(torch.cuda.current_stream().record_event())     # gyn is ready
             _side["keep"].append((xn, x2n, gyn, out_scale))                  # keep operands alive until the join
