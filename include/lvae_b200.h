@@ -65,7 +65,7 @@ int lvae_conv2d_tc(const void* x, const void* x2, const void* wp, const float* b
  * dy (B,H,W,N) bf16 with N in {64,128} (already multiplied by the Dropout2d mask); dw (N,I,k,k) fp32 +=,
  * dbias [N] += or NULL; ws = lvae_wgrad_tc_workspace(...) floats of scratch for the per-CTA partials. */
 int lvae_conv2d_wgrad_tc(const void* x, const void* x2, const void* dy, float* dw, float* dbias, float* ws, int B,
-                         int H, int W, int N, int ksize, int I_real, lvae_stream_t stream);
+                         int H, int W, int N, int ksize, int I_real, int N_real, int dyC, int dy_c0, lvae_stream_t stream);
 long long lvae_wgrad_tc_workspace(int B, int H, int W, int N, int ksize, int two_inputs);
 /* Same with per-channel reductions fused into the epilogue (bf16 output, N == 64, no residual / split):
  *   stats_acc  [2*64] += sum / sum-of-squares of the output as stored (the next BatchNorm's statistics),
@@ -178,7 +178,9 @@ int lvae_bernoulli_sample(const float* prob, float* out_nchw, int B, int hw, int
 /* 10-component discretized mixture of logistics (:183-230, discretized_mix_logistic_loss :291-382):
  * l (B,hw,100) NHWC, x (B,3,hw) NCHW in [0,1]; ll (B) must be zero on entry (fwd accumulates). */
 int lvae_dmol_fwd(const float* l, const float* x, float* ll, int B, int hw, lvae_stream_t stream);
-int lvae_dmol_bwd(const float* l, const float* x, const float* g_ll, float* dl, int B, int hw, lvae_stream_t stream);
+/* dl: fp32 (B,hw,100); or dl_bf16_128 != NULL: bf16 (B,hw,128) zero-padded, ready for the tcgen05 dgrad / wgrad of the head */
+int lvae_dmol_bwd(const float* l, const float* x, const float* g_ll, float* dl, void* dl_bf16_128, int B, int hw,
+                  lvae_stream_t stream);
 /* sample_from_discretized_mix_logistic (lib/stochastic.py:141-206) + rescale/clamp (likelihoods.py:221-225) */
 int lvae_dmol_sample(const float* l, float* out_nchw, int B, int hw, const void* rng_state,
                      unsigned long long stream_id, lvae_stream_t stream);

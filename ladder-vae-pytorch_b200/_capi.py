@@ -24,7 +24,7 @@ _SIGNATURES = {
     "lvae_conv2d_tc": [P, P, P, P, P, P, P, P, I, I, I, I, I, I, I, I, I, P],
     "lvae_conv2d_tc_ex": [P, P, P, P, P, P, P, P, I, I, I, I, I, I, I, I, I, P, P],
     "lvae_channel_scale": [P, P, P, I, I, I, I, P],
-    "lvae_conv2d_wgrad_tc": [P, P, P, P, P, P, I, I, I, I, I, I, P],
+    "lvae_conv2d_wgrad_tc": [P, P, P, P, P, P, I, I, I, I, I, I, I, I, I, P],
     "lvae_colsum": [P, P, P, I, I, I, I, P],
     "lvae_bn_stats": [P, P, L, I, I, P],
     "lvae_bn_finalize": [P, P, P, P, P, P, L, I, F, F, P],
@@ -48,7 +48,7 @@ _SIGNATURES = {
     "lvae_bernoulli_bwd": [P, P, P, P, P, I, I, I, P],
     "lvae_bernoulli_sample": [P, P, I, I, I, P, U, P],
     "lvae_dmol_fwd": [P, P, P, I, I, P],
-    "lvae_dmol_bwd": [P, P, P, P, I, I, P],
+    "lvae_dmol_bwd": [P, P, P, P, P, I, I, P],
     "lvae_dmol_sample": [P, P, I, I, P, U, P],
     "lvae_adamax_step": [P, P, P, P, L, F, F, F, F, F, P, F, P],
     "lvae_l2_norm": [P, L, P, P, P],

@@ -140,7 +140,7 @@ __device__ __forceinline__ float dmol_term(float x, float cen, float ls, float& 
 template <bool BWD>
 __global__ void __launch_bounds__(DM_TILE) dmol_kernel(const float* __restrict__ l, const float* __restrict__ x,
                                                        float* __restrict__ ll, const float* __restrict__ g_ll,
-                                                       float* __restrict__ dl, int hw) {
+                                                       float* __restrict__ dl, int hw, __nv_bfloat16* __restrict__ dl_lp) {
   pdl_wait();
   pdl_launch();
   extern __shared__ float sm[];  // DM_TILE * DM_PITCH (+32 for the reduction)
@@ -236,17 +236,28 @@ __global__ void __launch_bounds__(DM_TILE) dmol_kernel(const float* __restrict__
     if (threadIdx.x == 0) atomicAdd(ll + b, s);
   } else {
     __syncthreads();
-    float4* dst = reinterpret_cast<float4*>(dl + base);
-    int nq = npix * DM_P / 4;
-    for (int i = threadIdx.x; i < nq; i += DM_TILE) {
-      int e = i * 4;
-      float vv[4];
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        int rr = (e + j) / DM_P, cidx = (e + j) - rr * DM_P;
-        vv[j] = sm[rr * DM_PITCH + cidx];
+    if (dl_lp) {
+      // bf16, 128 channels per pixel (100 gradients + 28 zeros): the operand layout of the tcgen05 dgrad / wgrad of the head conv
+      __nv_bfloat16* dstp = dl_lp + ((long long)b * hw + pix0) * 128;
+      for (int i = threadIdx.x; i < npix * 32; i += DM_TILE) {       // quads of 4 channels
+        int rr = i >> 5, cq = (i & 31) * 4;
+        float v0 = cq < DM_P ? sm[rr * DM_PITCH + cq] : 0.f, v1 = cq + 1 < DM_P ? sm[rr * DM_PITCH + cq + 1] : 0.f;
+        float v2 = cq + 2 < DM_P ? sm[rr * DM_PITCH + cq + 2] : 0.f, v3 = cq + 3 < DM_P ? sm[rr * DM_PITCH + cq + 3] : 0.f;
+        st4<__nv_bfloat16>(dstp + rr * 128 + cq, make_float4(v0, v1, v2, v3));
       }
-      dst[i] = make_float4(vv[0], vv[1], vv[2], vv[3]);
+    } else {
+      float4* dst = reinterpret_cast<float4*>(dl + base);
+      int nq = npix * DM_P / 4;
+      for (int i = threadIdx.x; i < nq; i += DM_TILE) {
+        int e = i * 4;
+        float vv[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          int rr = (e + j) / DM_P, cidx = (e + j) - rr * DM_P;
+          vv[j] = sm[rr * DM_PITCH + cidx];
+        }
+        dst[i] = make_float4(vv[0], vv[1], vv[2], vv[3]);
+      }
     }
   }
 }
@@ -263,14 +274,16 @@ LVAE_API int lvae_dmol_fwd(const float* l, const float* x, float* ll, int B, int
     attr = true;
   }
   dim3 grid(cdiv(hw, DM_TILE), B);
-  lvae_launch(dmol_kernel<false>, grid, DM_TILE, DMOL_SMEM, stream, l, x, ll, nullptr, nullptr, hw);
+  lvae_launch(dmol_kernel<false>, grid, DM_TILE, DMOL_SMEM, stream, l, x, ll, nullptr, nullptr, hw, nullptr);
   LVAE_COUNT_LAUNCH();
   LVAE_CHECK_LAUNCH("dmol_fwd");
   return LVAE_OK;
 }
 
-LVAE_API int lvae_dmol_bwd(const float* l, const float* x, const float* g_ll, float* dl, int B, int hw, cudaStream_t stream) {
-  LVAE_REQUIRE(l && x && g_ll && dl && B > 0 && hw > 0, "dmol_bwd: bad args");
+// dl: fp32 (B,hw,100), or -- when dl_bf16_128 != NULL -- bf16 (B,hw,128) zero-padded (dl may then be NULL)
+LVAE_API int lvae_dmol_bwd(const float* l, const float* x, const float* g_ll, float* dl, void* dl_bf16_128, int B, int hw,
+                           cudaStream_t stream) {
+  LVAE_REQUIRE(l && x && g_ll && (dl || dl_bf16_128) && B > 0 && hw > 0, "dmol_bwd: bad args");
   static bool attr = false;
   if (!attr) {
     cudaFuncSetAttribute(dmol_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DMOL_SMEM);
@@ -278,7 +291,7 @@ LVAE_API int lvae_dmol_bwd(const float* l, const float* x, const float* g_ll, fl
     attr = true;
   }
   dim3 grid(cdiv(hw, DM_TILE), B);
-  lvae_launch(dmol_kernel<true>, grid, DM_TILE, DMOL_SMEM, stream, l, x, nullptr, g_ll, dl, hw);
+  lvae_launch(dmol_kernel<true>, grid, DM_TILE, DMOL_SMEM, stream, l, x, nullptr, g_ll, dl, hw, (__nv_bfloat16*)dl_bf16_128);
   LVAE_COUNT_LAUNCH();
   LVAE_CHECK_LAUNCH("dmol_bwd");
   return LVAE_OK;

@@ -28,6 +28,7 @@ struct WgParams {
   int n_bblk;                // dY channel blocks of 64 (1 or 2)  -> N = 64 * n_bblk
   int tmem_cols;
   int tiles_per_cta;
+  int dy_c0;                 // first dY channel of this launch (dY may be wider than N: split launches)
   float* ws;                 // (grid, n_pairs, 128, N) fp32 partials
   // A-block table: 2 per pair.  src: 0 = x, 1 = x2, 2 = ones tile, 3 = unused (zero rows, never read back)
   int8_t a_src[2 * WG_MAX_PAIRS], a_dx[2 * WG_MAX_PAIRS], a_dy[2 * WG_MAX_PAIRS];
@@ -154,7 +155,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
         if (elect_one()) {
           mbar_expect_tx(BAR(8 + bs), (uint32_t)(p.n_bblk * WG_BLK_BYTES));
           for (int j = 0; j < p.n_bblk; ++j)
-            tma_load_4d(smem_u32(sB + (bs * p.n_bblk + j) * WG_BLK_BYTES), &tmDY, BAR(8 + bs), 64 * j, w0, h0, n0);
+            tma_load_4d(smem_u32(sB + (bs * p.n_bblk + j) * WG_BLK_BYTES), &tmDY, BAR(8 + bs), p.dy_c0 + 64 * j, w0, h0, n0);
         }
         __syncwarp();
         if (++bs == WG_B_SLOTS) { bs = 0; bph ^= 1; }
@@ -253,7 +254,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
 //   ones:                              dbias[co] += sum (row 0 of the block only)
 struct RedParams {
   const float* ws; float* dw; float* dbias;
-  int n_cta, n_pairs, N, I, taps, I_real;
+  int n_cta, n_pairs, N, I, taps, I_real, N_real;
   int8_t kind[2 * WG_MAX_PAIRS];     // 0 tap block, 1 ones, 2 unused
   int8_t tap[2 * WG_MAX_PAIRS], ci0_blk[2 * WG_MAX_PAIRS];
 };
@@ -272,6 +273,7 @@ __global__ void wgrad_reduce_kernel(RedParams p) {
   const int kind = p.kind[blk];
   if (kind == 2 || (kind == 1 && ((row & 63) != 0 || !p.dbias))) return;
   if (kind == 0 && p.ci0_blk[blk] * 64 + (row & 63) >= p.I_real) return;      // zero-padded input channels
+  if (co >= p.N_real) return;                                                   // zero-padded output channels
   const int chunk = (p.n_cta + gridDim.y - 1) / gridDim.y;
   const int c_beg = blockIdx.y * chunk, c_end = min(p.n_cta, c_beg + chunk);
   if (c_beg >= c_end) return;
@@ -328,9 +330,12 @@ LVAE_API long long lvae_wgrad_tc_workspace(int B, int H, int W, int N, int ksize
 
 // x, x2: (B,H,W,64) bf16 (x2 optional); dy: (B,H,W,N) bf16, N in {64,128}, already multiplied by any Dropout2d mask.
 // dw: (N, I_real, k, k) fp32 (+=); I_real <= 64 * inputs (x may carry zero-padded channels beyond I_real, 0 = no padding);
-// dbias: [N] fp32 (+=) or NULL.  ws: workspace (see above).
+// dy may carry zero-padded channels beyond N_real (0 = none): dw is then (N_real, I_real, k, k) and dbias [N_real].
+// dY is (B,H,W,dyC) (dyC = 0 means N); this launch uses its channels [dy_c0, dy_c0 + N).
+// dbias: fp32 (+=) or NULL.  ws: workspace (see above).
 LVAE_API int lvae_conv2d_wgrad_tc(const void* x, const void* x2, const void* dy, float* dw, float* dbias, float* ws,
-                                  int B, int H, int W, int N, int ksize, int I_real, cudaStream_t stream) {
+                                  int B, int H, int W, int N, int ksize, int I_real, int N_real, int dyC, int dy_c0,
+                                  cudaStream_t stream) {
   LVAE_REQUIRE(x && dy && dw && ws, "conv2d_wgrad_tc: null pointer");
   LVAE_REQUIRE((N == 64 || N == 128) && (ksize == 1 || ksize == 3), "conv2d_wgrad_tc: N must be 64 or 128, ksize 1 or 3");
   LVAE_REQUIRE((W & (W - 1)) == 0 && (H & (H - 1)) == 0 && W <= 128, "conv2d_wgrad_tc: H and W must be powers of two (W <= 128)");
@@ -373,7 +378,10 @@ LVAE_API int lvae_conv2d_wgrad_tc(const void* x, const void* x2, const void* dy,
   CUtensorMap tmX, tmX2, tmDY;
   int r = make_act_map(enc, &tmX, x, B, H, W, 64, bw, bh, bn);
   if (!r) r = make_act_map(enc, &tmX2, x2 ? x2 : x, B, H, W, 64, bw, bh, bn);
-  if (!r) r = make_act_map(enc, &tmDY, dy, B, H, W, N, bw, bh, bn);
+  if (dyC <= 0) dyC = N;
+  LVAE_REQUIRE(dy_c0 % 64 == 0 && dy_c0 + N <= dyC, "conv2d_wgrad_tc: bad dY channel window");
+  p.dy_c0 = dy_c0;
+  if (!r) r = make_act_map(enc, &tmDY, dy, B, H, W, dyC, bw, bh, bn);
   if (r) { lvae_set_error("conv2d_wgrad_tc: tensor map encode failed: %d", r); return LVAE_ERR_CUDA; }
   const size_t smem = 1024 + (size_t)WG_PAIR_SLOTS * 2 * WG_BLK_BYTES + (size_t)WG_B_SLOTS * p.n_bblk * WG_BLK_BYTES + WG_BLK_BYTES + 256;
   static bool attr = false;
@@ -385,7 +393,7 @@ LVAE_API int lvae_conv2d_wgrad_tc(const void* x, const void* x2, const void* dy,
   lvae_launch(wgrad_tc_kernel, grid, WG_THREADS_TC, smem, stream, tmX, tmX2, tmDY, p);
   LVAE_COUNT_LAUNCH();
   LVAE_CHECK_LAUNCH("conv2d_wgrad_tc");
-  rp.ws = ws; rp.dw = dw; rp.dbias = dbias; rp.n_cta = grid; rp.n_pairs = p.n_pairs; rp.N = N; rp.I = 64 * inputs; rp.taps = taps; rp.I_real = I_real > 0 ? I_real : 64 * inputs;
+  rp.ws = ws; rp.dw = dw; rp.dbias = dbias; rp.n_cta = grid; rp.n_pairs = p.n_pairs; rp.N = N; rp.I = 64 * inputs; rp.taps = taps; rp.I_real = I_real > 0 ? I_real : 64 * inputs; rp.N_real = N_real > 0 ? N_real : N;
   const int per = p.n_pairs * 128 * N;
   const int ysplit = grid >= 64 ? 8 : (grid >= 16 ? 4 : 1);
   lvae_launch(wgrad_reduce_kernel, dim3((per + 255) / 256, ysplit), 256, 0, stream, rp);

@@ -98,6 +98,16 @@ class DiscretizedLogisticMixLikelihood(LikelihoodModule):
             raise NotImplementedError("the fused kernel is specialised for 10 mixture components")
         self.parameter_net = Conv2d(ch_in, 10 * n_components, kernel_size=3, padding=1)
 
+    def forward(self, input_, x):
+        # bf16 tensor-core path: conv + log-likelihood as one node (its backward feeds the tcgen05 dgrad / wgrad directly)
+        if x is not None and not self.parameter_net._forward_hooks:
+            fused = ops.dmol_head(input_, self.parameter_net, x)
+            if fused is not None:
+                ll, l = fused
+                params = {"mean": None, "all_params": l}
+                return ll, {"mean": None, "mode": None, "sample": self.sample(params), "params": params}
+        return super().forward(input_, x)
+
     def distr_params(self, x):
         l = self.parameter_net(x)
         return {"mean": None, "all_params": l if l.dtype == torch.float32 else l.float()}

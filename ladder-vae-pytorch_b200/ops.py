@@ -7,6 +7,7 @@ and nothing falls back to ATen for the hot ops; a missing library raises.
 """
 from __future__ import annotations
 
+import contextlib
 import ctypes
 import struct
 import threading
@@ -473,7 +474,7 @@ def conv_backward_raw(spec: ConvSpec, xn, x2n, weight, bias, out_scale, gyn, nee
                 and spec.k * spec.k * (2 if C2 else 1) <= 9:
             stats["tc_wgrad"] += 1
             call("lvae_conv2d_wgrad_tc", xn.data_ptr(), _p(x2n), gyn.data_ptr(), gwbuf.data_ptr(), _p(gbbuf),
-                 _wgrad_workspace(xn.device).data_ptr(), B, Hi, Wi, N, spec.k, spec.cin if padded else 0, _stream())
+                 _wgrad_workspace(xn.device).data_ptr(), B, Hi, Wi, N, spec.k, spec.cin if padded else 0, 0, 0, 0, _stream())
         elif not spec.transposed:
             stats["cc_wgrad"] += 1
             call("lvae_conv2d_wgrad", xn.data_ptr(), _p(x2n), gyn.data_ptr(), None, _p(out_scale),
@@ -1008,7 +1009,7 @@ class DmolFn(Function):
         ln, xc = ctx.saved_tensors
         B, H, W, C = ln.shape
         dl = torch.empty_like(ln)
-        call("lvae_dmol_bwd", ln.data_ptr(), xc.data_ptr(), g_ll.contiguous().float().data_ptr(), dl.data_ptr(), B,
+        call("lvae_dmol_bwd", ln.data_ptr(), xc.data_ptr(), g_ll.contiguous().float().data_ptr(), dl.data_ptr(), None, B,
              H * W, _stream())
         out = as_nchw(dl)
         return (out if ctx.in_dtype == torch.float32 else out.to(ctx.in_dtype)), None
@@ -1016,6 +1017,72 @@ class DmolFn(Function):
 
 def dmol_loglik(l, x):
     return DmolFn.apply(l, x)
+
+
+class DmolHeadFn(Function):
+    """parameter_net conv (64 -> 100, 3x3) + mixture-of-logistics log-likelihood as ONE autograd node on the bf16
+    tensor-core path: the likelihood backward writes its gradient directly as the zero-padded bf16 operand
+    (B,H,W,128) of the head conv's tcgen05 dgrad / wgrad (no fp32 round trip, no CUDA-core fallback for N = 100)."""
+
+    @staticmethod
+    def forward(ctx, h, weight, bias, x, spec):
+        hn = nhwc(h)
+        B, H, W, C = hn.shape
+        wp = spec.pack_tc_fwd.get(weight, torch.bfloat16)
+        stats["tc_fwd"] += 1
+        l = _conv_tc(hn, None, wp, bias, None, None, spec.cout, spec.k, False, True)      # fp32 (B,H,W,100)
+        xc = x.contiguous().float()
+        ll = torch.zeros((B,), dtype=torch.float32, device=hn.device)
+        call("lvae_dmol_fwd", l.data_ptr(), xc.data_ptr(), ll.data_ptr(), B, H * W, _stream())
+        ctx.save_for_backward(hn, l, xc, weight, bias)
+        ctx.spec = spec
+        lo = as_nchw(l)
+        ctx.mark_non_differentiable(lo)
+        return ll, lo
+
+    @staticmethod
+    def backward(ctx, g_ll, _g_l):
+        hn, l, xc, weight, bias = ctx.saved_tensors
+        spec = ctx.spec
+        B, H, W, C = hn.shape
+        dl = torch.empty((B, H, W, 128), dtype=torch.bfloat16, device=hn.device)
+        call("lvae_dmol_bwd", l.data_ptr(), xc.data_ptr(), g_ll.contiguous().float().data_ptr(), None, dl.data_ptr(), B,
+             H * W, _stream())
+        gh = None
+        if ctx.needs_input_grad[0]:
+            wpb = spec.pack_tc_bwd.get(weight, torch.bfloat16)
+            stats["tc_dgrad"] += 1
+            gh = as_nchw(_conv_tc(dl, None, wpb, None, None, None, spec.cin, spec.k, True, False))
+        gw = gb = None
+        if ctx.needs_input_grad[1]:
+            gwbuf, sunk = _param_grad_buffer(weight)
+            gbbuf, bsunk = _param_grad_buffer(bias)
+            side = None
+            if _side["streams"] and sunk and bsunk:
+                side = _side["streams"][_side["next"] % len(_side["streams"])]
+                _side["next"] += 1
+                side.wait_event(torch.cuda.current_stream().record_event())
+                _side["keep"].append((hn, dl))
+            with (torch.cuda.stream(side) if side is not None else contextlib.nullcontext()):
+                stats["tc_wgrad"] += 1
+                # five accumulator pairs x 128 columns would not fit TMEM: two launches over 64 output channels each
+                taps = spec.k * spec.k
+                for c0 in (0, 64):
+                    call("lvae_conv2d_wgrad_tc", hn.data_ptr(), None, dl.data_ptr(),
+                         gwbuf.data_ptr() + c0 * spec.cin * taps * 4, gbbuf.data_ptr() + c0 * 4,
+                         _wgrad_workspace(hn.device).data_ptr(), B, H, W, 64, spec.k, 0, min(64, spec.cout - c0), 128, c0,
+                         _stream())
+            gw, gb = (None if sunk else gwbuf), (None if bsunk else gbbuf)
+        return gh, gw, gb, None, None
+
+
+def dmol_head(h, conv, x):
+    """Fused head when the tensor-core path applies; returns (ll, params) or None."""
+    hn_ok = h.dtype == torch.bfloat16 and conv.spec.cout == 100 and conv.spec.cin == 64 and _tc_enabled[0] \
+        and conv.spec.tc_shape and _pow2(h.shape[2]) and _pow2(h.shape[3]) and h.shape[3] <= 128
+    if not hn_ok:
+        return None
+    return DmolHeadFn.apply(h, conv.weight, conv.bias, x, conv.spec)
 
 
 def dmol_sample(l):
