@@ -96,8 +96,9 @@ int lvae_pack_desc_size(void);
 int lvae_colsum(const void* dy, const float* scale, float* out, int B, int HW, int C, int dtype, lvae_stream_t stream);
 
 /* ---- BatchNorm2d (+ nonlinearity) : lib/nn.py:60,67,81 + models/lvae.py:64-69 ----
- * act: 0 none, 1 relu, 2 leaky_relu(0.01), 3 elu, 4 selu.  acc = 2*C doubles, zero on entry,
- * left zero on exit.  Train mode: stats -> finalize (also updates running_mean/var and
+ * act: 0 none, 1 relu, 2 leaky_relu(0.01), 3 elu, 4 selu.  acc = 8 stripes x 2*C doubles ([stripe][sum|sumsq][C];
+ * producers add into stripe blockIdx % 8 to cut atomic contention, consumers sum the stripes), zero on entry,
+ * left zero on exit by the unfused calls.  Train mode: stats -> finalize (also updates running_mean/var and
  * num_batches_tracked on the device) -> bn_act_fwd.  Eval mode: eval_prepare -> bn_act_fwd. */
 int lvae_bn_stats(const void* x, double* acc, long long P, int C, int dtype, lvae_stream_t stream);
 int lvae_bn_finalize(double* acc, float* save_mean, float* save_rstd, float* running_mean, float* running_var,

@@ -521,7 +521,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
               for (int j = 0; j < 32; ++j) {
                 const int c = c0 + j;
                 const float xhat = (xh[j] - sbn[c]) * sbn[64 + c];
-                const float g = f[j] * act_bwd(xhat * sbn[128 + c] + sbn[192 + c], p.bnb_act);
+                const float g = f[j] * act_bwd_t<true>(xhat * sbn[128 + c] + sbn[192 + c], p.bnb_act);
                 f[j] = g;
                 xh[j] = g * xhat;
               }
@@ -613,8 +613,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
       float sum = 0.f;
 #pragma unroll
       for (int qd = 0; qd < 4; ++qd) sum += sred[(st * 8 + hf * 4 + qd) * 32 + l];
-      if (st < 2) { if (p.stats_acc) atomicAdd(p.stats_acc + (st == 0 ? c : 64 + c), (double)sum); }
-      else if (p.bnb_acc) atomicAdd(p.bnb_acc + (st == 2 ? c : 64 + c), (double)sum);
+      const int stripe = (blockIdx.x & 7) * 128;                  // 8-way striped accumulators (see elementwise.cu)
+      if (st < 2) { if (p.stats_acc) atomicAdd(p.stats_acc + stripe + (st == 0 ? c : 64 + c), (double)sum); }
+      else if (p.bnb_acc) atomicAdd(p.bnb_acc + stripe + (st == 2 ? c : 64 + c), (double)sum);
     }
   }
   if (p.tma_store && threadIdx.x == 64) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");

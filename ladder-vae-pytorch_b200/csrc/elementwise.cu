@@ -42,6 +42,20 @@ template <typename T> __device__ __forceinline__ float round_to(float v);
 template <> __device__ __forceinline__ float round_to<float>(float v) { return v; }
 template <> __device__ __forceinline__ float round_to<__nv_bfloat16>(float v) { return __bfloat162float(__float2bfloat16(v)); }
 
+// Per-channel accumulators are striped BN_STRIPES ways ([stripe][2][C] doubles): producers add into stripe
+// (blockIdx.x % BN_STRIPES), consumers sum the stripes.
+constexpr int BN_STRIPES = 8;
+__device__ __forceinline__ double acc_sum(const double* acc, int idx, int C) {
+  double s = 0.0;
+#pragma unroll
+  for (int k = 0; k < BN_STRIPES; ++k) s += acc[k * 2 * C + idx];
+  return s;
+}
+__device__ __forceinline__ void acc_clear(double* acc, int idx, int C) {
+#pragma unroll
+  for (int k = 0; k < BN_STRIPES; ++k) acc[k * 2 * C + idx] = 0.0;
+}
+
 // =========================================================================================
 // BatchNorm2d statistics: per-channel sum / sum of squares over (B,H,W), accumulated in
 // double (fp32 partials per thread, double atomics per block).
@@ -76,8 +90,9 @@ __global__ void bn_stats_kernel(const T* __restrict__ x, double* __restrict__ ac
       a += (double)s_s[(r * CV + q) * V + e];
       b += (double)s_ss[(r * CV + q) * V + e];
     }
-    atomicAdd(acc + c, a);
-    atomicAdd(acc + C + c, b);
+    double* accs = acc + (blockIdx.x & (BN_STRIPES - 1)) * 2 * C;   // striped accumulators: 8x less atomic contention
+    atomicAdd(accs + c, a);
+    atomicAdd(accs + C + c, b);
   }
 }
 
@@ -89,8 +104,8 @@ __global__ void bn_finalize_kernel(double* acc, float* save_mean, float* save_rs
   pdl_launch();
   int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c < C) {
-    double mean = acc[c] / (double)P;
-    double var = acc[C + c] / (double)P - mean * mean;
+    double mean = acc_sum(acc, c, C) / (double)P;
+    double var = acc_sum(acc, C + c, C) / (double)P - mean * mean;
     if (var < 0.0) var = 0.0;
     save_mean[c] = (float)mean;
     save_rstd[c] = (float)(1.0 / sqrt(var + (double)eps));
@@ -99,8 +114,8 @@ __global__ void bn_finalize_kernel(double* acc, float* save_mean, float* save_rs
       running_mean[c] = (float)((1.0 - momentum) * (double)running_mean[c] + momentum * mean);
       running_var[c] = (float)((1.0 - momentum) * (double)running_var[c] + momentum * unb);
     }
-    acc[c] = 0.0;
-    acc[C + c] = 0.0;
+    acc_clear(acc, c, C);
+    acc_clear(acc, C + c, C);
   }
   if (c == 0 && num_batches_tracked) *num_batches_tracked += 1;
 }
@@ -138,7 +153,7 @@ __global__ void bn_act_fwd_kernel(const TI* __restrict__ x, TO* __restrict__ y, 
       o[3] = (o[3] - m.w) * r.w * g.w + b.w;
     }
 #pragma unroll
-    for (int j = 0; j < 4; ++j) o[j] = act_fwd(o[j], act);
+    for (int j = 0; j < 4; ++j) o[j] = act_fwd_t<sizeof(TO) == 2>(o[j], act);
     st4<TO>(y + i * 4, make_float4(o[0], o[1], o[2], o[3]));
   }
 }
@@ -168,7 +183,7 @@ __global__ void bn_act_bwd_reduce_kernel(const T* __restrict__ dy, const T* __re
 #pragma unroll
     for (int j = 0; j < V; ++j) {
       float xh = (xs[j] - mm[j]) * rr[j];
-      float gpre = ds[j] * act_bwd(xh * gg[j] + bb[j], act);
+      float gpre = ds[j] * act_bwd_t<sizeof(T) == 2>(xh * gg[j] + bb[j], act);
       s1[j] += gpre;
       s2[j] += gpre * xh;
     }
@@ -188,8 +203,9 @@ __global__ void bn_act_bwd_reduce_kernel(const T* __restrict__ dy, const T* __re
       u += (double)a1[(rrw * CV + q) * V + e];
       v += (double)a2[(rrw * CV + q) * V + e];
     }
-    atomicAdd(acc + cc, u);
-    atomicAdd(acc + C + cc, v);
+    double* accs = acc + (blockIdx.x & (BN_STRIPES - 1)) * 2 * C;
+    atomicAdd(accs + cc, u);
+    atomicAdd(accs + C + cc, v);
   }
 }
 
@@ -213,9 +229,9 @@ __global__ void bn_act_bwd_apply_kernel(const T* __restrict__ dy, const T* __res
     for (int j = 0; j < 4; ++j) {
       float mj = mean[c + j], rj = rstd[c + j], gj = gamma[c + j], bj = beta[c + j];
       float xh = (xs[j] - mj) * rj;
-      float gpre = ds[j] * act_bwd(xh * gj + bj, act);
+      float gpre = ds[j] * act_bwd_t<sizeof(T) == 2>(xh * gj + bj, act);
       if (training) {
-        float m1 = (float)(acc[c + j] * invP), m2 = (float)(acc[C + c + j] * invP);
+        float m1 = (float)(acc_sum(acc, c + j, C) * invP), m2 = (float)(acc_sum(acc, C + c + j, C) * invP);
         o[j] = gj * rj * (gpre - m1 - xh * m2);
       } else {
         o[j] = gj * rj * gpre;
@@ -230,10 +246,10 @@ __global__ void bn_bwd_params_kernel(double* acc, float* dgamma, float* dbeta, i
   pdl_launch();
   int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c < C) {
-    if (dbeta) dbeta[c] += (float)acc[c];
-    if (dgamma) dgamma[c] += (float)acc[C + c];
-    acc[c] = 0.0;
-    acc[C + c] = 0.0;
+    if (dbeta) dbeta[c] += (float)acc_sum(acc, c, C);
+    if (dgamma) dgamma[c] += (float)acc_sum(acc, C + c, C);
+    acc_clear(acc, c, C);
+    acc_clear(acc, C + c, C);
   }
 }
 
@@ -244,8 +260,9 @@ __global__ void act_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ x
   pdl_launch();
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nquads; i += (long long)gridDim.x * blockDim.x) {
     float4 xv = ld4<T>(x + i * 4), dv = ld4<T>(dy + i * 4);
-    st4<T>(dx + i * 4, make_float4(dv.x * act_bwd(xv.x, act), dv.y * act_bwd(xv.y, act), dv.z * act_bwd(xv.z, act),
-                                   dv.w * act_bwd(xv.w, act)));
+    constexpr bool F = sizeof(T) == 2;
+    st4<T>(dx + i * 4, make_float4(dv.x * act_bwd_t<F>(xv.x, act), dv.y * act_bwd_t<F>(xv.y, act), dv.z * act_bwd_t<F>(xv.z, act),
+                                   dv.w * act_bwd_t<F>(xv.w, act)));
   }
 }
 
@@ -386,8 +403,9 @@ __global__ void gate_fwd_kernel(const T* __restrict__ h, const T* __restrict__ r
     long long row = i / CV;
     int c = (int)(i - row * CV) * 4;
     float4 a = ld4<T>(h + row * 2 * C + c), g = ld4<T>(h + row * 2 * C + C + c);
-    float4 o = make_float4(act_fwd(a.x, act) * sigmoidf_(g.x), act_fwd(a.y, act) * sigmoidf_(g.y),
-                           act_fwd(a.z, act) * sigmoidf_(g.z), act_fwd(a.w, act) * sigmoidf_(g.w));
+    constexpr bool F = sizeof(T) == 2;
+    float4 o = make_float4(act_fwd_t<F>(a.x, act) * sigmoid_t<F>(g.x), act_fwd_t<F>(a.y, act) * sigmoid_t<F>(g.y),
+                           act_fwd_t<F>(a.z, act) * sigmoid_t<F>(g.z), act_fwd_t<F>(a.w, act) * sigmoid_t<F>(g.w));
     if (res) {
       float4 r = ld4<T>(res + i * 4);
       o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
@@ -411,9 +429,9 @@ __global__ void gate_bwd_kernel(const T* __restrict__ dout, const T* __restrict_
     ldv<T, V>(dout + i * V, dv);
 #pragma unroll
     for (int j = 0; j < V; ++j) {
-      float s = sigmoidf_(gv[j]);
-      da[j] = dv[j] * s * act_bwd(av[j], act);
-      dg[j] = dv[j] * act_fwd(av[j], act) * s * (1.f - s);
+      float s = sigmoid_t<sizeof(T) == 2>(gv[j]);
+      da[j] = dv[j] * s * act_bwd_t<sizeof(T) == 2>(av[j], act);
+      dg[j] = dv[j] * act_fwd_t<sizeof(T) == 2>(av[j], act) * s * (1.f - s);
     }
     stv<T, V>(dh + row * 2 * C + c, da);
     stv<T, V>(dh + row * 2 * C + C + c, dg);
@@ -697,8 +715,8 @@ __global__ void bn_act_fwd2_kernel(const TI* __restrict__ x, TO* __restrict__ y,
   for (int ch = threadIdx.x; ch < C; ch += blockDim.x) {
     float mean, rstd;
     if (training) {
-      double m = acc[ch] / (double)P;
-      double var = acc[C + ch] / (double)P - m * m;
+      double m = acc_sum(acc, ch, C) / (double)P;
+      double var = acc_sum(acc, C + ch, C) / (double)P - m * m;
       if (var < 0.0) var = 0.0;
       mean = (float)m;
       rstd = rsqrtf((float)var + eps);
@@ -731,7 +749,7 @@ __global__ void bn_act_fwd2_kernel(const TI* __restrict__ x, TO* __restrict__ y,
     float v[V];
     ldv<TI, V>(x + i * V, v);
 #pragma unroll
-    for (int j = 0; j < V; ++j) v[j] = act_fwd(v[j] * sc[j] + sh[j], act);
+    for (int j = 0; j < V; ++j) v[j] = act_fwd_t<sizeof(TO) == 2>(v[j] * sc[j] + sh[j], act);
     stv<TO, V>(y + i * V, v);
   }
 }
@@ -745,24 +763,28 @@ __global__ void bn_act_bwd2_kernel(const T* __restrict__ dy, const T* __restrict
                                    int training) {
   pdl_wait();
   pdl_launch();
+  __shared__ float s_m1[256], s_m2[256];
   const int CV = C / V;
   const long long stride = (long long)gridDim.x * blockDim.x;
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const int c = (int)(i % CV) * V;
   const double invP = 1.0 / (double)P;
+  for (int ch = threadIdx.x; ch < C; ch += blockDim.x) {
+    const double a1 = acc_sum(acc, ch, C), a2 = acc_sum(acc, C + ch, C);
+    s_m1[ch] = (float)(a1 * invP);
+    s_m2[ch] = (float)(a2 * invP);
+    if (blockIdx.x == 0) {
+      if (dbeta) dbeta[ch] += (float)a1;
+      if (dgamma) dgamma[ch] += (float)a2;
+    }
+  }
+  __syncthreads();
   float m[V], r[V], g[V], b[V], m1[V], m2[V];
 #pragma unroll
   for (int j = 0; j < V; ++j) {
     m[j] = save[c + j]; r[j] = save[C + c + j]; g[j] = gamma[c + j]; b[j] = beta[c + j];
-    m1[j] = (float)(acc[c + j] * invP);
-    m2[j] = (float)(acc[C + c + j] * invP);
-  }
-  if (blockIdx.x == 0 && threadIdx.x < CV) {
-#pragma unroll
-    for (int j = 0; j < V; ++j) {
-      if (dbeta) dbeta[c + j] += (float)acc[c + j];
-      if (dgamma) dgamma[c + j] += (float)acc[C + c + j];
-    }
+    m1[j] = s_m1[c + j];
+    m2[j] = s_m2[c + j];
   }
   for (; i < nvec; i += stride) {
     float xs[V], ds[V], o[V];
@@ -771,7 +793,7 @@ __global__ void bn_act_bwd2_kernel(const T* __restrict__ dy, const T* __restrict
 #pragma unroll
     for (int j = 0; j < V; ++j) {
       float xh = (xs[j] - m[j]) * r[j];
-      float gpre = ds[j] * act_bwd(xh * g[j] + b[j], act);
+      float gpre = ds[j] * act_bwd_t<sizeof(T) == 2>(xh * g[j] + b[j], act);
       o[j] = training ? g[j] * r[j] * (gpre - m1[j] - xh * m2[j]) : g[j] * r[j] * gpre;
     }
     if (post_scale) {
@@ -881,7 +903,7 @@ __global__ void gate_fwd_stats_kernel(const T* __restrict__ h, const T* __restri
     ldv<T, V>(h + row * 2 * C + c, a);
     ldv<T, V>(h + row * 2 * C + C + c, g);
 #pragma unroll
-    for (int j = 0; j < V; ++j) o[j] = act_fwd(a[j], act) * sigmoidf_(g[j]);
+    for (int j = 0; j < V; ++j) o[j] = act_fwd_t<sizeof(T) == 2>(a[j], act) * sigmoid_t<sizeof(T) == 2>(g[j]);
     if (res) {
       float r[V];
       ldv<T, V>(res + i * V, r);
@@ -909,8 +931,9 @@ __global__ void gate_fwd_stats_kernel(const T* __restrict__ h, const T* __restri
       a += (double)s_s[t * V + e];
       b += (double)s_ss[t * V + e];
     }
-    atomicAdd(acc + cch, a);
-    atomicAdd(acc + C + cch, b);
+    double* accs = acc + (blockIdx.x & (BN_STRIPES - 1)) * 2 * C;
+    atomicAdd(accs + cch, a);
+    atomicAdd(accs + C + cch, b);
   }
 }
 

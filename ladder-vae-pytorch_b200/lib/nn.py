@@ -51,7 +51,7 @@ class BatchNorm2d(nn.BatchNorm2d):
     def stat_acc(self, device):
         acc = getattr(self, "_stat_acc", None)
         if acc is None or acc.device != device:
-            acc = torch.zeros(2 * self.num_features, dtype=torch.float64, device=device)
+            acc = torch.zeros(ops.BN_STRIPES * 2 * self.num_features, dtype=torch.float64, device=device)
             self._stat_acc = acc
         return acc
 

@@ -110,7 +110,7 @@ class LadderVAE(BaseGenerativeModel):
         if arena is None or arena.device != device:
             from lvae_b200.lib.nn import BatchNorm2d
             bns = [m for m in self.modules() if isinstance(m, BatchNorm2d)]
-            arena = torch.zeros((max(1, len(bns)), 6, self.n_filters), dtype=torch.float64, device=device)
+            arena = torch.zeros((max(1, len(bns)), 3, ops.BN_STRIPES, 2, self.n_filters), dtype=torch.float64, device=device)
             for i, bn in enumerate(bns):
                 if bn.num_features == self.n_filters:
                     bn._lvae_scratch = arena[i]

@@ -588,6 +588,7 @@ def bn_act(x, bn, act_id: int, out_dtype=None):
 
 
 # --------------------------------------------------------------------------- BatchNorm scratch arena
+BN_STRIPES = 8
 _bn_epoch = [0]
 _whole_block = [True]
 
@@ -609,12 +610,12 @@ def new_forward_epoch() -> int:
 
 
 def bn_scratch(bn, device):
-    """(6, C) float64 scratch of one BatchNorm2d: rows 0-1 forward sum / sum-of-squares, rows 2-3 backward sums,
-    rows 4-5 statistics of the output of the residual block this BatchNorm opens.  Clean (all zero) at first use
-    in a forward epoch when it lives in a model arena; otherwise zeroed on demand."""
+    """(3, 8, 2, C) float64 scratch of one BatchNorm2d: [0] forward sum / sum-of-squares, [1] backward sums, [2] statistics
+    of the output of the residual block this BatchNorm opens; each 8-way striped (see csrc/elementwise.cu).  Clean
+    (all zero) at first use in a forward epoch when it lives in a model arena; otherwise zeroed on demand."""
     acc = getattr(bn, "_lvae_scratch", None)
     if acc is None or acc.device != device:
-        acc = torch.zeros((6, bn.num_features), dtype=torch.float64, device=device)
+        acc = torch.zeros((3, BN_STRIPES, 2, bn.num_features), dtype=torch.float64, device=device)
         bn._lvae_scratch = acc
         bn._lvae_scratch_owned = True
         bn._lvae_epoch_fwd = bn._lvae_epoch_bwd = -1
@@ -655,7 +656,7 @@ class GatedBlockFn(Function):
                 if given_acc is not None:
                     acc = given_acc
                 else:
-                    acc = sc[0:2]
+                    acc = sc[0]
                     _bn_clean(bn, acc, "fwd")
                     call("lvae_bn_stats", inp.data_ptr(), acc.data_ptr(), Pn, C, dt, _stream())
             out = torch.empty_like(inp)
@@ -668,7 +669,7 @@ class GatedBlockFn(Function):
         a1 = bn_fwd(xn, bn1, sc1, saves[0], g1, b1, x_stats)
         acc2 = None
         if training and C == 64:
-            acc2 = sc2[0:2]
+            acc2 = sc2[0]
             _bn_clean(bn2, acc2, "fwd")
             y1, fused = conv_forward_raw(conv1.spec, a1, None, w1, cb1, m1, None, stats_acc=acc2)   # BN2 statistics in the epilogue
             if not fused:
@@ -681,7 +682,7 @@ class GatedBlockFn(Function):
         out = torch.empty_like(xn)
         out_stats = None
         if training and 256 % (C // 4) == 0:
-            out_stats = sc1[4:6]                      # statistics of this block's output, for the next block's BN1
+            out_stats = sc1[2]                        # statistics of this block's output, for the next block's BN1
             _bn_clean(bn1, out_stats, "out")
             call("lvae_gate_fwd_stats", h.data_ptr(), xn.data_ptr(), out.data_ptr(), out_stats.data_ptr(), Pn, C, gact, dt, _stream())
         else:
@@ -708,7 +709,7 @@ class GatedBlockFn(Function):
         # 1x1 gate conv: dgrad carries conv2's Dropout2d mask in its epilogue -> gradient wrt conv2's raw output
         dy2, _, gwg, ggb = conv_backward_raw(gconv.spec, y2, None, wg, gbias, None, dh, True, ng[9], ng[10], dx_scale=m2)
         sc1b, sc2b = bn_scratch(bn1, dev), bn_scratch(bn2, dev)
-        acc1b, acc2b = sc1b[2:4], sc2b[2:4]
+        acc1b, acc2b = sc1b[1], sc2b[1]
         _bn_clean(bn1, acc1b, "bwd")
         _bn_clean(bn2, acc2b, "bwd")
         # conv2 (dy2 is already masked); its dgrad epilogue also accumulates BN2's backward sums

@@ -18,8 +18,8 @@ for HW in (32, 16, 8, 4):
     ds = [torch.randn(P, C, device="cuda").to(bf) for _ in range(nbuf)]
     hs = [torch.randn(P, 2 * C, device="cuda").to(bf) for _ in range(nbuf)]
     dhs = [torch.empty(P, 2 * C, device="cuda", dtype=bf) for _ in range(nbuf)]
-    acc = torch.zeros(2, C, dtype=torch.float64, device="cuda")
-    acc[0] = 0.1 * P; acc[1] = 1.5 * P
+    acc = torch.zeros(8, 2, C, dtype=torch.float64, device="cuda")      # 8-way striped accumulators
+    acc[0, 0] = 0.1 * P; acc[0, 1] = 1.5 * P
     save = torch.zeros(2, C, device="cuda"); save[1] = 1.0
     gamma = torch.ones(C, device="cuda"); beta = torch.zeros(C, device="cuda")
     rm = torch.zeros(C, device="cuda"); rv = torch.ones(C, device="cuda")
