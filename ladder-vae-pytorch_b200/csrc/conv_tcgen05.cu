@@ -261,6 +261,9 @@ __device__ __forceinline__ void epilogue16(const uint32_t* __restrict__ r, const
   }
 }
 
+// FUSE: 0 plain epilogue, 1 output statistics (stats_acc), 2 BatchNorm-backward sums (bnb_*).  A template parameter so
+// that the plain kernel carries no accumulator registers (the 10-warp CTA caps ptxas at 168 registers per thread).
+template <int FUSE>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmY,
@@ -435,15 +438,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     const int half = (warp - 2) >> 2;                          // which 32-column chunks (even / odd) this warp drains
     const int row = quad * 32 + lane;
     const int hw = p.H * p.W;
-    float red0 = 0.f, red1 = 0.f, red2 = 0.f, red3 = 0.f;      // per-lane (= channel 32*half + lane) running sums
+    float accA[FUSE ? 32 : 1], accB[FUSE ? 32 : 1];               // row-private partial sums of the fused reduction
+#pragma unroll
+    for (int j = 0; j < (FUSE ? 32 : 1); ++j) accA[j] = accB[j] = 0.f;
     int it = 0;
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
       const int buf = it & 1;
       const uint32_t use = (uint32_t)(it >> 1);
       if (p.dbg && blockIdx.x == 0 && warp == 2 && lane == 0) p.dbg[it * 8 + 3] = clock64();
-      mbar_wait(BAR(2 * S + 1 + buf), use & 1);
-      tc_fence_after();
-      if (p.dbg && blockIdx.x == 0 && warp == 2 && lane == 0) p.dbg[it * 8 + 4] = clock64();
       long long m = (long long)tile * TC_BM + row;
       if (p.halo) {
         int n0 = tile / p.tiles_per_img;
@@ -452,14 +454,24 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         m = ((long long)n0 * p.H + ty * 16 + (row >> 3)) * p.W + tx * 8 + (row & 7);
       }
       const bool valid = m < p.M_total;
+      uint4 xu[4];
+      if (FUSE == 2) {                                             // BatchNorm input rows: fetched while the MMAs still run
+        const uint4* xr = reinterpret_cast<const uint4*>(p.bnb_x + (valid ? m : 0) * 64 + 32 * half);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) xu[q] = __ldg(xr + q);
+      }
+      mbar_wait(BAR(2 * S + 1 + buf), use & 1);
+      tc_fence_after();
+      if (p.dbg && blockIdx.x == 0 && warp == 2 && lane == 0) p.dbg[it * 8 + 4] = clock64();
       const int b = valid ? (int)(m / hw) : 0;
       const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * p.Npad);
       const float* scale_row = p.out_scale ? p.out_scale + (long long)b * p.N : nullptr;
-      if (p.tma_store) {
+      if (FUSE != 0 || p.tma_store) {
         // ---- TMEM -> registers (bias, Dropout2d scale, bf16 pack), release the accumulator, stage in smem, TMA store ----
-        uint4 packed[2][4];
+        constexpr int NCH = FUSE ? 1 : 2;                           // fused reductions: N = 64, one chunk per thread
+        uint4 packed[NCH][4];
 #pragma unroll
-        for (int nch = 0; nch < 2; ++nch) {                      // N <= 128 on this path: at most two chunks per thread
+        for (int nch = 0; nch < NCH; ++nch) {                      // N <= 128 on this path: at most two chunks per thread
           const int c0 = 32 * half + 64 * nch;
           if (c0 >= p.Npad) break;
           uint32_t r[32];
@@ -482,53 +494,32 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
 #pragma unroll
             for (int e = 0; e < 4; ++e) h2[e] = __floats2bfloat162_rn(f[8 * q + 2 * e], f[8 * q + 2 * e + 1]);
           }
-          if (nch == 0 && (p.stats_acc || p.bnb_acc)) {
-            // values as stored (bf16-rounded); rows past the end of the tensor contribute nothing
+          if (FUSE != 0 && nch == 0) {
+            // values as stored (bf16-rounded); rows past the end of the tensor contribute nothing.  Per-thread
+            // (row-private) partial sums stay in registers across tiles; one transposing butterfly per CTA at the end.
 #pragma unroll
             for (int j = 0; j < 32; ++j) f[j] = valid ? __bfloat162float(__float2bfloat16(f[j])) : 0.f;
-            if (p.stats_acc) {
-              float sq[32];
+            if (FUSE == 1) {
 #pragma unroll
-              for (int j = 0; j < 32; ++j) sq[j] = f[j] * f[j];
-              if (!p.bnb_acc) {
-                warp_transpose_sum32(f, lane);
-                red0 += f[0];
-              } else {
-                float cp[32];
-#pragma unroll
-                for (int j = 0; j < 32; ++j) cp[j] = f[j];
-                warp_transpose_sum32(cp, lane);
-                red0 += cp[0];
-              }
-              warp_transpose_sum32(sq, lane);
-              red1 += sq[0];
-            }
-            if (p.bnb_acc) {
+              for (int j = 0; j < 32; ++j) { accA[j] += f[j]; accB[j] = fmaf(f[j], f[j], accB[j]); }
+            } else {
               // g = dy * act'(xhat*gamma + beta), accumulate sum(g) and sum(g*xhat) per channel
-              float xh[32];
-              const __nv_bfloat16* xr = p.bnb_x + (valid ? m : 0) * 64 + c0;
 #pragma unroll
               for (int q = 0; q < 4; ++q) {
-                const uint4 u = __ldg(reinterpret_cast<const uint4*>(xr) + q);
-                const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&u);
+                const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&xu[q]);
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
                   const float2 t = __bfloat1622float2(h2[e]);
-                  xh[8 * q + 2 * e] = t.x; xh[8 * q + 2 * e + 1] = t.y;
+#pragma unroll
+                  for (int w = 0; w < 2; ++w) {
+                    const int j = 8 * q + 2 * e + w, c = c0 + j;
+                    const float xhat = ((w ? t.y : t.x) - sbn[c]) * sbn[64 + c];
+                    const float g = f[j] * act_bwd_t<true>(xhat * sbn[128 + c] + sbn[192 + c], p.bnb_act);
+                    accA[j] += g;
+                    accB[j] = fmaf(g, xhat, accB[j]);
+                  }
                 }
               }
-#pragma unroll
-              for (int j = 0; j < 32; ++j) {
-                const int c = c0 + j;
-                const float xhat = (xh[j] - sbn[c]) * sbn[64 + c];
-                const float g = f[j] * act_bwd_t<true>(xhat * sbn[128 + c] + sbn[192 + c], p.bnb_act);
-                f[j] = g;
-                xh[j] = g * xhat;
-              }
-              warp_transpose_sum32(f, lane);
-              warp_transpose_sum32(xh, lane);
-              red2 += f[0];
-              red3 += xh[0];
             }
           }
         }
@@ -539,7 +530,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         if (threadIdx.x == 64) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
         asm volatile("bar.sync 1, 256;" ::: "memory");
 #pragma unroll
-        for (int nch = 0; nch < 2; ++nch) {
+        for (int nch = 0; nch < NCH; ++nch) {
           const int c0 = 32 * half + 64 * nch;
           if (c0 >= p.Npad) break;
           uint8_t* blk = sOut + (c0 >> 6) * TC_STAGE_BYTES + row * 128;
@@ -600,13 +591,16 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
       if (p.dbg && blockIdx.x == 0 && warp == 2 && lane == 0) p.dbg[it * 8 + 5] = clock64();
       if (lane == 0) mbar_arrive(BAR(2 * S + 3 + buf));
     }
-    if (p.stats_acc || p.bnb_acc) {
+    if (FUSE != 0) {
       // combine the four lane quadrants (rows) per channel, one double atomic per channel and statistic per CTA
       const int e = warp - 2;                                      // 0..7 = half * 4 + quad-order
-      sred[(0 * 8 + e) * 32 + lane] = red0;
-      sred[(1 * 8 + e) * 32 + lane] = red1;
-      sred[(2 * 8 + e) * 32 + lane] = red2;
-      sred[(3 * 8 + e) * 32 + lane] = red3;
+      warp_transpose_sum32(accA, lane);                            // accA[0] = sum over this warp's 32 rows of channel 32*half + lane
+      warp_transpose_sum32(accB, lane);
+      const bool is_stats = FUSE == 1;
+      sred[(0 * 8 + e) * 32 + lane] = is_stats ? accA[0] : 0.f;
+      sred[(1 * 8 + e) * 32 + lane] = is_stats ? accB[0] : 0.f;
+      sred[(2 * 8 + e) * 32 + lane] = is_stats ? 0.f : accA[0];
+      sred[(3 * 8 + e) * 32 + lane] = is_stats ? 0.f : accB[0];
       asm volatile("bar.sync 1, 256;" ::: "memory");
       const int t = threadIdx.x - 64;                              // 0..255 -> (statistic, channel)
       const int st = t >> 6, c = t & 63, hf = c >> 5, l = c & 31;
@@ -702,6 +696,7 @@ LVAE_API int lvae_conv2d_tc_ex(const void* x, const void* x2, const void* wp, co
     p.bnb_x = (const __nv_bfloat16*)fuse->bnb_x; p.bnb_save = fuse->bnb_save; p.bnb_gamma = fuse->bnb_gamma;
     p.bnb_beta = fuse->bnb_beta; p.bnb_acc = fuse->bnb_acc; p.bnb_act = fuse->bnb_act;
     LVAE_REQUIRE(!p.bnb_acc || (p.bnb_x && p.bnb_save && p.bnb_gamma && p.bnb_beta), "conv2d_tc: incomplete BatchNorm-backward fusion arguments");
+    LVAE_REQUIRE(!(p.bnb_acc && p.stats_acc), "conv2d_tc: output statistics and BatchNorm-backward sums cannot be fused into the same launch");
   }
   const int inputs = x2 ? 2 : 1;
   const int taps = ksize * ksize;
@@ -791,13 +786,17 @@ LVAE_API int lvae_conv2d_tc_ex(const void* x, const void* x2, const void* wp, co
   }
   static size_t attr_smem = 0;
   if (smem > attr_smem) {
-    cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024));
+    cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024));
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024));
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024));
     if (e != cudaSuccess) { lvae_set_error("conv2d_tc: cannot raise dynamic smem: %s", cudaGetErrorString(e)); return LVAE_ERR_CUDA; }
     attr_smem = 227 * 1024;
   }
   const int n_tiles = p.halo ? B * p.tiles_per_img : (p.M_total + TC_BM - 1) / TC_BM;
   const int grid = n_tiles < lvae_num_sms() ? n_tiles : lvae_num_sms();
-  lvae_launch(conv_tc_kernel, grid, TC_THREADS, smem, stream, tmA0, tmA1, tmW, tmY, tmY2, p);
+  if (p.stats_acc) lvae_launch(conv_tc_kernel<1>, grid, TC_THREADS, smem, stream, tmA0, tmA1, tmW, tmY, tmY2, p);
+  else if (p.bnb_acc) lvae_launch(conv_tc_kernel<2>, grid, TC_THREADS, smem, stream, tmA0, tmA1, tmW, tmY, tmY2, p);
+  else lvae_launch(conv_tc_kernel<0>, grid, TC_THREADS, smem, stream, tmA0, tmA1, tmW, tmY, tmY2, p);
   LVAE_COUNT_LAUNCH();
   LVAE_CHECK_LAUNCH("conv2d_tc");
   return LVAE_OK;

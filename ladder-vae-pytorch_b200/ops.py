@@ -9,6 +9,7 @@ from __future__ import annotations
 
 import contextlib
 import ctypes
+import os
 import struct
 import threading
 from contextlib import contextmanager
@@ -343,6 +344,11 @@ def _wgrad_workspace(device) -> torch.Tensor:
     return ws
 
 
+# largest pixel count (B*H*W) for which the per-channel reductions ride in the conv epilogue instead of a pass of their own
+_FUSE_STATS_MAXPIX = int(os.environ.get("LVAE_FUSE_STATS_MAXPIX", str(1 << 40)))
+_FUSE_BNB_MAXPIX = int(os.environ.get("LVAE_FUSE_BNB_MAXPIX", str(1 << 40)))
+
+
 def _tc_fusable(N, out_f32, res, nsplit=0) -> bool:
     """Can the conv's epilogue carry a fused per-channel reduction (TMA-store path of lvae_conv2d_tc)?"""
     return N == 64 and not out_f32 and res is None and not nsplit
@@ -394,7 +400,7 @@ def conv_forward_raw(spec: ConvSpec, xn, x2n, weight, bias, out_scale, resn, sta
     if spec.tc_forward_ok(xn, x2n) and (resn is None or resn.dtype == (torch.float32 if want_f32 else torch.bfloat16)):
         wp = spec.pack_tc_fwd.get(weight, torch.bfloat16)
         stats["tc_fwd"] += 1
-        fused = stats_acc is not None and _tc_fusable(spec.cout, want_f32, resn)
+        fused = stats_acc is not None and _tc_fusable(spec.cout, want_f32, resn) and _FUSE_STATS_MAXPIX >= xn.shape[0] * xn.shape[1] * xn.shape[2]
         y = _conv_tc(xn, x2n, wp, bias, out_scale, resn, spec.cout, spec.k, False, want_f32,
                      stats_acc=stats_acc if fused else None)
         return (y, fused) if stats_acc is not None else y
@@ -435,7 +441,8 @@ def conv_backward_raw(spec: ConvSpec, xn, x2n, weight, bias, out_scale, gyn, nee
             wpb = spec.pack_tc_bwd.get(weight, torch.bfloat16)
             stats["tc_dgrad"] += 1
             if x2n is None:
-                fuse_bnb = bnb is not None and not padded and _tc_fusable(spec.cin, False, None)
+                fuse_bnb = (bnb is not None and not padded and _tc_fusable(spec.cin, False, None)
+                            and _FUSE_BNB_MAXPIX >= gyn.shape[0] * gyn.shape[1] * gyn.shape[2])
                 gx = _conv_tc(gyn, None, wpb, None, dx_scale, None, spec.cin, spec.k, True, False,
                               bnb=bnb if fuse_bnb else None)
                 if fuse_bnb:
