@@ -63,10 +63,24 @@ int lvae_conv2d_tc(const void* x, const void* x2, const void* wp, const float* b
 /* bf16 tensor-core weight gradient for the same convolutions (reduction over pixels, MN-major operands,
  * two filter taps per M = 128 MMA, bias gradient from an all-ones operand block): x, x2 (B,H,W,64) bf16,
  * dy (B,H,W,N) bf16 with N in {64,128} (already multiplied by the Dropout2d mask); dw (N,I,k,k) fp32 +=,
- * dbias [N] += or NULL; ws = lvae_wgrad_tc_workspace(...) floats of scratch for the per-CTA partials. */
+ * dbias [N] += or NULL; ws = lvae_wgrad_tc_workspace(...) floats of scratch (one packed gradient, see below). */
 int lvae_conv2d_wgrad_tc(const void* x, const void* x2, const void* dy, float* dw, float* dbias, float* ws, int B,
                          int H, int W, int N, int ksize, int I_real, int N_real, int dyC, int dy_c0, lvae_stream_t stream);
 long long lvae_wgrad_tc_workspace(int B, int H, int W, int N, int ksize, int two_inputs);
+/* The same gradient in two steps, for callers that batch the re-layout (engine.py: one unpack launch per training step
+ * instead of one per convolution; replaces the per-parameter `.grad` accumulation of loss.backward(),
+ * experiment_manager.py:78-80 / boilr's training loop).  lvae_conv2d_wgrad_tc_acc ADDS the gradient into the packed
+ * buffer gp (lvae_wgrad_tc_packed_size floats: [pair][128 rows = two (tap, input-block) row blocks of 64 ci][N]) with TMA
+ * reduce-stores from every CTA; lvae_wgrad_unpack_batched adds n packed buffers into their (O,I,kh,kw) gradients
+ * (descriptors of lvae_wgrad_unpack_desc_size bytes each, built on the host by lvae_wgrad_unpack_desc and copied to
+ * device memory; clear != 0 also zeroes gp for the next step). */
+long long lvae_wgrad_tc_packed_size(int N, int ksize, int two_inputs);
+int lvae_conv2d_wgrad_tc_acc(const void* x, const void* x2, const void* dy, float* gp, int B, int H, int W, int N,
+                             int ksize, int dyC, int dy_c0, lvae_stream_t stream);
+int lvae_wgrad_unpack_desc_size(void);
+int lvae_wgrad_unpack_desc(void* desc_host, const float* gp, float* dw, float* dbias, int N, int ksize, int two_inputs,
+                           int I_real, int N_real, int clear);
+int lvae_wgrad_unpack_batched(const void* desc_dev, int n, int max_n_real, lvae_stream_t stream);
 /* Same with per-channel reductions fused into the epilogue (bf16 output, N == 64, no residual / split):
  *   stats_acc  [2*64] += sum / sum-of-squares of the output as stored (the next BatchNorm's statistics),
  *   bnb_*      BatchNorm-backward sums over this data-gradient output dy: bnb_acc [2*64] += sum(g), sum(g*xhat) with

@@ -25,6 +25,9 @@ _SIGNATURES = {
     "lvae_conv2d_tc_ex": [P, P, P, P, P, P, P, P, I, I, I, I, I, I, I, I, I, P, P],
     "lvae_channel_scale": [P, P, P, I, I, I, I, P],
     "lvae_conv2d_wgrad_tc": [P, P, P, P, P, P, I, I, I, I, I, I, I, I, I, P],
+    "lvae_conv2d_wgrad_tc_acc": [P, P, P, P, I, I, I, I, I, I, I, P],
+    "lvae_wgrad_unpack_desc": [P, P, P, P, I, I, I, I, I, I],
+    "lvae_wgrad_unpack_batched": [P, I, I, P],
     "lvae_colsum": [P, P, P, I, I, I, I, P],
     "lvae_bn_stats": [P, P, L, I, I, P],
     "lvae_bn_finalize": [P, P, P, P, P, P, L, I, F, F, P],
@@ -66,6 +69,8 @@ _SPECIAL = {
     "lvae_conv2d_tc_debug": ([c_void_p], None),
     "lvae_get_pdl": ([], c_int),
     "lvae_wgrad_tc_workspace": ([I, I, I, I, I, I], c_longlong),
+    "lvae_wgrad_tc_packed_size": ([I, I, I], c_longlong),
+    "lvae_wgrad_unpack_desc_size": ([], c_int),
 }
 
 

@@ -7,11 +7,14 @@
 // runs over the rows.  One tcgen05.mma (M = 128, N = co, K = 16 pixels) consumes TWO activation
 // tiles stacked along M (two filter taps, or a tap and an all-ones tile whose accumulator rows are
 // the bias gradient), so a 3x3 convolution needs five accumulators of 64 TMEM columns each.
-// Every CTA reduces its share of the pixel tiles into TMEM, then writes ONE fp32 partial to a
-// workspace; lvae_wgrad_reduce sums the partials and scatters into the (O, I, kh, kw) gradient.
+// Every CTA reduces its share of the pixel tiles into TMEM, then adds its fp32 partial into the PACKED gradient
+// Gp[(pair, row)][co] with TMA reduce-stores (cp.reduce.async.bulk.tensor ... .add: the additions happen in L2, there is
+// no per-CTA workspace and no reduction pass).  lvae_wgrad_unpack[_batched] re-lays Gp into the (O, I, kh, kw) gradient.
 // Shifted 4-D TMA boxes implement im2col, out-of-bounds zero fill implements the padding.
 #include "common.cuh"
 #include <cuda.h>
+#include <stdlib.h>
+#include <string.h>
 
 namespace {
 
@@ -21,6 +24,9 @@ constexpr int WG_BLK_BYTES = WG_TILE * 64 * 2;   // 16 KB
 constexpr int WG_MAX_PAIRS = 5;
 constexpr int WG_PAIR_SLOTS = 4;
 constexpr int WG_B_SLOTS = 2;
+constexpr int WG_HALO_BYTES = 18 * 16 * 128;                         // 36 KB
+constexpr int WG_HALO_STAGE_BYTES = WG_HALO_BYTES + WG_BLK_BYTES;    // + the dY tile
+constexpr int WG_HALO_STAGES = 3;
 
 struct WgParams {
   int M_total, H, W;
@@ -29,7 +35,10 @@ struct WgParams {
   int tmem_cols;
   int tiles_per_cta;
   int dy_c0;                 // first dY channel of this launch (dY may be wider than N: split launches)
-  float* ws;                 // (grid, n_pairs, 128, N) fp32 partials
+  // halo mode (3x3, one input, N = 64, W % 8 == 0, H % 16 == 0): pixel tiles are 16 rows x 8 columns and ONE TMA box of
+  // 18 rows x 16 columns serves all nine taps (shifted MN-major descriptors, SBO = one 16-pixel image row = 2048 B)
+  int halo, tiles_x, tiles_per_img;
+
   // A-block table: 2 per pair.  src: 0 = x, 1 = x2, 2 = ones tile, 3 = unused (zero rows, never read back)
   int8_t a_src[2 * WG_MAX_PAIRS], a_dx[2 * WG_MAX_PAIRS], a_dy[2 * WG_MAX_PAIRS];
 };
@@ -60,11 +69,11 @@ __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* tm,
 }
 // MN-major, 128B-swizzled operand: 64 MN elements per 128-byte row, 8 K-rows per 1024-byte atom (SBO),
 // next block of 64 MN elements LBO bytes further.
-__device__ __forceinline__ uint64_t umma_desc_mn_sw128(uint32_t saddr, uint32_t lbo_bytes) {
+__device__ __forceinline__ uint64_t umma_desc_mn_sw128(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes = 1024) {
   uint64_t d = 0;
   d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
   d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
-  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)(sbo_bytes >> 4) << 32;
   d |= (uint64_t)1 << 46;
   d |= (uint64_t)2 << 61;
   return d;
@@ -104,19 +113,21 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
 
 __global__ void __launch_bounds__(WG_THREADS_TC, 1)
 wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmX2,
-                const __grid_constant__ CUtensorMap tmDY, const WgParams p) {
+                const __grid_constant__ CUtensorMap tmDY, const __grid_constant__ CUtensorMap tmGp, const WgParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint8_t* sPair = smem;                                                   // WG_PAIR_SLOTS x 32 KB
   uint8_t* sB = sPair + WG_PAIR_SLOTS * 2 * WG_BLK_BYTES;                  // WG_B_SLOTS x n_bblk x 16 KB
-  uint8_t* sOnes = sB + WG_B_SLOTS * p.n_bblk * WG_BLK_BYTES;              // 16 KB of bf16 1.0
+  // halo mode re-uses the same region as WG_HALO_STAGES x (36 KB halo tile + 16 KB dY tile); the ones tile sits above both
+  uint8_t* sOnes = p.halo ? smem + WG_HALO_STAGES * WG_HALO_STAGE_BYTES
+                          : sB + WG_B_SLOTS * p.n_bblk * WG_BLK_BYTES;     // 16 KB of bf16 1.0
   uint64_t* bars = (uint64_t*)(sOnes + WG_BLK_BYTES);
   // barriers: [0,4) pair full, [4,8) pair empty, [8,10) b full, [10,12) b empty, 12: accumulators done
   uint32_t* tmem_slot = (uint32_t*)(bars + 16);
   const uint32_t bar0 = smem_u32(bars);
   auto BAR = [&](int i) { return bar0 + 8u * (uint32_t)i; };
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int n_tiles = (p.M_total + WG_TILE - 1) / WG_TILE;
+  const int n_tiles = p.halo ? (p.M_total / (p.H * p.W)) * p.tiles_per_img : (p.M_total + WG_TILE - 1) / WG_TILE;
   const int tile_beg = blockIdx.x * p.tiles_per_cta;
   const int tile_end = min(n_tiles, tile_beg + p.tiles_per_cta);
   const int N = 64 * p.n_bblk;
@@ -140,7 +151,25 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
   pdl_launch();
 
   if (warp == 0) {
-    {
+    if (p.halo) {
+      // ===================== TMA producer, halo mode: one halo box + one dY box per tile =====================
+      int st = 0;
+      uint32_t ph = 0;
+      for (int tile = tile_beg; tile < tile_end; ++tile) {
+        const int n0 = tile / p.tiles_per_img;
+        const int r = tile - n0 * p.tiles_per_img;
+        const int ty = r / p.tiles_x, tx = r - ty * p.tiles_x;
+        mbar_wait(BAR(4 + st), ph ^ 1);
+        if (elect_one()) {
+          uint8_t* stage = smem + st * WG_HALO_STAGE_BYTES;
+          mbar_expect_tx(BAR(st), (uint32_t)WG_HALO_STAGE_BYTES);
+          tma_load_4d(smem_u32(stage), &tmX, BAR(st), 0, tx * 8 - 1, ty * 16 - 1, n0);
+          tma_load_4d(smem_u32(stage + WG_HALO_BYTES), &tmDY, BAR(st), p.dy_c0, tx * 8, ty * 16, n0);
+        }
+        __syncwarp();
+        if (++st == WG_HALO_STAGES) { st = 0; ph ^= 1; }
+      }
+    } else {
       // ===================== TMA producer (whole warp loops, one elected lane issues) =====================
       const int hw = p.H * p.W;
       int ps = 0, bs = 0;
@@ -186,6 +215,39 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
                              ((uint32_t)(N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
       int ps = 0, bs = 0;
       uint32_t pph = 0, bph = 0;
+      if (p.halo) {
+        int st = 0;
+        uint32_t ph = 0;
+        const uint32_t ones = smem_u32(sOnes);
+        for (int tile = tile_beg; tile < tile_end; ++tile) {
+          mbar_wait(BAR(st), ph);
+          tc_fence_after();
+          const uint32_t h_addr = smem_u32(smem + st * WG_HALO_STAGE_BYTES);
+          const uint32_t b_addr = h_addr + WG_HALO_BYTES;
+          if (elect_one()) {
+            for (int pr = 0; pr < p.n_pairs; ++pr) {
+              // block (dy,dx): the tile's first pixel sits at halo row 1+dy, column 1+dx; halo rows are 16 pixels (2048 B)
+              const uint32_t a0 = h_addr + (uint32_t)(((1 + p.a_dy[2 * pr]) * 16 + (1 + p.a_dx[2 * pr])) * 128);
+              const bool second_ones = p.a_src[2 * pr + 1] == 2;
+              const uint32_t a1 = h_addr + (uint32_t)(((1 + p.a_dy[2 * pr + 1]) * 16 + (1 + p.a_dx[2 * pr + 1])) * 128);
+              const uint32_t d_tmem = tmem_u + (uint32_t)(pr * N);
+#pragma unroll
+              for (int k = 0; k < WG_TILE / 16; ++k) {
+                // K-step k = output rows 2k, 2k+1 of the tile = two 8-pixel groups one halo row (2048 B) apart
+                const uint32_t ak = a0 + k * 4096;
+                const uint32_t lbo = second_ones ? ones - ak : a1 - a0;
+                umma_bf16(d_tmem, umma_desc_mn_sw128(ak, lbo, 2048), umma_desc_mn_sw128(b_addr + k * 2048, WG_BLK_BYTES),
+                          idesc, (uint32_t)((tile != tile_beg) || k != 0));
+              }
+            }
+            umma_commit(BAR(4 + st));
+          }
+          __syncwarp();
+          if (++st == WG_HALO_STAGES) { st = 0; ph ^= 1; }
+        }
+        if (elect_one()) umma_commit(BAR(12));
+        __syncwarp();
+      } else {
       for (int tile = tile_beg; tile < tile_end; ++tile) {
         mbar_wait(BAR(8 + bs), bph);
         tc_fence_after();
@@ -217,29 +279,40 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
       }
       if (elect_one()) umma_commit(BAR(12));
       __syncwarp();
+      }
     }
   } else {
-    // ===================== epilogue: TMEM -> fp32 partial in the workspace =====================
+    // ===================== epilogue: TMEM -> registers -> swizzled staging tile -> TMA reduce-add into Gp ==========
+    // The staging tiles (2 x 16 KB: 128 rows x 32 fp32 columns, 128B-swizzled) alias the operand pipeline, which is idle
+    // once the last MMA has completed.
     const int quad = warp & 3;
     const int row = quad * 32 + lane;
+    const bool leader = threadIdx.x == 64;
     mbar_wait(BAR(12), 0);
     tc_fence_after();
-    float* wsc = p.ws + (size_t)blockIdx.x * p.n_pairs * 128 * N;
-    for (int pr = 0; pr < p.n_pairs; ++pr) {
-      const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(pr * N);
-      float* dst = wsc + ((size_t)pr * 128 + row) * N;
-      for (int c0 = 0; c0 < N; c0 += 32) {
-        uint32_t r[32];
-        tmem_ld32(taddr + (uint32_t)c0, r);
-        if (tile_beg >= tile_end) {
+    if (tile_beg < tile_end) {                         // a CTA without work has nothing to add
+      int nbuf = 0;
+      for (int pr = 0; pr < p.n_pairs; ++pr) {
+        const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(pr * N);
+        for (int c0 = 0; c0 < N; c0 += 32, ++nbuf) {
+          uint8_t* stg = smem + (nbuf & 1) * WG_BLK_BYTES;
+          uint32_t r[32];
+          tmem_ld32(taddr + (uint32_t)c0, r);
+          if (leader) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");   // the store two tiles back has read its buffer
+          asm volatile("bar.sync 1, 128;" ::: "memory");
 #pragma unroll
-          for (int j = 0; j < 32; ++j) r[j] = 0u;          // CTA without work: contribute zeros
+          for (int q = 0; q < 8; ++q)
+            *reinterpret_cast<uint4*>(stg + row * 128 + ((q ^ (row & 7)) << 4)) = make_uint4(r[4 * q], r[4 * q + 1], r[4 * q + 2], r[4 * q + 3]);
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          asm volatile("bar.sync 1, 128;" ::: "memory");
+          if (leader) {
+            asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3}], [%1];"
+                         ::"l"(&tmGp), "r"(smem_u32(stg)), "r"(c0), "r"(pr * 128) : "memory");
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+          }
         }
-#pragma unroll
-        for (int q = 0; q < 8; ++q)
-          reinterpret_cast<float4*>(dst + c0)[q] = make_float4(__uint_as_float(r[4 * q]), __uint_as_float(r[4 * q + 1]),
-                                                               __uint_as_float(r[4 * q + 2]), __uint_as_float(r[4 * q + 3]));
       }
+      if (leader) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     }
   }
   tc_fence_before();
@@ -249,49 +322,86 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
   }
 }
 
-// sum the per-CTA partials and accumulate into the torch-layout gradient: block blk (= pair*2 + half) of kind
-//   tap t, input-channel offset ci0:   dw[(co*I + ci0 + ci)*taps + t] += sum      (ci = row % 64)
-//   ones:                              dbias[co] += sum (row 0 of the block only)
-struct RedParams {
-  const float* ws; float* dw; float* dbias;
-  int n_cta, n_pairs, N, I, taps, I_real, N_real;
+// Packed gradient Gp -> torch-layout gradient.  Block blk (= pair*2 + half) of Gp holds 64 rows x N columns of kind
+//   tap t, input-channel block s:   dw[(co*I_real + 64 s + ci)*taps + t] += Gp[blk*64 + ci][co]
+//   ones:                            dbias[co] += Gp[blk*64][co]
+// One descriptor per convolution (host-built, lvae_wgrad_unpack_desc); the batched kernel walks a device table of them.
+struct UnpackDesc {
+  const float* gp; float* dw; float* dbias;
+  int n_pairs, N, taps, I_real, N_real, clear;
   int8_t kind[2 * WG_MAX_PAIRS];     // 0 tap block, 1 ones, 2 unused
   int8_t tap[2 * WG_MAX_PAIRS], ci0_blk[2 * WG_MAX_PAIRS];
+  int8_t pad_[2];
 };
+static_assert(sizeof(UnpackDesc) == 80, "UnpackDesc layout is mirrored by engine.py");
 
-__global__ void wgrad_reduce_kernel(RedParams p) {
+constexpr int UNPACK_CO = 4;          // output channels per CTA: each writes 4 contiguous (I_real * taps) runs of dw
+
+// A CTA gathers Gp[*][co0..co0+3] for every (tap, ci) into shared memory laid out like dw, then adds contiguous runs.
+// With clear != 0 it also zeroes what it consumed, so Gp is ready for the next step.
+__device__ __forceinline__ void unpack_body(const UnpackDesc& d, float (*tile)[9 * 64 + 1]) {
+  const int co0 = blockIdx.x * UNPACK_CO;
+  if (co0 >= d.N_real) return;
+  const int run = d.I_real * d.taps;                       // floats per output channel in dw
+  float* gp = const_cast<float*>(d.gp);
+  for (int i = threadIdx.x; i < d.n_pairs * 128; i += blockDim.x) {
+    const int blk = i >> 6, ci = i & 63;
+    const int kind = d.kind[blk];
+    float4 v = *reinterpret_cast<const float4*>(gp + (size_t)i * d.N + co0);
+    if (d.clear) *reinterpret_cast<float4*>(gp + (size_t)i * d.N + co0) = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (kind == 0) {
+      const int cin = d.ci0_blk[blk] * 64 + ci;
+      if (cin < d.I_real) {
+        const int o = cin * d.taps + d.tap[blk];
+        tile[0][o] = v.x; tile[1][o] = v.y; tile[2][o] = v.z; tile[3][o] = v.w;
+      }
+    } else if (kind == 1 && ci == 0 && d.dbias) {
+      const float vv[4] = {v.x, v.y, v.z, v.w};
+      for (int j = 0; j < UNPACK_CO; ++j)
+        if (co0 + j < d.N_real) d.dbias[co0 + j] += vv[j];
+    }
+  }
+  __syncthreads();
+  for (int j = 0; j < UNPACK_CO; ++j) {
+    if (co0 + j >= d.N_real) break;
+    float* dst = d.dw + (size_t)(co0 + j) * run;
+    for (int o = threadIdx.x; o < run; o += blockDim.x) dst[o] += tile[j][o];
+  }
+}
+
+// grid (ceil(max N_real / 4), n_desc): one descriptor of the device table per blockIdx.y
+__global__ void __launch_bounds__(256) wgrad_unpack_kernel(const UnpackDesc* __restrict__ table) {
   pdl_wait();
   pdl_launch();
-  // grid.y splits the partials: each thread sums its slice of CTAs (independent loads, 4 in flight), then adds
-  const int per = p.n_pairs * 128 * p.N;
-  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= per) return;
-  const int co = idx % p.N;
-  const int row = (idx / p.N) % 128;
-  const int pr = idx / (p.N * 128);
-  const int blk = pr * 2 + (row >> 6);
-  const int kind = p.kind[blk];
-  if (kind == 2 || (kind == 1 && ((row & 63) != 0 || !p.dbias))) return;
-  if (kind == 0 && p.ci0_blk[blk] * 64 + (row & 63) >= p.I_real) return;      // zero-padded input channels
-  if (co >= p.N_real) return;                                                   // zero-padded output channels
-  const int chunk = (p.n_cta + gridDim.y - 1) / gridDim.y;
-  const int c_beg = blockIdx.y * chunk, c_end = min(p.n_cta, c_beg + chunk);
-  if (c_beg >= c_end) return;
-  const float* src = p.ws + idx;
-  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-  int c = c_beg;
-  for (; c + 4 <= c_end; c += 4) {
-    s0 += __ldg(src + (size_t)c * per);
-    s1 += __ldg(src + (size_t)(c + 1) * per);
-    s2 += __ldg(src + (size_t)(c + 2) * per);
-    s3 += __ldg(src + (size_t)(c + 3) * per);
-  }
-  for (; c < c_end; ++c) s0 += __ldg(src + (size_t)c * per);
-  const float s = (s0 + s1) + (s2 + s3);
-  float* dst = kind == 1 ? p.dbias + co
-                         : p.dw + ((size_t)co * p.I_real + p.ci0_blk[blk] * 64 + (row & 63)) * p.taps + p.tap[blk];
-  if (gridDim.y == 1) *dst += s;
-  else atomicAdd(dst, s);
+  __shared__ UnpackDesc d;
+  __shared__ float tile[UNPACK_CO][9 * 64 + 1];
+  if (threadIdx.x < sizeof(UnpackDesc) / 4)
+    reinterpret_cast<uint32_t*>(&d)[threadIdx.x] = reinterpret_cast<const uint32_t*>(table + blockIdx.y)[threadIdx.x];
+  __syncthreads();
+  unpack_body(d, tile);
+}
+// single convolution, descriptor passed by value
+__global__ void __launch_bounds__(256) wgrad_unpack_one_kernel(const UnpackDesc dpar) {
+  pdl_wait();
+  pdl_launch();
+  __shared__ UnpackDesc d;
+  __shared__ float tile[UNPACK_CO][9 * 64 + 1];
+  if (threadIdx.x == 0) d = dpar;
+  __syncthreads();
+  unpack_body(d, tile);
+}
+
+void fill_unpack_desc(UnpackDesc* d, const float* gp, float* dw, float* dbias, int N, int ksize, int inputs, int I_real,
+                      int N_real, int clear) {
+  memset(d, 0, sizeof(*d));
+  const int taps = ksize * ksize;
+  int nblk = 0;
+  for (int t = 0; t < taps; ++t)
+    for (int s = 0; s < inputs && nblk < 2 * WG_MAX_PAIRS - 1; ++s, ++nblk) { d->kind[nblk] = 0; d->tap[nblk] = (int8_t)t; d->ci0_blk[nblk] = (int8_t)s; }
+  if (nblk % 2 == 0 && nblk < 2 * WG_MAX_PAIRS - 1) { d->kind[nblk] = 2; ++nblk; }
+  d->kind[nblk] = 1; ++nblk;
+  d->gp = gp; d->dw = dw; d->dbias = dbias; d->n_pairs = nblk / 2; d->N = N; d->taps = taps;
+  d->I_real = I_real > 0 ? I_real : 64 * inputs; d->N_real = N_real > 0 ? N_real : N; d->clear = clear;
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
@@ -319,85 +429,132 @@ int make_act_map(EncodeTiledFn enc, CUtensorMap* tm, const void* ptr, int B, int
 
 }  // namespace
 
-// Workspace floats needed by lvae_conv2d_wgrad_tc for these shapes (0 if unsupported).
-LVAE_API long long lvae_wgrad_tc_workspace(int B, int H, int W, int N, int ksize, int two_inputs) {
-  if (!(N == 64 || N == 128) || !(ksize == 1 || ksize == 3)) return 0;
-  int ablk = ksize * ksize * (two_inputs ? 2 : 1) + 1;
-  int n_pairs = (ablk + 1) / 2;
-  if (n_pairs * N > 512) return 0;
-  return (long long)lvae_num_sms() * n_pairs * 128 * N;
+static bool wgrad_shape_ok(int N, int ksize, int inputs) {
+  if (!(N == 64 || N == 128) || !(ksize == 1 || ksize == 3) || inputs < 1 || inputs > 2) return false;
+  const int nblk = ksize * ksize * inputs;
+  const int n_pairs = (nblk + 1 + (nblk % 2 == 0 ? 1 : 0)) / 2;
+  return n_pairs <= WG_MAX_PAIRS && n_pairs * N <= 512;
 }
 
-// x, x2: (B,H,W,64) bf16 (x2 optional); dy: (B,H,W,N) bf16, N in {64,128}, already multiplied by any Dropout2d mask.
-// dw: (N, I_real, k, k) fp32 (+=); I_real <= 64 * inputs (x may carry zero-padded channels beyond I_real, 0 = no padding);
-// dy may carry zero-padded channels beyond N_real (0 = none): dw is then (N_real, I_real, k, k) and dbias [N_real].
-// dY is (B,H,W,dyC) (dyC = 0 means N); this launch uses its channels [dy_c0, dy_c0 + N).
-// dbias: fp32 (+=) or NULL.  ws: workspace (see above).
-LVAE_API int lvae_conv2d_wgrad_tc(const void* x, const void* x2, const void* dy, float* dw, float* dbias, float* ws,
-                                  int B, int H, int W, int N, int ksize, int I_real, int N_real, int dyC, int dy_c0,
-                                  cudaStream_t stream) {
-  LVAE_REQUIRE(x && dy && dw && ws, "conv2d_wgrad_tc: null pointer");
+// Floats in the packed gradient Gp of one convolution (0 if the shape is unsupported): pairs x 128 rows x N columns.
+LVAE_API long long lvae_wgrad_tc_packed_size(int N, int ksize, int two_inputs) {
+  const int inputs = two_inputs ? 2 : 1;
+  if (!wgrad_shape_ok(N, ksize, inputs)) return 0;
+  const int nblk = ksize * ksize * inputs;
+  return (long long)((nblk + 1 + (nblk % 2 == 0 ? 1 : 0)) / 2) * 128 * N;
+}
+// kept for callers of the previous interface: the workspace of lvae_conv2d_wgrad_tc is one packed gradient
+LVAE_API long long lvae_wgrad_tc_workspace(int B, int H, int W, int N, int ksize, int two_inputs) {
+  (void)B; (void)H; (void)W;
+  return lvae_wgrad_tc_packed_size(N, ksize, two_inputs);
+}
+
+// Gp += wgrad.  x, x2: (B,H,W,64) bf16 (x2 optional); dY: (B,H,W,dyC) bf16 (dyC = 0 means N), already multiplied by any
+// Dropout2d mask; this launch uses its channels [dy_c0, dy_c0 + N), N in {64, 128}.  gp: lvae_wgrad_tc_packed_size floats.
+LVAE_API int lvae_conv2d_wgrad_tc_acc(const void* x, const void* x2, const void* dy, float* gp, int B, int H, int W, int N,
+                                      int ksize, int dyC, int dy_c0, cudaStream_t stream) {
+  LVAE_REQUIRE(x && dy && gp, "conv2d_wgrad_tc: null pointer");
   LVAE_REQUIRE((N == 64 || N == 128) && (ksize == 1 || ksize == 3), "conv2d_wgrad_tc: N must be 64 or 128, ksize 1 or 3");
   LVAE_REQUIRE((W & (W - 1)) == 0 && (H & (H - 1)) == 0 && W <= 128, "conv2d_wgrad_tc: H and W must be powers of two (W <= 128)");
   EncodeTiledFn enc = wg_get_encode();
   if (!enc) { lvae_set_error("conv2d_wgrad_tc: cuTensorMapEncodeTiled unavailable"); return LVAE_ERR_CUDA; }
   const int inputs = x2 ? 2 : 1, taps = ksize * ksize;
-  LVAE_REQUIRE(taps * inputs + 1 + ((taps * inputs) % 2 == 0 ? 1 : 0) <= 2 * WG_MAX_PAIRS,
-               "conv2d_wgrad_tc: too many operand blocks (3x3 over two inputs is not supported)");
+  LVAE_REQUIRE(wgrad_shape_ok(N, ksize, inputs), "conv2d_wgrad_tc: too many operand blocks (3x3 over two inputs is not supported)");
   WgParams p{};
-  RedParams rp{};
   int nblk = 0;
   for (int t = 0; t < taps; ++t) {
     int oy = t / ksize - ksize / 2, ox = t % ksize - ksize / 2;
-    for (int s = 0; s < inputs; ++s, ++nblk) {
-      p.a_src[nblk] = (int8_t)s; p.a_dx[nblk] = (int8_t)ox; p.a_dy[nblk] = (int8_t)oy;
-      rp.kind[nblk] = 0; rp.tap[nblk] = (int8_t)t; rp.ci0_blk[nblk] = (int8_t)s;
-    }
+    for (int s = 0; s < inputs; ++s, ++nblk) { p.a_src[nblk] = (int8_t)s; p.a_dx[nblk] = (int8_t)ox; p.a_dy[nblk] = (int8_t)oy; }
   }
   // the ones block must be the SECOND half of a pair (its half of the descriptor is not advanced along K)
-  if (nblk % 2 == 0) { p.a_src[nblk] = 0; p.a_dx[nblk] = 0; p.a_dy[nblk] = 0; rp.kind[nblk] = 2; ++nblk; }
-  p.a_src[nblk] = 2; rp.kind[nblk] = 1; ++nblk;
+  if (nblk % 2 == 0) { p.a_src[nblk] = 0; p.a_dx[nblk] = 0; p.a_dy[nblk] = 0; ++nblk; }
+  p.a_src[nblk] = 2; ++nblk;
   p.n_pairs = nblk / 2;
-  LVAE_REQUIRE(p.n_pairs <= WG_MAX_PAIRS, "conv2d_wgrad_tc: too many operand blocks");
   p.n_bblk = N / 64;
-  LVAE_REQUIRE(p.n_pairs * N <= 512, "conv2d_wgrad_tc: accumulators do not fit TMEM");
   p.tmem_cols = 32;
   while (p.tmem_cols < p.n_pairs * N) p.tmem_cols *= 2;
   p.M_total = B * H * W; p.H = H; p.W = W;
-  const int n_tiles = (p.M_total + WG_TILE - 1) / WG_TILE;
+  static int halo_env = -1;
+  if (halo_env < 0) { const char* e = getenv("LVAE_WGRAD_HALO"); halo_env = e ? atoi(e) : 1; }
+  p.halo = (halo_env && ksize == 3 && !x2 && N == 64 && W % 8 == 0 && H % 16 == 0) ? 1 : 0;
+  p.tiles_x = W / 8;
+  p.tiles_per_img = (W / 8) * (H / 16);
+  const int n_tiles = p.halo ? B * p.tiles_per_img : (p.M_total + WG_TILE - 1) / WG_TILE;
   int grid = n_tiles < lvae_num_sms() ? n_tiles : lvae_num_sms();
-  // fewer, fatter CTAs for small problems: every CTA costs one partial in the reduction
+  // fewer, fatter CTAs for small problems: every CTA costs one pass of reduce-stores over the whole gradient
   if (n_tiles <= lvae_num_sms() && n_tiles >= 8) grid = (n_tiles + 1) / 2;
   p.tiles_per_cta = (n_tiles + grid - 1) / grid;
   grid = (n_tiles + p.tiles_per_cta - 1) / p.tiles_per_cta;
-  p.ws = ws;
-  const int bw = W;
+  int bw = W;
   int bh = 1;
   while (bh * 2 <= H && bh * 2 * bw <= WG_TILE) bh *= 2;
-  const int bn = WG_TILE / (bw * bh);
-  CUtensorMap tmX, tmX2, tmDY;
-  int r = make_act_map(enc, &tmX, x, B, H, W, 64, bw, bh, bn);
+  int bn = WG_TILE / (bw * bh);
+  if (p.halo) { bw = 8; bh = 16; bn = 1; }
+  CUtensorMap tmX, tmX2, tmDY, tmGp;
+  int r = p.halo ? make_act_map(enc, &tmX, x, B, H, W, 64, 16, 18, 1) : make_act_map(enc, &tmX, x, B, H, W, 64, bw, bh, bn);
   if (!r) r = make_act_map(enc, &tmX2, x2 ? x2 : x, B, H, W, 64, bw, bh, bn);
   if (dyC <= 0) dyC = N;
   LVAE_REQUIRE(dy_c0 % 64 == 0 && dy_c0 + N <= dyC, "conv2d_wgrad_tc: bad dY channel window");
   p.dy_c0 = dy_c0;
   if (!r) r = make_act_map(enc, &tmDY, dy, B, H, W, dyC, bw, bh, bn);
+  if (!r) {
+    // Gp as a 2-D fp32 tensor (rows = pairs x 128, columns = N); the reduce-store box is 128 rows x 32 columns (128 B)
+    cuuint64_t gdim[2] = {(cuuint64_t)N, (cuuint64_t)p.n_pairs * 128};
+    cuuint64_t gstr[1] = {(cuuint64_t)N * 4};
+    cuuint32_t box[2] = {32, 128};
+    cuuint32_t estr[2] = {1, 1};
+    r = (int)enc(&tmGp, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)gp, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                 CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  }
   if (r) { lvae_set_error("conv2d_wgrad_tc: tensor map encode failed: %d", r); return LVAE_ERR_CUDA; }
-  const size_t smem = 1024 + (size_t)WG_PAIR_SLOTS * 2 * WG_BLK_BYTES + (size_t)WG_B_SLOTS * p.n_bblk * WG_BLK_BYTES + WG_BLK_BYTES + 256;
+  const size_t smem = p.halo ? 1024 + (size_t)WG_HALO_STAGES * WG_HALO_STAGE_BYTES + WG_BLK_BYTES + 256
+                             : 1024 + (size_t)WG_PAIR_SLOTS * 2 * WG_BLK_BYTES + (size_t)WG_B_SLOTS * p.n_bblk * WG_BLK_BYTES + WG_BLK_BYTES + 256;
   static bool attr = false;
   if (!attr) {
     cudaError_t e = cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) { lvae_set_error("conv2d_wgrad_tc: cannot raise dynamic smem: %s", cudaGetErrorString(e)); return LVAE_ERR_CUDA; }
     attr = true;
   }
-  lvae_launch(wgrad_tc_kernel, grid, WG_THREADS_TC, smem, stream, tmX, tmX2, tmDY, p);
+  lvae_launch(wgrad_tc_kernel, grid, WG_THREADS_TC, smem, stream, tmX, tmX2, tmDY, tmGp, p);
   LVAE_COUNT_LAUNCH();
   LVAE_CHECK_LAUNCH("conv2d_wgrad_tc");
-  rp.ws = ws; rp.dw = dw; rp.dbias = dbias; rp.n_cta = grid; rp.n_pairs = p.n_pairs; rp.N = N; rp.I = 64 * inputs; rp.taps = taps; rp.I_real = I_real > 0 ? I_real : 64 * inputs; rp.N_real = N_real > 0 ? N_real : N;
-  const int per = p.n_pairs * 128 * N;
-  const int ysplit = grid >= 64 ? 8 : (grid >= 16 ? 4 : 1);
-  lvae_launch(wgrad_reduce_kernel, dim3((per + 255) / 256, ysplit), 256, 0, stream, rp);
+  return LVAE_OK;
+}
+
+// Bytes of one unpack descriptor and its construction on the host (the engine keeps a device table of them).
+LVAE_API int lvae_wgrad_unpack_desc_size(void) { return (int)sizeof(UnpackDesc); }
+LVAE_API int lvae_wgrad_unpack_desc(void* desc_host, const float* gp, float* dw, float* dbias, int N, int ksize, int two_inputs,
+                                    int I_real, int N_real, int clear) {
+  LVAE_REQUIRE(desc_host && gp && dw, "wgrad_unpack_desc: null pointer");
+  LVAE_REQUIRE(wgrad_shape_ok(N, ksize, two_inputs ? 2 : 1), "wgrad_unpack_desc: unsupported shape");
+  fill_unpack_desc((UnpackDesc*)desc_host, gp, dw, dbias, N, ksize, two_inputs ? 2 : 1, I_real, N_real, clear);
+  return LVAE_OK;
+}
+// dw / dbias += unpack(Gp) for n descriptors in device memory (max_n_real: largest N_real among them)
+LVAE_API int lvae_wgrad_unpack_batched(const void* desc_dev, int n, int max_n_real, cudaStream_t stream) {
+  LVAE_REQUIRE(desc_dev && n > 0 && max_n_real > 0, "wgrad_unpack_batched: bad args");
+  lvae_launch(wgrad_unpack_kernel, dim3(cdiv(max_n_real, UNPACK_CO), n), 256, 0, stream, (const UnpackDesc*)desc_dev);
   LVAE_COUNT_LAUNCH();
-  LVAE_CHECK_LAUNCH("wgrad_reduce");
+  LVAE_CHECK_LAUNCH("wgrad_unpack");
+  return LVAE_OK;
+}
+
+// One-call form: dw (N_real, I_real, k, k) fp32 += wgrad, dbias [N_real] += column sums (or NULL).  x may carry zero-padded
+// channels beyond I_real (0 = none), dY beyond N_real (0 = none).  ws: lvae_wgrad_tc_workspace floats, overwritten.
+LVAE_API int lvae_conv2d_wgrad_tc(const void* x, const void* x2, const void* dy, float* dw, float* dbias, float* ws,
+                                  int B, int H, int W, int N, int ksize, int I_real, int N_real, int dyC, int dy_c0,
+                                  cudaStream_t stream) {
+  LVAE_REQUIRE(x && dy && dw && ws, "conv2d_wgrad_tc: null pointer");
+  const long long n = lvae_wgrad_tc_packed_size(N, ksize, x2 != nullptr);
+  LVAE_REQUIRE(n > 0, "conv2d_wgrad_tc: unsupported shape");
+  cudaError_t e = cudaMemsetAsync(ws, 0, (size_t)n * 4, stream);
+  if (e != cudaSuccess) { lvae_set_error("conv2d_wgrad_tc: memset failed: %s", cudaGetErrorString(e)); return LVAE_ERR_CUDA; }
+  int rc = lvae_conv2d_wgrad_tc_acc(x, x2, dy, ws, B, H, W, N, ksize, dyC, dy_c0, stream);
+  if (rc) return rc;
+  UnpackDesc d;
+  fill_unpack_desc(&d, ws, dw, dbias, N, ksize, x2 ? 2 : 1, I_real, N_real, 0);
+  lvae_launch(wgrad_unpack_one_kernel, dim3(cdiv(d.N_real, UNPACK_CO), 1), 256, 0, stream, d);
+  LVAE_COUNT_LAUNCH();
+  LVAE_CHECK_LAUNCH("wgrad_unpack");
   return LVAE_OK;
 }

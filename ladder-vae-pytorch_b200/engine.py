@@ -9,6 +9,7 @@ the arena in buckets, outside the graph] -> fused Adamax + L2 norm.
 """
 from __future__ import annotations
 
+import ctypes
 import math
 import os
 import struct
@@ -84,6 +85,51 @@ class ParamArena:
         for p in self.params:
             if hasattr(p, "_lvae_grad_sink"):
                 del p._lvae_grad_sink
+            if hasattr(p, "_lvae_gp"):
+                del p._lvae_gp
+
+
+class PackedGradArena:
+    """Packed weight gradients of every convolution the tcgen05 wgrad kernel serves (lvae_conv2d_wgrad_tc_acc adds
+    into them with TMA reduce-stores), and the device table that lets ONE launch per step re-lay all of them into the
+    (O,I,kh,kw) gradient arena and clear them again."""
+
+    def __init__(self, model: torch.nn.Module):
+        lib = _capi.lib()
+        convs = []
+        for m in model.modules():
+            if isinstance(m, (Conv2d, ConvTranspose2d)):
+                sp = m.spec
+                w = m.weight
+                if not (w.requires_grad and hasattr(w, "_lvae_grad_sink") and sp.tc_shape and sp.cout in (64, 128)):
+                    continue
+                two = sp.cin == 128 and sp.k == 1
+                if not (sp.cin <= 64 or two):
+                    continue
+                n = int(lib.lvae_wgrad_tc_packed_size(sp.cout, sp.k, int(two)))
+                if n > 0 and (m.bias is None or hasattr(m.bias, "_lvae_grad_sink")):
+                    convs.append((m, two, n))
+        self.n = len(convs)
+        if not self.n:
+            return
+        dev = convs[0][0].weight.device
+        self.flat = torch.zeros(sum(n for _, _, n in convs), dtype=torch.float32, device=dev)
+        dsz = int(lib.lvae_wgrad_unpack_desc_size())
+        host = ctypes.create_string_buffer(dsz * self.n)
+        off = 0
+        for i, (m, two, n) in enumerate(convs):
+            gp = self.flat[off:off + n]
+            off += n
+            m.weight._lvae_gp = gp
+            bias_sink = m.bias._lvae_grad_sink if m.bias is not None else None
+            call("lvae_wgrad_unpack_desc", ctypes.addressof(host) + i * dsz, gp.data_ptr(), m.weight._lvae_grad_sink.data_ptr(),
+                 bias_sink.data_ptr() if bias_sink is not None else None, m.spec.cout, m.spec.k, int(two), m.spec.cin,
+                 m.spec.cout, 1)
+        self.table = torch.frombuffer(bytearray(host.raw), dtype=torch.uint8).to(dev)
+
+    def unpack(self):
+        if self.n:
+            call("lvae_wgrad_unpack_batched", self.table.data_ptr(), self.n, 128, _stream())
 
 
 class PackTable:
@@ -130,6 +176,7 @@ class TrainEngine:
         self.l2 = torch.zeros((), dtype=torch.float32, device=dev)
         self.compute_l2 = compute_l2
         self.packs = PackTable(model, getattr(model, "compute_dtype", torch.float32))
+        self.gpacks = PackedGradArena(model)
         self.buckets = bucket_ranges(self.arena.numel, bucket_bytes)
         self.x = torch.zeros((batch_size, model.color_ch) + tuple(model.img_shape), dtype=torch.float32, device=dev)
         self.use_graph = use_graph
@@ -159,6 +206,7 @@ class TrainEngine:
         finally:
             ops.join_side_stream()
             ops.set_side_stream(None)
+        self.gpacks.unpack()
         elbo = (out["ll"] - out["kl_sep"]).mean()
         self.out = {"loss": loss.detach(), "elbo": elbo.detach(), "recons": recons.detach(), "kl": out["kl"].detach(),
                     "kl_avg_layerwise": out["kl_avg_layerwise"].detach()}

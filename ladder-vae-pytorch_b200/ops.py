@@ -334,12 +334,11 @@ stats = {"tc_fwd": 0, "tc_dgrad": 0, "tc_wgrad": 0, "cc_fwd": 0, "cc_dgrad": 0, 
 
 
 def _wgrad_workspace(device) -> torch.Tensor:
-    """Scratch for the per-CTA partials of lvae_conv2d_wgrad_tc (stream-ordered reuse: one per stream)."""
+    """Scratch packed gradient of lvae_conv2d_wgrad_tc (stream-ordered reuse: one per stream)."""
     key = (device, torch.cuda.current_stream().cuda_stream)
     ws = _wgrad_ws.get(key)
     if ws is None:
-        sms = torch.cuda.get_device_properties(device).multi_processor_count
-        ws = torch.empty(sms * 512 * 128, dtype=torch.float32, device=device)
+        ws = torch.empty(512 * 128, dtype=torch.float32, device=device)        # one packed gradient (<= 5 pairs x 128 x 64)
         _wgrad_ws[key] = ws
     return ws
 
@@ -480,8 +479,14 @@ def conv_backward_raw(spec: ConvSpec, xn, x2n, weight, bias, out_scale, gyn, nee
         if use_tc and out_scale is None and C1 == 64 and C2 in (0, 64) and N in (64, 128) and gyn.dtype == torch.bfloat16 \
                 and spec.k * spec.k * (2 if C2 else 1) <= 9:
             stats["tc_wgrad"] += 1
-            call("lvae_conv2d_wgrad_tc", xn.data_ptr(), _p(x2n), gyn.data_ptr(), gwbuf.data_ptr(), _p(gbbuf),
-                 _wgrad_workspace(xn.device).data_ptr(), B, Hi, Wi, N, spec.k, spec.cin if padded else 0, 0, 0, 0, _stream())
+            gp = getattr(weight, "_lvae_gp", None) if (sunk and bsunk) else None
+            if gp is not None:
+                # engine-owned packed gradient: every CTA reduce-adds into it, the engine unpacks all of them in one launch
+                call("lvae_conv2d_wgrad_tc_acc", xn.data_ptr(), _p(x2n), gyn.data_ptr(), gp.data_ptr(), B, Hi, Wi, N, spec.k,
+                     0, 0, _stream())
+            else:
+                call("lvae_conv2d_wgrad_tc", xn.data_ptr(), _p(x2n), gyn.data_ptr(), gwbuf.data_ptr(), _p(gbbuf),
+                     _wgrad_workspace(xn.device).data_ptr(), B, Hi, Wi, N, spec.k, spec.cin if padded else 0, 0, 0, 0, _stream())
         elif not spec.transposed:
             stats["cc_wgrad"] += 1
             call("lvae_conv2d_wgrad", xn.data_ptr(), _p(x2n), gyn.data_ptr(), None, _p(out_scale),

@@ -11,7 +11,8 @@ from lvae_b200 import _capi, ops  # noqa: E402
 
 B, C = 256, 64
 one = len(sys.argv) > 1 and sys.argv[1] == "--one"
-shapes = [(int(os.environ.get("HW", "16")), 3, 64)] if one else [(32, 3, 64), (16, 3, 64), (8, 3, 64), (4, 3, 64), (2, 3, 64), (16, 1, 128), (32, 3, 100)]
+wgrad = "--wgrad" in sys.argv
+shapes = [(int(os.environ.get("HW", "16")), 3, 64)] if one else [(32, 3, 64), (16, 3, 64), (8, 3, 64), (4, 3, 64), (16, 1, 128)] if "--wgrad" in sys.argv else [(32, 3, 64), (16, 3, 64), (8, 3, 64), (4, 3, 64), (2, 3, 64), (16, 1, 128), (32, 3, 100)]
 s = torch.cuda.current_stream()
 for HW, k, N in shapes:
     per = B * HW * HW * (C + N) * 2
@@ -22,7 +23,17 @@ for HW, k, N in shapes:
     wp = ops.WeightPack(N, C, k * k, 2).get(w, torch.bfloat16)
     bias = torch.zeros(N, device="cuda")
 
+    dw = torch.zeros(N, C, k, k, device="cuda")
+    db = torch.zeros(N, device="cuda")
+    ws = torch.empty(148 * 512 * 128, device="cuda")
+
+    def launch_wgrad(i):
+        _capi.call("lvae_conv2d_wgrad_tc", xs[i % nbuf].data_ptr(), None, ys[i % nbuf].data_ptr(), dw.data_ptr(), db.data_ptr(),
+                   ws.data_ptr(), B, HW, HW, N, k, 0, 0, 0, 0, torch.cuda.current_stream().cuda_stream)
+
     def launch(i):
+        if wgrad:
+            return launch_wgrad(i)
         _capi.call("lvae_conv2d_tc", xs[i % nbuf].data_ptr(), None, wp.data_ptr(), bias.data_ptr(), None, None,
                    ys[i % nbuf].data_ptr(), None, 0, B, HW, HW, C, N, k, 0, 0, torch.cuda.current_stream().cuda_stream)
     launch(0)

@@ -25,6 +25,8 @@ CASES = [
     (64, 64, 3, 4, 4, 3, 0, True),       # 48 pixels: partial tile, batch dimension out of bounds in the box
     (64, 64, 3, 2, 2, 40, 0, True),      # 160 pixels: two tiles, second partial
     (64, 64, 3, 64, 64, 1, 0, True),
+    (64, 64, 3, 16, 8, 3, 0, True),      # non-square halo tiles (one tile column)
+    (64, 64, 3, 32, 16, 2, 0, False),
     (64, 128, 1, 16, 16, 2, 0, True),    # gate conv
     (64, 64, 1, 8, 8, 4, 64, True),      # merge conv over two inputs
     (64, 100, 3, 32, 32, 2, 0, True),    # DMoL head (N padded to 112)
