@@ -70,8 +70,13 @@ enum { ACT_NONE = 0, ACT_RELU = 1, ACT_LEAKY = 2, ACT_ELU = 3, ACT_SELU = 4 };
 
 // FAST (bf16 activations): ex2.approx-based exponentials, ~2 instructions instead of the ~40 of expm1f / expf;
 // their 1e-7 absolute error is far below bf16 rounding.  The fp32 parity mode keeps the exact functions.
-template <bool FAST> __device__ __forceinline__ float exp_t(float v) { return FAST ? __expf(v) : expf(v); }
-template <bool FAST> __device__ __forceinline__ float expm1_t(float v) { return FAST ? __expf(v) - 1.f : expm1f(v); }
+__device__ __forceinline__ float ex2_approx(float x) {        // one MUFU.EX2, no range fix-ups (flushes denormals)
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+template <bool FAST> __device__ __forceinline__ float exp_t(float v) { return FAST ? ex2_approx(v * 1.4426950408889634f) : expf(v); }
+template <bool FAST> __device__ __forceinline__ float expm1_t(float v) { return FAST ? ex2_approx(v * 1.4426950408889634f) - 1.f : expm1f(v); }
 template <bool FAST>
 __device__ __forceinline__ float act_fwd_t(float v, int act) {
   switch (act) {
@@ -97,7 +102,7 @@ __device__ __forceinline__ float act_fwd(float v, int act) { return act_fwd_t<fa
 __device__ __forceinline__ float act_bwd(float v, int act) { return act_bwd_t<false>(v, act); }
 
 template <bool FAST> __device__ __forceinline__ float sigmoid_t(float v) {
-  return FAST ? __fdividef(1.f, 1.f + __expf(-v)) : 1.f / (1.f + expf(-v));
+  return FAST ? __fdividef(1.f, 1.f + ex2_approx(-1.4426950408889634f * v)) : 1.f / (1.f + expf(-v));
 }
 __device__ __forceinline__ float sigmoidf_(float v) { return sigmoid_t<false>(v); }
 // torch softplus (beta 1, threshold 20)

@@ -270,7 +270,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
                const __grid_constant__ CUtensorMap tmY2, const TcParams p) {
   extern __shared__ uint8_t smem_raw[];
   // 1024-byte alignment for the 128B swizzle atoms
-  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  // (offset arithmetic on the __shared__ array, not on a uintptr_t: the compiler keeps the shared address space)
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   const int wbytes_kb = p.Npad * 128;                        // one k-block of weights
   uint8_t* sW = smem;                                        // n_kb * Npad * 128
   uint8_t* sA = sW + ((p.n_kb * wbytes_kb + 1023) & ~1023);  // n_stages * 16 KB
@@ -281,8 +282,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
   const int S = p.n_stages;
   uint32_t* tmem_slot = (uint32_t*)(bars + 2 * S + 5);
   float* sbias = (float*)(bars + 32);                         // Npad floats (<= 256), zero beyond N / when bias == null
-  float* sbn = sbias + 256;                                   // [mean | rstd | gamma | beta] x 64 (fused BatchNorm-backward reduction)
-  float* sred = sbn + 256;                                    // 4 x 8 warps x 32 lanes reduction scratch
+  float* sred = sbias + 256;                                  // 2 statistics x 8 warps x 64 channels (fused reductions)
   const uint32_t bar0 = smem_u32(bars);
   auto BAR = [&](int i) { return bar0 + 8u * (uint32_t)i; };
 
@@ -314,12 +314,6 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     __syncwarp();
   }
   for (int i = threadIdx.x; i < p.Npad; i += TC_THREADS) sbias[i] = (p.bias && i < p.N) ? p.bias[i] : 0.f;
-  if (p.bnb_acc && threadIdx.x < 64) {                          // parameters / saved statistics: written long before this kernel
-    sbn[threadIdx.x] = p.bnb_save[threadIdx.x];
-    sbn[64 + threadIdx.x] = p.bnb_save[64 + threadIdx.x];
-    sbn[128 + threadIdx.x] = p.bnb_gamma[threadIdx.x];
-    sbn[192 + threadIdx.x] = p.bnb_beta[threadIdx.x];
-  }
   if (warp == 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(p.tmem_cols) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -438,9 +432,42 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     const int half = (warp - 2) >> 2;                          // which 32-column chunks (even / odd) this warp drains
     const int row = quad * 32 + lane;
     const int hw = p.H * p.W;
-    float accA[FUSE ? 32 : 1], accB[FUSE ? 32 : 1];               // row-private partial sums of the fused reduction
+    // Fused reductions (FUSE != 0) run as a second, channel-major pass over the staged bf16 output tile: epilogue warp e
+    // owns rows [16 e, 16 e + 16), lane l owns channels 2l and 2l+1, so the per-channel constants and the running sums
+    // live in a handful of registers and no cross-lane traffic is needed until the CTA's last tile.
+    const int ew = warp - 2;
+    float ra0 = 0.f, ra1 = 0.f, rb0 = 0.f, rb1 = 0.f;              // sums A / B of channels 2l, 2l+1
+    float kx0 = 0.f, kx1 = 0.f, kb0 = 0.f, kb1 = 0.f, kg0 = 0.f, kg1 = 0.f, kc0 = 0.f, kc1 = 0.f;
+    if (FUSE == 2) {
+      // xhat = x * kx + kb;  pre-activation = xhat * gamma + beta = x * kg + kc   (saved statistics / parameters: written
+      // long before this kernel, safe to read ahead of pdl_wait's successor ordering)
+      const float m0 = p.bnb_save[2 * lane], m1 = p.bnb_save[2 * lane + 1];
+      const float r0 = p.bnb_save[64 + 2 * lane], r1 = p.bnb_save[64 + 2 * lane + 1];
+      const float g0 = p.bnb_gamma[2 * lane], g1 = p.bnb_gamma[2 * lane + 1];
+      kx0 = r0; kx1 = r1; kb0 = -m0 * r0; kb1 = -m1 * r1;
+      kg0 = r0 * g0; kg1 = r1 * g1;
+      kc0 = p.bnb_beta[2 * lane] - m0 * r0 * g0; kc1 = p.bnb_beta[2 * lane + 1] - m1 * r1 * g1;
+    }
+    // pixel index of staged row (16 ew + i) of a tile = row_base(tile) + (halo ? (i >> 3) * W + (i & 7) : i)
+    auto row_base = [&](int tile) -> long long {
+      if (p.halo) {
+        int n0 = tile / p.tiles_per_img;
+        int rr = tile - n0 * p.tiles_per_img;
+        int ty = rr / p.tiles_x, tx = rr - ty * p.tiles_x;
+        return ((long long)n0 * p.H + ty * 16 + ew * 2) * p.W + tx * 8;
+      }
+      return (long long)tile * TC_BM + ew * 16;
+    };
+    const int rstep = p.halo ? p.W - 8 : 0;                        // extra pixels skipped after 8 rows of the staged tile
+    uint32_t xq[FUSE == 2 ? 16 : 1];                               // BatchNorm input of this tile (channels 2l, 2l+1)
+    auto load_xq = [&](long long rb) {
+      const uint32_t* xb = reinterpret_cast<const uint32_t*>(p.bnb_x + rb * 64) + lane;
 #pragma unroll
-    for (int j = 0; j < (FUSE ? 32 : 1); ++j) accA[j] = accB[j] = 0.f;
+      for (int i = 0; i < (FUSE == 2 ? 16 : 1); ++i) {
+        const int off = i + (i >> 3) * rstep;
+        xq[i] = rb + off < p.M_total ? __ldg(xb + off * 32) : 0u;
+      }
+    };
     int it = 0;
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
       const int buf = it & 1;
@@ -454,12 +481,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         m = ((long long)n0 * p.H + ty * 16 + (row >> 3)) * p.W + tx * 8 + (row & 7);
       }
       const bool valid = m < p.M_total;
-      uint4 xu[4];
-      if (FUSE == 2) {                                             // BatchNorm input rows: fetched while the MMAs still run
-        const uint4* xr = reinterpret_cast<const uint4*>(p.bnb_x + (valid ? m : 0) * 64 + 32 * half);
-#pragma unroll
-        for (int q = 0; q < 4; ++q) xu[q] = __ldg(xr + q);
-      }
+      const long long rbase = row_base(tile);
+      if (FUSE == 2) load_xq(rbase);                               // BatchNorm input rows: fetched while the MMAs still run
       mbar_wait(BAR(2 * S + 1 + buf), use & 1);
       tc_fence_after();
       if (p.dbg && blockIdx.x == 0 && warp == 2 && lane == 0) p.dbg[it * 8 + 4] = clock64();
@@ -493,34 +516,6 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
             __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&packed[nch][q]);
 #pragma unroll
             for (int e = 0; e < 4; ++e) h2[e] = __floats2bfloat162_rn(f[8 * q + 2 * e], f[8 * q + 2 * e + 1]);
-          }
-          if (FUSE != 0 && nch == 0) {
-            // values as stored (bf16-rounded); rows past the end of the tensor contribute nothing.  Per-thread
-            // (row-private) partial sums stay in registers across tiles; one transposing butterfly per CTA at the end.
-#pragma unroll
-            for (int j = 0; j < 32; ++j) f[j] = valid ? __bfloat162float(__float2bfloat16(f[j])) : 0.f;
-            if (FUSE == 1) {
-#pragma unroll
-              for (int j = 0; j < 32; ++j) { accA[j] += f[j]; accB[j] = fmaf(f[j], f[j], accB[j]); }
-            } else {
-              // g = dy * act'(xhat*gamma + beta), accumulate sum(g) and sum(g*xhat) per channel
-#pragma unroll
-              for (int q = 0; q < 4; ++q) {
-                const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&xu[q]);
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                  const float2 t = __bfloat1622float2(h2[e]);
-#pragma unroll
-                  for (int w = 0; w < 2; ++w) {
-                    const int j = 8 * q + 2 * e + w, c = c0 + j;
-                    const float xhat = ((w ? t.y : t.x) - sbn[c]) * sbn[64 + c];
-                    const float g = f[j] * act_bwd_t<true>(xhat * sbn[128 + c] + sbn[192 + c], p.bnb_act);
-                    accA[j] += g;
-                    accB[j] = fmaf(g, xhat, accB[j]);
-                  }
-                }
-              }
-            }
           }
         }
         tc_fence_before();
@@ -560,6 +555,37 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
           }
           asm volatile("cp.async.bulk.commit_group;" ::: "memory");
         }
+        if (FUSE != 0) {
+          // second pass over the staged tile (values as stored, bf16-rounded); the TMA store only reads it concurrently
+          const int nrows = p.halo ? 128 : (int)min((long long)128, p.M_total - (long long)tile * TC_BM);   // rows past the end contribute nothing
+          const bool elu = p.bnb_act == ACT_ELU;                     // the model's default: branch-free fast path
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const int r = ew * 16 + i;
+            const bool rv = r < nrows;
+            const uint32_t u = *reinterpret_cast<const uint32_t*>(sOut + r * 128 + ((((lane >> 2) ^ (r & 7))) << 4) + (lane & 3) * 4);
+            const float y0 = rv ? __uint_as_float(u << 16) : 0.f, y1 = rv ? __uint_as_float(u & 0xFFFF0000u) : 0.f;
+            if (FUSE == 1) {
+              ra0 += y0; ra1 += y1;
+              rb0 = fmaf(y0, y0, rb0); rb1 = fmaf(y1, y1, rb1);
+            } else {
+              // g = dy * act'(xhat * gamma + beta); accumulate sum(g) and sum(g * xhat) per channel
+              const float x0 = __uint_as_float(xq[i] << 16), x1 = __uint_as_float(xq[i] & 0xFFFF0000u);
+              const float h0 = fmaf(x0, kx0, kb0), h1 = fmaf(x1, kx1, kb1);
+              const float t0 = fmaf(x0, kg0, kc0), t1 = fmaf(x1, kg1, kc1);
+              float g0, g1;
+              if (elu) {                                             // ELU' = 1 (t > 0) or exp(t)
+                g0 = y0 * (t0 > 0.f ? 1.f : ex2_approx(t0 * 1.4426950408889634f));
+                g1 = y1 * (t1 > 0.f ? 1.f : ex2_approx(t1 * 1.4426950408889634f));
+              } else {
+                g0 = y0 * act_bwd_t<true>(t0, p.bnb_act);
+                g1 = y1 * act_bwd_t<true>(t1, p.bnb_act);
+              }
+              ra0 += g0; ra1 += g1;
+              rb0 = fmaf(g0, h0, rb0); rb1 = fmaf(g1, h1, rb1);
+            }
+          }
+        }
         if (p.dbg && blockIdx.x == 0 && warp == 2 && lane == 0) p.dbg[it * 8 + 5] = clock64();
         continue;
       }
@@ -592,24 +618,19 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
       if (lane == 0) mbar_arrive(BAR(2 * S + 3 + buf));
     }
     if (FUSE != 0) {
-      // combine the four lane quadrants (rows) per channel, one double atomic per channel and statistic per CTA
-      const int e = warp - 2;                                      // 0..7 = half * 4 + quad-order
-      warp_transpose_sum32(accA, lane);                            // accA[0] = sum over this warp's 32 rows of channel 32*half + lane
-      warp_transpose_sum32(accB, lane);
-      const bool is_stats = FUSE == 1;
-      sred[(0 * 8 + e) * 32 + lane] = is_stats ? accA[0] : 0.f;
-      sred[(1 * 8 + e) * 32 + lane] = is_stats ? accB[0] : 0.f;
-      sred[(2 * 8 + e) * 32 + lane] = is_stats ? 0.f : accA[0];
-      sred[(3 * 8 + e) * 32 + lane] = is_stats ? 0.f : accB[0];
+      // combine the eight row groups per channel: one double atomic per channel and statistic per CTA
+      sred[(0 * 8 + ew) * 64 + 2 * lane] = ra0; sred[(0 * 8 + ew) * 64 + 2 * lane + 1] = ra1;
+      sred[(1 * 8 + ew) * 64 + 2 * lane] = rb0; sred[(1 * 8 + ew) * 64 + 2 * lane + 1] = rb1;
       asm volatile("bar.sync 1, 256;" ::: "memory");
-      const int t = threadIdx.x - 64;                              // 0..255 -> (statistic, channel)
-      const int st = t >> 6, c = t & 63, hf = c >> 5, l = c & 31;
-      float sum = 0.f;
+      const int t = threadIdx.x - 64;                              // 0..127 -> (statistic, channel)
+      if (t < 128) {
+        const int st = t >> 6, c = t & 63;
+        float sum = 0.f;
 #pragma unroll
-      for (int qd = 0; qd < 4; ++qd) sum += sred[(st * 8 + hf * 4 + qd) * 32 + l];
-      const int stripe = (blockIdx.x & 7) * 128;                  // 8-way striped accumulators (see elementwise.cu)
-      if (st < 2) { if (p.stats_acc) atomicAdd(p.stats_acc + stripe + (st == 0 ? c : 64 + c), (double)sum); }
-      else if (p.bnb_acc) atomicAdd(p.bnb_acc + stripe + (st == 2 ? c : 64 + c), (double)sum);
+        for (int e = 0; e < 8; ++e) sum += sred[(st * 8 + e) * 64 + c];
+        double* acc = (FUSE == 1 ? p.stats_acc : p.bnb_acc) + (blockIdx.x & 7) * 128;   // 8-way striped (see elementwise.cu)
+        atomicAdd(acc + st * 64 + c, (double)sum);
+      }
     }
   }
   if (p.tma_store && threadIdx.x == 64) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");

@@ -115,7 +115,7 @@ __global__ void __launch_bounds__(WG_THREADS_TC, 1)
 wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmX2,
                 const __grid_constant__ CUtensorMap tmDY, const __grid_constant__ CUtensorMap tmGp, const WgParams p) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // keeps the shared address space
   uint8_t* sPair = smem;                                                   // WG_PAIR_SLOTS x 32 KB
   uint8_t* sB = sPair + WG_PAIR_SLOTS * 2 * WG_BLK_BYTES;                  // WG_B_SLOTS x n_bblk x 16 KB
   // halo mode re-uses the same region as WG_HALO_STAGES x (36 KB halo tile + 16 KB dY tile); the ones tile sits above both
@@ -335,7 +335,7 @@ struct UnpackDesc {
 };
 static_assert(sizeof(UnpackDesc) == 80, "UnpackDesc layout is mirrored by engine.py");
 
-constexpr int UNPACK_CO = 4;          // output channels per CTA: each writes 4 contiguous (I_real * taps) runs of dw
+constexpr int UNPACK_CO = 16;         // output channels per CTA (64-byte segments of Gp rows); each writes 16 contiguous (I_real * taps) runs of dw
 
 // A CTA gathers Gp[*][co0..co0+3] for every (tap, ci) into shared memory laid out like dw, then adds contiguous runs.
 // With clear != 0 it also zeroes what it consumed, so Gp is ready for the next step.
@@ -344,21 +344,25 @@ __device__ __forceinline__ void unpack_body(const UnpackDesc& d, float (*tile)[9
   if (co0 >= d.N_real) return;
   const int run = d.I_real * d.taps;                       // floats per output channel in dw
   float* gp = const_cast<float*>(d.gp);
-  for (int i = threadIdx.x; i < d.n_pairs * 128; i += blockDim.x) {
+  for (int idx = threadIdx.x; idx < d.n_pairs * 128 * (UNPACK_CO / 4); idx += blockDim.x) {
+    const int i = idx / (UNPACK_CO / 4), part = idx % (UNPACK_CO / 4);          // Gp row, float4 within the 64-byte segment
     const int blk = i >> 6, ci = i & 63;
     const int kind = d.kind[blk];
-    float4 v = *reinterpret_cast<const float4*>(gp + (size_t)i * d.N + co0);
-    if (d.clear) *reinterpret_cast<float4*>(gp + (size_t)i * d.N + co0) = make_float4(0.f, 0.f, 0.f, 0.f);
+    float* src = gp + (size_t)i * d.N + co0 + 4 * part;
+    const float4 v = *reinterpret_cast<const float4*>(src);
+    if (d.clear) *reinterpret_cast<float4*>(src) = make_float4(0.f, 0.f, 0.f, 0.f);
+    const float vv[4] = {v.x, v.y, v.z, v.w};
     if (kind == 0) {
       const int cin = d.ci0_blk[blk] * 64 + ci;
       if (cin < d.I_real) {
         const int o = cin * d.taps + d.tap[blk];
-        tile[0][o] = v.x; tile[1][o] = v.y; tile[2][o] = v.z; tile[3][o] = v.w;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) tile[4 * part + e][o] = vv[e];
       }
     } else if (kind == 1 && ci == 0 && d.dbias) {
-      const float vv[4] = {v.x, v.y, v.z, v.w};
-      for (int j = 0; j < UNPACK_CO; ++j)
-        if (co0 + j < d.N_real) d.dbias[co0 + j] += vv[j];
+#pragma unroll
+      for (int e = 0; e < 4; ++e)
+        if (co0 + 4 * part + e < d.N_real) d.dbias[co0 + 4 * part + e] += vv[e];
     }
   }
   __syncthreads();
@@ -369,7 +373,7 @@ __device__ __forceinline__ void unpack_body(const UnpackDesc& d, float (*tile)[9
   }
 }
 
-// grid (ceil(max N_real / 4), n_desc): one descriptor of the device table per blockIdx.y
+// grid (ceil(max N_real / 16), n_desc): one descriptor of the device table per blockIdx.y
 __global__ void __launch_bounds__(256) wgrad_unpack_kernel(const UnpackDesc* __restrict__ table) {
   pdl_wait();
   pdl_launch();

@@ -12,6 +12,8 @@ from lvae_b200 import _capi, ops  # noqa: E402
 B, C = 256, 64
 one = len(sys.argv) > 1 and sys.argv[1] == "--one"
 wgrad = "--wgrad" in sys.argv
+fuse_mode = 2 if "--bnb" in sys.argv else (1 if "--stats" in sys.argv else 0)   # fused epilogue reductions (N = 64 only)
+import ctypes  # noqa: E402
 shapes = [(int(os.environ.get("HW", "16")), 3, 64)] if one else [(32, 3, 64), (16, 3, 64), (8, 3, 64), (4, 3, 64), (16, 1, 128)] if "--wgrad" in sys.argv else [(32, 3, 64), (16, 3, 64), (8, 3, 64), (4, 3, 64), (2, 3, 64), (16, 1, 128), (32, 3, 100)]
 s = torch.cuda.current_stream()
 for HW, k, N in shapes:
@@ -31,9 +33,26 @@ for HW, k, N in shapes:
         _capi.call("lvae_conv2d_wgrad_tc", xs[i % nbuf].data_ptr(), None, ys[i % nbuf].data_ptr(), dw.data_ptr(), db.data_ptr(),
                    ws.data_ptr(), B, HW, HW, N, k, 0, 0, 0, 0, torch.cuda.current_stream().cuda_stream)
 
+    acc = torch.zeros(8, 2, 64, dtype=torch.float64, device="cuda")
+    save = torch.cat([torch.zeros(64), torch.ones(64)]).cuda()
+    gamma, beta = torch.ones(64, device="cuda"), torch.zeros(64, device="cuda")
+    fz = _capi.ConvFuse()
+    if fuse_mode == 1:
+        fz.stats_acc = acc.data_ptr()
+    elif fuse_mode == 2:
+        fz.bnb_save, fz.bnb_gamma, fz.bnb_beta, fz.bnb_acc, fz.bnb_act = save.data_ptr(), gamma.data_ptr(), beta.data_ptr(), acc.data_ptr(), 3
+
+    def launch_fused(i):
+        if fuse_mode == 2:
+            fz.bnb_x = xs[(i + 1) % nbuf].data_ptr()
+        _capi.call("lvae_conv2d_tc_ex", xs[i % nbuf].data_ptr(), None, wp.data_ptr(), bias.data_ptr(), None, None,
+                   ys[i % nbuf].data_ptr(), None, 0, B, HW, HW, C, N, k, 0, 0, ctypes.addressof(fz), torch.cuda.current_stream().cuda_stream)
+
     def launch(i):
         if wgrad:
             return launch_wgrad(i)
+        if fuse_mode and N == 64:
+            return launch_fused(i)
         _capi.call("lvae_conv2d_tc", xs[i % nbuf].data_ptr(), None, wp.data_ptr(), bias.data_ptr(), None, None,
                    ys[i % nbuf].data_ptr(), None, 0, B, HW, HW, C, N, k, 0, 0, torch.cuda.current_stream().cuda_stream)
     launch(0)
