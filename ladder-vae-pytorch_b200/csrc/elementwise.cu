@@ -38,6 +38,29 @@ template <> __device__ __forceinline__ void stv<__nv_bfloat16, 8>(__nv_bfloat16*
   for (int j = 0; j < 4; ++j) h[j] = __floats2bfloat162_rn(f[2 * j], f[2 * j + 1]);
   *reinterpret_cast<uint4*>(p) = u;
 }
+
+// Raw (unconverted) vector loads: a kernel issues them BEFORE its prologue (statistics tables, barriers) and converts
+// after it, so the first global round trip overlaps the prologue; inside the loop the next iteration's loads are in
+// flight while the current one computes.
+template <typename T, int V> struct RawV;
+template <> struct RawV<float, 4> { float4 v; };
+template <> struct RawV<__nv_bfloat16, 4> { uint2 v; };
+template <> struct RawV<__nv_bfloat16, 8> { uint4 v; };
+template <typename T, int V> __device__ __forceinline__ RawV<T, V> ldraw(const T* p) {
+  RawV<T, V> r;
+  r.v = *reinterpret_cast<const decltype(r.v)*>(p);
+  return r;
+}
+__device__ __forceinline__ void unraw(const RawV<float, 4>& r, float* f) { f[0] = r.v.x; f[1] = r.v.y; f[2] = r.v.z; f[3] = r.v.w; }
+__device__ __forceinline__ void unraw(const RawV<__nv_bfloat16, 4>& r, float* f) {
+  f[0] = __uint_as_float(r.v.x << 16); f[1] = __uint_as_float(r.v.x & 0xFFFF0000u);
+  f[2] = __uint_as_float(r.v.y << 16); f[3] = __uint_as_float(r.v.y & 0xFFFF0000u);
+}
+__device__ __forceinline__ void unraw(const RawV<__nv_bfloat16, 8>& r, float* f) {
+  const uint32_t w[4] = {r.v.x, r.v.y, r.v.z, r.v.w};
+#pragma unroll
+  for (int j = 0; j < 4; ++j) { f[2 * j] = __uint_as_float(w[j] << 16); f[2 * j + 1] = __uint_as_float(w[j] & 0xFFFF0000u); }
+}
 template <typename T> __device__ __forceinline__ float round_to(float v);
 template <> __device__ __forceinline__ float round_to<float>(float v) { return v; }
 template <> __device__ __forceinline__ float round_to<__nv_bfloat16>(float v) { return __bfloat162float(__float2bfloat16(v)); }
@@ -711,6 +734,11 @@ __global__ void bn_act_fwd2_kernel(const TI* __restrict__ x, TO* __restrict__ y,
   pdl_launch();
   __shared__ __align__(16) float s_scale[256], s_shift[256];       // y = act(x * scale + shift), C <= 256
   const int CV = C / V;
+  const long long stride = (long long)gridDim.x * blockDim.x;      // multiple of CV by construction
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  bool has = i < nvec;
+  RawV<TI, V> rx;
+  if (has) rx = ldraw<TI, V>(x + i * V);                           // in flight during the statistics prologue
   // one thread per channel derives the statistics (the only double-precision math in the kernel)
   for (int ch = threadIdx.x; ch < C; ch += blockDim.x) {
     float mean, rstd;
@@ -739,23 +767,26 @@ __global__ void bn_act_fwd2_kernel(const TI* __restrict__ x, TO* __restrict__ y,
   }
   if (blockIdx.x == 0 && threadIdx.x == 0 && training && nbt) *nbt += 1;
   __syncthreads();
-  const long long stride = (long long)gridDim.x * blockDim.x;      // multiple of CV by construction
-  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const int c = (int)(i % CV) * V;
   float sc[V], sh[V];
 #pragma unroll
   for (int j = 0; j < V; ++j) { sc[j] = s_scale[c + j]; sh[j] = s_shift[c + j]; }
-  for (; i < nvec; i += stride) {
+  while (has) {
     float v[V];
-    ldv<TI, V>(x + i * V, v);
+    unraw(rx, v);
+    const long long inext = i + stride;
+    const bool hn = inext < nvec;
+    if (hn) rx = ldraw<TI, V>(x + inext * V);
 #pragma unroll
     for (int j = 0; j < V; ++j) v[j] = act_fwd_t<sizeof(TO) == 2>(v[j] * sc[j] + sh[j], act);
     stv<TO, V>(y + i * V, v);
+    i = inext;
+    has = hn;
   }
 }
 
 template <typename T, int V>
-__global__ void bn_act_bwd2_kernel(const T* __restrict__ dy, const T* __restrict__ x, T* __restrict__ dx,
+__global__ void __launch_bounds__(256, 3) bn_act_bwd2_kernel(const T* __restrict__ dy, const T* __restrict__ x, T* __restrict__ dx,
                                    const float* __restrict__ save, const float* __restrict__ gamma,
                                    const float* __restrict__ beta, const double* __restrict__ acc,
                                    float* dgamma, float* dbeta, const float* __restrict__ post_scale,
@@ -763,52 +794,72 @@ __global__ void bn_act_bwd2_kernel(const T* __restrict__ dy, const T* __restrict
                                    int training) {
   pdl_wait();
   pdl_launch();
-  __shared__ float s_m1[256], s_m2[256];
+  // per-channel constants live in shared memory (two float4 per channel), not in 6 x V registers per thread
+  __shared__ __align__(16) float s_t[6][256];                     // mean, rstd, gamma, beta, m1, m2 (SoA: conflict-free V-wide reads)
   const int CV = C / V;
   const long long stride = (long long)gridDim.x * blockDim.x;
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const int c = (int)(i % CV) * V;
+  bool has = i < nvec;
+  RawV<T, V> rx, rd, ra;
+  if (has) {                                                       // in flight during the prologue
+    rx = ldraw<T, V>(x + i * V);
+    rd = ldraw<T, V>(dy + i * V);
+    if (add) ra = ldraw<T, V>(add + i * V);
+  }
   const double invP = 1.0 / (double)P;
   for (int ch = threadIdx.x; ch < C; ch += blockDim.x) {
     const double a1 = acc_sum(acc, ch, C), a2 = acc_sum(acc, C + ch, C);
-    s_m1[ch] = (float)(a1 * invP);
-    s_m2[ch] = (float)(a2 * invP);
+    const float mean = save[ch], rstd = save[C + ch], gm = gamma[ch];
+    s_t[0][ch] = mean; s_t[1][ch] = rstd; s_t[2][ch] = gm; s_t[3][ch] = beta[ch];
+    s_t[4][ch] = training ? (float)(a1 * invP) : 0.f;
+    s_t[5][ch] = training ? (float)(a2 * invP) : 0.f;
     if (blockIdx.x == 0) {
       if (dbeta) dbeta[ch] += (float)a1;
       if (dgamma) dgamma[ch] += (float)a2;
     }
   }
   __syncthreads();
-  float m[V], r[V], g[V], b[V], m1[V], m2[V];
+  while (has) {
+    float xs[V], ds[V], av[V], o[V];
+    unraw(rx, xs);
+    unraw(rd, ds);
+    if (add) unraw(ra, av);
+    const long long inext = i + stride;
+    const bool hn = inext < nvec;
+    if (hn) {
+      rx = ldraw<T, V>(x + inext * V);
+      rd = ldraw<T, V>(dy + inext * V);
+      if (add) ra = ldraw<T, V>(add + inext * V);
+    }
+    int cc = c;
+    asm volatile("" : "+r"(cc));                                  // keep the table reads inside the loop (not hoisted into 6 x V registers)
 #pragma unroll
-  for (int j = 0; j < V; ++j) {
-    m[j] = save[c + j]; r[j] = save[C + c + j]; g[j] = gamma[c + j]; b[j] = beta[c + j];
-    m1[j] = s_m1[c + j];
-    m2[j] = s_m2[c + j];
-  }
-  for (; i < nvec; i += stride) {
-    float xs[V], ds[V], o[V];
-    ldv<T, V>(x + i * V, xs);
-    ldv<T, V>(dy + i * V, ds);
+    for (int q = 0; q < V / 4; ++q) {                              // four channels at a time: 6 LDS.128, 24 live constants
+      float tb[6][4];
 #pragma unroll
-    for (int j = 0; j < V; ++j) {
-      float xh = (xs[j] - m[j]) * r[j];
-      float gpre = ds[j] * act_bwd_t<sizeof(T) == 2>(xh * g[j] + b[j], act);
-      o[j] = training ? g[j] * r[j] * (gpre - m1[j] - xh * m2[j]) : g[j] * r[j] * gpre;
+      for (int k = 0; k < 6; ++k) *reinterpret_cast<float4*>(&tb[k][0]) = *reinterpret_cast<const float4*>(&s_t[k][cc + 4 * q]);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int j = 4 * q + e;
+        const float xh = (xs[j] - tb[0][e]) * tb[1][e];
+        const float gpre = ds[j] * act_bwd_t<sizeof(T) == 2>(fmaf(xh, tb[2][e], tb[3][e]), act);
+        o[j] = tb[2][e] * tb[1][e] * (gpre - tb[4][e] - xh * tb[5][e]);
+      }
     }
     if (post_scale) {
-      long long bidx = (i / CV) / hw;
-      const float* ps = post_scale + bidx * C + c;
+      const unsigned bidx = (unsigned)(i / CV) / (unsigned)hw;      // pixel and image indices fit 32 bits
+      const float* ps = post_scale + (size_t)bidx * C + c;
 #pragma unroll
       for (int j = 0; j < V; ++j) o[j] *= ps[j];
     }
     if (add) {
-      float a[V];
-      ldv<T, V>(add + i * V, a);
 #pragma unroll
-      for (int j = 0; j < V; ++j) o[j] += a[j];
+      for (int j = 0; j < V; ++j) o[j] += av[j];
     }
     stv<T, V>(dx + i * V, o);
+    i = inext;
+    has = hn;
   }
 }
 
