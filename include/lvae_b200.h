@@ -93,6 +93,12 @@ typedef struct {
   const float* bnb_beta;
   double* bnb_acc;
   int bnb_act;
+  /* gated residual (lib/nn.py:121-126 GateLayer2d + the residual add of :99) in the epilogue of its 1x1 conv (N = 128):
+   * gate_out (M,64) bf16 = act(h[:, :64]) * sigmoid(h[:, 64:]) + gate_x; h itself still goes to y (saved for backward);
+   * stats_acc, when set, then accumulates the statistics of gate_out (the next block's first BatchNorm) */
+  const void* gate_x;
+  void* gate_out;
+  int gate_act;
 } LvaeConvFuse;
 int lvae_conv2d_tc_ex(const void* x, const void* x2, const void* wp, const float* bias, const float* out_scale,
                       const void* res, void* y, void* y2, int nsplit, int B, int H, int W, int Cin, int N, int ksize,

@@ -51,6 +51,10 @@ struct TcParams {
   const float* bnb_save; const float* bnb_gamma; const float* bnb_beta;
   double* bnb_acc;          // += sum(g), sum(g * xhat), g = dy * act'(xhat*gamma+beta)
   int bnb_act;
+  // gated-residual epilogue (1x1 gate conv, N == 128): out = act(h[:, :64]) * sigmoid(h[:, 64:]) + gate_x, stored through tmY2;
+  // stats_acc (optional) then accumulates the statistics of out
+  const __nv_bfloat16* gate_x;
+  int gate_act;
   int tma_store;            // bf16 output, N % 64 == 0, no residual: epilogue stages the tile in smem and stores it with TMA
   long long* dbg;           // optional per-tile clock64 trace of CTA 0 (profiling aid, normally null)
   int8_t dx[TC_MAX_KB], dy[TC_MAX_KB], src[TC_MAX_KB], coff[TC_MAX_KB];   // coff: channel offset / 64 inside the tensor
@@ -261,7 +265,8 @@ __device__ __forceinline__ void epilogue16(const uint32_t* __restrict__ r, const
   }
 }
 
-// FUSE: 0 plain epilogue, 1 output statistics (stats_acc), 2 BatchNorm-backward sums (bnb_*).  A template parameter so
+// FUSE: 0 plain epilogue, 1 output statistics (stats_acc), 2 BatchNorm-backward sums (bnb_*), 3 gated residual output
+// (+ its statistics).  A template parameter so
 // that the plain kernel carries no accumulator registers (the 10-warp CTA caps ptxas at 168 registers per thread).
 template <int FUSE>
 __global__ void __launch_bounds__(TC_THREADS, 1)
@@ -277,7 +282,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
   uint8_t* sA = sW + ((p.n_kb * wbytes_kb + 1023) & ~1023);  // n_stages * 16 KB
   const int stage_bytes = p.halo ? p.stage_bytes : TC_STAGE_BYTES;
   uint8_t* sOut = sA + p.n_stages * stage_bytes;             // (N/64) x 16 KB output staging (TMA-store epilogue only)
-  uint64_t* bars = (uint64_t*)(sOut + (p.tma_store ? (p.Npad / 64) * TC_STAGE_BYTES : 0));
+  uint64_t* bars = (uint64_t*)(sOut + (p.tma_store ? (p.Npad / 64 + (FUSE == 3 ? 1 : 0)) * TC_STAGE_BYTES : 0));
   // barrier layout: [0..S) full, [S..2S) empty, 2S: weights, 2S+1..2S+2: tmem_full[2], 2S+3..2S+4: tmem_empty[2]
   const int S = p.n_stages;
   uint32_t* tmem_slot = (uint32_t*)(bars + 2 * S + 5);
@@ -459,11 +464,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
       return (long long)tile * TC_BM + ew * 16;
     };
     const int rstep = p.halo ? p.W - 8 : 0;                        // extra pixels skipped after 8 rows of the staged tile
-    uint32_t xq[FUSE == 2 ? 16 : 1];                               // BatchNorm input of this tile (channels 2l, 2l+1)
+    uint32_t xq[FUSE >= 2 ? 16 : 1];                               // BatchNorm input / residual input of this tile (channels 2l, 2l+1)
     auto load_xq = [&](long long rb) {
-      const uint32_t* xb = reinterpret_cast<const uint32_t*>(p.bnb_x + rb * 64) + lane;
+      const uint32_t* xb = reinterpret_cast<const uint32_t*>((FUSE == 3 ? p.gate_x : p.bnb_x) + rb * 64) + lane;
 #pragma unroll
-      for (int i = 0; i < (FUSE == 2 ? 16 : 1); ++i) {
+      for (int i = 0; i < (FUSE >= 2 ? 16 : 1); ++i) {
         const int off = i + (i >> 3) * rstep;
         xq[i] = rb + off < p.M_total ? __ldg(xb + off * 32) : 0u;
       }
@@ -491,7 +496,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
       const float* scale_row = p.out_scale ? p.out_scale + (long long)b * p.N : nullptr;
       if (FUSE != 0 || p.tma_store) {
         // ---- TMEM -> registers (bias, Dropout2d scale, bf16 pack), release the accumulator, stage in smem, TMA store ----
-        constexpr int NCH = FUSE ? 1 : 2;                           // fused reductions: N = 64, one chunk per thread
+        constexpr int NCH = (FUSE == 1 || FUSE == 2) ? 1 : 2;       // fused reductions: N = 64, one chunk per thread
         uint4 packed[NCH][4];
 #pragma unroll
         for (int nch = 0; nch < NCH; ++nch) {                      // N <= 128 on this path: at most two chunks per thread
@@ -521,6 +526,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(BAR(2 * S + 3 + buf));          // accumulator free again: next-but-one tile may start
+        if (FUSE == 3) load_xq(rbase);                               // residual input rows (in flight across the staging barriers)
         // the previous tile's TMA store must have finished reading the staging buffer
         if (threadIdx.x == 64) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
         asm volatile("bar.sync 1, 256;" ::: "memory");
@@ -555,7 +561,48 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
           }
           asm volatile("cp.async.bulk.commit_group;" ::: "memory");
         }
-        if (FUSE != 0) {
+        if (FUSE == 3) {
+          // gate pass over the staged h tile (a = block 0, gate = block 1; values as stored): out -> third staging block
+          const int nrows = p.halo ? 128 : (int)min((long long)128, p.M_total - (long long)tile * TC_BM);
+          uint8_t* sGate = sOut + 2 * TC_STAGE_BYTES;
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const int r = ew * 16 + i;
+            const int pos = r * 128 + ((((lane >> 2) ^ (r & 7))) << 4) + (lane & 3) * 4;
+            const uint32_t ua = *reinterpret_cast<const uint32_t*>(sOut + pos);
+            const uint32_t ug = *reinterpret_cast<const uint32_t*>(sOut + TC_STAGE_BYTES + pos);
+            const float a0 = __uint_as_float(ua << 16), a1 = __uint_as_float(ua & 0xFFFF0000u);
+            const float s0 = __uint_as_float(ug << 16), s1 = __uint_as_float(ug & 0xFFFF0000u);
+            const float x0 = __uint_as_float(xq[i] << 16), x1 = __uint_as_float(xq[i] & 0xFFFF0000u);
+            const float o0 = fmaf(act_fwd_t<true>(a0, p.gate_act), sigmoid_t<true>(s0), x0);
+            const float o1 = fmaf(act_fwd_t<true>(a1, p.gate_act), sigmoid_t<true>(s1), x1);
+            const __nv_bfloat162 ob = __floats2bfloat162_rn(o0, o1);
+            const uint32_t uo = *reinterpret_cast<const uint32_t*>(&ob);
+            *reinterpret_cast<uint32_t*>(sGate + pos) = uo;
+            if (r < nrows) {                                          // statistics of the output as stored
+              const float q0 = __uint_as_float(uo << 16), q1 = __uint_as_float(uo & 0xFFFF0000u);
+              ra0 += q0; ra1 += q1;
+              rb0 = fmaf(q0, q0, rb0); rb1 = fmaf(q1, q1, rb1);
+            }
+          }
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          asm volatile("bar.sync 1, 256;" ::: "memory");
+          if (threadIdx.x == 64) {
+            int c1, c2, c3;
+            if (p.halo) {
+              int n0 = tile / p.tiles_per_img;
+              int r2 = tile - n0 * p.tiles_per_img;
+              c3 = n0; c2 = (r2 / p.tiles_x) * 16; c1 = (r2 % p.tiles_x) * 8;
+            } else {
+              int p0 = tile * TC_BM;
+              c3 = p0 / hw;
+              int rem = p0 - c3 * hw;
+              c2 = rem / p.W; c1 = rem - c2 * p.W;
+            }
+            tma_store_4d(&tmY2, smem_u32(sGate), 0, c1, c2, c3);
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+          }
+        } else if (FUSE != 0) {
           // second pass over the staged tile (values as stored, bf16-rounded); the TMA store only reads it concurrently
           const int nrows = p.halo ? 128 : (int)min((long long)128, p.M_total - (long long)tile * TC_BM);   // rows past the end contribute nothing
           const bool elu = p.bnb_act == ACT_ELU;                     // the model's default: branch-free fast path
@@ -628,8 +675,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         float sum = 0.f;
 #pragma unroll
         for (int e = 0; e < 8; ++e) sum += sred[(st * 8 + e) * 64 + c];
-        double* acc = (FUSE == 1 ? p.stats_acc : p.bnb_acc) + (blockIdx.x & 7) * 128;   // 8-way striped (see elementwise.cu)
-        atomicAdd(acc + st * 64 + c, (double)sum);
+        double* acc = (FUSE == 2 ? p.bnb_acc : p.stats_acc);
+        if (acc) atomicAdd(acc + (blockIdx.x & 7) * 128 + st * 64 + c, (double)sum);   // 8-way striped (see elementwise.cu)
       }
     }
   }
@@ -678,6 +725,9 @@ struct LvaeConvFuse {
   const float* bnb_beta;
   double* bnb_acc;
   int bnb_act;
+  const void* gate_x;
+  void* gate_out;
+  int gate_act;
 };
 
 LVAE_API int lvae_conv2d_tc_ex(const void* x, const void* x2, const void* wp, const float* bias, const float* out_scale,
@@ -718,6 +768,11 @@ LVAE_API int lvae_conv2d_tc_ex(const void* x, const void* x2, const void* wp, co
     p.bnb_beta = fuse->bnb_beta; p.bnb_acc = fuse->bnb_acc; p.bnb_act = fuse->bnb_act;
     LVAE_REQUIRE(!p.bnb_acc || (p.bnb_x && p.bnb_save && p.bnb_gamma && p.bnb_beta), "conv2d_tc: incomplete BatchNorm-backward fusion arguments");
     LVAE_REQUIRE(!(p.bnb_acc && p.stats_acc), "conv2d_tc: output statistics and BatchNorm-backward sums cannot be fused into the same launch");
+    if (fuse->gate_out) {
+      LVAE_REQUIRE(fuse->gate_x && N == 128 && !y2 && !res && !out_f32 && !p.bnb_acc,
+                   "conv2d_tc: the gated-residual epilogue needs N == 128, bf16 output, no residual / split");
+      p.gate_x = (const __nv_bfloat16*)fuse->gate_x; p.gate_act = fuse->gate_act;
+    }
   }
   const int inputs = x2 ? 2 : 1;
   const int taps = ksize * ksize;
@@ -752,8 +807,9 @@ LVAE_API int lvae_conv2d_tc_ex(const void* x, const void* x2, const void* wp, co
   static int tst_env = -1;
   if (tst_env < 0) { const char* e = getenv("LVAE_CONV_TMA_STORE"); tst_env = e ? atoi(e) : 1; }
   p.tma_store = (tst_env && !out_f32 && N % 64 == 0 && N <= 128 && !res && (!y2 || nsplit % 64 == 0)) ? 1 : 0;
-  const int out_stage = p.tma_store ? (p.Npad / 64) * TC_STAGE_BYTES : 0;
-  LVAE_REQUIRE(!(p.stats_acc || p.bnb_acc) || (p.tma_store && N == 64 && !y2),
+  const int out_stage = p.tma_store ? (p.Npad / 64 + (p.gate_x ? 1 : 0)) * TC_STAGE_BYTES : 0;
+  LVAE_REQUIRE(!p.gate_x || p.tma_store, "conv2d_tc: the gated-residual epilogue needs the TMA-store path");
+  LVAE_REQUIRE(!(p.stats_acc || p.bnb_acc) || (p.tma_store && (N == 64 || p.gate_x) && !y2),
                "conv2d_tc: fused reductions need the TMA-store path (bf16 output, N == 64, no residual, no split)");
   p.halo = (halo_env && ksize == 3 && !x2 && Cin == 64 && W % 8 == 0 && H % 16 == 0 &&
             (max_smem - wbytes - out_stage) / (18 * 16 * 128) >= 2) ? 1 : 0;
@@ -772,14 +828,15 @@ LVAE_API int lvae_conv2d_tc_ex(const void* x, const void* x2, const void* wp, co
   memset(&tmY2, 0, sizeof(tmY2));
   if (p.tma_store) {
     // output maps: same pixel box as the activation tiles (8 x 16 pixels in halo mode), 64 channels per box
-    for (int which = 0; which < (y2 ? 2 : 1); ++which) {
-      const int ncols = y2 ? (which ? N - nsplit : nsplit) : N;
+    void* const gate_out = (fuse && fuse->gate_out) ? fuse->gate_out : nullptr;
+    for (int which = 0; which < ((y2 || gate_out) ? 2 : 1); ++which) {
+      const int ncols = gate_out ? (which ? 64 : N) : (y2 ? (which ? N - nsplit : nsplit) : N);
       cuuint64_t gdim[4] = {(cuuint64_t)ncols, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
       cuuint64_t gstr[3] = {(cuuint64_t)ncols * 2, (cuuint64_t)W * ncols * 2, (cuuint64_t)H * W * ncols * 2};
       cuuint32_t box[4] = {64, (cuuint32_t)p.bw, (cuuint32_t)p.bh, (cuuint32_t)p.bn};
       if (p.halo) { box[1] = 8; box[2] = 16; box[3] = 1; }
       cuuint32_t estr[4] = {1, 1, 1, 1};
-      CUresult r = enc(which ? &tmY2 : &tmY, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, which ? y2 : y, gdim, gstr, box, estr,
+      CUresult r = enc(which ? &tmY2 : &tmY, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, which ? (gate_out ? gate_out : y2) : y, gdim, gstr, box, estr,
                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
       if (r != CUDA_SUCCESS) { lvae_set_error("conv2d_tc: tensor map (y) encode failed: %d", (int)r); return LVAE_ERR_CUDA; }
@@ -810,12 +867,14 @@ LVAE_API int lvae_conv2d_tc_ex(const void* x, const void* x2, const void* wp, co
     cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024));
     if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024));
     if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024));
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tc_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024));
     if (e != cudaSuccess) { lvae_set_error("conv2d_tc: cannot raise dynamic smem: %s", cudaGetErrorString(e)); return LVAE_ERR_CUDA; }
     attr_smem = 227 * 1024;
   }
   const int n_tiles = p.halo ? B * p.tiles_per_img : (p.M_total + TC_BM - 1) / TC_BM;
   const int grid = n_tiles < lvae_num_sms() ? n_tiles : lvae_num_sms();
-  if (p.stats_acc) lvae_launch(conv_tc_kernel<1>, grid, TC_THREADS, smem, stream, tmA0, tmA1, tmW, tmY, tmY2, p);
+  if (p.gate_x) lvae_launch(conv_tc_kernel<3>, grid, TC_THREADS, smem, stream, tmA0, tmA1, tmW, tmY, tmY2, p);
+  else if (p.stats_acc) lvae_launch(conv_tc_kernel<1>, grid, TC_THREADS, smem, stream, tmA0, tmA1, tmW, tmY, tmY2, p);
   else if (p.bnb_acc) lvae_launch(conv_tc_kernel<2>, grid, TC_THREADS, smem, stream, tmA0, tmA1, tmW, tmY, tmY2, p);
   else lvae_launch(conv_tc_kernel<0>, grid, TC_THREADS, smem, stream, tmA0, tmA1, tmW, tmY, tmY2, p);
   LVAE_COUNT_LAUNCH();

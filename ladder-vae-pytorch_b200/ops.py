@@ -353,7 +353,7 @@ def _tc_fusable(N, out_f32, res, nsplit=0) -> bool:
     return N == 64 and not out_f32 and res is None and not nsplit
 
 
-def _conv_tc(x, x2, wp, bias, out_scale, res, N, ksize, flip, out_f32, nsplit=0, stats_acc=None, bnb=None):
+def _conv_tc(x, x2, wp, bias, out_scale, res, N, ksize, flip, out_f32, nsplit=0, stats_acc=None, bnb=None, gate=None):
     """Launch the tcgen05 kernel.  Returns y, or (y, y2) when nsplit splits the output columns.
     stats_acc: (2,64) float64 accumulator for the output's per-channel statistics; bnb = (x, save, gamma, beta, acc, act):
     BatchNorm-backward sums over the output (both fused into the epilogue)."""
@@ -365,9 +365,14 @@ def _conv_tc(x, x2, wp, bias, out_scale, res, N, ksize, flip, out_f32, nsplit=0,
     else:
         y, y2 = torch.empty((B, H, W, N), dtype=odt, device=x.device), None
     fuse = None
-    if stats_acc is not None or bnb is not None:
+    gate_out = None
+    if stats_acc is not None or bnb is not None or gate is not None:
         f = _capi.ConvFuse()
         f.stats_acc = _p(stats_acc)
+        if gate is not None:            # (residual input (B,H,W,64) bf16, activation id): gated residual output in the epilogue
+            gx, gact = gate
+            gate_out = torch.empty_like(gx)
+            f.gate_x, f.gate_out, f.gate_act = gx.data_ptr(), gate_out.data_ptr(), int(gact)
         if bnb is not None:
             bx, bsave, bgamma, bbeta, bacc, bact = bnb
             f.bnb_x, f.bnb_save, f.bnb_gamma, f.bnb_beta = bx.data_ptr(), bsave.data_ptr(), bgamma.data_ptr(), bbeta.data_ptr()
@@ -375,6 +380,8 @@ def _conv_tc(x, x2, wp, bias, out_scale, res, N, ksize, flip, out_f32, nsplit=0,
         fuse = ctypes.addressof(f)
     call("lvae_conv2d_tc_ex", x.data_ptr(), _p(x2), wp.data_ptr(), _p(bias), _p(out_scale), _p(res), y.data_ptr(), _p(y2),
          nsplit, B, H, W, C, N, ksize, 1 if flip else 0, 1 if out_f32 else 0, fuse, _stream())
+    if gate is not None:
+        return y, gate_out
     return (y, y2) if nsplit else y
 
 
@@ -603,6 +610,7 @@ def bn_act(x, bn, act_id: int, out_dtype=None):
 BN_STRIPES = 8
 _bn_epoch = [0]
 _whole_block = [True]
+_gate_fused = [os.environ.get("LVAE_GATE_FUSED", "1") != "0"]
 
 
 def set_whole_block(flag: bool) -> None:
@@ -690,15 +698,25 @@ class GatedBlockFn(Function):
             y1 = conv_forward_raw(conv1.spec, a1, None, w1, cb1, m1, None)
         a2 = bn_fwd(y1, bn2, sc2, saves[1], g2, b2, acc2)
         y2 = conv_forward_raw(conv2.spec, a2, None, w2, cb2, m2, None)
-        h = conv_forward_raw(gconv.spec, y2, None, wg, gbias, None, None)
-        out = torch.empty_like(xn)
         out_stats = None
         if training and 256 % (C // 4) == 0:
             out_stats = sc1[2]                        # statistics of this block's output, for the next block's BN1
             _bn_clean(bn1, out_stats, "out")
-            call("lvae_gate_fwd_stats", h.data_ptr(), xn.data_ptr(), out.data_ptr(), out_stats.data_ptr(), Pn, C, gact, dt, _stream())
+        gspec = gconv.spec
+        if (_gate_fused[0] and C == 64 and gspec.cout == 128 and xn.dtype == torch.bfloat16 and not gspec.out_fp32
+                and gspec.tc_forward_ok(y2, None)):
+            # gate, residual add and the output statistics ride in the epilogue of the 1x1 gate conv
+            stats["tc_fwd"] += 1
+            stats["gate_fused"] = stats.get("gate_fused", 0) + 1
+            h, out = _conv_tc(y2, None, gspec.pack_tc_fwd.get(wg, torch.bfloat16), gbias, None, None, 128, gspec.k, False, False,
+                              stats_acc=out_stats, gate=(xn, gact))
         else:
-            call("lvae_gate_fwd", h.data_ptr(), xn.data_ptr(), out.data_ptr(), Pn, C, gact, dt, _stream())
+            h = conv_forward_raw(gspec, y2, None, wg, gbias, None, None)
+            out = torch.empty_like(xn)
+            if out_stats is not None:
+                call("lvae_gate_fwd_stats", h.data_ptr(), xn.data_ptr(), out.data_ptr(), out_stats.data_ptr(), Pn, C, gact, dt, _stream())
+            else:
+                call("lvae_gate_fwd", h.data_ptr(), xn.data_ptr(), out.data_ptr(), Pn, C, gact, dt, _stream())
         ctx.save_for_backward(xn, a1, y1, a2, y2, h, saves, g1, b1, w1, cb1, g2, b2, w2, cb2, wg, gbias, m1, m2)
         ctx.blk, ctx.training = blk, training
         blk[0]._lvae_last_out_stats = (out_stats, Pn, _bn_epoch[0]) if out_stats is not None else None
