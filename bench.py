@@ -209,9 +209,16 @@ def conv_roofline(torch, pk, dtype="bf16"):
     achieved = flops / (us * 1e-6) / 1e12
     bytes_alg = 2.0 * B * H * W * C * (2 if dtype == "bf16" else 4)
     return {"bound": "tensor", "kernel": name, "achieved": achieved, "peak": pk["tf_burst"], "unit": "TFLOP/s",
-            "frac": achieved / pk["tf_burst"], "traffic": None, "us_per_launch": us, "flops_per_launch": flops,
+            "frac": achieved / pk["tf_burst"], "traffic": NCU_CONV_DRAM_BYTES if dtype == "bf16" else None,
+            "traffic_unit": "bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum, profiles/ncu_conv_tc_r01_final.txt)",
+            "us_per_launch": us, "flops_per_launch": flops,
             "algorithmic_bytes_per_launch": bytes_alg, "hbm_gbs_at_this_rate": bytes_alg / (us * 1e-6) / 1e9,
             "peak_source": "%s bf16 burst (kernel timed alone)" % pk["src"]}
+
+
+# dram__bytes_read.sum + dram__bytes_write.sum of this kernel from one `ncu --set full` capture (profiles/ncu_conv_tc_r01_final.txt):
+# 8.53 MB read (8.39 MB activations + weights), 0 written (the output is still dirty in L2 when the kernel ends)
+NCU_CONV_DRAM_BYTES = 8526336
 
 
 def main():
