@@ -18,10 +18,33 @@ struct ConvArgs {
   void* y;              // (B,Ho,Wo,N)
   int B, Hi, Wi, C1, C2, Ho, Wo, N, ldw;
   int kh, kw, stride, pad, mode;  // mode 0: iy = oy*stride - pad + ky ; mode 1: iy = (oy + pad - ky)/stride
+  // mode 1 with stride 2: output pixels are enumerated parity-class-major ((oy&1, ox&1) constant per CTA), so a CTA
+  // skips the filter taps that never meet its class (3/4 of a 3x3 kernel's work)
+  int cls;
 };
 
 constexpr int CG_BM = 128, CG_BN = 64, CG_BK = 32, CG_THREADS = 256;
 constexpr int CG_APITCH = CG_BK + 4;
+
+// output pixel (b, oy, ox) of GEMM row m
+__device__ __forceinline__ void decode_pixel(const ConvArgs& a, long long M, long long m, int& b, int& oy, int& ox) {
+  if (a.cls) {
+    const long long Mq = M >> 2;
+    const int c = (int)(m / Mq);
+    const int r = (int)(m - (long long)c * Mq);
+    const int Hq = a.Ho >> 1, Wq = a.Wo >> 1;
+    b = r / (Hq * Wq);
+    const int r2 = r - b * (Hq * Wq);
+    oy = 2 * (r2 / Wq) + (c >> 1);
+    ox = 2 * (r2 % Wq) + (c & 1);
+  } else {
+    const int hw = a.Ho * a.Wo;
+    b = (int)(m / hw);
+    const int r = (int)(m - (long long)b * hw);
+    oy = r / a.Wo;
+    ox = r - oy * a.Wo;
+  }
+}
 
 template <typename T, bool VEC>
 __global__ void __launch_bounds__(CG_THREADS) conv_gather_kernel(ConvArgs a) {
@@ -46,11 +69,7 @@ __global__ void __launch_bounds__(CG_THREADS) conv_gather_kernel(ConvArgs a) {
   for (int i = 0; i < 4; ++i) {
     long long m = m0 + (t >> 3) + 32 * i;
     if (m < M) {
-      int hw = a.Ho * a.Wo;
-      pb[i] = (int)(m / hw);
-      int r = (int)(m - (long long)pb[i] * hw);
-      py[i] = r / a.Wo;
-      px[i] = r - py[i] * a.Wo;
+      decode_pixel(a, M, m, pb[i], py[i], px[i]);
     } else {
       pb[i] = -1; py[i] = 0; px[i] = 0;
     }
@@ -148,15 +167,29 @@ __global__ void __launch_bounds__(CG_THREADS) conv_gather_kernel(ConvArgs a) {
     }
   };
 
-  load_tiles(0);
-  for (int k0 = 0; k0 < K; k0 += CG_BK) {
+  // parity-class mode: the CTA's class and the taps that can reach it
+  const int ccls = a.cls ? (int)(m0 / (M >> 2)) : 0;
+  auto next_valid = [&](int k0) {
+    if (a.cls) {
+      while (k0 < K) {
+        const int tap = k0 / Cin, ky = tap / a.kw, kx = tap - ky * a.kw;
+        if ((((ccls >> 1) + a.pad + ky) & 1) == 0 && (((ccls & 1) + a.pad + kx) & 1) == 0) break;
+        k0 += CG_BK;
+      }
+    }
+    return k0;
+  };
+  int k0 = next_valid(0);
+  if (k0 < K) load_tiles(k0);
+  while (k0 < K) {
+    const int kn = next_valid(k0 + CG_BK);
     __syncthreads();
 #pragma unroll
     for (int i = 0; i < 4; ++i) *reinterpret_cast<float4*>(&As[(t >> 3) + 32 * i][kq * 4]) = ra[i];
 #pragma unroll
     for (int i = 0; i < 2; ++i) *reinterpret_cast<float4*>(&Bs[(t >> 4) + 16 * i][bq * 4]) = rb[i];
     __syncthreads();
-    if (k0 + CG_BK < K) load_tiles(k0 + CG_BK);
+    if (kn < K) load_tiles(kn);
 #pragma unroll
     for (int k4 = 0; k4 < CG_BK; k4 += 4) {
       float4 b4[4];
@@ -171,6 +204,7 @@ __global__ void __launch_bounds__(CG_THREADS) conv_gather_kernel(ConvArgs a) {
         acc[i][0] += a4.w * b4[3].x; acc[i][1] += a4.w * b4[3].y; acc[i][2] += a4.w * b4[3].z; acc[i][3] += a4.w * b4[3].w;
       }
     }
+    k0 = kn;
   }
 
   // --- epilogue: (acc + bias) * out_scale + res ---
@@ -178,7 +212,6 @@ __global__ void __launch_bounds__(CG_THREADS) conv_gather_kernel(ConvArgs a) {
   const T* res = (const T*)a.res;
   const int n = n0 + tn * 4;
   if (n >= a.N) return;
-  const int hw = a.Ho * a.Wo;
   float bv[4];
 #pragma unroll
   for (int j = 0; j < 4; ++j) bv[j] = (a.bias && n + j < a.N) ? a.bias[n + j] : 0.f;
@@ -187,14 +220,15 @@ __global__ void __launch_bounds__(CG_THREADS) conv_gather_kernel(ConvArgs a) {
   for (int i = 0; i < 8; ++i) {
     long long m = m0 + tm * 8 + i;
     if (m >= M) break;
-    int b = (int)(m / hw);
+    int b, oy, ox;
+    decode_pixel(a, M, m, b, oy, ox);
     float o[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       o[j] = acc[i][j] + bv[j];
       if (a.out_scale && n + j < a.N) o[j] *= a.out_scale[(long long)b * a.N + n + j];
     }
-    long long off = m * a.N + n;
+    long long off = (((long long)b * a.Ho + oy) * a.Wo + ox) * a.N + n;
     if (vec_out) {
       if (res) {
         float4 r = ld4<T>(res + off);
@@ -221,8 +255,9 @@ LVAE_API int lvae_conv2d_gather(const void* x, const void* x2, const void* wp, c
   LVAE_REQUIRE(ldw % 4 == 0 && ldw >= N, "conv2d_gather: ldw must be a multiple of 4 and >= N");
   LVAE_REQUIRE(mode == 0 || mode == 1, "conv2d_gather: bad mode");
   LVAE_REQUIRE(dtype == 0 || dtype == 1, "conv2d_gather: dtype must be 0 (f32) or 1 (bf16)");
-  ConvArgs a{x, x2, wp, bias, in_scale, out_scale, res, y, B, Hi, Wi, C1, C2, Ho, Wo, N, ldw, kh, kw, stride, pad, mode};
   long long M = (long long)B * Ho * Wo;
+  const int cls = (mode == 1 && stride == 2 && Ho % 2 == 0 && Wo % 2 == 0 && (M / 4) % CG_BM == 0 && (C1 + C2) % CG_BK == 0) ? 1 : 0;
+  ConvArgs a{x, x2, wp, bias, in_scale, out_scale, res, y, B, Hi, Wi, C1, C2, Ho, Wo, N, ldw, kh, kw, stride, pad, mode, cls};
   dim3 grid(cdiv(M, CG_BM), cdiv(N, CG_BN));
   bool vec = (C1 % 4 == 0) && (C2 % 4 == 0);
   if (dtype == 0) {

@@ -46,6 +46,9 @@ CONV_CASES = [
     (16, 16, 3, 1, 1, False, 5, 5, 3, 0),
     (6, 8, 3, 1, 1, False, 5, 5, 3, 0),
     (8, 8, 3, 2, 1, True, 3, 5, 2, 0),
+    (64, 64, 3, 2, 1, False, 16, 16, 2, 0),   # dgrad: parity-class-major transposed gather (tap skipping)
+    (64, 64, 3, 2, 1, True, 8, 8, 2, 0),      # forward: the same path
+    (32, 32, 3, 2, 1, True, 8, 16, 3, 0),
 ]
 
 
