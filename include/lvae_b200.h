@@ -73,7 +73,8 @@ long long lvae_wgrad_tc_workspace(int B, int H, int W, int N, int ksize, int two
  * buffer gp (lvae_wgrad_tc_packed_size floats: [pair][128 rows = two (tap, input-block) row blocks of 64 ci][N]) with TMA
  * reduce-stores from every CTA; lvae_wgrad_unpack_batched adds n packed buffers into their (O,I,kh,kw) gradients
  * (descriptors of lvae_wgrad_unpack_desc_size bytes each, built on the host by lvae_wgrad_unpack_desc and copied to
- * device memory; clear != 0 also zeroes gp for the next step). */
+ * device memory; clear bit 0: also zero gp for the next step; bit 1: overwrite dw / dbias instead of adding, for callers
+ * that know nothing else contributed to them). */
 long long lvae_wgrad_tc_packed_size(int N, int ksize, int two_inputs);
 int lvae_conv2d_wgrad_tc_acc(const void* x, const void* x2, const void* dy, float* gp, int B, int H, int W, int N,
                              int ksize, int dyC, int dy_c0, lvae_stream_t stream);

@@ -344,32 +344,57 @@ __device__ __forceinline__ void unpack_body(const UnpackDesc& d, float (*tile)[9
   if (co0 >= d.N_real) return;
   const int run = d.I_real * d.taps;                       // floats per output channel in dw
   float* gp = const_cast<float*>(d.gp);
-  for (int idx = threadIdx.x; idx < d.n_pairs * 128 * (UNPACK_CO / 4); idx += blockDim.x) {
-    const int i = idx / (UNPACK_CO / 4), part = idx % (UNPACK_CO / 4);          // Gp row, float4 within the 64-byte segment
-    const int blk = i >> 6, ci = i & 63;
-    const int kind = d.kind[blk];
-    float* src = gp + (size_t)i * d.N + co0 + 4 * part;
-    const float4 v = *reinterpret_cast<const float4*>(src);
-    if (d.clear) *reinterpret_cast<float4*>(src) = make_float4(0.f, 0.f, 0.f, 0.f);
-    const float vv[4] = {v.x, v.y, v.z, v.w};
-    if (kind == 0) {
-      const int cin = d.ci0_blk[blk] * 64 + ci;
-      if (cin < d.I_real) {
-        const int o = cin * d.taps + d.tap[blk];
+  const int n_items = d.n_pairs * 128 * (UNPACK_CO / 4);
+  const bool clear = (d.clear & 1) != 0, overwrite = (d.clear & 2) != 0;
+  // four independent 16-byte loads in flight per thread
+  for (int base = threadIdx.x; base < n_items; base += 4 * blockDim.x) {
+    float4 v[4];
 #pragma unroll
-        for (int e = 0; e < 4; ++e) tile[4 * part + e][o] = vv[e];
+    for (int u = 0; u < 4; ++u) {
+      const int idx = base + u * blockDim.x;
+      if (idx < n_items) v[u] = *reinterpret_cast<const float4*>(gp + (size_t)(idx / (UNPACK_CO / 4)) * d.N + co0 + 4 * (idx % (UNPACK_CO / 4)));
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int idx = base + u * blockDim.x;
+      if (idx >= n_items) break;
+      const int i = idx / (UNPACK_CO / 4), part = idx % (UNPACK_CO / 4);        // Gp row, float4 within the 64-byte segment
+      const int blk = i >> 6, ci = i & 63;
+      const int kind = d.kind[blk];
+      if (clear) *reinterpret_cast<float4*>(gp + (size_t)i * d.N + co0 + 4 * part) = make_float4(0.f, 0.f, 0.f, 0.f);
+      const float vv[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+      if (kind == 0) {
+        const int cin = d.ci0_blk[blk] * 64 + ci;
+        if (cin < d.I_real) {
+          const int o = cin * d.taps + d.tap[blk];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) tile[4 * part + e][o] = vv[e];
+        }
+      } else if (kind == 1 && ci == 0 && d.dbias) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+          if (co0 + 4 * part + e < d.N_real) {
+            if (overwrite) d.dbias[co0 + 4 * part + e] = vv[e];
+            else d.dbias[co0 + 4 * part + e] += vv[e];
+          }
       }
-    } else if (kind == 1 && ci == 0 && d.dbias) {
-#pragma unroll
-      for (int e = 0; e < 4; ++e)
-        if (co0 + 4 * part + e < d.N_real) d.dbias[co0 + 4 * part + e] += vv[e];
     }
   }
   __syncthreads();
-  for (int j = 0; j < UNPACK_CO; ++j) {
-    if (co0 + j >= d.N_real) break;
-    float* dst = d.dw + (size_t)(co0 + j) * run;
-    for (int o = threadIdx.x; o < run; o += blockDim.x) dst[o] += tile[j][o];
+  // contiguous runs of dw: (co0 + j) * run .. + run; all UNPACK_CO runs of this CTA are adjacent in memory
+  const int nco = min(UNPACK_CO, d.N_real - co0);
+  float* dst = d.dw + (size_t)co0 * run;
+  const int total = nco * run;
+  if (overwrite) {
+    for (int o = threadIdx.x; o < total; o += blockDim.x) dst[o] = tile[o / run][o % run];
+  } else {
+    for (int base = threadIdx.x; base < total; base += 4 * blockDim.x) {
+      float old[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) { const int o = base + u * blockDim.x; if (o < total) old[u] = dst[o]; }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) { const int o = base + u * blockDim.x; if (o < total) dst[o] = old[u] + tile[o / run][o % run]; }
+    }
   }
 }
 

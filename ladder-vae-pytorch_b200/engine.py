@@ -121,15 +121,32 @@ class PackedGradArena:
             gp = self.flat[off:off + n]
             off += n
             m.weight._lvae_gp = gp
+            m.weight._lvae_gp_id = i
             bias_sink = m.bias._lvae_grad_sink if m.bias is not None else None
             call("lvae_wgrad_unpack_desc", ctypes.addressof(host) + i * dsz, gp.data_ptr(), m.weight._lvae_grad_sink.data_ptr(),
                  bias_sink.data_ptr() if bias_sink is not None else None, m.spec.cout, m.spec.k, int(two), m.spec.cin,
-                 m.spec.cout, 1)
-        self.table = torch.frombuffer(bytearray(host.raw), dtype=torch.uint8).to(dev)
+                 m.spec.cout, 1)      # clear Gp; ADD into the arena (a generic-path fallback may have written it too)
+        self.dsz = dsz
+        self.table = torch.frombuffer(bytearray(host.raw), dtype=torch.uint8).to(dev).view(self.n, dsz)
+        self._sub = {}
 
-    def unpack(self):
-        if self.n:
-            call("lvae_wgrad_unpack_batched", self.table.data_ptr(), self.n, 128, _stream())
+    def unpack(self, ids=None):
+        """Re-lay the packed gradients `ids` (default: all) into the gradient arena, on the current stream.  Sub-tables are
+        cached per id tuple (built during the eager warm-up steps, so nothing is allocated under graph capture)."""
+        if not self.n:
+            return
+        if ids is None:
+            tab, n = self.table, self.n
+        else:
+            key = tuple(ids)
+            if not key:
+                return
+            tab = self._sub.get(key)
+            if tab is None:
+                tab = self.table[torch.tensor(key, dtype=torch.long, device=self.table.device)].contiguous()
+                self._sub[key] = tab
+            n = len(key)
+        call("lvae_wgrad_unpack_batched", tab.data_ptr(), n, 128, _stream())
 
 
 class PackTable:
@@ -199,14 +216,20 @@ class TrainEngine:
         out = self.model(self.x)
         recons = (-out["ll"]).mean()
         loss = recons + out["kl_loss"] * self.beta_kl
-        if self.side_stream is not None:
-            ops.set_side_stream(self.side_stream)
+        ops.set_side_stream(self.side_stream)          # (None: everything on this stream; also resets the wgrad log)
         try:
             loss.backward()
+            # re-lay the packed weight gradients where their wgrads ran: each side stream unpacks its own convolutions
+            # (concurrently with the main stream's tail), then the streams join
+            for slot, ids in ops.packed_grad_log().items():
+                if slot >= 0 and self.side_stream is not None:
+                    with torch.cuda.stream(self.side_stream[slot]):
+                        self.gpacks.unpack(ids)
+                else:
+                    self.gpacks.unpack(ids)
         finally:
             ops.join_side_stream()
             ops.set_side_stream(None)
-        self.gpacks.unpack()
         elbo = (out["ll"] - out["kl_sep"]).mean()
         self.out = {"loss": loss.detach(), "elbo": elbo.detach(), "recons": recons.detach(), "kl": out["kl"].detach(),
                     "kl_avg_layerwise": out["kl_avg_layerwise"].detach()}

@@ -309,7 +309,7 @@ class ConvSpec:
 # Weight gradients depend only on saved activations and the output gradient, and nothing reads them before the
 # optimizer: the engine lets them run on a side stream (a parallel branch of the captured graph) so that the
 # small, latency-bound wgrad kernels overlap the dgrad / BatchNorm chain.
-_side = {"streams": None, "keep": [], "next": 0}
+_side = {"streams": None, "keep": [], "next": 0, "log": {}}     # log: stream slot (-1 = current stream) -> packed-gradient ids
 
 
 def set_side_stream(streams) -> None:
@@ -319,6 +319,12 @@ def set_side_stream(streams) -> None:
     _side["streams"] = list(streams) if streams else None
     _side["keep"] = []
     _side["next"] = 0
+    _side["log"] = {}
+
+
+def packed_grad_log():
+    """{stream slot: [packed-gradient ids whose wgrad was issued there since set_side_stream]} (slot -1: current stream)."""
+    return _side["log"]
 
 
 def join_side_stream() -> None:
@@ -474,9 +480,10 @@ def conv_backward_raw(spec: ConvSpec, xn, x2n, weight, bias, out_scale, gyn, nee
         gbbuf, bsunk = (None, True)
         if bias is not None and need_b:
             gbbuf, bsunk = _param_grad_buffer(bias)
-        side = None
+        side, slot = None, -1
         if _side["streams"] and sunk and bsunk:
-            side = _side["streams"][_side["next"] % len(_side["streams"])]
+            slot = _side["next"] % len(_side["streams"])
+            side = _side["streams"][slot]
             _side["next"] += 1
         if side is not None:
             side.wait_event(torch.cuda.current_stream().record_event())     # gyn is ready
@@ -488,7 +495,8 @@ def conv_backward_raw(spec: ConvSpec, xn, x2n, weight, bias, out_scale, gyn, nee
             stats["tc_wgrad"] += 1
             gp = getattr(weight, "_lvae_gp", None) if (sunk and bsunk) else None
             if gp is not None:
-                # engine-owned packed gradient: every CTA reduce-adds into it, the engine unpacks all of them in one launch
+                # engine-owned packed gradient: every CTA reduce-adds into it, the engine unpacks them in batched launches
+                _side["log"].setdefault(slot, []).append(weight._lvae_gp_id)
                 call("lvae_conv2d_wgrad_tc_acc", xn.data_ptr(), _p(x2n), gyn.data_ptr(), gp.data_ptr(), B, Hi, Wi, N, spec.k,
                      0, 0, _stream())
             else:
