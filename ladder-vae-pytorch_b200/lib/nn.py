@@ -28,8 +28,8 @@ class Conv2d(nn.Conv2d):
             raise NotImplementedError("lvae_b200.Conv2d supports square, ungrouped, undilated, zero-padded convs")
         self.spec = ops.ConvSpec(self.out_channels, self.in_channels, k[0], s[0], p[0])
 
-    def forward(self, x, x2=None, out_scale=None, res=None):
-        return ops.conv2d(x, self.weight, self.bias, self.spec, x2=x2, out_scale=out_scale, res=res)
+    def forward(self, x, x2=None, out_scale=None, res=None, stats_bn=None):
+        return ops.conv2d(x, self.weight, self.bias, self.spec, x2=x2, out_scale=out_scale, res=res, stats_bn=stats_bn)
 
 
 class ConvTranspose2d(nn.ConvTranspose2d):

@@ -103,7 +103,9 @@ class MergeLayer(nn.Module):
         if _hooked(self):
             return self.layer(torch.cat((x, y), dim=1))
         if isinstance(self.layer, nn.Sequential):
-            return self.layer[1](self.layer[0](x, x2=y))
+            blk = self.layer[1]
+            first = blk.block[0] if getattr(blk, "_whole_block", False) else None      # BatchNorm that opens the block
+            return blk(self.layer[0](x, x2=y, stats_bn=first if (first is not None and self.training) else None))
         return self.layer(x, x2=y)
 
 

@@ -526,14 +526,23 @@ class Conv2dFn(Function):
     """y = (conv(cat(x, x2)) + bias) * out_scale[b, c] + res   (Conv2d or ConvTranspose2d)."""
 
     @staticmethod
-    def forward(ctx, x, x2, weight, bias, out_scale, res, spec: ConvSpec):
+    def forward(ctx, x, x2, weight, bias, out_scale, res, spec: ConvSpec, stats_bn=None):
         _require_cuda(x)
         xn = nhwc(x)
         x2n = nhwc(x2) if x2 is not None else None
         resn = nhwc(res) if res is not None else None
         if out_scale is not None:
             out_scale = out_scale.reshape(xn.shape[0], spec.cout)
-        y = conv_forward_raw(spec, xn, x2n, weight, bias, out_scale, resn)
+        spec._last_stats = None
+        if stats_bn is not None and stats_bn.training and stats_bn.num_features == spec.cout == 64:
+            # the consumer is a BatchNorm in train mode: its statistics ride in this conv's epilogue when the tcgen05 path runs
+            acc = bn_scratch(stats_bn, xn.device)[0]
+            _bn_clean(stats_bn, acc, "fwd")
+            y, fused = conv_forward_raw(spec, xn, x2n, weight, bias, out_scale, resn, stats_acc=acc)
+            if fused:
+                spec._last_stats = (acc, y.shape[0] * y.shape[1] * y.shape[2], _bn_epoch[0])
+        else:
+            y = conv_forward_raw(spec, xn, x2n, weight, bias, out_scale, resn)
         ctx.spec = spec
         ctx.save_for_backward(xn, x2n, weight, bias, out_scale)
         ctx.has_res = res is not None
@@ -548,11 +557,17 @@ class Conv2dFn(Function):
                                             ctx.needs_input_grad[2], ctx.needs_input_grad[3])
         gres = gy if ctx.has_res and ctx.needs_input_grad[5] else None
         return (as_nchw(gx) if gx is not None else None, as_nchw(gx2) if gx2 is not None else None, gw, gb, None,
-                gres, None)
+                gres, None, None)
 
 
-def conv2d(x, weight, bias, spec: ConvSpec, x2=None, out_scale=None, res=None):
-    return Conv2dFn.apply(x, x2, weight, bias, out_scale, res, spec)
+def conv2d(x, weight, bias, spec: ConvSpec, x2=None, out_scale=None, res=None, stats_bn=None):
+    """stats_bn: the train-mode BatchNorm2d that consumes the output next (its statistics are then accumulated by this
+    conv's epilogue and handed over through the output tensor, like a gated block does for its successor)."""
+    out = Conv2dFn.apply(x, x2, weight, bias, out_scale, res, spec, stats_bn)
+    if stats_bn is not None and getattr(spec, "_last_stats", None) is not None:
+        out._lvae_stats = spec._last_stats
+        spec._last_stats = None
+    return out
 
 
 # --------------------------------------------------------------------------- BatchNorm (+ nonlinearity)
