@@ -509,9 +509,14 @@ LVAE_API int lvae_conv2d_wgrad_tc_acc(const void* x, const void* x2, const void*
   p.tiles_x = W / 8;
   p.tiles_per_img = (W / 8) * (H / 16);
   const int n_tiles = p.halo ? B * p.tiles_per_img : (p.M_total + WG_TILE - 1) / WG_TILE;
-  int grid = n_tiles < lvae_num_sms() ? n_tiles : lvae_num_sms();
-  // fewer, fatter CTAs for small problems: every CTA costs one pass of reduce-stores over the whole gradient
-  if (n_tiles <= lvae_num_sms() && n_tiles >= 8) grid = (n_tiles + 1) / 2;
+  // Few, fat CTAs: every CTA pays one pass of reduce-stores over the whole packed gradient (160 KB for a 3x3 conv), so the
+  // SM-time of the launch is minimised by giving each CTA several pixel tiles; the kernel runs on a side stream, its latency
+  // does not matter, and the SMs it leaves alone serve the main stream's convolutions (LVAE_WGRAD_TILES_PER_CTA, default 8).
+  static int tpc_env = 0;
+  if (!tpc_env) { const char* e = getenv("LVAE_WGRAD_TILES_PER_CTA"); tpc_env = e ? atoi(e) : 8; if (tpc_env < 1) tpc_env = 1; }
+  int grid = (n_tiles + tpc_env - 1) / tpc_env;
+  if (grid > lvae_num_sms()) grid = lvae_num_sms();
+  if (grid < 1) grid = 1;
   p.tiles_per_cta = (n_tiles + grid - 1) / grid;
   grid = (n_tiles + p.tiles_per_cta - 1) / p.tiles_per_cta;
   int bw = W;
