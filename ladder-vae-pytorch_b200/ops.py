@@ -927,6 +927,7 @@ class StochasticFn(Function):
     @staticmethod
     def forward(ctx, q_params, p_params, eps, forced, use_mode, analytical, lowp_copy):
         _require_cuda(p_params)
+        ctx.set_materialize_grads(False)         # unused outputs (z, kl_spatial, logp, logq ...) arrive as None, not as zero tensors
         pn = nhwc(p_params).float()
         qn = nhwc(q_params).float() if q_params is not None else None
         ref = qn if qn is not None else pn
@@ -1082,6 +1083,7 @@ class DmolHeadFn(Function):
 
     @staticmethod
     def forward(ctx, h, weight, bias, x, spec):
+        ctx.set_materialize_grads(False)
         hn = nhwc(h)
         B, H, W, C = hn.shape
         wp = spec.pack_tc_fwd.get(weight, torch.bfloat16)
@@ -1100,6 +1102,10 @@ class DmolHeadFn(Function):
     def backward(ctx, g_ll, _g_l):
         hn, l, xc, weight, bias = ctx.saved_tensors
         spec = ctx.spec
+        if g_ll is None:
+            if _g_l is not None:
+                raise RuntimeError("DmolHeadFn: gradients through the raw likelihood parameters are not supported")
+            return None, None, None, None, None
         B, H, W, C = hn.shape
         dl = torch.empty((B, H, W, 128), dtype=torch.bfloat16, device=hn.device)
         call("lvae_dmol_bwd", l.data_ptr(), xc.data_ptr(), g_ll.contiguous().float().data_ptr(), None, dl.data_ptr(), B,
