@@ -104,6 +104,15 @@ typedef struct {
 int lvae_conv2d_tc_ex(const void* x, const void* x2, const void* wp, const float* bias, const float* out_scale,
                       const void* res, void* y, void* y2, int nsplit, int B, int H, int W, int Cin, int N, int ksize,
                       int flip, int out_f32, const LvaeConvFuse* fuse, lvae_stream_t stream);
+/* Stride-2 3x3 convolutions 64 -> 64 on the same tcgen05 kernel (the down / up-sampling pre_convs of
+ * models/lvae_layers.py:261-276).  kind 0 "gather": y (B,Hg,Wg,N) from x (B,2Hg,2Wg,64) = Conv2d(stride 2, pad 1) forward
+ * and ConvTranspose2d(stride 2, pad 1, output_padding 1) input gradient (TMA traverses x with element stride 2).  kind 1
+ * "transposed": y (B,2Hg,2Wg,N) from x (B,Hg,Wg,64) = ConvTranspose2d forward and Conv2d(stride 2) input gradient, as four
+ * launches, one per output parity class (1 + 2 + 2 + 4 filter taps), each storing through a tensor map that steps two
+ * output pixels.  wp: nine packed [64][64] blocks, block t = tap (t/3, t%3), rows = output channel (lvae_pack_weights
+ * mode 2 / 3).  bias, out_scale (B,N) optional.  Hg, Wg powers of two, Wg <= 64. */
+int lvae_conv2d_tc_s2(const void* x, const void* wp, const float* bias, const float* out_scale, void* y, int B, int Hg,
+                      int Wg, int N, int kind, lvae_stream_t stream);
 /* profiling aid: CTA 0 of subsequent lvae_conv2d_tc launches records clock64 stamps per tile into dev_buf (NULL = off) */
 void lvae_conv2d_tc_debug(long long* dev_buf);
 /* y = x * scale[b,c] (Dropout2d mask on a gradient tensor ahead of the TMA-fed dgrad) */

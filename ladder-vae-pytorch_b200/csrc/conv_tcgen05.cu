@@ -58,6 +58,11 @@ struct TcParams {
   int tma_store;            // bf16 output, N % 64 == 0, no residual: epilogue stages the tile in smem and stores it with TMA
   long long* dbg;           // optional per-tile clock64 trace of CTA 0 (profiling aid, normally null)
   int8_t dx[TC_MAX_KB], dy[TC_MAX_KB], src[TC_MAX_KB], coff[TC_MAX_KB];   // coff: channel offset / 64 inside the tensor
+  // stride-2 convolutions (lvae_conv2d_tc_s2): the tile's pixel coordinates are multiplied by in_stride before the tap
+  // offset is added (the input tensor map then traverses with the same element stride), and k-block kb reads weight
+  // block wblk[kb] of the packed buffer (a parity class of a transposed convolution uses a subset of the nine taps)
+  int in_stride, use_wblk;
+  int8_t wblk[TC_MAX_KB];
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -314,7 +319,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     // weights were packed many kernels ago: fetch them before waiting on the previous kernel (PDL prologue)
     if (elect_one()) {
       mbar_expect_tx(BAR(2 * S), (uint32_t)(p.n_kb * wbytes_kb));
-      for (int kb = 0; kb < p.n_kb; ++kb) tma_load_2d(smem_u32(sW + kb * wbytes_kb), &tmW, BAR(2 * S), 0, kb * p.Npad);
+      for (int kb = 0; kb < p.n_kb; ++kb)
+        tma_load_2d(smem_u32(sW + kb * wbytes_kb), &tmW, BAR(2 * S), 0, (p.use_wblk ? p.wblk[kb] : kb) * p.Npad);
     }
     __syncwarp();
   }
@@ -356,6 +362,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         int rem = p0 - n0 * hw;
         int h0 = rem / p.W;
         int w0 = rem - h0 * p.W;
+        if (p.in_stride > 1) { h0 *= p.in_stride; w0 *= p.in_stride; }
         for (int kb = 0; kb < p.n_kb; ++kb) {
           mbar_wait(BAR(S + stage), phase ^ 1);
           if (elect_one()) {
@@ -879,6 +886,103 @@ LVAE_API int lvae_conv2d_tc_ex(const void* x, const void* x2, const void* wp, co
   else lvae_launch(conv_tc_kernel<0>, grid, TC_THREADS, smem, stream, tmA0, tmA1, tmW, tmY, tmY2, p);
   LVAE_COUNT_LAUNCH();
   LVAE_CHECK_LAUNCH("conv2d_tc");
+  return LVAE_OK;
+}
+
+// Stride-2 3x3 convolutions of 64 -> 64 channels on the same kernel (bf16 in / out, TMA-store epilogue).
+//   kind 0 "strided gather":  y[b,oy,ox,:] = bias + sum_t x[b, 2oy-1+ky, 2ox-1+kx, :] . Wt         x (B,2Ho,2Wo,64) -> y (B,Ho,Wo,N)
+//           = Conv2d(stride 2, pad 1) forward, and the input gradient of ConvTranspose2d(stride 2, pad 1, output_padding 1)
+//   kind 1 "transposed":      y[b,2iy-1+ky,2ix-1+kx,:] += x[b,iy,ix,:] . Wt                         x (B,Hi,Wi,64) -> y (B,2Hi,2Wi,N)
+//           = ConvTranspose2d forward, and the input gradient of Conv2d(stride 2, pad 1).  Run as four launches, one per
+//           output parity class (oy&1, ox&1): class (py,px) is a stride-1 convolution over the INPUT grid with the taps
+//           {ky : ky = 1 if py == 0 else 0 or 2} x {kx likewise} (input offset +1 for k = 0, else 0), written through a
+//           tensor map whose strides step two output pixels -- 1 + 2 + 2 + 4 = 9 tap-GEMMs in total, no zero work.
+// wp: nine packed [Npad][64] weight blocks, block t = tap (ky,kx) = (t/3, t%3), rows = output channel, K = input channel
+// (lvae_pack_weights mode 2 for Conv2d forward / ConvTranspose2d dgrad with the transposed-conv weight read as (O=ci, I=co);
+// mode 3 for the other two).  Hg, Wg: the smaller of the two grids (Ho,Wo for kind 0; Hi,Wi for kind 1), powers of two.
+LVAE_API int lvae_conv2d_tc_s2(const void* x, const void* wp, const float* bias, const float* out_scale, void* y, int B,
+                               int Hg, int Wg, int N, int kind, cudaStream_t stream) {
+  LVAE_REQUIRE(x && wp && y, "conv2d_tc_s2: null pointer");
+  LVAE_REQUIRE(N == 64, "conv2d_tc_s2: 64 output channels");
+  LVAE_REQUIRE((Wg & (Wg - 1)) == 0 && (Hg & (Hg - 1)) == 0 && Wg >= 1 && Wg <= 64 && Hg >= 1, "conv2d_tc_s2: grid must be powers of two, W <= 64");
+  LVAE_REQUIRE(kind == 0 || kind == 1, "conv2d_tc_s2: bad kind");
+  EncodeTiledFn enc = get_encode();
+  if (!enc) { lvae_set_error("conv2d_tc_s2: cuTensorMapEncodeTiled unavailable"); return LVAE_ERR_CUDA; }
+  const int Cin = 64, Hb = 2 * Hg, Wb = 2 * Wg;               // the bigger grid
+  static size_t attr_smem = 0;
+  if (!attr_smem) {
+    cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024));
+    if (e != cudaSuccess) { lvae_set_error("conv2d_tc_s2: cannot raise dynamic smem: %s", cudaGetErrorString(e)); return LVAE_ERR_CUDA; }
+    attr_smem = 227 * 1024;
+  }
+  for (int cls = 0; cls < (kind == 0 ? 1 : 4); ++cls) {
+    TcParams p{};
+    p.bias = bias; p.out_scale = out_scale; p.y = y;
+    p.M_total = B * Hg * Wg; p.H = Hg; p.W = Wg; p.N = N; p.Npad = 64;
+    p.dbg = nullptr;
+    p.use_wblk = 1;
+    p.in_stride = kind == 0 ? 2 : 1;
+    int kb = 0;
+    const int py = cls >> 1, px = cls & 1;
+    for (int ky = 0; ky < 3; ++ky)
+      for (int kx = 0; kx < 3; ++kx) {
+        int oy, ox;
+        if (kind == 0) { oy = ky - 1; ox = kx - 1; }
+        else {
+          if ((py == 0) != (ky == 1) || (px == 0) != (kx == 1)) continue;       // this tap never reaches the class
+          oy = ky == 0 ? 1 : 0; ox = kx == 0 ? 1 : 0;
+        }
+        p.dy[kb] = (int8_t)oy; p.dx[kb] = (int8_t)ox; p.src[kb] = 0; p.coff[kb] = 0; p.wblk[kb] = (int8_t)(ky * 3 + kx);
+        ++kb;
+      }
+    p.n_kb = kb;
+    p.bw = Wg;
+    p.bh = pow2_floor_le(Hg, TC_BM / p.bw);
+    p.bn = TC_BM / (p.bw * p.bh);
+    p.tmem_cols = 128;
+    p.tma_store = 1;
+    p.halo = 0;
+    p.stage_bytes = TC_STAGE_BYTES;
+    const int wbytes = ((p.n_kb * p.Npad * 128) + 1023) & ~1023;
+    p.n_stages = 8;
+    const size_t smem = 1024 + (size_t)wbytes + (size_t)p.n_stages * TC_STAGE_BYTES + TC_STAGE_BYTES + 8192;
+    CUtensorMap tmA, tmW, tmY, tmY2;
+    memset(&tmY2, 0, sizeof(tmY2));
+    {
+      // input: for kind 0 the (bigger) input grid is traversed with element stride 2, so a box of 2*bw x 2*bh input
+      // pixels delivers the bw x bh pixels one filter tap needs for a tile of output pixels
+      const int Hi = kind == 0 ? Hb : Hg, Wi = kind == 0 ? Wb : Wg, st = kind == 0 ? 2 : 1;
+      cuuint64_t gdim[4] = {(cuuint64_t)Cin, (cuuint64_t)Wi, (cuuint64_t)Hi, (cuuint64_t)B};
+      cuuint64_t gstr[3] = {(cuuint64_t)Cin * 2, (cuuint64_t)Wi * Cin * 2, (cuuint64_t)Hi * Wi * Cin * 2};
+      cuuint32_t box[4] = {64, (cuuint32_t)(p.bw * st), (cuuint32_t)(p.bh * st), (cuuint32_t)p.bn};
+      cuuint32_t estr[4] = {1, (cuuint32_t)st, (cuuint32_t)st, 1};
+      CUresult r = enc(&tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, (void*)x, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                       CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (r != CUDA_SUCCESS) { lvae_set_error("conv2d_tc_s2: tensor map (x) encode failed: %d", (int)r); return LVAE_ERR_CUDA; }
+      // output: kind 0 the plain (B,Hg,Wg,N) tensor; kind 1 the parity class (py,px) of the (B,2Hg,2Wg,N) tensor
+      const size_t Wo = kind == 0 ? Wg : Wb, Ho = kind == 0 ? Hg : Hb, step = kind == 0 ? 1 : 2;
+      char* ybase = (char*)y + (kind == 0 ? 0 : ((size_t)py * Wo + px) * N * 2);
+      cuuint64_t odim[4] = {(cuuint64_t)N, (cuuint64_t)Wg, (cuuint64_t)Hg, (cuuint64_t)B};
+      cuuint64_t ostr[3] = {(cuuint64_t)(step * N * 2), (cuuint64_t)(step * Wo * N * 2), (cuuint64_t)(Ho * Wo * N * 2)};
+      cuuint32_t obox[4] = {64, (cuuint32_t)p.bw, (cuuint32_t)p.bh, (cuuint32_t)p.bn};
+      cuuint32_t one[4] = {1, 1, 1, 1};
+      r = enc(&tmY, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, (void*)ybase, odim, ostr, obox, one, CU_TENSOR_MAP_INTERLEAVE_NONE,
+              CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (r != CUDA_SUCCESS) { lvae_set_error("conv2d_tc_s2: tensor map (y) encode failed: %d", (int)r); return LVAE_ERR_CUDA; }
+      cuuint64_t wdim[2] = {64, (cuuint64_t)9 * p.Npad};
+      cuuint64_t wstr[1] = {128};
+      cuuint32_t wbox[2] = {64, (cuuint32_t)p.Npad};
+      cuuint32_t westr[2] = {1, 1};
+      r = enc(&tmW, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (void*)wp, wdim, wstr, wbox, westr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+              CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (r != CUDA_SUCCESS) { lvae_set_error("conv2d_tc_s2: tensor map (w) encode failed: %d", (int)r); return LVAE_ERR_CUDA; }
+    }
+    const int n_tiles = (p.M_total + TC_BM - 1) / TC_BM;
+    const int grid = n_tiles < lvae_num_sms() ? n_tiles : lvae_num_sms();
+    lvae_launch(conv_tc_kernel<0>, grid, TC_THREADS, smem, stream, tmA, tmA, tmW, tmY, tmY2, p);
+    LVAE_COUNT_LAUNCH();
+    LVAE_CHECK_LAUNCH("conv2d_tc_s2");
+  }
   return LVAE_OK;
 }
 

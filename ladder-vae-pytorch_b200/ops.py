@@ -248,6 +248,7 @@ class WeightPack:
 
 
 _tc_enabled = [True]
+_s2_enabled = [os.environ.get("LVAE_CONV_S2_TC", "1") != "0"]
 
 
 def set_tensor_cores(flag: bool) -> None:
@@ -276,12 +277,27 @@ class ConvSpec:
         self.tc_shape = (not transposed) and stride == 1 and k in (1, 3) and pad == k // 2
         self.pack_tc_fwd = WeightPack(cout, cin, taps, 2) if self.tc_shape else None
         self.pack_tc_bwd = WeightPack(cout, cin, taps, 3) if self.tc_shape else None
+        # stride-2 3x3 64 -> 64 (the down / up-sampling convs): lvae_conv2d_tc_s2.  With d0, d1 = the weight tensor's first
+        # two dims, the "gather" kind multiplies by blocks [N = d0][K = d1] (mode 2), the "transposed" kind by [N = d1][K = d0]
+        # (mode 3).  Conv2d: forward = gather, dgrad = transposed; ConvTranspose2d: the other way round.
+        self.s2_shape = (k == 3 and stride == 2 and pad == 1 and cin == 64 and cout == 64
+                         and (not transposed or output_padding == 1))
+        d0, d1 = (cin, cout) if transposed else (cout, cin)
+        self.pack_s2_gather = WeightPack(d0, d1, taps, 2) if self.s2_shape else None
+        self.pack_s2_scatter = WeightPack(d0, d1, taps, 3) if self.s2_shape else None
 
     def packs(self, bf16: bool):
         out = [self.pack_fwd, self.pack_bwd]
         if bf16 and self.tc_shape:
             out += [self.pack_tc_fwd, self.pack_tc_bwd]
+        if bf16 and self.s2_shape:
+            out += [self.pack_s2_gather, self.pack_s2_scatter]
         return out
+
+    def s2_ok(self, t, small_h: int, small_w: int) -> bool:
+        """tcgen05 path for the stride-2 convs: bf16 (B,H,W,64) operand, the smaller grid a power of two, W <= 64."""
+        return (_tc_enabled[0] and _s2_enabled[0] and self.s2_shape and t.dtype == torch.bfloat16 and t.shape[3] == 64
+                and _pow2(small_h) and _pow2(small_w) and small_w <= 64)
 
     def out_hw(self, h, w):
         if not self.transposed:
@@ -407,6 +423,15 @@ def conv_forward_raw(spec: ConvSpec, xn, x2n, weight, bias, out_scale, resn, sta
     assert padded or C1 + C2 == spec.cin, "conv input channels %d+%d != %d" % (C1, C2, spec.cin)
     Ho, Wo = spec.out_hw(Hi, Wi)
     want_f32 = spec.out_fp32 and xn.dtype == torch.bfloat16
+    if x2n is None and resn is None and not want_f32 and spec.s2_shape:
+        hs, ws = (Hi, Wi) if spec.transposed else (Ho, Wo)
+        if spec.s2_ok(xn, hs, ws):
+            stats["tc_fwd"] += 1
+            pack = spec.pack_s2_scatter if spec.transposed else spec.pack_s2_gather
+            y = torch.empty((B, Ho, Wo, spec.cout), dtype=torch.bfloat16, device=xn.device)
+            call("lvae_conv2d_tc_s2", xn.data_ptr(), pack.get(weight, torch.bfloat16).data_ptr(), _p(bias), _p(out_scale),
+                 y.data_ptr(), B, hs, ws, spec.cout, 1 if spec.transposed else 0, _stream())
+            return (y, False) if stats_acc is not None else y
     if padded and not spec.tc_forward_ok(xn, x2n):
         xn, C1 = xn[..., :spec.cin].contiguous(), spec.cin
     if spec.tc_forward_ok(xn, x2n) and (resn is None or resn.dtype == (torch.float32 if want_f32 else torch.bfloat16)):
@@ -443,13 +468,23 @@ def conv_backward_raw(spec: ConvSpec, xn, x2n, weight, bias, out_scale, gyn, nee
     padded = x2n is None and C1 > spec.cin
     if padded and not use_tc:
         xn, C1, padded = xn[..., :spec.cin].contiguous(), spec.cin, False
-    if use_tc and out_scale is not None:
+    # stride-2 convs on the tensor cores: dgrad of Conv2d = "transposed" kind over the dy grid, dgrad of ConvTranspose2d =
+    # "gather" kind onto the (smaller) x grid
+    hs2, ws2 = (Hi, Wi) if spec.transposed else (Ho, Wo)
+    use_s2 = need_x and x2n is None and spec.s2_shape and spec.s2_ok(gyn, hs2, ws2) and xn.dtype == torch.bfloat16 and C1 == 64
+    if (use_tc or use_s2) and out_scale is not None:
         # TMA-fed operands never pass through registers: apply the Dropout2d mask in a separate pass
         gys = torch.empty_like(gyn)
         call("lvae_channel_scale", gyn.data_ptr(), out_scale.data_ptr(), gys.data_ptr(), B, Ho * Wo, N, _dt(gyn), _stream())
         gyn, out_scale = gys, None
     if need_x:
-        if use_tc:
+        if use_s2:
+            stats["tc_dgrad"] += 1
+            pack = spec.pack_s2_gather if spec.transposed else spec.pack_s2_scatter
+            gx = torch.empty((B, Hi, Wi, 64), dtype=torch.bfloat16, device=gyn.device)
+            call("lvae_conv2d_tc_s2", gyn.data_ptr(), pack.get(weight, torch.bfloat16).data_ptr(), None, _p(dx_scale),
+                 gx.data_ptr(), B, hs2, ws2, 64, 0 if spec.transposed else 1, _stream())
+        elif use_tc:
             wpb = spec.pack_tc_bwd.get(weight, torch.bfloat16)
             stats["tc_dgrad"] += 1
             if x2n is None:
