@@ -113,6 +113,10 @@ int lvae_conv2d_tc_ex(const void* x, const void* x2, const void* wp, const float
  * mode 2 / 3).  bias, out_scale (B,N) optional.  Hg, Wg powers of two, Wg <= 64. */
 int lvae_conv2d_tc_s2(const void* x, const void* wp, const float* bias, const float* out_scale, void* y, int B, int Hg,
                       int Wg, int N, int kind, lvae_stream_t stream);
+/* Narrow-output 3x3 "same" convolution, 64 bf16 channels -> N <= 4 (the Bernoulli head's parameter_net,
+ * lib/likelihoods.py:61: 64 -> 1): bandwidth-bound, 8 lanes per pixel.  w: torch (N,64,3,3) fp32; y (B,H,W,N) fp32 / bf16. */
+int lvae_conv3x3_narrow(const void* x, const float* w, const float* bias, void* y, int B, int H, int W, int N, int out_f32,
+                        lvae_stream_t stream);
 /* profiling aid: CTA 0 of subsequent lvae_conv2d_tc launches records clock64 stamps per tile into dev_buf (NULL = off) */
 void lvae_conv2d_tc_debug(long long* dev_buf);
 /* y = x * scale[b,c] (Dropout2d mask on a gradient tensor ahead of the TMA-fed dgrad) */

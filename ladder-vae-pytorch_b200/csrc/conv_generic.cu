@@ -558,3 +558,69 @@ LVAE_API int lvae_colsum(const void* dy, const float* scale, float* out, int B, 
   LVAE_CHECK_LAUNCH("colsum");
   return LVAE_OK;
 }
+
+// ------------------------------------------------------------------------------------------
+// Narrow-output 3x3 convolution: 64 bf16 channels -> N <= 4 outputs per pixel (the Bernoulli head's parameter_net,
+// lib/likelihoods.py:61, 64 -> 1 at 28x28).  A 128x64 GEMM tile would waste 63/64 of its columns there; this is a
+// bandwidth problem: 8 lanes own one pixel (16 bytes = 8 channels each, so a pixel row is one coalesced 128-byte read),
+// the taps' weights sit in shared memory as fp32, partial dot products meet in a 3-step lane butterfly.
+// w: torch layout (N, 64, 3, 3) fp32; y: (B,H,W,N) fp32 or bf16.
+// ------------------------------------------------------------------------------------------
+template <typename TO>
+__global__ void __launch_bounds__(256) conv3x3_narrow_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ w,
+                                                             const float* __restrict__ bias, TO* __restrict__ y, long long M,
+                                                             int H, int W, int N) {
+  pdl_wait();
+  pdl_launch();
+  __shared__ float sw[4][9][64];
+  for (int i = threadIdx.x; i < N * 9 * 64; i += blockDim.x) {
+    const int n = i / 576, r = i - n * 576, ci = r / 9, t = r - ci * 9;      // torch (n, ci, ky, kx) order
+    sw[n][t][ci] = w[i];
+  }
+  __syncthreads();
+  const int sub = threadIdx.x & 7;                                            // which 8 channels of the pixel
+  const int hw = H * W;
+  for (long long m = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 3; m < ((M + 31) & ~31LL);
+       m += ((long long)gridDim.x * blockDim.x) >> 3) {
+    const bool live = m < M;
+    const long long mm = live ? m : 0;
+    const int b = (int)(mm / hw);
+    const int r = (int)(mm - (long long)b * hw);
+    const int py = r / W, px = r - py * W;
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int t = 0; t < 9; ++t) {
+      const int iy = py + t / 3 - 1, ix = px + t % 3 - 1;
+      if (live && iy >= 0 && iy < H && ix >= 0 && ix < W) {
+        const uint4 u = *reinterpret_cast<const uint4*>(x + (((long long)b * H + iy) * W + ix) * 64 + sub * 8);
+        const uint32_t wd[4] = {u.x, u.y, u.z, u.w};
+        float v[8];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { v[2 * j] = __uint_as_float(wd[j] << 16); v[2 * j + 1] = __uint_as_float(wd[j] & 0xFFFF0000u); }
+        for (int n = 0; n < N; ++n) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) acc[n] = fmaf(v[j], sw[n][t][sub * 8 + j], acc[n]);
+        }
+      }
+    }
+    for (int n = 0; n < N; ++n) {
+      float a = acc[n];
+      a += __shfl_xor_sync(0xffffffffu, a, 1);
+      a += __shfl_xor_sync(0xffffffffu, a, 2);
+      a += __shfl_xor_sync(0xffffffffu, a, 4);
+      if (live && sub == 0) st1<TO>(y + m * N + n, a + (bias ? bias[n] : 0.f));
+    }
+  }
+}
+
+LVAE_API int lvae_conv3x3_narrow(const void* x, const float* w, const float* bias, void* y, int B, int H, int W, int N,
+                                 int out_f32, cudaStream_t stream) {
+  LVAE_REQUIRE(x && w && y && B > 0 && H > 0 && W > 0 && N >= 1 && N <= 4, "conv3x3_narrow: bad args (1 <= N <= 4)");
+  const long long M = (long long)B * H * W;
+  const int grid = (int)min((long long)8 * lvae_num_sms(), (M * 8 + 255) / 256);
+  if (out_f32) lvae_launch(conv3x3_narrow_kernel<float>, grid, 256, 0, stream, (const __nv_bfloat16*)x, w, bias, (float*)y, M, H, W, N);
+  else lvae_launch(conv3x3_narrow_kernel<__nv_bfloat16>, grid, 256, 0, stream, (const __nv_bfloat16*)x, w, bias, (__nv_bfloat16*)y, M, H, W, N);
+  LVAE_COUNT_LAUNCH();
+  LVAE_CHECK_LAUNCH("conv3x3_narrow");
+  return LVAE_OK;
+}

@@ -432,6 +432,14 @@ def conv_forward_raw(spec: ConvSpec, xn, x2n, weight, bias, out_scale, resn, sta
             call("lvae_conv2d_tc_s2", xn.data_ptr(), pack.get(weight, torch.bfloat16).data_ptr(), _p(bias), _p(out_scale),
                  y.data_ptr(), B, hs, ws, spec.cout, 1 if spec.transposed else 0, _stream())
             return (y, False) if stats_acc is not None else y
+    if (spec.cout <= 4 and spec.k == 3 and spec.stride == 1 and spec.pad == 1 and not spec.transposed and x2n is None
+            and resn is None and out_scale is None and xn.dtype == torch.bfloat16 and C1 == 64 and spec.cin == 64):
+        # narrow head (Bernoulli parameter_net, 64 -> 1): a GEMM tile would be 63/64 padding
+        stats["narrow_fwd"] = stats.get("narrow_fwd", 0) + 1
+        y = torch.empty((B, Ho, Wo, spec.cout), dtype=torch.float32 if want_f32 else torch.bfloat16, device=xn.device)
+        call("lvae_conv3x3_narrow", xn.data_ptr(), weight.data_ptr(), _p(bias), y.data_ptr(), B, Hi, Wi, spec.cout,
+             1 if want_f32 else 0, _stream())
+        return (y, False) if stats_acc is not None else y
     if padded and not spec.tc_forward_ok(xn, x2n):
         xn, C1 = xn[..., :spec.cin].contiguous(), spec.cin
     if spec.tc_forward_ok(xn, x2n) and (resn is None or resn.dtype == (torch.float32 if want_f32 else torch.bfloat16)):

@@ -164,3 +164,30 @@ def test_tc_stride2_conv_forward_backward(case):
     assert rel_err(xd.grad.float(), xr.grad) < 6e-3
     assert rel_err(mod.weight.grad, wr.grad) < 5e-3
     assert rel_err(mod.bias.grad, br.grad) < 5e-3
+
+
+@pytest.mark.parametrize("cout,H,W,B,out_fp32", [(1, 28, 28, 3, True), (2, 7, 5, 4, True), (4, 8, 8, 2, False), (1, 3, 3, 1, True)])
+def test_narrow_head_conv(cout, H, W, B, out_fp32):
+    """64 -> N <= 4 3x3 conv (Bernoulli parameter_net) takes the bandwidth-bound narrow kernel in the bf16 pipeline."""
+    import lvae_b200
+    from lvae_b200.lib.nn import Conv2d
+    from lvae_b200 import ops
+    g = torch.Generator().manual_seed(cout * 100 + H)
+    x = torch.randn(B, 64, H, W, generator=g).to(torch.bfloat16)
+    mod = Conv2d(64, cout, 3, padding=1).cuda()
+    mod.spec.out_fp32 = out_fp32
+    xr = x.double().requires_grad_(True)
+    wr, br = mod.weight.detach().double().cpu().requires_grad_(True), mod.bias.detach().double().cpu().requires_grad_(True)
+    yr = F.conv2d(xr, wr, br, padding=1)
+    gy = torch.randn(yr.shape, generator=g)
+    yr.backward(gy.double())
+    xd = phys_nhwc(x.cuda()).requires_grad_(True)
+    n0 = ops.stats.get("narrow_fwd", 0)
+    y = mod(xd)
+    assert ops.stats.get("narrow_fwd", 0) == n0 + 1
+    assert y.dtype == (torch.float32 if out_fp32 else torch.bfloat16)
+    assert rel_err(y.float(), yr) < (1e-5 if out_fp32 else 6e-3)
+    y.backward(gy.cuda().to(y.dtype))
+    torch.cuda.synchronize()
+    assert rel_err(xd.grad.float(), xr.grad) < 8e-3
+    assert rel_err(mod.weight.grad, wr.grad) < 8e-3
