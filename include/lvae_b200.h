@@ -100,6 +100,7 @@ typedef struct {
   const void* gate_x;
   void* gate_out;
   int gate_act;
+  int gate_skip_h;      /* eval mode: do not store h (y may then be NULL): nothing runs backward */
 } LvaeConvFuse;
 int lvae_conv2d_tc_ex(const void* x, const void* x2, const void* wp, const float* bias, const float* out_scale,
                       const void* res, void* y, void* y2, int nsplit, int B, int H, int W, int Cin, int N, int ksize,

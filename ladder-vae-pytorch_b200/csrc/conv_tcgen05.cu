@@ -55,6 +55,7 @@ struct TcParams {
   // stats_acc (optional) then accumulates the statistics of out
   const __nv_bfloat16* gate_x;
   int gate_act;
+  int gate_skip_h;          // eval mode: h = [a | g] is only staged for the gate pass, never stored (nothing runs backward)
   int tma_store;            // bf16 output, N % 64 == 0, no residual: epilogue stages the tile in smem and stores it with TMA
   long long* dbg;           // optional per-tile clock64 trace of CTA 0 (profiling aid, normally null)
   int8_t dx[TC_MAX_KB], dy[TC_MAX_KB], src[TC_MAX_KB], coff[TC_MAX_KB];   // coff: channel offset / 64 inside the tensor
@@ -562,7 +563,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
             int rem = p0 - c3 * hw;
             c2 = rem / p.W; c1 = rem - c2 * p.W;
           }
-          for (int j = 0; j < p.Npad / 64; ++j) {
+          for (int j = 0; j < p.Npad / 64 && !(FUSE == 3 && p.gate_skip_h); ++j) {
             const bool second = p.y2 != nullptr && j * 64 >= p.nsplit;
             tma_store_4d(second ? &tmY2 : &tmY, smem_u32(sOut + j * TC_STAGE_BYTES), second ? j * 64 - p.nsplit : j * 64, c1, c2, c3);
           }
@@ -735,6 +736,7 @@ struct LvaeConvFuse {
   const void* gate_x;
   void* gate_out;
   int gate_act;
+  int gate_skip_h;
 };
 
 LVAE_API int lvae_conv2d_tc_ex(const void* x, const void* x2, const void* wp, const float* bias, const float* out_scale,
@@ -752,7 +754,7 @@ LVAE_API int lvae_conv2d_tc(const void* x, const void* x2, const void* wp, const
 LVAE_API int lvae_conv2d_tc_ex(const void* x, const void* x2, const void* wp, const float* bias, const float* out_scale,
                                const void* res, void* y, void* y2, int nsplit, int B, int H, int W, int Cin, int N,
                                int ksize, int flip, int out_f32, const LvaeConvFuse* fuse, cudaStream_t stream) {
-  LVAE_REQUIRE(x && wp && y, "conv2d_tc: null pointer");
+  LVAE_REQUIRE(x && wp && (y || (fuse && fuse->gate_out && fuse->gate_skip_h)), "conv2d_tc: null pointer");
   LVAE_REQUIRE(Cin % 64 == 0 && Cin >= 64 && Cin <= 256 && (ksize == 1 || ksize == 3),
                "conv2d_tc: needs a multiple of 64 input channels per tensor and a 1x1 or 3x3 kernel");
   LVAE_REQUIRE(N >= 1 && N <= 256, "conv2d_tc: 1 <= N <= 256");
@@ -778,7 +780,7 @@ LVAE_API int lvae_conv2d_tc_ex(const void* x, const void* x2, const void* wp, co
     if (fuse->gate_out) {
       LVAE_REQUIRE(fuse->gate_x && N == 128 && !y2 && !res && !out_f32 && !p.bnb_acc,
                    "conv2d_tc: the gated-residual epilogue needs N == 128, bf16 output, no residual / split");
-      p.gate_x = (const __nv_bfloat16*)fuse->gate_x; p.gate_act = fuse->gate_act;
+      p.gate_x = (const __nv_bfloat16*)fuse->gate_x; p.gate_act = fuse->gate_act; p.gate_skip_h = fuse->gate_skip_h;
     }
   }
   const int inputs = x2 ? 2 : 1;
@@ -836,7 +838,7 @@ LVAE_API int lvae_conv2d_tc_ex(const void* x, const void* x2, const void* wp, co
   if (p.tma_store) {
     // output maps: same pixel box as the activation tiles (8 x 16 pixels in halo mode), 64 channels per box
     void* const gate_out = (fuse && fuse->gate_out) ? fuse->gate_out : nullptr;
-    for (int which = 0; which < ((y2 || gate_out) ? 2 : 1); ++which) {
+    for (int which = (gate_out && p.gate_skip_h) ? 1 : 0; which < ((y2 || gate_out) ? 2 : 1); ++which) {
       const int ncols = gate_out ? (which ? 64 : N) : (y2 ? (which ? N - nsplit : nsplit) : N);
       cuuint64_t gdim[4] = {(cuuint64_t)ncols, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
       cuuint64_t gstr[3] = {(cuuint64_t)ncols * 2, (cuuint64_t)W * ncols * 2, (cuuint64_t)H * W * ncols * 2};

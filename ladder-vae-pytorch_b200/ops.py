@@ -395,6 +395,7 @@ def _conv_tc(x, x2, wp, bias, out_scale, res, N, ksize, flip, out_f32, nsplit=0,
             gx, gact = gate
             gate_out = torch.empty_like(gx)
             f.gate_x, f.gate_out, f.gate_act = gx.data_ptr(), gate_out.data_ptr(), int(gact)
+            f.gate_skip_h = 0 if _gate_keep_h[0] else 1     # no backward will run (no_grad caller): h = [a | g] is not stored
         if bnb is not None:
             bx, bsave, bgamma, bbeta, bacc, bact = bnb
             f.bnb_x, f.bnb_save, f.bnb_gamma, f.bnb_beta = bx.data_ptr(), bsave.data_ptr(), bgamma.data_ptr(), bbeta.data_ptr()
@@ -679,6 +680,7 @@ BN_STRIPES = 8
 _bn_epoch = [0]
 _whole_block = [True]
 _gate_fused = [os.environ.get("LVAE_GATE_FUSED", "1") != "0"]
+_gate_keep_h = [True]     # set per call by gated_block(): autograd.Function.forward always runs with grad mode off
 
 
 def set_whole_block(flag: bool) -> None:
@@ -848,6 +850,7 @@ def gated_block(x, bn1, conv1, drop1, bn2, conv2, drop2, gate_layer, act_id):
     if m2 is not None:
         m2 = m2.reshape(x.shape[0], -1)
     blk = (bn1, bn2, conv1, conv2, gate_layer.conv, act_id, getattr(gate_layer.nonlin, "act_id", 0))
+    _gate_keep_h[0] = torch.is_grad_enabled()
     out = GatedBlockFn.apply(x, bn1.weight, bn1.bias, conv1.weight, conv1.bias, bn2.weight, bn2.bias, conv2.weight,
                              conv2.bias, gate_layer.conv.weight, gate_layer.conv.bias, m1, m2, blk, x_stats, training)
     if training and bn1._lvae_last_out_stats is not None:
