@@ -519,8 +519,6 @@ def conv_backward_raw(spec: ConvSpec, xn, x2n, weight, bias, out_scale, gyn, nee
             else:
                 assert dx_scale is None
                 gx, gx2 = gcat[..., :C1], gcat[..., C1:]
-    if need_w and os.environ.get("LVAE_EXPERIMENT_SKIP_WGRAD") == "1":
-        need_w = False          # timing experiment only (wrong gradients): how much do the side-stream wgrads cost the main stream?
     if need_w:
         gwbuf, sunk = _param_grad_buffer(weight)
         gbbuf, bsunk = (None, True)
