@@ -287,6 +287,10 @@ class ConvSpec:
         self.pack_s2_scatter = WeightPack(d0, d1, taps, 3) if self.s2_shape else None
 
     def packs(self, bf16: bool):
+        """Packs the engine refreshes in its one batched launch per step.  In the bf16 pipeline the convolutions that run on
+        the tensor cores only need their tcgen05 operand tiles; a CUDA-core fallback (odd image size) re-packs on demand."""
+        if bf16 and self.tc_shape and self.cin % 64 == 0:
+            return [self.pack_tc_fwd, self.pack_tc_bwd]
         out = [self.pack_fwd, self.pack_bwd]
         if bf16 and self.tc_shape:
             out += [self.pack_tc_fwd, self.pack_tc_bwd]
