@@ -73,3 +73,34 @@ def test_error_conventions(libpath):
         ResidualBlock(8, ELU, block_type="bacdbacd", dropout=None)
     with pytest.raises(RuntimeError, match="Unrecognized likelihood"):
         lvae_b200.LadderVAE(1, [4], img_shape=(8, 8), likelihood_form="x", res_block_type="bacdbac", merge_type="residual")
+
+
+def test_conv_spec_routing_and_pack_policy(libpath):
+    """Host-side routing tables (no device work): which convolutions are eligible for the tcgen05 kernels and which packed
+    weight layouts the engine refreshes per step."""
+    import lvae_b200
+    from lvae_b200.lib.nn import Conv2d, ConvTranspose2d
+    res = Conv2d(64, 64, 3, padding=1).spec                       # residual conv
+    gate = Conv2d(64, 128, 1).spec                                # gate conv
+    merge = Conv2d(128, 64, 1).spec                               # two-input merge
+    zout = Conv2d(32, 64, 3, padding=1).spec                      # conv_out of the stochastic block (input padded to 64)
+    stem = Conv2d(3, 64, 5, padding=2, stride=2).spec
+    down = Conv2d(64, 64, 3, padding=1, stride=2).spec
+    up = ConvTranspose2d(64, 64, 3, padding=1, stride=2, output_padding=1).spec
+    up_nopad = ConvTranspose2d(64, 64, 3, padding=1, stride=2).spec
+    assert res.tc_shape and gate.tc_shape and merge.tc_shape and zout.tc_shape
+    assert not stem.tc_shape and not down.tc_shape and not up.tc_shape
+    assert down.s2_shape and up.s2_shape and not up_nopad.s2_shape and not res.s2_shape and not stem.s2_shape
+    # bf16 pipeline: tensor-core convs only refresh their tcgen05 tiles; padded-input and CUDA-core convs keep the generic rows
+    assert [p.mode for p in res.packs(True)] == [2, 3]
+    assert [p.mode for p in gate.packs(True)] == [2, 3]
+    assert sorted(p.mode for p in zout.packs(True)) == [0, 1, 2, 3]
+    assert sorted(p.mode for p in stem.packs(True)) == [0, 1]
+    assert sorted(p.mode for p in down.packs(True)) == [0, 1, 2, 3]
+    assert sorted(p.mode for p in res.packs(False)) == [0, 1]
+    # tcgen05 tile geometry: [tap][k-block][Npad][64]
+    assert res.pack_tc_fwd.rows == 9 * 1 * 64 and gate.pack_tc_fwd.rows == 1 * 1 * 128 and merge.pack_tc_fwd.rows == 1 * 2 * 64
+    # the two orientations of a stride-2 conv: Conv2d (co,ci) forward = gather (N=co), ConvTranspose2d (ci,co) forward = scatter (N=co)
+    assert (down.pack_s2_gather.mode, down.pack_s2_scatter.mode) == (2, 3)
+    assert (up.pack_s2_gather.O, up.pack_s2_gather.I) == (64, 64)
+    assert down.out_hw(16, 16) == (8, 8) and up.out_hw(8, 8) == (16, 16)
