@@ -325,7 +325,7 @@ def main():
                 "e2e": {"value": batch / (e2e_ms * 1e-3), "unit": "images/s with a %d-sample bound" % K,
                         "h2d_bytes_per_step": x_host.numel() * 4, "d2h_bytes_per_step": res_host.numel() * 4},
                 "gpu_launches": launches, "clocks": clocks}
-        if rank == 0 and not args.no_cpu_baseline:
+        if rank == 0 and not args.no_cpu_baseline and world == 1:
             line["cpu_baseline"] = {k: v for k, v in cpu_baseline_iw(32, 3).items() if k != "s_per_forward"}
         if rank == 0:
             print(json.dumps(line), flush=True)
@@ -384,7 +384,7 @@ def main():
             "peak_mem_gb": mem_gb, "loss": final_loss}
     if rank == 0:
         line["roofline"] = conv_roofline(torch, pk, args.dtype)
-        if not args.no_cpu_baseline:
+        if not args.no_cpu_baseline and world == 1:          # the CPU baseline is a single-GPU-run item (rank 0, N = 1 only)
             cb = cpu_baseline_train(cfg_name, 16, 2)
             line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
         print(json.dumps(line), flush=True)
