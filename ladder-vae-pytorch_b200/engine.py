@@ -12,8 +12,7 @@ from __future__ import annotations
 import ctypes
 import math
 import os
-import struct
-from typing import Dict, List, Optional
+from typing import Dict, Optional
 
 import torch
 import torch.distributed as dist

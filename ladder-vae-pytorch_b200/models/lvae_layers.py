@@ -7,8 +7,7 @@ from __future__ import annotations
 import torch
 from torch import nn
 
-from lvae_b200.lib.nn import (Conv2d, ConvTranspose2d, LeakyReLU, ResidualBlock, ResidualGatedBlock, _hooked,
-                              resolve_nonlin)
+from lvae_b200.lib.nn import Conv2d, ConvTranspose2d, LeakyReLU, ResidualBlock, ResidualGatedBlock, _hooked
 from lvae_b200.lib.stochastic import NormalStochasticBlock2d
 
 
