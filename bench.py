@@ -252,7 +252,7 @@ def main():
     import lvae_b200
     from lvae_b200 import _capi
     from lvae_b200.engine import IWEvaluator, TrainEngine
-    from oracle import lvae_oracle as O        # config table only (cpu_baseline leg below times it)
+    from lvae_b200.configs import baseline_config        # product-side config table (the oracle is only the cpu_baseline leg)
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the product has no CPU path")
@@ -264,7 +264,7 @@ def main():
     pk = peaks()
     cfg_name, batch = CONFIGS[args.workload]
     batch = args.batch or batch
-    cfg = O.baseline_config(cfg_name)
+    cfg = baseline_config(cfg_name)
     torch.manual_seed(42)
     lvae_b200.manual_seed(1234 + rank)
     model = lvae_b200.LadderVAE(**cfg.kwargs()).cuda()

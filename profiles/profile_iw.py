@@ -5,7 +5,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 import lvae_b200
 from lvae_b200.engine import IWEvaluator
-from oracle import lvae_oracle as O          # config table only
+from lvae_b200.configs import baseline_config
 from bench import synthetic_batch
 
 ap = argparse.ArgumentParser()
@@ -13,7 +13,7 @@ ap.add_argument("--dtype", default="bf16")
 ap.add_argument("--batch", type=int, default=1000)
 ap.add_argument("--top", type=int, default=24)
 args = ap.parse_args()
-cfg = O.baseline_config("mnist12")
+cfg = baseline_config("mnist12")
 torch.manual_seed(42)
 model = lvae_b200.LadderVAE(**cfg.kwargs()).cuda()
 if args.dtype == "bf16":

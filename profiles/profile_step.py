@@ -11,7 +11,7 @@ import torch  # noqa: E402
 
 import lvae_b200  # noqa: E402
 from lvae_b200.engine import TrainEngine  # noqa: E402
-from oracle import lvae_oracle as O  # noqa: E402  (config table only)
+from lvae_b200.configs import baseline_config
 from bench import synthetic_batch  # noqa: E402
 
 ap = argparse.ArgumentParser()
@@ -24,7 +24,7 @@ ap.add_argument("--top", type=int, default=30)
 ap.add_argument("--hist", default="", help="comma list of kernel-name substrings: print a duration histogram for each")
 args = ap.parse_args()
 
-cfg = O.baseline_config(args.config)
+cfg = baseline_config(args.config)
 torch.manual_seed(42)
 model = lvae_b200.LadderVAE(**cfg.kwargs()).cuda()
 if args.dtype == "bf16":

@@ -4,10 +4,10 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 import lvae_b200
 from lvae_b200.engine import TrainEngine
-from oracle import lvae_oracle as O
+from lvae_b200.configs import baseline_config
 from bench import synthetic_batch
 
-cfg = O.baseline_config("cifar15")
+cfg = baseline_config("cifar15")
 torch.manual_seed(42)
 model = lvae_b200.LadderVAE(**cfg.kwargs()).cuda()
 model.set_compute_dtype(torch.bfloat16)

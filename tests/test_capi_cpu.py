@@ -104,3 +104,21 @@ def test_conv_spec_routing_and_pack_policy(libpath):
     assert (down.pack_s2_gather.mode, down.pack_s2_scatter.mode) == (2, 3)
     assert (up.pack_s2_gather.O, up.pack_s2_gather.I) == (64, 64)
     assert down.out_hw(16, 16) == (8, 8) and up.out_hw(8, 8) == (16, 16)
+
+
+def test_product_config_table_matches_oracle(libpath):
+    """bench.py builds its models from lvae_b200.configs (the product never imports the oracle); the table must stay in
+    step with the oracle's, which is the one pinned against the reference."""
+    import lvae_b200
+    from lvae_b200.configs import baseline_config, baseline_kwargs
+    from oracle import lvae_oracle as O
+    for name in ("mnist3", "mnist12", "cifar15", "celeba20"):
+        ours, ref = baseline_kwargs(name), O.baseline_config(name).kwargs()
+        assert set(ours) == set(ref)
+        for k in ref:
+            a, b = ours[k], ref[k]
+            assert (list(a) == list(b)) if isinstance(b, (list, tuple)) else (a == b), (name, k, a, b)
+        cfg = baseline_config(name)
+        assert cfg.color_ch == ref["color_ch"] and tuple(cfg.img_shape) == tuple(ref["img_shape"]) and cfg.kwargs() == ours
+    model = lvae_b200.LadderVAE(**baseline_kwargs("mnist3"))          # construction needs no device
+    assert len(model.state_dict()) == len(O.param_shapes(O.baseline_config("mnist3"))) or len(model.state_dict()) > 100
