@@ -29,6 +29,8 @@ constexpr int TC_BM = 128;             // pixels per tile
 constexpr int TC_BK = 64;              // channels per k-block (= one 128-byte swizzle row of bf16)
 constexpr int TC_STAGE_BYTES = TC_BM * TC_BK * 2;   // 16 KB
 constexpr int TC_MAX_KB = 36;          // k-blocks per tile: taps x input k-blocks
+constexpr int TC_F32_PITCH = 17;       // floats per row of a warp's 32 x 16 transposition buffer (odd pitch: conflict-free row writes)
+constexpr int TC_F32_STAGE_BYTES = 8 * 32 * TC_F32_PITCH * 4;   // eight epilogue warps
 
 struct TcParams {
   const float* bias;        // [N] or null
@@ -57,6 +59,8 @@ struct TcParams {
   int gate_act;
   int gate_skip_h;          // eval mode: h = [a | g] is only staged for the gate pass, never stored (nothing runs backward)
   int tma_store;            // bf16 output, N % 64 == 0, no residual: epilogue stages the tile in smem and stores it with TMA
+  int f32_stage;            // fp32 output, no residual / split (LVAE_CONV_F32_STAGE=1): each epilogue warp transposes 32 rows x 16
+                            // columns through a private smem buffer, so the global stores are 64-byte row segments
   long long* dbg;           // optional per-tile clock64 trace of CTA 0 (profiling aid, normally null)
   int8_t dx[TC_MAX_KB], dy[TC_MAX_KB], src[TC_MAX_KB], coff[TC_MAX_KB];   // coff: channel offset / 64 inside the tensor
   // stride-2 convolutions (lvae_conv2d_tc_s2): the tile's pixel coordinates are multiplied by in_stride before the tap
@@ -245,7 +249,7 @@ __device__ __forceinline__ void epilogue16(const uint32_t* __restrict__ r, const
 }
 
 // FUSE: 0 plain epilogue, 1 output statistics (stats_acc), 2 BatchNorm-backward sums (bnb_*), 3 gated residual output
-// (+ its statistics).  A template parameter so
+// (+ its statistics), 4 plain epilogue with warp-transposed (coalesced) fp32 stores (p.f32_stage).  A template parameter so
 // that the plain kernel carries no accumulator registers (the 10-warp CTA caps ptxas at 168 registers per thread).
 template <int FUSE>
 __global__ void __launch_bounds__(TC_THREADS, 1)
@@ -261,7 +265,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
   uint8_t* sA = sW + ((p.n_kb * wbytes_kb + 1023) & ~1023);  // n_stages * 16 KB
   const int stage_bytes = p.halo ? p.stage_bytes : TC_STAGE_BYTES;
   uint8_t* sOut = sA + p.n_stages * stage_bytes;             // (N/64) x 16 KB output staging (TMA-store epilogue only)
-  uint64_t* bars = (uint64_t*)(sOut + (p.tma_store ? (p.Npad / 64 + (FUSE == 3 ? 1 : 0)) * TC_STAGE_BYTES : 0));
+  uint64_t* bars = (uint64_t*)(sOut + (p.tma_store ? (p.Npad / 64 + (FUSE == 3 ? 1 : 0)) * TC_STAGE_BYTES
+                                                   : (FUSE == 4 ? TC_F32_STAGE_BYTES : 0)));
   // barrier layout: [0..S) full, [S..2S) empty, 2S: weights, 2S+1..2S+2: tmem_full[2], 2S+3..2S+4: tmem_empty[2]
   const int S = p.n_stages;
   uint32_t* tmem_slot = (uint32_t*)(bars + 2 * S + 5);
@@ -445,11 +450,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
       return (long long)tile * TC_BM + ew * 16;
     };
     const int rstep = p.halo ? p.W - 8 : 0;                        // extra pixels skipped after 8 rows of the staged tile
-    uint32_t xq[FUSE >= 2 ? 16 : 1];                               // BatchNorm input / residual input of this tile (channels 2l, 2l+1)
+    uint32_t xq[(FUSE == 2 || FUSE == 3) ? 16 : 1];                               // BatchNorm input / residual input of this tile (channels 2l, 2l+1)
     auto load_xq = [&](long long rb) {
       const uint32_t* xb = reinterpret_cast<const uint32_t*>((FUSE == 3 ? p.gate_x : p.bnb_x) + rb * 64) + lane;
 #pragma unroll
-      for (int i = 0; i < (FUSE >= 2 ? 16 : 1); ++i) {
+      for (int i = 0; i < ((FUSE == 2 || FUSE == 3) ? 16 : 1); ++i) {
         const int off = i + (i >> 3) * rstep;
         xq[i] = rb + off < p.M_total ? __ldg(xb + off * 32) : 0u;
       }
@@ -475,7 +480,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
       const int b = valid ? (int)(m / hw) : 0;
       const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * p.Npad);
       const float* scale_row = p.out_scale ? p.out_scale + (long long)b * p.N : nullptr;
-      if (FUSE != 0 || p.tma_store) {
+      if ((FUSE != 0 && FUSE != 4) || p.tma_store) {
         // ---- TMEM -> registers (bias, Dropout2d scale, bf16 pack), release the accumulator, stage in smem, TMA store ----
         constexpr int NCH = (FUSE == 1 || FUSE == 2) ? 1 : 2;       // fused reductions: N = 64, one chunk per thread
         uint4 packed[NCH][4];
@@ -583,7 +588,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
             tma_store_4d(&tmY2, smem_u32(sGate), 0, c1, c2, c3);
             asm volatile("cp.async.bulk.commit_group;" ::: "memory");
           }
-        } else if (FUSE != 0) {
+        } else if (FUSE == 1 || FUSE == 2) {
           // second pass over the staged tile (values as stored, bf16-rounded); the TMA store only reads it concurrently
           const int nrows = p.halo ? 128 : (int)min((long long)128, p.M_total - (long long)tile * TC_BM);   // rows past the end contribute nothing
           const bool elu = p.bnb_act == ACT_ELU;                     // the model's default: branch-free fast path
@@ -617,6 +622,47 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         if (p.dbg && blockIdx.x == 0 && warp == 2 && lane == 0) p.dbg[it * 8 + 5] = clock64();
         continue;
       }
+      if (FUSE == 4) {
+        // ---- fp32 output, coalesced: a thread's 16 columns of its row go to the warp's [32][17] buffer, then lane l writes
+        // column (l & 15) of rows 2i + (l >> 4): every warp store covers two 64-byte row segments (full sectors) instead
+        // of 32 scattered 16-byte pieces ----
+        float* wbuf = reinterpret_cast<float*>(sOut) + (warp - 2) * (32 * TC_F32_PITCH);
+        const int m_i = valid ? (int)m : -1;
+        float* const yf = (float*)p.y;
+        for (int c0 = 32 * half; c0 < p.Npad; c0 += 64) {
+          uint32_t r[32];
+          const bool two = c0 + 32 <= p.Npad;
+          if (two) tmem_ld32_nowait(taddr + (uint32_t)c0, r);
+          else tmem_ld16_nowait(taddr + (uint32_t)c0, r);
+          tmem_wait_ld();
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const int c = c0 + 16 * h;
+            if ((h == 1 && !two) || c >= p.N) break;             // warp-uniform
+            const int nvalid = min(16, p.N - c);
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              float v = __uint_as_float(r[16 * h + j]) + sbias[c + j];
+              if (scale_row && j < nvalid) v *= __ldg(scale_row + c + j);
+              wbuf[lane * TC_F32_PITCH + j] = v;
+            }
+            __syncwarp();
+            const int cl = lane & 15;
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              const int rr = 2 * i + (lane >> 4);
+              const int mr = __shfl_sync(0xffffffffu, m_i, rr);
+              if (mr >= 0 && cl < nvalid) yf[(size_t)mr * p.N + c + cl] = wbuf[rr * TC_F32_PITCH + cl];
+            }
+            __syncwarp();
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (p.dbg && blockIdx.x == 0 && warp == 2 && lane == 0) p.dbg[it * 8 + 5] = clock64();
+        if (lane == 0) mbar_arrive(BAR(2 * S + 3 + buf));
+        continue;
+      }
       for (int c0 = 32 * half; c0 < p.Npad; c0 += 64) {
         uint32_t r[32];
         const bool two = c0 + 32 <= p.Npad;
@@ -645,7 +691,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
       if (p.dbg && blockIdx.x == 0 && warp == 2 && lane == 0) p.dbg[it * 8 + 5] = clock64();
       if (lane == 0) mbar_arrive(BAR(2 * S + 3 + buf));
     }
-    if (FUSE != 0) {
+    if (FUSE != 0 && FUSE != 4) {
       // combine the eight row groups per channel: one double atomic per channel and statistic per CTA
       sred[(0 * 8 + ew) * 64 + 2 * lane] = ra0; sred[(0 * 8 + ew) * 64 + 2 * lane + 1] = ra1;
       sred[(1 * 8 + ew) * 64 + 2 * lane] = rb0; sred[(1 * 8 + ew) * 64 + 2 * lane + 1] = rb1;
@@ -789,7 +835,10 @@ LVAE_API int lvae_conv2d_tc_ex(const void* x, const void* x2, const void* wp, co
   static int tst_env = -1;
   if (tst_env < 0) { const char* e = getenv("LVAE_CONV_TMA_STORE"); tst_env = e ? atoi(e) : 1; }
   p.tma_store = (tst_env && !out_f32 && N % 64 == 0 && N <= 128 && !res && (!y2 || nsplit % 64 == 0)) ? 1 : 0;
-  const int out_stage = p.tma_store ? (p.Npad / 64 + (p.gate_x ? 1 : 0)) * TC_STAGE_BYTES : 0;
+  static int f32s_env = -1;
+  if (f32s_env < 0) { const char* e = getenv("LVAE_CONV_F32_STAGE"); f32s_env = e ? atoi(e) : 0; }
+  p.f32_stage = (f32s_env && out_f32 && !res && !y2 && !p.tma_store) ? 1 : 0;
+  const int out_stage = p.tma_store ? (p.Npad / 64 + (p.gate_x ? 1 : 0)) * TC_STAGE_BYTES : (p.f32_stage ? TC_F32_STAGE_BYTES : 0);
   LVAE_REQUIRE(!p.gate_x || p.tma_store, "conv2d_tc: the gated-residual epilogue needs the TMA-store path");
   LVAE_REQUIRE(!(p.stats_acc || p.bnb_acc) || (p.tma_store && (N == 64 || p.gate_x) && !y2),
                "conv2d_tc: fused reductions need the TMA-store path (bf16 output, N == 64, no residual, no split)");
@@ -850,6 +899,7 @@ LVAE_API int lvae_conv2d_tc_ex(const void* x, const void* x2, const void* wp, co
     if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024));
     if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024));
     if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tc_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024));
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tc_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024));
     if (e != cudaSuccess) { lvae_set_error("conv2d_tc: cannot raise dynamic smem: %s", cudaGetErrorString(e)); return LVAE_ERR_CUDA; }
     attr_smem = 227 * 1024;
   }
@@ -858,6 +908,7 @@ LVAE_API int lvae_conv2d_tc_ex(const void* x, const void* x2, const void* wp, co
   if (p.gate_x) lvae_launch(conv_tc_kernel<3>, grid, TC_THREADS, smem, stream, tmA0, tmA1, tmW, tmY, tmY2, p);
   else if (p.stats_acc) lvae_launch(conv_tc_kernel<1>, grid, TC_THREADS, smem, stream, tmA0, tmA1, tmW, tmY, tmY2, p);
   else if (p.bnb_acc) lvae_launch(conv_tc_kernel<2>, grid, TC_THREADS, smem, stream, tmA0, tmA1, tmW, tmY, tmY2, p);
+  else if (p.f32_stage) lvae_launch(conv_tc_kernel<4>, grid, TC_THREADS, smem, stream, tmA0, tmA1, tmW, tmY, tmY2, p);
   else lvae_launch(conv_tc_kernel<0>, grid, TC_THREADS, smem, stream, tmA0, tmA1, tmW, tmY, tmY2, p);
   LVAE_COUNT_LAUNCH();
   LVAE_CHECK_LAUNCH("conv2d_tc");
