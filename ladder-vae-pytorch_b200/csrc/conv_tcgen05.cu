@@ -21,6 +21,7 @@
 #include <cuda.h>
 #include <stdlib.h>
 #include <string.h>
+#include <mutex>
 
 namespace {
 
@@ -62,6 +63,7 @@ struct TcParams {
   int f32_stage;            // fp32 output, no residual / split (LVAE_CONV_F32_STAGE=1): each epilogue warp transposes 32 rows x 16
                             // columns through a private smem buffer, so the global stores are 64-byte row segments
   long long* dbg;           // optional per-tile clock64 trace of CTA 0 (profiling aid, normally null)
+  int* sched;               // dynamic tile scheduler (DYN kernels): {next tile, finished CTAs}, zero between launches
   int8_t dx[TC_MAX_KB], dy[TC_MAX_KB], src[TC_MAX_KB], coff[TC_MAX_KB];   // coff: channel offset / 64 inside the tensor
   // stride-2 convolutions (lvae_conv2d_tc_s2): the tile's pixel coordinates are multiplied by in_stride before the tap
   // offset is added (the input tensor map then traverses with the same element stride), and k-block kb reads weight
@@ -251,7 +253,11 @@ __device__ __forceinline__ void epilogue16(const uint32_t* __restrict__ r, const
 // FUSE: 0 plain epilogue, 1 output statistics (stats_acc), 2 BatchNorm-backward sums (bnb_*), 3 gated residual output
 // (+ its statistics), 4 plain epilogue with warp-transposed (coalesced) fp32 stores (p.f32_stage).  A template parameter so
 // that the plain kernel carries no accumulator registers (the 10-warp CTA caps ptxas at 168 registers per thread).
-template <int FUSE>
+// DYN (LVAE_CONV_DYNAMIC=1): tiles are not assigned round-robin but drawn from a global counter by the producer warp and
+// handed to the MMA / epilogue warps through a shared-memory ring, so a CTA that reaches its SM late (the SMs are shared
+// with the weight-gradient kernels of the side streams) takes fewer tiles instead of stretching the launch.
+constexpr int TC_RING = 4;
+template <int FUSE, bool DYN>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmY,
@@ -274,6 +280,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
   float* sred = sbias + 256;                                  // 2 statistics x 8 warps x 64 channels (fused reductions)
   const uint32_t bar0 = smem_u32(bars);
   auto BAR = [&](int i) { return bar0 + 8u * (uint32_t)i; };
+  int* const ring_ids = (int*)(sred + 2 * 8 * 64);               // TC_RING tile indices (DYN only)
+  const uint32_t rbar0 = smem_u32(ring_ids + TC_RING);           // TC_RING "published" + TC_RING "consumed" barriers
+  auto RFULL = [&](int i) { return rbar0 + 8u * (uint32_t)i; };
+  auto REMPTY = [&](int i) { return rbar0 + 8u * (uint32_t)(TC_RING + i); };
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_tiles = p.halo ? (p.M_total / (p.H * p.W)) * p.tiles_per_img : (p.M_total + TC_BM - 1) / TC_BM;
@@ -291,6 +301,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     mbar_init(BAR(2 * S + 2), 1);
     mbar_init(BAR(2 * S + 3), 8);      // one arrive per epilogue warp
     mbar_init(BAR(2 * S + 4), 8);
+    if (DYN) {
+      for (int i = 0; i < TC_RING; ++i) {
+        mbar_init(RFULL(i), 1);          // the producer's elected lane
+        mbar_init(REMPTY(i), 9);         // MMA warp + eight epilogue warps
+      }
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 0) {
@@ -314,6 +330,31 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
   const uint32_t tmem_base = *tmem_slot;
   pdl_wait();          // activations / residual / dropout mask come from the previous kernels
   pdl_launch();
+  // tile sequence of this CTA (warp-converged calls): round-robin, or drawn from / read out of the ring
+  int ring_i = 0;
+  uint32_t ring_ph = 0;
+  auto draw_tile = [&]() -> int {                                 // producer warp
+    int t = 0;
+    if (lane == 0) t = atomicAdd(p.sched, 1);
+    t = __shfl_sync(0xffffffffu, t, 0);
+    if (t >= n_tiles) t = -1;
+    mbar_wait(REMPTY(ring_i), ring_ph ^ 1);
+    if (lane == 0) {
+      ring_ids[ring_i] = t;
+      mbar_arrive(RFULL(ring_i));                                 // release: the index is visible to whoever sees the phase flip
+    }
+    __syncwarp();
+    if (++ring_i == TC_RING) { ring_i = 0; ring_ph ^= 1; }
+    return t;
+  };
+  auto take_tile = [&]() -> int {                                 // MMA warp, epilogue warps
+    mbar_wait(RFULL(ring_i), ring_ph);
+    const int t = ring_ids[ring_i];
+    __syncwarp();
+    if (lane == 0) mbar_arrive(REMPTY(ring_i));
+    if (++ring_i == TC_RING) { ring_i = 0; ring_ph ^= 1; }
+    return t;
+  };
 
   if (warp == 0) {
     // ===================== TMA producer (whole warp loops, one elected lane issues) =====================
@@ -321,7 +362,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
       int stage = 0;
       uint32_t phase = 0;
       const int hw = p.H * p.W;
-      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+      for (int tile = DYN ? draw_tile() : (int)blockIdx.x; DYN ? tile >= 0 : tile < n_tiles;
+           tile = DYN ? draw_tile() : tile + (int)gridDim.x) {
         if (p.halo) {
           int n0 = tile / p.tiles_per_img;
           int r = tile - n0 * p.tiles_per_img;
@@ -367,7 +409,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
-      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+      for (int tile = DYN ? take_tile() : (int)blockIdx.x; DYN ? tile >= 0 : tile < n_tiles;
+           tile = DYN ? take_tile() : tile + (int)gridDim.x, ++it) {
         const int buf = it & 1;
         const uint32_t use = (uint32_t)(it >> 1);
         mbar_wait(BAR(2 * S + 3 + buf), (use & 1) ^ 1);      // epilogue drained this accumulator
@@ -460,7 +503,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
       }
     };
     int it = 0;
-    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+    for (int tile = DYN ? take_tile() : (int)blockIdx.x; DYN ? tile >= 0 : tile < n_tiles;
+         tile = DYN ? take_tile() : tile + (int)gridDim.x, ++it) {
       const int buf = it & 1;
       const uint32_t use = (uint32_t)(it >> 1);
       if (p.dbg && blockIdx.x == 0 && warp == 2 && lane == 0) p.dbg[it * 8 + 3] = clock64();
@@ -713,6 +757,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
   if (warp == 1) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(p.tmem_cols) : "memory");
   }
+  if (DYN && threadIdx.x == 0) {
+    // this CTA drew its last index before the barrier above; the last CTA to get here re-arms the counters for the next launch
+    const int done = atomicAdd(p.sched + 1, 1);
+    if (done == (int)gridDim.x - 1) {
+      p.sched[0] = 0;
+      p.sched[1] = 0;
+      __threadfence();
+    }
+  }
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
@@ -731,6 +784,36 @@ EncodeTiledFn get_encode() {
 }
 
 long long* g_tc_dbg = nullptr;
+
+// Counters of the dynamic tile scheduler: one {next tile, finished CTAs} pair per stream that launches DYN kernels (kernels of
+// one stream never overlap; the kernel itself re-arms its pair).  Allocated on first use outside stream capture -- the
+// engines run eager warm-up steps before they capture; until then (or beyond 32 streams) launches keep the static schedule.
+int* tc_sched_slot(cudaStream_t stream) {
+  static std::mutex mu;
+  static int* base = nullptr;
+  static bool failed = false;
+  static cudaStream_t keys[32];
+  static int n = 0;
+  std::lock_guard<std::mutex> lock(mu);
+  if (failed) return nullptr;
+  cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+  if (cudaStreamIsCapturing(stream, &cs) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+  if (!base) {
+    if (cs != cudaStreamCaptureStatusNone) return nullptr;
+    if (cudaMalloc(&base, 32 * 2 * sizeof(int)) != cudaSuccess || cudaMemset(base, 0, 32 * 2 * sizeof(int)) != cudaSuccess ||
+        cudaDeviceSynchronize() != cudaSuccess) {
+      cudaGetLastError();
+      failed = true;
+      base = nullptr;
+      return nullptr;
+    }
+  }
+  for (int i = 0; i < n; ++i)
+    if (keys[i] == stream) return base + 2 * i;
+  if (n == 32) return nullptr;
+  keys[n] = stream;
+  return base + 2 * (n++);
+}
 
 int pow2_floor_le(int v, int cap) {
   int r = 1;
@@ -895,21 +978,37 @@ LVAE_API int lvae_conv2d_tc_ex(const void* x, const void* x2, const void* wp, co
   }
   static size_t attr_smem = 0;
   if (smem > attr_smem) {
-    cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024));
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024));
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024));
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tc_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024));
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tc_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024));
+    const int cap = 227 * 1024;
+    cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tc_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tc_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tc_kernel<3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tc_kernel<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tc_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tc_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tc_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tc_kernel<3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tc_kernel<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap);
     if (e != cudaSuccess) { lvae_set_error("conv2d_tc: cannot raise dynamic smem: %s", cudaGetErrorString(e)); return LVAE_ERR_CUDA; }
     attr_smem = 227 * 1024;
   }
   const int n_tiles = p.halo ? B * p.tiles_per_img : (p.M_total + TC_BM - 1) / TC_BM;
   const int grid = n_tiles < lvae_num_sms() ? n_tiles : lvae_num_sms();
-  if (p.gate_x) lvae_launch(conv_tc_kernel<3>, grid, TC_THREADS, smem, stream, tmA0, tmA1, tmW, tmY, tmY2, p);
-  else if (p.stats_acc) lvae_launch(conv_tc_kernel<1>, grid, TC_THREADS, smem, stream, tmA0, tmA1, tmW, tmY, tmY2, p);
-  else if (p.bnb_acc) lvae_launch(conv_tc_kernel<2>, grid, TC_THREADS, smem, stream, tmA0, tmA1, tmW, tmY, tmY2, p);
-  else if (p.f32_stage) lvae_launch(conv_tc_kernel<4>, grid, TC_THREADS, smem, stream, tmA0, tmA1, tmW, tmY, tmY2, p);
-  else lvae_launch(conv_tc_kernel<0>, grid, TC_THREADS, smem, stream, tmA0, tmA1, tmW, tmY, tmY2, p);
+  static int dyn_env = -1;
+  if (dyn_env < 0) { const char* e = getenv("LVAE_CONV_DYNAMIC"); dyn_env = e ? atoi(e) : 0; }
+  p.sched = (dyn_env && n_tiles > grid) ? tc_sched_slot(stream) : nullptr;     // one tile per CTA: nothing to balance
+  if (p.sched) {
+    p.dbg = nullptr;
+    if (p.gate_x) lvae_launch(conv_tc_kernel<3, true>, grid, TC_THREADS, smem, stream, tmA0, tmA1, tmW, tmY, tmY2, p);
+    else if (p.stats_acc) lvae_launch(conv_tc_kernel<1, true>, grid, TC_THREADS, smem, stream, tmA0, tmA1, tmW, tmY, tmY2, p);
+    else if (p.bnb_acc) lvae_launch(conv_tc_kernel<2, true>, grid, TC_THREADS, smem, stream, tmA0, tmA1, tmW, tmY, tmY2, p);
+    else if (p.f32_stage) lvae_launch(conv_tc_kernel<4, true>, grid, TC_THREADS, smem, stream, tmA0, tmA1, tmW, tmY, tmY2, p);
+    else lvae_launch(conv_tc_kernel<0, true>, grid, TC_THREADS, smem, stream, tmA0, tmA1, tmW, tmY, tmY2, p);
+  } else if (p.gate_x) lvae_launch(conv_tc_kernel<3, false>, grid, TC_THREADS, smem, stream, tmA0, tmA1, tmW, tmY, tmY2, p);
+  else if (p.stats_acc) lvae_launch(conv_tc_kernel<1, false>, grid, TC_THREADS, smem, stream, tmA0, tmA1, tmW, tmY, tmY2, p);
+  else if (p.bnb_acc) lvae_launch(conv_tc_kernel<2, false>, grid, TC_THREADS, smem, stream, tmA0, tmA1, tmW, tmY, tmY2, p);
+  else if (p.f32_stage) lvae_launch(conv_tc_kernel<4, false>, grid, TC_THREADS, smem, stream, tmA0, tmA1, tmW, tmY, tmY2, p);
+  else lvae_launch(conv_tc_kernel<0, false>, grid, TC_THREADS, smem, stream, tmA0, tmA1, tmW, tmY, tmY2, p);
   LVAE_COUNT_LAUNCH();
   LVAE_CHECK_LAUNCH("conv2d_tc");
   return LVAE_OK;
@@ -937,7 +1036,7 @@ LVAE_API int lvae_conv2d_tc_s2(const void* x, const void* wp, const float* bias,
   const int Cin = 64, Hb = 2 * Hg, Wb = 2 * Wg;               // the bigger grid
   static size_t attr_smem = 0;
   if (!attr_smem) {
-    cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024));
+    cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024));
     if (e != cudaSuccess) { lvae_set_error("conv2d_tc_s2: cannot raise dynamic smem: %s", cudaGetErrorString(e)); return LVAE_ERR_CUDA; }
     attr_smem = 227 * 1024;
   }
@@ -1005,7 +1104,7 @@ LVAE_API int lvae_conv2d_tc_s2(const void* x, const void* wp, const float* bias,
     }
     const int n_tiles = (p.M_total + TC_BM - 1) / TC_BM;
     const int grid = n_tiles < lvae_num_sms() ? n_tiles : lvae_num_sms();
-    lvae_launch(conv_tc_kernel<0>, grid, TC_THREADS, smem, stream, tmA, tmA, tmW, tmY, tmY2, p);
+    lvae_launch(conv_tc_kernel<0, false>, grid, TC_THREADS, smem, stream, tmA, tmA, tmW, tmY, tmY2, p);
     LVAE_COUNT_LAUNCH();
     LVAE_CHECK_LAUNCH("conv2d_tc_s2");
   }
