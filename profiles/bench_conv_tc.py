@@ -17,10 +17,11 @@ import ctypes  # noqa: E402
 shapes = [(int(os.environ.get("HW", "16")), 3, 64)] if one else [(32, 3, 64), (16, 3, 64), (8, 3, 64), (4, 3, 64), (16, 1, 128)] if "--wgrad" in sys.argv else [(32, 3, 64), (16, 3, 64), (8, 3, 64), (4, 3, 64), (2, 3, 64), (16, 1, 128), (32, 3, 100)]
 s = torch.cuda.current_stream()
 for HW, k, N in shapes:
-    per = B * HW * HW * (C + N) * 2
+    f32_out = N == 100                       # the DMoL head writes fp32 likelihood parameters (as in the model)
+    per = B * HW * HW * (C * 2 + N * (4 if f32_out else 2))
     nbuf = max(2, int(300e6 // per) + 1)
     xs = [torch.randn(B, HW, HW, C, device="cuda").to(torch.bfloat16) for _ in range(nbuf)]
-    ys = [torch.empty(B, HW, HW, N, device="cuda", dtype=torch.bfloat16) for _ in range(nbuf)]
+    ys = [torch.empty(B, HW, HW, N, device="cuda", dtype=torch.float32 if f32_out else torch.bfloat16) for _ in range(nbuf)]
     w = torch.randn(N, C, k, k, device="cuda") / 24
     wp = ops.WeightPack(N, C, k * k, 2).get(w, torch.bfloat16)
     bias = torch.zeros(N, device="cuda")
@@ -54,7 +55,7 @@ for HW, k, N in shapes:
         if fuse_mode and N == 64:
             return launch_fused(i)
         _capi.call("lvae_conv2d_tc", xs[i % nbuf].data_ptr(), None, wp.data_ptr(), bias.data_ptr(), None, None,
-                   ys[i % nbuf].data_ptr(), None, 0, B, HW, HW, C, N, k, 0, 0, torch.cuda.current_stream().cuda_stream)
+                   ys[i % nbuf].data_ptr(), None, 0, B, HW, HW, C, N, k, 0, 1 if f32_out else 0, torch.cuda.current_stream().cuda_stream)
     launch(0)
     torch.cuda.synchronize()
     if one:
