@@ -155,6 +155,51 @@ __device__ __forceinline__ uint32_t elect_one() {
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
+// ---- CTA pair (cta_group::2, PAIR kernels): two CTAs of a cluster run ONE tcgen05.mma of M = 256 -- each CTA contributes its
+// own 128-pixel A tile and its own TMEM accumulator, and HALF of the B (weight) rows, so a CTA reads 4 KB + 1 KB instead of
+// 4 KB + 2 KB of shared memory per MMA.  Only the even CTA (the leader) issues MMAs; TMA loads of both CTAs complete on the
+// leader's barriers, tcgen05.commit multicasts its arrivals to both CTAs.
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+// shared::cluster address of the same shared-memory offset in CTA `rank` of this cluster
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t saddr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_bar) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_bar) : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tma_load_4d_pair(uint32_t dst, const CUtensorMap* tm, uint32_t leader_bar, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(dst), "l"(tm), "r"(leader_bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap* tm, uint32_t leader_bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(tm), "r"(leader_bar), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void umma_bf16_pair(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  const uint32_t z = 0;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, {%5, %5, %5, %5, %5, %5, %5, %5}, p;\n\t}"
+      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(z) : "memory");
+}
+// arrive on the barrier at this shared-memory offset in BOTH CTAs of the pair once the MMAs issued so far have retired
+__device__ __forceinline__ void umma_commit_pair(uint32_t bar) {
+  const uint16_t mask = 3;
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"(mask) : "memory");
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
@@ -257,7 +302,8 @@ __device__ __forceinline__ void epilogue16(const uint32_t* __restrict__ r, const
 // handed to the MMA / epilogue warps through a shared-memory ring, so a CTA that reaches its SM late (the SMs are shared
 // with the weight-gradient kernels of the side streams) takes fewer tiles instead of stretching the launch.
 constexpr int TC_RING = 4;
-template <int FUSE, bool DYN>
+// PAIR (LVAE_CONV_CTA2=1; halo mode, N == 64, an even number of tiles): CTA pairs on cta_group::2, see the helpers above.
+template <int FUSE, bool DYN, bool PAIR = false>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmY,
@@ -266,7 +312,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
   // 1024-byte alignment for the 128B swizzle atoms
   // (offset arithmetic on the __shared__ array, not on a uintptr_t: the compiler keeps the shared address space)
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  const int wbytes_kb = p.Npad * 128;                        // one k-block of weights
+  const int wbytes_kb = (PAIR ? p.Npad / 2 : p.Npad) * 128;  // one k-block of weights (a CTA pair holds half of the rows each)
   uint8_t* sW = smem;                                        // n_kb * Npad * 128
   uint8_t* sA = sW + ((p.n_kb * wbytes_kb + 1023) & ~1023);  // n_stages * 16 KB
   const int stage_bytes = p.halo ? p.stage_bytes : TC_STAGE_BYTES;
@@ -299,8 +345,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     mbar_init(BAR(2 * S), 1);
     mbar_init(BAR(2 * S + 1), 1);
     mbar_init(BAR(2 * S + 2), 1);
-    mbar_init(BAR(2 * S + 3), 8);      // one arrive per epilogue warp
-    mbar_init(BAR(2 * S + 4), 8);
+    mbar_init(BAR(2 * S + 3), PAIR ? 16 : 8);      // one arrive per epilogue warp (of both CTAs of a pair, on the leader)
+    mbar_init(BAR(2 * S + 4), PAIR ? 16 : 8);
     if (DYN) {
       for (int i = 0; i < TC_RING; ++i) {
         mbar_init(RFULL(i), 1);          // the producer's elected lane
@@ -309,7 +355,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 0) {
+  const uint32_t pair_rank = PAIR ? cluster_ctarank() : 0u;
+  // shared::cluster address, in the pair's leader, of the barrier at this CTA's offset `bar`
+  auto LEADER = [&](uint32_t bar) { return mapa_u32(bar, 0u); };
+  if (!PAIR && warp == 0) {
     __syncwarp();
     // weights were packed many kernels ago: fetch them before waiting on the previous kernel (PDL prologue)
     if (elect_one()) {
@@ -321,12 +370,29 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
   }
   for (int i = threadIdx.x; i < p.Npad; i += TC_THREADS) sbias[i] = (p.bias && i < p.N) ? p.bias[i] : 0.f;
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(p.tmem_cols) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if (PAIR) {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(p.tmem_cols) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(p.tmem_cols) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
   }
   tc_fence_before();
-  __syncthreads();
+  if (PAIR) cluster_sync_all();          // the peer's barriers are initialised before anything signals them
+  else __syncthreads();
   tc_fence_after();
+  if (PAIR && warp == 0) {
+    // both CTAs' halves of the weights complete on the leader's barrier (only the leader's MMA warp waits for them)
+    if (elect_one()) {
+      if (pair_rank == 0) mbar_expect_tx(BAR(2 * S), (uint32_t)(2 * p.n_kb * wbytes_kb));
+      const uint32_t lbar = LEADER(BAR(2 * S));
+      for (int kb = 0; kb < p.n_kb; ++kb)
+        tma_load_2d_pair(smem_u32(sW + kb * wbytes_kb), &tmW, lbar, 0,
+                         (p.use_wblk ? p.wblk[kb] : kb) * p.Npad + (int)pair_rank * (p.Npad / 2));
+    }
+    __syncwarp();
+  }
   const uint32_t tmem_base = *tmem_slot;
   pdl_wait();          // activations / residual / dropout mask come from the previous kernels
   pdl_launch();
@@ -371,8 +437,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
           mbar_wait(BAR(S + stage), phase ^ 1);
           if (p.dbg && blockIdx.x == 0 && lane == 0) p.dbg[(tile / gridDim.x) * 8 + 6] = clock64();
           if (elect_one()) {
-            mbar_expect_tx(BAR(stage), (uint32_t)stage_bytes);
-            tma_load_4d(smem_u32(sA + stage * stage_bytes), &tmA0, BAR(stage), 0, tx * 8 - 1, ty * 16 - 1, n0);
+            if (PAIR) {
+              // the leader's barrier collects both CTAs' tiles (the peer's bytes may land before the leader has armed it)
+              if (pair_rank == 0) mbar_expect_tx(BAR(stage), (uint32_t)(2 * stage_bytes));
+              tma_load_4d_pair(smem_u32(sA + stage * stage_bytes), &tmA0, LEADER(BAR(stage)), 0, tx * 8 - 1, ty * 16 - 1, n0);
+            } else {
+              mbar_expect_tx(BAR(stage), (uint32_t)stage_bytes);
+              tma_load_4d(smem_u32(sA + stage * stage_bytes), &tmA0, BAR(stage), 0, tx * 8 - 1, ty * 16 - 1, n0);
+            }
           }
           __syncwarp();
           if (++stage == S) { stage = 0; phase ^= 1; }
@@ -396,13 +468,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         }
       }
     }
-  } else if (warp == 1) {
-    // ===================== MMA issuer =====================
+  } else if (warp == 1 && pair_rank == 0) {
+    // ===================== MMA issuer (pair mode: the leader CTA only) =====================
     // The whole warp runs the loop (converged); one elected lane issues tcgen05.mma / tcgen05.commit, so ptxas keeps
     // descriptors and the TMEM address in uniform registers.
     {
       // instruction descriptor: D fp32, A/B bf16, both K-major, M = 128, N = Npad
-      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.Npad >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.Npad >> 3) << 17) | ((uint32_t)((PAIR ? 2 * TC_BM : TC_BM) >> 4) << 24);
       const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
       mbar_wait(BAR(2 * S), 0);
       tc_fence_after();
@@ -429,11 +501,18 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
               const uint64_t adesc = umma_desc_k_sw128_shifted(a_start, 2048, p.bo_mode);
               const uint64_t bdesc = umma_desc_k_sw128(smem_u32(sW + kb * wbytes_kb));
 #pragma unroll
-              for (int k = 0; k < TC_BK / 16; ++k)
-                umma_bf16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (uint32_t)((kb | k) != 0));
+              for (int k = 0; k < TC_BK / 16; ++k) {
+                if (PAIR) umma_bf16_pair(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (uint32_t)((kb | k) != 0));
+                else umma_bf16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (uint32_t)((kb | k) != 0));
+              }
             }
-            umma_commit(BAR(S + stage));
-            umma_commit(BAR(2 * S + 1 + buf));
+            if (PAIR) {
+              umma_commit_pair(BAR(S + stage));           // both CTAs' producers may refill this stage
+              umma_commit_pair(BAR(2 * S + 1 + buf));     // both CTAs' epilogues may drain their halves of the accumulator
+            } else {
+              umma_commit(BAR(S + stage));
+              umma_commit(BAR(2 * S + 1 + buf));
+            }
           }
           __syncwarp();
           if (++stage == S) { stage = 0; phase ^= 1; }
@@ -460,7 +539,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         __syncwarp();
       }
     }
-  } else {
+  } else if (warp >= 2) {
     // ===================== epilogue (8 warps: quadrant x column half) =====================
     const int quad = warp & 3;                                 // TMEM lane quadrant this warp may read
     const int half = (warp - 2) >> 2;                          // which 32-column chunks (even / odd) this warp drains
@@ -555,7 +634,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         }
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(BAR(2 * S + 3 + buf));          // accumulator free again: next-but-one tile may start
+        if (lane == 0) { if (PAIR) mbar_arrive_cluster(LEADER(BAR(2 * S + 3 + buf))); else mbar_arrive(BAR(2 * S + 3 + buf)); }          // accumulator free again: next-but-one tile may start
         if (FUSE == 3) load_xq(rbase);                               // residual input rows (in flight across the staging barriers)
         // the previous tile's TMA store must have finished reading the staging buffer
         if (threadIdx.x == 64) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
@@ -704,7 +783,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         tc_fence_before();
         __syncwarp();
         if (p.dbg && blockIdx.x == 0 && warp == 2 && lane == 0) p.dbg[it * 8 + 5] = clock64();
-        if (lane == 0) mbar_arrive(BAR(2 * S + 3 + buf));
+        if (lane == 0) { if (PAIR) mbar_arrive_cluster(LEADER(BAR(2 * S + 3 + buf))); else mbar_arrive(BAR(2 * S + 3 + buf)); }
         continue;
       }
       for (int c0 = 32 * half; c0 < p.Npad; c0 += 64) {
@@ -733,7 +812,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
       tc_fence_before();
       __syncwarp();
       if (p.dbg && blockIdx.x == 0 && warp == 2 && lane == 0) p.dbg[it * 8 + 5] = clock64();
-      if (lane == 0) mbar_arrive(BAR(2 * S + 3 + buf));
+      if (lane == 0) { if (PAIR) mbar_arrive_cluster(LEADER(BAR(2 * S + 3 + buf))); else mbar_arrive(BAR(2 * S + 3 + buf)); }
     }
     if (FUSE != 0 && FUSE != 4) {
       // combine the eight row groups per channel: one double atomic per channel and statistic per CTA
@@ -753,9 +832,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
   }
   if (p.tma_store && threadIdx.x == 64) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   tc_fence_before();
-  __syncthreads();
+  if (PAIR) cluster_sync_all();          // the leader's MMAs read this CTA's weights and write its TMEM until its last tile retires
+  else __syncthreads();
   if (warp == 1) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(p.tmem_cols) : "memory");
+    if (PAIR) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(p.tmem_cols) : "memory");
+    else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(p.tmem_cols) : "memory");
   }
   if (DYN && threadIdx.x == 0) {
     // this CTA drew its last index before the barrier above; the last CTA to get here re-arms the counters for the next launch
@@ -784,6 +865,26 @@ EncodeTiledFn get_encode() {
 }
 
 long long* g_tc_dbg = nullptr;
+
+// lvae_launch with a cluster of two CTAs (the cta_group::2 kernels) on top of the programmatic-dependent-launch attribute
+template <typename... KArgs, typename... Args>
+cudaError_t lvae_launch_pair(void (*kernel)(KArgs...), int grid, int block, size_t smem, cudaStream_t stream, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(block);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[2];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = g_lvae_pdl ? 1 : 0;
+  attr[1].id = cudaLaunchAttributeClusterDimension;
+  attr[1].val.clusterDim.x = 2;
+  attr[1].val.clusterDim.y = 1;
+  attr[1].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 2;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
 
 // Counters of the dynamic tile scheduler: one {next tile, finished CTAs} pair per stream that launches DYN kernels (kernels of
 // one stream never overlap; the kernel itself re-arms its pair).  Allocated on first use outside stream capture -- the
@@ -906,15 +1007,21 @@ LVAE_API int lvae_conv2d_tc_ex(const void* x, const void* x2, const void* wp, co
   p.tmem_cols = 32;
   while (p.tmem_cols < 2 * p.Npad) p.tmem_cols *= 2;
   LVAE_REQUIRE(p.tmem_cols <= 512, "conv2d_tc: accumulator does not fit TMEM");
-  const int wbytes = ((p.n_kb * p.Npad * 128) + 1023) & ~1023;
   const int max_smem = 227 * 1024 - 1024 /*align*/ - 8192 /*barriers, bias, BatchNorm table, reduction scratch*/;
-  static int halo_env = -1, bo_env = 0;
+  static int halo_env = -1, bo_env = 0, pair_env = 0;
   if (halo_env < 0) {
     const char* e = getenv("LVAE_CONV_HALO");
     halo_env = e ? atoi(e) : 1;
     const char* b = getenv("LVAE_HALO_BO");
     bo_env = b ? atoi(b) : 0;   // the hardware swizzle is a function of the absolute shared-memory address: no base offset
+    const char* c = getenv("LVAE_CONV_CTA2");
+    pair_env = c ? atoi(c) : 0;
   }
+  // CTA pairs (cta_group::2): halo-mode 3x3 convolutions of 64 -> 64 channels with an even number of 16x8-pixel tiles and
+  // no gate / split / residual extras; each CTA of a pair keeps half of the weight rows
+  const bool pair = pair_env && halo_env && ksize == 3 && !x2 && Cin == 64 && N == 64 && W % 8 == 0 && H % 16 == 0 && !y2 && !res &&
+                    !p.gate_x && ((B * (W / 8) * (H / 16)) % 2 == 0) && lvae_num_sms() >= 2;
+  const int wbytes = ((p.n_kb * (pair ? p.Npad / 2 : p.Npad) * 128) + 1023) & ~1023;
   static int tst_env = -1;
   if (tst_env < 0) { const char* e = getenv("LVAE_CONV_TMA_STORE"); tst_env = e ? atoi(e) : 1; }
   p.tma_store = (tst_env && !out_f32 && N % 64 == 0 && N <= 128 && !res && (!y2 || nsplit % 64 == 0)) ? 1 : 0;
@@ -970,7 +1077,7 @@ LVAE_API int lvae_conv2d_tc_ex(const void* x, const void* x2, const void* wp, co
     if (r != CUDA_SUCCESS) { lvae_set_error("conv2d_tc: tensor map (x2) encode failed: %d", (int)r); return LVAE_ERR_CUDA; }
     cuuint64_t wdim[2] = {64, (cuuint64_t)p.n_kb * p.Npad};
     cuuint64_t wstr[1] = {128};
-    cuuint32_t wbox[2] = {64, (cuuint32_t)p.Npad};
+    cuuint32_t wbox[2] = {64, (cuuint32_t)(pair ? p.Npad / 2 : p.Npad)};
     cuuint32_t westr[2] = {1, 1};
     r = enc(&tmW, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (void*)wp, wdim, wstr, wbox, westr, CU_TENSOR_MAP_INTERLEAVE_NONE,
             CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -989,6 +1096,10 @@ LVAE_API int lvae_conv2d_tc_ex(const void* x, const void* x2, const void* wp, co
     if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tc_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tc_kernel<3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tc_kernel<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tc_kernel<0, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tc_kernel<1, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tc_kernel<2, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tc_kernel<4, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap);
     if (e != cudaSuccess) { lvae_set_error("conv2d_tc: cannot raise dynamic smem: %s", cudaGetErrorString(e)); return LVAE_ERR_CUDA; }
     attr_smem = 227 * 1024;
   }
@@ -996,6 +1107,22 @@ LVAE_API int lvae_conv2d_tc_ex(const void* x, const void* x2, const void* wp, co
   const int grid = n_tiles < lvae_num_sms() ? n_tiles : lvae_num_sms();
   static int dyn_env = -1;
   if (dyn_env < 0) { const char* e = getenv("LVAE_CONV_DYNAMIC"); dyn_env = e ? atoi(e) : 0; }
+  if (pair && p.halo) {
+    // clusters of two CTAs; both CTAs of a pair run the same number of tiles (n_tiles and the grid are even)
+    const int pgrid = grid & ~1;
+    p.dbg = nullptr;
+    p.sched = nullptr;
+    cudaError_t e;
+    if (p.stats_acc) e = lvae_launch_pair(conv_tc_kernel<1, false, true>, pgrid, TC_THREADS, smem, stream, tmA0, tmA1, tmW, tmY, tmY2, p);
+    else if (p.bnb_acc) e = lvae_launch_pair(conv_tc_kernel<2, false, true>, pgrid, TC_THREADS, smem, stream, tmA0, tmA1, tmW, tmY, tmY2, p);
+    else if (p.f32_stage) e = lvae_launch_pair(conv_tc_kernel<4, false, true>, pgrid, TC_THREADS, smem, stream, tmA0, tmA1, tmW, tmY, tmY2, p);
+    else e = lvae_launch_pair(conv_tc_kernel<0, false, true>, pgrid, TC_THREADS, smem, stream, tmA0, tmA1, tmW, tmY, tmY2, p);
+    if (e != cudaSuccess) { lvae_set_error("conv2d_tc: cluster launch failed: %s", cudaGetErrorString(e)); return LVAE_ERR_CUDA; }
+    LVAE_COUNT_LAUNCH();
+    LVAE_CHECK_LAUNCH("conv2d_tc (cta pair)");
+    return LVAE_OK;
+  }
+  LVAE_REQUIRE(!pair, "conv2d_tc: internal: CTA-pair weights layout without halo mode");
   p.sched = (dyn_env && n_tiles > grid) ? tc_sched_slot(stream) : nullptr;     // one tile per CTA: nothing to balance
   if (p.sched) {
     p.dbg = nullptr;
