@@ -211,8 +211,13 @@ def log_discretized_logistic(x, mean, log_scale, n_bins=256, reduce="mean", doub
 def log_normal(x, mean, logvar, reduce="mean"):
     """Diagonal Gaussian log-density summed over (c,h,w) (likelihoods.py:391-411)."""
     logvar = _input_check(x, mean, logvar, reduce)
-    lp = -0.5 * ((x - mean) ** 2 / logvar.exp() + logvar + math.log(2 * math.pi))
+    lp = -0.5 * ((x - mean) ** 2 / logvar.exp() + logvar + _LOG_2PI)
     return _reduce(lp.sum((1, 2, 3)), reduce)
+
+
+# The reference adds log(2 pi) as a float32 0-dim tensor (likelihoods.py:408), so float64 inputs also see the
+# float32-rounded constant (1.8378770351...); a Python double here would differ from it by 3e-8 per element.
+_LOG_2PI = float(torch.tensor(2 * math.pi, dtype=torch.float32).log())
 
 
 def _reduce(x, reduce):
