@@ -74,7 +74,8 @@ def logistic_rsample(mu_ls):
     except TypeError:
         mu, log_scale = mu_ls
     u = torch.empty_like(mu).uniform_(1e-7, 1 - 1e-7)
-    return mu + log_scale.exp() * (torch.log(u) - torch.log1p(-u))
+    # log(1 - u), not log1p(-u): bit-for-bit what the reference draws from the same generator state (:135)
+    return mu + log_scale.exp() * (torch.log(u) - torch.log(1 - u))
 
 
 def sample_from_discretized_mix_logistic(l):
