@@ -129,3 +129,20 @@ def test_base_model_checkpoint_roundtrip(tmp_path):
         assert k1 == k2 and torch.equal(v1, v2)
     m2.increment_global_step()
     assert m2.global_step == 31
+
+
+@pytest.mark.skipif(not ref_loader.reference_available(), reason="reference tree not mounted")
+def test_log_bernoulli_tensor_form_is_bit_identical_to_reference():
+    """The probability-form Bernoulli log-likelihood used outside the fused forward (likelihoods.py:385-388), including
+    the saturated probabilities where BCE clamps the logs at -100."""
+    L = _ours()
+    ref = ref_loader.load_reference()["likelihoods"]
+    g = torch.Generator().manual_seed(0)
+    for dt in (torch.float32, torch.float64):
+        p = torch.rand(4, 1, 28, 28, generator=g).to(dt)
+        p[0, 0, 0, :4] = torch.tensor([0.0, 1.0, 1e-30, 1 - 1e-7]).to(dt)
+        x = (torch.rand(4, 1, 28, 28, generator=g) < 0.15).to(dt)
+        assert torch.equal(L.log_bernoulli(x, p, reduce="none"), ref.log_bernoulli(x, p, reduce="none"))
+        soft = torch.rand(4, 1, 28, 28, generator=g).to(dt)
+        assert torch.equal(L.log_bernoulli(soft, p, reduce="mean"), ref.log_bernoulli(soft, p, reduce="mean"))
+        assert torch.equal(L.log_bernoulli(soft, p, reduce="sum"), ref.log_bernoulli(soft, p, reduce="sum"))
