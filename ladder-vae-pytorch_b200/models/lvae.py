@@ -185,7 +185,7 @@ class LadderVAE(BaseGenerativeModel):
         z, kl, kl_spatial = [None] * L, [None] * L, [None] * L
         if forced_latent is None:
             forced_latent = [None] * L
-        logprob_p = 0.
+        logprob_p = []
         out = None
         for i in reversed(range(L)):
             bu_value = bu_values[i] if inference_mode else None
@@ -194,8 +194,10 @@ class LadderVAE(BaseGenerativeModel):
                 n_img_prior=n_img_prior, use_mode=i in mode_layers, force_constant_output=i in constant_layers,
                 forced_latent=forced_latent[i])
             z[i], kl[i], kl_spatial[i] = aux["z"], aux["kl_samplewise"], aux["kl_spatial"]
-            logprob_p = logprob_p + aux["logprob_p"].mean()
+            logprob_p.append(aux["logprob_p"])
         out = self.final_top_down(out)
+        # sum over layers of the batch means (lvae.py:301-302) as three launches instead of one mean + one add per layer
+        logprob_p = torch.stack(logprob_p, dim=0).mean(dim=1).sum()
         return out, {"z": z, "kl": kl, "kl_spatial": kl_spatial, "logprob_p": logprob_p}
 
     def pad_input(self, x):
