@@ -216,6 +216,32 @@ def conv_roofline(torch, pk, dtype="bf16"):
             "peak_source": "%s bf16 burst (kernel timed alone)" % pk["src"]}
 
 
+def hbm_rooflines(workload):
+    """Secondary roofline entries for the HBM-bound kernels north_star names (fused stochastic block, likelihoods): the
+    microbenchmarks of profiles/bench_hbm_kernels.py (CUDA-graph replay over rotating buffers larger than L2, CUDA events on
+    the capturing stream, algorithmic bytes of SURVEY.md 8d over the measured copy bandwidth).  Never fatal: an exception
+    is reported in place of the numbers; the table it prints goes to stderr."""
+    import contextlib
+    import importlib.util
+    try:
+        spec = importlib.util.spec_from_file_location("bench_hbm_kernels", os.path.join(ROOT, "profiles", "bench_hbm_kernels.py"))
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+        peak, src = mod.hbm_peak()
+        rows = []
+        with contextlib.redirect_stdout(sys.stderr):
+            if workload == "iw":
+                mod.bench_stochastic(rows, peak, src, B=1000)
+                mod.bench_bernoulli(rows, peak, src)
+            else:
+                mod.bench_stochastic(rows, peak, src)
+                mod.bench_dmol(rows, peak, src)
+        keep = ("kernel", "shape", "us_per_launch", "achieved", "peak", "unit", "frac", "bound")
+        return [{k: r[k] for k in keep} for r in rows]
+    except Exception as e:  # noqa: BLE001
+        return {"error": repr(e)[:300]}
+
+
 # dram__bytes_read.sum + dram__bytes_write.sum of this kernel from one `ncu --set full` capture (profiles/ncu_conv_tc_r01_final.txt):
 # 8.53 MB read (8.39 MB activations + weights), 0 written (the output is still dirty in L2 when the kernel ends)
 NCU_CONV_DRAM_BYTES = 8526336
@@ -238,6 +264,7 @@ def main():
     ap.add_argument("--side-streams", type=int, default=2, help="number of side streams the weight-gradient kernels rotate over")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-hbm-rooflines", action="store_true", help="skip the stochastic / likelihood kernel microbenchmarks")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -325,6 +352,8 @@ def main():
                 "e2e": {"value": batch / (e2e_ms * 1e-3), "unit": "images/s with a %d-sample bound" % K,
                         "h2d_bytes_per_step": x_host.numel() * 4, "d2h_bytes_per_step": res_host.numel() * 4},
                 "gpu_launches": launches, "clocks": clocks}
+        if rank == 0 and world == 1 and not args.no_hbm_rooflines:
+            line["roofline_hbm"] = hbm_rooflines("iw")
         if rank == 0 and not args.no_cpu_baseline and world == 1:
             line["cpu_baseline"] = {k: v for k, v in cpu_baseline_iw(32, 3).items() if k != "s_per_forward"}
         if rank == 0:
@@ -384,6 +413,8 @@ def main():
             "peak_mem_gb": mem_gb, "loss": final_loss}
     if rank == 0:
         line["roofline"] = conv_roofline(torch, pk, args.dtype)
+        if world == 1 and not args.no_hbm_rooflines:
+            line["roofline_hbm"] = hbm_rooflines(args.workload)
         if not args.no_cpu_baseline and world == 1:          # the CPU baseline is a single-GPU-run item (rank 0, N = 1 only)
             cb = cpu_baseline_train(cfg_name, 16, 2)
             line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
