@@ -416,7 +416,7 @@ def main():
         if world == 1 and not args.no_hbm_rooflines:
             line["roofline_hbm"] = hbm_rooflines(args.workload)
         if not args.no_cpu_baseline and world == 1:          # the CPU baseline is a single-GPU-run item (rank 0, N = 1 only)
-            cb = cpu_baseline_train(cfg_name, 16, 2)
+            cb = cpu_baseline_train(cfg_name, 16, 6)          # ~5-10 s of CPU work on the box's host cores
             line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
         print(json.dumps(line), flush=True)
     if world > 1:
