@@ -105,6 +105,17 @@ typedef struct {
 int lvae_conv2d_tc_ex(const void* x, const void* x2, const void* wp, const float* bias, const float* out_scale,
                       const void* res, void* y, void* y2, int nsplit, int B, int H, int W, int Cin, int N, int ksize,
                       int flip, int out_f32, const LvaeConvFuse* fuse, lvae_stream_t stream);
+/* The tail of a gated residual block as one launch (opt-in from Python with LVAE_CONV_GATE_CHAIN=1):
+ *   c2 = (conv3x3(a2) + bias2) * scale2      second 3x3 convolution of lib/nn.py:83-87 with its Dropout2d mask (B,64) or NULL
+ *   h  = conv1x1(c2) + bias_g  (128 ch)      GateLayer2d's convolution, lib/nn.py:118
+ *   out = act(h[:, :64]) * sigmoid(h[:, 64:]) + x_res          lib/nn.py:121-126 and the residual add :99
+ * The 1x1 GEMM reads the bf16 tile that the 3x3 epilogue stages in shared memory for its TMA store (csrc/conv_gate_tcgen05.cu).
+ * a2, x_res, c2, out: (B,H,W,64) bf16; h: (B,H,W,128) bf16; c2 and h both NULL in eval mode.  w2p: nine packed [64][64]
+ * blocks, wgp: one packed [128][64] block (lvae_pack_weights mode 2).  stats_acc: 8-way striped (8,2,64) doubles, += the
+ * per-channel sum / sum of squares of out, or NULL.  H, W powers of two, W <= 128. */
+int lvae_conv_gate_tc(const void* a2, const void* w2p, const float* bias2, const float* scale2, const void* wgp,
+                      const float* bias_g, const void* x_res, void* c2, void* h, void* out, double* stats_acc, int B, int H,
+                      int W, int gate_act, lvae_stream_t stream);
 /* Stride-2 3x3 convolutions 64 -> 64 on the same tcgen05 kernel (the down / up-sampling pre_convs of
  * models/lvae_layers.py:261-276).  kind 0 "gather": y (B,Hg,Wg,N) from x (B,2Hg,2Wg,64) = Conv2d(stride 2, pad 1) forward
  * and ConvTranspose2d(stride 2, pad 1, output_padding 1) input gradient (TMA traverses x with element stride 2).  kind 1

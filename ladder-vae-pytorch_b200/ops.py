@@ -683,6 +683,19 @@ _bn_epoch = [0]
 _whole_block = [True]
 _gate_fused = [os.environ.get("LVAE_GATE_FUSED", "1") != "0"]
 _gate_keep_h = [True]     # set per call by gated_block(): autograd.Function.forward always runs with grad mode off
+# opt-in (not yet validated on a GPU): conv2 + gate conv + gate as ONE launch, the 1x1 GEMM reading the staged conv2 tile
+_gate_chain = [os.environ.get("LVAE_CONV_GATE_CHAIN", "0") != "0"]
+
+
+def _conv_gate_chain(a2, w2p, bias2, mask2, wgp, gbias, xn, gact, stats_acc, keep):
+    """lvae_conv_gate_tc: returns (c2, h, out); c2 and h are None when nothing will run backward (keep = False)."""
+    B, H, W, _ = a2.shape
+    out = torch.empty_like(xn)
+    c2 = torch.empty_like(a2) if keep else None
+    h = torch.empty((B, H, W, 128), dtype=torch.bfloat16, device=a2.device) if keep else None
+    call("lvae_conv_gate_tc", a2.data_ptr(), w2p.data_ptr(), _p(bias2), _p(mask2), wgp.data_ptr(), _p(gbias), xn.data_ptr(),
+         _p(c2), _p(h), out.data_ptr(), _p(stats_acc), B, H, W, int(gact), _stream())
+    return c2, h, out
 
 
 def set_whole_block(flag: bool) -> None:
@@ -769,13 +782,23 @@ class GatedBlockFn(Function):
         else:
             y1 = conv_forward_raw(conv1.spec, a1, None, w1, cb1, m1, None)
         a2 = bn_fwd(y1, bn2, sc2, saves[1], g2, b2, acc2)
-        y2 = conv_forward_raw(conv2.spec, a2, None, w2, cb2, m2, None)
+        gspec = gconv.spec
+        # opt-in: conv2, the 1x1 gate conv and the gate itself as one launch (csrc/conv_gate_tcgen05.cu)
+        chain = (_gate_chain[0] and C == 64 and gspec.cout == 128 and gspec.k == 1 and conv2.spec.k == 3 and conv2.spec.cout == 64
+                 and xn.dtype == torch.bfloat16 and not gspec.out_fp32 and not conv2.spec.out_fp32
+                 and conv2.spec.tc_forward_ok(a2, None) and gspec.tc_forward_ok(a2, None)
+                 and (m2 is None or (m2.dtype == torch.float32 and m2.is_contiguous())))
+        y2 = None if chain else conv_forward_raw(conv2.spec, a2, None, w2, cb2, m2, None)
         out_stats = None
         if training and 256 % (C // 4) == 0:
             out_stats = sc1[2]                        # statistics of this block's output, for the next block's BN1
             _bn_clean(bn1, out_stats, "out")
-        gspec = gconv.spec
-        if (_gate_fused[0] and C == 64 and gspec.cout == 128 and xn.dtype == torch.bfloat16 and not gspec.out_fp32
+        if chain:
+            stats["tc_fwd"] += 2
+            stats["gate_chain"] = stats.get("gate_chain", 0) + 1
+            y2, h, out = _conv_gate_chain(a2, conv2.spec.pack_tc_fwd.get(w2, torch.bfloat16), cb2, m2,
+                                          gspec.pack_tc_fwd.get(wg, torch.bfloat16), gbias, xn, gact, out_stats, _gate_keep_h[0])
+        elif (_gate_fused[0] and C == 64 and gspec.cout == 128 and xn.dtype == torch.bfloat16 and not gspec.out_fp32
                 and gspec.tc_forward_ok(y2, None)):
             # gate, residual add and the output statistics ride in the epilogue of the 1x1 gate conv
             stats["tc_fwd"] += 1
