@@ -1,4 +1,4 @@
-"""Model checks of the two mbarrier protocols added to csrc/conv_tcgen05.cu without a GPU at hand: random interleavings of
+"""Model checks of the mbarrier protocols added to csrc/conv_tcgen05.cu without a GPU at hand: random interleavings of
 the participating warps over a small Python model of mbarrier phases (arrival count + transaction bytes) must never
 deadlock and must hand every consumer exactly the producer's sequence.  This checks the PROTOCOL (counts, parities,
 who arrives where), not the PTX; the kernels' own parity tests run on the GPU (`profiles/ab_switches.sh`, `ab_cta2.sh`).
@@ -8,6 +8,8 @@ who arrives where), not the PTX; the kernels' own parity tests run on the GPU (`
 * pair: cta_group::2 kernels: the leader's `full[s]` collects both CTAs' TMA bytes (the peer's may land before the leader
   arms it), `tcgen05.commit` multicast arrives on `empty[s]` and `tmem_full[buf]` of both CTAs, the sixteen epilogue warps of
   both CTAs arrive on the leader's `tmem_empty[buf]`.
+* chain: conv_gate_tc_kernel (csrc/conv_gate_tcgen05.cu): the 3x3 MMAs of tile i+1 are issued before the gate MMAs of tile i,
+  with ONE staged-c2 buffer (reused for `out`) and ONE gate accumulator; the gate GEMM must always find tile i's c2 staged.
 """
 import random
 
@@ -180,3 +182,113 @@ def _pair(seed, iters, stages):
 def test_cta_pair_barrier_protocol():
     for seed in range(120):
         _pair(seed, random.Random(seed).randint(1, 15), random.Random(seed + 1).randint(2, 4))
+
+
+def _chain(seed, n_tiles, stages, taps):
+    """conv_gate_tc_kernel: 3x3 MMAs of tile i+1 issued before the gate MMAs of tile i; one staged-c2 buffer and one gate
+    accumulator; the epilogue runs phase 1 (stage c2) and phase 2 (drain the gate accumulator) of a tile back to back."""
+    rnd = random.Random(seed)
+    full = [MBar(1) for _ in range(stages)]
+    empty = [MBar(1) for _ in range(stages)]
+    a1_full, a1_empty = [MBar(1), MBar(1)], [MBar(8), MBar(8)]
+    c2_staged, a2_full, a2_empty = MBar(1), MBar(1), MBar(8)
+    stage_tile = [None] * stages
+    acc1, acc2, s_c2 = [None, None], [None], [None]
+    inflight, outs = [], []
+
+    def producer():
+        st = ph = 0
+        for tile in range(n_tiles):
+            for t in range(taps):
+                while not empty[st].ready(ph ^ 1):
+                    yield
+                full[st].arrive(expect_tx=1)
+                inflight.append(("tma", st, (tile, t)))
+                yield
+                st += 1
+                if st == stages:
+                    st, ph = 0, ph ^ 1
+
+    def mma():
+        st = ph = 0
+
+        def gate(j):
+            while not a2_empty.ready((j & 1) ^ 1):
+                yield
+            while not c2_staged.ready(j & 1):
+                yield
+            assert s_c2[0] == ("c2", j)                    # the staged tile is tile j's c2, not yet overwritten by `out`
+            inflight.append(("gate", j))
+            yield
+
+        for it in range(n_tiles):
+            buf, use = it & 1, it >> 1
+            while not a1_empty[buf].ready((use & 1) ^ 1):
+                yield
+            for t in range(taps):
+                while not full[st].ready(ph):
+                    yield
+                assert stage_tile[st] == (it, t)
+                inflight.append(("conv", st, buf, it, t == taps - 1))
+                yield
+                st += 1
+                if st == stages:
+                    st, ph = 0, ph ^ 1
+            if it > 0:
+                yield from gate(it - 1)
+        if n_tiles > 0:
+            yield from gate(n_tiles - 1)
+
+    def epilogue(w):
+        for it in range(n_tiles):
+            buf, use = it & 1, it >> 1
+            while not a1_full[buf].ready(use & 1):
+                yield
+            assert acc1[buf] == it
+            yield
+            a1_empty[buf].arrive()
+            if w == 0:
+                s_c2[0] = ("c2", it)                       # (all warps write; modelled once, after the staging barrier)
+                c2_staged.arrive()
+            yield
+            while not a2_full.ready(it & 1):
+                yield
+            assert acc2[0] == it
+            yield
+            a2_empty.arrive()
+            if w == 0:
+                s_c2[0] = ("out", it)
+                outs.append(it)
+            for _ in range(rnd.randint(0, 4)):
+                yield
+
+    def asynchronous():
+        while True:
+            if inflight and rnd.random() < 0.6:
+                tmas = [e for e in inflight if e[0] == "tma"]
+                pipe = [e for e in inflight if e[0] != "tma"]              # the tensor pipe retires in issue order
+                ev = rnd.choice(tmas) if tmas and (not pipe or rnd.random() < 0.5) else pipe[0]
+                inflight.remove(ev)
+                if ev[0] == "tma":
+                    stage_tile[ev[1]] = ev[2]
+                    full[ev[1]].complete_tx(1)
+                elif ev[0] == "conv":
+                    _, st, buf, it, last = ev
+                    empty[st].arrive()
+                    if last:
+                        acc1[buf] = it
+                        a1_full[buf].arrive()
+                else:
+                    assert s_c2[0] == ("c2", ev[1])
+                    acc2[0] = ev[1]
+                    a2_full.arrive()
+            yield
+
+    _run([producer(), mma()] + [epilogue(w) for w in range(8)], rnd, asynchronous())
+    assert outs == list(range(n_tiles))
+
+
+def test_conv_gate_chain_protocol():
+    for seed in range(120):
+        r = random.Random(seed)
+        _chain(seed, r.randint(1, 12), r.randint(2, 5), r.choice([1, 9]))
