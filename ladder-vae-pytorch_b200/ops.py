@@ -685,6 +685,18 @@ _gate_fused = [os.environ.get("LVAE_GATE_FUSED", "1") != "0"]
 _gate_keep_h = [True]     # set per call by gated_block(): autograd.Function.forward always runs with grad mode off
 # opt-in (not yet validated on a GPU): conv2 + gate conv + gate as ONE launch, the 1x1 GEMM reading the staged conv2 tile
 _gate_chain = [os.environ.get("LVAE_CONV_GATE_CHAIN", "0") != "0"]
+# opt-in (not yet validated on a GPU): gate backward + 1x1 gate-conv data gradient as ONE launch
+_gate_bwd_chain = [os.environ.get("LVAE_GATE_BWD_CHAIN", "0") != "0"]
+
+
+def _gate_bwd_dgrad_chain(gn, h, wpb, mask2, gact):
+    """lvae_gate_bwd_dgrad_tc: returns (dh, dc2) = (gate backward wrt h, its 1x1 data gradient times the Dropout2d mask)."""
+    B, H, W, _ = gn.shape
+    dh = torch.empty_like(h)
+    dc2 = torch.empty_like(gn)
+    call("lvae_gate_bwd_dgrad_tc", gn.data_ptr(), h.data_ptr(), wpb.data_ptr(), _p(mask2), dh.data_ptr(), dc2.data_ptr(),
+         B, H * W, int(gact), _stream())
+    return dh, dc2
 
 
 def _conv_gate_chain(a2, w2p, bias2, mask2, wgp, gbias, xn, gact, stats_acc, keep):
@@ -828,11 +840,21 @@ class GatedBlockFn(Function):
         if gn.dtype != xn.dtype:
             gn = gn.to(xn.dtype)
         ng = ctx.needs_input_grad
-        # gate
-        dh = torch.empty_like(h)
-        call("lvae_gate_bwd", gn.data_ptr(), h.data_ptr(), dh.data_ptr(), Pn, C, gact, dt, _stream())
-        # 1x1 gate conv: dgrad carries conv2's Dropout2d mask in its epilogue -> gradient wrt conv2's raw output
-        dy2, _, gwg, ggb = conv_backward_raw(gconv.spec, y2, None, wg, gbias, None, dh, True, ng[9], ng[10], dx_scale=m2)
+        gsp = gconv.spec
+        if (_gate_bwd_chain[0] and C == 64 and gsp.cout == 128 and gsp.k == 1 and gsp.tc_shape and xn.dtype == torch.bfloat16
+                and h.dtype == torch.bfloat16 and gn.is_contiguous()
+                and (m2 is None or (m2.dtype == torch.float32 and m2.is_contiguous()))):
+            # opt-in: gate backward and the 1x1 data gradient in one launch (csrc/gate_dgrad_tcgen05.cu); weight gradient as usual
+            stats["tc_dgrad"] += 1
+            stats["gate_bwd_chain"] = stats.get("gate_bwd_chain", 0) + 1
+            dh, dy2 = _gate_bwd_dgrad_chain(gn, h, gsp.pack_tc_bwd.get(wg, torch.bfloat16), m2, gact)
+            _, _, gwg, ggb = conv_backward_raw(gsp, y2, None, wg, gbias, None, dh, False, ng[9], ng[10])
+        else:
+            # gate
+            dh = torch.empty_like(h)
+            call("lvae_gate_bwd", gn.data_ptr(), h.data_ptr(), dh.data_ptr(), Pn, C, gact, dt, _stream())
+            # 1x1 gate conv: dgrad carries conv2's Dropout2d mask in its epilogue -> gradient wrt conv2's raw output
+            dy2, _, gwg, ggb = conv_backward_raw(gsp, y2, None, wg, gbias, None, dh, True, ng[9], ng[10], dx_scale=m2)
         sc1b, sc2b = bn_scratch(bn1, dev), bn_scratch(bn2, dev)
         acc1b, acc2b = sc1b[1], sc2b[1]
         _bn_clean(bn1, acc1b, "bwd")

@@ -24,8 +24,8 @@ done
 # the chained conv2 + gate kernel: kernel-level bit-exactness against the two-launch path, then the model tests with it on
 LVAE_TEST_EXPERIMENTAL=1 $T $PY -m pytest tests/test_experimental_gpu.py -m gpu -q > gpurun_out/ab_tests_experimental.log 2>&1
 echo "experimental tests rc=$? ($(tail -1 gpurun_out/ab_tests_experimental.log))" | tee -a gpurun_out/ab_summary.log
-LVAE_CONV_GATE_CHAIN=1 $T $PY -m pytest tests/test_model_gpu.py tests/test_engine_gpu.py -m gpu -q > gpurun_out/ab_tests_LVAE_CONV_GATE_CHAIN.log 2>&1
-echo "LVAE_CONV_GATE_CHAIN=1 tests rc=$? ($(tail -1 gpurun_out/ab_tests_LVAE_CONV_GATE_CHAIN.log))" | tee -a gpurun_out/ab_summary.log
+LVAE_CONV_GATE_CHAIN=1 LVAE_GATE_BWD_CHAIN=1 $T $PY -m pytest tests/test_model_gpu.py tests/test_engine_gpu.py -m gpu -q > gpurun_out/ab_tests_LVAE_GATE_CHAINS.log 2>&1
+echo "LVAE_CONV_GATE_CHAIN=1 LVAE_GATE_BWD_CHAIN=1 tests rc=$? ($(tail -1 gpurun_out/ab_tests_LVAE_GATE_CHAINS.log))" | tee -a gpurun_out/ab_summary.log
 
 echo "== microbenchmarks ==" | tee -a gpurun_out/ab_summary.log
 $T $PY profiles/bench_hbm_kernels.py > gpurun_out/ab_hbm_default.log 2>&1
@@ -55,7 +55,9 @@ run_bench f32stage LVAE_CONV_F32_STAGE=1
 run_bench dmolfast LVAE_DMOL_FAST=1
 run_bench dynamic LVAE_CONV_DYNAMIC=1
 run_bench gatechain LVAE_CONV_GATE_CHAIN=1
-run_bench all LVAE_CONV_F32_STAGE=1 LVAE_DMOL_FAST=1 LVAE_CONV_DYNAMIC=1 LVAE_CONV_GATE_CHAIN=1
+run_bench gatebwdchain LVAE_GATE_BWD_CHAIN=1
+run_bench bothchains LVAE_CONV_GATE_CHAIN=1 LVAE_GATE_BWD_CHAIN=1
+run_bench all LVAE_CONV_F32_STAGE=1 LVAE_DMOL_FAST=1 LVAE_CONV_DYNAMIC=1 LVAE_CONV_GATE_CHAIN=1 LVAE_GATE_BWD_CHAIN=1
 echo "== IW-1000 (MNIST-12, batch 1000) ==" | tee -a gpurun_out/ab_summary.log
 $T $PY bench.py --workload iw --steps 1 --no-cpu-baseline > gpurun_out/ab_iw_default.json 2>&1
 LVAE_CONV_DYNAMIC=1 $T $PY bench.py --workload iw --steps 1 --no-cpu-baseline > gpurun_out/ab_iw_dynamic.json 2>&1

@@ -79,3 +79,68 @@ def test_conv_gate_chain_in_the_model(monkeypatch):
     assert abs(l0 - l1) <= 1e-6 * abs(l0)
     for n in g0:
         assert torch.allclose(g0[n], g1[n], rtol=1e-4, atol=1e-6), n
+
+
+BWD_CASES = [(2, 16, 16, True, 3), (3, 32, 32, True, 3), (5, 8, 8, False, 3), (3, 4, 4, True, 3), (40, 2, 2, True, 1),
+             (1, 2, 2, True, 3), (7, 4, 2, False, 4)]
+
+
+@pytest.mark.parametrize("case", BWD_CASES)
+def test_gate_bwd_dgrad_chain_matches_two_launches(case):
+    """lvae_gate_bwd_dgrad_tc against lvae_gate_bwd followed by the tcgen05 1x1 data gradient (mask in its epilogue)."""
+    import lvae_b200  # noqa: F401
+    from lvae_b200 import ops
+    B, H, W, masked, act = case
+    g = torch.Generator().manual_seed(B * 1000 + H * 10 + W)
+    bf = torch.bfloat16
+    gout = torch.randn(B, H, W, 64, generator=g).to(bf).cuda()
+    h = torch.randn(B, H, W, 128, generator=g).to(bf).cuda()
+    wg = (torch.randn(128, 64, 1, 1, generator=g) / 8).cuda()
+    m2 = ((torch.rand(B, 64, generator=g) > 0.2).float() / 0.8).cuda() if masked else None
+    wpb = ops.WeightPack(128, 64, 1, 3).get(wg, bf)
+    dh_ref = torch.empty_like(h)
+    ops.call("lvae_gate_bwd", gout.data_ptr(), h.data_ptr(), dh_ref.data_ptr(), B * H * W, 64, act, 1, ops._stream())
+    if ops._pow2(H) and ops._pow2(W):
+        dc2_ref = ops._conv_tc(dh_ref, None, wpb, None, m2, None, 64, 1, True, False)
+    else:
+        dc2_ref = None
+    dh, dc2 = ops._gate_bwd_dgrad_chain(gout, h, wpb, m2, act)
+    torch.cuda.synchronize()
+    assert torch.equal(dh, dh_ref)
+    if dc2_ref is not None:
+        assert torch.equal(dc2, dc2_ref)
+    # float64 reference of the data gradient from the bf16-rounded dh
+    ref = torch.einsum("bhwk,kc->bhwc", dh_ref.double().cpu(), wg.to(bf).double().cpu().view(128, 64))
+    if m2 is not None:
+        ref = ref * m2.double().cpu().view(B, 1, 1, 64)
+    err = (dc2.double().cpu() - ref).abs().max() / ref.abs().max()
+    assert float(err) < 6e-3
+
+
+def test_gate_chains_in_the_model_backward(monkeypatch):
+    """Both chained kernels on: same loss and gradients as the default path."""
+    import lvae_b200
+    from lvae_b200 import ops
+    from oracle import lvae_oracle as O
+    from oracle.make_golden import make_inputs, small_cfg
+    cfg = small_cfg(n_filters=64, z_dims=[32, 32, 32], dropout=0.2)
+    x, eps, masks = make_inputs(cfg, 4, 5, True)
+    results = []
+    for on in (False, True):
+        monkeypatch.setattr(ops, "_gate_chain", [on])
+        monkeypatch.setattr(ops, "_gate_bwd_chain", [on])
+        model = lvae_b200.LadderVAE(**cfg.kwargs())
+        model.load_state_dict(O.make_params(cfg, 3))
+        model = model.cuda().train().set_compute_dtype(torch.bfloat16)
+        ops.stats["gate_bwd_chain"] = 0
+        with lvae_b200.inject(eps=[e.float().cuda() for e in eps[0]], masks=[m.float().cuda() for m in masks]):
+            out = model(x.float().cuda())
+        loss = (-out["ll"]).mean() + out["kl_loss"]
+        loss.backward()
+        torch.cuda.synchronize()
+        assert (ops.stats.get("gate_bwd_chain", 0) > 0) == on
+        results.append((float(loss), {n: p.grad.float().clone() for n, p in model.named_parameters() if p.grad is not None}))
+    (l0, g0), (l1, g1) = results
+    assert abs(l0 - l1) <= 1e-6 * abs(l0)
+    for n in g0:
+        assert torch.allclose(g0[n], g1[n], rtol=1e-4, atol=1e-6), n
