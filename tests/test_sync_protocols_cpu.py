@@ -10,6 +10,9 @@ who arrives where), not the PTX; the kernels' own parity tests run on the GPU (`
   both CTAs arrive on the leader's `tmem_empty[buf]`.
 * chain: conv_gate_tc_kernel (csrc/conv_gate_tcgen05.cu): the 3x3 MMAs of tile i+1 are issued before the gate MMAs of tile i,
   with ONE staged-c2 buffer (reused for `out`) and ONE gate accumulator; the gate GEMM must always find tile i's c2 staged.
+* gate_dgrad: gate_dgrad_tc_kernel (csrc/gate_dgrad_tcgen05.cu): eight warps produce operand tile i+1 into the other buffer
+  before draining accumulator i.  (The model shows why the CTA barrier in front of the `a_ready` arrive is essential: without
+  it a slow warp can miss a phase of `a_free`.)
 """
 import random
 
@@ -292,3 +295,78 @@ def test_conv_gate_chain_protocol():
     for seed in range(120):
         r = random.Random(seed)
         _chain(seed, r.randint(1, 12), r.randint(2, 5), r.choice([1, 9]))
+
+
+def _gate_dgrad(seed, n_tiles):
+    """gate_dgrad_tc_kernel: eight warps produce operand tile i+1 (double buffered) before they drain the accumulator of
+    tile i; the MMA warp needs a produced operand and a drained accumulator."""
+    rnd = random.Random(seed)
+    a_ready, a_free = [MBar(1), MBar(1)], [MBar(1), MBar(1)]
+    acc_full, acc_empty = [MBar(1), MBar(1)], [MBar(8), MBar(8)]
+    s_a, acc, inflight, outs = [None, None], [None, None], [], []
+
+    def mma():
+        for it in range(n_tiles):
+            buf, use = it & 1, it >> 1
+            while not acc_empty[buf].ready((use & 1) ^ 1):
+                yield
+            while not a_ready[buf].ready(use & 1):
+                yield
+            assert s_a[buf] == it
+            inflight.append((buf, it))
+            yield
+
+    cta_bar = {"n": 0, "gen": 0}                         # bar.sync 1, 256 among the eight warps
+
+    def bar_sync():
+        gen = cta_bar["gen"]
+        cta_bar["n"] += 1
+        if cta_bar["n"] == 8:
+            cta_bar["n"], cta_bar["gen"] = 0, gen + 1
+        while cta_bar["gen"] == gen:
+            yield
+
+    def warp(w):
+        def produce(j):
+            buf, use = j & 1, j >> 1
+            while not a_free[buf].ready((use & 1) ^ 1):
+                yield
+            s_a[buf] = j                                   # every warp writes its share of the operand tile
+            yield from bar_sync()                          # ... and only then may thread 0 publish it
+            if w == 0:
+                a_ready[buf].arrive()
+            yield
+
+        if n_tiles > 0:
+            yield from produce(0)
+        for it in range(n_tiles):
+            buf, use = it & 1, it >> 1
+            if it + 1 < n_tiles:
+                yield from produce(it + 1)
+            while not acc_full[buf].ready(use & 1):
+                yield
+            assert acc[buf] == it
+            yield
+            acc_empty[buf].arrive()
+            if w == 0:
+                outs.append(it)
+            for _ in range(rnd.randint(0, 3)):
+                yield
+
+    def asynchronous():
+        while True:
+            if inflight and rnd.random() < 0.5:
+                buf, it = inflight.pop(0)                  # in issue order
+                assert s_a[buf] == it                      # the operand buffer was not overwritten while the MMAs read it
+                acc[buf] = it
+                a_free[buf].arrive()
+                acc_full[buf].arrive()
+            yield
+
+    _run([mma()] + [warp(w) for w in range(8)], rnd, asynchronous())
+    assert outs == list(range(n_tiles))
+
+
+def test_gate_dgrad_chain_protocol():
+    for seed in range(120):
+        _gate_dgrad(seed, random.Random(seed).randint(1, 14))
