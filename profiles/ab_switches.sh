@@ -5,7 +5,7 @@
 # exercise each variant, with the switch set), then device-time microbenchmarks, then the full training-step bench.
 set -u
 mkdir -p gpurun_out
-T="timeout 600"
+T="timeout 300"    # a hang of an unvalidated kernel must not hold the box
 PY=python
 
 echo "== default parity ==" | tee gpurun_out/ab_summary.log
