@@ -1084,13 +1084,22 @@ LVAE_API int lvae_conv2d_tc_ex(const void* x, const void* x2, const void* wp, co
     if (r != CUDA_SUCCESS) { lvae_set_error("conv2d_tc: tensor map (w) encode failed: %d", (int)r); return LVAE_ERR_CUDA; }
   }
   static size_t attr_smem = 0;
+  const int cap = 227 * 1024;
   if (smem > attr_smem) {
-    const int cap = 227 * 1024;
+    // the four kernels of the default path (exactly what was validated on the GPU)
     cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tc_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tc_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tc_kernel<3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tc_kernel<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap);
+    if (e != cudaSuccess) { lvae_set_error("conv2d_tc: cannot raise dynamic smem: %s", cudaGetErrorString(e)); return LVAE_ERR_CUDA; }
+    attr_smem = 227 * 1024;
+  }
+  static int dyn_env = -1;
+  if (dyn_env < 0) { const char* e = getenv("LVAE_CONV_DYNAMIC"); dyn_env = e ? atoi(e) : 0; }
+  static bool attr_optin = false;
+  if (!attr_optin && (p.f32_stage || dyn_env || pair)) {
+    // opt-in variants: only touched when one of their switches is set
+    cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tc_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tc_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tc_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap);
@@ -1100,13 +1109,11 @@ LVAE_API int lvae_conv2d_tc_ex(const void* x, const void* x2, const void* wp, co
     if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tc_kernel<1, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tc_kernel<2, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tc_kernel<4, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap);
-    if (e != cudaSuccess) { lvae_set_error("conv2d_tc: cannot raise dynamic smem: %s", cudaGetErrorString(e)); return LVAE_ERR_CUDA; }
-    attr_smem = 227 * 1024;
+    if (e != cudaSuccess) { lvae_set_error("conv2d_tc: cannot raise dynamic smem (opt-in kernels): %s", cudaGetErrorString(e)); return LVAE_ERR_CUDA; }
+    attr_optin = true;
   }
   const int n_tiles = p.halo ? B * p.tiles_per_img : (p.M_total + TC_BM - 1) / TC_BM;
   const int grid = n_tiles < lvae_num_sms() ? n_tiles : lvae_num_sms();
-  static int dyn_env = -1;
-  if (dyn_env < 0) { const char* e = getenv("LVAE_CONV_DYNAMIC"); dyn_env = e ? atoi(e) : 0; }
   if (pair && p.halo) {
     // clusters of two CTAs; both CTAs of a pair run the same number of tiles (n_tiles and the grid are even)
     const int pgrid = grid & ~1;

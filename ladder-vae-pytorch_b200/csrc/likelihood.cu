@@ -293,8 +293,10 @@ static bool dmol_fast() {
     fast = e ? atoi(e) : 0;
     cudaFuncSetAttribute(dmol_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DMOL_SMEM);
     cudaFuncSetAttribute(dmol_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DMOL_SMEM);
-    cudaFuncSetAttribute(dmol_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DMOL_SMEM);
-    cudaFuncSetAttribute(dmol_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DMOL_SMEM);
+    if (fast) {                                        // the opt-in kernels are only touched when their switch is set
+      cudaFuncSetAttribute(dmol_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DMOL_SMEM);
+      cudaFuncSetAttribute(dmol_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DMOL_SMEM);
+    }
   }
   return fast != 0;
 }
