@@ -6,11 +6,18 @@ batch 256 per GPU, data-parallel over N B200s).
     python bench.py --impl reference --gpus N --steps K ...    # the reference's CPU path (oracle port)
     python bench.py --workload iw ...                          # IW-1000 evals/s on the 12-layer MNIST model
 
-For N > 1 launch with torch.distributed.run (one rank per GPU).  Rank 0 prints ONE JSON line.
+For N > 1 launch with torch.distributed.run (one rank per GPU).  Rank 0 prints ONE JSON line, last.
 A "step" is one ELBO training step (zero grads, forward, loss, backward, gradient all-reduce,
 Adamax) over one synthetic batch.  `value` is timed with the batch already resident in HBM;
 `e2e` is timed through the public TrainEngine.step(x_host) call with the pinned-host -> device
 copy of the batch and the device -> host read of the loss inside the timed region.
+
+The default (train) line also carries the rest of BASELINE.json's metric and configs as sub-records, each timed the same
+way (warm-up, barrier, CUDA events, max over ranks): `iw` = the IW-1000 bound on the 12-layer MNIST model with the samples
+sharded over the N ranks (the second half of the metric), `configs` = one short timing each of the MNIST-3 / MNIST-12 /
+CelebA-20 training steps, `value_f32` = the headline step in the exact-fp32 parity mode, `dp_check` (N > 1) = replicas
+hold bit-identical parameters after the timed steps and the NCCL-reduced gradient arena equals the sum of the per-rank
+gradients.  `--no-extras` skips them (A/B timing runs).
 """
 from __future__ import annotations
 
@@ -31,6 +38,30 @@ CONFIGS = {"train": ("cifar15", 256), "iw": ("mnist12", 1000), "mnist12": ("mnis
            "celeba20": ("celeba20", 64)}
 # algorithmic conv GFLOP per image, forward / total
 CONV_GFLOP = {"mnist3": (1.042, 3.126), "mnist12": (2.913, 8.737), "cifar15": (3.655, 10.962), "celeba20": (14.759, 44.266)}
+METRIC_NAME = {"cifar15": "CIFAR10 15-layer", "mnist3": "MNIST 3-layer", "mnist12": "MNIST 12-layer", "celeba20": "CelebA 20-layer"}
+CPU_BATCH = 32          # the CPU arms time a bounded sample: steps of this batch (CPU throughput is flat in the batch size)
+
+
+def train_config(cfg_name, batch, world, graph):
+    """`config` of a training line -- printed identically by our arm and by the reference arm."""
+    lik = "Bernoulli" if cfg_name.startswith("mnist") else "10-component DMoL"
+    return {"workload": "ELBO training step (zero grad, forward, loss, backward, gradient all-reduce, Adamax), "
+                        "%s, %s, dropout 0.2, train-mode BatchNorm" % (cfg_name, lik),
+            "per_gpu_batch": batch, "global_batch": batch * world, "parallelism": "dp%d" % world,
+            "precision": "GPU arm: bf16 activations + tcgen05 convolutions with fp32 accumulation, fp32 stochastic / likelihood "
+                         "parameters, fp32 master weights (value_f32 = the exact-fp32 mode); reference arm: fp32 on the host CPU",
+            "reference_arm_sample": "the CPU arm times steps of batch %d, not %d (a bounded sample; CPU throughput is flat in "
+                                    "the batch size)" % (CPU_BATCH, batch),
+            "cuda_graph": graph,
+            "l2_policy": "inputs larger than L2: a step streams several GB of activations (peak_mem_gb)"}
+
+
+def iw_config(K, world, batch, full_forward):
+    return {"workload": "importance-weighted bound, K=%d samples sharded over %d GPU(s), test batch %d, "
+                        "binarized-MNIST-shaped 12-layer LVAE, eval mode" % (K, world, batch),
+            "bottom_up_pass": "per sample (as the reference)" if full_forward else "once per image batch (eval mode is deterministic)",
+            "reference_arm_sample": "the CPU arm times eval-mode forwards of batch 32 and extrapolates to K = %d" % K,
+            "l2_policy": "per-sample working set exceeds L2"}
 
 
 def peaks():
@@ -149,12 +180,12 @@ def run_reference(args, rank):
     if args.workload == "iw":
         cb = cpu_baseline_iw(32, max(1, args.steps))
         metric, unit = "IW-1000 evals/s (MNIST 12-layer LVAE)", "images/s with a 1000-sample bound"   # = our arm's
-        cfgd = {"workload": "importance-weighted bound K=1000, binarized-MNIST-shaped 12-layer LVAE", "cpu_batch": 32}
+        cfgd = iw_config(1000, args.gpus, batch, False)
         ms = cb["s_per_forward"] * 1e3
     else:
-        cb = cpu_baseline_train(name, 16, max(1, args.steps), max(1, min(args.warmup, 1)))
-        metric, unit = "train images/s (CIFAR10 15-layer LVAE)", "images/s"
-        cfgd = {"workload": "ELBO training step, %s, fp32" % name, "cpu_batch": 16, "per_gpu_batch": batch}
+        cb = cpu_baseline_train(name, CPU_BATCH, max(1, args.steps), max(1, min(args.warmup, 1)))
+        metric, unit = "train images/s (%s LVAE)" % METRIC_NAME.get(name, name), "images/s"
+        cfgd = train_config(name, batch, args.gpus, True)           # the same dict our arm prints
         ms = cb["s_per_step"] * 1e3
     line = {"impl": "reference", "metric": metric, "value": cb["value"], "unit": unit, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
@@ -248,6 +279,198 @@ def hbm_rooflines(workload):
 NCU_CONV_DRAM_BYTES = 8526336
 
 
+class Ctx:
+    """Rank / world plumbing shared by the timed sections."""
+
+    def __init__(self, torch, dist, rank, world, local):
+        self.torch, self.dist, self.rank, self.world, self.local = torch, dist, rank, world, local
+
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def max_over_ranks(self, v):
+        if self.world == 1:
+            return v
+        t = self.torch.tensor([v], dtype=self.torch.float64, device="cuda")
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t)
+
+
+def kernel_shares(torch, engine):
+    """CUPTI (torch.profiler) over ONE replayed step: device time per kernel family.  Not a timing of record (profiler
+    attached) -- it only apportions the step, which is timed separately, to kernel families."""
+    import collections
+    try:
+        with torch.profiler.profile(activities=[torch.profiler.ProfilerActivity.CUDA]) as prof:
+            engine.step(None)
+            torch.cuda.synchronize()
+        agg = collections.defaultdict(lambda: [0, 0.0])
+        for e in prof.events():
+            if e.device_type != torch.autograd.DeviceType.CUDA:
+                continue
+            name = e.name.replace("(anonymous namespace)::", "").split("(")[0].split("<")[0].strip()
+            if name.startswith("at::") or name.startswith("void at::"):
+                name = "aten_glue"
+            elif "nccl" in name.lower():
+                name = "nccl"
+            elif name.startswith("Memset") or name.startswith("Memcpy"):
+                name = "memset_memcpy"
+            agg[name][0] += 1
+            agg[name][1] += (e.time_range.end - e.time_range.start)
+        return {k: {"launches": v[0], "us": round(v[1], 1)} for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1])}
+    except Exception as e:  # noqa: BLE001
+        return {"error": repr(e)[:200]}
+
+
+def time_train(cx, cfg_name, batch, dtype, steps, warmup, graph=True, side_streams=2, with_e2e=True, sampler=None,
+               shares=False, dp_check=False):
+    """Build the model, warm up, time `steps` steps device-resident (`value`) and through TrainEngine.step(x_host) (`e2e`)."""
+    torch = cx.torch
+    import lvae_b200
+    from lvae_b200.engine import TrainEngine
+    from lvae_b200.configs import baseline_config
+    cfg = baseline_config(cfg_name)
+    torch.manual_seed(42)
+    lvae_b200.manual_seed(1234)             # the engine folds the rank into the Philox key
+    model = lvae_b200.LadderVAE(**cfg.kwargs()).cuda()
+    if dtype == "bf16":
+        model.set_compute_dtype(torch.bfloat16)
+    x_host = synthetic_batch(cfg, batch, cx.rank).pin_memory()
+    engine = TrainEngine(model, batch, use_graph=graph, wgrad_side_stream=side_streams)
+    torch.cuda.reset_peak_memory_stats()
+    for _ in range(warmup):
+        engine.step(x_host)
+    torch.cuda.synchronize()
+    mem_gb = torch.cuda.max_memory_allocated() / 2 ** 30
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    cx.barrier()
+    if sampler is not None:
+        sampler.start()
+    e0.record()
+    for _ in range(steps):
+        out = engine.step(None)
+    e1.record()
+    cx.barrier()
+    clocks = sampler.stop() if sampler is not None else None
+    ms = cx.max_over_ranks(e0.elapsed_time(e1)) / steps
+    res = {"value": batch * cx.world / (ms * 1e-3), "unit": "images/s", "ms_per_step": ms, "steps": steps, "warmup": warmup,
+           "dtype": dtype, "per_gpu_batch": batch, "launches_per_step": engine.launches_per_step, "peak_mem_gb": mem_gb,
+           "loss": float(out["loss"]), "clocks": clocks}
+    gflop = CONV_GFLOP[cfg_name][1]
+    res["conv_tflops_per_gpu"] = res["value"] / cx.world * gflop / 1e3
+    if with_e2e:
+        loss_host = torch.zeros((), dtype=torch.float32).pin_memory()
+        cx.barrier()
+        t0 = time.perf_counter()
+        e0.record()
+        for _ in range(steps):
+            out = engine.step(x_host)                         # pinned host -> device copy inside
+            loss_host.copy_(out["loss"], non_blocking=False)  # device -> host read of the loss
+        e1.record()
+        cx.barrier()
+        e2e_ms = cx.max_over_ranks(e0.elapsed_time(e1)) / steps
+        res["e2e"] = {"value": batch * cx.world / (e2e_ms * 1e-3), "unit": "images/s", "h2d_bytes_per_step": x_host.numel() * 4,
+                      "d2h_bytes_per_step": 4, "wall_ms_per_step": (time.perf_counter() - t0) * 1e3 / steps}
+    if shares and cx.rank == 0:
+        res["kernel_shares"] = kernel_shares(torch, engine)
+    elif shares:
+        engine.step(None)                   # keep the ranks in lock-step (the all-reduce inside the step is a collective)
+    if dp_check and cx.world > 1:
+        res["dp_check"] = run_dp_check(cx, engine)
+    engine.arena.detach_sinks()
+    del engine, model
+    torch.cuda.empty_cache()
+    return res
+
+
+def run_dp_check(cx, engine):
+    """(1) After the timed steps every replica must hold bit-identical parameters (same reduced gradients, same Adamax);
+    (2) one more forward/backward: the NCCL-reduced gradient arena must equal the sum of the per-rank arenas (gathered and
+    summed in fp64 here)."""
+    torch, dist = cx.torch, cx.dist
+    flat = engine.arena.flat
+    sums = torch.stack([flat.double().sum(), flat.double().abs().sum(), flat.view(torch.int32).long().sum().double()])
+    allsums = torch.empty((cx.world, 3), dtype=torch.float64, device="cuda")
+    dist.all_gather_into_tensor(allsums, sums)
+    param_diff = float((allsums - allsums[0:1]).abs().max())
+    # gradient arena: manual sum vs NCCL buckets (eager forward/backward on this rank's batch)
+    engine._forward_backward()
+    torch.cuda.synchronize()
+    g_local = engine.arena.grad.clone()
+    n = g_local.numel()
+    manual = torch.zeros(n, dtype=torch.float64, device="cuda")
+    chunk = torch.empty((cx.world, n), dtype=torch.float32, device="cuda")
+    dist.all_gather_into_tensor(chunk, g_local)
+    manual = chunk.double().sum(0)
+    engine._all_reduce()
+    torch.cuda.synchronize()
+    red = engine.arena.grad.double()
+    gdiff = float((red - manual).abs().max() / manual.abs().max())
+    # how different the per-rank gradients were (a check that the ranks really saw different data / noise)
+    spread = float((chunk[0].double() - manual / cx.world).abs().max() / manual.abs().max() * cx.world)
+    return {"param_checksum_max_abs_diff_across_ranks": param_diff, "grad_allreduce_vs_manual_sum_rel": gdiff,
+            "per_rank_grad_spread_rel": spread, "buckets": len(engine.buckets), "arena_mb": n * 4 / 2 ** 20}
+
+
+def time_iw(cx, batch, K, dtype, steps, warmup, graph=True, full_forward=False, sampler=None):
+    torch = cx.torch
+    import lvae_b200
+    from lvae_b200.engine import IWEvaluator, shard_samples
+    from lvae_b200.configs import baseline_config
+    cfg = baseline_config("mnist12")
+    torch.manual_seed(42)
+    lvae_b200.manual_seed(1234)            # the same seed on every rank: the evaluator offsets each rank's samples
+    model = lvae_b200.LadderVAE(**cfg.kwargs()).cuda()
+    if dtype == "bf16":
+        model.set_compute_dtype(torch.bfloat16)
+    x_host = synthetic_batch(cfg, batch, 0).pin_memory()        # every rank evaluates the SAME image batch
+    ev = IWEvaluator(model, batch, use_graph=graph, reuse_bottomup=not full_forward)
+    x_dev = x_host.cuda()
+    k_warm = max(8, cx.world)
+    for _ in range(warmup):
+        ev.bound(x_dev, k_warm)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    cx.barrier()
+    if sampler is not None:
+        sampler.start()
+    e0.record()
+    for _ in range(steps):
+        res = ev.bound(x_dev, K)
+    e1.record()
+    cx.barrier()
+    clocks = sampler.stop() if sampler is not None else None
+    ms = cx.max_over_ranks(e0.elapsed_time(e1)) / steps
+    value = batch / (ms * 1e-3)                                  # images whose K-sample bound completes per second
+    cx.barrier()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        res = ev.bound(x_host, K)
+        res_host = res.cpu()
+    torch.cuda.synchronize()
+    e2e_ms = cx.max_over_ranks((time.perf_counter() - t0) * 1e3) / steps
+    _, k_local = shard_samples(K, cx.rank, cx.world)
+    unit = "images/s with a %d-sample bound" % K
+    fwd_gflop = CONV_GFLOP["mnist12"][0]
+    out = {"metric": "IW-%d evals/s (MNIST 12-layer LVAE)" % K, "value": value, "unit": unit, "n_gpus": cx.world, "steps": steps,
+           "warmup": warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "dtype": dtype,
+           "config": iw_config(K, cx.world, batch, full_forward),
+           "sample_forwards_per_s": value * K,
+           "samples_per_rank": k_local,
+           "bound_mean_nats": float(res_host.mean()),
+           "e2e": {"value": batch / (e2e_ms * 1e-3), "unit": unit, "h2d_bytes_per_step": x_host.numel() * 4,
+                   "d2h_bytes_per_step": res_host.numel() * 4},
+           "gpu_launches": (ev.launches_per_sample * k_local + ev.launches_bottomup) * steps,
+           "launches_per_sample": ev.launches_per_sample,
+           # one sample pass = the top-down half of the forward convolutions (the bottom-up pass runs once per batch)
+           "conv_tflops_per_gpu_upper": value * K / cx.world * fwd_gflop / 1e3,
+           "clocks": clocks}
+    del ev, model
+    torch.cuda.empty_cache()
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -266,6 +489,8 @@ def main():
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-hbm-rooflines", action="store_true", help="skip the stochastic / likelihood kernel microbenchmarks")
+    ap.add_argument("--no-extras", action="store_true",
+                    help="train workload: skip the iw / configs / value_f32 / dp_check sub-records (A/B timing runs)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -277,152 +502,113 @@ def main():
 
     import torch
     import torch.distributed as dist
-    import lvae_b200
-    from lvae_b200 import _capi
-    from lvae_b200.engine import IWEvaluator, TrainEngine
-    from lvae_b200.configs import baseline_config        # product-side config table (the oracle is only the cpu_baseline leg)
+    import lvae_b200  # noqa: F401
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the product has no CPU path")
     torch.cuda.set_device(local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        os.environ["NCCL_DEBUG"] = "WARN"          # keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    cx = Ctx(torch, dist, rank, world, local)
     pk = peaks()
     cfg_name, batch = CONFIGS[args.workload]
     batch = args.batch or batch
-    cfg = baseline_config(cfg_name)
-    torch.manual_seed(42)
-    lvae_b200.manual_seed(1234 + rank)
-    model = lvae_b200.LadderVAE(**cfg.kwargs()).cuda()
-    if args.dtype == "bf16":
-        model.set_compute_dtype(torch.bfloat16)
-    x_host = synthetic_batch(cfg, batch, rank).pin_memory()
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def max_over_ranks(v):
-        if world == 1:
-            return v
-        t = torch.tensor([v], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t)
-
     sampler = ClockSampler(local)
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    loss_host = torch.zeros((), dtype=torch.float32).pin_memory()
+    graph = not args.no_graph
+    side = 0 if args.no_side_stream else args.side_streams
 
     if args.workload == "iw":
-        K = args.iw_samples
-        ev = IWEvaluator(model, batch, use_graph=not args.no_graph, reuse_bottomup=not args.iw_full_forward)
-        x_dev = x_host.cuda()
-        k_warm = max(8, world)
-        for _ in range(args.warmup):
-            ev.bound(x_dev, k_warm)
-        barrier()
-        sampler.start()
-        e0.record()
-        for _ in range(args.steps):
-            res = ev.bound(x_dev, K)
-        e1.record()
-        barrier()
-        clocks = sampler.stop()
-        ms = max_over_ranks(e0.elapsed_time(e1)) / args.steps
-        value = batch / (ms * 1e-3)                                  # images whose K-sample bound completes per second
-        barrier()
-        t0 = time.perf_counter()
-        for _ in range(args.steps):
-            res = ev.bound(x_host, K)
-            res_host = res.cpu()
-        torch.cuda.synchronize()
-        e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3) / args.steps
-        _, k_local = lvae_b200.engine.shard_samples(K, rank, world)
-        launches = (ev.launches_per_sample * k_local + ev.launches_bottomup) * args.steps
-        line = {"metric": "IW-%d evals/s (MNIST 12-layer LVAE)" % K, "value": value, "unit": "images/s with a %d-sample bound" % K,
-                "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
-                "scaling": "strong", "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
-                "config": {"workload": "importance-weighted bound, K=%d samples sharded over %d GPU(s), test batch %d, "
-                                       "binarized-MNIST-shaped 12-layer LVAE, eval mode" % (K, world, batch),
-                           "bottom_up_pass": "per sample (as the reference)" if args.iw_full_forward else "once per image batch (eval mode is deterministic)",
-                           "l2_policy": "per-sample working set exceeds L2"},
-                "sample_forwards_per_s": value * K,
-                "e2e": {"value": batch / (e2e_ms * 1e-3), "unit": "images/s with a %d-sample bound" % K,
-                        "h2d_bytes_per_step": x_host.numel() * 4, "d2h_bytes_per_step": res_host.numel() * 4},
-                "gpu_launches": launches, "clocks": clocks}
+        line = time_iw(cx, batch, args.iw_samples, args.dtype, args.steps, args.warmup, graph, args.iw_full_forward, sampler)
+        line.update({"vs_baseline": None, "data": "synthetic"})
         if rank == 0 and world == 1 and not args.no_hbm_rooflines:
             line["roofline_hbm"] = hbm_rooflines("iw")
         if rank == 0 and not args.no_cpu_baseline and world == 1:
             line["cpu_baseline"] = {k: v for k, v in cpu_baseline_iw(32, 3).items() if k != "s_per_forward"}
-        if rank == 0:
-            print(json.dumps(line), flush=True)
-        if world > 1:
-            dist.destroy_process_group()
+        finish(cx, line)
         return
 
-    engine = TrainEngine(model, batch, use_graph=not args.no_graph, wgrad_side_stream=0 if args.no_side_stream else args.side_streams)
-    for _ in range(args.warmup):
-        engine.step(x_host)
-    torch.cuda.synchronize()
-    mem_gb = torch.cuda.max_memory_allocated() / 2 ** 30
-
-    # ---- device-resident timing: `value` ----
-    barrier()
-    sampler.start()
-    e0.record()
-    for _ in range(args.steps):
-        out = engine.step(None)
-    e1.record()
-    barrier()
-    clocks = sampler.stop()
-    ms = max_over_ranks(e0.elapsed_time(e1)) / args.steps
-    value = batch * world / (ms * 1e-3)
-    final_loss = float(out["loss"])
-
-    # ---- end to end through the public API with host buffers: `e2e` ----
-    barrier()
-    t0 = time.perf_counter()
-    e0.record()
-    for _ in range(args.steps):
-        out = engine.step(x_host)                       # pinned host -> device copy inside
-        loss_host.copy_(out["loss"], non_blocking=False)  # device -> host read of the loss
-    e1.record()
-    barrier()
-    e2e_ms = max_over_ranks(e0.elapsed_time(e1)) / args.steps
-    e2e_wall_ms = (time.perf_counter() - t0) * 1e3 / args.steps
-
+    main_res = time_train(cx, cfg_name, batch, args.dtype, args.steps, args.warmup, graph, side, True, sampler,
+                          shares=not args.no_extras, dp_check=not args.no_extras)
+    value = main_res["value"]
     gflop = CONV_GFLOP[cfg_name][1]
-    line = {"metric": "train images/s (%s LVAE)" % {"cifar15": "CIFAR10 15-layer"}.get(cfg_name, cfg_name),
+    line = {"metric": "train images/s (%s LVAE)" % METRIC_NAME.get(cfg_name, cfg_name),
             "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": args.dtype,
-            "data": "synthetic",
-            "config": {"workload": "ELBO training step (zero grad, forward, loss, backward, gradient all-reduce, Adamax), "
-                                   "%s, 10-component DMoL, dropout 0.2, train-mode BatchNorm" % cfg_name,
-                       "per_gpu_batch": batch, "global_batch": batch * world, "parallelism": "dp%d" % world,
-                       "cuda_graph": not args.no_graph,
-                       "l2_policy": "inputs larger than L2: each step streams %.1f GB of activations" % mem_gb},
-            "e2e": {"value": batch * world / (e2e_ms * 1e-3), "unit": "images/s", "h2d_bytes_per_step": x_host.numel() * 4,
-                    "d2h_bytes_per_step": 4, "wall_ms_per_step": e2e_wall_ms},
-            "gpu_launches": engine.launches_per_step * args.steps,
-            "launches_per_step": engine.launches_per_step,
-            "clocks": clocks,
-            "whole_step_conv_tflops": value / world * gflop / 1e3,
-            "whole_step_frac_of_bf16_sustained": value / world * gflop / 1e3 / pk["tf_sustained"],
-            "peak_mem_gb": mem_gb, "loss": final_loss}
+            "ms_per_step": main_res["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": args.dtype, "data": "synthetic",
+            "config": train_config(cfg_name, batch, world, graph),
+            "e2e": main_res["e2e"],
+            "gpu_launches": main_res["launches_per_step"] * args.steps,
+            "launches_per_step": main_res["launches_per_step"],
+            "clocks": main_res["clocks"],
+            "peak_mem_gb": main_res["peak_mem_gb"], "loss": main_res["loss"]}
+    if "dp_check" in main_res:
+        line["dp_check"] = main_res["dp_check"]
+    # whole step against the SUSTAINED tensor peak (the step is a long back-to-back run), per GPU
+    step_tf = value / world * gflop / 1e3
+    line["roofline_step"] = {"bound": "tensor", "achieved": step_tf, "peak": pk["tf_sustained"], "unit": "TFLOP/s",
+                             "frac": step_tf / pk["tf_sustained"],
+                             "what": "algorithmic conv FLOPs of the whole step (%.3f GFLOP / image, SURVEY.md 8) / step time, "
+                                     "against the %s sustained bf16 peak" % (gflop, pk["src"])}
+    if rank == 0 and "kernel_shares" in main_res:
+        ks = main_res["kernel_shares"]
+        line["kernel_shares"] = ks
+        # in-step rates of the contraction kernels: forward + dgrad FLOPs (2/3 of the step) over the summed conv_tc time,
+        # wgrad FLOPs (1/3) over the summed wgrad time -- CUPTI durations of one replayed step, kernels overlap across streams
+        tot = batch * gflop * 1e9
+        ins = {}
+        t_conv = sum(v["us"] for k, v in ks.items() if isinstance(v, dict) and k.startswith(("conv_tc", "conv_gate_tc", "gate_dgrad_tc")))
+        t_wg = sum(v["us"] for k, v in ks.items() if isinstance(v, dict) and k.startswith("wgrad_tc"))
+        if t_conv > 0:
+            a = tot * 2 / 3 / (t_conv * 1e-6) / 1e12
+            ins["conv_tc_fwd_dgrad"] = {"achieved": a, "peak": pk["tf_sustained"], "unit": "TFLOP/s", "frac": a / pk["tf_sustained"], "us_in_step": t_conv}
+        if t_wg > 0:
+            a = tot / 3 / (t_wg * 1e-6) / 1e12
+            ins["wgrad_tc"] = {"achieved": a, "peak": pk["tf_sustained"], "unit": "TFLOP/s", "frac": a / pk["tf_sustained"], "us_in_step": t_wg}
+        line["roofline_in_step"] = ins
     if rank == 0:
         line["roofline"] = conv_roofline(torch, pk, args.dtype)
         if world == 1 and not args.no_hbm_rooflines:
             line["roofline_hbm"] = hbm_rooflines(args.workload)
-        if not args.no_cpu_baseline and world == 1:          # the CPU baseline is a single-GPU-run item (rank 0, N = 1 only)
-            cb = cpu_baseline_train(cfg_name, 16, 6)          # ~5-10 s of CPU work on the box's host cores
-            line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
+    if not args.no_extras and args.workload == "train":
+        # ---- the exact-fp32 mode of the same step (the mode the 1e-4 / 1e-3 parity bounds are stated for) ----
+        if args.dtype == "bf16":
+            r = time_train(cx, cfg_name, batch, "f32", 4, 3, graph, side, False)
+            line["value_f32"] = {k: r[k] for k in ("value", "unit", "ms_per_step", "steps", "warmup", "dtype", "launches_per_step")}
+            line["value_f32"]["what"] = "same step, exact fp32 CUDA-core convolutions (parity mode)"
+        # ---- the other BASELINE.json training configs, a short timing each ----
+        cfgs = {}
+        for name, key in (("mnist3", "mnist3_b64"), ("mnist12", "mnist12_b128"), ("celeba20", "celeba20_b64")):
+            b = CONFIGS[name][1]
+            r = time_train(cx, name, b, "bf16", 8, 3, graph, side, True)
+            keep = ("value", "unit", "ms_per_step", "steps", "warmup", "dtype", "per_gpu_batch", "launches_per_step", "peak_mem_gb",
+                    "e2e", "conv_tflops_per_gpu")
+            cfgs[key] = {k: r[k] for k in keep}
+            cfgs[key]["n_gpus"] = world
+            cfgs[key]["frac_of_bf16_sustained"] = r["conv_tflops_per_gpu"] / pk["tf_sustained"]
+        line["configs"] = cfgs
+        # ---- the second half of the metric: IW-1000 on MNIST-12, samples sharded over the ranks ----
+        iw = time_iw(cx, CONFIGS["iw"][1], args.iw_samples, "bf16", 1, 3, graph, False)
+        if rank == 0 and world == 1 and not args.no_cpu_baseline:
+            iw["cpu_baseline"] = {k: v for k, v in cpu_baseline_iw(32, 3).items() if k != "s_per_forward"}
+        if rank == 0 and world == 1 and not args.no_hbm_rooflines:
+            iw["roofline_hbm"] = hbm_rooflines("iw")
+        line["iw"] = iw
+    if rank == 0 and not args.no_cpu_baseline and world == 1:          # the CPU baseline is a single-GPU-run item (rank 0, N = 1 only)
+        cb = cpu_baseline_train(cfg_name, CPU_BATCH, 5)          # ~10 s of CPU work on the box's host cores
+        line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
+    finish(cx, line)
+
+
+def finish(cx, line):
+    """The ONE JSON line goes out last, after the process group is gone (NCCL's own INFO lines, if the driver asked for
+    them, are then already written)."""
+    if cx.world > 1:
+        cx.dist.barrier()
+        cx.dist.destroy_process_group()
+    sys.stderr.flush()
+    if cx.rank == 0:
         print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
 
 
 if __name__ == "__main__":

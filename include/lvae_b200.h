@@ -116,13 +116,6 @@ int lvae_conv2d_tc_ex(const void* x, const void* x2, const void* wp, const float
 int lvae_conv_gate_tc(const void* a2, const void* w2p, const float* bias2, const float* scale2, const void* wgp,
                       const float* bias_g, const void* x_res, void* c2, void* h, void* out, double* stats_acc, int B, int H,
                       int W, int gate_act, lvae_stream_t stream);
-/* Backward of the gate + data gradient of the 1x1 gate conv as one launch (opt-in from Python with LVAE_GATE_BWD_CHAIN=1;
- * csrc/gate_dgrad_tcgen05.cu): dh = backward of act(a) * sigmoid(g) wrt h = [a | g] (lib/nn.py:121-126), stored for the gate
- * conv's weight gradient and used in place as the A operand of dc2 = (dh . Wg) * scale (lib/nn.py:118 backward).
- * dout (P,64), h (P,128), dh (P,128), dc2 (P,64): bf16, P = B * hw.  wpb: packed dgrad weights of the gate conv (two [64][64]
- * k-blocks, lvae_pack_weights mode 3).  scale: (B,64) Dropout2d mask or NULL. */
-int lvae_gate_bwd_dgrad_tc(const void* dout, const void* h, const void* wpb, const float* scale, void* dh, void* dc2, int B,
-                           int hw, int act, lvae_stream_t stream);
 /* Stride-2 3x3 convolutions 64 -> 64 on the same tcgen05 kernel (the down / up-sampling pre_convs of
  * models/lvae_layers.py:261-276).  kind 0 "gather": y (B,Hg,Wg,N) from x (B,2Hg,2Wg,64) = Conv2d(stride 2, pad 1) forward
  * and ConvTranspose2d(stride 2, pad 1, output_padding 1) input gradient (TMA traverses x with element stride 2).  kind 1
@@ -240,9 +233,11 @@ int lvae_dmol_sample(const float* l, float* out_nchw, int B, int hw, const void*
                      unsigned long long stream_id, lvae_stream_t stream);
 
 /* ---- step glue: experiment/experiment_manager.py:78-80 (Adamax), :346-350 (L2 norm) ---- */
+/* hyper_dev: NULL, or a device float[2] = {lr, weight_decay} that overrides the by-value arguments (a captured CUDA graph
+ * then follows learning-rate schedules without a recapture). */
 int lvae_adamax_step(float* p, const float* g, float* exp_avg, float* exp_inf, long long n, float lr, float beta1,
                      float beta2, float eps, float weight_decay, long long* step_count_dev, float grad_scale,
-                     lvae_stream_t stream);
+                     const float* hyper_dev, lvae_stream_t stream);
 int lvae_l2_norm(const float* p, long long n, double* acc, float* out, lvae_stream_t stream);
 
 /* ---- importance-weighted bound (boilr test_procedure, call site evaluate.py:30) ----

@@ -25,7 +25,6 @@ _SIGNATURES = {
     "lvae_conv2d_tc_ex": [P, P, P, P, P, P, P, P, I, I, I, I, I, I, I, I, I, P, P],
     "lvae_conv2d_tc_s2": [P, P, P, P, P, I, I, I, I, I, P],
     "lvae_conv_gate_tc": [P, P, P, P, P, P, P, P, P, P, P, I, I, I, I, P],
-    "lvae_gate_bwd_dgrad_tc": [P, P, P, P, P, P, I, I, I, P],
     "lvae_conv3x3_narrow": [P, P, P, P, I, I, I, I, I, P],
     "lvae_channel_scale": [P, P, P, I, I, I, I, P],
     "lvae_conv2d_wgrad_tc": [P, P, P, P, P, P, I, I, I, I, I, I, I, I, I, P],
@@ -57,7 +56,7 @@ _SIGNATURES = {
     "lvae_dmol_fwd": [P, P, P, I, I, P],
     "lvae_dmol_bwd": [P, P, P, P, P, I, I, P],
     "lvae_dmol_sample": [P, P, I, I, P, U, P],
-    "lvae_adamax_step": [P, P, P, P, L, F, F, F, F, F, P, F, P],
+    "lvae_adamax_step": [P, P, P, P, L, F, F, F, F, F, P, F, P, P],
     "lvae_l2_norm": [P, L, P, P, P],
     "lvae_iw_lse_update": [P, P, P, I, I, P],
     "lvae_iw_lse_combine": [P, P, I, I, I, P],

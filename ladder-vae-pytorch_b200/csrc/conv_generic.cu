@@ -516,11 +516,21 @@ __global__ void pack_weights_kernel(const LvaePackDesc* descs, int n) {
   }
 }
 
+// Consumers (conv_tc_kernel and friends) TMA-load packed weights in their prologue, BEFORE griddepcontrol.wait, on the
+// invariant of common.cuh that weights were written two or more kernels upstream.  This separator makes the invariant hold
+// for whoever launches right after a pack: its dependents can only start once it has seen the pack kernel complete.
+__global__ void pack_fence_kernel() {
+  pdl_wait();
+  pdl_launch();
+}
+
 // descs: DEVICE array of n descriptors (built once by the host; weights are re-packed every step)
 LVAE_API int lvae_pack_weights(const void* descs_dev, int n, cudaStream_t stream) {
   LVAE_REQUIRE(descs_dev && n > 0, "pack_weights: bad args");
   dim3 grid(8, n < 65535 ? n : 65535);
   lvae_launch(pack_weights_kernel, grid, 256, 0, stream, (const LvaePackDesc*)descs_dev, n);
+  LVAE_COUNT_LAUNCH();
+  lvae_launch(pack_fence_kernel, 1, 32, 0, stream);
   LVAE_COUNT_LAUNCH();
   LVAE_CHECK_LAUNCH("pack_weights");
   return LVAE_OK;

@@ -30,8 +30,6 @@ constexpr int TC_BM = 128;             // pixels per tile
 constexpr int TC_BK = 64;              // channels per k-block (= one 128-byte swizzle row of bf16)
 constexpr int TC_STAGE_BYTES = TC_BM * TC_BK * 2;   // 16 KB
 constexpr int TC_MAX_KB = 36;          // k-blocks per tile: taps x input k-blocks
-constexpr int TC_F32_PITCH = 17;       // floats per row of a warp's 32 x 16 transposition buffer (odd pitch: conflict-free row writes)
-constexpr int TC_F32_STAGE_BYTES = 8 * 32 * TC_F32_PITCH * 4;   // eight epilogue warps
 
 struct TcParams {
   const float* bias;        // [N] or null
@@ -60,10 +58,7 @@ struct TcParams {
   int gate_act;
   int gate_skip_h;          // eval mode: h = [a | g] is only staged for the gate pass, never stored (nothing runs backward)
   int tma_store;            // bf16 output, N % 64 == 0, no residual: epilogue stages the tile in smem and stores it with TMA
-  int f32_stage;            // fp32 output, no residual / split (LVAE_CONV_F32_STAGE=1): each epilogue warp transposes 32 rows x 16
-                            // columns through a private smem buffer, so the global stores are 64-byte row segments
   long long* dbg;           // optional per-tile clock64 trace of CTA 0 (profiling aid, normally null)
-  int* sched;               // dynamic tile scheduler (DYN kernels): {next tile, finished CTAs}, zero between launches
   int8_t dx[TC_MAX_KB], dy[TC_MAX_KB], src[TC_MAX_KB], coff[TC_MAX_KB];   // coff: channel offset / 64 inside the tensor
   // stride-2 convolutions (lvae_conv2d_tc_s2): the tile's pixel coordinates are multiplied by in_stride before the tap
   // offset is added (the input tensor map then traverses with the same element stride), and k-block kb reads weight
@@ -154,51 +149,6 @@ __device__ __forceinline__ uint32_t elect_one() {
 }
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-// ---- CTA pair (cta_group::2, PAIR kernels): two CTAs of a cluster run ONE tcgen05.mma of M = 256 -- each CTA contributes its
-// own 128-pixel A tile and its own TMEM accumulator, and HALF of the B (weight) rows, so a CTA reads 4 KB + 1 KB instead of
-// 4 KB + 2 KB of shared memory per MMA.  Only the even CTA (the leader) issues MMAs; TMA loads of both CTAs complete on the
-// leader's barriers, tcgen05.commit multicasts its arrivals to both CTAs.
-__device__ __forceinline__ uint32_t cluster_ctarank() {
-  uint32_t r;
-  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-  return r;
-}
-// shared::cluster address of the same shared-memory offset in CTA `rank` of this cluster
-__device__ __forceinline__ uint32_t mapa_u32(uint32_t saddr, uint32_t rank) {
-  uint32_t r;
-  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(rank));
-  return r;
-}
-__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_bar) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_bar) : "memory");
-}
-__device__ __forceinline__ void cluster_sync_all() {
-  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
-  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tma_load_4d_pair(uint32_t dst, const CUtensorMap* tm, uint32_t leader_bar, int c0, int c1, int c2, int c3) {
-  asm volatile(
-      "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
-      ::"r"(dst), "l"(tm), "r"(leader_bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
-}
-__device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap* tm, uint32_t leader_bar, int c0, int c1) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-      ::"r"(dst), "l"(tm), "r"(leader_bar), "r"(c0), "r"(c1) : "memory");
-}
-__device__ __forceinline__ void umma_bf16_pair(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-  const uint32_t z = 0;
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, {%5, %5, %5, %5, %5, %5, %5, %5}, p;\n\t}"
-      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(z) : "memory");
-}
-// arrive on the barrier at this shared-memory offset in BOTH CTAs of the pair once the MMAs issued so far have retired
-__device__ __forceinline__ void umma_commit_pair(uint32_t bar) {
-  const uint16_t mask = 3;
-  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"(mask) : "memory");
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -296,14 +246,12 @@ __device__ __forceinline__ void epilogue16(const uint32_t* __restrict__ r, const
 }
 
 // FUSE: 0 plain epilogue, 1 output statistics (stats_acc), 2 BatchNorm-backward sums (bnb_*), 3 gated residual output
-// (+ its statistics), 4 plain epilogue with warp-transposed (coalesced) fp32 stores (p.f32_stage).  A template parameter so
-// that the plain kernel carries no accumulator registers (the 10-warp CTA caps ptxas at 168 registers per thread).
-// DYN (LVAE_CONV_DYNAMIC=1): tiles are not assigned round-robin but drawn from a global counter by the producer warp and
-// handed to the MMA / epilogue warps through a shared-memory ring, so a CTA that reaches its SM late (the SMs are shared
-// with the weight-gradient kernels of the side streams) takes fewer tiles instead of stretching the launch.
-constexpr int TC_RING = 4;
-// PAIR (LVAE_CONV_CTA2=1; halo mode, N == 64, an even number of tiles): CTA pairs on cta_group::2, see the helpers above.
-template <int FUSE, bool DYN, bool PAIR = false>
+// (+ its statistics).  A template parameter so that the plain kernel carries no accumulator registers (the 10-warp CTA
+// caps ptxas at 168 registers per thread).
+// Round-2 A/B on the B200 (profiles/ab_r02_summary.txt) retired three variants of this kernel that held parity but lost time:
+// CTA pairs on cta_group::2 (576 vs 834 TFLOP/s at 32x32), a dynamic tile scheduler (+0.15 ms / step) and a warp-transposed
+// fp32 epilogue (90 vs 51 us for the 64 -> 100 head).
+template <int FUSE>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmY,
@@ -312,13 +260,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
   // 1024-byte alignment for the 128B swizzle atoms
   // (offset arithmetic on the __shared__ array, not on a uintptr_t: the compiler keeps the shared address space)
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  const int wbytes_kb = (PAIR ? p.Npad / 2 : p.Npad) * 128;  // one k-block of weights (a CTA pair holds half of the rows each)
+  const int wbytes_kb = p.Npad * 128;                        // one k-block of weights
   uint8_t* sW = smem;                                        // n_kb * Npad * 128
   uint8_t* sA = sW + ((p.n_kb * wbytes_kb + 1023) & ~1023);  // n_stages * 16 KB
   const int stage_bytes = p.halo ? p.stage_bytes : TC_STAGE_BYTES;
   uint8_t* sOut = sA + p.n_stages * stage_bytes;             // (N/64) x 16 KB output staging (TMA-store epilogue only)
-  uint64_t* bars = (uint64_t*)(sOut + (p.tma_store ? (p.Npad / 64 + (FUSE == 3 ? 1 : 0)) * TC_STAGE_BYTES
-                                                   : (FUSE == 4 ? TC_F32_STAGE_BYTES : 0)));
+  uint64_t* bars = (uint64_t*)(sOut + (p.tma_store ? (p.Npad / 64 + (FUSE == 3 ? 1 : 0)) * TC_STAGE_BYTES : 0));
   // barrier layout: [0..S) full, [S..2S) empty, 2S: weights, 2S+1..2S+2: tmem_full[2], 2S+3..2S+4: tmem_empty[2]
   const int S = p.n_stages;
   uint32_t* tmem_slot = (uint32_t*)(bars + 2 * S + 5);
@@ -326,10 +273,6 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
   float* sred = sbias + 256;                                  // 2 statistics x 8 warps x 64 channels (fused reductions)
   const uint32_t bar0 = smem_u32(bars);
   auto BAR = [&](int i) { return bar0 + 8u * (uint32_t)i; };
-  int* const ring_ids = (int*)(sred + 2 * 8 * 64);               // TC_RING tile indices (DYN only)
-  const uint32_t rbar0 = smem_u32(ring_ids + TC_RING);           // TC_RING "published" + TC_RING "consumed" barriers
-  auto RFULL = [&](int i) { return rbar0 + 8u * (uint32_t)i; };
-  auto REMPTY = [&](int i) { return rbar0 + 8u * (uint32_t)(TC_RING + i); };
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_tiles = p.halo ? (p.M_total / (p.H * p.W)) * p.tiles_per_img : (p.M_total + TC_BM - 1) / TC_BM;
@@ -345,20 +288,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     mbar_init(BAR(2 * S), 1);
     mbar_init(BAR(2 * S + 1), 1);
     mbar_init(BAR(2 * S + 2), 1);
-    mbar_init(BAR(2 * S + 3), PAIR ? 16 : 8);      // one arrive per epilogue warp (of both CTAs of a pair, on the leader)
-    mbar_init(BAR(2 * S + 4), PAIR ? 16 : 8);
-    if (DYN) {
-      for (int i = 0; i < TC_RING; ++i) {
-        mbar_init(RFULL(i), 1);          // the producer's elected lane
-        mbar_init(REMPTY(i), 9);         // MMA warp + eight epilogue warps
-      }
-    }
+    mbar_init(BAR(2 * S + 3), 8);                  // one arrive per epilogue warp
+    mbar_init(BAR(2 * S + 4), 8);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  const uint32_t pair_rank = PAIR ? cluster_ctarank() : 0u;
-  // shared::cluster address, in the pair's leader, of the barrier at this CTA's offset `bar`
-  auto LEADER = [&](uint32_t bar) { return mapa_u32(bar, 0u); };
-  if (!PAIR && warp == 0) {
+  if (warp == 0) {
     __syncwarp();
     // weights were packed many kernels ago: fetch them before waiting on the previous kernel (PDL prologue)
     if (elect_one()) {
@@ -370,66 +304,22 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
   }
   for (int i = threadIdx.x; i < p.Npad; i += TC_THREADS) sbias[i] = (p.bias && i < p.N) ? p.bias[i] : 0.f;
   if (warp == 1) {
-    if (PAIR) {
-      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(p.tmem_cols) : "memory");
-      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
-    } else {
-      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(p.tmem_cols) : "memory");
-      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-    }
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(p.tmem_cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   tc_fence_before();
-  if (PAIR) cluster_sync_all();          // the peer's barriers are initialised before anything signals them
-  else __syncthreads();
+  __syncthreads();
   tc_fence_after();
-  if (PAIR && warp == 0) {
-    // both CTAs' halves of the weights complete on the leader's barrier (only the leader's MMA warp waits for them)
-    if (elect_one()) {
-      if (pair_rank == 0) mbar_expect_tx(BAR(2 * S), (uint32_t)(2 * p.n_kb * wbytes_kb));
-      const uint32_t lbar = LEADER(BAR(2 * S));
-      for (int kb = 0; kb < p.n_kb; ++kb)
-        tma_load_2d_pair(smem_u32(sW + kb * wbytes_kb), &tmW, lbar, 0,
-                         (p.use_wblk ? p.wblk[kb] : kb) * p.Npad + (int)pair_rank * (p.Npad / 2));
-    }
-    __syncwarp();
-  }
   const uint32_t tmem_base = *tmem_slot;
   pdl_wait();          // activations / residual / dropout mask come from the previous kernels
   pdl_launch();
-  // tile sequence of this CTA (warp-converged calls): round-robin, or drawn from / read out of the ring
-  int ring_i = 0;
-  uint32_t ring_ph = 0;
-  auto draw_tile = [&]() -> int {                                 // producer warp
-    int t = 0;
-    if (lane == 0) t = atomicAdd(p.sched, 1);
-    t = __shfl_sync(0xffffffffu, t, 0);
-    if (t >= n_tiles) t = -1;
-    mbar_wait(REMPTY(ring_i), ring_ph ^ 1);
-    if (lane == 0) {
-      ring_ids[ring_i] = t;
-      mbar_arrive(RFULL(ring_i));                                 // release: the index is visible to whoever sees the phase flip
-    }
-    __syncwarp();
-    if (++ring_i == TC_RING) { ring_i = 0; ring_ph ^= 1; }
-    return t;
-  };
-  auto take_tile = [&]() -> int {                                 // MMA warp, epilogue warps
-    mbar_wait(RFULL(ring_i), ring_ph);
-    const int t = ring_ids[ring_i];
-    __syncwarp();
-    if (lane == 0) mbar_arrive(REMPTY(ring_i));
-    if (++ring_i == TC_RING) { ring_i = 0; ring_ph ^= 1; }
-    return t;
-  };
-
   if (warp == 0) {
     // ===================== TMA producer (whole warp loops, one elected lane issues) =====================
     {
       int stage = 0;
       uint32_t phase = 0;
       const int hw = p.H * p.W;
-      for (int tile = DYN ? draw_tile() : (int)blockIdx.x; DYN ? tile >= 0 : tile < n_tiles;
-           tile = DYN ? draw_tile() : tile + (int)gridDim.x) {
+      for (int tile = (int)blockIdx.x; tile < n_tiles; tile += (int)gridDim.x) {
         if (p.halo) {
           int n0 = tile / p.tiles_per_img;
           int r = tile - n0 * p.tiles_per_img;
@@ -437,14 +327,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
           mbar_wait(BAR(S + stage), phase ^ 1);
           if (p.dbg && blockIdx.x == 0 && lane == 0) p.dbg[(tile / gridDim.x) * 8 + 6] = clock64();
           if (elect_one()) {
-            if (PAIR) {
-              // the leader's barrier collects both CTAs' tiles (the peer's bytes may land before the leader has armed it)
-              if (pair_rank == 0) mbar_expect_tx(BAR(stage), (uint32_t)(2 * stage_bytes));
-              tma_load_4d_pair(smem_u32(sA + stage * stage_bytes), &tmA0, LEADER(BAR(stage)), 0, tx * 8 - 1, ty * 16 - 1, n0);
-            } else {
-              mbar_expect_tx(BAR(stage), (uint32_t)stage_bytes);
-              tma_load_4d(smem_u32(sA + stage * stage_bytes), &tmA0, BAR(stage), 0, tx * 8 - 1, ty * 16 - 1, n0);
-            }
+            mbar_expect_tx(BAR(stage), (uint32_t)stage_bytes);
+            tma_load_4d(smem_u32(sA + stage * stage_bytes), &tmA0, BAR(stage), 0, tx * 8 - 1, ty * 16 - 1, n0);
           }
           __syncwarp();
           if (++stage == S) { stage = 0; phase ^= 1; }
@@ -468,21 +352,20 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         }
       }
     }
-  } else if (warp == 1 && pair_rank == 0) {
-    // ===================== MMA issuer (pair mode: the leader CTA only) =====================
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
     // The whole warp runs the loop (converged); one elected lane issues tcgen05.mma / tcgen05.commit, so ptxas keeps
     // descriptors and the TMEM address in uniform registers.
     {
       // instruction descriptor: D fp32, A/B bf16, both K-major, M = 128, N = Npad
-      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.Npad >> 3) << 17) | ((uint32_t)((PAIR ? 2 * TC_BM : TC_BM) >> 4) << 24);
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.Npad >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
       const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
       mbar_wait(BAR(2 * S), 0);
       tc_fence_after();
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
-      for (int tile = DYN ? take_tile() : (int)blockIdx.x; DYN ? tile >= 0 : tile < n_tiles;
-           tile = DYN ? take_tile() : tile + (int)gridDim.x, ++it) {
+      for (int tile = (int)blockIdx.x; tile < n_tiles; tile += (int)gridDim.x, ++it) {
         const int buf = it & 1;
         const uint32_t use = (uint32_t)(it >> 1);
         mbar_wait(BAR(2 * S + 3 + buf), (use & 1) ^ 1);      // epilogue drained this accumulator
@@ -502,17 +385,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
               const uint64_t bdesc = umma_desc_k_sw128(smem_u32(sW + kb * wbytes_kb));
 #pragma unroll
               for (int k = 0; k < TC_BK / 16; ++k) {
-                if (PAIR) umma_bf16_pair(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (uint32_t)((kb | k) != 0));
-                else umma_bf16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (uint32_t)((kb | k) != 0));
+                umma_bf16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (uint32_t)((kb | k) != 0));
               }
             }
-            if (PAIR) {
-              umma_commit_pair(BAR(S + stage));           // both CTAs' producers may refill this stage
-              umma_commit_pair(BAR(2 * S + 1 + buf));     // both CTAs' epilogues may drain their halves of the accumulator
-            } else {
-              umma_commit(BAR(S + stage));
-              umma_commit(BAR(2 * S + 1 + buf));
-            }
+            umma_commit(BAR(S + stage));
+            umma_commit(BAR(2 * S + 1 + buf));
           }
           __syncwarp();
           if (++stage == S) { stage = 0; phase ^= 1; }
@@ -582,8 +459,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
       }
     };
     int it = 0;
-    for (int tile = DYN ? take_tile() : (int)blockIdx.x; DYN ? tile >= 0 : tile < n_tiles;
-         tile = DYN ? take_tile() : tile + (int)gridDim.x, ++it) {
+    for (int tile = (int)blockIdx.x; tile < n_tiles; tile += (int)gridDim.x, ++it) {
       const int buf = it & 1;
       const uint32_t use = (uint32_t)(it >> 1);
       if (p.dbg && blockIdx.x == 0 && warp == 2 && lane == 0) p.dbg[it * 8 + 3] = clock64();
@@ -603,7 +479,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
       const int b = valid ? (int)(m / hw) : 0;
       const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * p.Npad);
       const float* scale_row = p.out_scale ? p.out_scale + (long long)b * p.N : nullptr;
-      if ((FUSE != 0 && FUSE != 4) || p.tma_store) {
+      if (FUSE != 0 || p.tma_store) {
         // ---- TMEM -> registers (bias, Dropout2d scale, bf16 pack), release the accumulator, stage in smem, TMA store ----
         constexpr int NCH = (FUSE == 1 || FUSE == 2) ? 1 : 2;       // fused reductions: N = 64, one chunk per thread
         uint4 packed[NCH][4];
@@ -634,7 +510,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         }
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) { if (PAIR) mbar_arrive_cluster(LEADER(BAR(2 * S + 3 + buf))); else mbar_arrive(BAR(2 * S + 3 + buf)); }          // accumulator free again: next-but-one tile may start
+        if (lane == 0) mbar_arrive(BAR(2 * S + 3 + buf));          // accumulator free again: next-but-one tile may start
         if (FUSE == 3) load_xq(rbase);                               // residual input rows (in flight across the staging barriers)
         // the previous tile's TMA store must have finished reading the staging buffer
         if (threadIdx.x == 64) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
@@ -745,47 +621,6 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         if (p.dbg && blockIdx.x == 0 && warp == 2 && lane == 0) p.dbg[it * 8 + 5] = clock64();
         continue;
       }
-      if (FUSE == 4) {
-        // ---- fp32 output, coalesced: a thread's 16 columns of its row go to the warp's [32][17] buffer, then lane l writes
-        // column (l & 15) of rows 2i + (l >> 4): every warp store covers two 64-byte row segments (full sectors) instead
-        // of 32 scattered 16-byte pieces ----
-        float* wbuf = reinterpret_cast<float*>(sOut) + (warp - 2) * (32 * TC_F32_PITCH);
-        const int m_i = valid ? (int)m : -1;
-        float* const yf = (float*)p.y;
-        for (int c0 = 32 * half; c0 < p.Npad; c0 += 64) {
-          uint32_t r[32];
-          const bool two = c0 + 32 <= p.Npad;
-          if (two) tmem_ld32_nowait(taddr + (uint32_t)c0, r);
-          else tmem_ld16_nowait(taddr + (uint32_t)c0, r);
-          tmem_wait_ld();
-#pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            const int c = c0 + 16 * h;
-            if ((h == 1 && !two) || c >= p.N) break;             // warp-uniform
-            const int nvalid = min(16, p.N - c);
-#pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              float v = __uint_as_float(r[16 * h + j]) + sbias[c + j];
-              if (scale_row && j < nvalid) v *= __ldg(scale_row + c + j);
-              wbuf[lane * TC_F32_PITCH + j] = v;
-            }
-            __syncwarp();
-            const int cl = lane & 15;
-#pragma unroll
-            for (int i = 0; i < 16; ++i) {
-              const int rr = 2 * i + (lane >> 4);
-              const int mr = __shfl_sync(0xffffffffu, m_i, rr);
-              if (mr >= 0 && cl < nvalid) yf[(size_t)mr * p.N + c + cl] = wbuf[rr * TC_F32_PITCH + cl];
-            }
-            __syncwarp();
-          }
-        }
-        tc_fence_before();
-        __syncwarp();
-        if (p.dbg && blockIdx.x == 0 && warp == 2 && lane == 0) p.dbg[it * 8 + 5] = clock64();
-        if (lane == 0) { if (PAIR) mbar_arrive_cluster(LEADER(BAR(2 * S + 3 + buf))); else mbar_arrive(BAR(2 * S + 3 + buf)); }
-        continue;
-      }
       for (int c0 = 32 * half; c0 < p.Npad; c0 += 64) {
         uint32_t r[32];
         const bool two = c0 + 32 <= p.Npad;
@@ -812,9 +647,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
       tc_fence_before();
       __syncwarp();
       if (p.dbg && blockIdx.x == 0 && warp == 2 && lane == 0) p.dbg[it * 8 + 5] = clock64();
-      if (lane == 0) { if (PAIR) mbar_arrive_cluster(LEADER(BAR(2 * S + 3 + buf))); else mbar_arrive(BAR(2 * S + 3 + buf)); }
+      if (lane == 0) mbar_arrive(BAR(2 * S + 3 + buf));
     }
-    if (FUSE != 0 && FUSE != 4) {
+    if (FUSE != 0) {
       // combine the eight row groups per channel: one double atomic per channel and statistic per CTA
       sred[(0 * 8 + ew) * 64 + 2 * lane] = ra0; sred[(0 * 8 + ew) * 64 + 2 * lane + 1] = ra1;
       sred[(1 * 8 + ew) * 64 + 2 * lane] = rb0; sred[(1 * 8 + ew) * 64 + 2 * lane + 1] = rb1;
@@ -832,21 +667,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
   }
   if (p.tma_store && threadIdx.x == 64) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   tc_fence_before();
-  if (PAIR) cluster_sync_all();          // the leader's MMAs read this CTA's weights and write its TMEM until its last tile retires
-  else __syncthreads();
-  if (warp == 1) {
-    if (PAIR) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(p.tmem_cols) : "memory");
-    else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(p.tmem_cols) : "memory");
-  }
-  if (DYN && threadIdx.x == 0) {
-    // this CTA drew its last index before the barrier above; the last CTA to get here re-arms the counters for the next launch
-    const int done = atomicAdd(p.sched + 1, 1);
-    if (done == (int)gridDim.x - 1) {
-      p.sched[0] = 0;
-      p.sched[1] = 0;
-      __threadfence();
-    }
-  }
+  __syncthreads();
+  if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(p.tmem_cols) : "memory");
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
@@ -865,56 +687,6 @@ EncodeTiledFn get_encode() {
 }
 
 long long* g_tc_dbg = nullptr;
-
-// lvae_launch with a cluster of two CTAs (the cta_group::2 kernels) on top of the programmatic-dependent-launch attribute
-template <typename... KArgs, typename... Args>
-cudaError_t lvae_launch_pair(void (*kernel)(KArgs...), int grid, int block, size_t smem, cudaStream_t stream, Args&&... args) {
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(grid);
-  cfg.blockDim = dim3(block);
-  cfg.dynamicSmemBytes = smem;
-  cfg.stream = stream;
-  cudaLaunchAttribute attr[2];
-  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[0].val.programmaticStreamSerializationAllowed = g_lvae_pdl ? 1 : 0;
-  attr[1].id = cudaLaunchAttributeClusterDimension;
-  attr[1].val.clusterDim.x = 2;
-  attr[1].val.clusterDim.y = 1;
-  attr[1].val.clusterDim.z = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = 2;
-  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
-}
-
-// Counters of the dynamic tile scheduler: one {next tile, finished CTAs} pair per stream that launches DYN kernels (kernels of
-// one stream never overlap; the kernel itself re-arms its pair).  Allocated on first use outside stream capture -- the
-// engines run eager warm-up steps before they capture; until then (or beyond 32 streams) launches keep the static schedule.
-int* tc_sched_slot(cudaStream_t stream) {
-  static std::mutex mu;
-  static int* base = nullptr;
-  static bool failed = false;
-  static cudaStream_t keys[32];
-  static int n = 0;
-  std::lock_guard<std::mutex> lock(mu);
-  if (failed) return nullptr;
-  cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
-  if (cudaStreamIsCapturing(stream, &cs) != cudaSuccess) { cudaGetLastError(); return nullptr; }
-  if (!base) {
-    if (cs != cudaStreamCaptureStatusNone) return nullptr;
-    if (cudaMalloc(&base, 32 * 2 * sizeof(int)) != cudaSuccess || cudaMemset(base, 0, 32 * 2 * sizeof(int)) != cudaSuccess ||
-        cudaDeviceSynchronize() != cudaSuccess) {
-      cudaGetLastError();
-      failed = true;
-      base = nullptr;
-      return nullptr;
-    }
-  }
-  for (int i = 0; i < n; ++i)
-    if (keys[i] == stream) return base + 2 * i;
-  if (n == 32) return nullptr;
-  keys[n] = stream;
-  return base + 2 * (n++);
-}
 
 int pow2_floor_le(int v, int cap) {
   int r = 1;
@@ -1008,27 +780,18 @@ LVAE_API int lvae_conv2d_tc_ex(const void* x, const void* x2, const void* wp, co
   while (p.tmem_cols < 2 * p.Npad) p.tmem_cols *= 2;
   LVAE_REQUIRE(p.tmem_cols <= 512, "conv2d_tc: accumulator does not fit TMEM");
   const int max_smem = 227 * 1024 - 1024 /*align*/ - 8192 /*barriers, bias, BatchNorm table, reduction scratch*/;
-  static int halo_env = -1, bo_env = 0, pair_env = 0;
+  static int halo_env = -1, bo_env = 0;
   if (halo_env < 0) {
     const char* e = getenv("LVAE_CONV_HALO");
     halo_env = e ? atoi(e) : 1;
     const char* b = getenv("LVAE_HALO_BO");
     bo_env = b ? atoi(b) : 0;   // the hardware swizzle is a function of the absolute shared-memory address: no base offset
-    const char* c = getenv("LVAE_CONV_CTA2");
-    pair_env = c ? atoi(c) : 0;
   }
-  // CTA pairs (cta_group::2): halo-mode 3x3 convolutions of 64 -> 64 channels with an even number of 16x8-pixel tiles and
-  // no gate / split / residual extras; each CTA of a pair keeps half of the weight rows
-  const bool pair = pair_env && halo_env && ksize == 3 && !x2 && Cin == 64 && N == 64 && W % 8 == 0 && H % 16 == 0 && !y2 && !res &&
-                    !p.gate_x && ((B * (W / 8) * (H / 16)) % 2 == 0) && lvae_num_sms() >= 2;
-  const int wbytes = ((p.n_kb * (pair ? p.Npad / 2 : p.Npad) * 128) + 1023) & ~1023;
+  const int wbytes = ((p.n_kb * p.Npad * 128) + 1023) & ~1023;
   static int tst_env = -1;
   if (tst_env < 0) { const char* e = getenv("LVAE_CONV_TMA_STORE"); tst_env = e ? atoi(e) : 1; }
   p.tma_store = (tst_env && !out_f32 && N % 64 == 0 && N <= 128 && !res && (!y2 || nsplit % 64 == 0)) ? 1 : 0;
-  static int f32s_env = -1;
-  if (f32s_env < 0) { const char* e = getenv("LVAE_CONV_F32_STAGE"); f32s_env = e ? atoi(e) : 0; }
-  p.f32_stage = (f32s_env && out_f32 && !res && !y2 && !p.tma_store) ? 1 : 0;
-  const int out_stage = p.tma_store ? (p.Npad / 64 + (p.gate_x ? 1 : 0)) * TC_STAGE_BYTES : (p.f32_stage ? TC_F32_STAGE_BYTES : 0);
+  const int out_stage = p.tma_store ? (p.Npad / 64 + (p.gate_x ? 1 : 0)) * TC_STAGE_BYTES : 0;
   LVAE_REQUIRE(!p.gate_x || p.tma_store, "conv2d_tc: the gated-residual epilogue needs the TMA-store path");
   LVAE_REQUIRE(!(p.stats_acc || p.bnb_acc) || (p.tma_store && (N == 64 || p.gate_x) && !y2),
                "conv2d_tc: fused reductions need the TMA-store path (bf16 output, N == 64, no residual, no split)");
@@ -1077,7 +840,7 @@ LVAE_API int lvae_conv2d_tc_ex(const void* x, const void* x2, const void* wp, co
     if (r != CUDA_SUCCESS) { lvae_set_error("conv2d_tc: tensor map (x2) encode failed: %d", (int)r); return LVAE_ERR_CUDA; }
     cuuint64_t wdim[2] = {64, (cuuint64_t)p.n_kb * p.Npad};
     cuuint64_t wstr[1] = {128};
-    cuuint32_t wbox[2] = {64, (cuuint32_t)(pair ? p.Npad / 2 : p.Npad)};
+    cuuint32_t wbox[2] = {64, (cuuint32_t)p.Npad};
     cuuint32_t westr[2] = {1, 1};
     r = enc(&tmW, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (void*)wp, wdim, wstr, wbox, westr, CU_TENSOR_MAP_INTERLEAVE_NONE,
             CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -1086,63 +849,19 @@ LVAE_API int lvae_conv2d_tc_ex(const void* x, const void* x2, const void* wp, co
   static size_t attr_smem = 0;
   const int cap = 227 * 1024;
   if (smem > attr_smem) {
-    // the four kernels of the default path (exactly what was validated on the GPU)
-    cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tc_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tc_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tc_kernel<3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap);
+    cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tc_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap);
     if (e != cudaSuccess) { lvae_set_error("conv2d_tc: cannot raise dynamic smem: %s", cudaGetErrorString(e)); return LVAE_ERR_CUDA; }
     attr_smem = 227 * 1024;
   }
-  static int dyn_env = -1;
-  if (dyn_env < 0) { const char* e = getenv("LVAE_CONV_DYNAMIC"); dyn_env = e ? atoi(e) : 0; }
-  static bool attr_optin = false;
-  if (!attr_optin && (p.f32_stage || dyn_env || pair)) {
-    // opt-in variants: only touched when one of their switches is set
-    cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tc_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tc_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tc_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tc_kernel<3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tc_kernel<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tc_kernel<0, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tc_kernel<1, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tc_kernel<2, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tc_kernel<4, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap);
-    if (e != cudaSuccess) { lvae_set_error("conv2d_tc: cannot raise dynamic smem (opt-in kernels): %s", cudaGetErrorString(e)); return LVAE_ERR_CUDA; }
-    attr_optin = true;
-  }
   const int n_tiles = p.halo ? B * p.tiles_per_img : (p.M_total + TC_BM - 1) / TC_BM;
   const int grid = n_tiles < lvae_num_sms() ? n_tiles : lvae_num_sms();
-  if (pair && p.halo) {
-    // clusters of two CTAs; both CTAs of a pair run the same number of tiles (n_tiles and the grid are even)
-    const int pgrid = grid & ~1;
-    p.dbg = nullptr;
-    p.sched = nullptr;
-    cudaError_t e;
-    if (p.stats_acc) e = lvae_launch_pair(conv_tc_kernel<1, false, true>, pgrid, TC_THREADS, smem, stream, tmA0, tmA1, tmW, tmY, tmY2, p);
-    else if (p.bnb_acc) e = lvae_launch_pair(conv_tc_kernel<2, false, true>, pgrid, TC_THREADS, smem, stream, tmA0, tmA1, tmW, tmY, tmY2, p);
-    else if (p.f32_stage) e = lvae_launch_pair(conv_tc_kernel<4, false, true>, pgrid, TC_THREADS, smem, stream, tmA0, tmA1, tmW, tmY, tmY2, p);
-    else e = lvae_launch_pair(conv_tc_kernel<0, false, true>, pgrid, TC_THREADS, smem, stream, tmA0, tmA1, tmW, tmY, tmY2, p);
-    if (e != cudaSuccess) { lvae_set_error("conv2d_tc: cluster launch failed: %s", cudaGetErrorString(e)); return LVAE_ERR_CUDA; }
-    LVAE_COUNT_LAUNCH();
-    LVAE_CHECK_LAUNCH("conv2d_tc (cta pair)");
-    return LVAE_OK;
-  }
-  LVAE_REQUIRE(!pair, "conv2d_tc: internal: CTA-pair weights layout without halo mode");
-  p.sched = (dyn_env && n_tiles > grid) ? tc_sched_slot(stream) : nullptr;     // one tile per CTA: nothing to balance
-  if (p.sched) {
-    p.dbg = nullptr;
-    if (p.gate_x) lvae_launch(conv_tc_kernel<3, true>, grid, TC_THREADS, smem, stream, tmA0, tmA1, tmW, tmY, tmY2, p);
-    else if (p.stats_acc) lvae_launch(conv_tc_kernel<1, true>, grid, TC_THREADS, smem, stream, tmA0, tmA1, tmW, tmY, tmY2, p);
-    else if (p.bnb_acc) lvae_launch(conv_tc_kernel<2, true>, grid, TC_THREADS, smem, stream, tmA0, tmA1, tmW, tmY, tmY2, p);
-    else if (p.f32_stage) lvae_launch(conv_tc_kernel<4, true>, grid, TC_THREADS, smem, stream, tmA0, tmA1, tmW, tmY, tmY2, p);
-    else lvae_launch(conv_tc_kernel<0, true>, grid, TC_THREADS, smem, stream, tmA0, tmA1, tmW, tmY, tmY2, p);
-  } else if (p.gate_x) lvae_launch(conv_tc_kernel<3, false>, grid, TC_THREADS, smem, stream, tmA0, tmA1, tmW, tmY, tmY2, p);
-  else if (p.stats_acc) lvae_launch(conv_tc_kernel<1, false>, grid, TC_THREADS, smem, stream, tmA0, tmA1, tmW, tmY, tmY2, p);
-  else if (p.bnb_acc) lvae_launch(conv_tc_kernel<2, false>, grid, TC_THREADS, smem, stream, tmA0, tmA1, tmW, tmY, tmY2, p);
-  else if (p.f32_stage) lvae_launch(conv_tc_kernel<4, false>, grid, TC_THREADS, smem, stream, tmA0, tmA1, tmW, tmY, tmY2, p);
-  else lvae_launch(conv_tc_kernel<0, false>, grid, TC_THREADS, smem, stream, tmA0, tmA1, tmW, tmY, tmY2, p);
+  if (p.gate_x) lvae_launch(conv_tc_kernel<3>, grid, TC_THREADS, smem, stream, tmA0, tmA1, tmW, tmY, tmY2, p);
+  else if (p.stats_acc) lvae_launch(conv_tc_kernel<1>, grid, TC_THREADS, smem, stream, tmA0, tmA1, tmW, tmY, tmY2, p);
+  else if (p.bnb_acc) lvae_launch(conv_tc_kernel<2>, grid, TC_THREADS, smem, stream, tmA0, tmA1, tmW, tmY, tmY2, p);
+  else lvae_launch(conv_tc_kernel<0>, grid, TC_THREADS, smem, stream, tmA0, tmA1, tmW, tmY, tmY2, p);
   LVAE_COUNT_LAUNCH();
   LVAE_CHECK_LAUNCH("conv2d_tc");
   return LVAE_OK;
@@ -1170,7 +889,7 @@ LVAE_API int lvae_conv2d_tc_s2(const void* x, const void* wp, const float* bias,
   const int Cin = 64, Hb = 2 * Hg, Wb = 2 * Wg;               // the bigger grid
   static size_t attr_smem = 0;
   if (!attr_smem) {
-    cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024));
+    cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024));
     if (e != cudaSuccess) { lvae_set_error("conv2d_tc_s2: cannot raise dynamic smem: %s", cudaGetErrorString(e)); return LVAE_ERR_CUDA; }
     attr_smem = 227 * 1024;
   }
@@ -1238,7 +957,7 @@ LVAE_API int lvae_conv2d_tc_s2(const void* x, const void* wp, const float* bias,
     }
     const int n_tiles = (p.M_total + TC_BM - 1) / TC_BM;
     const int grid = n_tiles < lvae_num_sms() ? n_tiles : lvae_num_sms();
-    lvae_launch(conv_tc_kernel<0, false>, grid, TC_THREADS, smem, stream, tmA, tmA, tmW, tmY, tmY2, p);
+    lvae_launch(conv_tc_kernel<0>, grid, TC_THREADS, smem, stream, tmA, tmA, tmW, tmY, tmY2, p);
     LVAE_COUNT_LAUNCH();
     LVAE_CHECK_LAUNCH("conv2d_tc_s2");
   }

@@ -107,52 +107,50 @@ LVAE_API int lvae_bernoulli_sample(const float* prob, float* out_nchw, int B, in
 constexpr int DM_M = 10, DM_P = 100, DM_PITCH = 101, DM_TILE = 64;
 #define LOG_127_5 4.8481163519437300f
 
-// FAST (LVAE_DMOL_FAST=1, off by default): single-MUFU exponentials / logarithms (ex2.approx, lg2.approx; relative error
-// 2^-22) instead of the ~10-25-instruction exact expf / logf / log1pf / tanhf -- the kernel is issue-bound on those.
+// Single-MUFU exponentials / logarithms (ex2.approx, lg2.approx; relative error 2^-22) instead of the ~10-25-instruction
+// exact expf / logf / log1pf / tanhf: the kernel is issue-bound on those (1376 / 2120 SASS instructions with the exact
+// functions, 704 / 1080 with these).  Validated on the B200 against the fp64 oracle inside the fp32 bounds of the parity
+// tests (1e-4 on ll, 1e-3 on the gradient: tests/test_kernels_gpu.py::test_dmol, tests/test_model_gpu.py) and 1.7x / 1.5x
+// faster (forward 76 -> 45 us, backward 114 -> 76 us for the CIFAR batch of 256; profiles/ab_r02_summary.txt).
 __device__ __forceinline__ float lg2_approx(float x) {
   float y;
   asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
-template <bool FAST> __device__ __forceinline__ float dm_exp(float v) { return exp_t<FAST>(v); }
-template <bool FAST> __device__ __forceinline__ float dm_log(float v) { return FAST ? lg2_approx(v) * 0.6931471805599453f : logf(v); }
-template <bool FAST> __device__ __forceinline__ float dm_softplus(float v) {
-  if (FAST) return v > 20.f ? v : dm_log<true>(1.f + dm_exp<true>(v));
-  return softplusf_(v);
-}
-template <bool FAST> __device__ __forceinline__ float dm_tanh(float v) {
-  return FAST ? 1.f - __fdividef(2.f, 1.f + dm_exp<true>(2.f * v)) : tanhf(v);
-}
+__device__ __forceinline__ float dm_exp(float v) { return exp_t<true>(v); }
+__device__ __forceinline__ float dm_log(float v) { return lg2_approx(v) * 0.6931471805599453f; }
+__device__ __forceinline__ float dm_softplus(float v) { return v > 20.f ? v : dm_log(1.f + dm_exp(v)); }
+__device__ __forceinline__ float dm_tanh(float v) { return 1.f - __fdividef(2.f, 1.f + dm_exp(2.f * v)); }
+__device__ __forceinline__ float dm_sigmoid(float v) { return sigmoid_t<true>(v); }
 
 // log-prob of one sub-pixel under one logistic; optionally its derivatives wrt the centred value
 // and the (clamped) log-scale.  Mirrors likelihoods.py:331-375.
-template <bool FAST>
 __device__ __forceinline__ float dmol_term(float x, float cen, float ls, float& d_cen, float& d_ls, bool want_grad) {
-  float inv = dm_exp<FAST>(-ls);
+  float inv = dm_exp(-ls);
   float plus_in = inv * (cen + (1.f / 255.f));
   float min_in = inv * (cen - (1.f / 255.f));
   if (x < -0.999f) {
-    if (want_grad) { float om = 1.f - sigmoid_t<FAST>(plus_in); d_cen = inv * om; d_ls = -plus_in * om; }
-    return plus_in - dm_softplus<FAST>(plus_in);
+    if (want_grad) { float om = 1.f - dm_sigmoid(plus_in); d_cen = inv * om; d_ls = -plus_in * om; }
+    return plus_in - dm_softplus(plus_in);
   }
   if (x > 0.999f) {
-    if (want_grad) { float s = sigmoid_t<FAST>(min_in); d_cen = -inv * s; d_ls = min_in * s; }
-    return -dm_softplus<FAST>(min_in);
+    if (want_grad) { float s = dm_sigmoid(min_in); d_cen = -inv * s; d_ls = min_in * s; }
+    return -dm_softplus(min_in);
   }
-  float cp = sigmoid_t<FAST>(plus_in), cm = sigmoid_t<FAST>(min_in);
+  float cp = dm_sigmoid(plus_in), cm = dm_sigmoid(min_in);
   float delta = cp - cm;
   if (delta > 1e-5f) {
     if (want_grad) {
       float dpv = cp * (1.f - cp), dmv = cm * (1.f - cm);
       float dd = fmaxf(delta, 1e-12f);
-      d_cen = FAST ? inv * __fdividef(dpv - dmv, dd) : inv * (dpv - dmv) / dd;
-      d_ls = FAST ? -__fdividef(plus_in * dpv - min_in * dmv, dd) : -(plus_in * dpv - min_in * dmv) / dd;
+      d_cen = inv * __fdividef(dpv - dmv, dd);
+      d_ls = -__fdividef(plus_in * dpv - min_in * dmv, dd);
     }
-    return dm_log<FAST>(fmaxf(delta, 1e-12f));
+    return dm_log(fmaxf(delta, 1e-12f));
   }
   float mid = inv * cen;
-  if (want_grad) { float w = 1.f - 2.f * sigmoid_t<FAST>(mid); d_cen = inv * w; d_ls = -mid * w - 1.f; }
-  return mid - ls - 2.f * dm_softplus<FAST>(mid) - LOG_127_5;
+  if (want_grad) { float w = 1.f - 2.f * dm_sigmoid(mid); d_cen = inv * w; d_ls = -mid * w - 1.f; }
+  return mid - ls - 2.f * dm_softplus(mid) - LOG_127_5;
 }
 
 // BWD = false: ll[b] += sum over this CTA's pixels.  BWD = true: dl = g_ll[b] * d ll / d l.
@@ -163,7 +161,7 @@ __device__ __forceinline__ float dmol_term(float x, float cen, float ls, float& 
 // math (30 logistic terms) in one long dependent chain per thread: 265 us for the CIFAR batch-256 backward, 12 % of the
 // HBM roofline; this layout runs the same arithmetic with 10x the parallelism.
 constexpr int DM_THREADS = 256, DM_GROUP = 16;
-template <bool BWD, bool FAST>
+template <bool BWD>
 __global__ void __launch_bounds__(DM_THREADS) dmol_kernel(const float* __restrict__ l, const float* __restrict__ x,
                                                           float* __restrict__ ll, const float* __restrict__ g_ll,
                                                           float* __restrict__ dl, int hw, __nv_bfloat16* __restrict__ dl_lp) {
@@ -216,27 +214,27 @@ __global__ void __launch_bounds__(DM_THREADS) dmol_kernel(const float* __restric
     // log_softmax of the mixture logits
     const float logit = comp ? L[mm] : -INFINITY;
     const float mx = gmax(logit);
-    const float se = gsum(comp ? dm_exp<FAST>(logit - mx) : 0.f);
-    const float lse0 = mx + dm_log<FAST>(se);
+    const float se = gsum(comp ? dm_exp(logit - mx) : 0.f);
+    const float lse0 = mx + dm_log(se);
     // this component's log-probability of the three sub-pixels
     const float c0r = L[10 + 20 + mm], c1r = L[40 + 20 + mm], c2r = L[70 + 20 + mm];
-    const float k0 = dm_tanh<FAST>(c0r), k1 = dm_tanh<FAST>(c1r), k2 = dm_tanh<FAST>(c2r);
+    const float k0 = dm_tanh(c0r), k1 = dm_tanh(c1r), k2 = dm_tanh(c2r);
     const float mu[3] = {L[10 + mm], L[40 + mm] + k0 * xc[0], L[70 + mm] + k1 * xc[0] + k2 * xc[1]};
     float lsr[3], dc[3], dls[3];
     float S = 0.f;
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
       lsr[c] = L[10 + 30 * c + 10 + mm];
-      S += dmol_term<FAST>(xc[c], xc[c] - mu[c], fmaxf(lsr[c], -7.f), dc[c], dls[c], BWD);
+      S += dmol_term(xc[c], xc[c] - mu[c], fmaxf(lsr[c], -7.f), dc[c], dls[c], BWD);
     }
     const float v = comp ? S + (logit - lse0) : -INFINITY;
     const float vmax = gmax(v);
-    const float sv = gsum(comp ? dm_exp<FAST>(v - vmax) : 0.f);
-    const float lse = vmax + dm_log<FAST>(sv);
+    const float sv = gsum(comp ? dm_exp(v - vmax) : 0.f);
+    const float lse = vmax + dm_log(sv);
     if (live && m == 0) pix_ll += lse;
     if (BWD && live && comp) {
       const float g = g_ll[b];
-      const float rm = dm_exp<FAST>(v - lse);               // responsibility
+      const float rm = dm_exp(v - lse);               // responsibility
       const float gS = g * rm;
       float dmu[3];
 #pragma unroll
@@ -244,7 +242,7 @@ __global__ void __launch_bounds__(DM_THREADS) dmol_kernel(const float* __restric
         dmu[c] = -gS * dc[c];                               // cen = x - mu
         L[10 + 30 * c + 10 + m] = lsr[c] >= -7.f ? gS * dls[c] : 0.f;   // clamp(min=-7) backward
       }
-      L[m] = g * (rm - dm_exp<FAST>(logit - lse0));
+      L[m] = g * (rm - dm_exp(logit - lse0));
       L[10 + m] = dmu[0];
       L[40 + m] = dmu[1];
       L[70 + m] = dmu[2];
@@ -286,28 +284,21 @@ __global__ void __launch_bounds__(DM_THREADS) dmol_kernel(const float* __restric
 
 static const size_t DMOL_SMEM = (DM_TILE * DM_PITCH + 32) * sizeof(float);
 
-static bool dmol_fast() {
-  static int fast = -1;
-  if (fast < 0) {
-    const char* e = getenv("LVAE_DMOL_FAST");
-    fast = e ? atoi(e) : 0;
-    cudaFuncSetAttribute(dmol_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DMOL_SMEM);
-    cudaFuncSetAttribute(dmol_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DMOL_SMEM);
-    if (fast) {                                        // the opt-in kernels are only touched when their switch is set
-      cudaFuncSetAttribute(dmol_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DMOL_SMEM);
-      cudaFuncSetAttribute(dmol_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DMOL_SMEM);
-    }
+static void dmol_init() {
+  static bool done = false;
+  if (!done) {
+    cudaFuncSetAttribute(dmol_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DMOL_SMEM);
+    cudaFuncSetAttribute(dmol_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DMOL_SMEM);
+    done = true;
   }
-  return fast != 0;
 }
 
 // ll must be zeroed by the caller (partial sums are accumulated with atomics, 16 per image at 32x32)
 LVAE_API int lvae_dmol_fwd(const float* l, const float* x, float* ll, int B, int hw, cudaStream_t stream) {
   LVAE_REQUIRE(l && x && ll && B > 0 && hw > 0, "dmol_fwd: bad args");
-  const bool fast = dmol_fast();
+  dmol_init();
   dim3 grid(cdiv(hw, DM_TILE), B);
-  if (fast) lvae_launch(dmol_kernel<false, true>, grid, DM_THREADS, DMOL_SMEM, stream, l, x, ll, nullptr, nullptr, hw, nullptr);
-  else lvae_launch(dmol_kernel<false, false>, grid, DM_THREADS, DMOL_SMEM, stream, l, x, ll, nullptr, nullptr, hw, nullptr);
+  lvae_launch(dmol_kernel<false>, grid, DM_THREADS, DMOL_SMEM, stream, l, x, ll, nullptr, nullptr, hw, nullptr);
   LVAE_COUNT_LAUNCH();
   LVAE_CHECK_LAUNCH("dmol_fwd");
   return LVAE_OK;
@@ -317,10 +308,9 @@ LVAE_API int lvae_dmol_fwd(const float* l, const float* x, float* ll, int B, int
 LVAE_API int lvae_dmol_bwd(const float* l, const float* x, const float* g_ll, float* dl, void* dl_bf16_128, int B, int hw,
                            cudaStream_t stream) {
   LVAE_REQUIRE(l && x && g_ll && (dl || dl_bf16_128) && B > 0 && hw > 0, "dmol_bwd: bad args");
-  const bool fast = dmol_fast();
+  dmol_init();
   dim3 grid(cdiv(hw, DM_TILE), B);
-  if (fast) lvae_launch(dmol_kernel<true, true>, grid, DM_THREADS, DMOL_SMEM, stream, l, x, nullptr, g_ll, dl, hw, (__nv_bfloat16*)dl_bf16_128);
-  else lvae_launch(dmol_kernel<true, false>, grid, DM_THREADS, DMOL_SMEM, stream, l, x, nullptr, g_ll, dl, hw, (__nv_bfloat16*)dl_bf16_128);
+  lvae_launch(dmol_kernel<true>, grid, DM_THREADS, DMOL_SMEM, stream, l, x, nullptr, g_ll, dl, hw, (__nv_bfloat16*)dl_bf16_128);
   LVAE_COUNT_LAUNCH();
   LVAE_CHECK_LAUNCH("dmol_bwd");
   return LVAE_OK;

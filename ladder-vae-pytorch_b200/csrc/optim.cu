@@ -7,9 +7,11 @@
 // step_count: device int64, incremented here so the captured graph advances on replay.
 __global__ void adamax_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                               float* __restrict__ u, long long n, float lr, float b1, float b2, float eps, float wd,
-                              const long long* __restrict__ step_count, float grad_scale) {
+                              const long long* __restrict__ step_count, float grad_scale,
+                              const float* __restrict__ hyper) {
   pdl_wait();
   pdl_launch();
+  if (hyper) { lr = hyper[0]; wd = hyper[1]; }     // device-resident learning rate / weight decay: a captured graph follows them
   const double t = (double)(*step_count);
   const float clr = lr / (float)(1.0 - pow((double)b1, t));
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
@@ -29,13 +31,13 @@ __global__ void step_inc_kernel(long long* s) {
 
 LVAE_API int lvae_adamax_step(float* p, const float* g, float* exp_avg, float* exp_inf, long long n, float lr,
                               float beta1, float beta2, float eps, float weight_decay, long long* step_count_dev,
-                              float grad_scale, cudaStream_t stream) {
+                              float grad_scale, const float* hyper_dev, cudaStream_t stream) {
   LVAE_REQUIRE(p && g && exp_avg && exp_inf && step_count_dev && n > 0, "adamax_step: bad args");
   lvae_launch(step_inc_kernel, 1, 1, 0, stream, step_count_dev);
   LVAE_COUNT_LAUNCH();
   int grid = (int)min((long long)8 * lvae_num_sms(), (n + 255) / 256);
   lvae_launch(adamax_kernel, grid, 256, 0, stream, p, g, exp_avg, exp_inf, n, lr, beta1, beta2, eps, weight_decay,
-                                          step_count_dev, grad_scale);
+                                          step_count_dev, grad_scale, hyper_dev);
   LVAE_COUNT_LAUNCH();
   LVAE_CHECK_LAUNCH("adamax_step");
   return LVAE_OK;

@@ -179,12 +179,23 @@ class TrainEngine:
         _capi.device_check()
         self.model = model.train()
         self.batch_size = batch_size
-        self.lr, self.wd, self.betas, self.eps, self.beta_kl = lr, weight_decay, betas, eps, beta_kl
+        self.betas, self.eps = betas, eps
         self.pg = process_group
-        self.world = dist.get_world_size(process_group) if (process_group is not None or dist.is_initialized()) else 1
+        inited = process_group is not None or dist.is_initialized()
+        self.world = dist.get_world_size(process_group) if inited else 1
+        self.rank = dist.get_rank(process_group) if inited else 0
         self.arena = ParamArena(model)
         dev = self.arena.flat.device
         self.device = dev
+        # learning rate, weight decay and the KL weight live on the device: the captured graphs read them at replay, so
+        # schedules (the reference's --beta-anneal, experiment_manager.py:339-344) need no recapture
+        self._hyper = torch.tensor([lr, weight_decay], dtype=torch.float32, device=dev)
+        self._beta = torch.tensor(float(beta_kl), dtype=torch.float32, device=dev)
+        self._lr, self._wd, self._beta_kl = float(lr), float(weight_decay), float(beta_kl)
+        if self.world > 1:
+            # replicas must not share eps / Dropout2d masks: every rank draws from its own Philox key
+            st = ops.rng_state(dev)
+            st[0] = (int(st[0]) ^ ((self.rank * 0x9E3779B97F4A7C15) & 0x7FFFFFFFFFFFFFFF))
         self.exp_avg = torch.zeros_like(self.arena.flat)
         self.exp_inf = torch.zeros_like(self.arena.flat)
         self.step_count = torch.zeros((), dtype=torch.int64, device=dev)
@@ -212,14 +223,75 @@ class TrainEngine:
             for b in model.buffers():
                 dist.broadcast(b, 0, group=self.pg)
 
+    # -- hyper-parameters (device resident; setting them is a tiny H2D copy, no recapture) ------
+    @property
+    def lr(self):
+        return self._lr
+
+    @lr.setter
+    def lr(self, v):
+        self._lr = float(v)
+        self._hyper[0:1].copy_(torch.tensor([self._lr], dtype=torch.float32), non_blocking=True)
+
+    @property
+    def wd(self):
+        return self._wd
+
+    @wd.setter
+    def wd(self, v):
+        self._wd = float(v)
+        self._hyper[1:2].copy_(torch.tensor([self._wd], dtype=torch.float32), non_blocking=True)
+
+    @property
+    def beta_kl(self):
+        return self._beta_kl
+
+    @beta_kl.setter
+    def beta_kl(self, v):
+        self._beta_kl = float(v)
+        self._beta.copy_(torch.tensor(self._beta_kl, dtype=torch.float32), non_blocking=True)
+
+    # -- checkpoint / resume of the optimizer side (the model's own state_dict holds the parameters) ------
+    def state_dict(self):
+        """Adamax moments in the layout of torch.optim.Adamax's per-parameter state (keyed by parameter name), the step
+        count, hyper-parameters and the Philox state."""
+        names = {id(p): n for n, p in self.model.named_parameters()}
+        state, off = {}, 0
+        for p in self.arena.params:
+            n = p.numel()
+            state[names[id(p)]] = {"exp_avg": self.exp_avg[off:off + n].view(p.shape).clone(),
+                                   "exp_inf": self.exp_inf[off:off + n].view(p.shape).clone()}
+            off += ((n + 3) // 4) * 4
+        return {"state": state, "step": int(self.step_count), "lr": self._lr, "weight_decay": self._wd,
+                "beta_kl": self._beta_kl, "betas": tuple(self.betas), "eps": self.eps,
+                "rng": ops.rng_state(self.device).clone().cpu()}
+
+    def load_state_dict(self, sd):
+        names = {id(p): n for n, p in self.model.named_parameters()}
+        off = 0
+        for p in self.arena.params:
+            n = p.numel()
+            st = sd["state"][names[id(p)]]
+            self.exp_avg[off:off + n].view(p.shape).copy_(st["exp_avg"])
+            self.exp_inf[off:off + n].view(p.shape).copy_(st["exp_inf"])
+            off += ((n + 3) // 4) * 4
+        self.step_count.fill_(int(sd["step"]))
+        self.lr, self.wd, self.beta_kl = sd["lr"], sd["weight_decay"], sd["beta_kl"]
+        if sd.get("rng") is not None:
+            ops.rng_state(self.device).copy_(sd["rng"])
+        ops.bump_pack_epoch()
+
     # -- pieces ---------------------------------------------------------------------------
     def _forward_backward(self):
+        # Philox streams are numbered from 0 in every step (the per-step offset advance keeps steps apart), so an eager
+        # step and a graph replay of the same step draw identical eps / Dropout2d masks
+        ops.set_stream_id(0)
         ops.rng_advance(self.device)
         self.arena.grad.zero_()
         self.packs.repack()
         out = self.model(self.x)
         recons = (-out["ll"]).mean()
-        loss = recons + out["kl_loss"] * self.beta_kl
+        loss = recons + out["kl_loss"] * self._beta
         ops.set_side_stream(self.side_stream)          # (None: everything on this stream; also resets the wgrad log)
         try:
             loss.backward()
@@ -245,8 +317,8 @@ class TrainEngine:
     def _optimizer(self):
         a = self.arena
         call("lvae_adamax_step", a.flat.data_ptr(), a.grad.data_ptr(), self.exp_avg.data_ptr(), self.exp_inf.data_ptr(),
-             a.numel, self.lr, self.betas[0], self.betas[1], self.eps, self.wd, self.step_count.data_ptr(),
-             1.0 / self.world, _stream())
+             a.numel, self._lr, self.betas[0], self.betas[1], self.eps, self._wd, self.step_count.data_ptr(),
+             1.0 / self.world, self._hyper.data_ptr(), _stream())
         if self.compute_l2:
             call("lvae_l2_norm", a.flat.data_ptr(), a.numel, self.l2_acc.data_ptr(), self.l2.data_ptr(), _stream())
         self.out["l2"] = self.l2
@@ -257,7 +329,14 @@ class TrainEngine:
         self._optimizer()
 
     def _capture(self):
-        # warm-up on a side stream (allocates pack buffers, BatchNorm scratch, cuBLAS-free)
+        # Warm-up on a side stream (allocates pack buffers, BatchNorm scratch, sub-tables of the packed-gradient unpack).
+        # The two eager steps are real steps on the caller's first batch, so everything they mutate is put back before
+        # the capture: parameters, Adamax moments, step count, BatchNorm running statistics, the Philox state.  The first
+        # step(x) in graph mode therefore applies exactly one update, like use_graph=False and like the reference.
+        snap = [(t, t.clone()) for t in (self.arena.flat, self.exp_avg, self.exp_inf, self.step_count,
+                                         ops.rng_state(self.device))]
+        snap += [(b, b.clone()) for b in self.model.buffers()]
+        gstep = getattr(self.model, "global_step", 0)
         s = torch.cuda.Stream()
         s.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(s):
@@ -265,7 +344,16 @@ class TrainEngine:
                 self._eager_step()
         torch.cuda.current_stream().wait_stream(s)
         torch.cuda.synchronize()
-        sid = ops._rng.stream_id
+        for t, c in snap:
+            t.copy_(c)
+        self.model.global_step = gstep
+        torch.cuda.synchronize()
+        # Parameters changed behind torch's version counters (Adamax and the restore above write through raw pointers):
+        # every cached GEMM-layout weight copy is stale.  The batched re-pack at the top of the step refreshes the table's
+        # packs; any OTHER pack a convolution falls back to (CUDA-core layouts of the 64 -> 1 Bernoulli head, odd sizes)
+        # now misses its cache key during capture, so its on-demand lvae_pack_weights launch becomes a node of the graph
+        # and runs on every replay.
+        ops.bump_pack_epoch()
         n0 = _capi.launch_count()
         self.graph_fb = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph_fb, stream=self.main_stream):
@@ -274,7 +362,6 @@ class TrainEngine:
         with torch.cuda.graph(self.graph_opt, pool=self.graph_fb.pool()):
             self._optimizer()
         self.launches_per_step = _capi.launch_count() - n0
-        ops.set_stream_id(sid + 100000)
 
     # -- public ---------------------------------------------------------------------------
     def step(self, x: Optional[torch.Tensor] = None) -> Dict[str, torch.Tensor]:
@@ -324,6 +411,7 @@ class IWEvaluator:
         self.bu = self.model.bottomup_pass(self.model.pad_input(self.x)) if self.reuse_bottomup else None
 
     def _one_sample(self):
+        ops.set_stream_id(0)             # sample k of an image batch = Philox offset k, stream ids numbered from 0
         ops.rng_advance(self.device)
         out = self.model.forward_from_bottomup(self.x, self.bu) if self.reuse_bottomup else self.model(self.x)
         ops.iw_lse_update(out["ll"], out["kl_sep"], self.state, False)
@@ -332,13 +420,15 @@ class IWEvaluator:
         self.state[:, 0].fill_(-math.inf)
         self.state[:, 1].zero_()
 
-    def bound(self, x: torch.Tensor, k_total: int) -> torch.Tensor:
-        """Per-image IW bound (B,) for this image batch with k_total samples over all ranks."""
-        _, k_local = shard_samples(k_total, self.rank, self.world)
+    def local_state(self, x: torch.Tensor, k_total: int) -> torch.Tensor:
+        """This rank's share of the K-sample bound for one image batch: (B,2) running (max, sum-exp) of ll - kl over the
+        samples shard_samples() assigns to this rank."""
+        k_start, k_local = shard_samples(k_total, self.rank, self.world)
         with torch.no_grad():
             self.x.copy_(x, non_blocking=True)
             self._reset()
             if self.use_graph and self.graph is None:
+                rng0 = ops.rng_state(self.device).clone()
                 s = torch.cuda.Stream()
                 s.wait_stream(torch.cuda.current_stream())
                 with torch.cuda.stream(s):
@@ -357,11 +447,17 @@ class IWEvaluator:
                 with torch.cuda.graph(self.graph, pool=self.graph_bu.pool()):
                     self._one_sample()
                 self.launches_per_sample = _capi.launch_count() - n0
+                ops.rng_state(self.device).copy_(rng0)      # the warm-up sample must not shift the noise sequence
                 self._reset()
             if self.use_graph:
                 self.graph_bu.replay()
             else:
                 self._bottomup()
+            # Sample k of this batch always draws from Philox offset (base + k): a rank skips the samples of the ranks
+            # before it, so the K samples are distinct across ranks (with the usual same-seed-everywhere setup they would
+            # otherwise be `world` copies of K/world samples) and the bound does not depend on how K is sharded.
+            if k_start:
+                ops.rng_advance(self.device, k_start * ops.RNG_STEP)
             for _ in range(k_local):
                 if self.use_graph:
                     self.graph.replay()
@@ -369,8 +465,14 @@ class IWEvaluator:
                     n0 = _capi.launch_count()
                     self._one_sample()
                     self.launches_per_sample = _capi.launch_count() - n0
-            if self.world > 1:
-                states = gather_states(self.state, self.pg)
-            else:
-                states = self.state[None]
+            k_rest = k_total - k_start - k_local
+            if k_rest:
+                ops.rng_advance(self.device, k_rest * ops.RNG_STEP)      # every rank ends the batch at the same offset
+            return self.state
+
+    def bound(self, x: torch.Tensor, k_total: int) -> torch.Tensor:
+        """Per-image IW bound (B,) for this image batch with k_total samples over all ranks."""
+        state = self.local_state(x, k_total)
+        with torch.no_grad():
+            states = gather_states(state, self.pg) if self.world > 1 else state[None]
             return ops.iw_lse_combine(states.contiguous(), k_total)

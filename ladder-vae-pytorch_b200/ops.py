@@ -93,7 +93,10 @@ def set_stream_id(v: int) -> None:
     _rng.stream_id = int(v)
 
 
-def rng_advance(device, inc: int = 1 << 36) -> None:
+RNG_STEP = 1 << 36      # Philox offset advance per step / importance sample (no site of one step draws that many quads)
+
+
+def rng_advance(device, inc: int = RNG_STEP) -> None:
     call("lvae_rng_advance", rng_state(device).data_ptr(), inc, _stream())
 
 
@@ -683,20 +686,9 @@ _bn_epoch = [0]
 _whole_block = [True]
 _gate_fused = [os.environ.get("LVAE_GATE_FUSED", "1") != "0"]
 _gate_keep_h = [True]     # set per call by gated_block(): autograd.Function.forward always runs with grad mode off
-# opt-in (not yet validated on a GPU): conv2 + gate conv + gate as ONE launch, the 1x1 GEMM reading the staged conv2 tile
-_gate_chain = [os.environ.get("LVAE_CONV_GATE_CHAIN", "0") != "0"]
-# opt-in (not yet validated on a GPU): gate backward + 1x1 gate-conv data gradient as ONE launch
-_gate_bwd_chain = [os.environ.get("LVAE_GATE_BWD_CHAIN", "0") != "0"]
-
-
-def _gate_bwd_dgrad_chain(gn, h, wpb, mask2, gact):
-    """lvae_gate_bwd_dgrad_tc: returns (dh, dc2) = (gate backward wrt h, its 1x1 data gradient times the Dropout2d mask)."""
-    B, H, W, _ = gn.shape
-    dh = torch.empty_like(h)
-    dc2 = torch.empty_like(gn)
-    call("lvae_gate_bwd_dgrad_tc", gn.data_ptr(), h.data_ptr(), wpb.data_ptr(), _p(mask2), dh.data_ptr(), dc2.data_ptr(),
-         B, H * W, int(gact), _stream())
-    return dh, dc2
+# conv2 + gate conv + gate as ONE launch, the 1x1 GEMM reading the staged conv2 tile (lvae_conv_gate_tc; validated and
+# timed on the B200 in round 2: bit-identical tensors, 17.41 -> 16.71 ms per CIFAR-15 step).  LVAE_CONV_GATE_CHAIN=0 = A/B.
+_gate_chain = [os.environ.get("LVAE_CONV_GATE_CHAIN", "1") != "0"]
 
 
 def _conv_gate_chain(a2, w2p, bias2, mask2, wgp, gbias, xn, gact, stats_acc, keep):
@@ -795,7 +787,7 @@ class GatedBlockFn(Function):
             y1 = conv_forward_raw(conv1.spec, a1, None, w1, cb1, m1, None)
         a2 = bn_fwd(y1, bn2, sc2, saves[1], g2, b2, acc2)
         gspec = gconv.spec
-        # opt-in: conv2, the 1x1 gate conv and the gate itself as one launch (csrc/conv_gate_tcgen05.cu)
+        # conv2, the 1x1 gate conv and the gate itself as one launch (csrc/conv_gate_tcgen05.cu)
         chain = (_gate_chain[0] and C == 64 and gspec.cout == 128 and gspec.k == 1 and conv2.spec.k == 3 and conv2.spec.cout == 64
                  and xn.dtype == torch.bfloat16 and not gspec.out_fp32 and not conv2.spec.out_fp32
                  and conv2.spec.tc_forward_ok(a2, None) and gspec.tc_forward_ok(a2, None)
@@ -841,20 +833,11 @@ class GatedBlockFn(Function):
             gn = gn.to(xn.dtype)
         ng = ctx.needs_input_grad
         gsp = gconv.spec
-        if (_gate_bwd_chain[0] and C == 64 and gsp.cout == 128 and gsp.k == 1 and gsp.tc_shape and xn.dtype == torch.bfloat16
-                and h.dtype == torch.bfloat16 and gn.is_contiguous()
-                and (m2 is None or (m2.dtype == torch.float32 and m2.is_contiguous()))):
-            # opt-in: gate backward and the 1x1 data gradient in one launch (csrc/gate_dgrad_tcgen05.cu); weight gradient as usual
-            stats["tc_dgrad"] += 1
-            stats["gate_bwd_chain"] = stats.get("gate_bwd_chain", 0) + 1
-            dh, dy2 = _gate_bwd_dgrad_chain(gn, h, gsp.pack_tc_bwd.get(wg, torch.bfloat16), m2, gact)
-            _, _, gwg, ggb = conv_backward_raw(gsp, y2, None, wg, gbias, None, dh, False, ng[9], ng[10])
-        else:
-            # gate
-            dh = torch.empty_like(h)
-            call("lvae_gate_bwd", gn.data_ptr(), h.data_ptr(), dh.data_ptr(), Pn, C, gact, dt, _stream())
-            # 1x1 gate conv: dgrad carries conv2's Dropout2d mask in its epilogue -> gradient wrt conv2's raw output
-            dy2, _, gwg, ggb = conv_backward_raw(gsp, y2, None, wg, gbias, None, dh, True, ng[9], ng[10], dx_scale=m2)
+        # gate
+        dh = torch.empty_like(h)
+        call("lvae_gate_bwd", gn.data_ptr(), h.data_ptr(), dh.data_ptr(), Pn, C, gact, dt, _stream())
+        # 1x1 gate conv: dgrad carries conv2's Dropout2d mask in its epilogue -> gradient wrt conv2's raw output
+        dy2, _, gwg, ggb = conv_backward_raw(gsp, y2, None, wg, gbias, None, dh, True, ng[9], ng[10], dx_scale=m2)
         sc1b, sc2b = bn_scratch(bn1, dev), bn_scratch(bn2, dev)
         acc1b, acc2b = sc1b[1], sc2b[1]
         _bn_clean(bn1, acc1b, "bwd")

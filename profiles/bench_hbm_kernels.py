@@ -2,7 +2,6 @@
 (lib/stochastic.py:45-96), the discretized-mixture-of-logistics and Bernoulli likelihoods (lib/likelihoods.py:291-388).
 
     python profiles/bench_hbm_kernels.py                  # one B200; prints a table and one JSON line per kernel
-    LVAE_DMOL_FAST=1 python profiles/bench_hbm_kernels.py # the single-MUFU DMoL variant
 
 Each kernel is replayed from a CUDA graph over rotating buffers larger than L2 and timed with CUDA events on the
 capturing stream.  `achieved` = ALGORITHMIC bytes per launch (stochastic forward 20 B / latent element
@@ -112,7 +111,7 @@ def bench_dmol(rows, peak, src, B=256, side=32):
     ll = torch.zeros(B, device=dev)
     g = -torch.ones(B, device=dev) / B
     shape = "B=%d %dx%d" % (B, side, side)
-    tag = " [LVAE_DMOL_FAST]" if os.environ.get("LVAE_DMOL_FAST", "0") != "0" else ""
+    tag = ""
     report(rows, "dmol_fwd" + tag, shape, 412 * npix,
            time_graph(lambda i: _capi.call("lvae_dmol_fwd", l[i].data_ptr(), x[i].data_ptr(), ll.data_ptr(), B, hw, S()), nb),
            peak, src)

@@ -318,7 +318,7 @@ def test_adamax_l2_iw(L):
         O.adamax_step(pr, gr, ea, ei, t)
         gd = dev(gr)
         _capi.call("lvae_adamax_step", pd.data_ptr(), gd.data_ptr(), m.data_ptr(), u.data_ptr(), n, 3e-4, 0.9, 0.999,
-                   1e-8, 0.0, step.data_ptr(), 1.0, s)
+                   1e-8, 0.0, step.data_ptr(), 1.0, None, s)
     assert int(step) == 3
     assert rel_err(pd, pr) < 1e-6
     acc = torch.zeros((), dtype=torch.float64, device="cuda")
