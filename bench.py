@@ -311,7 +311,9 @@ def kernel_shares(torch, engine):
             if e.device_type != torch.autograd.DeviceType.CUDA:
                 continue
             name = e.name.replace("(anonymous namespace)::", "").split("(")[0].split("<")[0].strip()
-            if name.startswith("at::") or name.startswith("void at::"):
+            if name.startswith("void "):
+                name = name[5:]
+            if name.startswith("at::"):
                 name = "aten_glue"
             elif "nccl" in name.lower():
                 name = "nccl"

@@ -208,11 +208,22 @@ int lvae_sum_batch(const float* x, float* out, int B, long long n, int accumulat
 int lvae_stoch_fwd(const float* q, const float* p, int p_broadcast, const float* eps, const float* forced,
                    const void* rng_state, unsigned long long stream_id, float* z, void* z_bf16, int z_bf16_pitch, float* kl_sample,
                    float* kl_spatial, float* logp, float* logq, int B, int hw, int Z, int use_mode, int analytical,
-                   lvae_stream_t stream);
+                   void* ws, lvae_stream_t stream);
+/* ws: NULL (one CTA per sample) or a device workspace of lvae_stoch_ws_bytes(B) bytes, zeroed once by the caller, that lets
+ * the kernel split a sample over several CTAs (their per-sample sums are combined in a fixed order: deterministic). */
+long long lvae_stoch_ws_bytes(int B);
 /* z_kind: 1 reparameterised sample, 2 mode, 0 forced latent.  dq, dp: (B,hw,2Z). */
 int lvae_stoch_bwd(const float* q, const float* p, int p_broadcast, const float* z, const float* g_z,
                    const float* g_kl, const float* g_logp, const float* g_logq, const float* g_kls, float* dq,
                    float* dp, int B, int hw, int Z, int analytical, int z_kind, lvae_stream_t stream);
+/* Free bits + KL bookkeeping of LadderVAE.forward (models/lvae.py:192-198; boilr free_bits_kl) and the log p(z) total of
+ * topdown_pass (:301-302) in one launch over the (L,B) matrices whose rows the L stochastic kernels wrote:
+ * kl_sep (B), scalars[3] = {kl, kl_loss, logp}, kl_avg_layerwise (L), coef (L,B) = d kl_loss / d kl (kept for the backward). */
+int lvae_kl_bookkeeping(const float* kl_rows, const float* logp_rows, int L, int B, float free_bits, float* kl_sep,
+                        float* scalars, float* kl_avg_layerwise, float* coef, lvae_stream_t stream);
+/* g_scalars: device float[3], upstream gradients of {kl, kl_loss, logp}; g_kl_sep (B) / g_kl_avg (L) / g_logp_rows optional */
+int lvae_kl_bookkeeping_bwd(const float* coef, const float* g_scalars, const float* g_kl_sep, const float* g_kl_avg, int L,
+                            int B, float* g_kl_rows, float* g_logp_rows, lvae_stream_t stream);
 
 /* ---- likelihoods: lib/likelihoods.py ----
  * Bernoulli (:51-78, log_bernoulli :385-388): logits (B,hw,C) NHWC, x (B,C,hw) NCHW. */

@@ -48,8 +48,10 @@ _SIGNATURES = {
     "lvae_dropout_masks": [P, L, F, P, U, P],
     "lvae_rng_advance": [P, U, P],
     "lvae_sum_batch": [P, P, I, L, I, P],
-    "lvae_stoch_fwd": [P, P, I, P, P, P, U, P, P, I, P, P, P, P, I, I, I, I, I, P],
+    "lvae_stoch_fwd": [P, P, I, P, P, P, U, P, P, I, P, P, P, P, I, I, I, I, I, P, P],
     "lvae_stoch_bwd": [P, P, I, P, P, P, P, P, P, P, P, I, I, I, I, I, P],
+    "lvae_kl_bookkeeping": [P, P, I, I, F, P, P, P, P, P],
+    "lvae_kl_bookkeeping_bwd": [P, P, P, P, I, I, P, P, P],
     "lvae_bernoulli_fwd": [P, P, P, P, I, I, I, P],
     "lvae_bernoulli_bwd": [P, P, P, P, P, I, I, I, P],
     "lvae_bernoulli_sample": [P, P, I, I, I, P, U, P],
@@ -74,6 +76,7 @@ _SPECIAL = {
     "lvae_wgrad_tc_workspace": ([I, I, I, I, I, I], c_longlong),
     "lvae_wgrad_tc_packed_size": ([I, I, I], c_longlong),
     "lvae_wgrad_unpack_desc_size": ([], c_int),
+    "lvae_stoch_ws_bytes": ([I], c_longlong),
 }
 
 

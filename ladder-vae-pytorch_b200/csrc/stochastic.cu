@@ -1,15 +1,44 @@
 // Fused diagonal-Gaussian stochastic block (everything between the conv_in_* outputs and the
 // conv_out input of NormalStochasticBlock2d, lib/stochastic.py:45-96 and kl_normal_mc :209-226):
 // reparameterised sample (external eps or Philox), log p(z), log q(z), MC or analytic KL per
-// sample, analytic KL per pixel.  One CTA per sample; a group of G lanes owns one pixel so the
-// per-pixel (channel) reduction is a warp shuffle and the per-sample one a block reduction.
+// sample, analytic KL per pixel -- and (lvae_kl_bookkeeping) the free-bits clamp and the KL / log p
+// bookkeeping of LadderVAE.forward (models/lvae.py:192-198,301-302) over all layers in one launch.
 // Pure HBM-bound: 20 B per latent element forward, 40 B backward.
 //
 // Layout: q, p are (B, hw, 2Z) fp32 rows = [mu(Z) | logvar(Z)] (NHWC conv outputs);
 // p may be batch-broadcast (p_bstride = 0: learned top prior, lvae_layers.py:131-136).
+//
+// Round-2 redesign (the round-1 kernel ran at 22 % / 42 % of the copy bandwidth at 16x16, issue-bound):
+//  * grid = (pixel chunks, samples) instead of one CTA per sample, so that small batches of large latents (CelebA: 64 x
+//    32x32) still fill 148 SMs; the per-sample sums of a multi-chunk launch are combined by the LAST CTA of each sample
+//    in chunk order (deterministic: no floating-point atomics), through a caller-provided workspace;
+//  * 4 MUFU per latent element instead of ~275 instructions: sigma_q = ex2(lv_q * log2e/2), 1/sigma_p^2 = ex2(-lv_p *
+//    log2e), the variance ratio is sigma_q^2 / sigma_p^2 (no third exponential, no divisions), log sigma = lv/2 (the
+//    reference's log(exp(lv/2)) round trip, stochastic.py:45-46, differs from it by <= 1 ulp), log q(z) of a reparameterised
+//    sample is -eps^2/2 - lv_q/2 - log(2 pi)/2, Box-Muller on lg2/sqrt/sin/cos.approx.  All inside the 1e-4 (forward) and
+//    1e-3 (gradient) fp32 bounds of tests/test_kernels_gpu.py::test_stochastic_core against the fp64 oracle;
+//  * the backward reads and writes 16 bytes per thread; dL/dz arrives as the fp32 tensor the conv_out data gradient wrote
+//    (its tcgen05 epilogue stores fp32 for this one consumer: no pad / slice / cast passes in between).
 #include "common.cuh"
 
 #define HALF_LOG_2PI 0.91893853320467274178f
+#define LOG2E 1.4426950408889634f
+
+namespace {
+
+__device__ __forceinline__ float lg2a(float x) { float y; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float sqrta(float x) { float y; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float sina(float x) { float y; asm("sin.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float cosa(float x) { float y; asm("cos.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+
+// 4 standard normals (Box-Muller on the approximate MUFU functions: the argument of sin / cos stays inside [-pi, pi],
+// where their absolute error is 2^-21; the noise only has to be N(0,1), tests/test_kernels_gpu.py checks its moments)
+__device__ __forceinline__ float4 philox_normal4_fast(const PhiloxState& st, unsigned long long stream, unsigned long long idx) {
+  float4 u = philox_uniform4(st, stream, idx);
+  const float r0 = sqrta(-1.3862943611198906f * lg2a(u.x)), r1 = sqrta(-1.3862943611198906f * lg2a(u.z));   // sqrt(-2 ln u)
+  const float a0 = 6.283185307179586f * u.y - 3.141592653589793f, a1 = 6.283185307179586f * u.w - 3.141592653589793f;
+  return make_float4(r0 * cosa(a0), r0 * sina(a0), r1 * cosa(a1), r1 * sina(a1));
+}
 
 struct StochArgs {
   const float* q;       // may be null (generation: sample from p)
@@ -28,78 +57,94 @@ struct StochArgs {
   float* logq;          // (B) or null
   int B, hw, Z;
   int use_mode, analytical;
+  int chunk_pix, nchunk;   // pixels per CTA, CTAs per sample
+  float* ws_part;          // (B, nchunk, 3) partial sums (nchunk > 1)
+  unsigned int* ws_cnt;    // (B) arrival tickets, zero between launches
 };
 
+constexpr int ST_THREADS = 256;
+
 template <int VEC>
-__global__ void __launch_bounds__(256) stoch_fwd_kernel(StochArgs a) {
+__global__ void __launch_bounds__(ST_THREADS) stoch_fwd_kernel(StochArgs a) {
   pdl_wait();
   pdl_launch();
   __shared__ float red[32];
-  const int b = blockIdx.x;
+  __shared__ unsigned int s_last;
+  const int b = blockIdx.y;
   const int ZV = a.Z / VEC;
   int G = 1;
   while (G < ZV && G < 32) G <<= 1;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
   const int ppw = 32 / G;                 // pixels per warp per iteration
   const int gl = lane % G, gp = lane / G;
+  const bool sampled = !a.eps && !a.forced && !a.use_mode;
+  const bool reparam = !a.forced && !a.use_mode;       // z = mu + sigma * e with e known exactly
   PhiloxState st;
-  if (!a.eps && !a.forced && !a.use_mode) st = *a.rng;
+  if (sampled) st = *a.rng;
   const float* qb = a.q ? a.q + (long long)b * a.hw * 2 * a.Z : nullptr;
   const float* pb = a.p + (long long)b * a.p_bstride;
+  const int pix_begin = blockIdx.x * a.chunk_pix;
+  const int pix_end = min(a.hw, pix_begin + a.chunk_pix);
   float s_kl = 0.f, s_lp = 0.f, s_lq = 0.f;
-  for (int pix0 = warp * ppw; pix0 < a.hw; pix0 += nwarp * ppw) {
-    int pix = pix0 + gp;
-    bool pvalid = pix < a.hw;
+  for (int pix0 = pix_begin + warp * ppw; pix0 < pix_end; pix0 += nwarp * ppw) {
+    const int pix = pix0 + gp;
+    const bool pvalid = pix < pix_end;
     float kls = 0.f;
     if (pvalid) {
       for (int cv = gl; cv < ZV; cv += G) {
-        int c = cv * VEC;
-        long long row = (long long)pix * 2 * a.Z;
-        long long zi = ((long long)b * a.hw + pix) * a.Z + c;
+        const int c = cv * VEC;
+        const long long row = (long long)pix * 2 * a.Z;
+        const long long zi = ((long long)b * a.hw + pix) * a.Z + c;
         float mq[VEC], lq[VEC], mp[VEC], lp[VEC], e[VEC], zz[VEC];
         if (VEC == 4) {
           float4 t;
-          t = *reinterpret_cast<const float4*>(pb + row + c); mp[0] = t.x; mp[1] = t.y; mp[2] = t.z; mp[3] = t.w;
-          t = *reinterpret_cast<const float4*>(pb + row + a.Z + c); lp[0] = t.x; lp[1] = t.y; lp[2] = t.z; lp[3] = t.w;
+          t = __ldg(reinterpret_cast<const float4*>(pb + row + c)); mp[0] = t.x; mp[1] = t.y; mp[2] = t.z; mp[3] = t.w;
+          t = __ldg(reinterpret_cast<const float4*>(pb + row + a.Z + c)); lp[0] = t.x; lp[1] = t.y; lp[2] = t.z; lp[3] = t.w;
           if (qb) {
-            t = *reinterpret_cast<const float4*>(qb + row + c); mq[0] = t.x; mq[1] = t.y; mq[2] = t.z; mq[3] = t.w;
-            t = *reinterpret_cast<const float4*>(qb + row + a.Z + c); lq[0] = t.x; lq[1] = t.y; lq[2] = t.z; lq[3] = t.w;
+            t = __ldg(reinterpret_cast<const float4*>(qb + row + c)); mq[0] = t.x; mq[1] = t.y; mq[2] = t.z; mq[3] = t.w;
+            t = __ldg(reinterpret_cast<const float4*>(qb + row + a.Z + c)); lq[0] = t.x; lq[1] = t.y; lq[2] = t.z; lq[3] = t.w;
           }
-          if (a.forced) { t = *reinterpret_cast<const float4*>(a.forced + zi); zz[0] = t.x; zz[1] = t.y; zz[2] = t.z; zz[3] = t.w; }
-          else if (a.eps) { t = *reinterpret_cast<const float4*>(a.eps + zi); e[0] = t.x; e[1] = t.y; e[2] = t.z; e[3] = t.w; }
-          else if (!a.use_mode) { t = philox_normal4(st, a.stream_id, (unsigned long long)(zi >> 2)); e[0] = t.x; e[1] = t.y; e[2] = t.z; e[3] = t.w; }
+          if (a.forced) { t = __ldg(reinterpret_cast<const float4*>(a.forced + zi)); zz[0] = t.x; zz[1] = t.y; zz[2] = t.z; zz[3] = t.w; }
+          else if (a.eps) { t = __ldg(reinterpret_cast<const float4*>(a.eps + zi)); e[0] = t.x; e[1] = t.y; e[2] = t.z; e[3] = t.w; }
+          else if (!a.use_mode) { t = philox_normal4_fast(st, a.stream_id, (unsigned long long)(zi >> 2)); e[0] = t.x; e[1] = t.y; e[2] = t.z; e[3] = t.w; }
         } else {
           mp[0] = pb[row + c]; lp[0] = pb[row + a.Z + c];
           if (qb) { mq[0] = qb[row + c]; lq[0] = qb[row + a.Z + c]; }
           if (a.forced) zz[0] = a.forced[zi];
           else if (a.eps) e[0] = a.eps[zi];
           else if (!a.use_mode) {
-            float4 t = philox_normal4(st, a.stream_id, (unsigned long long)(zi >> 2));
+            float4 t = philox_normal4_fast(st, a.stream_id, (unsigned long long)(zi >> 2));
             int k = (int)(zi & 3);
             e[0] = k == 0 ? t.x : (k == 1 ? t.y : (k == 2 ? t.z : t.w));
           }
         }
 #pragma unroll
         for (int j = 0; j < VEC; ++j) {
-          float smu = qb ? mq[j] : mp[j], slv = qb ? lq[j] : lp[j];
+          const float smu = qb ? mq[j] : mp[j], slv = qb ? lq[j] : lp[j];
+          const float ss = ex2_approx(slv * (0.5f * LOG2E));            // sigma of the sampling distribution
           float zv;
           if (a.forced) zv = zz[j];
           else if (a.use_mode) zv = smu;
-          else zv = smu + expf(slv * 0.5f) * e[j];
+          else zv = fmaf(ss, e[j], smu);
           zz[j] = zv;
-          // log N(z; mu, exp(lv/2)) in torch.distributions' form
-          float sp = expf(lp[j] * 0.5f);
-          float dp = zv - mp[j];
-          float logp = -(dp * dp) / (2.f * sp * sp) - logf(sp) - HALF_LOG_2PI;
+          // log N(z; mu, sigma) = -(z - mu)^2 / (2 sigma^2) - log sigma - log(2 pi)/2, log sigma = lv / 2
+          const float ivp = qb ? ex2_approx(-lp[j] * LOG2E) : 0.f;      // 1 / sigma_p^2
+          const float dp = zv - mp[j];
+          float logp;
+          if (qb) logp = -0.5f * dp * dp * ivp - 0.5f * lp[j] - HALF_LOG_2PI;
+          else logp = (reparam ? -0.5f * e[j] * e[j] : (a.use_mode ? 0.f : -0.5f * dp * dp * ex2_approx(-lp[j] * LOG2E))) - 0.5f * lp[j] - HALF_LOG_2PI;
           s_lp += logp;
           if (qb) {
-            float sq = expf(lq[j] * 0.5f);
-            float dq = zv - mq[j];
-            float logq = -(dq * dq) / (2.f * sq * sq) - logf(sq) - HALF_LOG_2PI;
+            float logq;
+            if (reparam) logq = -0.5f * e[j] * e[j] - 0.5f * lq[j] - HALF_LOG_2PI;
+            else {
+              const float dq = zv - mq[j];
+              logq = -0.5f * dq * dq * ex2_approx(-lq[j] * LOG2E) - 0.5f * lq[j] - HALF_LOG_2PI;
+            }
             s_lq += logq;
-            float r = sq / sp, vr = r * r;
-            float t1 = (mq[j] - mp[j]) / sp;
-            float kl_an = 0.5f * (vr + t1 * t1 - 1.f - logf(vr));
+            const float vr = ss * ss * ivp;                              // sigma_q^2 / sigma_p^2
+            const float dm = mq[j] - mp[j];
+            const float kl_an = 0.5f * (vr + dm * dm * ivp - 1.f - (lq[j] - lp[j]));
             kls += kl_an;
             s_kl += a.analytical ? kl_an : (logq - logp);
           }
@@ -116,104 +161,263 @@ __global__ void __launch_bounds__(256) stoch_fwd_kernel(StochArgs a) {
     // zero padding of the low-precision copy (channels Z .. pitch)
     if (pvalid && a.z_lp) {
       __nv_bfloat16* zr = (__nv_bfloat16*)a.z_lp + ((long long)b * a.hw + pix) * a.z_lp_pitch;
-      for (int cz = a.Z + gl; cz < a.z_lp_pitch; cz += G) zr[cz] = __float2bfloat16(0.f);
+      if (VEC == 4) { for (int cz = a.Z + 4 * gl; cz < a.z_lp_pitch; cz += 4 * G) *reinterpret_cast<uint2*>(zr + cz) = make_uint2(0u, 0u); }
+      else { for (int cz = a.Z + gl; cz < a.z_lp_pitch; cz += G) zr[cz] = __float2bfloat16(0.f); }
     }
     // per-pixel channel reduction inside the lane group
     for (int o = G >> 1; o > 0; o >>= 1) kls += __shfl_xor_sync(0xffffffffu, kls, o);
     if (pvalid && gl == 0 && a.kl_spatial) a.kl_spatial[(long long)b * a.hw + pix] = kls;
   }
-  float v;
-  v = block_sum(s_lp, red);
-  if (threadIdx.x == 0) a.logp[b] = v;
+  float v_lp = block_sum(s_lp, red), v_lq = 0.f, v_kl = 0.f;
   if (a.q) {
-    v = block_sum(s_lq, red);
-    if (threadIdx.x == 0 && a.logq) a.logq[b] = v;
-    v = block_sum(s_kl, red);
-    if (threadIdx.x == 0 && a.kl_sample) a.kl_sample[b] = v;
+    v_lq = block_sum(s_lq, red);
+    v_kl = block_sum(s_kl, red);
+  }
+  if (a.nchunk == 1) {
+    if (threadIdx.x == 0) {
+      a.logp[b] = v_lp;
+      if (a.q && a.logq) a.logq[b] = v_lq;
+      if (a.q && a.kl_sample) a.kl_sample[b] = v_kl;
+    }
+    return;
+  }
+  // several CTAs per sample: publish this chunk's partial sums; the last CTA of the sample adds them up in chunk order
+  if (threadIdx.x == 0) {
+    float* part = a.ws_part + ((long long)b * a.nchunk + blockIdx.x) * 3;
+    part[0] = v_lp; part[1] = v_lq; part[2] = v_kl;
+    __threadfence();
+    s_last = atomicAdd(a.ws_cnt + b, 1u);
+  }
+  __syncthreads();
+  if (s_last != (unsigned int)(a.nchunk - 1)) return;
+  if (threadIdx.x == 0) {
+    __threadfence();
+    const volatile float* part = a.ws_part + (long long)b * a.nchunk * 3;
+    float t0 = 0.f, t1 = 0.f, t2 = 0.f;
+    for (int c = 0; c < a.nchunk; ++c) { t0 += part[3 * c]; t1 += part[3 * c + 1]; t2 += part[3 * c + 2]; }
+    a.logp[b] = t0;
+    if (a.q && a.logq) a.logq[b] = t1;
+    if (a.q && a.kl_sample) a.kl_sample[b] = t2;
+    a.ws_cnt[b] = 0u;                      // re-armed for the next launch (stream order)
   }
 }
+
+}  // namespace
+
+// workspace of a multi-chunk launch: B * 64 * 3 floats of partial sums + B tickets (zero-initialised ONCE by the caller;
+// launches that share it must be stream-ordered)
+LVAE_API long long lvae_stoch_ws_bytes(int B) { return (long long)B * (64 * 3 * 4 + 4); }
 
 LVAE_API int lvae_stoch_fwd(const float* q, const float* p, int p_broadcast, const float* eps, const float* forced,
                             const void* rng_state, unsigned long long stream_id, float* z, void* z_bf16, int z_bf16_pitch,
                             float* kl_sample, float* kl_spatial, float* logp, float* logq, int B, int hw, int Z,
-                            int use_mode, int analytical, cudaStream_t stream) {
+                            int use_mode, int analytical, void* ws, cudaStream_t stream) {
   LVAE_REQUIRE(p && z && logp && B > 0 && hw > 0 && Z > 0, "stoch_fwd: bad args");
   LVAE_REQUIRE(eps || forced || use_mode || rng_state, "stoch_fwd: need eps, forced latent, mode, or an RNG state");
   LVAE_REQUIRE(!z_bf16 || (z_bf16_pitch >= Z && z_bf16_pitch % 4 == 0), "stoch_fwd: bad low-precision pitch");
   StochArgs a{q, p, p_broadcast ? 0LL : (long long)hw * 2 * Z, eps, forced, (const PhiloxState*)rng_state, stream_id,
-              z, z_bf16, z_bf16_pitch, kl_sample, kl_spatial, logp, logq, B, hw, Z, use_mode, analytical};
-  if (Z % 4 == 0) lvae_launch(stoch_fwd_kernel<4>, B, 256, 0, stream, a);
-  else lvae_launch(stoch_fwd_kernel<1>, B, 256, 0, stream, a);
+              z, z_bf16, z_bf16_pitch, kl_sample, kl_spatial, logp, logq, B, hw, Z, use_mode, analytical, hw, 1, nullptr, nullptr};
+  // pixels one CTA covers per pass of its 8 warps; a chunk = two passes (16-byte loads of two pixels in flight per thread),
+  // unless that would need more than 64 chunks per sample or there is no workspace for the cross-CTA sums
+  const int vec = Z % 4 == 0 ? 4 : 1;
+  int G = 1;
+  while (G < Z / vec && G < 32) G <<= 1;
+  const int per_pass = (ST_THREADS / 32) * (32 / G);
+  if (ws && hw > 2 * per_pass) {
+    int chunk = 2 * per_pass;
+    while ((hw + chunk - 1) / chunk > 64) chunk *= 2;
+    a.chunk_pix = chunk;
+    a.nchunk = (hw + chunk - 1) / chunk;
+    a.ws_part = (float*)ws;
+    a.ws_cnt = (unsigned int*)((float*)ws + (long long)B * 64 * 3);
+  }
+  dim3 grid(a.nchunk, B);
+  if (vec == 4) lvae_launch(stoch_fwd_kernel<4>, grid, ST_THREADS, 0, stream, a);
+  else lvae_launch(stoch_fwd_kernel<1>, grid, ST_THREADS, 0, stream, a);
   LVAE_COUNT_LAUNCH();
   LVAE_CHECK_LAUNCH("stoch_fwd");
   return LVAE_OK;
 }
 
 // ------------------------------------------------------------------------------------------
-// backward.  Inputs: upstream grads g_z (B,hw,Z) [null = 0], g_kl (B), g_logp (B), g_logq (B),
-// g_kls (B,hw) [any may be null = 0].  Outputs dq, dp (B,hw,2Z) (dp is per sample; the caller
-// sums over the batch when p was broadcast).  eps is never needed: sigma_q*eps == z - mu_q.
+// backward.  Inputs: upstream grads g_z (B,hw,Z) [null = 0], g_kl (B), g_logp (B), g_logq (B), g_kls (B,hw) [any may be
+// null = 0].  Outputs dq, dp (B,hw,2Z) (dp is per sample; the
+// caller sums over the batch when p was broadcast).  eps is never needed: sigma_q*eps == z - mu_q.
 // ------------------------------------------------------------------------------------------
+namespace {
+
 struct StochBwdArgs {
   const float* q; const float* p; long long p_bstride; const float* z;
-  const float* g_z; const float* g_kl; const float* g_logp; const float* g_logq; const float* g_kls;
+  const float* g_z;
+  const float* g_kl; const float* g_logp; const float* g_logq; const float* g_kls;
   float* dq; float* dp;
   int B, hw, Z, analytical, z_is_sample;  // z_is_sample: 1 rsample, 0 forced latent (no dz/dq path), 2 mode (dz/dmu only)
+  long long nvec;                          // B * hw * Z / VEC
 };
 
+template <int VEC>
 __global__ void __launch_bounds__(256) stoch_bwd_kernel(StochBwdArgs a) {
   pdl_wait();
   pdl_launch();
-  const int b = blockIdx.x;
-  const float gkl = a.g_kl ? a.g_kl[b] : 0.f, glp = a.g_logp ? a.g_logp[b] : 0.f, glq = a.g_logq ? a.g_logq[b] : 0.f;
-  const float* qb = a.q + (long long)b * a.hw * 2 * a.Z;
-  const float* pb = a.p + (long long)b * a.p_bstride;
-  float* dqb = a.dq + (long long)b * a.hw * 2 * a.Z;
-  float* dpb = a.dp + (long long)b * a.hw * 2 * a.Z;
-  const int n = a.hw * a.Z;
-  for (int i = threadIdx.x; i < n; i += blockDim.x) {
-    int pix = i / a.Z, c = i - pix * a.Z;
-    long long row = (long long)pix * 2 * a.Z;
-    float mq = qb[row + c], lq = qb[row + a.Z + c], mp = pb[row + c], lp = pb[row + a.Z + c];
-    float zv = a.z[(long long)b * n + i];
-    float gz = a.g_z ? a.g_z[(long long)b * n + i] : 0.f;
-    float gks = a.g_kls ? a.g_kls[(long long)b * a.hw + pix] : 0.f;
-    float ivq = expf(-lq), ivp = expf(-lp);     // 1/sigma^2
-    float aq = zv - mq, ap = zv - mp;
-    // coefficients on log q(z) and log p(z)
-    float cq = glq + (a.analytical ? 0.f : gkl);
-    float cp = glp - (a.analytical ? 0.f : gkl);
-    // d/dz of (cq*logq + cp*logp) plus upstream
-    float gzt = gz - cq * aq * ivq - cp * ap * ivp;
-    // direct parameter terms
-    float dmq = cq * aq * ivq, dlq = cq * (0.5f * aq * aq * ivq - 0.5f);
-    float dmp = cp * ap * ivp, dlp = cp * (0.5f * ap * ap * ivp - 0.5f);
-    // analytic KL terms (always for kl_spatial, for kl_sample when analytical)
-    float ga = gks + (a.analytical ? gkl : 0.f);
-    if (ga != 0.f) {
-      float vr = expf(lq - lp), dm = mq - mp;
-      dmq += ga * dm * ivp;
-      dmp -= ga * dm * ivp;
-      dlq += ga * 0.5f * (vr - 1.f);
-      dlp += ga * 0.5f * (1.f - vr - dm * dm * ivp);
+  const int ZV = a.Z / VEC;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < a.nvec; i += (long long)gridDim.x * blockDim.x) {
+    const long long pixg = i / ZV;                         // global pixel index b * hw + pix
+    const int c = (int)(i - pixg * ZV) * VEC;
+    const int b = (int)(pixg / a.hw);
+    const int pix = (int)(pixg - (long long)b * a.hw);
+    const long long rowq = pixg * 2 * a.Z;
+    const long long rowp = (long long)b * a.p_bstride + (long long)pix * 2 * a.Z;
+    float mq[VEC], lq[VEC], mp[VEC], lp[VEC], zv[VEC], gz[VEC];
+    if (VEC == 4) {
+      float4 t;
+      t = __ldg(reinterpret_cast<const float4*>(a.q + rowq + c)); mq[0] = t.x; mq[1] = t.y; mq[2] = t.z; mq[3] = t.w;
+      t = __ldg(reinterpret_cast<const float4*>(a.q + rowq + a.Z + c)); lq[0] = t.x; lq[1] = t.y; lq[2] = t.z; lq[3] = t.w;
+      t = __ldg(reinterpret_cast<const float4*>(a.p + rowp + c)); mp[0] = t.x; mp[1] = t.y; mp[2] = t.z; mp[3] = t.w;
+      t = __ldg(reinterpret_cast<const float4*>(a.p + rowp + a.Z + c)); lp[0] = t.x; lp[1] = t.y; lp[2] = t.z; lp[3] = t.w;
+      t = __ldg(reinterpret_cast<const float4*>(a.z + pixg * a.Z + c)); zv[0] = t.x; zv[1] = t.y; zv[2] = t.z; zv[3] = t.w;
+      gz[0] = gz[1] = gz[2] = gz[3] = 0.f;
+      if (a.g_z) { t = __ldg(reinterpret_cast<const float4*>(a.g_z + pixg * a.Z + c)); gz[0] = t.x; gz[1] = t.y; gz[2] = t.z; gz[3] = t.w; }
+    } else {
+      mq[0] = a.q[rowq + c]; lq[0] = a.q[rowq + a.Z + c]; mp[0] = a.p[rowp + c]; lp[0] = a.p[rowp + a.Z + c];
+      zv[0] = a.z[pixg * a.Z + c];
+      gz[0] = a.g_z ? a.g_z[pixg * a.Z + c] : 0.f;
     }
-    // reparameterisation path z = mu_q + sigma_q*eps
-    if (a.z_is_sample == 1) { dmq += gzt; dlq += gzt * 0.5f * aq; }
-    else if (a.z_is_sample == 2) { dmq += gzt; }
-    dqb[row + c] = dmq; dqb[row + a.Z + c] = dlq;
-    dpb[row + c] = dmp; dpb[row + a.Z + c] = dlp;
+    const float gkl = a.g_kl ? __ldg(a.g_kl + b) : 0.f, glp = a.g_logp ? __ldg(a.g_logp + b) : 0.f;
+    const float glq = a.g_logq ? __ldg(a.g_logq + b) : 0.f;
+    const float gks = a.g_kls ? __ldg(a.g_kls + pixg) : 0.f;
+    // coefficients on log q(z) and log p(z)
+    const float cq = glq + (a.analytical ? 0.f : gkl);
+    const float cp = glp - (a.analytical ? 0.f : gkl);
+    const float ga = gks + (a.analytical ? gkl : 0.f);      // coefficient on the analytic KL
+    float dmq[VEC], dlq[VEC], dmp[VEC], dlp[VEC];
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) {
+      const float ivq = ex2_approx(-lq[j] * LOG2E), ivp = ex2_approx(-lp[j] * LOG2E);     // 1/sigma^2
+      const float aq = zv[j] - mq[j], ap = zv[j] - mp[j];
+      // d/dz of (cq*logq + cp*logp) plus upstream
+      const float gzt = gz[j] - cq * aq * ivq - cp * ap * ivp;
+      // direct parameter terms
+      float tmq = cq * aq * ivq, tlq = cq * (0.5f * aq * aq * ivq - 0.5f);
+      float tmp_ = cp * ap * ivp, tlp = cp * (0.5f * ap * ap * ivp - 0.5f);
+      // analytic KL terms (always for kl_spatial, for kl_sample when analytical)
+      if (ga != 0.f) {
+        const float vr = ex2_approx((lq[j] - lp[j]) * LOG2E), dm = mq[j] - mp[j];
+        tmq += ga * dm * ivp;
+        tmp_ -= ga * dm * ivp;
+        tlq += ga * 0.5f * (vr - 1.f);
+        tlp += ga * 0.5f * (1.f - vr - dm * dm * ivp);
+      }
+      // reparameterisation path z = mu_q + sigma_q*eps
+      if (a.z_is_sample == 1) { tmq += gzt; tlq += gzt * 0.5f * aq; }
+      else if (a.z_is_sample == 2) { tmq += gzt; }
+      dmq[j] = tmq; dlq[j] = tlq; dmp[j] = tmp_; dlp[j] = tlp;
+    }
+    if (VEC == 4) {
+      *reinterpret_cast<float4*>(a.dq + rowq + c) = make_float4(dmq[0], dmq[1], dmq[2], dmq[3]);
+      *reinterpret_cast<float4*>(a.dq + rowq + a.Z + c) = make_float4(dlq[0], dlq[1], dlq[2], dlq[3]);
+      *reinterpret_cast<float4*>(a.dp + rowq + c) = make_float4(dmp[0], dmp[1], dmp[2], dmp[3]);
+      *reinterpret_cast<float4*>(a.dp + rowq + a.Z + c) = make_float4(dlp[0], dlp[1], dlp[2], dlp[3]);
+    } else {
+      a.dq[rowq + c] = dmq[0]; a.dq[rowq + a.Z + c] = dlq[0];
+      a.dp[rowq + c] = dmp[0]; a.dp[rowq + a.Z + c] = dlp[0];
+    }
   }
 }
 
+}  // namespace
+
 LVAE_API int lvae_stoch_bwd(const float* q, const float* p, int p_broadcast, const float* z, const float* g_z,
-                            const float* g_kl, const float* g_logp, const float* g_logq, const float* g_kls,
-                            float* dq, float* dp, int B, int hw, int Z, int analytical, int z_kind,
-                            cudaStream_t stream) {
+                            const float* g_kl, const float* g_logp, const float* g_logq, const float* g_kls, float* dq,
+                            float* dp, int B, int hw, int Z, int analytical, int z_kind, cudaStream_t stream) {
   LVAE_REQUIRE(q && p && z && dq && dp && B > 0, "stoch_bwd: bad args");
-  StochBwdArgs a{q, p, p_broadcast ? 0LL : (long long)hw * 2 * Z, z, g_z, g_kl, g_logp, g_logq, g_kls, dq, dp,
-                 B, hw, Z, analytical, z_kind};
-  lvae_launch(stoch_bwd_kernel, B, 256, 0, stream, a);
+  const int vec = Z % 4 == 0 ? 4 : 1;
+  StochBwdArgs a{q, p, p_broadcast ? 0LL : (long long)hw * 2 * Z, z, g_z,
+                 g_kl, g_logp, g_logq, g_kls, dq, dp, B, hw, Z, analytical, z_kind, (long long)B * hw * Z / vec};
+  const int grid = (int)min((long long)lvae_num_sms() * 8, (a.nvec + 255) / 256);
+  if (vec == 4) lvae_launch(stoch_bwd_kernel<4>, grid, 256, 0, stream, a);
+  else lvae_launch(stoch_bwd_kernel<1>, grid, 256, 0, stream, a);
   LVAE_COUNT_LAUNCH();
   LVAE_CHECK_LAUNCH("stoch_bwd");
+  return LVAE_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// KL / free-bits bookkeeping of LadderVAE.forward (models/lvae.py:192-198) and the log p(z) total of topdown_pass
+// (:301-302) over the (L,B) matrices whose rows the stochastic kernels of the L layers wrote:
+//   kl_sep[b] = sum_l kl[l,b];  kl = mean_b kl_sep;  kl_avg_layerwise[l] = mean_b kl[l,b];
+//   kl_loss = sum_l mean_b max(kl[l,b], free_bits)   (boilr free_bits_kl: per-sample, per-layer clamp, then the batch
+//   mean; free_bits < 1e-6 switches the clamp off);  logp = sum_l mean_b logp[l,b].
+// coef[l,b] = d kl_loss / d kl[l,b] = (kl[l,b] >= free_bits or clamp off) / B is kept for the backward.
+// One CTA: the matrices are a few thousand floats; per-layer sums are warp-shuffle + block reductions in a fixed order.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) kl_bookkeeping_kernel(const float* __restrict__ kl, const float* __restrict__ lp,
+                                                             int L, int B, float free_bits, float* __restrict__ kl_sep,
+                                                             float* __restrict__ scalars, float* __restrict__ kl_avg,
+                                                             float* __restrict__ coef) {
+  pdl_wait();
+  pdl_launch();
+  __shared__ float red[32];
+  const float invB = 1.f / (float)B;
+  const bool clamp = free_bits >= 1e-6f;
+  float tot_kl = 0.f, tot_loss = 0.f, tot_lp = 0.f;        // valid in thread 0
+  for (int l = 0; l < L; ++l) {
+    float s = 0.f, sf = 0.f, sp = 0.f;
+    for (int b = threadIdx.x; b < B; b += blockDim.x) {
+      const float v = kl[(long long)l * B + b];
+      const bool pass = !clamp || v >= free_bits;          // torch.clamp(min): gradient 1 where kl >= free_bits
+      s += v;
+      sf += pass ? v : free_bits;
+      if (coef) coef[(long long)l * B + b] = pass ? invB : 0.f;
+      if (lp) sp += lp[(long long)l * B + b];
+    }
+    s = block_sum(s, red);
+    sf = block_sum(sf, red);
+    sp = block_sum(sp, red);
+    if (threadIdx.x == 0) {
+      kl_avg[l] = s * invB;
+      tot_kl += s * invB; tot_loss += sf * invB; tot_lp += sp * invB;
+    }
+  }
+  for (int b = threadIdx.x; b < B; b += blockDim.x) {
+    float s = 0.f;
+    for (int l = 0; l < L; ++l) s += kl[(long long)l * B + b];
+    kl_sep[b] = s;
+  }
+  if (threadIdx.x == 0) { scalars[0] = tot_kl; scalars[1] = tot_loss; scalars[2] = tot_lp; }
+}
+
+// scalars: float[3] = {kl, kl_loss, logp}; logp_rows / coef may be NULL
+LVAE_API int lvae_kl_bookkeeping(const float* kl_rows, const float* logp_rows, int L, int B, float free_bits, float* kl_sep,
+                                 float* scalars, float* kl_avg_layerwise, float* coef, cudaStream_t stream) {
+  LVAE_REQUIRE(kl_rows && kl_sep && scalars && kl_avg_layerwise && L > 0 && B > 0, "kl_bookkeeping: bad args");
+  lvae_launch(kl_bookkeeping_kernel, 1, 256, 0, stream, kl_rows, logp_rows, L, B, free_bits, kl_sep, scalars, kl_avg_layerwise, coef);
+  LVAE_COUNT_LAUNCH();
+  LVAE_CHECK_LAUNCH("kl_bookkeeping");
+  return LVAE_OK;
+}
+
+// g_kl[l,b] = g_loss * coef[l,b] + g_klmean / B + g_sep[b] + g_avg[l] / B;  g_lp[l,b] = g_logp / B
+// g_scalars: device float[3] = upstream gradients of {kl, kl_loss, logp} (entries of absent gradients are 0)
+__global__ void kl_bookkeeping_bwd_kernel(const float* __restrict__ coef, const float* __restrict__ g_scalars,
+                                          const float* __restrict__ g_sep, const float* __restrict__ g_avg, int L, int B,
+                                          float* __restrict__ g_kl, float* __restrict__ g_lp) {
+  pdl_wait();
+  pdl_launch();
+  const float invB = 1.f / (float)B;
+  const float gk = g_scalars[0] * invB, gl = g_scalars[1], gp = g_scalars[2] * invB;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < L * B; i += gridDim.x * blockDim.x) {
+    const int l = i / B, b = i - l * B;
+    g_kl[i] = gl * coef[i] + gk + (g_sep ? g_sep[b] : 0.f) + (g_avg ? g_avg[l] * invB : 0.f);
+    if (g_lp) g_lp[i] = gp;
+  }
+}
+
+LVAE_API int lvae_kl_bookkeeping_bwd(const float* coef, const float* g_scalars, const float* g_kl_sep, const float* g_kl_avg,
+                                     int L, int B, float* g_kl_rows, float* g_logp_rows, cudaStream_t stream) {
+  LVAE_REQUIRE(coef && g_scalars && g_kl_rows && L > 0 && B > 0, "kl_bookkeeping_bwd: bad args");
+  lvae_launch(kl_bookkeeping_bwd_kernel, cdiv((long long)L * B, 256), 256, 0, stream, coef, g_scalars, g_kl_sep, g_kl_avg, L, B,
+              g_kl_rows, g_logp_rows);
+  LVAE_COUNT_LAUNCH();
+  LVAE_CHECK_LAUNCH("kl_bookkeeping_bwd");
   return LVAE_OK;
 }

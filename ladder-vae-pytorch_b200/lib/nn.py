@@ -28,8 +28,9 @@ class Conv2d(nn.Conv2d):
             raise NotImplementedError("lvae_b200.Conv2d supports square, ungrouped, undilated, zero-padded convs")
         self.spec = ops.ConvSpec(self.out_channels, self.in_channels, k[0], s[0], p[0])
 
-    def forward(self, x, x2=None, out_scale=None, res=None, stats_bn=None):
-        return ops.conv2d(x, self.weight, self.bias, self.spec, x2=x2, out_scale=out_scale, res=res, stats_bn=stats_bn)
+    def forward(self, x, x2=None, out_scale=None, res=None, stats_bn=None, x_lowp=None):
+        return ops.conv2d(x, self.weight, self.bias, self.spec, x2=x2, out_scale=out_scale, res=res, stats_bn=stats_bn,
+                          x_lowp=x_lowp)
 
 
 class ConvTranspose2d(nn.ConvTranspose2d):

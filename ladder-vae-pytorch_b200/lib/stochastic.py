@@ -51,7 +51,7 @@ class NormalStochasticBlock2d(nn.Module):
             p_shared = p_params[0:1].expand_as(p_params).contiguous()
             z, z_lp, _, _, logprob_p, _ = ops.stochastic_core(None, p_params, forced=z, lowp_copy=lowp)
             p_params = p_shared
-        out = self.conv_out(z_lp if z_lp is not None else z)
+        out = self.conv_out(z, x_lowp=z_lp)
         data = {
             "z": z,
             "p_params": p_params,

@@ -11,7 +11,7 @@ import torch
 from torch import nn
 
 from lvae_b200 import ops
-from lvae_b200.boilr_compat import BaseGenerativeModel, free_bits_kl
+from lvae_b200.boilr_compat import BaseGenerativeModel
 from lvae_b200.lib.likelihoods import (BernoulliLikelihood, DiscretizedLogisticLikelihood,
                                        DiscretizedLogisticMixLikelihood, GaussianLikelihood)
 from lvae_b200.lib.nn import Conv2d, Dropout2d, Interpolate, NONLIN
@@ -144,17 +144,18 @@ class LadderVAE(BaseGenerativeModel):
         ll, lik = self.likelihood(out, x)
         ops.clear_masks()
 
-        kl = torch.stack(td["kl"], dim=1)            # (batch, layers)
-        kl_sep = kl.sum(1)
+        # free bits + KL bookkeeping (models/lvae.py:192-198 of the reference) over the (layers, batch) matrix whose rows
+        # the stochastic kernels wrote: one launch (lvae_kl_bookkeeping), one more in the backward
+        book = td["book"]
         return {
             "ll": ll,
             "z": td["z"],
-            "kl": kl_sep.mean(),
-            "kl_sep": kl_sep,
-            "kl_avg_layerwise": kl.mean(0),
+            "kl": book["kl"],
+            "kl_sep": book["kl_sep"],
+            "kl_avg_layerwise": book["kl_avg_layerwise"],
             "kl_spatial": td["kl_spatial"],
-            "kl_loss": free_bits_kl(kl, self.free_bits).sum(),
-            "logp": td["logprob_p"],
+            "kl_loss": book["kl_loss"],
+            "logp": book["logp"],
             "out_mean": lik["mean"],
             "out_mode": lik["mode"],
             "out_sample": lik["sample"],
@@ -185,8 +186,10 @@ class LadderVAE(BaseGenerativeModel):
         z, kl, kl_spatial = [None] * L, [None] * L, [None] * L
         if forced_latent is None:
             forced_latent = [None] * L
-        logprob_p = []
+        logprob_p = [None] * L
         out = None
+        if inference_mode:
+            ops.begin_kl_rows(L, bu_values[-1].shape[0], bu_values[-1].device)
         for i in reversed(range(L)):
             bu_value = bu_values[i] if inference_mode else None
             out, _pre_residual, aux = self.top_down_layers[i](
@@ -194,11 +197,16 @@ class LadderVAE(BaseGenerativeModel):
                 n_img_prior=n_img_prior, use_mode=i in mode_layers, force_constant_output=i in constant_layers,
                 forced_latent=forced_latent[i])
             z[i], kl[i], kl_spatial[i] = aux["z"], aux["kl_samplewise"], aux["kl_spatial"]
-            logprob_p.append(aux["logprob_p"])
+            logprob_p[i] = aux["logprob_p"]
         out = self.final_top_down(out)
-        # sum over layers of the batch means (lvae.py:301-302) as three launches instead of one mean + one add per layer
-        logprob_p = torch.stack(logprob_p, dim=0).mean(dim=1).sum()
-        return out, {"z": z, "kl": kl, "kl_spatial": kl_spatial, "logprob_p": logprob_p}
+        data = {"z": z, "kl": kl, "kl_spatial": kl_spatial}
+        if inference_mode:
+            # sum over layers of the batch means of log p(z) (lvae.py:301-302) comes out of the same launch as the KL terms
+            data["book"] = ops.kl_bookkeeping(kl, logprob_p, self.free_bits, rows=ops.end_kl_rows())
+            data["logprob_p"] = data["book"]["logp"]
+        else:
+            data["logprob_p"] = torch.stack(logprob_p, dim=0).mean(dim=1).sum()
+        return out, data
 
     def pad_input(self, x):
         """Zero-pad (centred) to the next multiple of the overall downscale factor and hand the

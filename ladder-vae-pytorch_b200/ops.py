@@ -109,6 +109,10 @@ class StepContext(threading.local):
         self.masks: Optional[List[torch.Tensor]] = None
         self.mask_arena: Optional[torch.Tensor] = None
         self.mask_cursor = 0
+        # (3, L, B) fp32 rows [kl_samplewise | logprob_p | logprob_q] of the L stochastic layers of one top-down pass: every
+        # layer's kernel writes its row, lvae_kl_bookkeeping reads the matrices (no torch.stack, no per-layer reductions)
+        self.kl_rows: Optional[torch.Tensor] = None
+        self.kl_cursor = 0
 
 
 _ctx = StepContext()
@@ -144,6 +148,28 @@ def prepare_masks(n_sites: int, batch: int, channels: int, p: float, device) -> 
     call("lvae_dropout_masks", arena.data_ptr(), arena.numel(), float(p), rng_state(device).data_ptr(),
          next_stream_id(), _stream())
     _ctx.mask_arena, _ctx.mask_cursor = arena, 0
+
+
+def begin_kl_rows(n_layers: int, batch: int, device) -> None:
+    """LadderVAE.topdown_pass (inference): reserve one row per stochastic layer for this pass."""
+    _ctx.kl_rows = torch.empty((3, n_layers, batch), dtype=torch.float32, device=device)
+    _ctx.kl_cursor = 0
+
+
+def end_kl_rows():
+    rows, _ctx.kl_rows = _ctx.kl_rows, None
+    return rows
+
+
+def _take_kl_row(batch: int, device):
+    """(kl, logp, logq) output vectors of one stochastic block: the next row of the pass's matrices, or fresh tensors."""
+    r = _ctx.kl_rows
+    if r is not None and _ctx.kl_cursor < r.shape[1] and r.shape[2] == batch and r.device == device:
+        i = _ctx.kl_cursor
+        _ctx.kl_cursor += 1
+        return r[0, i], r[1, i], r[2, i]
+    v = torch.empty((3, batch), dtype=torch.float32, device=device)
+    return v[0], v[1], v[2]
 
 
 def clear_masks() -> None:
@@ -506,13 +532,13 @@ def conv_backward_raw(spec: ConvSpec, xn, x2n, weight, bias, out_scale, gyn, nee
             if x2n is None:
                 fuse_bnb = (bnb is not None and not padded and _tc_fusable(spec.cin, False, None)
                             and _FUSE_BNB_MAXPIX >= gyn.shape[0] * gyn.shape[1] * gyn.shape[2])
-                gx = _conv_tc(gyn, None, wpb, None, dx_scale, None, spec.cin, spec.k, True, False,
+                # padded (conv_out of a stochastic block reading the 64-channel bf16 copy of z): the gradient goes to the
+                # fp32, Z-channel z the autograd graph holds -> fp32 epilogue, no padding channels
+                gx = _conv_tc(gyn, None, wpb, None, dx_scale, None, spec.cin, spec.k, True, padded,
                               bnb=bnb if fuse_bnb else None)
                 if fuse_bnb:
                     stats["bnb_fused"] = stats.get("bnb_fused", 0) + 1
                     conv_backward_raw.last_fused = True
-                if padded:          # gradient wrt the zero-padded input: the padding channels get zeros
-                    gx = torch.nn.functional.pad(gx, (0, C1 - spec.cin))
             else:
                 assert dx_scale is None
                 gx, gx2 = _conv_tc(gyn, None, wpb, None, None, None, spec.cin, spec.k, True, False, nsplit=C1)
@@ -577,9 +603,12 @@ class Conv2dFn(Function):
     """y = (conv(cat(x, x2)) + bias) * out_scale[b, c] + res   (Conv2d or ConvTranspose2d)."""
 
     @staticmethod
-    def forward(ctx, x, x2, weight, bias, out_scale, res, spec: ConvSpec, stats_bn=None):
+    def forward(ctx, x, x2, weight, bias, out_scale, res, spec: ConvSpec, stats_bn=None, x_lowp=None):
         _require_cuda(x)
-        xn = nhwc(x)
+        # x_lowp: the kernel's actual operand when the caller already holds a bf16, channel-padded copy of x (the stochastic
+        # kernel writes z both as fp32 and as the 64-channel bf16 operand of conv_out); x itself then only carries the autograd
+        # edge, and the data gradient comes back in x's own shape and dtype (fp32 epilogue): no pad / slice / cast passes
+        xn = nhwc(x_lowp) if x_lowp is not None else nhwc(x)
         x2n = nhwc(x2) if x2 is not None else None
         resn = nhwc(res) if res is not None else None
         if out_scale is not None:
@@ -608,13 +637,13 @@ class Conv2dFn(Function):
                                             ctx.needs_input_grad[2], ctx.needs_input_grad[3])
         gres = gy if ctx.has_res and ctx.needs_input_grad[5] else None
         return (as_nchw(gx) if gx is not None else None, as_nchw(gx2) if gx2 is not None else None, gw, gb, None,
-                gres, None, None)
+                gres, None, None, None)
 
 
-def conv2d(x, weight, bias, spec: ConvSpec, x2=None, out_scale=None, res=None, stats_bn=None):
+def conv2d(x, weight, bias, spec: ConvSpec, x2=None, out_scale=None, res=None, stats_bn=None, x_lowp=None):
     """stats_bn: the train-mode BatchNorm2d that consumes the output next (its statistics are then accumulated by this
     conv's epilogue and handed over through the output tensor, like a gated block does for its successor)."""
-    out = Conv2dFn.apply(x, x2, weight, bias, out_scale, res, spec, stats_bn)
+    out = Conv2dFn.apply(x, x2, weight, bias, out_scale, res, spec, stats_bn, x_lowp)
     if stats_bn is not None and getattr(spec, "_last_stats", None) is not None:
         out._lvae_stats = spec._last_stats
         spec._last_stats = None
@@ -997,6 +1026,20 @@ def crop(x, size):
 
 
 # --------------------------------------------------------------------------- stochastic block core
+_stoch_ws = {}
+
+
+def _stoch_workspace(batch: int, device) -> torch.Tensor:
+    """Zero-initialised scratch that lets lvae_stoch_fwd split one sample over several CTAs (stream-ordered reuse)."""
+    key = (device, torch.cuda.current_stream().cuda_stream)
+    ws = _stoch_ws.get(key)
+    need = int(_capi.lib().lvae_stoch_ws_bytes(batch))
+    if ws is None or ws.numel() < need:
+        ws = torch.zeros(need, dtype=torch.uint8, device=device)
+        _stoch_ws[key] = ws
+    return ws
+
+
 class StochasticFn(Function):
     """Everything between conv_in_* and conv_out of NormalStochasticBlock2d (lib/stochastic.py:45-96)."""
 
@@ -1017,10 +1060,9 @@ class StochasticFn(Function):
         # bf16 copy of z for conv_out, zero-padded to 64 channels so that the conv runs on the tensor cores
         zp = 64 if (lowp_copy and Z < 64) else Z
         z_lp = torch.empty((B, H, W, zp), dtype=torch.bfloat16, device=dev) if lowp_copy else None
-        logp = torch.empty((B,), dtype=torch.float32, device=dev)
+        kl_row, logp, logq_row = _take_kl_row(B, dev)
         if qn is not None:
-            kl = torch.empty((B,), dtype=torch.float32, device=dev)
-            logq = torch.empty((B,), dtype=torch.float32, device=dev)
+            kl, logq = kl_row, logq_row
             kls = torch.empty((B, H, W), dtype=torch.float32, device=dev)
         else:
             kl = logq = kls = None
@@ -1028,13 +1070,15 @@ class StochasticFn(Function):
         call("lvae_stoch_fwd", _p(qn), pn.data_ptr(), 1 if p_broadcast else 0, _p(epsn), _p(forcedn),
              rng_state(dev).data_ptr() if need_rng else None, next_stream_id() if need_rng else 0,
              z.data_ptr(), _p(z_lp), zp, _p(kl), _p(kls), logp.data_ptr(), _p(logq), B, hw, Z,
-             1 if use_mode else 0, 1 if analytical else 0, _stream())
+             1 if use_mode else 0, 1 if analytical else 0, _stoch_workspace(B, dev).data_ptr(), _stream())
         ctx.save_for_backward(qn, pn, z)
         ctx.meta = (B, hw, Z, p_broadcast, analytical, 0 if forced is not None else (2 if use_mode else 1))
         ctx.q_dtype = q_params.dtype if q_params is not None else None
         ctx.p_dtype = p_params.dtype
         zo = as_nchw(z)
         zlo = as_nchw(z_lp) if z_lp is not None else None
+        if zlo is not None:
+            ctx.mark_non_differentiable(zlo)      # conv_out takes it as a side operand; the gradient flows through z
         return zo, zlo, kl, kls, logp, logq
 
     @staticmethod
@@ -1044,9 +1088,6 @@ class StochasticFn(Function):
             raise RuntimeError("backward through prior sampling is not supported")
         B, hw, Z, p_broadcast, analytical, z_kind = ctx.meta
         gz = nhwc(g_z).float() if g_z is not None else None
-        if g_zlp is not None:       # gradient that arrived through the bf16 copy of z (input of conv_out)
-            gl = nhwc(g_zlp)[..., :Z].float()
-            gz = gl if gz is None else gz + gl
         cg = lambda t: t.contiguous().float() if t is not None else None
         g_kl, g_kls, g_logp, g_logq = cg(g_kl), cg(g_kls), cg(g_logp), cg(g_logq)
         dq = torch.empty_like(qn)
@@ -1068,6 +1109,69 @@ class StochasticFn(Function):
 
 def stochastic_core(q_params, p_params, eps=None, forced=None, use_mode=False, analytical=False, lowp_copy=False):
     return StochasticFn.apply(q_params, p_params, eps, forced, use_mode, analytical, lowp_copy)
+
+
+class KLBookFn(Function):
+    """Free bits and the KL / log p bookkeeping of LadderVAE.forward (models/lvae.py:192-198,301-302; boilr free_bits_kl)
+    as ONE launch over the (L,B) matrices the stochastic kernels filled, with a one-launch backward.
+    apply(free_bits, L, rows_or_None, kl_0 .. kl_{L-1}, logp_0 .. logp_{L-1}) -> (kl_sep, kl, kl_avg_layerwise, kl_loss, logp)."""
+
+    @staticmethod
+    def forward(ctx, free_bits, L, rows, *vecs):
+        kls, lps = vecs[:L], vecs[L:]
+        B = kls[0].shape[0]
+        dev = kls[0].device
+        # the vectors are the rows of the pass's (3,L,B) matrix when LadderVAE.topdown_pass reserved it; anything else
+        # (blocks called on their own, a batch-size change mid-pass) is gathered first
+        in_place = (rows is not None and rows.shape[1] == L and rows.shape[2] == B and
+                    all(kls[i].data_ptr() == rows[0, i].data_ptr() and lps[i].data_ptr() == rows[1, i].data_ptr() for i in range(L)))
+        if in_place:
+            klm, lpm = rows[0], rows[1]
+        else:
+            klm = torch.stack([k.float() for k in kls]).contiguous()
+            lpm = torch.stack([v.float() for v in lps]).contiguous()
+        kl_sep = torch.empty((B,), dtype=torch.float32, device=dev)
+        scal = torch.empty((3,), dtype=torch.float32, device=dev)
+        avg = torch.empty((L,), dtype=torch.float32, device=dev)
+        coef = torch.empty((L, B), dtype=torch.float32, device=dev)
+        call("lvae_kl_bookkeeping", klm.data_ptr(), lpm.data_ptr(), L, B, float(free_bits), kl_sep.data_ptr(), scal.data_ptr(),
+             avg.data_ptr(), coef.data_ptr(), _stream())
+        ctx.save_for_backward(coef)
+        ctx.L, ctx.B = L, B
+        ctx.set_materialize_grads(False)
+        return kl_sep, scal[0], avg, scal[1], scal[2]
+
+    @staticmethod
+    def backward(ctx, g_sep, g_kl, g_avg, g_loss, g_lp):
+        (coef,) = ctx.saved_tensors
+        L, B = ctx.L, ctx.B
+        dev = coef.device
+        parts = [g_kl, g_loss, g_lp]
+        if all(p is None for p in parts):
+            gs = torch.zeros((3,), dtype=torch.float32, device=dev)
+        else:
+            z = None
+            cols = []
+            for p in parts:
+                if p is None:
+                    if z is None:
+                        z = torch.zeros((), dtype=torch.float32, device=dev)
+                    cols.append(z)
+                else:
+                    cols.append(p.float().reshape(()))
+            gs = torch.stack(cols)
+        gk = torch.empty((L, B), dtype=torch.float32, device=dev)
+        gl = torch.empty((L, B), dtype=torch.float32, device=dev) if g_lp is not None else None
+        call("lvae_kl_bookkeeping_bwd", coef.data_ptr(), gs.data_ptr(), _p(g_sep.contiguous().float() if g_sep is not None else None),
+             _p(g_avg.contiguous().float() if g_avg is not None else None), L, B, gk.data_ptr(), _p(gl), _stream())
+        return (None, None, None) + tuple(gk[i] for i in range(L)) + tuple((gl[i] if gl is not None else None) for i in range(L))
+
+
+def kl_bookkeeping(kl_list, logp_list, free_bits: float, rows=None):
+    """-> dict(kl_sep (B,), kl, kl_avg_layerwise (L,), kl_loss, logp) from the per-layer (B,) vectors."""
+    L = len(kl_list)
+    kl_sep, kl, avg, loss, lp = KLBookFn.apply(float(free_bits), L, rows, *kl_list, *logp_list)
+    return {"kl_sep": kl_sep, "kl": kl, "kl_avg_layerwise": avg, "kl_loss": loss, "logp": lp}
 
 
 # --------------------------------------------------------------------------- likelihoods

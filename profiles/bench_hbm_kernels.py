@@ -64,9 +64,9 @@ def report(rows, name, shape, nbytes, us, peak, src):
     print("%-26s %-26s %8.2f us  %7.0f GB/s  %5.1f %% of %s peak" % (name, shape, us, gbs, 100 * gbs / peak, src))
 
 
-def bench_stochastic(rows, peak, src, B=256, Z=32):
+def bench_stochastic(rows, peak, src, B=256, Z=32, sides=(16, 8, 4, 2)):
     dev = torch.device("cuda")
-    for hw_side in (16, 8, 4, 2):
+    for hw_side in sides:
         hw = hw_side * hw_side
         n_el = B * hw * Z
         fwd_bytes = 20 * n_el + 4 * B * hw
@@ -84,11 +84,12 @@ def bench_stochastic(rows, peak, src, B=256, Z=32):
         logq = torch.empty(B, device=dev)
         g1 = torch.ones(B, device=dev)
         rng = ops.rng_state(dev)
+        ws = ops._stoch_workspace(B, dev)
 
         def fwd(i):
             _capi.call("lvae_stoch_fwd", q[i].data_ptr(), p[i].data_ptr(), 0, None, None, rng.data_ptr(), 7 + i,
                        z[i].data_ptr(), None, Z, kl.data_ptr(), kls.data_ptr(), logp.data_ptr(), logq.data_ptr(), B, hw, Z,
-                       0, 0, S())
+                       0, 0, ws.data_ptr(), S())
 
         def bwd(i):
             _capi.call("lvae_stoch_bwd", q[i].data_ptr(), p[i].data_ptr(), 0, z[i].data_ptr(), gz[i].data_ptr(),

@@ -186,7 +186,10 @@ def test_engine_hyperparameters_follow_without_recapture_and_state_dict_roundtri
     eng2 = TrainEngine(model2, 4, use_graph=False)
     eng2.load_state_dict(sd)
     assert int(eng2.step_count) == 4 and eng2.beta_kl == 0.0
-    assert float((eng2.exp_inf - eng.exp_inf).abs().max()) == 0.0 and float((eng2.exp_avg - eng.exp_avg).abs().max()) == 0.0
+    sd2 = eng2.state_dict()
+    for n in sd["state"]:                                   # (the arena's alignment padding is not part of the state)
+        for k in ("exp_avg", "exp_inf"):
+            assert torch.equal(sd2["state"][n][k], sd["state"][n][k]), (n, k)
 
 
 def test_iw_graph_equals_eager_and_sharding_is_invariant():

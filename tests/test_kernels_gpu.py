@@ -191,7 +191,10 @@ def test_upsample_crop_pad(L):
 
 @pytest.mark.parametrize("Z,hw,analytical,broadcast", [(32, (8, 8), False, False), (32, (2, 2), False, True),
                                                        (32, (4, 4), True, False), (6, (3, 5), False, False),
-                                                       (8, (4, 4), False, True), (64, (4, 4), False, False)])
+                                                       (8, (4, 4), False, True), (64, (4, 4), False, False),
+                                                       # several CTAs per sample (deterministic cross-CTA finish)
+                                                       (32, (32, 32), False, False), (32, (16, 16), True, True),
+                                                       (6, (24, 20), False, False)])
 def test_stochastic_core(L, Z, hw, analytical, broadcast):
     from oracle import lvae_oracle as O
     from lvae_b200 import ops
@@ -219,6 +222,62 @@ def test_stochastic_core(L, Z, hw, analytical, broadcast):
      + (lqo * dev(w[4])).sum()).backward()
     assert rel_err(qd.grad, qr.grad) < GTOL
     assert rel_err(pd.grad, pr.grad) < GTOL
+
+
+def test_stochastic_core_other_z_kinds(L):
+    """Mode (z = mu_q), forced latent and sampling from the prior (q absent) against the fp64 closed forms."""
+    from oracle import lvae_oracle as O
+    from lvae_b200 import ops
+    g = torch.Generator().manual_seed(11)
+    B, Z, hw = 4, 32, (16, 16)
+    q = torch.randn(B, 2 * Z, *hw, generator=g, dtype=torch.float64)
+    p = torch.randn(B, 2 * Z, *hw, generator=g, dtype=torch.float64)
+    qm, ql = q.chunk(2, 1)
+    pm, pl = p.chunk(2, 1)
+    forced = torch.randn(B, Z, *hw, generator=g, dtype=torch.float64)
+    for kind, zref in (("mode", qm), ("forced", forced)):
+        zz, _, klo, klso, lpo, lqo = ops.stochastic_core(dev(q), dev(p), forced=dev(forced) if kind == "forced" else None,
+                                                         use_mode=kind == "mode")
+        logp = O.normal_log_prob(zref, pm, pl).sum((1, 2, 3))
+        logq = O.normal_log_prob(zref, qm, ql).sum((1, 2, 3))
+        assert rel_err(zz, zref) < TOL and rel_err(lpo, logp) < TOL and rel_err(lqo, logq) < TOL, kind
+        assert rel_err(klo, logq - logp) < TOL and rel_err(klso, O.normal_kl(qm, ql, pm, pl).sum(1)) < TOL, kind
+    eps = torch.randn(B, Z, *hw, generator=g, dtype=torch.float64)
+    zz, _, klo, klso, lpo, lqo = ops.stochastic_core(None, dev(p), eps=dev(eps))
+    zref = pm + (pl / 2).exp() * eps
+    assert klo is None and klso is None and lqo is None
+    assert rel_err(zz, zref) < TOL and rel_err(lpo, O.normal_log_prob(zref, pm, pl).sum((1, 2, 3))) < TOL
+
+
+@pytest.mark.parametrize("Lr,B,fb", [(15, 256, 1.0), (3, 7, 0.5), (12, 1000, 0.0), (20, 64, 2.0)])
+def test_kl_bookkeeping(L, Lr, B, fb):
+    """lvae_kl_bookkeeping (+ backward) against the oracle's free_bits_kl and the sums of models/lvae.py:192-198."""
+    from oracle import lvae_oracle as O
+    from lvae_b200 import ops
+    g = torch.Generator().manual_seed(Lr * 1000 + B)
+    kl = (torch.rand(Lr, B, generator=g, dtype=torch.float64) * 2 * max(fb, 0.5)).requires_grad_(True)     # about half below the clamp
+    lp = torch.randn(Lr, B, generator=g, dtype=torch.float64).requires_grad_(True)
+    klbl = kl.t()                                           # (batch, layers), the reference's layout
+    ref = {"kl_sep": klbl.sum(1), "kl": klbl.sum(1).mean(), "kl_avg_layerwise": klbl.mean(0),
+           "kl_loss": O.free_bits_kl(klbl, fb).sum(), "logp": lp.mean(1).sum()}
+    w = {k: torch.randn(v.shape, generator=g, dtype=torch.float64) for k, v in ref.items()}
+    sum((ref[k] * w[k]).sum() for k in ref).backward()
+    for as_rows in (True, False):
+        if as_rows:                                         # rows of one (3,L,B) matrix, as LadderVAE.topdown_pass hands them over
+            rows = torch.zeros(3, Lr, B, device="cuda")
+            rows[0].copy_(kl.detach())
+            rows[1].copy_(lp.detach())
+            rows.requires_grad_(True)
+            kls, lps = [rows[0, i] for i in range(Lr)], [rows[1, i] for i in range(Lr)]
+            out = ops.kl_bookkeeping(kls, lps, fb, rows=rows.detach())
+        else:                                               # unrelated vectors: gathered first
+            kd, ld = dev(kl.detach(), True), dev(lp.detach(), True)
+            out = ops.kl_bookkeeping([kd[i] for i in range(Lr)], [ld[i] for i in range(Lr)], fb)
+        for k in ref:
+            assert rel_err(out[k], ref[k]) < 1e-5, (k, as_rows)
+        sum((out[k] * dev(w[k])).sum() for k in ref).backward()
+        gk, gl = (rows.grad[0], rows.grad[1]) if as_rows else (kd.grad, ld.grad)
+        assert rel_err(gk, kl.grad) < 1e-5 and rel_err(gl, lp.grad) < 1e-5, as_rows
 
 
 def test_stochastic_philox_statistics(L):
