@@ -29,6 +29,7 @@ class Conv2d(nn.Conv2d):
         self.spec = ops.ConvSpec(self.out_channels, self.in_channels, k[0], s[0], p[0])
 
     def forward(self, x, x2=None, out_scale=None, res=None, stats_bn=None, x_lowp=None):
+        ops.note_conv_call(bool(self._forward_hooks))
         return ops.conv2d(x, self.weight, self.bias, self.spec, x2=x2, out_scale=out_scale, res=res, stats_bn=stats_bn,
                           x_lowp=x_lowp)
 
@@ -43,6 +44,7 @@ class ConvTranspose2d(nn.ConvTranspose2d):
                                  output_padding=op[0])
 
     def forward(self, x, out_scale=None, res=None):
+        ops.note_conv_call(bool(self._forward_hooks))
         return ops.conv2d(x, self.weight, self.bias, self.spec, out_scale=out_scale, res=res)
 
 

@@ -223,6 +223,21 @@ def bump_pack_epoch() -> None:
 
 
 
+_hook_dirty = [False]
+
+
+def note_conv_call(hooked: bool) -> None:
+    """Forward hooks on conv modules (boilr's data_dependent_init, experiment_manager.py:62-72) rewrite `weight.data` in
+    place AFTER the module's forward, which torch's version counter does not see.  A hooked call marks the packed-weight
+    caches suspect; the first conv module called without hooks afterwards (the stem, at the top of the next forward)
+    invalidates them all."""
+    if hooked:
+        _hook_dirty[0] = True
+    elif _hook_dirty[0]:
+        _hook_dirty[0] = False
+        bump_pack_epoch()
+
+
 class WeightPack:
     """GEMM-ready copy of one conv weight (see lvae_pack_weights).  Re-packed when the
     parameter's version counter or storage changes (i.e. after every optimizer step).
