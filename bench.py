@@ -397,15 +397,24 @@ def run_dp_check(cx, engine):
     allsums = torch.empty((cx.world, 3), dtype=torch.float64, device="cuda")
     dist.all_gather_into_tensor(allsums, sums)
     param_diff = float((allsums - allsums[0:1]).abs().max())
-    # gradient arena: manual sum vs NCCL buckets (eager forward/backward on this rank's batch)
+    # gradient arena: the engine's (overlapped, bucketed) NCCL reduction against a manual fp64 sum of the per-rank arenas.
+    # Pass 1 with the reduction switched off gives this rank's own gradients; pass 2 replays the same step (same Philox
+    # state) through the engine's normal path.
+    from lvae_b200 import ops
+    rng = ops.rng_state(torch.device("cuda", torch.cuda.current_device()))
+    rng0 = rng.clone()
+    overlap = engine.overlap
+    engine.overlap = False
     engine._forward_backward()
     torch.cuda.synchronize()
     g_local = engine.arena.grad.clone()
     n = g_local.numel()
-    manual = torch.zeros(n, dtype=torch.float64, device="cuda")
     chunk = torch.empty((cx.world, n), dtype=torch.float32, device="cuda")
     dist.all_gather_into_tensor(chunk, g_local)
     manual = chunk.double().sum(0)
+    engine.overlap = overlap
+    rng.copy_(rng0)
+    engine._forward_backward()
     engine._all_reduce()
     torch.cuda.synchronize()
     red = engine.arena.grad.double()
@@ -413,7 +422,9 @@ def run_dp_check(cx, engine):
     # how different the per-rank gradients were (a check that the ranks really saw different data / noise)
     spread = float((chunk[0].double() - manual / cx.world).abs().max() / manual.abs().max() * cx.world)
     return {"param_checksum_max_abs_diff_across_ranks": param_diff, "grad_allreduce_vs_manual_sum_rel": gdiff,
-            "per_rank_grad_spread_rel": spread, "buckets": len(engine.buckets), "arena_mb": n * 4 / 2 ** 20}
+            "per_rank_grad_spread_rel": spread, "buckets": len(engine.buckets), "arena_mb": n * 4 / 2 ** 20,
+            "allreduce_overlapped_with_backward": bool(engine.overlap),
+            "buckets_flushed_early": [k for k, c in enumerate(engine._ready_counts or []) if c > 0]}
 
 
 def time_iw(cx, batch, K, dtype, steps, warmup, graph=True, full_forward=False, sampler=None):

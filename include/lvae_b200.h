@@ -209,8 +209,9 @@ int lvae_stoch_fwd(const float* q, const float* p, int p_broadcast, const float*
                    const void* rng_state, unsigned long long stream_id, float* z, void* z_bf16, int z_bf16_pitch, float* kl_sample,
                    float* kl_spatial, float* logp, float* logq, int B, int hw, int Z, int use_mode, int analytical,
                    void* ws, lvae_stream_t stream);
-/* ws: NULL (one CTA per sample) or a device workspace of lvae_stoch_ws_bytes(B) bytes, zeroed once by the caller, that lets
- * the kernel split a sample over several CTAs (their per-sample sums are combined in a fixed order: deterministic). */
+/* ws: NULL (one CTA per sample) or a device workspace of lvae_stoch_ws_bytes(B) bytes, zeroed once by the caller and used
+ * with this one batch size, that lets the kernel split a sample over several CTAs (their per-sample sums are combined in
+ * a fixed order: deterministic). */
 long long lvae_stoch_ws_bytes(int B);
 /* z_kind: 1 reparameterised sample, 2 mode, 0 forced latent.  dq, dp: (B,hw,2Z). */
 int lvae_stoch_bwd(const float* q, const float* p, int p_broadcast, const float* z, const float* g_z,

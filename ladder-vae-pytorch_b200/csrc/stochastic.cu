@@ -64,12 +64,16 @@ struct StochArgs {
 
 constexpr int ST_THREADS = 256;
 
-template <int VEC>
-__global__ void __launch_bounds__(ST_THREADS) stoch_fwd_kernel(StochArgs a) {
+// TRAIN = the training / IW-evaluation case (q present, Philox noise, no forced latent, no mode): a template flag so that
+// the hot instantiation carries none of the other cases' branches and fits 64 registers (4 CTAs per SM; the generic one
+// needed 112 and ran at a quarter of the occupancy).
+template <int VEC, bool TRAIN>
+__global__ void __launch_bounds__(ST_THREADS, TRAIN ? 4 : 2) stoch_fwd_kernel(StochArgs a) {
   pdl_wait();
   pdl_launch();
-  __shared__ float red[32];
+  __shared__ float red[3][ST_THREADS / 32];
   __shared__ unsigned int s_last;
+  if (TRAIN) { a.forced = nullptr; a.eps = nullptr; a.use_mode = 0; }
   const int b = blockIdx.y;
   const int ZV = a.Z / VEC;
   int G = 1;
@@ -81,7 +85,7 @@ __global__ void __launch_bounds__(ST_THREADS) stoch_fwd_kernel(StochArgs a) {
   const bool reparam = !a.forced && !a.use_mode;       // z = mu + sigma * e with e known exactly
   PhiloxState st;
   if (sampled) st = *a.rng;
-  const float* qb = a.q ? a.q + (long long)b * a.hw * 2 * a.Z : nullptr;
+  const float* qb = (TRAIN || a.q) ? a.q + (long long)b * a.hw * 2 * a.Z : nullptr;
   const float* pb = a.p + (long long)b * a.p_bstride;
   const int pix_begin = blockIdx.x * a.chunk_pix;
   const int pix_end = min(a.hw, pix_begin + a.chunk_pix);
@@ -168,10 +172,14 @@ __global__ void __launch_bounds__(ST_THREADS) stoch_fwd_kernel(StochArgs a) {
     for (int o = G >> 1; o > 0; o >>= 1) kls += __shfl_xor_sync(0xffffffffu, kls, o);
     if (pvalid && gl == 0 && a.kl_spatial) a.kl_spatial[(long long)b * a.hw + pix] = kls;
   }
-  float v_lp = block_sum(s_lp, red), v_lq = 0.f, v_kl = 0.f;
-  if (a.q) {
-    v_lq = block_sum(s_lq, red);
-    v_kl = block_sum(s_kl, red);
+  // the three per-sample sums in one block reduction (results valid in thread 0)
+  float v_lp = warp_sum(s_lp), v_lq = warp_sum(s_lq), v_kl = warp_sum(s_kl);
+  if (lane == 0) { red[0][warp] = v_lp; red[1][warp] = v_lq; red[2][warp] = v_kl; }
+  __syncthreads();
+  if (warp == 0) {
+    v_lp = warp_sum(lane < nwarp ? red[0][lane] : 0.f);
+    v_lq = warp_sum(lane < nwarp ? red[1][lane] : 0.f);
+    v_kl = warp_sum(lane < nwarp ? red[2][lane] : 0.f);
   }
   if (a.nchunk == 1) {
     if (threadIdx.x == 0) {
@@ -204,8 +212,9 @@ __global__ void __launch_bounds__(ST_THREADS) stoch_fwd_kernel(StochArgs a) {
 
 }  // namespace
 
-// workspace of a multi-chunk launch: B * 64 * 3 floats of partial sums + B tickets (zero-initialised ONCE by the caller;
-// launches that share it must be stream-ordered)
+// workspace of a multi-chunk launch: B arrival tickets, then B * 64 * 3 floats of partial sums.  Zero-initialised ONCE by
+// the caller and used with ONE batch size B (the tickets must stay zero between launches); launches that share it must be
+// stream-ordered
 LVAE_API long long lvae_stoch_ws_bytes(int B) { return (long long)B * (64 * 3 * 4 + 4); }
 
 LVAE_API int lvae_stoch_fwd(const float* q, const float* p, int p_broadcast, const float* eps, const float* forced,
@@ -217,23 +226,26 @@ LVAE_API int lvae_stoch_fwd(const float* q, const float* p, int p_broadcast, con
   LVAE_REQUIRE(!z_bf16 || (z_bf16_pitch >= Z && z_bf16_pitch % 4 == 0), "stoch_fwd: bad low-precision pitch");
   StochArgs a{q, p, p_broadcast ? 0LL : (long long)hw * 2 * Z, eps, forced, (const PhiloxState*)rng_state, stream_id,
               z, z_bf16, z_bf16_pitch, kl_sample, kl_spatial, logp, logq, B, hw, Z, use_mode, analytical, hw, 1, nullptr, nullptr};
-  // pixels one CTA covers per pass of its 8 warps; a chunk = two passes (16-byte loads of two pixels in flight per thread),
-  // unless that would need more than 64 chunks per sample or there is no workspace for the cross-CTA sums
+  // pixels one CTA covers per pass of its 8 warps; a chunk = one pass (every thread handles one 16-byte group of channels:
+  // all loads of the launch are independent and in flight at once), unless that would need more than 64 chunks per
+  // sample or there is no workspace for the cross-CTA sums
   const int vec = Z % 4 == 0 ? 4 : 1;
   int G = 1;
   while (G < Z / vec && G < 32) G <<= 1;
   const int per_pass = (ST_THREADS / 32) * (32 / G);
-  if (ws && hw > 2 * per_pass) {
-    int chunk = 2 * per_pass;
+  if (ws && hw > per_pass) {
+    int chunk = per_pass;
     while ((hw + chunk - 1) / chunk > 64) chunk *= 2;
     a.chunk_pix = chunk;
     a.nchunk = (hw + chunk - 1) / chunk;
-    a.ws_part = (float*)ws;
-    a.ws_cnt = (unsigned int*)((float*)ws + (long long)B * 64 * 3);
+    a.ws_cnt = (unsigned int*)ws;
+    a.ws_part = (float*)ws + B;
   }
   dim3 grid(a.nchunk, B);
-  if (vec == 4) lvae_launch(stoch_fwd_kernel<4>, grid, ST_THREADS, 0, stream, a);
-  else lvae_launch(stoch_fwd_kernel<1>, grid, ST_THREADS, 0, stream, a);
+  const bool train = q && !eps && !forced && !use_mode;
+  if (vec == 4 && train) lvae_launch(stoch_fwd_kernel<4, true>, grid, ST_THREADS, 0, stream, a);
+  else if (vec == 4) lvae_launch(stoch_fwd_kernel<4, false>, grid, ST_THREADS, 0, stream, a);
+  else lvae_launch(stoch_fwd_kernel<1, false>, grid, ST_THREADS, 0, stream, a);
   LVAE_COUNT_LAUNCH();
   LVAE_CHECK_LAUNCH("stoch_fwd");
   return LVAE_OK;

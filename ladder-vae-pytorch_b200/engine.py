@@ -55,12 +55,35 @@ def gather_states(state: torch.Tensor, group=None) -> torch.Tensor:
     return out.view((world,) + tuple(state.shape))
 
 
+def grad_ready_order(model: torch.nn.Module):
+    """Trainable parameters in the order the backward pass finishes their gradients: likelihood head, final top-down
+    blocks, top-down layers bottom -> top, bottom-up layers top -> bottom, stem (the reverse of LadderVAE.forward,
+    models/lvae.py:172-214; autograd runs the later-created nodes first), each module's own parameters reversed.  Buckets
+    of the gradient arena cut in this order complete one after the other during the backward, so their all-reduce can
+    start early.  Any other model: reversed registration order."""
+    groups = []
+    if all(hasattr(model, a) for a in ("likelihood", "final_top_down", "top_down_layers", "bottom_up_layers", "first_bottom_up")):
+        groups = [model.likelihood, model.final_top_down, *list(model.top_down_layers),
+                  *reversed(list(model.bottom_up_layers)), model.first_bottom_up]
+    seen, out = set(), []
+    for g in groups:
+        for p in reversed(list(g.parameters())):
+            if p.requires_grad and id(p) not in seen:
+                seen.add(id(p))
+                out.append(p)
+    for p in reversed(list(model.parameters())):
+        if p.requires_grad and id(p) not in seen:
+            seen.add(id(p))
+            out.append(p)
+    return out
+
+
 class ParamArena:
-    """All trainable parameters of a model as views into one flat fp32 buffer, with a parallel
-    gradient buffer that the wgrad / BatchNorm / prior kernels accumulate into directly."""
+    """All trainable parameters of a model as views into one flat fp32 buffer (laid out in gradient-ready order), with a
+    parallel gradient buffer that the wgrad / BatchNorm / prior kernels accumulate into directly."""
 
     def __init__(self, model: torch.nn.Module):
-        params = [p for p in model.parameters() if p.requires_grad]
+        params = grad_ready_order(model)
         if not params:
             raise RuntimeError("model has no trainable parameters")
         dev = params[0].device
@@ -71,7 +94,9 @@ class ParamArena:
         self.flat = torch.zeros(self.numel, dtype=torch.float32, device=dev)
         self.grad = torch.zeros(self.numel, dtype=torch.float32, device=dev)
         self.params, off = params, 0
+        self.offsets = {}
         for p, n in zip(params, sizes):
+            self.offsets[id(p)] = off
             view = self.flat[off:off + p.numel()].view(p.shape)
             view.copy_(p.data)
             p.data = view
@@ -175,7 +200,8 @@ class TrainEngine:
 
     def __init__(self, model, batch_size: int, lr: float = 3e-4, weight_decay: float = 0.0, betas=(0.9, 0.999),
                  eps: float = 1e-8, beta_kl: float = 1.0, use_graph: bool = True, process_group=None,
-                 bucket_bytes: int = 25 << 20, compute_l2: bool = True, wgrad_side_stream: bool = True):
+                 bucket_bytes: int = 12 << 20, compute_l2: bool = True, wgrad_side_stream: bool = True,
+                 overlap_allreduce: bool = True):
         _capi.device_check()
         self.model = model.train()
         self.batch_size = batch_size
@@ -205,6 +231,21 @@ class TrainEngine:
         self.packs = PackTable(model, getattr(model, "compute_dtype", torch.float32))
         self.gpacks = PackedGradArena(model)
         self.buckets = bucket_ranges(self.arena.numel, bucket_bytes)
+        # data parallel: bucket k of the gradient arena is all-reduced on the communication stream as soon as the backward has
+        # issued its last gradient (the arena is in gradient-ready order), overlapping NCCL with the rest of the backward
+        self.overlap = bool(overlap_allreduce) and self.world > 1 and os.environ.get("LVAE_OVERLAP_ALLREDUCE", "1") != "0"
+        self.comm_stream = torch.cuda.Stream(device=dev) if self.overlap else None
+        starts = [s for s, _ in self.buckets]
+        import bisect
+        self._bucket_of = {pid: bisect.bisect_right(starts, off) - 1 for pid, off in self.arena.offsets.items()}
+        self._gp_bucket = {}
+        for m in model.modules():
+            if isinstance(m, (Conv2d, ConvTranspose2d)) and hasattr(m.weight, "_lvae_gp_id"):
+                ks = [self._bucket_of[id(m.weight)]] + ([self._bucket_of[id(m.bias)]] if m.bias is not None and id(m.bias) in self._bucket_of else [])
+                self._gp_bucket[m.weight._lvae_gp_id] = min(ks)
+        self._ready_counts = None          # parameters per bucket that announce their gradient (calibrated on the first step)
+        self._flushed = set()
+        self._unpacked = set()
         self.x = torch.zeros((batch_size, model.color_ch) + tuple(model.img_shape), dtype=torch.float32, device=dev)
         self.use_graph = use_graph
         n_side = int(wgrad_side_stream) if not isinstance(wgrad_side_stream, bool) else (2 if wgrad_side_stream else 0)
@@ -293,25 +334,72 @@ class TrainEngine:
         recons = (-out["ll"]).mean()
         loss = recons + out["kl_loss"] * self._beta
         ops.set_side_stream(self.side_stream)          # (None: everything on this stream; also resets the wgrad log)
+        self._flushed, self._unpacked = set(), set()
+        record = None
+        if self.overlap:
+            if self._ready_counts is None:
+                record = set()                         # first step: learn which parameters announce their gradients
+                ops.grad_track_begin(self._bucket_of, [], self._flush_bucket, record)
+            else:
+                ops.grad_track_begin(self._bucket_of, self._ready_counts, self._flush_bucket)
         try:
             loss.backward()
-            # re-lay the packed weight gradients where their wgrads ran: each side stream unpacks its own convolutions
-            # (concurrently with the main stream's tail), then the streams join
-            for slot, ids in ops.packed_grad_log().items():
-                if slot >= 0 and self.side_stream is not None:
-                    with torch.cuda.stream(self.side_stream[slot]):
-                        self.gpacks.unpack(ids)
-                else:
-                    self.gpacks.unpack(ids)
+            ops.grad_track_end()
+            if record is not None:
+                counts = [0] * len(self.buckets)
+                for pid in record:
+                    counts[self._bucket_of[pid]] += 1
+                # a bucket that also holds gradients autograd accumulates by itself (no announcement) waits for the end
+                silent = [0] * len(self.buckets)
+                for pid, k in self._bucket_of.items():
+                    if pid not in record:
+                        silent[k] += 1
+                self._ready_counts = [c if (c > 0 and silent[k] == 0) else -1 for k, c in enumerate(counts)]
+            # re-lay the remaining packed weight gradients where their wgrads ran: each side stream unpacks its own
+            # convolutions (concurrently with the main stream's tail), then the streams join
+            self._unpack_ready(None)
+            if self.overlap:
+                for k in range(len(self.buckets)):
+                    self._flush_bucket(k)
+                torch.cuda.current_stream().wait_stream(self.comm_stream)
         finally:
+            ops.grad_track_end()
             ops.join_side_stream()
             ops.set_side_stream(None)
         elbo = (out["ll"] - out["kl_sep"]).mean()
         self.out = {"loss": loss.detach(), "elbo": elbo.detach(), "recons": recons.detach(), "kl": out["kl"].detach(),
                     "kl_avg_layerwise": out["kl_avg_layerwise"].detach()}
 
+    def _unpack_ready(self, bucket):
+        """Unpack the packed weight gradients issued so far (of `bucket`, or all that are left) on the streams that ran them."""
+        for slot, ids in ops.packed_grad_log().items():
+            todo = [i for i in ids if i not in self._unpacked and (bucket is None or self._gp_bucket.get(i) == bucket)]
+            if not todo:
+                continue
+            self._unpacked.update(todo)
+            if slot >= 0 and self.side_stream is not None:
+                with torch.cuda.stream(self.side_stream[slot]):
+                    self.gpacks.unpack(todo)
+            else:
+                self.gpacks.unpack(todo)
+
+    def _flush_bucket(self, k):
+        """All gradients of bucket k have been issued: unpack its packed weight gradients and all-reduce it on the
+        communication stream (behind everything issued so far on the main and side streams)."""
+        if k in self._flushed:
+            return
+        self._flushed.add(k)
+        self._unpack_ready(k)
+        cs = self.comm_stream
+        cs.wait_stream(torch.cuda.current_stream())
+        for st in (self.side_stream or []):
+            cs.wait_stream(st)
+        s, e = self.buckets[k]
+        with torch.cuda.stream(cs):
+            dist.all_reduce(self.arena.grad[s:e], op=dist.ReduceOp.SUM, group=self.pg)
+
     def _all_reduce(self):
-        if self.world > 1:
+        if self.world > 1 and not self.overlap:
             all_reduce_buckets(self.arena.grad, self.buckets, self.pg)
 
     def _optimizer(self):

@@ -165,7 +165,7 @@ def _take_kl_row(batch: int, device):
     """(kl, logp, logq) output vectors of one stochastic block: the next row of the pass's matrices, or fresh tensors."""
     r = _ctx.kl_rows
     if r is not None and _ctx.kl_cursor < r.shape[1] and r.shape[2] == batch and r.device == device:
-        i = _ctx.kl_cursor
+        i = r.shape[1] - 1 - _ctx.kl_cursor        # the top-down pass visits layers L-1 .. 0: row index = layer index
         _ctx.kl_cursor += 1
         return r[0, i], r[1, i], r[2, i]
     v = torch.empty((3, batch), dtype=torch.float32, device=device)
@@ -204,9 +204,50 @@ def grad_sink(param) -> Optional[torch.Tensor]:
     return getattr(param, "_lvae_grad_sink", None)
 
 
+# Gradient-readiness tracking for the data-parallel engine: the arena is cut into buckets in the order the backward pass
+# produces gradients; when the last parameter gradient of a bucket has been issued, the engine's flush callback unpacks the
+# bucket's packed weight gradients and starts its NCCL all-reduce on the communication stream while the backward goes on.
+_grad_track = {"on": False, "record": None, "bucket_of": {}, "remaining": [], "pending": [], "seen": set(), "flush": None}
+
+
+def grad_track_begin(bucket_of, counts, flush, record=None) -> None:
+    _grad_track.update(on=True, record=record, bucket_of=bucket_of, remaining=list(counts), pending=[], seen=set(), flush=flush)
+
+
+def grad_track_end() -> None:
+    """Flush whatever became ready at the last gradient site and stop tracking."""
+    t = _grad_track
+    if t["on"]:
+        for k in t["pending"]:
+            t["flush"](k)
+    t.update(on=False, record=None, pending=[], flush=None)
+
+
+def _grad_note(param) -> None:
+    t = _grad_track
+    if t["pending"]:                 # buckets completed by the PREVIOUS site: its launches have been issued by now
+        for k in t["pending"]:
+            t["flush"](k)
+        t["pending"] = []
+    pid = id(param)
+    if pid in t["seen"]:
+        return
+    t["seen"].add(pid)
+    if t["record"] is not None:
+        t["record"].add(pid)
+    k = t["bucket_of"].get(pid)
+    if k is None or not t["remaining"]:
+        return
+    t["remaining"][k] -= 1
+    if t["remaining"][k] == 0:
+        t["pending"].append(k)
+
+
 def _param_grad_buffer(param):
     sink = grad_sink(param)
     if sink is not None:
+        if _grad_track["on"]:
+            _grad_note(param)
         return sink, True
     return torch.zeros_like(param, dtype=torch.float32, memory_format=torch.contiguous_format), False
 
@@ -1046,11 +1087,10 @@ _stoch_ws = {}
 
 def _stoch_workspace(batch: int, device) -> torch.Tensor:
     """Zero-initialised scratch that lets lvae_stoch_fwd split one sample over several CTAs (stream-ordered reuse)."""
-    key = (device, torch.cuda.current_stream().cuda_stream)
+    key = (device, torch.cuda.current_stream().cuda_stream, batch)      # one buffer per batch size: its tickets stay zero
     ws = _stoch_ws.get(key)
-    need = int(_capi.lib().lvae_stoch_ws_bytes(batch))
-    if ws is None or ws.numel() < need:
-        ws = torch.zeros(need, dtype=torch.uint8, device=device)
+    if ws is None:
+        ws = torch.zeros(int(_capi.lib().lvae_stoch_ws_bytes(batch)), dtype=torch.uint8, device=device)
         _stoch_ws[key] = ws
     return ws
 
@@ -1141,6 +1181,7 @@ class KLBookFn(Function):
         in_place = (rows is not None and rows.shape[1] == L and rows.shape[2] == B and
                     all(kls[i].data_ptr() == rows[0, i].data_ptr() and lps[i].data_ptr() == rows[1, i].data_ptr() for i in range(L)))
         if in_place:
+            stats["kl_rows_in_place"] = stats.get("kl_rows_in_place", 0) + 1
             klm, lpm = rows[0], rows[1]
         else:
             klm = torch.stack([k.float() for k in kls]).contiguous()

@@ -35,11 +35,15 @@ def run_ours(model, cfg, meta, k=0):
 
 @pytest.mark.parametrize("name", CASES)
 def test_model_matches_golden(name):
+    from lvae_b200 import ops
     cfg, meta, g = load_golden(name)
     model = build(cfg, meta)
+    n_in_place = ops.stats.get("kl_rows_in_place", 0)
     with torch.set_grad_enabled(meta["training"]):
         out = run_ours(model, cfg, meta)
         loss = (-out["ll"]).mean() + out["kl_loss"]
+    # free bits / KL bookkeeping ran as one launch over the rows the stochastic kernels wrote (no gather)
+    assert ops.stats.get("kl_rows_in_place", 0) == n_in_place + 1
     assert rel_err(out["ll"], g["f64_ll"]) < 1e-4
     assert rel_err(out["kl_sep"], g["f64_kl_sep"]) < 1e-4
     assert rel_err(out["kl_avg_layerwise"], g["f64_kl_avg_layerwise"]) < 1e-4
@@ -119,6 +123,50 @@ def test_hooked_path_matches_fused_path():
             h.remove()
     assert len(calls) > 10
     assert rel_err(b["ll"], a["ll"]) < 1e-5 and rel_err(b["kl_sep"], a["kl_sep"]) < 1e-5
+
+
+@pytest.mark.parametrize("name", ["small_dmol_eval_b4", "mnist3_eval_b4"])
+def test_prior_pass_matches_oracle(name):
+    """The generative (prior) pass of models/lvae.py:229-315,351-362 against the oracle, on everything that is
+    deterministic given the noise: ancestral sampling with injected eps, all layers at their mode (`mode_layers`), and a
+    batch-constant top layer (`constant_layers`, lib/stochastic.py:71-73).  Compared on the likelihood parameters the
+    decoder produces (the pixel sample drawn from them is random and has its own distribution test)."""
+    import lvae_b200
+    cfg, meta, g = load_golden(name)
+    model = build(cfg, meta).eval()
+    P = O.make_params(cfg, meta["weight_seed"], torch.float64)
+    n, L = 5, len(cfg.z_dims)
+    gen = torch.Generator().manual_seed(77)
+    eps = [torch.randn(s, generator=gen, dtype=torch.float64) for s in reversed(O.latent_shapes(cfg, n))]
+
+    def ours(mode_layers, constant_layers, e):
+        with torch.no_grad(), lvae_b200.inject(eps=[t.float().cuda() for t in e] if e is not None else None):
+            out, data = model.topdown_pass(n_img_prior=n, mode_layers=mode_layers, constant_layers=constant_layers)
+            out = lvae_b200.ops.crop(out, cfg.img_shape)
+            _, lik = model.likelihood(out, None)
+        lp = lik["params"]
+        return (lp["all_params"] if isinstance(lp, dict) else lp), data
+
+    def oracle(mode_layers, constant_layers, e):
+        r = O._Run(cfg, {k: v.clone() for k, v in P.items()}, False, list(e) if e is not None else None, None, None)
+        with torch.no_grad():
+            out, data = O.topdown_pass(r, None, n, tuple(mode_layers), tuple(constant_layers))
+            out = O.crop_img(out, cfg.img_shape)
+            lp = O.likelihood(r, out, None)[1]["params"]
+        return (lp["all_params"] if isinstance(lp, dict) else lp), data
+
+    all_layers = list(range(L))
+    for ml, cl, e in ((all_layers, [], None),                       # every layer at the mode of its prior: no noise at all
+                      ([], [], eps),                                # ancestral sampling with the same eps
+                      ([0], [L - 1], [eps[0]] + eps[1:L - 1])):     # top layer constant over the batch, bottom layer at its mode
+        a, da = ours(ml, cl, e)
+        b, db = oracle(ml, cl, e)
+        assert rel_err(a, b) < 1e-4, (ml, cl)
+        for i in range(L):
+            assert rel_err(da["z"][i], db["z"][i]) < 1e-4, (ml, cl, i)
+    # the prior pass records log p(z) per layer and no KL
+    assert all(k is None for k in da["kl"])
+    assert rel_err(da["logprob_p"], db["logprob_p"]) < 1e-4
 
 
 def test_sample_prior_and_modes():
