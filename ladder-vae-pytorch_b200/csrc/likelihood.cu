@@ -104,7 +104,7 @@ LVAE_API int lvae_bernoulli_sample(const float* prob, float* out_nchw, int B, in
 // =========================================================================================
 // Discretized mixture of logistics, 10 components, 3 colour channels
 // =========================================================================================
-constexpr int DM_M = 10, DM_P = 100, DM_PITCH = 101, DM_TILE = 64;
+constexpr int DM_M = 10, DM_P = 100, DM_PITCH = 107, DM_TILE = 72;   // pitch % 32 = 11: the three pixel rows of a warp hit disjoint banks
 #define LOG_127_5 4.8481163519437300f
 
 // Single-MUFU exponentials / logarithms (ex2.approx, lg2.approx; relative error 2^-22) instead of the ~10-25-instruction
@@ -137,8 +137,12 @@ __device__ __forceinline__ float dmol_term(float x, float cen, float ls, float& 
     if (want_grad) { float s = dm_sigmoid(min_in); d_cen = -inv * s; d_ls = min_in * s; }
     return -dm_softplus(min_in);
   }
-  float cp = dm_sigmoid(plus_in), cm = dm_sigmoid(min_in);
-  float delta = cp - cm;
+  // both logistic CDFs from ONE reciprocal: cp = 1 / (1 + e_p), cm = 1 / (1 + e_m), r = 1 / ((1 + e_p)(1 + e_m)).  The exponents
+  // are clamped to +-30 (sigmoid is 0 / 1 to fp32 resolution beyond that) so that the product cannot overflow.
+  const float e_p = dm_exp(-fminf(fmaxf(plus_in, -30.f), 30.f)), e_m = dm_exp(-fminf(fmaxf(min_in, -30.f), 30.f));
+  const float r = __fdividef(1.f, (1.f + e_p) * (1.f + e_m));
+  const float cp = r * (1.f + e_m), cm = r * (1.f + e_p);
+  const float delta = r * (e_m - e_p);
   if (delta > 1e-5f) {
     if (want_grad) {
       float dpv = cp * (1.f - cp), dmv = cm * (1.f - cm);
@@ -154,13 +158,15 @@ __device__ __forceinline__ float dmol_term(float x, float cen, float ls, float& 
 }
 
 // BWD = false: ll[b] += sum over this CTA's pixels.  BWD = true: dl = g_ll[b] * d ll / d l.
-// A CTA stages DM_TILE pixels x 100 parameters in shared memory (coalesced 400-byte rows), then SIXTEEN lanes work on one
-// pixel, lane m < 10 owning mixture component m: its three per-colour log-probabilities (and, backward, its ten parameter
-// gradients, written back over the staged parameters) are independent of the other components; the two logsumexps over
-// the components are 4-step butterflies inside the 16-lane group.  One thread per pixel left the MUFU-heavy per-component
-// math (30 logistic terms) in one long dependent chain per thread: 265 us for the CIFAR batch-256 backward, 12 % of the
-// HBM roofline; this layout runs the same arithmetic with 10x the parallelism.
-constexpr int DM_THREADS = 256, DM_GROUP = 16;
+// A CTA stages DM_TILE pixels x 100 parameters in shared memory (coalesced 400-byte rows), then TEN lanes work on one
+// pixel -- a warp covers three pixels, lanes 30 and 31 idle along -- lane m owning mixture component m: its three per-colour
+// log-probabilities (and, backward, its ten parameter gradients, written back over the staged parameters) are independent
+// of the other components; the two logsumexps over the components are guarded 4-step shuffle trees inside the 10-lane
+// segment plus one broadcast.  History: one thread per pixel left the MUFU-heavy per-component math (30 logistic terms) in
+// one long dependent chain per thread (265 us for the CIFAR batch-256 backward); 16 lanes per pixel with 6 of them idle ran
+// the same arithmetic with 10x the parallelism but wasted 37 % of the issue slots of an issue-bound kernel (76 us); this
+// layout wastes 6 %.
+constexpr int DM_THREADS = 256, DM_SEG = 10, DM_PIX_PER_PASS = (DM_THREADS / 32) * 3;
 template <bool BWD>
 __global__ void __launch_bounds__(DM_THREADS) dmol_kernel(const float* __restrict__ l, const float* __restrict__ x,
                                                           float* __restrict__ ll, const float* __restrict__ g_ll,
@@ -189,23 +195,34 @@ __global__ void __launch_bounds__(DM_THREADS) dmol_kernel(const float* __restric
     }
   }
   __syncthreads();
-  const int m = threadIdx.x & (DM_GROUP - 1);              // mixture component of this lane (lanes 10..15 idle along)
-  const int slot = threadIdx.x / DM_GROUP;                 // pixel slot within a pass
-  const bool comp = m < DM_M;
-  const int mm = comp ? m : 0;
+  const int lane = threadIdx.x & 31;
+  const int seg = lane / DM_SEG;                            // pixel of this lane within its warp (3 = the two idle lanes)
+  const int m = lane - seg * DM_SEG;                        // mixture component of this lane
+  const int seg_base = seg * DM_SEG;
+  const int slot = (threadIdx.x >> 5) * 3 + min(seg, 2);    // pixel slot within a pass
+  const bool comp = seg < 3;
+  const int mm = m;
   float pix_ll = 0.f;
-  auto gmax = [](float v) {
+  // reductions over the 10 lanes of a segment: guarded shuffle-down tree (offsets 8, 4, 2, 1 leave the result in the
+  // segment's first lane), then a broadcast from that lane.  All 32 lanes take part in every shuffle.
+  auto gmax = [&](float v) {
 #pragma unroll
-    for (int o = DM_GROUP / 2; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o, DM_GROUP));
-    return v;
+    for (int o = 8; o > 0; o >>= 1) {
+      const float t = __shfl_down_sync(0xffffffffu, v, o);
+      if (m + o < DM_SEG) v = fmaxf(v, t);
+    }
+    return __shfl_sync(0xffffffffu, v, seg_base);
   };
-  auto gsum = [](float v) {
+  auto gsum = [&](float v) {
 #pragma unroll
-    for (int o = DM_GROUP / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o, DM_GROUP);
-    return v;
+    for (int o = 8; o > 0; o >>= 1) {
+      const float t = __shfl_down_sync(0xffffffffu, v, o);
+      if (m + o < DM_SEG) v += t;
+    }
+    return __shfl_sync(0xffffffffu, v, seg_base);
   };
-  for (int r = slot; r < ((npix + DM_THREADS / DM_GROUP - 1) / (DM_THREADS / DM_GROUP)) * (DM_THREADS / DM_GROUP); r += DM_THREADS / DM_GROUP) {
-    const bool live = r < npix;                             // whole groups stay in the loop together (shuffles)
+  for (int r = slot; r < ((npix + DM_PIX_PER_PASS - 1) / DM_PIX_PER_PASS) * DM_PIX_PER_PASS; r += DM_PIX_PER_PASS) {
+    const bool live = comp && r < npix;                     // whole warps stay in the loop together (shuffles)
     float* L = sm + (live ? r : 0) * DM_PITCH;
     const int pix = pix0 + (live ? r : 0);
     float xc[3];

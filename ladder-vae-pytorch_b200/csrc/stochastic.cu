@@ -67,8 +67,10 @@ constexpr int ST_THREADS = 256;
 // TRAIN = the training / IW-evaluation case (q present, Philox noise, no forced latent, no mode): a template flag so that
 // the hot instantiation carries none of the other cases' branches and fits 64 registers (4 CTAs per SM; the generic one
 // needed 112 and ran at a quarter of the occupancy).
-template <int VEC, bool TRAIN>
+// ZC = 32 (the reference's z_dims, README.md:175-196) makes the lane-group geometry compile-time constants (0 = generic).
+template <int VEC, bool TRAIN, int ZC>
 __global__ void __launch_bounds__(ST_THREADS, TRAIN ? 4 : 2) stoch_fwd_kernel(StochArgs a) {
+  if (ZC) a.Z = ZC;
   pdl_wait();
   pdl_launch();
   __shared__ float red[3][ST_THREADS / 32];
@@ -77,8 +79,9 @@ __global__ void __launch_bounds__(ST_THREADS, TRAIN ? 4 : 2) stoch_fwd_kernel(St
   const int b = blockIdx.y;
   const int ZV = a.Z / VEC;
   int G = 1;
-  while (G < ZV && G < 32) G <<= 1;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+  if (ZC) G = ZC / VEC;                   // 8 lanes per pixel for Z = 32
+  else while (G < ZV && G < 32) G <<= 1;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = ST_THREADS >> 5;
   const int ppw = 32 / G;                 // pixels per warp per iteration
   const int gl = lane % G, gp = lane / G;
   const bool sampled = !a.eps && !a.forced && !a.use_mode;
@@ -243,9 +246,10 @@ LVAE_API int lvae_stoch_fwd(const float* q, const float* p, int p_broadcast, con
   }
   dim3 grid(a.nchunk, B);
   const bool train = q && !eps && !forced && !use_mode;
-  if (vec == 4 && train) lvae_launch(stoch_fwd_kernel<4, true>, grid, ST_THREADS, 0, stream, a);
-  else if (vec == 4) lvae_launch(stoch_fwd_kernel<4, false>, grid, ST_THREADS, 0, stream, a);
-  else lvae_launch(stoch_fwd_kernel<1, false>, grid, ST_THREADS, 0, stream, a);
+  if (vec == 4 && train && Z == 32) lvae_launch(stoch_fwd_kernel<4, true, 32>, grid, ST_THREADS, 0, stream, a);
+  else if (vec == 4 && train) lvae_launch(stoch_fwd_kernel<4, true, 0>, grid, ST_THREADS, 0, stream, a);
+  else if (vec == 4) lvae_launch(stoch_fwd_kernel<4, false, 0>, grid, ST_THREADS, 0, stream, a);
+  else lvae_launch(stoch_fwd_kernel<1, false, 0>, grid, ST_THREADS, 0, stream, a);
   LVAE_COUNT_LAUNCH();
   LVAE_CHECK_LAUNCH("stoch_fwd");
   return LVAE_OK;

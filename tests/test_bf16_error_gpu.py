@@ -78,11 +78,14 @@ def test_bf16_training_step_error_at_the_bench_shape():
             "(%s), median %.5f; per-tensor rel L2 max %.3e (%s), median %.3e; %d tensors"
             % (a["loss"], b["loss"], nats, e_loss, e_ll, e_ll_mean, e_kl, e_kll, cos_all, cos[0][0], cos[0][1], cos[len(cos) // 2][0],
                l2[0][0], l2[0][1], l2[len(l2) // 2][0], len(cos)))
-    # bounds: ~3x the measured level (profiles/bf16_error_r02.txt)
-    assert e_loss < 3e-3 and e_ll_mean < 3e-3
-    assert e_ll < 1e-2 and e_kl < 3e-2
-    assert cos_all > 0.995
-    assert cos[len(cos) // 2][0] > 0.995
+    # bounds: ~3x the measured level (profiles/bf16_error_r02.txt: loss 8.0e-5, ll mean 2.2e-5, ll per image 6.8e-5, kl_sep
+    # 9.4e-4, kl per layer 3.3e-4; cosine whole vector 0.999993, per tensor min 0.99966 / median 0.99999; rel L2 max 2.6e-2 /
+    # median 4.8e-3)
+    assert e_loss < 2.5e-4 and e_ll_mean < 7e-5 and e_ll < 2e-4
+    assert e_kl < 3e-3 and e_kll < 1e-3
+    assert cos_all > 0.99998
+    assert cos[0][0] > 0.999 and cos[len(cos) // 2][0] > 0.99997
+    assert l2[0][0] < 8e-2 and l2[len(l2) // 2][0] < 1.5e-2
 
 
 def test_bf16_iw_bound_error_in_nats():
@@ -107,4 +110,5 @@ def test_bf16_iw_bound_error_in_nats():
             "per image |diff| mean %.4f max %.4f nats" % (float(bounds[torch.float32].mean()), float(bounds[torch.bfloat16].mean()),
                                                          mean_diff, float(d.mean()), float(d.max())))
     assert torch.isfinite(bounds[torch.bfloat16]).all()
-    assert mean_diff < 1.0 and float(d.max()) < 5.0
+    # measured: 0.275 nats on the mean of a -6288.65-nat bound (4.4e-5 relative), per image 1.01 nats mean / 3.46 max
+    assert mean_diff < 0.9 and float(d.mean()) < 3.0 and float(d.max()) < 10.0

@@ -185,6 +185,23 @@ def test_sample_prior_and_modes():
         model.top_down_layers[-1](torch.zeros(1, 16, 2, 2, device="cuda"))
 
 
+# (ll, kl_sep, loss, gradient norms): ~3x the levels measured on the B200 (profiles/bf16_error_r02.txt); tiny batches make
+# the train-mode BatchNorm statistics, and with them the bf16 rounding, noisier than at the bench batch of 256
+BF16_GOLDEN_TOL = {"mnist3_train_b4": (2e-2, 2e-2, 2e-2, 5e-2), "cifar15_train_b2": (2e-2, 2e-2, 2e-2, 5e-2),
+                   "mnist12_eval_b2": (2e-2, 2e-2, 2e-2, 5e-2)}
+
+
+def _record_bf16(line):
+    import os
+    d = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
+    try:
+        os.makedirs(d, exist_ok=True)
+        with open(os.path.join(d, "measured_bf16_golden.txt"), "a") as fh:
+            fh.write(line + "\n")
+    except OSError:
+        pass
+
+
 @pytest.mark.parametrize("name", ["mnist3_train_b4", "cifar15_train_b2", "mnist12_eval_b2"])
 def test_bf16_tensor_core_pipeline_close_to_golden(name):
     """bf16 activations + tcgen05 convolutions (fp32 accumulation; stochastic and likelihood
@@ -199,9 +216,8 @@ def test_bf16_tensor_core_pipeline_close_to_golden(name):
         out = run_ours(model, cfg, meta)
         loss = (-out["ll"]).mean() + out["kl_loss"]
     assert out["ll"].dtype == torch.float32
-    assert rel_err(out["ll"], g["f64_ll"]) < 2e-2
-    assert rel_err(out["kl_sep"], g["f64_kl_sep"]) < 2e-2
-    assert rel_err(loss, g["f64_loss"]) < 2e-2
+    e_ll, e_kl, e_loss = rel_err(out["ll"], g["f64_ll"]), rel_err(out["kl_sep"], g["f64_kl_sep"]), rel_err(loss, g["f64_loss"])
+    e_g = 0.0
     if meta["training"]:
         loss.backward()
         names = [str(n) for n in g["f64_grad_names"]]
@@ -209,7 +225,11 @@ def test_bf16_tensor_core_pipeline_close_to_golden(name):
         ours = np.array([float(params[n].grad.double().pow(2).sum().sqrt()) if params[n].grad is not None else 0.0
                          for n in names])
         ref = g["f64_grad_l2"]
-        assert np.abs(ours - ref).max() < 5e-2 * ref.max(), names[int(np.abs(ours - ref).argmax())]
+        e_g = float(np.abs(ours - ref).max() / ref.max())
+    _record_bf16("%s (batch %d, vs the reference's fp64 golden): ll rel(max) %.2e, kl_sep rel(max) %.2e, loss rel %.2e, "
+                 "gradient norms rel(max) %.2e" % (name, meta["batch"], e_ll, e_kl, e_loss, e_g))
+    lim = BF16_GOLDEN_TOL[name]
+    assert e_ll < lim[0] and e_kl < lim[1] and e_loss < lim[2] and e_g < lim[3], (e_ll, e_kl, e_loss, e_g)
 
 
 def test_whole_block_schedule_matches_op_by_op():
