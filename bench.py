@@ -393,10 +393,11 @@ def run_dp_check(cx, engine):
     summed in fp64 here)."""
     torch, dist = cx.torch, cx.dist
     flat = engine.arena.flat
-    sums = torch.stack([flat.double().sum(), flat.double().abs().sum(), flat.view(torch.int32).long().sum().double()])
-    allsums = torch.empty((cx.world, 3), dtype=torch.float64, device="cuda")
-    dist.all_gather_into_tensor(allsums, sums)
-    param_diff = float((allsums - allsums[0:1]).abs().max())
+    ref0 = flat.clone()
+    dist.broadcast(ref0, 0)                                   # rank 0's parameters
+    d = torch.stack([(flat - ref0).abs().max().double(), (flat.view(torch.int32) != ref0.view(torch.int32)).sum().double()])
+    dist.all_reduce(d, op=dist.ReduceOp.MAX)
+    param_diff, param_bits = float(d[0]), int(d[1])
     # gradient arena: the engine's (overlapped, bucketed) NCCL reduction against a manual fp64 sum of the per-rank arenas.
     # Pass 1 with the reduction switched off gives this rank's own gradients; pass 2 replays the same step (same Philox
     # state) through the engine's normal path.
@@ -419,9 +420,15 @@ def run_dp_check(cx, engine):
     torch.cuda.synchronize()
     red = engine.arena.grad.double()
     gdiff = float((red - manual).abs().max() / manual.abs().max())
+    gdiff_l2 = float((red - manual).norm() / manual.norm())
+    # per bucket, against the bucket's own largest gradient (a bucket reduced too early shows up here even if its
+    # gradients are small next to the global maximum)
+    gdiff_bucket = max(float((red[s:e] - manual[s:e]).abs().max() / manual[s:e].abs().max().clamp_min(1e-30)) for s, e in engine.buckets)
     # how different the per-rank gradients were (a check that the ranks really saw different data / noise)
     spread = float((chunk[0].double() - manual / cx.world).abs().max() / manual.abs().max() * cx.world)
-    return {"param_checksum_max_abs_diff_across_ranks": param_diff, "grad_allreduce_vs_manual_sum_rel": gdiff,
+    return {"param_max_abs_diff_vs_rank0": param_diff, "param_elements_not_bit_identical": param_bits,
+            "grad_allreduce_vs_manual_sum_rel": gdiff, "grad_allreduce_vs_manual_sum_rel_l2": gdiff_l2,
+            "grad_allreduce_vs_manual_sum_rel_worst_bucket": gdiff_bucket,
             "per_rank_grad_spread_rel": spread, "buckets": len(engine.buckets), "arena_mb": n * 4 / 2 ** 20,
             "allreduce_overlapped_with_backward": bool(engine.overlap),
             "buckets_flushed_early": [k for k, c in enumerate(engine._ready_counts or []) if c > 0]}

@@ -223,12 +223,20 @@ def grad_track_end() -> None:
     t.update(on=False, record=None, pending=[], flush=None)
 
 
-def _grad_note(param) -> None:
+def grad_site() -> None:
+    """Called at the top of every function that produces parameter gradients (conv / BatchNorm / head backward), before it
+    announces its own parameters: everything the earlier sites announced has been launched by now, so the buckets they
+    completed can go out.  (A site announces weight AND bias before it launches: flushing from inside the announcement
+    would reduce a bucket ahead of the kernel that writes its last gradient.)"""
     t = _grad_track
-    if t["pending"]:                 # buckets completed by the PREVIOUS site: its launches have been issued by now
+    if t["on"] and t["pending"]:
         for k in t["pending"]:
             t["flush"](k)
         t["pending"] = []
+
+
+def _grad_note(param) -> None:
+    t = _grad_track
     pid = id(param)
     if pid in t["seen"]:
         return
@@ -555,6 +563,7 @@ def conv_backward_raw(spec: ConvSpec, xn, x2n, weight, bias, out_scale, gyn, nee
     gradient wrt the masked output; pass None when gyn is already the gradient wrt the raw conv output).
     ``dx_scale`` (B, Cin) is folded into the dgrad epilogue: the returned dx is multiplied by it (the mask of the
     conv that produced xn).  Returns (gx, gx2, gw, gb); gw / gb are None when accumulated into a gradient sink."""
+    grad_site()
     if gyn.dtype != xn.dtype:
         gyn = gyn.to(xn.dtype)
     B, Hi, Wi, C1 = xn.shape
@@ -737,6 +746,7 @@ class BnActFn(Function):
 
     @staticmethod
     def backward(ctx, gy):
+        grad_site()
         xn, mean, rstd, gamma, beta = ctx.saved_tensors
         gyn = nhwc(gy)
         if gyn.dtype != xn.dtype:
@@ -933,6 +943,7 @@ class GatedBlockFn(Function):
         fused2 = conv_backward_raw.last_fused
 
         def bn_bwd(dy, xin, bn, acc, save, gamma, beta, post_scale, add, skip_reduce):
+            grad_site()
             dgam, gsunk = _param_grad_buffer(gamma)
             dbet, bsunk = _param_grad_buffer(beta)
             dxo = torch.empty_like(xin)
@@ -1336,6 +1347,7 @@ class DmolHeadFn(Function):
 
     @staticmethod
     def backward(ctx, g_ll, _g_l):
+        grad_site()
         hn, l, xc, weight, bias = ctx.saved_tensors
         spec = ctx.spec
         if g_ll is None:

@@ -93,3 +93,102 @@ def test_shard_samples_partition():
                 assert s == pos
                 pos += c
             assert max(c for _, c in parts) - min(c for _, c in parts) <= 1
+
+
+def _worker_overlap(rank, world, port, tmp):
+    """The overlapped reduction's host logic end to end on gloo: parameters announce their gradients in backward order
+    (ops._param_grad_buffer -> ops._grad_note), each bucket is all-reduced by the flush callback once its last gradient
+    has been announced AND the next gradient site has begun (ops.grad_site: the announcing site's own launches are then
+    behind it), the rest at the end -- and the arena ends up as the sum over ranks."""
+    import sys
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import bisect
+    import lvae_b200  # noqa: F401
+    from lvae_b200 import ops
+    from lvae_b200.engine import bucket_ranges
+    g = torch.Generator().manual_seed(7)
+    sizes = [int(s) for s in torch.randint(1, 4000, (60,), generator=g)]
+    params = [torch.nn.Parameter(torch.zeros(s)) for s in sizes]          # arena (= gradient-ready) order
+    offs, off = {}, 0
+    for p_, s in zip(params, sizes):
+        offs[id(p_)] = off
+        off += (s + 3) // 4 * 4
+    grad = torch.zeros(off)
+    buckets = bucket_ranges(off, bucket_bytes=32 * 1024)
+    assert len(buckets) >= 4
+    starts = [s for s, _ in buckets]
+    bucket_of = {pid: bisect.bisect_right(starts, o) - 1 for pid, o in offs.items()}
+    silent = {id(params[17])}                                             # one gradient autograd accumulates by itself
+    counts = [0] * len(buckets)
+    for p_ in params:
+        if id(p_) not in silent:
+            counts[bucket_of[id(p_)]] += 1
+    kq = bucket_of[id(params[17])]
+    counts[kq] = -1                                                       # its bucket waits for the end
+    flushed, written = [], set()
+
+    def flush(k):
+        s, e = buckets[k]
+        # everything of bucket k must have been written by now (except the silent one, which only the final flush covers)
+        for p_ in params:
+            if bucket_of[id(p_)] == k and id(p_) not in silent:
+                assert id(p_) in written, "bucket %d flushed before all of its gradients were issued" % k
+        flushed.append(k)
+        dist.all_reduce(grad[s:e])
+
+    ops.grad_track_begin(bucket_of, counts, flush)
+    gr = torch.Generator().manual_seed(1000 + rank)
+    local = torch.zeros(off)
+    for p_ in params:
+        p_._lvae_grad_sink = grad[offs[id(p_)]:offs[id(p_)] + p_.numel()]
+        v = torch.randn(p_.numel(), generator=gr)
+        local[offs[id(p_)]:offs[id(p_)] + p_.numel()] = v
+        if id(p_) in silent:
+            p_._lvae_grad_sink.copy_(v)                                   # written without an announcement
+            continue
+        # a gradient site: flush what earlier sites completed, announce (twice, like weight + bias of one conv: the second
+        # announcement must not trigger the flush of a bucket this very site completes), THEN "launch" the gradient kernel
+        ops.grad_site()
+        sink, sunk = ops._param_grad_buffer(p_)
+        sink2, _ = ops._param_grad_buffer(p_)
+        assert sunk and sink2 is sink
+        sink.copy_(v)
+        written.add(id(p_))
+    early = list(flushed)
+    ops.grad_track_end()
+    for k in range(len(buckets)):
+        if k not in flushed:
+            flush(k)
+    assert early == sorted(early) and kq not in early and len(early) >= len(buckets) - 2
+    assert sorted(flushed) == list(range(len(buckets)))
+    both = [torch.zeros_like(local) for _ in range(world)]
+    dist.all_gather(both, local)
+    assert torch.allclose(grad, sum(both), atol=1e-6)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_overlapped_bucket_flush_two_rank_gloo(tmp_path):
+    mp.spawn(_worker_overlap, args=(2, _free_port(), str(tmp_path)), nprocs=2, join=True)
+
+
+def test_grad_ready_order_and_iw_shard_offsets():
+    import sys
+    sys.path.insert(0, ROOT)
+    import lvae_b200
+    from lvae_b200.configs import baseline_config
+    from lvae_b200.engine import grad_ready_order
+    m = lvae_b200.LadderVAE(**baseline_config("mnist3").kwargs())
+    names = {id(p): n for n, p in m.named_parameters()}
+    order = [names[id(p)] for p in grad_ready_order(m)]
+    assert sorted(order) == sorted(names.values()) and len(set(order)) == len(order)
+    assert order[0].startswith("likelihood.") and order[-1] == "first_bottom_up.0.weight"
+    first = {g: min(i for i, n in enumerate(order) if n.startswith(g)) for g in
+             ("likelihood.", "final_top_down.", "top_down_layers.0.", "top_down_layers.2.", "bottom_up_layers.2.",
+              "bottom_up_layers.0.", "first_bottom_up.")}
+    seq = [first[g] for g in ("likelihood.", "final_top_down.", "top_down_layers.0.", "top_down_layers.2.",
+                              "bottom_up_layers.2.", "bottom_up_layers.0.", "first_bottom_up.")]
+    assert seq == sorted(seq)                       # the order LadderVAE's backward finishes them in
