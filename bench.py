@@ -398,6 +398,17 @@ def run_dp_check(cx, engine):
     d = torch.stack([(flat - ref0).abs().max().double(), (flat.view(torch.int32) != ref0.view(torch.int32)).sum().double()])
     dist.all_reduce(d, op=dist.ReduceOp.MAX)
     param_diff, param_bits = float(d[0]), int(d[1])
+    where = []
+    if param_bits and cx.rank == cx.world - 1:                # which tensors (diagnostic; printed to stderr by the last rank)
+        names = {id(p): n for n, p in engine.model.named_parameters()}
+        bad = (flat.view(torch.int32) != ref0.view(torch.int32))
+        for p in engine.arena.params:
+            off = engine.arena.offsets[id(p)]
+            c = int(bad[off:off + p.numel()].sum())
+            if c:
+                where.append((c, p.numel(), names[id(p)], engine._bucket_of[id(p)]))
+        where.sort(reverse=True)
+        sys.stderr.write("dp_check: %d tensors with elements that differ from rank 0; largest: %s\n" % (len(where), where[:12]))
     # gradient arena: the engine's (overlapped, bucketed) NCCL reduction against a manual fp64 sum of the per-rank arenas.
     # Pass 1 with the reduction switched off gives this rank's own gradients; pass 2 replays the same step (same Philox
     # state) through the engine's normal path.

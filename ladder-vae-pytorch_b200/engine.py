@@ -41,6 +41,18 @@ def bucket_ranges(numel: int, bucket_bytes: int = 25 << 20, elem_bytes: int = 4)
     return [(s, min(numel, s + per)) for s in range(0, numel, per)]
 
 
+def bucket_ranges_aligned(starts, numel: int, bucket_bytes: int = 25 << 20, elem_bytes: int = 4):
+    """Like bucket_ranges, but every cut falls on a tensor boundary (`starts` = sorted start offsets of the tensors in the
+    arena): a bucket is reduced as soon as its last gradient is out, so no tensor may straddle two buckets."""
+    per = max(1, bucket_bytes // elem_bytes)
+    cuts, begin = [0], 0
+    for s in list(starts)[1:]:
+        if s - begin >= per:
+            cuts.append(s)
+            begin = s
+    return [(a, b) for a, b in zip(cuts, cuts[1:] + [numel])]
+
+
 def all_reduce_buckets(flat: torch.Tensor, buckets, group=None) -> None:
     """Sum-all-reduce a flat gradient arena bucket by bucket (NCCL on GPUs; device agnostic)."""
     for s, e in buckets:
@@ -230,7 +242,7 @@ class TrainEngine:
         self.compute_l2 = compute_l2
         self.packs = PackTable(model, getattr(model, "compute_dtype", torch.float32))
         self.gpacks = PackedGradArena(model)
-        self.buckets = bucket_ranges(self.arena.numel, bucket_bytes)
+        self.buckets = bucket_ranges_aligned(sorted(self.arena.offsets.values()), self.arena.numel, bucket_bytes)
         # data parallel: bucket k of the gradient arena is all-reduced on the communication stream as soon as the backward has
         # issued its last gradient (the arena is in gradient-ready order), overlapping NCCL with the rest of the backward
         self.overlap = bool(overlap_allreduce) and self.world > 1 and os.environ.get("LVAE_OVERLAP_ALLREDUCE", "1") != "0"

@@ -108,7 +108,7 @@ def _worker_overlap(rank, world, port, tmp):
     import bisect
     import lvae_b200  # noqa: F401
     from lvae_b200 import ops
-    from lvae_b200.engine import bucket_ranges
+    from lvae_b200.engine import bucket_ranges_aligned
     g = torch.Generator().manual_seed(7)
     sizes = [int(s) for s in torch.randint(1, 4000, (60,), generator=g)]
     params = [torch.nn.Parameter(torch.zeros(s)) for s in sizes]          # arena (= gradient-ready) order
@@ -117,8 +117,10 @@ def _worker_overlap(rank, world, port, tmp):
         offs[id(p_)] = off
         off += (s + 3) // 4 * 4
     grad = torch.zeros(off)
-    buckets = bucket_ranges(off, bucket_bytes=32 * 1024)
-    assert len(buckets) >= 4
+    buckets = bucket_ranges_aligned(sorted(offs.values()), off, bucket_bytes=32 * 1024)
+    assert len(buckets) >= 4 and buckets[0][0] == 0 and buckets[-1][1] == off
+    assert all(a[1] == b[0] for a, b in zip(buckets, buckets[1:]))
+    assert all(s in set(offs.values()) for s, _ in buckets)        # every cut on a tensor boundary: no tensor straddles two buckets
     starts = [s for s, _ in buckets]
     bucket_of = {pid: bisect.bisect_right(starts, o) - 1 for pid, o in offs.items()}
     silent = {id(params[17])}                                             # one gradient autograd accumulates by itself
