@@ -101,30 +101,7 @@ typedef struct {
   void* gate_out;
   int gate_act;
   int gate_skip_h;      /* eval mode: do not store h (y may then be NULL): nothing runs backward */
-  /* BatchNorm APPLY behind a grid barrier, for launches with one tile per CTA (lvae_conv2d_tc_one_tile_per_cta: the <= 8x8
-   * rungs at batch 256), lib/nn.py:78-89: post_counter = device uint32, zero at launch.
-   *   with stats_acc: once the statistics of y are complete the staged tile is normalised + activated and stored a second
-   *     time: post_out (B,H,W,64) bf16 = act(bn(y)) with the consumer BatchNorm's post_gamma / post_beta; post_save
-   *     [mean | rstd] is written for the backward, the running statistics / num_batches_tracked are updated;
-   *   with bnb_acc: once the BatchNorm-backward sums are complete, y receives the gradient wrt the BatchNorm INPUT,
-   *     times post_scale (B,64) (Dropout2d mask of the conv that produced it) plus post_add (M,64) bf16 (residual
-   *     gradient); post_dgamma / post_dbeta += the parameter gradients. */
-  unsigned int* post_counter;
-  void* post_out;
-  const float* post_gamma;
-  const float* post_beta;
-  float* post_save;
-  float* post_running_mean;
-  float* post_running_var;
-  long long* post_nbt;
-  float post_momentum, post_eps;
-  int post_act;
-  float* post_dgamma;
-  float* post_dbeta;
-  const float* post_scale;
-  const void* post_add;
 } LvaeConvFuse;
-int lvae_conv2d_tc_one_tile_per_cta(int B, int H, int W);
 int lvae_conv2d_tc_ex(const void* x, const void* x2, const void* wp, const float* bias, const float* out_scale,
                       const void* res, void* y, void* y2, int nsplit, int B, int H, int W, int Cin, int N, int ksize,
                       int flip, int out_f32, const LvaeConvFuse* fuse, lvae_stream_t stream);

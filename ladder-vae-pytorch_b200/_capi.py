@@ -77,7 +77,6 @@ _SPECIAL = {
     "lvae_wgrad_tc_packed_size": ([I, I, I], c_longlong),
     "lvae_wgrad_unpack_desc_size": ([], c_int),
     "lvae_stoch_ws_bytes": ([I], c_longlong),
-    "lvae_conv2d_tc_one_tile_per_cta": ([I, I, I], c_int),
 }
 
 
@@ -85,11 +84,7 @@ class ConvFuse(ctypes.Structure):
     """LvaeConvFuse of include/lvae_b200.h."""
     _fields_ = [("stats_acc", c_void_p), ("bnb_x", c_void_p), ("bnb_save", c_void_p), ("bnb_gamma", c_void_p),
                 ("bnb_beta", c_void_p), ("bnb_acc", c_void_p), ("bnb_act", c_int), ("gate_x", c_void_p),
-                ("gate_out", c_void_p), ("gate_act", c_int), ("gate_skip_h", c_int),
-                ("post_counter", c_void_p), ("post_out", c_void_p), ("post_gamma", c_void_p), ("post_beta", c_void_p),
-                ("post_save", c_void_p), ("post_running_mean", c_void_p), ("post_running_var", c_void_p), ("post_nbt", c_void_p),
-                ("post_momentum", c_float), ("post_eps", c_float), ("post_act", c_int), ("post_dgamma", c_void_p),
-                ("post_dbeta", c_void_p), ("post_scale", c_void_p), ("post_add", c_void_p)]
+                ("gate_out", c_void_p), ("gate_act", c_int), ("gate_skip_h", c_int)]
 
 
 def exported_symbols():

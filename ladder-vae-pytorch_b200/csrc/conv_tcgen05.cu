@@ -58,23 +58,6 @@ struct TcParams {
   int gate_act;
   int gate_skip_h;          // eval mode: h = [a | g] is only staged for the gate pass, never stored (nothing runs backward)
   int tma_store;            // bf16 output, N % 64 == 0, no residual: epilogue stages the tile in smem and stores it with TMA
-  // BatchNorm apply fused behind a grid barrier (launches with ONE tile per CTA, i.e. n_tiles <= #SMs: the <= 8x8 rungs at
-  // batch 256).  FUSE == 1: after the statistics of the conv output are complete, the staged tile is normalised + activated in
-  // place and stored a second time (post_out = act(bn(y)): the next conv's input; y itself is still stored for the backward).
-  // FUSE == 2: after the BatchNorm-backward sums are complete, the staged data-gradient tile is turned into the gradient wrt
-  // the BatchNorm input (times the Dropout2d mask of the conv that produced it, plus the residual gradient) and ONLY that is
-  // stored.  Removes one elementwise launch (and one pass over the tensor) per BatchNorm at the launch-bound rungs.
-  int post;                 // 0 off
-  unsigned int* post_counter;   // grid barrier ticket, zero at launch
-  long long post_count;     // P = B*H*W (elements per channel)
-  const float* post_gamma; const float* post_beta;     // FUSE == 1: the consumer BatchNorm's parameters
-  float* post_save;         // FUSE == 1: [mean | rstd] written for the backward
-  float* post_running_mean; float* post_running_var; long long* post_nbt;
-  float post_momentum, post_eps;
-  int post_act;
-  float* post_dgamma; float* post_dbeta;               // FUSE == 2: += parameter gradients
-  const float* post_scale;  // FUSE == 2: (B,64) Dropout2d mask multiplied into dx, or null
-  const __nv_bfloat16* post_add;   // FUSE == 2: (M,64) residual gradient added to dx, or null
   long long* dbg;           // optional per-tile clock64 trace of CTA 0 (profiling aid, normally null)
   int8_t dx[TC_MAX_KB], dy[TC_MAX_KB], src[TC_MAX_KB], coff[TC_MAX_KB];   // coff: channel offset / 64 inside the tensor
   // stride-2 convolutions (lvae_conv2d_tc_s2): the tile's pixel coordinates are multiplied by in_stride before the tap
@@ -557,7 +540,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
             int rem = p0 - c3 * hw;
             c2 = rem / p.W; c1 = rem - c2 * p.W;
           }
-          for (int j = 0; j < p.Npad / 64 && !(FUSE == 3 && p.gate_skip_h) && !(FUSE == 2 && p.post); ++j) {
+          for (int j = 0; j < p.Npad / 64 && !(FUSE == 3 && p.gate_skip_h); ++j) {
             const bool second = p.y2 != nullptr && j * 64 >= p.nsplit;
             tma_store_4d(second ? &tmY2 : &tmY, smem_u32(sOut + j * TC_STAGE_BYTES), second ? j * 64 - p.nsplit : j * 64, c1, c2, c3);
           }
@@ -680,118 +663,6 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         double* acc = (FUSE == 2 ? p.bnb_acc : p.stats_acc);
         if (acc) atomicAdd(acc + (blockIdx.x & 7) * 128 + st * 64 + c, (double)sum);   // 8-way striped (see elementwise.cu)
       }
-      if constexpr (FUSE == 1 || FUSE == 2) if (p.post) {
-        // ---- grid barrier: every CTA holds exactly one tile, still staged in shared memory (bf16, 128B-swizzled) ----
-        __threadfence();
-        asm volatile("bar.sync 1, 256;" ::: "memory");
-        if (threadIdx.x == 64) {
-          atomicAdd(p.post_counter, 1u);
-          while (*reinterpret_cast<volatile unsigned int*>(p.post_counter) < gridDim.x) {}
-          __threadfence();
-          asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");     // the store of y has read the staging tile
-        }
-        asm volatile("bar.sync 1, 256;" ::: "memory");
-        const double* acc = (FUSE == 2 ? p.bnb_acc : p.stats_acc);
-        double sA[2] = {0.0, 0.0}, sB[2] = {0.0, 0.0};                         // channels 2l, 2l+1
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {
-          sA[0] += __ldcg(acc + k * 128 + 2 * lane); sA[1] += __ldcg(acc + k * 128 + 2 * lane + 1);
-          sB[0] += __ldcg(acc + k * 128 + 64 + 2 * lane); sB[1] += __ldcg(acc + k * 128 + 64 + 2 * lane + 1);
-        }
-        const double invP = 1.0 / (double)p.post_count;
-        const int tile = (int)blockIdx.x;
-        const long long rbase = row_base(tile);
-        const int nrows = p.halo ? 128 : (int)min((long long)128, p.M_total - (long long)tile * TC_BM);
-        if constexpr (FUSE == 1) {
-          float sc[2], sh[2];
-#pragma unroll
-          for (int j = 0; j < 2; ++j) {
-            const int ch = 2 * lane + j;
-            const double m = sA[j] * invP;
-            double var = sB[j] * invP - m * m;
-            if (var < 0.0) var = 0.0;
-            const float mean = (float)m, rstd = rsqrtf((float)var + p.post_eps);
-            if (blockIdx.x == 0 && ew == 0) {
-              p.post_save[ch] = mean;
-              p.post_save[64 + ch] = rstd;
-              if (p.post_running_mean) {
-                const double unb = p.post_count > 1 ? var * (double)p.post_count / (double)(p.post_count - 1) : var;
-                p.post_running_mean[ch] = (float)((1.0 - p.post_momentum) * (double)p.post_running_mean[ch] + p.post_momentum * m);
-                p.post_running_var[ch] = (float)((1.0 - p.post_momentum) * (double)p.post_running_var[ch] + p.post_momentum * unb);
-              }
-            }
-            sc[j] = rstd * p.post_gamma[ch];
-            sh[j] = p.post_beta[ch] - mean * sc[j];
-          }
-          if (blockIdx.x == 0 && threadIdx.x == 64 && p.post_nbt) *p.post_nbt += 1;
-#pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            const int r = ew * 16 + i;
-            uint32_t* q = reinterpret_cast<uint32_t*>(sOut + r * 128 + ((((lane >> 2) ^ (r & 7))) << 4) + (lane & 3) * 4);
-            const uint32_t u = *q;
-            const float y0 = __uint_as_float(u << 16), y1 = __uint_as_float(u & 0xFFFF0000u);
-            const __nv_bfloat162 ob = __floats2bfloat162_rn(act_fwd_t<true>(fmaf(y0, sc[0], sh[0]), p.post_act),
-                                                            act_fwd_t<true>(fmaf(y1, sc[1], sh[1]), p.post_act));
-            *q = *reinterpret_cast<const uint32_t*>(&ob);
-          }
-        } else {
-          const float m1[2] = {(float)(sA[0] * invP), (float)(sA[1] * invP)}, m2[2] = {(float)(sB[0] * invP), (float)(sB[1] * invP)};
-          if (blockIdx.x == 0 && ew == 0) {
-            if (p.post_dbeta) { p.post_dbeta[2 * lane] += (float)sA[0]; p.post_dbeta[2 * lane + 1] += (float)sA[1]; }
-            if (p.post_dgamma) { p.post_dgamma[2 * lane] += (float)sB[0]; p.post_dgamma[2 * lane + 1] += (float)sB[1]; }
-          }
-          const bool elu = p.bnb_act == ACT_ELU;
-          const int hwp = p.H * p.W;
-#pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            const int r = ew * 16 + i;
-            if (r >= nrows) continue;
-            const long long pix = rbase + i + (i >> 3) * rstep;                  // global pixel index of this staged row
-            uint32_t* q = reinterpret_cast<uint32_t*>(sOut + r * 128 + ((((lane >> 2) ^ (r & 7))) << 4) + (lane & 3) * 4);
-            const uint32_t u = *q;
-            const float y0 = __uint_as_float(u << 16), y1 = __uint_as_float(u & 0xFFFF0000u);
-            const float x0 = __uint_as_float(xq[i] << 16), x1 = __uint_as_float(xq[i] & 0xFFFF0000u);
-            const float h0 = fmaf(x0, kx0, kb0), h1 = fmaf(x1, kx1, kb1);
-            const float t0 = fmaf(x0, kg0, kc0), t1 = fmaf(x1, kg1, kc1);
-            float g0, g1;
-            if (elu) {
-              g0 = y0 * (t0 > 0.f ? 1.f : ex2_approx(t0 * 1.4426950408889634f));
-              g1 = y1 * (t1 > 0.f ? 1.f : ex2_approx(t1 * 1.4426950408889634f));
-            } else {
-              g0 = y0 * act_bwd_t<true>(t0, p.bnb_act);
-              g1 = y1 * act_bwd_t<true>(t1, p.bnb_act);
-            }
-            float o0 = kg0 * (g0 - m1[0] - h0 * m2[0]), o1 = kg1 * (g1 - m1[1] - h1 * m2[1]);
-            if (p.post_scale) {
-              const float2 ps = __ldg(reinterpret_cast<const float2*>(p.post_scale + (pix / hwp) * 64) + lane);
-              o0 *= ps.x; o1 *= ps.y;
-            }
-            if (p.post_add) {
-              const uint32_t ua = __ldg(reinterpret_cast<const uint32_t*>(p.post_add + pix * 64) + lane);
-              o0 += __uint_as_float(ua << 16); o1 += __uint_as_float(ua & 0xFFFF0000u);
-            }
-            const __nv_bfloat162 ob = __floats2bfloat162_rn(o0, o1);
-            *q = *reinterpret_cast<const uint32_t*>(&ob);
-          }
-        }
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        asm volatile("bar.sync 1, 256;" ::: "memory");
-        if (threadIdx.x == 64) {
-          int c1, c2, c3;
-          if (p.halo) {
-            int n0 = tile / p.tiles_per_img;
-            int r2 = tile - n0 * p.tiles_per_img;
-            c3 = n0; c2 = (r2 / p.tiles_x) * 16; c1 = (r2 % p.tiles_x) * 8;
-          } else {
-            int p0 = tile * TC_BM;
-            c3 = p0 / hw;
-            int rem = p0 - c3 * hw;
-            c2 = rem / p.W; c1 = rem - c2 * p.W;
-          }
-          tma_store_4d(FUSE == 1 ? &tmY2 : &tmY, smem_u32(sOut), 0, c1, c2, c3);
-          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-        }
-      }
     }
   }
   if (p.tma_store && threadIdx.x == 64) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
@@ -841,15 +712,6 @@ struct LvaeConvFuse {
   void* gate_out;
   int gate_act;
   int gate_skip_h;
-  // BatchNorm apply behind a grid barrier (one tile per CTA): see TcParams::post
-  unsigned int* post_counter;
-  void* post_out;                       // with stats_acc: act(bn(y)) (B,H,W,64) bf16
-  const float* post_gamma; const float* post_beta; float* post_save;
-  float* post_running_mean; float* post_running_var; long long* post_nbt;
-  float post_momentum, post_eps;
-  int post_act;
-  float* post_dgamma; float* post_dbeta;        // with bnb_acc: y becomes the gradient wrt the BatchNorm input
-  const float* post_scale; const void* post_add;
 };
 
 LVAE_API int lvae_conv2d_tc_ex(const void* x, const void* x2, const void* wp, const float* bias, const float* out_scale,
@@ -894,18 +756,6 @@ LVAE_API int lvae_conv2d_tc_ex(const void* x, const void* x2, const void* wp, co
       LVAE_REQUIRE(fuse->gate_x && N == 128 && !y2 && !res && !out_f32 && !p.bnb_acc,
                    "conv2d_tc: the gated-residual epilogue needs N == 128, bf16 output, no residual / split");
       p.gate_x = (const __nv_bfloat16*)fuse->gate_x; p.gate_act = fuse->gate_act; p.gate_skip_h = fuse->gate_skip_h;
-    }
-    if (fuse->post_counter) {
-      LVAE_REQUIRE((p.stats_acc && fuse->post_out && fuse->post_gamma && fuse->post_beta && fuse->post_save) || p.bnb_acc,
-                   "conv2d_tc: incomplete arguments for the BatchNorm apply behind the grid barrier");
-      LVAE_REQUIRE(!p.gate_x && N == 64 && !y2 && !res && !out_f32, "conv2d_tc: the fused BatchNorm apply needs the N == 64 bf16 TMA-store path");
-      p.post = 1;
-      p.post_counter = fuse->post_counter; p.post_count = (long long)B * H * W;
-      p.post_gamma = fuse->post_gamma; p.post_beta = fuse->post_beta; p.post_save = fuse->post_save;
-      p.post_running_mean = fuse->post_running_mean; p.post_running_var = fuse->post_running_var; p.post_nbt = fuse->post_nbt;
-      p.post_momentum = fuse->post_momentum; p.post_eps = fuse->post_eps; p.post_act = fuse->post_act;
-      p.post_dgamma = fuse->post_dgamma; p.post_dbeta = fuse->post_dbeta;
-      p.post_scale = fuse->post_scale; p.post_add = (const __nv_bfloat16*)fuse->post_add;
     }
   }
   const int inputs = x2 ? 2 : 1;
@@ -962,7 +812,7 @@ LVAE_API int lvae_conv2d_tc_ex(const void* x, const void* x2, const void* wp, co
   memset(&tmY2, 0, sizeof(tmY2));
   if (p.tma_store) {
     // output maps: same pixel box as the activation tiles (8 x 16 pixels in halo mode), 64 channels per box
-    void* const gate_out = (fuse && fuse->gate_out) ? fuse->gate_out : ((p.post && p.stats_acc) ? fuse->post_out : nullptr);
+    void* const gate_out = (fuse && fuse->gate_out) ? fuse->gate_out : nullptr;
     for (int which = (gate_out && p.gate_skip_h) ? 1 : 0; which < ((y2 || gate_out) ? 2 : 1); ++which) {
       const int ncols = gate_out ? (which ? 64 : N) : (y2 ? (which ? N - nsplit : nsplit) : N);
       cuuint64_t gdim[4] = {(cuuint64_t)ncols, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
@@ -1008,8 +858,6 @@ LVAE_API int lvae_conv2d_tc_ex(const void* x, const void* x2, const void* wp, co
   }
   const int n_tiles = p.halo ? B * p.tiles_per_img : (p.M_total + TC_BM - 1) / TC_BM;
   const int grid = n_tiles < lvae_num_sms() ? n_tiles : lvae_num_sms();
-  // the grid barrier needs every CTA resident at once and exactly one (still staged) tile per CTA
-  LVAE_REQUIRE(!p.post || (n_tiles <= lvae_num_sms() && p.tma_store), "conv2d_tc: fused BatchNorm apply needs n_tiles <= #SMs");
   if (p.gate_x) lvae_launch(conv_tc_kernel<3>, grid, TC_THREADS, smem, stream, tmA0, tmA1, tmW, tmY, tmY2, p);
   else if (p.stats_acc) lvae_launch(conv_tc_kernel<1>, grid, TC_THREADS, smem, stream, tmA0, tmA1, tmW, tmY, tmY2, p);
   else if (p.bnb_acc) lvae_launch(conv_tc_kernel<2>, grid, TC_THREADS, smem, stream, tmA0, tmA1, tmW, tmY, tmY2, p);
@@ -1114,13 +962,6 @@ LVAE_API int lvae_conv2d_tc_s2(const void* x, const void* wp, const float* bias,
     LVAE_CHECK_LAUNCH("conv2d_tc_s2");
   }
   return LVAE_OK;
-}
-
-// 1 if a conv over (B,H,W) pixels runs with one tile per CTA (so that the BatchNorm apply can ride behind a grid barrier)
-LVAE_API int lvae_conv2d_tc_one_tile_per_cta(int B, int H, int W) {
-  const bool halo = (W % 8 == 0 && H % 16 == 0);
-  const long long n_tiles = halo ? (long long)B * (W / 8) * (H / 16) : ((long long)B * H * W + TC_BM - 1) / TC_BM;
-  return n_tiles <= lvae_num_sms() ? 1 : 0;
 }
 
 // profiling aid: device buffer (>= 8 * tiles-per-CTA int64) that CTA 0 of the following conv2d_tc launches fills with

@@ -110,14 +110,10 @@ class LadderVAE(BaseGenerativeModel):
         if arena is None or arena.device != device:
             from lvae_b200.lib.nn import BatchNorm2d
             bns = [m for m in self.modules() if isinstance(m, BatchNorm2d)]
-            n_acc = 3 * ops.BN_STRIPES * 2 * self.n_filters
-            # per BatchNorm: the striped statistics accumulators, then 8 doubles (= 16 uint32) of grid-barrier tickets for the
-            # BatchNorm applies fused into the convolutions (ops._bn_post_counter); ONE memset per forward clears all of it
-            arena = torch.zeros((max(1, len(bns)), n_acc + 8), dtype=torch.float64, device=device)
+            arena = torch.zeros((max(1, len(bns)), 3, ops.BN_STRIPES, 2, self.n_filters), dtype=torch.float64, device=device)
             for i, bn in enumerate(bns):
                 if bn.num_features == self.n_filters:
-                    bn._lvae_scratch = arena[i, :n_acc].view(3, ops.BN_STRIPES, 2, self.n_filters)
-                    bn._lvae_counters = arena[i, n_acc:].view(torch.int32)
+                    bn._lvae_scratch = arena[i]
                     bn._lvae_scratch_owned = False
                     bn._lvae_epoch_fwd = bn._lvae_epoch_bwd = bn._lvae_epoch_out = -1
             self._lvae_bn_arena = arena

@@ -472,7 +472,7 @@ def _tc_fusable(N, out_f32, res, nsplit=0) -> bool:
     return N == 64 and not out_f32 and res is None and not nsplit
 
 
-def _conv_tc(x, x2, wp, bias, out_scale, res, N, ksize, flip, out_f32, nsplit=0, stats_acc=None, bnb=None, gate=None, post=None):
+def _conv_tc(x, x2, wp, bias, out_scale, res, N, ksize, flip, out_f32, nsplit=0, stats_acc=None, bnb=None, gate=None):
     """Launch the tcgen05 kernel.  Returns y, or (y, y2) when nsplit splits the output columns.
     stats_acc: (2,64) float64 accumulator for the output's per-channel statistics; bnb = (x, save, gamma, beta, acc, act):
     BatchNorm-backward sums over the output (both fused into the epilogue)."""
@@ -485,24 +485,9 @@ def _conv_tc(x, x2, wp, bias, out_scale, res, N, ksize, flip, out_f32, nsplit=0,
         y, y2 = torch.empty((B, H, W, N), dtype=odt, device=x.device), None
     fuse = None
     gate_out = None
-    post_out = None
     if stats_acc is not None or bnb is not None or gate is not None:
         f = _capi.ConvFuse()
         f.stats_acc = _p(stats_acc)
-        if post is not None:
-            # BatchNorm apply behind a grid barrier (one tile per CTA).  Forward (with stats_acc): dict(counter, gamma, beta,
-            # save, running_mean, running_var, nbt, momentum, eps, act) -> second output act(bn(y)).  Backward (with bnb):
-            # dict(counter, dgamma, dbeta, scale, add) -> y is the gradient wrt the BatchNorm input.
-            f.post_counter = post["counter"].data_ptr()
-            if stats_acc is not None:
-                post_out = torch.empty((B, H, W, 64), dtype=torch.bfloat16, device=x.device)
-                f.post_out = post_out.data_ptr()
-                f.post_gamma, f.post_beta, f.post_save = post["gamma"].data_ptr(), post["beta"].data_ptr(), post["save"].data_ptr()
-                f.post_running_mean, f.post_running_var, f.post_nbt = _p(post["running_mean"]), _p(post["running_var"]), _p(post["nbt"])
-                f.post_momentum, f.post_eps, f.post_act = float(post["momentum"]), float(post["eps"]), int(post["act"])
-            else:
-                f.post_dgamma, f.post_dbeta = post["dgamma"].data_ptr(), post["dbeta"].data_ptr()
-                f.post_scale, f.post_add = _p(post["scale"]), _p(post["add"])
         if gate is not None:            # (residual input (B,H,W,64) bf16, activation id): gated residual output in the epilogue
             gx, gact = gate
             gate_out = torch.empty_like(gx)
@@ -517,8 +502,6 @@ def _conv_tc(x, x2, wp, bias, out_scale, res, N, ksize, flip, out_f32, nsplit=0,
          nsplit, B, H, W, C, N, ksize, 1 if flip else 0, 1 if out_f32 else 0, fuse, _stream())
     if gate is not None:
         return y, gate_out
-    if post_out is not None:
-        return y, post_out
     return (y, y2) if nsplit else y
 
 
@@ -529,7 +512,7 @@ def _gather(x, x2, wp, ld, bias, in_scale, out_scale, res, B, Hi, Wi, C1, C2, Ho
     return y
 
 
-def conv_forward_raw(spec: ConvSpec, xn, x2n, weight, bias, out_scale, resn, stats_acc=None, post=None):
+def conv_forward_raw(spec: ConvSpec, xn, x2n, weight, bias, out_scale, resn, stats_acc=None):
     """(conv(cat(xn, x2n)) + bias) * out_scale + resn on NHWC tensors.  bf16 activations on eligible shapes run on
     the tensor cores (lvae_conv2d_tc), everything else on the CUDA-core implicit GEMM (lvae_conv2d_gather)."""
     B, Hi, Wi, C1 = xn.shape
@@ -561,11 +544,6 @@ def conv_forward_raw(spec: ConvSpec, xn, x2n, weight, bias, out_scale, resn, sta
         wp = spec.pack_tc_fwd.get(weight, torch.bfloat16)
         stats["tc_fwd"] += 1
         fused = stats_acc is not None and _tc_fusable(spec.cout, want_f32, resn) and _FUSE_STATS_MAXPIX >= xn.shape[0] * xn.shape[1] * xn.shape[2]
-        if fused and post is not None and x2n is None and spec.k == 3:
-            # conv + statistics + [grid barrier] + BatchNorm apply of the consumer: returns (y, act(bn(y))), "post"
-            stats["bn_post_fwd"] = stats.get("bn_post_fwd", 0) + 1
-            y, a = _conv_tc(xn, None, wp, bias, out_scale, None, spec.cout, spec.k, False, False, stats_acc=stats_acc, post=post)
-            return (y, a), "post"
         y = _conv_tc(xn, x2n, wp, bias, out_scale, resn, spec.cout, spec.k, False, want_f32,
                      stats_acc=stats_acc if fused else None)
         return (y, fused) if stats_acc is not None else y
@@ -580,7 +558,7 @@ def conv_forward_raw(spec: ConvSpec, xn, x2n, weight, bias, out_scale, resn, sta
 
 
 def conv_backward_raw(spec: ConvSpec, xn, x2n, weight, bias, out_scale, gyn, need_x=True, need_w=True, need_b=True,
-                      dx_scale=None, bnb=None, bnb_post=None):
+                      dx_scale=None, bnb=None):
     """Data and parameter gradients of conv_forward_raw.  ``out_scale`` is the forward's Dropout2d mask (gyn is the
     gradient wrt the masked output; pass None when gyn is already the gradient wrt the raw conv output).
     ``dx_scale`` (B, Cin) is folded into the dgrad epilogue: the returned dx is multiplied by it (the mask of the
@@ -621,15 +599,11 @@ def conv_backward_raw(spec: ConvSpec, xn, x2n, weight, bias, out_scale, gyn, nee
                             and _FUSE_BNB_MAXPIX >= gyn.shape[0] * gyn.shape[1] * gyn.shape[2])
                 # padded (conv_out of a stochastic block reading the 64-channel bf16 copy of z): the gradient goes to the
                 # fp32, Z-channel z the autograd graph holds -> fp32 epilogue, no padding channels
-                use_post = fuse_bnb and bnb_post is not None and spec.k == 3
                 gx = _conv_tc(gyn, None, wpb, None, dx_scale, None, spec.cin, spec.k, True, padded,
-                              bnb=bnb if fuse_bnb else None, post=bnb_post if use_post else None)
+                              bnb=bnb if fuse_bnb else None)
                 if fuse_bnb:
                     stats["bnb_fused"] = stats.get("bnb_fused", 0) + 1
                     conv_backward_raw.last_fused = True
-                if use_post:       # gx is already the gradient wrt the BatchNorm input (apply fused behind the grid barrier)
-                    stats["bn_post_bwd"] = stats.get("bn_post_bwd", 0) + 1
-                    conv_backward_raw.last_fused = "post"
             else:
                 assert dx_scale is None
                 gx, gx2 = _conv_tc(gyn, None, wpb, None, None, None, spec.cin, spec.k, True, False, nsplit=C1)
@@ -852,23 +826,6 @@ def bn_scratch(bn, device):
     return acc
 
 
-_bn_post = [os.environ.get("LVAE_BN_POST", "1") != "0"]
-
-
-def _bn_post_counter(bn, slot: int, B: int, H: int, W: int, dtype):
-    """Grid-barrier ticket for the fused BatchNorm apply (slot 0 forward, 1 backward) when it can be used: tcgen05 path on
-    bf16, one tile per CTA, and the BatchNorm's scratch lives in the model arena (zeroed once per forward, so the ticket
-    is zero at launch)."""
-    if not (_bn_post[0] and _tc_enabled[0] and dtype == torch.bfloat16 and bn.num_features == 64):
-        return None
-    ctr = getattr(bn, "_lvae_counters", None)
-    if ctr is None or getattr(bn, "_lvae_scratch_owned", True) or not _pow2(H) or not _pow2(W):
-        return None
-    if not _capi.lib().lvae_conv2d_tc_one_tile_per_cta(B, H, W):
-        return None
-    return ctr[slot:slot + 1]
-
-
 def _bn_clean(bn, acc_rows, which: str):
     """Make sure the accumulator rows are zero before accumulating into them."""
     attr = "_lvae_epoch_" + which
@@ -915,24 +872,15 @@ class GatedBlockFn(Function):
 
         a1 = bn_fwd(xn, bn1, sc1, saves[0], g1, b1, x_stats)
         acc2 = None
-        a2 = None
         if training and C == 64:
             acc2 = sc2[0]
             _bn_clean(bn2, acc2, "fwd")
-            ctr = _bn_post_counter(bn2, 0, B, H, W, xn.dtype)
-            post = None
-            if ctr is not None:
-                post = dict(counter=ctr, gamma=g2, beta=b2, save=saves[1], running_mean=bn2.running_mean, running_var=bn2.running_var,
-                            nbt=bn2.num_batches_tracked, momentum=bn2.momentum if bn2.momentum is not None else 0.1, eps=bn2.eps, act=act)
-            y1, fused = conv_forward_raw(conv1.spec, a1, None, w1, cb1, m1, None, stats_acc=acc2, post=post)   # BN2 statistics in the epilogue
-            if fused == "post":
-                y1, a2 = y1                      # ... and BN2 + activation applied behind the grid barrier: no separate pass
-            elif not fused:
+            y1, fused = conv_forward_raw(conv1.spec, a1, None, w1, cb1, m1, None, stats_acc=acc2)   # BN2 statistics in the epilogue
+            if not fused:
                 call("lvae_bn_stats", y1.data_ptr(), acc2.data_ptr(), Pn, C, dt, _stream())
         else:
             y1 = conv_forward_raw(conv1.spec, a1, None, w1, cb1, m1, None)
-        if a2 is None:
-            a2 = bn_fwd(y1, bn2, sc2, saves[1], g2, b2, acc2)
+        a2 = bn_fwd(y1, bn2, sc2, saves[1], g2, b2, acc2)
         gspec = gconv.spec
         # conv2, the 1x1 gate conv and the gate itself as one launch (csrc/conv_gate_tcgen05.cu)
         chain = (_gate_chain[0] and C == 64 and gspec.cout == 128 and gspec.k == 1 and conv2.spec.k == 3 and conv2.spec.cout == 64
@@ -989,16 +937,10 @@ class GatedBlockFn(Function):
         acc1b, acc2b = sc1b[1], sc2b[1]
         _bn_clean(bn1, acc1b, "bwd")
         _bn_clean(bn2, acc2b, "bwd")
-        def post_bwd(bn, gamma, beta, scale, add):
-            """Arguments of the fused BatchNorm-backward apply (grid barrier in the dgrad kernel), or None."""
-            ctr = _bn_post_counter(bn, 1, B, H, W, xn.dtype) if (training and C == 64) else None
-            if ctr is None:
-                return None, None, None
-            grad_site()
-            dgam, gsunk = _param_grad_buffer(gamma)
-            dbet, bsunk = _param_grad_buffer(beta)
-            return (dict(counter=ctr, dgamma=dgam, dbeta=dbet, scale=scale, add=add), (None if gsunk else dgam),
-                    (None if bsunk else dbet))
+        # conv2 (dy2 is already masked); its dgrad epilogue also accumulates BN2's backward sums
+        da2, _, gw2, gcb2 = conv_backward_raw(conv2.spec, a2, None, w2, cb2, None, dy2, True, ng[7], ng[8],
+                                              bnb=(y1, saves[1], g2, b2, acc2b, act) if C == 64 else None)
+        fused2 = conv_backward_raw.last_fused
 
         def bn_bwd(dy, xin, bn, acc, save, gamma, beta, post_scale, add, skip_reduce):
             grad_site()
@@ -1010,26 +952,13 @@ class GatedBlockFn(Function):
                  act, 1 if training else 0, dt, 1 if skip_reduce else 0, _stream())
             return dxo, (None if gsunk else dgam), (None if bsunk else dbet)
 
-        # conv2 (dy2 is already masked); its dgrad epilogue also accumulates BN2's backward sums and -- with one tile per
-        # CTA -- applies BN2's backward (and conv1's Dropout2d mask) behind a grid barrier: it then returns dy1 directly
-        p2, gg2, gb2 = post_bwd(bn2, g2, b2, m1, None)
-        da2, _, gw2, gcb2 = conv_backward_raw(conv2.spec, a2, None, w2, cb2, None, dy2, True, ng[7], ng[8],
-                                              bnb=(y1, saves[1], g2, b2, acc2b, act) if C == 64 else None, bnb_post=p2)
-        fused2 = conv_backward_raw.last_fused
-        if fused2 == "post":
-            dy1 = da2
-        else:
-            # BN2 + act backward, conv1's mask fused -> gradient wrt conv1's raw output
-            dy1, gg2, gb2 = bn_bwd(da2, y1, bn2, acc2b, saves[1], g2, b2, m1, None, fused2)
-        p1, gg1, gb1 = post_bwd(bn1, g1, b1, None, gn)
+        # BN2 + act backward, conv1's mask fused -> gradient wrt conv1's raw output
+        dy1, gg2, gb2 = bn_bwd(da2, y1, bn2, acc2b, saves[1], g2, b2, m1, None, fused2)
         da1, _, gw1, gcb1 = conv_backward_raw(conv1.spec, a1, None, w1, cb1, None, dy1, True, ng[3], ng[4],
-                                              bnb=(xn, saves[0], g1, b1, acc1b, act) if C == 64 else None, bnb_post=p1)
+                                              bnb=(xn, saves[0], g1, b1, acc1b, act) if C == 64 else None)
         fused1 = conv_backward_raw.last_fused
-        if fused1 == "post":
-            dx = da1
-        else:
-            # BN1 + act backward, residual gradient fused
-            dx, gg1, gb1 = bn_bwd(da1, xn, bn1, acc1b, saves[0], g1, b1, None, gn, fused1)
+        # BN1 + act backward, residual gradient fused
+        dx, gg1, gb1 = bn_bwd(da1, xn, bn1, acc1b, saves[0], g1, b1, None, gn, fused1)
         return (as_nchw(dx), gg1, gb1, gw1, gcb1, gg2, gb2, gw2, gcb2, gwg, ggb, None, None, None, None, None)
 
 
