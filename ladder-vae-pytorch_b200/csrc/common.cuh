@@ -4,7 +4,6 @@
 #include <cuda_bf16.h>
 #include <stdint.h>
 #include <stdio.h>
-#include <stdlib.h>
 #include <math.h>
 
 #define LVAE_API extern "C" __attribute__((visibility("default")))
@@ -208,15 +207,3 @@ static inline int lvae_num_sms() {
   return n;
 }
 static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
-// Persistent-CTA grid for n_tiles equal tiles: the launch lasts as long as its busiest CTA (ceil(n_tiles / #SMs) tiles), so
-// use only as many CTAs as that depth needs -- 512 tiles on 148 SMs run 4 deep on 128 CTAs exactly as fast as on 148, and
-// the 20 SMs left over serve the weight-gradient kernels of the side streams.  (LVAE_BALANCED_GRID=0: min(n_tiles, #SMs).)
-static inline int lvae_balanced_grid(int n_tiles) {
-  static int on = -1;
-  if (on < 0) { const char* e = getenv("LVAE_BALANCED_GRID"); on = e ? atoi(e) : 1; }
-  const int sms = lvae_num_sms();
-  if (n_tiles <= sms) return n_tiles;
-  if (!on) return sms;
-  const int depth = (n_tiles + sms - 1) / sms;
-  return (n_tiles + depth - 1) / depth;
-}

@@ -566,7 +566,7 @@ LVAE_API int lvae_conv_gate_tc(const void* a2, const void* w2p, const float* bia
     attr = true;
   }
   const int n_tiles = p.halo ? B * p.tiles_per_img : (p.M_total + CG_BM - 1) / CG_BM;
-  const int grid = lvae_balanced_grid(n_tiles);
+  const int grid = n_tiles < lvae_num_sms() ? n_tiles : lvae_num_sms();
   lvae_launch(conv_gate_tc_kernel, grid, CG_THREADS, smem, stream, tmA, tmW2, tmWg, tmC2, tmH, tmOut, p);
   LVAE_COUNT_LAUNCH();
   LVAE_CHECK_LAUNCH("conv_gate_tc");

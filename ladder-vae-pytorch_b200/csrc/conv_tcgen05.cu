@@ -857,7 +857,7 @@ LVAE_API int lvae_conv2d_tc_ex(const void* x, const void* x2, const void* wp, co
     attr_smem = 227 * 1024;
   }
   const int n_tiles = p.halo ? B * p.tiles_per_img : (p.M_total + TC_BM - 1) / TC_BM;
-  const int grid = lvae_balanced_grid(n_tiles);
+  const int grid = n_tiles < lvae_num_sms() ? n_tiles : lvae_num_sms();
   if (p.gate_x) lvae_launch(conv_tc_kernel<3>, grid, TC_THREADS, smem, stream, tmA0, tmA1, tmW, tmY, tmY2, p);
   else if (p.stats_acc) lvae_launch(conv_tc_kernel<1>, grid, TC_THREADS, smem, stream, tmA0, tmA1, tmW, tmY, tmY2, p);
   else if (p.bnb_acc) lvae_launch(conv_tc_kernel<2>, grid, TC_THREADS, smem, stream, tmA0, tmA1, tmW, tmY, tmY2, p);
@@ -956,7 +956,7 @@ LVAE_API int lvae_conv2d_tc_s2(const void* x, const void* wp, const float* bias,
       if (r != CUDA_SUCCESS) { lvae_set_error("conv2d_tc_s2: tensor map (w) encode failed: %d", (int)r); return LVAE_ERR_CUDA; }
     }
     const int n_tiles = (p.M_total + TC_BM - 1) / TC_BM;
-    const int grid = lvae_balanced_grid(n_tiles);
+    const int grid = n_tiles < lvae_num_sms() ? n_tiles : lvae_num_sms();
     lvae_launch(conv_tc_kernel<0>, grid, TC_THREADS, smem, stream, tmA, tmA, tmW, tmY, tmY2, p);
     LVAE_COUNT_LAUNCH();
     LVAE_CHECK_LAUNCH("conv2d_tc_s2");
