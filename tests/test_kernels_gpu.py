@@ -280,6 +280,36 @@ def test_kl_bookkeeping(L, Lr, B, fb):
         assert rel_err(gk, kl.grad) < 1e-5 and rel_err(gl, lp.grad) < 1e-5, as_rows
 
 
+@pytest.mark.parametrize("B,hw,broadcast", [(5, (16, 16), False), (3, (8, 8), False), (2, (32, 32), False), (4, (4, 4), False),
+                                            (3, (2, 2), True)])
+def test_stochastic_core_with_philox_noise(L, B, hw, broadcast):
+    """The training path draws eps inside the kernel (Philox), so it cannot be fed the oracle's eps: instead the noise is
+    recovered from the sample, eps = (z - mu_q) / sigma_q, and every other output (log p, log q, Monte-Carlo KL, analytic KL
+    per pixel, the bf16 copy of z) is checked against the fp64 closed forms for THAT noise.  Covers the staged, persistent
+    kernel (>= 64 pixels per sample) and the plain one."""
+    from oracle import lvae_oracle as O
+    from lvae_b200 import ops
+    Z = 32
+    g = torch.Generator().manual_seed(B * 100 + hw[0])
+    q = torch.randn(B, 2 * Z, *hw, generator=g, dtype=torch.float64) * 0.7
+    p = torch.randn(1 if broadcast else B, 2 * Z, *hw, generator=g, dtype=torch.float64) * 0.7
+    L.manual_seed(21)
+    zz, zlp, klo, klso, lpo, lqo = ops.stochastic_core(dev(q), dev(p), lowp_copy=True)
+    qm, ql = q.chunk(2, 1)
+    pm, pl = p.chunk(2, 1)
+    z = zz.double().cpu()
+    eps = (z - qm) / (ql / 2).exp()
+    assert abs(float(eps.mean())) < 0.05 and abs(float(eps.std()) - 1) < 0.05       # it IS standard normal noise
+    logp = O.normal_log_prob(z, pm, pl).sum((1, 2, 3))
+    logq = O.normal_log_prob(z, qm, ql).sum((1, 2, 3))
+    assert rel_err(lpo, logp) < TOL and rel_err(lqo, logq) < 5 * TOL      # log q from the recovered eps: (z - mu) / sigma rounding
+    assert rel_err(klo, logq - logp) < 2e-4
+    assert rel_err(klso, O.normal_kl(qm, ql, pm, pl).sum(1)) < TOL
+    assert tuple(zlp.shape) == (B, 64) + tuple(hw)
+    assert float((zlp[:, :Z].double().cpu() - z).abs().max()) <= 2 ** -8 * float(z.abs().max()) + 1e-6     # bf16 rounding of z
+    assert float(zlp[:, Z:].abs().max()) == 0.0                                                            # zero-padded channels
+
+
 def test_stochastic_philox_statistics(L):
     from lvae_b200 import ops
     L.manual_seed(7)
