@@ -215,168 +215,6 @@ __global__ void __launch_bounds__(ST_THREADS, TRAIN ? 4 : 2) stoch_fwd_kernel(St
 }
 
 
-// ------------------------------------------------------------------------------------------
-// Staged forward for the hot case (q present, Z = 32, p per sample, reparameterised sample from Philox or external eps):
-// persistent CTAs stream work items (sample b, chunk of 32 pixels) through a 3-stage shared-memory ring filled by bulk
-// asynchronous copies (cp.async.bulk + mbarrier: the q rows and the p rows of a chunk are two contiguous 8 KB blocks), so
-// the loads of the next items are in flight while the current one is computed.  The plain kernel above issues its loads
-// and then spends ~3/4 of every CTA's life computing with nothing in flight (ncu: issue slots 42 % busy, DRAM 21 %, 43 %
-// occupancy; raising the occupancy from 4 to 6 CTAs per SM alone took 17.0 -> 13.3 us at 16x16).
-// ------------------------------------------------------------------------------------------
-constexpr int SG_PIX = 32;                          // pixels per work item: 32 x 8 quads = 256 threads
-constexpr int SG_ROW = 2 * 32 * 4;                  // bytes per pixel row [mu(32) | logvar(32)] fp32
-constexpr int SG_BLK = SG_PIX * SG_ROW;             // 8 KB
-constexpr int SG_STAGES = 3;
-
-__device__ __forceinline__ uint32_t sg_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void sg_mbar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
-}
-__device__ __forceinline__ void sg_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void sg_wait(uint32_t bar, uint32_t parity) {
-  uint32_t ok = 0;
-  while (!ok) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
-  }
-}
-__device__ __forceinline__ void sg_bulk_load(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-               ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
-}
-
-template <bool PHILOX>
-__global__ void __launch_bounds__(ST_THREADS, 4) stoch_fwd_staged_kernel(StochArgs a) {
-  extern __shared__ __align__(128) uint8_t sg_smem[];    // SG_STAGES x {q block, p block}
-  uint8_t (*stage)[2][SG_BLK] = reinterpret_cast<uint8_t (*)[2][SG_BLK]>(sg_smem);
-  __shared__ __align__(8) uint64_t full[SG_STAGES];
-  __shared__ float red[3][ST_THREADS / 32];
-  __shared__ unsigned int s_last;
-  constexpr int Z = 32;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int gl = lane & 7;                               // 16-byte group of channels
-  const int px = threadIdx.x >> 3;                       // pixel of the item
-  const int n_items = a.B * a.nchunk;                    // chunk-major inside a sample: item = b * nchunk + c
-  if (threadIdx.x == 0) {
-    for (int s = 0; s < SG_STAGES; ++s) sg_mbar_init(sg_u32(&full[s]), 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  __syncthreads();
-  pdl_wait();
-  pdl_launch();
-  PhiloxState st;
-  if (PHILOX) st = *a.rng;
-  auto issue = [&](int item, int s) {                    // thread 0 only
-    const int b = item / a.nchunk, c = item - b * a.nchunk;
-    const int npx = min(SG_PIX, a.hw - c * SG_PIX);
-    const uint32_t bytes = (uint32_t)npx * SG_ROW;
-    const long long off = ((long long)b * a.hw + (long long)c * SG_PIX) * 2 * Z;
-    sg_expect_tx(sg_u32(&full[s]), 2 * bytes);
-    sg_bulk_load(sg_u32(&stage[s][0][0]), a.q + off, bytes, sg_u32(&full[s]));
-    sg_bulk_load(sg_u32(&stage[s][1][0]), a.p + off, bytes, sg_u32(&full[s]));
-  };
-  if (threadIdx.x == 0)
-    for (int s = 0; s < SG_STAGES; ++s) {
-      const int item = (int)blockIdx.x + s * (int)gridDim.x;
-      if (item < n_items) issue(item, s);
-    }
-  int s = 0;
-  uint32_t ph = 0;
-  for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-    const int b = item / a.nchunk, c = item - b * a.nchunk;
-    const int pix = c * SG_PIX + px;
-    const bool pvalid = pix < a.hw;
-    const long long zi = ((long long)b * a.hw + pix) * Z + 4 * gl;
-    float4 e4 = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (pvalid) {                                       // the noise does not depend on the staged data: draw it while they land
-      if (PHILOX) e4 = philox_normal4_fast(st, a.stream_id, (unsigned long long)(zi >> 2));
-      else e4 = __ldg(reinterpret_cast<const float4*>(a.eps + zi));
-    }
-    sg_wait(sg_u32(&full[s]), ph);
-    float s_kl = 0.f, s_lp = 0.f, s_lq = 0.f, kls = 0.f;
-    if (pvalid) {
-      const float4 mq4 = *reinterpret_cast<const float4*>(&stage[s][0][px * SG_ROW + 16 * gl]);
-      const float4 lq4 = *reinterpret_cast<const float4*>(&stage[s][0][px * SG_ROW + 128 + 16 * gl]);
-      const float4 mp4 = *reinterpret_cast<const float4*>(&stage[s][1][px * SG_ROW + 16 * gl]);
-      const float4 lp4 = *reinterpret_cast<const float4*>(&stage[s][1][px * SG_ROW + 128 + 16 * gl]);
-      const float mq[4] = {mq4.x, mq4.y, mq4.z, mq4.w}, lq[4] = {lq4.x, lq4.y, lq4.z, lq4.w};
-      const float mp[4] = {mp4.x, mp4.y, mp4.z, mp4.w}, lp[4] = {lp4.x, lp4.y, lp4.z, lp4.w};
-      const float e[4] = {e4.x, e4.y, e4.z, e4.w};
-      float zz[4];
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const float ss = ex2_approx(lq[j] * (0.5f * LOG2E));
-        const float zv = fmaf(ss, e[j], mq[j]);
-        zz[j] = zv;
-        const float ivp = ex2_approx(-lp[j] * LOG2E);
-        const float dp = zv - mp[j];
-        const float logp = -0.5f * dp * dp * ivp - 0.5f * lp[j] - HALF_LOG_2PI;
-        const float logq = -0.5f * e[j] * e[j] - 0.5f * lq[j] - HALF_LOG_2PI;
-        s_lp += logp;
-        s_lq += logq;
-        const float vr = ss * ss * ivp;
-        const float dm = mq[j] - mp[j];
-        const float kl_an = 0.5f * (vr + dm * dm * ivp - 1.f - (lq[j] - lp[j]));
-        kls += kl_an;
-        s_kl += a.analytical ? kl_an : (logq - logp);
-      }
-      *reinterpret_cast<float4*>(a.z + zi) = make_float4(zz[0], zz[1], zz[2], zz[3]);
-      if (a.z_lp) {
-        __nv_bfloat16* zr = (__nv_bfloat16*)a.z_lp + ((long long)b * a.hw + pix) * a.z_lp_pitch;
-        st4<__nv_bfloat16>(zr + 4 * gl, make_float4(zz[0], zz[1], zz[2], zz[3]));
-        for (int cz = Z + 4 * gl; cz < a.z_lp_pitch; cz += 32) *reinterpret_cast<uint2*>(zr + cz) = make_uint2(0u, 0u);
-      }
-    }
-    // per-pixel channel reduction inside the 8-lane group
-    kls += __shfl_xor_sync(0xffffffffu, kls, 4);
-    kls += __shfl_xor_sync(0xffffffffu, kls, 2);
-    kls += __shfl_xor_sync(0xffffffffu, kls, 1);
-    if (pvalid && gl == 0 && a.kl_spatial) a.kl_spatial[(long long)b * a.hw + pix] = kls;
-    float v_lp = warp_sum(s_lp), v_lq = warp_sum(s_lq), v_kl = warp_sum(s_kl);
-    if (lane == 0) { red[0][warp] = v_lp; red[1][warp] = v_lq; red[2][warp] = v_kl; }
-    __syncthreads();                                    // every thread has read its staged values: the stage may be refilled
-    if (threadIdx.x == 0) {
-      const int nxt = item + SG_STAGES * (int)gridDim.x;
-      if (nxt < n_items) issue(nxt, s);
-    }
-    if (warp == 0) {
-      v_lp = warp_sum(lane < ST_THREADS / 32 ? red[0][lane] : 0.f);
-      v_lq = warp_sum(lane < ST_THREADS / 32 ? red[1][lane] : 0.f);
-      v_kl = warp_sum(lane < ST_THREADS / 32 ? red[2][lane] : 0.f);
-      if (lane == 0) {
-        if (a.nchunk == 1) {
-          a.logp[b] = v_lp;
-          if (a.logq) a.logq[b] = v_lq;
-          if (a.kl_sample) a.kl_sample[b] = v_kl;
-        } else {
-          float* part = a.ws_part + ((long long)b * a.nchunk + c) * 3;
-          part[0] = v_lp; part[1] = v_lq; part[2] = v_kl;
-          __threadfence();
-          const unsigned int t = atomicAdd(a.ws_cnt + b, 1u);
-          if (t == (unsigned int)(a.nchunk - 1)) {        // last chunk of sample b: add the partial sums up in chunk order
-            __threadfence();
-            const volatile float* pp = a.ws_part + (long long)b * a.nchunk * 3;
-            float t0 = 0.f, t1 = 0.f, t2 = 0.f;
-            for (int k = 0; k < a.nchunk; ++k) { t0 += pp[3 * k]; t1 += pp[3 * k + 1]; t2 += pp[3 * k + 2]; }
-            a.logp[b] = t0;
-            if (a.logq) a.logq[b] = t1;
-            if (a.kl_sample) a.kl_sample[b] = t2;
-            a.ws_cnt[b] = 0u;
-          }
-        }
-      }
-    }
-    __syncthreads();                                    // red[] is reused by the next item
-    if (++s == SG_STAGES) { s = 0; ph ^= 1; }
-  }
-  (void)s_last;
-}
-
 }  // namespace
 
 // workspace of a multi-chunk launch: B arrival tickets, then B * 64 * 3 floats of partial sums.  Zero-initialised ONCE by
@@ -407,29 +245,6 @@ LVAE_API int lvae_stoch_fwd(const float* q, const float* p, int p_broadcast, con
     a.nchunk = (hw + chunk - 1) / chunk;
     a.ws_cnt = (unsigned int*)ws;
     a.ws_part = (float*)ws + B;
-  }
-  // hot case: staged, persistent kernel (q present, Z = 32, per-sample p, reparameterised sample, at least 64 pixels per sample)
-  static int staged_env = -1;
-  if (staged_env < 0) { const char* e = getenv("LVAE_STOCH_STAGED"); staged_env = e ? atoi(e) : 1; }
-  if (staged_env && q && !forced && !use_mode && Z == 32 && !p_broadcast && ws && hw >= 64 && (hw + SG_PIX - 1) / SG_PIX <= 64) {
-    a.chunk_pix = SG_PIX;
-    a.nchunk = (hw + SG_PIX - 1) / SG_PIX;
-    a.ws_cnt = (unsigned int*)ws;
-    a.ws_part = (float*)ws + B;
-    const long long items = (long long)B * a.nchunk;
-    const int g = (int)(items < 4LL * lvae_num_sms() ? items : 4LL * lvae_num_sms());
-    const size_t smem = (size_t)SG_STAGES * 2 * SG_BLK;
-    static bool attr = false;
-    if (!attr) {
-      cudaFuncSetAttribute(stoch_fwd_staged_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      cudaFuncSetAttribute(stoch_fwd_staged_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      attr = true;
-    }
-    if (eps) lvae_launch(stoch_fwd_staged_kernel<false>, g, ST_THREADS, smem, stream, a);
-    else lvae_launch(stoch_fwd_staged_kernel<true>, g, ST_THREADS, smem, stream, a);
-    LVAE_COUNT_LAUNCH();
-    LVAE_CHECK_LAUNCH("stoch_fwd (staged)");
-    return LVAE_OK;
   }
   dim3 grid(a.nchunk, B);
   const bool train = q && !eps && !forced && !use_mode;

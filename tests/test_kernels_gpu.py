@@ -285,8 +285,7 @@ def test_kl_bookkeeping(L, Lr, B, fb):
 def test_stochastic_core_with_philox_noise(L, B, hw, broadcast):
     """The training path draws eps inside the kernel (Philox), so it cannot be fed the oracle's eps: instead the noise is
     recovered from the sample, eps = (z - mu_q) / sigma_q, and every other output (log p, log q, Monte-Carlo KL, analytic KL
-    per pixel, the bf16 copy of z) is checked against the fp64 closed forms for THAT noise.  Covers the staged, persistent
-    kernel (>= 64 pixels per sample) and the plain one."""
+    per pixel, the bf16 copy of z) is checked against the fp64 closed forms for THAT noise.  Covers one and several CTAs per sample and the batch-broadcast prior."""
     from oracle import lvae_oracle as O
     from lvae_b200 import ops
     Z = 32
@@ -299,7 +298,8 @@ def test_stochastic_core_with_philox_noise(L, B, hw, broadcast):
     pm, pl = p.chunk(2, 1)
     z = zz.double().cpu()
     eps = (z - qm) / (ql / 2).exp()
-    assert abs(float(eps.mean())) < 0.05 and abs(float(eps.std()) - 1) < 0.05       # it IS standard normal noise
+    if eps.numel() >= 20000:
+        assert abs(float(eps.mean())) < 0.03 and abs(float(eps.std()) - 1) < 0.03   # it IS standard normal noise
     logp = O.normal_log_prob(z, pm, pl).sum((1, 2, 3))
     logq = O.normal_log_prob(z, qm, ql).sum((1, 2, 3))
     assert rel_err(lpo, logp) < TOL and rel_err(lqo, logq) < 5 * TOL      # log q from the recovered eps: (z - mu) / sigma rounding
