@@ -231,9 +231,7 @@ class TrainEngine:
         self._beta = torch.tensor(float(beta_kl), dtype=torch.float32, device=dev)
         self._lr, self._wd, self._beta_kl = float(lr), float(weight_decay), float(beta_kl)
         if self.world > 1:
-            # replicas must not share eps / Dropout2d masks: every rank draws from its own Philox key
-            st = ops.rng_state(dev)
-            st[0] = (int(st[0]) ^ ((self.rank * 0x9E3779B97F4A7C15) & 0x7FFFFFFFFFFFFFFF))
+            ops.fold_rank(self.rank)        # replicas must not share eps / Dropout2d masks: one Philox key per rank
         self.exp_avg = torch.zeros_like(self.arena.flat)
         self.exp_inf = torch.zeros_like(self.arena.flat)
         self.step_count = torch.zeros((), dtype=torch.int64, device=dev)
@@ -524,7 +522,7 @@ class IWEvaluator:
         """This rank's share of the K-sample bound for one image batch: (B,2) running (max, sum-exp) of ll - kl over the
         samples shard_samples() assigns to this rank."""
         k_start, k_local = shard_samples(k_total, self.rank, self.world)
-        with torch.no_grad():
+        with torch.no_grad(), ops.shared_key():
             self.x.copy_(x, non_blocking=True)
             self._reset()
             if self.use_graph and self.graph is None:

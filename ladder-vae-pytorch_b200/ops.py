@@ -63,6 +63,7 @@ class _Rng(threading.local):
         self.state = {}        # device index -> int64[2] tensor (seed, offset)
         self.seed = None
         self.stream_id = 0
+        self.rank = 0          # folded into the Philox key (data-parallel replicas must not share noise)
 
 
 _rng = _Rng()
@@ -74,14 +75,39 @@ def manual_seed(seed: int) -> None:
     _rng.stream_id = 0
 
 
+def _philox_key() -> int:
+    base = _rng.seed if _rng.seed is not None else (torch.initial_seed() & 0x7FFFFFFFFFFFFFFF)
+    return (base ^ ((_rng.rank * 0x9E3779B97F4A7C15) & 0x7FFFFFFFFFFFFFFF)) & 0x7FFFFFFFFFFFFFFF
+
+
 def rng_state(device) -> torch.Tensor:
     idx = device.index if device.index is not None else torch.cuda.current_device()
     st = _rng.state.get(idx)
     if st is None:
-        seed = _rng.seed if _rng.seed is not None else (torch.initial_seed() & 0x7FFFFFFFFFFFFFFF)
-        st = torch.tensor([seed, 0], dtype=torch.int64, device=torch.device("cuda", idx))
+        st = torch.tensor([_philox_key(), 0], dtype=torch.int64, device=torch.device("cuda", idx))
         _rng.state[idx] = st
     return st
+
+
+def fold_rank(rank: int) -> None:
+    """Give this process its own Philox key (seed ^ f(rank)); idempotent, keeps the offsets of existing states."""
+    if int(rank) == _rng.rank:
+        return
+    _rng.rank = int(rank)
+    for st in _rng.state.values():
+        st[0:1].fill_(_philox_key())
+
+
+@contextmanager
+def shared_key():
+    """Temporarily the SAME Philox key on every rank (the importance-weighted evaluator numbers its samples globally: sample k
+    of a batch is (key, offset k) on whichever rank computes it); the per-rank key of a training engine comes back after."""
+    rank = _rng.rank
+    fold_rank(0)
+    try:
+        yield
+    finally:
+        fold_rank(rank)
 
 
 def next_stream_id() -> int:
