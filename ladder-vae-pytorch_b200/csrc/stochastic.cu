@@ -12,6 +12,7 @@
 //  * grid = (pixel chunks, samples) instead of one CTA per sample, so that small batches of large latents (CelebA: 64 x
 //    32x32) still fill 148 SMs; the per-sample sums of a multi-chunk launch are combined by the LAST CTA of each sample
 //    in chunk order (deterministic: no floating-point atomics), through a caller-provided workspace;
+//  * the hot case (Z = 32, q present, reparameterised sample) has its own software-pipelined kernel (stoch_fwd_z32_kernel);
 //  * 4 MUFU per latent element instead of ~275 instructions: sigma_q = ex2(lv_q * log2e/2), 1/sigma_p^2 = ex2(-lv_p *
 //    log2e), the variance ratio is sigma_q^2 / sigma_p^2 (no third exponential, no divisions), log sigma = lv/2 (the
 //    reference's log(exp(lv/2)) round trip, stochastic.py:45-46, differs from it by <= 1 ulp), log q(z) of a reparameterised
@@ -65,13 +66,11 @@ struct StochArgs {
 
 constexpr int ST_THREADS = 256;
 
-// TRAIN = the training / IW-evaluation case (q present, Philox noise, no forced latent, no mode): a template flag so that
-// the hot instantiation carries none of the other cases' branches and fits 64 registers (4 CTAs per SM; the generic one
-// needed 112 and ran at a quarter of the occupancy).
-// ZC = 32 (the reference's z_dims, README.md:175-196) makes the lane-group geometry compile-time constants (0 = generic).
-template <int VEC, bool TRAIN, int ZC>
+// Generic kernel: any Z, forced latent / mode / sampling from the prior.  TRAIN = q present, Philox noise, no forced latent, no
+// mode: a template flag so that this instantiation carries none of the other cases' branches and fits 64 registers (4 CTAs
+// per SM; the all-cases one needs 112).
+template <int VEC, bool TRAIN>
 __global__ void __launch_bounds__(ST_THREADS, TRAIN ? 4 : 2) stoch_fwd_kernel(StochArgs a) {
-  if (ZC) a.Z = ZC;
   pdl_wait();
   pdl_launch();
   __shared__ float red[3][ST_THREADS / 32];
@@ -80,8 +79,7 @@ __global__ void __launch_bounds__(ST_THREADS, TRAIN ? 4 : 2) stoch_fwd_kernel(St
   const int b = blockIdx.y;
   const int ZV = a.Z / VEC;
   int G = 1;
-  if (ZC) G = ZC / VEC;                   // 8 lanes per pixel for Z = 32
-  else while (G < ZV && G < 32) G <<= 1;
+  while (G < ZV && G < 32) G <<= 1;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = ST_THREADS >> 5;
   const int ppw = 32 / G;                 // pixels per warp per iteration
   const int gl = lane % G, gp = lane / G;
@@ -360,12 +358,11 @@ LVAE_API int lvae_stoch_fwd(const float* q, const float* p, int p_broadcast, con
     a.ws_cnt = (unsigned int*)ws;
     a.ws_part = (float*)ws + B;
   }
-  // hot case: Z = 32, q present, reparameterised sample -> the software-pipelined kernel, PASSES pixels per thread
-  static int passes_env = -1;
-  if (passes_env < 0) { const char* e = getenv("LVAE_STOCH_PASSES"); passes_env = e ? atoi(e) : 2; }
-  if (passes_env && q && !forced && !use_mode && Z == 32) {
+  // hot case: Z = 32, q present, reparameterised sample -> the software-pipelined kernel, PASSES pixels per thread.  Measured
+  // at batch 256 (us, 16x16 / 8x8): generic 17.1 / 5.9, PASSES 1: 15.2 / 5.7, 2: 13.3 / 4.6, 4: 12.3 / 5.0
+  if (q && !forced && !use_mode && Z == 32) {
     const int ppp = ST_THREADS / 8;
-    int passes = passes_env;
+    int passes = hw >= 8 * ppp ? 4 : (hw >= 2 * ppp ? 2 : 1);
     if (!ws || hw <= ppp) passes = (hw + ppp - 1) / ppp;             // one CTA per sample
     if (passes != 1 && passes != 2 && passes != 4) passes = passes > 4 ? 0 : (passes == 3 ? 4 : passes);
     if (passes && (hw + ppp * passes - 1) / (ppp * passes) <= 64 && (ws || hw <= ppp * passes)) {
@@ -384,10 +381,9 @@ LVAE_API int lvae_stoch_fwd(const float* q, const float* p, int p_broadcast, con
   }
   dim3 grid(a.nchunk, B);
   const bool train = q && !eps && !forced && !use_mode;
-  if (vec == 4 && train && Z == 32) lvae_launch(stoch_fwd_kernel<4, true, 32>, grid, ST_THREADS, 0, stream, a);
-  else if (vec == 4 && train) lvae_launch(stoch_fwd_kernel<4, true, 0>, grid, ST_THREADS, 0, stream, a);
-  else if (vec == 4) lvae_launch(stoch_fwd_kernel<4, false, 0>, grid, ST_THREADS, 0, stream, a);
-  else lvae_launch(stoch_fwd_kernel<1, false, 0>, grid, ST_THREADS, 0, stream, a);
+  if (vec == 4 && train) lvae_launch(stoch_fwd_kernel<4, true>, grid, ST_THREADS, 0, stream, a);
+  else if (vec == 4) lvae_launch(stoch_fwd_kernel<4, false>, grid, ST_THREADS, 0, stream, a);
+  else lvae_launch(stoch_fwd_kernel<1, false>, grid, ST_THREADS, 0, stream, a);
   LVAE_COUNT_LAUNCH();
   LVAE_CHECK_LAUNCH("stoch_fwd");
   return LVAE_OK;
