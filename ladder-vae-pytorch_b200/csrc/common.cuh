@@ -105,6 +105,14 @@ template <bool FAST> __device__ __forceinline__ float sigmoid_t(float v) {
   return FAST ? __fdividef(1.f, 1.f + ex2_approx(-1.4426950408889634f * v)) : 1.f / (1.f + expf(-v));
 }
 __device__ __forceinline__ float sigmoidf_(float v) { return sigmoid_t<false>(v); }
+// ONE MUFU instead of two (ex2 + rcp): sigmoid(v) = 0.5 tanh(v / 2) + 0.5 on tanh.approx (relative error 2^-11, i.e. an absolute
+// error <= 2.5e-4 on the gate value -- below the 2^-9 rounding of the bf16 tensor it is multiplied into).  For the gate passes of
+// the bf16 convolution epilogues, whose 128 x 64 sigmoids + ELUs per tile make them MUFU-bound.
+__device__ __forceinline__ float sigmoid_tanh_approx(float v) {
+  float t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(0.5f * v));
+  return fmaf(t, 0.5f, 0.5f);
+}
 // torch softplus (beta 1, threshold 20)
 __device__ __forceinline__ float softplusf_(float v) { return v > 20.f ? v : log1pf(expf(v)); }
 

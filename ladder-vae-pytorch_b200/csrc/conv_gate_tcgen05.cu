@@ -428,8 +428,8 @@ conv_gate_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           const float a0 = __uint_as_float(ua << 16), a1 = __uint_as_float(ua & 0xFFFF0000u);
           const float s0 = __uint_as_float(ug << 16), s1 = __uint_as_float(ug & 0xFFFF0000u);
           const float x0 = __uint_as_float(xq[i] << 16), x1 = __uint_as_float(xq[i] & 0xFFFF0000u);
-          const float o0 = fmaf(act_fwd_t<true>(a0, p.gate_act), sigmoid_t<true>(s0), x0);
-          const float o1 = fmaf(act_fwd_t<true>(a1, p.gate_act), sigmoid_t<true>(s1), x1);
+          const float o0 = fmaf(act_fwd_t<true>(a0, p.gate_act), sigmoid_tanh_approx(s0), x0);
+          const float o1 = fmaf(act_fwd_t<true>(a1, p.gate_act), sigmoid_tanh_approx(s1), x1);
           const __nv_bfloat162 ob = __floats2bfloat162_rn(o0, o1);
           const uint32_t uo = *reinterpret_cast<const uint32_t*>(&ob);
           *reinterpret_cast<uint32_t*>(sC2 + pos) = uo;
