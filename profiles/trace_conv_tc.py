@@ -5,7 +5,7 @@ import torch
 import lvae_b200
 from lvae_b200 import _capi, ops
 HW = int(os.environ.get("HW", "32"))
-B, C, N, k = 256, 64, 64, 3
+B, C, N, k = int(os.environ.get("B", "256")), 64, 64, 3
 x = torch.randn(B, HW, HW, C, device="cuda").to(torch.bfloat16)
 y = torch.empty(B, HW, HW, N, device="cuda", dtype=torch.bfloat16)
 w = torch.randn(N, C, k, k, device="cuda") / 24
