@@ -315,6 +315,23 @@ __global__ void __launch_bounds__(WG_THREADS) conv_wgrad_kernel(WgradArgs a) {
   if (VEC) {
     tapv = kk / I; civ = kk - tapv * I; kyv = tapv / a.kw; kxv = tapv - kyv * a.kw;
   }
+  // scalar path (channel counts that are not a multiple of 4: the 3-channel stem, whose weight gradient closes the backward
+  // pass): the (ky, kx, ci) of this thread's four k are fixed over the whole pixel loop too -- decoded once, not per element
+  int ky4[4] = {0, 0, 0, 0}, kx4[4] = {0, 0, 0, 0}, ci4[4] = {0, 0, 0, 0};
+  if (!VEC) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int k = kk + j;
+      if (k < K) {
+        const int tap = k / I;
+        ci4[j] = k - tap * I;
+        ky4[j] = tap / a.kw;
+        kx4[j] = tap - ky4[j] * a.kw;
+      } else {
+        ci4[j] = -1;
+      }
+    }
+  }
   const int tk = t >> 4, tn = t & 15;
   float acc[4][4];
 #pragma unroll
@@ -365,17 +382,16 @@ __global__ void __launch_bounds__(WG_THREADS) conv_wgrad_kernel(WgradArgs a) {
           }
         } else {
           float tmp[4] = {0.f, 0.f, 0.f, 0.f};
+          const int iy0 = oy * a.stride - a.pad, ix0 = ox * a.stride - a.pad;
+#pragma unroll
           for (int j = 0; j < 4; ++j) {
-            int k = kk + j;
-            if (k < K) {
-              int tap = k / I, ci = k - tap * I, ky = tap / a.kw, kx = tap - ky * a.kw;
-              int iy = oy * a.stride - a.pad + ky, ix = ox * a.stride - a.pad + kx;
-              if (iy >= 0 && iy < a.Hi && ix >= 0 && ix < a.Wi) {
-                long long pix = ((long long)b * a.Hi + iy) * a.Wi + ix;
-                float v = ci < a.C1 ? ld1<T>(u + pix * a.C1 + ci) : ld1<T>(u2 + pix * a.C2 + (ci - a.C1));
-                if (a.in_scale) v *= a.in_scale[(long long)b * I + ci];
-                tmp[j] = v;
-              }
+            const int ci = ci4[j];
+            const int iy = iy0 + ky4[j], ix = ix0 + kx4[j];
+            if (ci >= 0 && iy >= 0 && iy < a.Hi && ix >= 0 && ix < a.Wi) {
+              const long long pix = ((long long)b * a.Hi + iy) * a.Wi + ix;
+              float v = ci < a.C1 ? ld1<T>(u + pix * a.C1 + ci) : ld1<T>(u2 + pix * a.C2 + (ci - a.C1));
+              if (a.in_scale) v *= a.in_scale[(long long)b * I + ci];
+              tmp[j] = v;
             }
           }
           va = make_float4(tmp[0], tmp[1], tmp[2], tmp[3]);
