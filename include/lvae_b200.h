@@ -78,6 +78,16 @@ long long lvae_wgrad_tc_workspace(int B, int H, int W, int N, int ksize, int two
 long long lvae_wgrad_tc_packed_size(int N, int ksize, int two_inputs);
 int lvae_conv2d_wgrad_tc_acc(const void* x, const void* x2, const void* dy, float* gp, int B, int H, int W, int N,
                              int ksize, int dyC, int dy_c0, lvae_stream_t stream);
+/* Weight gradient of the stride-2 3x3 64 -> 64 resampling convolutions (models/lvae_layers.py:261-276) on the same kernel:
+ * the tap-shifted operand xs (B,2Hg,2Wg,64) bf16 is read through an element-strided tensor map, c (B,Hg,Wg,64) bf16 lives
+ * on the small grid.  Conv2d(stride 2, pad 1): xs = input, c = dY (masked), dw (Cout,Cin,3,3), dbias = column sums of dY.
+ * ConvTranspose2d(stride 2, pad 1, output_padding 1): xs = dY (masked), c = input, dw (Cin,Cout,3,3), dbias must be NULL
+ * (its bias gradient sums the LARGE grid: lvae_colsum).  _acc adds into a packed buffer of
+ * lvae_wgrad_tc_packed_size(64, 3, 0) floats (unpack descriptor: N = 64, ksize = 3, one input); the one-call form
+ * takes such a buffer as scratch (ws) and adds into dw / dbias. */
+int lvae_conv2d_wgrad_tc_s2_acc(const void* xs, const void* c, float* gp, int B, int Hg, int Wg, lvae_stream_t stream);
+int lvae_conv2d_wgrad_tc_s2(const void* xs, const void* c, float* dw, float* dbias, float* ws, int B, int Hg, int Wg,
+                            lvae_stream_t stream);
 int lvae_wgrad_unpack_desc_size(void);
 int lvae_wgrad_unpack_desc(void* desc_host, const float* gp, float* dw, float* dbias, int N, int ksize, int two_inputs,
                            int I_real, int N_real, int clear);

@@ -29,6 +29,8 @@ _SIGNATURES = {
     "lvae_channel_scale": [P, P, P, I, I, I, I, P],
     "lvae_conv2d_wgrad_tc": [P, P, P, P, P, P, I, I, I, I, I, I, I, I, I, P],
     "lvae_conv2d_wgrad_tc_acc": [P, P, P, P, I, I, I, I, I, I, I, P],
+    "lvae_conv2d_wgrad_tc_s2_acc": [P, P, P, I, I, I, P],
+    "lvae_conv2d_wgrad_tc_s2": [P, P, P, P, P, I, I, I, P],
     "lvae_wgrad_unpack_desc": [P, P, P, P, I, I, I, I, I, I],
     "lvae_wgrad_unpack_batched": [P, I, I, P],
     "lvae_colsum": [P, P, P, I, I, I, I, P],

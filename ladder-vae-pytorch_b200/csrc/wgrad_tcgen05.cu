@@ -38,6 +38,9 @@ struct WgParams {
   // halo mode (3x3, one input, N = 64, W % 8 == 0, H % 16 == 0): pixel tiles are 16 rows x 8 columns and ONE TMA box of
   // 18 rows x 16 columns serves all nine taps (shifted MN-major descriptors, SBO = one 16-pixel image row = 2048 B)
   int halo, tiles_x, tiles_per_img;
+  // stride-2 convolutions (lvae_conv2d_wgrad_tc_s2*): the shifted operand lives on the grid of twice the size and its tensor
+  // map traverses it with element stride 2; a tile's pixel coordinates are multiplied by in_stride before the tap offset is added
+  int in_stride;
 
   // A-block table: 2 per pair.  src: 0 = x, 1 = x2, 2 = ones tile, 3 = unused (zero rows, never read back)
   int8_t a_src[2 * WG_MAX_PAIRS], a_dx[2 * WG_MAX_PAIRS], a_dy[2 * WG_MAX_PAIRS];
@@ -198,7 +201,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
               int src = p.a_src[2 * pr + h];
               if (src < 2)
                 tma_load_4d(smem_u32(sPair + (ps * 2 + h) * WG_BLK_BYTES), src ? &tmX2 : &tmX, BAR(ps), 0,
-                            w0 + p.a_dx[2 * pr + h], h0 + p.a_dy[2 * pr + h], n0);
+                            w0 * p.in_stride + p.a_dx[2 * pr + h], h0 * p.in_stride + p.a_dy[2 * pr + h], n0);
             }
           }
           __syncwarp();
@@ -447,11 +450,11 @@ EncodeTiledFn wg_get_encode() {
   return fn;
 }
 
-int make_act_map(EncodeTiledFn enc, CUtensorMap* tm, const void* ptr, int B, int H, int W, int C, int bw, int bh, int bn) {
+int make_act_map(EncodeTiledFn enc, CUtensorMap* tm, const void* ptr, int B, int H, int W, int C, int bw, int bh, int bn, int st = 1) {
   cuuint64_t gdim[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
   cuuint64_t gstr[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
-  cuuint32_t box[4] = {64, (cuuint32_t)bw, (cuuint32_t)bh, (cuuint32_t)bn};
-  cuuint32_t estr[4] = {1, 1, 1, 1};
+  cuuint32_t box[4] = {64, (cuuint32_t)(bw * st), (cuuint32_t)(bh * st), (cuuint32_t)bn};
+  cuuint32_t estr[4] = {1, (cuuint32_t)st, (cuuint32_t)st, 1};
   return (int)enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, (void*)ptr, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
 }
@@ -480,8 +483,25 @@ LVAE_API long long lvae_wgrad_tc_workspace(int B, int H, int W, int N, int ksize
 
 // Gp += wgrad.  x, x2: (B,H,W,64) bf16 (x2 optional); dY: (B,H,W,dyC) bf16 (dyC = 0 means N), already multiplied by any
 // Dropout2d mask; this launch uses its channels [dy_c0, dy_c0 + N), N in {64, 128}.  gp: lvae_wgrad_tc_packed_size floats.
+static int wgrad_tc_acc_impl(const void* x, const void* x2, const void* dy, float* gp, int B, int H, int W, int N,
+                             int ksize, int dyC, int dy_c0, int in_stride, cudaStream_t stream);
+
 LVAE_API int lvae_conv2d_wgrad_tc_acc(const void* x, const void* x2, const void* dy, float* gp, int B, int H, int W, int N,
                                       int ksize, int dyC, int dy_c0, cudaStream_t stream) {
+  return wgrad_tc_acc_impl(x, x2, dy, gp, B, H, W, N, ksize, dyC, dy_c0, 1, stream);
+}
+
+// Stride-2 3x3 convolutions 64 -> 64 (models/lvae_layers.py:261-276), Gp += sum over the (B,Hg,Wg) grid of
+//   xs[b, 2gy-1+ky, 2gx-1+kx, row] * c[b, gy, gx, col]      xs: (B,2Hg,2Wg,64) bf16, c: (B,Hg,Wg,64) bf16
+// Conv2d(stride 2, pad 1): xs = the input, c = dY -> rows = input channel, columns = output channel, ones row = bias gradient.
+// ConvTranspose2d(stride 2, pad 1, output_padding 1): xs = dY, c = the input -> rows = OUTPUT channel, columns = input
+// channel, which is the (Cin, Cout, 3, 3) layout of its weight under the same unpack formula (the ones row is then unused).
+LVAE_API int lvae_conv2d_wgrad_tc_s2_acc(const void* xs, const void* c, float* gp, int B, int Hg, int Wg, cudaStream_t stream) {
+  return wgrad_tc_acc_impl(xs, nullptr, c, gp, B, Hg, Wg, 64, 3, 64, 0, 2, stream);
+}
+
+static int wgrad_tc_acc_impl(const void* x, const void* x2, const void* dy, float* gp, int B, int H, int W, int N,
+                             int ksize, int dyC, int dy_c0, int in_stride, cudaStream_t stream) {
   LVAE_REQUIRE(x && dy && gp, "conv2d_wgrad_tc: null pointer");
   LVAE_REQUIRE((N == 64 || N == 128) && (ksize == 1 || ksize == 3), "conv2d_wgrad_tc: N must be 64 or 128, ksize 1 or 3");
   LVAE_REQUIRE((W & (W - 1)) == 0 && (H & (H - 1)) == 0 && W <= 128, "conv2d_wgrad_tc: H and W must be powers of two (W <= 128)");
@@ -505,7 +525,8 @@ LVAE_API int lvae_conv2d_wgrad_tc_acc(const void* x, const void* x2, const void*
   p.M_total = B * H * W; p.H = H; p.W = W;
   static int halo_env = -1;
   if (halo_env < 0) { const char* e = getenv("LVAE_WGRAD_HALO"); halo_env = e ? atoi(e) : 1; }
-  p.halo = (halo_env && ksize == 3 && !x2 && N == 64 && W % 8 == 0 && H % 16 == 0) ? 1 : 0;
+  p.in_stride = in_stride;
+  p.halo = (halo_env && in_stride == 1 && ksize == 3 && !x2 && N == 64 && W % 8 == 0 && H % 16 == 0) ? 1 : 0;
   p.tiles_x = W / 8;
   p.tiles_per_img = (W / 8) * (H / 16);
   const int n_tiles = p.halo ? B * p.tiles_per_img : (p.M_total + WG_TILE - 1) / WG_TILE;
@@ -525,7 +546,8 @@ LVAE_API int lvae_conv2d_wgrad_tc_acc(const void* x, const void* x2, const void*
   int bn = WG_TILE / (bw * bh);
   if (p.halo) { bw = 8; bh = 16; bn = 1; }
   CUtensorMap tmX, tmX2, tmDY, tmGp;
-  int r = p.halo ? make_act_map(enc, &tmX, x, B, H, W, 64, 16, 18, 1) : make_act_map(enc, &tmX, x, B, H, W, 64, bw, bh, bn);
+  int r = p.halo ? make_act_map(enc, &tmX, x, B, H, W, 64, 16, 18, 1)
+                 : make_act_map(enc, &tmX, x, B, H * in_stride, W * in_stride, 64, bw, bh, bn, in_stride);
   if (!r) r = make_act_map(enc, &tmX2, x2 ? x2 : x, B, H, W, 64, bw, bh, bn);
   if (dyC <= 0) dyC = N;
   LVAE_REQUIRE(dy_c0 % 64 == 0 && dy_c0 + N <= dyC, "conv2d_wgrad_tc: bad dY channel window");
@@ -568,6 +590,24 @@ LVAE_API int lvae_wgrad_unpack_desc(void* desc_host, const float* gp, float* dw,
 LVAE_API int lvae_wgrad_unpack_batched(const void* desc_dev, int n, int max_n_real, cudaStream_t stream) {
   LVAE_REQUIRE(desc_dev && n > 0 && max_n_real > 0, "wgrad_unpack_batched: bad args");
   lvae_launch(wgrad_unpack_kernel, dim3(cdiv(max_n_real, UNPACK_CO), n), 256, 0, stream, (const UnpackDesc*)desc_dev);
+  LVAE_COUNT_LAUNCH();
+  LVAE_CHECK_LAUNCH("wgrad_unpack");
+  return LVAE_OK;
+}
+
+// One-call form of the stride-2 gradient: dw (64, 64, 3, 3) fp32 += unpack(Gp) (see lvae_conv2d_wgrad_tc_s2_acc for the two operand
+// orders), dbias [64] += column sums of c, or NULL.  ws: lvae_wgrad_tc_packed_size(64, 3, 0) floats, overwritten.
+LVAE_API int lvae_conv2d_wgrad_tc_s2(const void* xs, const void* c, float* dw, float* dbias, float* ws, int B, int Hg, int Wg,
+                                     cudaStream_t stream) {
+  LVAE_REQUIRE(xs && c && dw && ws, "conv2d_wgrad_tc_s2: null pointer");
+  const long long n = lvae_wgrad_tc_packed_size(64, 3, 0);
+  cudaError_t e = cudaMemsetAsync(ws, 0, (size_t)n * 4, stream);
+  if (e != cudaSuccess) { lvae_set_error("conv2d_wgrad_tc_s2: memset failed: %s", cudaGetErrorString(e)); return LVAE_ERR_CUDA; }
+  int rc = lvae_conv2d_wgrad_tc_s2_acc(xs, c, ws, B, Hg, Wg, stream);
+  if (rc) return rc;
+  UnpackDesc d;
+  fill_unpack_desc(&d, ws, dw, dbias, 64, 3, 1, 64, 64, 0);
+  lvae_launch(wgrad_unpack_one_kernel, dim3(cdiv(d.N_real, UNPACK_CO), 1), 256, 0, stream, d);
   LVAE_COUNT_LAUNCH();
   LVAE_CHECK_LAUNCH("wgrad_unpack");
   return LVAE_OK;

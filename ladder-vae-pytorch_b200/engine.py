@@ -137,7 +137,16 @@ class PackedGradArena:
             if isinstance(m, (Conv2d, ConvTranspose2d)):
                 sp = m.spec
                 w = m.weight
-                if not (w.requires_grad and hasattr(w, "_lvae_grad_sink") and sp.tc_shape and sp.cout in (64, 128)):
+                if not (w.requires_grad and hasattr(w, "_lvae_grad_sink")):
+                    continue
+                if sp.s2_shape and ops._s2_wgrad_enabled[0]:
+                    # stride-2 resampling convs (lvae_conv2d_wgrad_tc_s2_acc): same packed layout as a 3x3 64 -> 64 conv.  A
+                    # ConvTranspose2d's bias gradient sums the large grid (lvae_colsum), not the packed ones-row.
+                    n = int(lib.lvae_wgrad_tc_packed_size(64, 3, 0))
+                    if m.bias is None or hasattr(m.bias, "_lvae_grad_sink"):
+                        convs.append((m, False, n))
+                    continue
+                if not (sp.tc_shape and sp.cout in (64, 128)):
                     continue
                 two = sp.cin == 128 and sp.k == 1
                 if not (sp.cin <= 64 or two):
@@ -158,7 +167,7 @@ class PackedGradArena:
             off += n
             m.weight._lvae_gp = gp
             m.weight._lvae_gp_id = i
-            bias_sink = m.bias._lvae_grad_sink if m.bias is not None else None
+            bias_sink = m.bias._lvae_grad_sink if (m.bias is not None and not m.spec.transposed) else None
             call("lvae_wgrad_unpack_desc", ctypes.addressof(host) + i * dsz, gp.data_ptr(), m.weight._lvae_grad_sink.data_ptr(),
                  bias_sink.data_ptr() if bias_sink is not None else None, m.spec.cout, m.spec.k, int(two), m.spec.cin,
                  m.spec.cout, 1)      # clear Gp; ADD into the arena (a generic-path fallback may have written it too)

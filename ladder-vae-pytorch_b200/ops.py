@@ -368,6 +368,7 @@ class WeightPack:
 
 _tc_enabled = [True]
 _s2_enabled = [os.environ.get("LVAE_CONV_S2_TC", "1") != "0"]
+_s2_wgrad_enabled = [os.environ.get("LVAE_WGRAD_S2_TC", "1") != "0"]     # A/B aid: stride-2 weight gradients on tcgen05
 
 
 def set_tensor_cores(flag: bool) -> None:
@@ -605,7 +606,10 @@ def conv_backward_raw(spec: ConvSpec, xn, x2n, weight, bias, out_scale, gyn, nee
     # "gather" kind onto the (smaller) x grid
     hs2, ws2 = (Hi, Wi) if spec.transposed else (Ho, Wo)
     use_s2 = need_x and x2n is None and spec.s2_shape and spec.s2_ok(gyn, hs2, ws2) and xn.dtype == torch.bfloat16 and C1 == 64
-    if (use_tc or use_s2) and out_scale is not None:
+    # ... and their weight gradients: the stride-2-shifted operand is read through an element-strided tensor map
+    use_s2w = (need_w and x2n is None and spec.s2_shape and spec.s2_ok(gyn, hs2, ws2) and xn.dtype == torch.bfloat16 and C1 == 64
+               and _s2_wgrad_enabled[0])
+    if (use_tc or use_s2 or use_s2w) and out_scale is not None:
         # TMA-fed operands never pass through registers: apply the Dropout2d mask in a separate pass
         gys = torch.empty_like(gyn)
         call("lvae_channel_scale", gyn.data_ptr(), out_scale.data_ptr(), gys.data_ptr(), B, Ho * Wo, N, _dt(gyn), _stream())
@@ -670,6 +674,18 @@ def conv_backward_raw(spec: ConvSpec, xn, x2n, weight, bias, out_scale, gyn, nee
             else:
                 call("lvae_conv2d_wgrad_tc", xn.data_ptr(), _p(x2n), gyn.data_ptr(), gwbuf.data_ptr(), _p(gbbuf),
                      _wgrad_workspace(xn.device).data_ptr(), B, Hi, Wi, N, spec.k, spec.cin if padded else 0, 0, 0, 0, _stream())
+        elif use_s2w:
+            stats["tc_wgrad"] += 1
+            big, small = (gyn, xn) if spec.transposed else (xn, gyn)
+            gp = getattr(weight, "_lvae_gp", None) if (sunk and bsunk) else None
+            if gp is not None:
+                _side["log"].setdefault(slot, []).append(weight._lvae_gp_id)
+                call("lvae_conv2d_wgrad_tc_s2_acc", big.data_ptr(), small.data_ptr(), gp.data_ptr(), B, hs2, ws2, _stream())
+            else:
+                call("lvae_conv2d_wgrad_tc_s2", big.data_ptr(), small.data_ptr(), gwbuf.data_ptr(),
+                     None if spec.transposed else _p(gbbuf), _wgrad_workspace(xn.device).data_ptr(), B, hs2, ws2, _stream())
+            if spec.transposed and gbbuf is not None:      # the bias gradient sums the large grid
+                call("lvae_colsum", gyn.data_ptr(), None, gbbuf.data_ptr(), B, Ho * Wo, N, _dt(gyn), _stream())
         elif not spec.transposed:
             stats["cc_wgrad"] += 1
             call("lvae_conv2d_wgrad", xn.data_ptr(), _p(x2n), gyn.data_ptr(), None, _p(out_scale),

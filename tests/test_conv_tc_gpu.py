@@ -161,6 +161,7 @@ def test_tc_stride2_conv_forward_backward(case):
     y.backward(gy.cuda())
     torch.cuda.synchronize()
     assert ops.stats["tc_dgrad"] == before["tc_dgrad"] + 1
+    assert ops.stats["tc_wgrad"] == before["tc_wgrad"] + 1, "stride-2 weight gradient did not take the tcgen05 path"
     assert rel_err(xd.grad.float(), xr.grad) < 6e-3
     assert rel_err(mod.weight.grad, wr.grad) < 5e-3
     assert rel_err(mod.bias.grad, br.grad) < 5e-3
