@@ -251,7 +251,9 @@ __device__ __forceinline__ void epilogue16(const uint32_t* __restrict__ r, const
 // Round-2 A/B on the B200 (profiles/ab_r02_summary.txt) retired three variants of this kernel that held parity but lost time:
 // CTA pairs on cta_group::2 (576 vs 834 TFLOP/s at 32x32), a dynamic tile scheduler (+0.15 ms / step) and a warp-transposed
 // fp32 epilogue (90 vs 51 us for the 64 -> 100 head).
-template <int FUSE>
+// ACT (FUSE 2 / 3 only): the activation of the fused BatchNorm-backward / gate pass as a compile-time constant (ACT_ELU, the
+// model default) or -1 = runtime value; a switch inside the unrolled second pass costs one jump table per element.
+template <int FUSE, int ACT = -1>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmY,
@@ -559,8 +561,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
             const float a0 = __uint_as_float(ua << 16), a1 = __uint_as_float(ua & 0xFFFF0000u);
             const float s0 = __uint_as_float(ug << 16), s1 = __uint_as_float(ug & 0xFFFF0000u);
             const float x0 = __uint_as_float(xq[i] << 16), x1 = __uint_as_float(xq[i] & 0xFFFF0000u);
-            const float o0 = fmaf(act_fwd_t<true>(a0, p.gate_act), sigmoid_tanh_approx(s0), x0);
-            const float o1 = fmaf(act_fwd_t<true>(a1, p.gate_act), sigmoid_tanh_approx(s1), x1);
+            const float o0 = fmaf(act_fwd_t<true>(a0, ACT >= 0 ? ACT : p.gate_act), sigmoid_tanh_approx(s0), x0);
+            const float o1 = fmaf(act_fwd_t<true>(a1, ACT >= 0 ? ACT : p.gate_act), sigmoid_tanh_approx(s1), x1);
             const __nv_bfloat162 ob = __floats2bfloat162_rn(o0, o1);
             const uint32_t uo = *reinterpret_cast<const uint32_t*>(&ob);
             *reinterpret_cast<uint32_t*>(sGate + pos) = uo;
@@ -590,7 +592,6 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         } else if (FUSE == 1 || FUSE == 2) {
           // second pass over the staged tile (values as stored, bf16-rounded); the TMA store only reads it concurrently
           const int nrows = p.halo ? 128 : (int)min((long long)128, p.M_total - (long long)tile * TC_BM);   // rows past the end contribute nothing
-          const bool elu = p.bnb_act == ACT_ELU;                     // the model's default: branch-free fast path
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
             const int r = ew * 16 + i;
@@ -605,14 +606,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
               const float x0 = __uint_as_float(xq[i] << 16), x1 = __uint_as_float(xq[i] & 0xFFFF0000u);
               const float h0 = fmaf(x0, kx0, kb0), h1 = fmaf(x1, kx1, kb1);
               const float t0 = fmaf(x0, kg0, kc0), t1 = fmaf(x1, kg1, kc1);
-              float g0, g1;
-              if (elu) {                                             // ELU' = 1 (t > 0) or exp(t)
-                g0 = y0 * (t0 > 0.f ? 1.f : ex2_approx(t0 * 1.4426950408889634f));
-                g1 = y1 * (t1 > 0.f ? 1.f : ex2_approx(t1 * 1.4426950408889634f));
-              } else {
-                g0 = y0 * act_bwd_t<true>(t0, p.bnb_act);
-                g1 = y1 * act_bwd_t<true>(t1, p.bnb_act);
-              }
+              const float g0 = y0 * act_bwd_t<true>(t0, ACT >= 0 ? ACT : p.bnb_act);
+              const float g1 = y1 * act_bwd_t<true>(t1, ACT >= 0 ? ACT : p.bnb_act);
               ra0 += g0; ra1 += g1;
               rb0 = fmaf(g0, h0, rb0); rb1 = fmaf(g1, h1, rb1);
             }
@@ -853,13 +848,17 @@ LVAE_API int lvae_conv2d_tc_ex(const void* x, const void* x2, const void* wp, co
     if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tc_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tc_kernel<2, ACT_ELU>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tc_kernel<3, ACT_ELU>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap);
     if (e != cudaSuccess) { lvae_set_error("conv2d_tc: cannot raise dynamic smem: %s", cudaGetErrorString(e)); return LVAE_ERR_CUDA; }
     attr_smem = 227 * 1024;
   }
   const int n_tiles = p.halo ? B * p.tiles_per_img : (p.M_total + TC_BM - 1) / TC_BM;
   const int grid = n_tiles < lvae_num_sms() ? n_tiles : lvae_num_sms();
-  if (p.gate_x) lvae_launch(conv_tc_kernel<3>, grid, TC_THREADS, smem, stream, tmA0, tmA1, tmW, tmY, tmY2, p);
+  if (p.gate_x && p.gate_act == ACT_ELU) lvae_launch(conv_tc_kernel<3, ACT_ELU>, grid, TC_THREADS, smem, stream, tmA0, tmA1, tmW, tmY, tmY2, p);
+  else if (p.gate_x) lvae_launch(conv_tc_kernel<3>, grid, TC_THREADS, smem, stream, tmA0, tmA1, tmW, tmY, tmY2, p);
   else if (p.stats_acc) lvae_launch(conv_tc_kernel<1>, grid, TC_THREADS, smem, stream, tmA0, tmA1, tmW, tmY, tmY2, p);
+  else if (p.bnb_acc && p.bnb_act == ACT_ELU) lvae_launch(conv_tc_kernel<2, ACT_ELU>, grid, TC_THREADS, smem, stream, tmA0, tmA1, tmW, tmY, tmY2, p);
   else if (p.bnb_acc) lvae_launch(conv_tc_kernel<2>, grid, TC_THREADS, smem, stream, tmA0, tmA1, tmW, tmY, tmY2, p);
   else lvae_launch(conv_tc_kernel<0>, grid, TC_THREADS, smem, stream, tmA0, tmA1, tmW, tmY, tmY2, p);
   LVAE_COUNT_LAUNCH();

@@ -438,11 +438,14 @@ __global__ void gate_fwd_kernel(const T* __restrict__ h, const T* __restrict__ r
   }
 }
 
-template <typename T, int V>
+// ACT >= 0: activation known at compile time (the launchers pick ACT_ELU, the model default); -1: runtime switch, which the
+// compiler turns into one jump table per element inside the unrolled loops
+template <typename T, int V, int ACT = -1>
 __global__ void gate_bwd_kernel(const T* __restrict__ dout, const T* __restrict__ h, T* __restrict__ dh,
-                                long long nvec, int C, int act) {
+                                long long nvec, int C, int act_rt) {
   pdl_wait();
   pdl_launch();
+  const int act = ACT >= 0 ? ACT : act_rt;
   const int CV = C / V;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (long long)gridDim.x * blockDim.x) {
     long long row = i / CV;
@@ -477,7 +480,8 @@ LVAE_API int lvae_gate_bwd(const void* dout, const void* h, void* dh, long long 
   LVAE_REQUIRE(dout && h && dh && P > 0 && C % 4 == 0, "gate_bwd: bad args");
   if (dtype == 1 && C % 8 == 0) {
     long long nv = P * (C / 8);
-    lvae_launch(gate_bwd_kernel<__nv_bfloat16, 8>, ew_grid(nv, 256), 256, 0, stream, (const __nv_bfloat16*)dout, (const __nv_bfloat16*)h, (__nv_bfloat16*)dh, nv, C, act);
+    if (act == ACT_ELU) lvae_launch(gate_bwd_kernel<__nv_bfloat16, 8, ACT_ELU>, ew_grid(nv, 256), 256, 0, stream, (const __nv_bfloat16*)dout, (const __nv_bfloat16*)h, (__nv_bfloat16*)dh, nv, C, act);
+    else lvae_launch(gate_bwd_kernel<__nv_bfloat16, 8>, ew_grid(nv, 256), 256, 0, stream, (const __nv_bfloat16*)dout, (const __nv_bfloat16*)h, (__nv_bfloat16*)dh, nv, C, act);
   } else {
     long long nq = P * (C / 4);
     int g = ew_grid(nq, 256);
@@ -794,14 +798,15 @@ LVAE_API int lvae_channel_scale(const void* x, const float* scale, void* y, int 
 //                (post_scale, the mask of the conv that produced x) and an optional residual add.
 // The accumulators are NOT cleared here: the model zeroes its whole BatchNorm scratch arena once per forward.
 // =========================================================================================
-template <typename TI, typename TO, int V>
+template <typename TI, typename TO, int V, int ACT = -1>
 __global__ void bn_act_fwd2_kernel(const TI* __restrict__ x, TO* __restrict__ y, const double* __restrict__ acc,
                                    const float* __restrict__ gamma, const float* __restrict__ beta,
                                    float* __restrict__ save, float* running_mean, float* running_var,
-                                   long long* nbt, long long nvec, long long P, int C, int act, int training,
+                                   long long* nbt, long long nvec, long long P, int C, int act_rt, int training,
                                    float momentum, float eps) {
   pdl_wait();
   pdl_launch();
+  const int act = ACT >= 0 ? ACT : act_rt;
   __shared__ __align__(16) float s_scale[256], s_shift[256];       // y = act(x * scale + shift), C <= 256
   const int CV = C / V;
   const long long stride = (long long)gridDim.x * blockDim.x;      // multiple of CV by construction
@@ -855,15 +860,16 @@ __global__ void bn_act_fwd2_kernel(const TI* __restrict__ x, TO* __restrict__ y,
   }
 }
 
-template <typename T, int V>
+template <typename T, int V, int ACT = -1>
 __global__ void __launch_bounds__(256, 3) bn_act_bwd2_kernel(const T* __restrict__ dy, const T* __restrict__ x, T* __restrict__ dx,
                                    const float* __restrict__ save, const float* __restrict__ gamma,
                                    const float* __restrict__ beta, const double* __restrict__ acc,
                                    float* dgamma, float* dbeta, const float* __restrict__ post_scale,
-                                   const T* __restrict__ add, long long nvec, long long P, int hw, int C, int act,
+                                   const T* __restrict__ add, long long nvec, long long P, int hw, int C, int act_rt,
                                    int training) {
   pdl_wait();
   pdl_launch();
+  const int act = ACT >= 0 ? ACT : act_rt;
   // per-channel constants live in shared memory (two float4 per channel), not in 6 x V registers per thread
   __shared__ __align__(16) float s_t[6][256];                     // mean, rstd, gamma, beta, m1, m2 (SoA: conflict-free V-wide reads)
   const int CV = C / V;
@@ -957,8 +963,12 @@ LVAE_API int lvae_bn_act_fwd2(const void* x, void* y, const double* acc, const f
   if (dtype_in == 1 && dtype_out == 1 && use_v8(1, C)) {
     long long nv = P * (C / 8);
     int g = ew_grid_aligned(nv, 256, C / 8);
-    lvae_launch(bn_act_fwd2_kernel<__nv_bfloat16, __nv_bfloat16, 8>, g, 256, 0, stream, (const __nv_bfloat16*)x, (__nv_bfloat16*)y, acc, gamma,
-        beta, save, running_mean, running_var, nbt, nv, P, C, act, training, momentum, eps);
+    if (act == ACT_ELU)
+      lvae_launch(bn_act_fwd2_kernel<__nv_bfloat16, __nv_bfloat16, 8, ACT_ELU>, g, 256, 0, stream, (const __nv_bfloat16*)x, (__nv_bfloat16*)y, acc, gamma,
+          beta, save, running_mean, running_var, nbt, nv, P, C, act, training, momentum, eps);
+    else
+      lvae_launch(bn_act_fwd2_kernel<__nv_bfloat16, __nv_bfloat16, 8>, g, 256, 0, stream, (const __nv_bfloat16*)x, (__nv_bfloat16*)y, acc, gamma,
+          beta, save, running_mean, running_var, nbt, nv, P, C, act, training, momentum, eps);
   } else {
     long long nq = P * (C / 4);
     int g = ew_grid_aligned(nq, 256, C / 4);
@@ -989,8 +999,12 @@ LVAE_API int lvae_bn_act_bwd2(const void* dy, const void* x, void* dx, const flo
   if (use_v8(dtype, C)) {
     long long nv = P * (C / 8);
     int g = ew_grid_aligned(nv, 256, C / 8);
-    lvae_launch(bn_act_bwd2_kernel<__nv_bfloat16, 8>, g, 256, 0, stream, (const __nv_bfloat16*)dy, (const __nv_bfloat16*)x, (__nv_bfloat16*)dx, save,
-        gamma, beta, acc, dgamma, dbeta, post_scale, (const __nv_bfloat16*)add, nv, P, hw, C, act, training);
+    if (act == ACT_ELU)
+      lvae_launch(bn_act_bwd2_kernel<__nv_bfloat16, 8, ACT_ELU>, g, 256, 0, stream, (const __nv_bfloat16*)dy, (const __nv_bfloat16*)x, (__nv_bfloat16*)dx, save,
+          gamma, beta, acc, dgamma, dbeta, post_scale, (const __nv_bfloat16*)add, nv, P, hw, C, act, training);
+    else
+      lvae_launch(bn_act_bwd2_kernel<__nv_bfloat16, 8>, g, 256, 0, stream, (const __nv_bfloat16*)dy, (const __nv_bfloat16*)x, (__nv_bfloat16*)dx, save,
+          gamma, beta, acc, dgamma, dbeta, post_scale, (const __nv_bfloat16*)add, nv, P, hw, C, act, training);
   } else {
     int g = ew_grid_aligned(nq, 256, C / 4);
     if (dtype == 0)
