@@ -364,8 +364,13 @@ conv_gate_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(BAR(B_A1E + buf));             // the 3x3 accumulator is free for the tile after next
-      // every TMA store of the previous tile (c2, h, out) has finished reading the staging buffers
-      if (threadIdx.x == 64) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+      // every TMA store of the previous tile (c2, h, out) has finished reading the staging buffers.  Eval fast path: the only
+      // store is `out`, staged alternately in the two (otherwise unused) h buffers, so it is enough that the store of the
+      // tile BEFORE the previous one has been read: the previous tile's store stays in flight instead of stalling this one
+      if (threadIdx.x == 64) {
+        if (!p.store_c2h && !p.stats_acc) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+        else asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+      }
       asm volatile("bar.sync 1, 256;" ::: "memory");
       {
         uint8_t* blk = sC2 + row * 128;
@@ -380,6 +385,59 @@ conv_gate_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           tma_store_4d(&tmC2, smem_u32(sC2), 0, c1, c2, c3);
           asm volatile("cp.async.bulk.commit_group;" ::: "memory");
         }
+      }
+      if (!p.store_c2h && !p.stats_acc) {
+        // ---------------- eval fast path (IW evaluator): nothing but `out` leaves the SM, so the gate is evaluated straight
+        // from the accumulator registers -- a thread's two 32-column loads are channels [32 half, 32 half + 32) of `a` and of
+        // `g` for its own pixel -- instead of staging h (2 x 16 KB) and re-reading it in a second, channel-major pass: one
+        // barrier and ~50 KB of shared-memory traffic per tile less.  Values are rounded to bf16 exactly where the staged
+        // path rounds them, so `out` is bit-identical.
+        mbar_wait(BAR(B_A2F), (uint32_t)(it & 1));
+        tc_fence_after();
+        uint32_t ra[32], rg[32];
+        tmem_ld32_nowait(lane_addr + (uint32_t)(128 + 32 * half), ra);
+        tmem_ld32_nowait(lane_addr + (uint32_t)(128 + 64 + 32 * half), rg);
+        tmem_wait_ld();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(BAR(B_A2E));                  // acc2 is free for the next tile's gate GEMM
+        uint4 xr[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+          xr[q] = valid ? __ldg(reinterpret_cast<const uint4*>(p.x_res + m * 64 + 32 * half) + q) : make_uint4(0u, 0u, 0u, 0u);
+        const float* ba = sbias + 64 + 32 * half;
+        const float* bg = sbias + 128 + 32 * half;
+        uint4 po[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const uint32_t* xw = reinterpret_cast<const uint32_t*>(&xr[q]);
+          uint32_t* ow = reinterpret_cast<uint32_t*>(&po[q]);
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const int c = 8 * q + 2 * e;
+            const __nv_bfloat162 ab = __floats2bfloat162_rn(__uint_as_float(ra[c]) + ba[c], __uint_as_float(ra[c + 1]) + ba[c + 1]);
+            const __nv_bfloat162 gb = __floats2bfloat162_rn(__uint_as_float(rg[c]) + bg[c], __uint_as_float(rg[c + 1]) + bg[c + 1]);
+            const float2 af = __bfloat1622float2(ab), gf = __bfloat1622float2(gb);
+            const float x0 = __uint_as_float(xw[e] << 16), x1 = __uint_as_float(xw[e] & 0xFFFF0000u);
+            const float o0 = fmaf(act_fwd_t<true>(af.x, gact), sigmoid_tanh_approx(gf.x), x0);
+            const float o1 = fmaf(act_fwd_t<true>(af.y, gact), sigmoid_tanh_approx(gf.y), x1);
+            const __nv_bfloat162 ob = __floats2bfloat162_rn(o0, o1);
+            ow[e] = *reinterpret_cast<const uint32_t*>(&ob);
+          }
+        }
+        uint8_t* sOutE = sH + (it & 1) * CG_TILE_BYTES;      // free since the store of tile it-2 was read (phase 1's wait)
+        {
+          uint8_t* blk = sOutE + row * 128;
+#pragma unroll
+          for (int q = 0; q < 4; ++q) *reinterpret_cast<uint4*>(blk + (((4 * half + q) ^ (row & 7)) << 4)) = po[q];
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        if (threadIdx.x == 64) {
+          tma_store_4d(&tmOut, smem_u32(sOutE), 0, c1, c2, c3);
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
+        continue;
       }
       // residual rows for the gate pass: in flight while the gate GEMM runs
       uint32_t xq[16];
