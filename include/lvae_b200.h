@@ -111,6 +111,15 @@ typedef struct {
   void* gate_out;
   int gate_act;
   int gate_skip_h;      /* eval mode: do not store h (y may then be NULL): nothing runs backward */
+  /* eval-mode BatchNorm2d + activation of the CONSUMER (lib/nn.py:84-85 in eval mode) folded into this conv (N == 64, no other
+   * fusion): y = act((conv + bias) * s + beta - mean * s), s = gamma * rsqrt(var + eps), from the running statistics.  For
+   * no_grad callers only (the IW evaluator): the pre-BatchNorm tensor is never materialised.  fold_gamma NULL = off. */
+  const float* fold_gamma;
+  const float* fold_beta;
+  const float* fold_mean;
+  const float* fold_var;
+  float fold_eps;
+  int fold_act;
 } LvaeConvFuse;
 int lvae_conv2d_tc_ex(const void* x, const void* x2, const void* wp, const float* bias, const float* out_scale,
                       const void* res, void* y, void* y2, int nsplit, int B, int H, int W, int Cin, int N, int ksize,

@@ -86,7 +86,9 @@ class ConvFuse(ctypes.Structure):
     """LvaeConvFuse of include/lvae_b200.h."""
     _fields_ = [("stats_acc", c_void_p), ("bnb_x", c_void_p), ("bnb_save", c_void_p), ("bnb_gamma", c_void_p),
                 ("bnb_beta", c_void_p), ("bnb_acc", c_void_p), ("bnb_act", c_int), ("gate_x", c_void_p),
-                ("gate_out", c_void_p), ("gate_act", c_int), ("gate_skip_h", c_int)]
+                ("gate_out", c_void_p), ("gate_act", c_int), ("gate_skip_h", c_int), ("fold_gamma", c_void_p),
+                ("fold_beta", c_void_p), ("fold_mean", c_void_p), ("fold_var", c_void_p), ("fold_eps", ctypes.c_float),
+                ("fold_act", c_int)]
 
 
 def exported_symbols():

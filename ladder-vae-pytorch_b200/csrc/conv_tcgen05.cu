@@ -58,6 +58,12 @@ struct TcParams {
   int gate_act;
   int gate_skip_h;          // eval mode: h = [a | g] is only staged for the gate pass, never stored (nothing runs backward)
   int tma_store;            // bf16 output, N % 64 == 0, no residual: epilogue stages the tile in smem and stores it with TMA
+  // eval-mode BatchNorm + activation of the CONSUMER folded into this conv's epilogue (FUSE 4, N == 64, no_grad callers):
+  // y = act((acc + bias) * s + (beta - mean * s)), s = gamma * rsqrt(var + eps) -- derived in the prologue from the running
+  // statistics, so the separate BatchNorm-apply pass (one read + one write of the tensor, one launch) disappears
+  const float* fold_gamma; const float* fold_beta; const float* fold_mean; const float* fold_var;
+  float fold_eps;
+  int fold_act;
   long long* dbg;           // optional per-tile clock64 trace of CTA 0 (profiling aid, normally null)
   int8_t dx[TC_MAX_KB], dy[TC_MAX_KB], src[TC_MAX_KB], coff[TC_MAX_KB];   // coff: channel offset / 64 inside the tensor
   // stride-2 convolutions (lvae_conv2d_tc_s2): the tile's pixel coordinates are multiplied by in_stride before the tap
@@ -245,7 +251,8 @@ __device__ __forceinline__ void epilogue16(const uint32_t* __restrict__ r, const
   }
 }
 
-// FUSE: 0 plain epilogue, 1 output statistics (stats_acc), 2 BatchNorm-backward sums (bnb_*), 3 gated residual output
+// FUSE: 0 plain epilogue, 1 output statistics (stats_acc), 2 BatchNorm-backward sums (bnb_*), 3 gated residual output, 4 eval-mode
+// BatchNorm + activation of the consumer (fold_*)
 // (+ its statistics).  A template parameter so that the plain kernel carries no accumulator registers (the 10-warp CTA
 // caps ptxas at 168 registers per thread).
 // Round-2 A/B on the B200 (profiles/ab_r02_summary.txt) retired three variants of this kernel that held parity but lost time:
@@ -304,7 +311,16 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     }
     __syncwarp();
   }
-  for (int i = threadIdx.x; i < p.Npad; i += TC_THREADS) sbias[i] = (p.bias && i < p.N) ? p.bias[i] : 0.f;
+  if (FUSE == 4) {
+    // per-channel affine of the folded BatchNorm (parameters and running statistics: written long before this launch)
+    for (int i = threadIdx.x; i < 64; i += TC_THREADS) {
+      const float sc = p.fold_gamma[i] * rsqrtf(p.fold_var[i] + p.fold_eps);
+      sred[i] = sc;
+      sbias[i] = fmaf(p.bias ? p.bias[i] : 0.f, sc, p.fold_beta[i] - p.fold_mean[i] * sc);
+    }
+  } else {
+    for (int i = threadIdx.x; i < p.Npad; i += TC_THREADS) sbias[i] = (p.bias && i < p.N) ? p.bias[i] : 0.f;
+  }
   if (warp == 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(p.tmem_cols) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -483,7 +499,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
       const float* scale_row = p.out_scale ? p.out_scale + (long long)b * p.N : nullptr;
       if (FUSE != 0 || p.tma_store) {
         // ---- TMEM -> registers (bias, Dropout2d scale, bf16 pack), release the accumulator, stage in smem, TMA store ----
-        constexpr int NCH = (FUSE == 1 || FUSE == 2) ? 1 : 2;       // fused reductions: N = 64, one chunk per thread
+        constexpr int NCH = (FUSE == 1 || FUSE == 2 || FUSE == 4) ? 1 : 2;       // fused reductions: N = 64, one chunk per thread
         uint4 packed[NCH][4];
 #pragma unroll
         for (int nch = 0; nch < NCH; ++nch) {                      // N <= 128 on this path: at most two chunks per thread
@@ -496,6 +512,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
 #pragma unroll
           for (int q = 0; q < 8; ++q) {
             const float4 b4 = *reinterpret_cast<const float4*>(sbias + c0 + 4 * q);
+            if (FUSE == 4) {
+              const float4 s4 = *reinterpret_cast<const float4*>(sred + c0 + 4 * q);
+              const int fact = ACT >= 0 ? ACT : p.fold_act;
+              f[4 * q] = act_fwd_t<true>(fmaf(__uint_as_float(r[4 * q]), s4.x, b4.x), fact);
+              f[4 * q + 1] = act_fwd_t<true>(fmaf(__uint_as_float(r[4 * q + 1]), s4.y, b4.y), fact);
+              f[4 * q + 2] = act_fwd_t<true>(fmaf(__uint_as_float(r[4 * q + 2]), s4.z, b4.z), fact);
+              f[4 * q + 3] = act_fwd_t<true>(fmaf(__uint_as_float(r[4 * q + 3]), s4.w, b4.w), fact);
+              continue;
+            }
             f[4 * q] = __uint_as_float(r[4 * q]) + b4.x; f[4 * q + 1] = __uint_as_float(r[4 * q + 1]) + b4.y;
             f[4 * q + 2] = __uint_as_float(r[4 * q + 2]) + b4.z; f[4 * q + 3] = __uint_as_float(r[4 * q + 3]) + b4.w;
             if (scale_row) {
@@ -644,7 +669,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
       if (p.dbg && blockIdx.x == 0 && warp == 2 && lane == 0) p.dbg[it * 8 + 5] = clock64();
       if (lane == 0) mbar_arrive(BAR(2 * S + 3 + buf));
     }
-    if (FUSE != 0) {
+    if (FUSE != 0 && FUSE != 4) {
       // combine the eight row groups per channel: one double atomic per channel and statistic per CTA
       sred[(0 * 8 + ew) * 64 + 2 * lane] = ra0; sred[(0 * 8 + ew) * 64 + 2 * lane + 1] = ra1;
       sred[(1 * 8 + ew) * 64 + 2 * lane] = rb0; sred[(1 * 8 + ew) * 64 + 2 * lane + 1] = rb1;
@@ -707,6 +732,12 @@ struct LvaeConvFuse {
   void* gate_out;
   int gate_act;
   int gate_skip_h;
+  const float* fold_gamma;
+  const float* fold_beta;
+  const float* fold_mean;
+  const float* fold_var;
+  float fold_eps;
+  int fold_act;
 };
 
 LVAE_API int lvae_conv2d_tc_ex(const void* x, const void* x2, const void* wp, const float* bias, const float* out_scale,
@@ -752,6 +783,13 @@ LVAE_API int lvae_conv2d_tc_ex(const void* x, const void* x2, const void* wp, co
                    "conv2d_tc: the gated-residual epilogue needs N == 128, bf16 output, no residual / split");
       p.gate_x = (const __nv_bfloat16*)fuse->gate_x; p.gate_act = fuse->gate_act; p.gate_skip_h = fuse->gate_skip_h;
     }
+    if (fuse->fold_gamma) {
+      LVAE_REQUIRE(fuse->fold_beta && fuse->fold_mean && fuse->fold_var && N == 64 && !y2 && !res && !out_f32 && !out_scale &&
+                   !p.bnb_acc && !p.stats_acc && !fuse->gate_out,
+                   "conv2d_tc: the folded eval-mode BatchNorm needs N == 64, bf16 output and no other epilogue fusion");
+      p.fold_gamma = fuse->fold_gamma; p.fold_beta = fuse->fold_beta; p.fold_mean = fuse->fold_mean; p.fold_var = fuse->fold_var;
+      p.fold_eps = fuse->fold_eps; p.fold_act = fuse->fold_act;
+    }
   }
   const int inputs = x2 ? 2 : 1;
   const int taps = ksize * ksize;
@@ -788,6 +826,7 @@ LVAE_API int lvae_conv2d_tc_ex(const void* x, const void* x2, const void* wp, co
   p.tma_store = (tst_env && !out_f32 && N % 64 == 0 && N <= 128 && !res && (!y2 || nsplit % 64 == 0)) ? 1 : 0;
   const int out_stage = p.tma_store ? (p.Npad / 64 + (p.gate_x ? 1 : 0)) * TC_STAGE_BYTES : 0;
   LVAE_REQUIRE(!p.gate_x || p.tma_store, "conv2d_tc: the gated-residual epilogue needs the TMA-store path");
+  LVAE_REQUIRE(!p.fold_gamma || p.tma_store, "conv2d_tc: the folded BatchNorm epilogue needs the TMA-store path");
   LVAE_REQUIRE(!(p.stats_acc || p.bnb_acc) || (p.tma_store && (N == 64 || p.gate_x) && !y2),
                "conv2d_tc: fused reductions need the TMA-store path (bf16 output, N == 64, no residual, no split)");
   p.halo = (halo_env && ksize == 3 && !x2 && Cin == 64 && W % 8 == 0 && H % 16 == 0 &&
@@ -850,12 +889,16 @@ LVAE_API int lvae_conv2d_tc_ex(const void* x, const void* x2, const void* wp, co
     if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tc_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tc_kernel<2, ACT_ELU>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tc_kernel<3, ACT_ELU>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tc_kernel<4, ACT_ELU>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tc_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap);
     if (e != cudaSuccess) { lvae_set_error("conv2d_tc: cannot raise dynamic smem: %s", cudaGetErrorString(e)); return LVAE_ERR_CUDA; }
     attr_smem = 227 * 1024;
   }
   const int n_tiles = p.halo ? B * p.tiles_per_img : (p.M_total + TC_BM - 1) / TC_BM;
   const int grid = n_tiles < lvae_num_sms() ? n_tiles : lvae_num_sms();
-  if (p.gate_x && p.gate_act == ACT_ELU) lvae_launch(conv_tc_kernel<3, ACT_ELU>, grid, TC_THREADS, smem, stream, tmA0, tmA1, tmW, tmY, tmY2, p);
+  if (p.fold_gamma && p.fold_act == ACT_ELU) lvae_launch(conv_tc_kernel<4, ACT_ELU>, grid, TC_THREADS, smem, stream, tmA0, tmA1, tmW, tmY, tmY2, p);
+  else if (p.fold_gamma) lvae_launch(conv_tc_kernel<4>, grid, TC_THREADS, smem, stream, tmA0, tmA1, tmW, tmY, tmY2, p);
+  else if (p.gate_x && p.gate_act == ACT_ELU) lvae_launch(conv_tc_kernel<3, ACT_ELU>, grid, TC_THREADS, smem, stream, tmA0, tmA1, tmW, tmY, tmY2, p);
   else if (p.gate_x) lvae_launch(conv_tc_kernel<3>, grid, TC_THREADS, smem, stream, tmA0, tmA1, tmW, tmY, tmY2, p);
   else if (p.stats_acc) lvae_launch(conv_tc_kernel<1>, grid, TC_THREADS, smem, stream, tmA0, tmA1, tmW, tmY, tmY2, p);
   else if (p.bnb_acc && p.bnb_act == ACT_ELU) lvae_launch(conv_tc_kernel<2, ACT_ELU>, grid, TC_THREADS, smem, stream, tmA0, tmA1, tmW, tmY, tmY2, p);

@@ -74,3 +74,78 @@ def test_conv_gate_chain_in_the_model(monkeypatch):
     assert abs(l0 - l1) <= 1e-6 * abs(l0)
     for n in g0:
         assert torch.allclose(g0[n], g1[n], rtol=1e-4, atol=1e-6), n
+
+
+@pytest.mark.parametrize("case", [(3, 16, 16, 3), (2, 32, 32, 3), (5, 8, 8, 3), (7, 4, 4, 1), (33, 2, 2, 3), (2, 16, 16, 4)])
+def test_eval_batchnorm_folded_into_conv_epilogue(case):
+    """conv_tc_kernel<4>: y = act(BN_eval(conv(x) + bias)) in ONE launch (the IW evaluator's conv1 + BatchNorm2) against the
+    conv followed by the BatchNorm-apply pass.  The two-pass route rounds the pre-BatchNorm tensor to bf16 before normalising,
+    the folded one does not, so they agree to bf16 rounding of the result, and the folded one is the closer of the two to the
+    fp32 evaluation of the same bf16 operands."""
+    import lvae_b200  # noqa: F401
+    from lvae_b200 import ops
+    from lvae_b200._capi import call
+    B, H, W, act = case
+    g = torch.Generator().manual_seed(B * 100 + H)
+    bf = torch.bfloat16
+    x = torch.randn(B, H, W, 64, generator=g).to(bf).cuda()
+    w = (torch.randn(64, 64, 3, 3, generator=g) / 24).cuda()
+    bias = torch.randn(64, generator=g).cuda()
+    gamma, beta = (torch.rand(64, generator=g) + 0.5).cuda(), torch.randn(64, generator=g).cuda()
+    mean, var = torch.randn(64, generator=g).cuda(), (torch.rand(64, generator=g) + 0.3).cuda()
+    eps = 1e-5
+    wp = ops.WeightPack(64, 64, 9, 2).get(w, bf)
+    # two passes: conv (bf16 out), then the eval-mode BatchNorm-apply kernel
+    c1 = ops._conv_tc(x, None, wp, bias, None, None, 64, 3, False, False)
+    ref = torch.empty_like(c1)
+    save = torch.empty(2, 64, device="cuda")
+    call("lvae_bn_act_fwd2", c1.data_ptr(), ref.data_ptr(), None, gamma.data_ptr(), beta.data_ptr(), save.data_ptr(),
+         mean.data_ptr(), var.data_ptr(), None, B * H * W, 64, act, 0, 0.1, eps, 1, 1, ops._stream())
+    # one launch
+    y = ops._conv_tc(x, None, wp, bias, None, None, 64, 3, False, False, fold=(gamma, beta, mean, var, eps, act))
+    # fp32 evaluation of the same bf16 operands
+    xf = x.float().permute(0, 3, 1, 2)
+    cf = torch.nn.functional.conv2d(xf, w.to(bf).float(), bias, padding=1)
+    nf = (cf - mean[None, :, None, None]) * torch.rsqrt(var + eps)[None, :, None, None] * gamma[None, :, None, None] \
+        + beta[None, :, None, None]
+    af = {1: torch.relu, 3: torch.nn.functional.elu, 4: torch.nn.functional.selu}[act](nf).permute(0, 2, 3, 1)
+    torch.cuda.synchronize()
+    err_fold = (y.float() - af).abs().max().item()
+    err_two = (ref.float() - af).abs().max().item()
+    scale = af.abs().max().item()
+    assert err_fold <= 6e-3 * scale, (err_fold, scale)            # bf16 rounding of the result (2^-9 relative) + MMA order
+    assert err_fold <= err_two * 1.05 + 1e-6, (err_fold, err_two)
+    assert (y.float() - ref.float()).abs().max().item() <= 2e-2 * scale
+
+
+def test_eval_block_with_folded_batchnorm_matches_unfolded(monkeypatch):
+    """A gated residual block in eval mode under no_grad (what the IW evaluator runs): BatchNorm2 folded into conv1's epilogue
+    against the separate BatchNorm-apply pass."""
+    import lvae_b200  # noqa: F401
+    from lvae_b200 import ops
+    from lvae_b200.lib.nn import ResidualGatedBlock
+    torch.manual_seed(3)
+    blk = ResidualGatedBlock(64, "elu", batchnorm=True, block_type="bacdbacd", dropout=0.2).cuda()
+    with torch.no_grad():
+        for m in blk.modules():
+            if hasattr(m, "running_mean") and m.running_mean is not None:
+                m.running_mean.normal_(0, 0.5)
+                m.running_var.uniform_(0.5, 2.0)
+                m.weight.uniform_(0.5, 1.5)
+                m.bias.normal_(0, 0.3)
+    blk.eval()
+    x = torch.randn(6, 16, 16, 64, device="cuda").to(torch.bfloat16).permute(0, 3, 1, 2)
+    outs = []
+    for fold in (False, True):
+        monkeypatch.setattr(ops, "_eval_bn_fold", [fold])
+        ops.stats["bn_fold"] = 0
+        with torch.no_grad():
+            outs.append(blk(x).float())
+        assert (ops.stats.get("bn_fold", 0) > 0) == fold
+    # with grad enabled (a backward may follow) the fold must stay off: the pre-BatchNorm tensor is needed
+    ops.stats["bn_fold"] = 0
+    blk(x)
+    assert ops.stats.get("bn_fold", 0) == 0
+    torch.cuda.synchronize()
+    d = (outs[0] - outs[1]).abs().max().item()
+    assert d <= 3e-2 * outs[0].abs().max().item(), d
