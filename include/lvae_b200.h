@@ -151,6 +151,8 @@ int lvae_conv3x3_narrow(const void* x, const float* w, const float* bias, void* 
                         lvae_stream_t stream);
 /* profiling aid: CTA 0 of subsequent lvae_conv2d_tc launches records clock64 stamps per tile into dev_buf (NULL = off) */
 void lvae_conv2d_tc_debug(long long* dev_buf);
+/* the same for lvae_conv_gate_tc (16 stamps per tile: epilogue phases in slots 0..6, MMA warp in 8..10) */
+void lvae_conv_gate_tc_debug(long long* dev_buf);
 /* y = x * scale[b,c] (Dropout2d mask on a gradient tensor ahead of the TMA-fed dgrad) */
 int lvae_channel_scale(const void* x, const float* scale, void* y, int B, int HW, int C, int dtype,
                        lvae_stream_t stream);

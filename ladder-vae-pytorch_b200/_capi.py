@@ -74,6 +74,7 @@ _SPECIAL = {
     "lvae_pack_desc_size": ([], c_int),
     "lvae_set_pdl": ([c_int], None),
     "lvae_conv2d_tc_debug": ([c_void_p], None),
+    "lvae_conv_gate_tc_debug": ([c_void_p], None),
     "lvae_get_pdl": ([], c_int),
     "lvae_wgrad_tc_workspace": ([I, I, I, I, I, I], c_longlong),
     "lvae_wgrad_tc_packed_size": ([I, I, I], c_longlong),

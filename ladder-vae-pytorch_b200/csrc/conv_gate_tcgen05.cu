@@ -32,9 +32,12 @@ struct CgParams {
   double* stats_acc;        // 8-way striped (sum, sum of squares) of out, or null
   int M_total, H, W;
   int n_stages, halo, stage_bytes, tiles_x, tiles_per_img;
+  int lg_w, lg_hw, lg_tx, lg_tpi;   // H, W (hence tiles_x, tiles_per_img) are powers of two: per-tile index arithmetic is shifts --
+                            // the 64-bit m / hw and the tile divisions cost ~800 cycles per tile on the epilogue's critical path
   int bw, bh, bn;           // per-tap TMA box (non-halo): bw*bh*bn == 128
   int gate_act;
   int store_c2h;            // 1: c2 and h are stored (a backward pass will read them); 0: eval, only out leaves the SM
+  long long* dbg;           // optional clock64 trace of CTA 0, 16 stamps per tile (lvae_conv_gate_tc_debug; normally null)
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -144,6 +147,7 @@ __device__ __forceinline__ void pack32(const uint32_t* r, const float* sb, const
 // inside the unrolled gate pass compiled to one jump table (LDC + BRX) per element: 34 indirect branches per tile-thread that
 // also kept the 16 iterations from overlapping (ncu, B = 1000: 1950 instructions per tile-thread, IPC 0.35 per scheduler).
 template <int ACT>
+#define CG_STAMP(slot) do { if (p.dbg && blockIdx.x == 0 && lane == 0) p.dbg[it * 16 + (slot)] = clock64(); } while (0)
 __global__ void __launch_bounds__(CG_THREADS, 1)
 conv_gate_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW2,
                     const __grid_constant__ CUtensorMap tmWg, const __grid_constant__ CUtensorMap tmC2,
@@ -258,6 +262,7 @@ conv_gate_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       mbar_wait(BAR(B_A2E), (uint32_t)((j & 1) ^ 1));        // epilogue drained acc2 of tile j-1
       mbar_wait(BAR(B_C2), (uint32_t)(j & 1));               // c2 of tile j is staged (and fenced for the async proxy)
       tc_fence_after();
+      if (p.dbg && blockIdx.x == 0 && lane == 0) p.dbg[j * 16 + 10] = clock64();
       if (elect_one()) {
         const uint64_t adesc = umma_desc_k_sw128(smem_u32(sC2));
         const uint64_t bdesc = umma_desc_k_sw128(smem_u32(sWg));
@@ -277,9 +282,11 @@ conv_gate_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       mbar_wait(BAR(B_A1E + buf), (use & 1) ^ 1);            // epilogue drained this 3x3 accumulator
       tc_fence_after();
       const uint32_t d_tmem = tmem_u + (uint32_t)(buf * 64);
+      CG_STAMP(8);
       if (p.halo) {
         mbar_wait(BAR(stage), phase);
         tc_fence_after();
+        CG_STAMP(9);
         const uint32_t a_base = smem_u32(sA + stage * stage_bytes);
         if (elect_one()) {
           for (int t = 0; t < CG_TAPS; ++t) {
@@ -330,30 +337,40 @@ conv_gate_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       const int buf = it & 1;
       const uint32_t use = (uint32_t)(it >> 1);
       // pixel of this thread's accumulator row; first pixel of the 16 staged rows this warp owns in the gate pass
-      long long m = (long long)tile * CG_BM + row;
-      long long rbase = (long long)tile * CG_BM + ew * 16;
+      int m = tile * CG_BM + row;                               // (M_total = B*H*W fits an int)
+      int rbase = tile * CG_BM + ew * 16;
       int c1, c2, c3;                                           // TMA-store coordinates of the tile
       if (p.halo) {
-        const int n0 = tile / p.tiles_per_img;
-        const int r = tile - n0 * p.tiles_per_img;
-        const int ty = r / p.tiles_x, tx = r - ty * p.tiles_x;
-        m = ((long long)n0 * p.H + ty * 16 + (row >> 3)) * p.W + tx * 8 + (row & 7);
-        rbase = ((long long)n0 * p.H + ty * 16 + ew * 2) * p.W + tx * 8;
+        const int n0 = tile >> p.lg_tpi;
+        const int r = tile & (p.tiles_per_img - 1);
+        const int ty = r >> p.lg_tx, tx = r & (p.tiles_x - 1);
+        m = (n0 * p.H + ty * 16 + (row >> 3)) * p.W + tx * 8 + (row & 7);
+        rbase = (n0 * p.H + ty * 16 + ew * 2) * p.W + tx * 8;
         c3 = n0; c2 = ty * 16; c1 = tx * 8;
       } else {
         const int p0 = tile * CG_BM;
-        c3 = p0 / hw;
-        const int rem = p0 - c3 * hw;
-        c2 = rem / p.W; c1 = rem - c2 * p.W;
+        c3 = p0 >> p.lg_hw;
+        const int rem = p0 & (hw - 1);
+        c2 = rem >> p.lg_w; c1 = rem & (p.W - 1);
       }
       const bool valid = m < p.M_total;
-      const int b = valid ? (int)(m / hw) : 0;
+      const int b = valid ? (m >> p.lg_hw) : 0;
       const float* scale_row = p.scale2 ? p.scale2 + (long long)b * 64 : nullptr;
       const uint32_t lane_addr = tmem_base + ((uint32_t)(quad * 32) << 16);
 
+      // eval fast path: this thread's half row of the residual, requested before anything of the tile is waited for (ncu: the
+      // first use of these loads, issued after the gate GEMM, was the largest single stall of the epilogue -- 20 % of its samples)
+      uint4 xr[4];
+      if (warp == 2) CG_STAMP(0);
+      if (!p.store_c2h && !p.stats_acc) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+          xr[q] = valid ? __ldg(reinterpret_cast<const uint4*>(p.x_res + (long long)m * 64 + 32 * half) + q) : make_uint4(0u, 0u, 0u, 0u);
+      }
       // ---------------- phase 1: c2 = (acc1 + bias2) * mask2 -> bf16 -> staged tile (+ TMA store) ----------------
       mbar_wait(BAR(B_A1F + buf), use & 1);
       tc_fence_after();
+      if (warp == 2) CG_STAMP(1);
       uint4 pc[4];
       {
         uint32_t r[32];
@@ -364,6 +381,7 @@ conv_gate_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(BAR(B_A1E + buf));             // the 3x3 accumulator is free for the tile after next
+      if (warp == 2) CG_STAMP(2);
       // every TMA store of the previous tile (c2, h, out) has finished reading the staging buffers.  Eval fast path: the only
       // store is `out`, staged alternately in the two (otherwise unused) h buffers, so it is enough that the store of the
       // tile BEFORE the previous one has been read: the previous tile's store stays in flight instead of stalling this one
@@ -379,6 +397,7 @@ conv_gate_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic writes -> visible to TMA and tcgen05.mma
       asm volatile("bar.sync 1, 256;" ::: "memory");
+      if (warp == 2) CG_STAMP(3);
       if (threadIdx.x == 64) {
         mbar_arrive(BAR(B_C2));                                  // the MMA warp may run the gate GEMM on the staged tile
         if (p.store_c2h) {
@@ -394,6 +413,7 @@ conv_gate_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         // path rounds them, so `out` is bit-identical.
         mbar_wait(BAR(B_A2F), (uint32_t)(it & 1));
         tc_fence_after();
+        if (warp == 2) CG_STAMP(4);
         uint32_t ra[32], rg[32];
         tmem_ld32_nowait(lane_addr + (uint32_t)(128 + 32 * half), ra);
         tmem_ld32_nowait(lane_addr + (uint32_t)(128 + 64 + 32 * half), rg);
@@ -401,10 +421,6 @@ conv_gate_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(BAR(B_A2E));                  // acc2 is free for the next tile's gate GEMM
-        uint4 xr[4];
-#pragma unroll
-        for (int q = 0; q < 4; ++q)
-          xr[q] = valid ? __ldg(reinterpret_cast<const uint4*>(p.x_res + m * 64 + 32 * half) + q) : make_uint4(0u, 0u, 0u, 0u);
         const float* ba = sbias + 64 + 32 * half;
         const float* bg = sbias + 128 + 32 * half;
         uint4 po[4];
@@ -425,6 +441,7 @@ conv_gate_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             ow[e] = *reinterpret_cast<const uint32_t*>(&ob);
           }
         }
+        if (warp == 2) CG_STAMP(5);
         uint8_t* sOutE = sH + (it & 1) * CG_TILE_BYTES;      // free since the store of tile it-2 was read (phase 1's wait)
         {
           uint8_t* blk = sOutE + row * 128;
@@ -437,12 +454,13 @@ conv_gate_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           tma_store_4d(&tmOut, smem_u32(sOutE), 0, c1, c2, c3);
           asm volatile("cp.async.bulk.commit_group;" ::: "memory");
         }
+        if (warp == 2) CG_STAMP(6);
         continue;
       }
       // residual rows for the gate pass: in flight while the gate GEMM runs
       uint32_t xq[16];
       {
-        const uint32_t* xb = reinterpret_cast<const uint32_t*>(p.x_res + rbase * 64) + lane;
+        const uint32_t* xb = reinterpret_cast<const uint32_t*>(p.x_res + (long long)rbase * 64) + lane;
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
           const int off = i + (i >> 3) * rstep;
@@ -553,7 +571,12 @@ int pow2_floor_le_cg(int v, int cap) {
   return r;
 }
 
+long long* g_cg_dbg = nullptr;
+
 }  // namespace
+
+// profiling aid: CTA 0 of subsequent lvae_conv_gate_tc launches records clock64 stamps (16 per tile) into dev_buf (NULL = off)
+LVAE_API void lvae_conv_gate_tc_debug(long long* dev_buf) { g_cg_dbg = dev_buf; }
 
 // a2, x_res, c2, out: (B,H,W,64) bf16 NHWC; h: (B,H,W,128) bf16.  w2p: nine packed [64][64] blocks (tap-major, rows = output
 // channel, lvae_pack_weights mode 2); wgp: one packed [128][64] block.  scale2: (B,64) or NULL.  c2 and h may both be NULL
@@ -572,12 +595,16 @@ LVAE_API int lvae_conv_gate_tc(const void* a2, const void* w2p, const float* bia
   p.M_total = B * H * W; p.H = H; p.W = W;
   p.gate_act = gate_act;
   p.store_c2h = c2 ? 1 : 0;
+  p.dbg = g_cg_dbg;
   static int halo_env = -1;
   if (halo_env < 0) { const char* e = getenv("LVAE_CONV_HALO"); halo_env = e ? atoi(e) : 1; }
   p.halo = (halo_env && W % 8 == 0 && H % 16 == 0) ? 1 : 0;
   p.stage_bytes = p.halo ? CG_HALO_BYTES : CG_TILE_BYTES;
   p.tiles_x = W / 8;
   p.tiles_per_img = (W / 8) * (H / 16);
+  auto lg2 = [](int v) { int l = 0; while ((1 << l) < v) ++l; return l; };
+  p.lg_w = lg2(W); p.lg_hw = lg2(H * W); p.lg_tx = lg2(p.tiles_x > 0 ? p.tiles_x : 1);
+  p.lg_tpi = lg2(p.tiles_per_img > 0 ? p.tiles_per_img : 1);
   p.bw = W;
   p.bh = pow2_floor_le_cg(H, CG_BM / p.bw);
   p.bn = CG_BM / (p.bw * p.bh);

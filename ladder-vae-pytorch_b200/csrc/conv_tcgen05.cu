@@ -46,6 +46,9 @@ struct TcParams {
   // halo mode (3x3, W % 8 == 0, H % 16 == 0): ONE TMA box of 18 rows x 16 columns per 16x8-pixel tile; the nine
   // tap operands are the same shared-memory tile read through shifted UMMA descriptors (no per-tap re-fetch)
   int halo, stage_bytes, tiles_x, tiles_per_img, bo_mode;
+  // H, W (hence tiles_x, tiles_per_img) are powers of two: the epilogue's per-tile index arithmetic is shifts and masks (the
+  // 64-bit m / hw and the tile divisions cost several hundred cycles per tile on the exposed tail of every launch)
+  int lg_w, lg_hw, lg_tx, lg_tpi;
   // reductions fused into the TMA-store epilogue (N == 64 only)
   double* stats_acc;        // += per-channel sum / sum of squares of the output as stored (next BatchNorm's statistics)
   const __nv_bfloat16* bnb_x;   // BatchNorm-backward reduction over this dgrad's output: BN input x (M,64)
@@ -459,10 +462,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     // pixel index of staged row (16 ew + i) of a tile = row_base(tile) + (halo ? (i >> 3) * W + (i & 7) : i)
     auto row_base = [&](int tile) -> long long {
       if (p.halo) {
-        int n0 = tile / p.tiles_per_img;
-        int rr = tile - n0 * p.tiles_per_img;
-        int ty = rr / p.tiles_x, tx = rr - ty * p.tiles_x;
-        return ((long long)n0 * p.H + ty * 16 + ew * 2) * p.W + tx * 8;
+        int n0 = tile >> p.lg_tpi;
+        int rr = tile & (p.tiles_per_img - 1);
+        int ty = rr >> p.lg_tx, tx = rr & (p.tiles_x - 1);
+        return (long long)((n0 * p.H + ty * 16 + ew * 2) * p.W + tx * 8);
       }
       return (long long)tile * TC_BM + ew * 16;
     };
@@ -481,12 +484,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
       const int buf = it & 1;
       const uint32_t use = (uint32_t)(it >> 1);
       if (p.dbg && blockIdx.x == 0 && warp == 2 && lane == 0) p.dbg[it * 8 + 3] = clock64();
-      long long m = (long long)tile * TC_BM + row;
+      long long m = (long long)tile * TC_BM + row;                 // (M_total = B*H*W fits an int)
       if (p.halo) {
-        int n0 = tile / p.tiles_per_img;
-        int r = tile - n0 * p.tiles_per_img;
-        int ty = r / p.tiles_x, tx = r - ty * p.tiles_x;
-        m = ((long long)n0 * p.H + ty * 16 + (row >> 3)) * p.W + tx * 8 + (row & 7);
+        int n0 = tile >> p.lg_tpi;
+        int r = tile & (p.tiles_per_img - 1);
+        int ty = r >> p.lg_tx, tx = r & (p.tiles_x - 1);
+        m = (long long)((n0 * p.H + ty * 16 + (row >> 3)) * p.W + tx * 8 + (row & 7));
       }
       const bool valid = m < p.M_total;
       const long long rbase = row_base(tile);
@@ -494,7 +497,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
       mbar_wait(BAR(2 * S + 1 + buf), use & 1);
       tc_fence_after();
       if (p.dbg && blockIdx.x == 0 && warp == 2 && lane == 0) p.dbg[it * 8 + 4] = clock64();
-      const int b = valid ? (int)(m / hw) : 0;
+      const int b = valid ? ((int)m >> p.lg_hw) : 0;
       const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * p.Npad);
       const float* scale_row = p.out_scale ? p.out_scale + (long long)b * p.N : nullptr;
       if (FUSE != 0 || p.tma_store) {
@@ -558,14 +561,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         if (threadIdx.x == 64) {
           int c1, c2, c3;
           if (p.halo) {
-            int n0 = tile / p.tiles_per_img;
-            int r2 = tile - n0 * p.tiles_per_img;
-            c3 = n0; c2 = (r2 / p.tiles_x) * 16; c1 = (r2 % p.tiles_x) * 8;
+            int n0 = tile >> p.lg_tpi;
+            int r2 = tile & (p.tiles_per_img - 1);
+            c3 = n0; c2 = (r2 >> p.lg_tx) * 16; c1 = (r2 & (p.tiles_x - 1)) * 8;
           } else {
             int p0 = tile * TC_BM;
-            c3 = p0 / hw;
-            int rem = p0 - c3 * hw;
-            c2 = rem / p.W; c1 = rem - c2 * p.W;
+            c3 = p0 >> p.lg_hw;
+            int rem = p0 & (hw - 1);
+            c2 = rem >> p.lg_w; c1 = rem & (p.W - 1);
           }
           for (int j = 0; j < p.Npad / 64 && !(FUSE == 3 && p.gate_skip_h); ++j) {
             const bool second = p.y2 != nullptr && j * 64 >= p.nsplit;
@@ -602,14 +605,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
           if (threadIdx.x == 64) {
             int c1, c2, c3;
             if (p.halo) {
-              int n0 = tile / p.tiles_per_img;
-              int r2 = tile - n0 * p.tiles_per_img;
-              c3 = n0; c2 = (r2 / p.tiles_x) * 16; c1 = (r2 % p.tiles_x) * 8;
+              int n0 = tile >> p.lg_tpi;
+              int r2 = tile & (p.tiles_per_img - 1);
+              c3 = n0; c2 = (r2 >> p.lg_tx) * 16; c1 = (r2 & (p.tiles_x - 1)) * 8;
             } else {
               int p0 = tile * TC_BM;
-              c3 = p0 / hw;
-              int rem = p0 - c3 * hw;
-              c2 = rem / p.W; c1 = rem - c2 * p.W;
+              c3 = p0 >> p.lg_hw;
+              int rem = p0 & (hw - 1);
+              c2 = rem >> p.lg_w; c1 = rem & (p.W - 1);
             }
             tma_store_4d(&tmY2, smem_u32(sGate), 0, c1, c2, c3);
             asm volatile("cp.async.bulk.commit_group;" ::: "memory");
@@ -707,6 +710,16 @@ EncodeTiledFn get_encode() {
 }
 
 long long* g_tc_dbg = nullptr;
+
+int lg2_ceil(int v) {
+  int l = 0;
+  while ((1 << l) < v) ++l;
+  return l;
+}
+void set_shifts(TcParams& p) {
+  p.lg_w = lg2_ceil(p.W); p.lg_hw = lg2_ceil(p.H * p.W);
+  p.lg_tx = lg2_ceil(p.tiles_x > 0 ? p.tiles_x : 1); p.lg_tpi = lg2_ceil(p.tiles_per_img > 0 ? p.tiles_per_img : 1);
+}
 
 int pow2_floor_le(int v, int cap) {
   int r = 1;
@@ -834,6 +847,7 @@ LVAE_API int lvae_conv2d_tc_ex(const void* x, const void* x2, const void* wp, co
   p.stage_bytes = 18 * 16 * 128;
   p.tiles_x = W / 8;
   p.tiles_per_img = (W / 8) * (H / 16);
+  set_shifts(p);
   p.bo_mode = bo_env;
   int stages = (max_smem - wbytes - out_stage) / (p.halo ? p.stage_bytes : TC_STAGE_BYTES);
   if (stages > 8) stages = 8;
@@ -999,6 +1013,7 @@ LVAE_API int lvae_conv2d_tc_s2(const void* x, const void* wp, const float* bias,
     }
     const int n_tiles = (p.M_total + TC_BM - 1) / TC_BM;
     const int grid = n_tiles < lvae_num_sms() ? n_tiles : lvae_num_sms();
+    set_shifts(p);
     lvae_launch(conv_tc_kernel<0>, grid, TC_THREADS, smem, stream, tmA, tmA, tmW, tmY, tmY2, p);
     LVAE_COUNT_LAUNCH();
     LVAE_CHECK_LAUNCH("conv2d_tc_s2");
