@@ -18,7 +18,11 @@
 
 namespace {
 
-constexpr int CG_THREADS = 320;            // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue
+// warp 0 TMA, warp 1 MMA, warps 2 .. 2 + EW - 1 epilogue.  EW = 16 (default): four warps per TMEM lane quadrant, 16 accumulator
+// columns per thread.  The epilogue of this kernel is a serial chain per tile (c2 -> gate GEMM -> gate -> store) that the clock64
+// trace (profiles/trace_conv_gate.py) shows to be latency-bound, not issue-bound: with 8 warps (two per scheduler) a tile took
+// ~4900 cycles at B = 1000 against ~2300 for its MMAs.
+constexpr int CG_EW_DEFAULT = 16;
 constexpr int CG_BM = 128;
 constexpr int CG_TILE_BYTES = CG_BM * 64 * 2;      // 16 KB: one 128-pixel x 64-channel bf16 tile
 constexpr int CG_HALO_BYTES = 18 * 16 * 128;       // 36 KB
@@ -120,13 +124,25 @@ __device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, uint32_t* r) {
         "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
       : "r"(taddr));
 }
+__device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+}
+template <int N> __device__ __forceinline__ void tmem_ldN_nowait(uint32_t taddr, uint32_t* r) {
+  if (N == 32) tmem_ld32_nowait(taddr, r);
+  else tmem_ld16_nowait(taddr, r);
+}
 __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
-// 32 accumulator columns [c0, c0 + 32) of this thread's row: + bias, * Dropout2d scale, packed to four 16-byte bf16 chunks
-__device__ __forceinline__ void pack32(const uint32_t* r, const float* sb, const float* scale_row, int c0, uint4* packed) {
-  float f[32];
+// N (16 / 32) accumulator columns [c0, c0 + N) of this thread's row: + bias, * Dropout2d scale, packed to N / 8 16-byte bf16 chunks
+template <int N>
+__device__ __forceinline__ void packN(const uint32_t* r, const float* sb, const float* scale_row, int c0, uint4* packed) {
+  float f[N];
 #pragma unroll
-  for (int q = 0; q < 8; ++q) {
+  for (int q = 0; q < N / 4; ++q) {
     const float4 b4 = *reinterpret_cast<const float4*>(sb + c0 + 4 * q);
     f[4 * q] = __uint_as_float(r[4 * q]) + b4.x; f[4 * q + 1] = __uint_as_float(r[4 * q + 1]) + b4.y;
     f[4 * q + 2] = __uint_as_float(r[4 * q + 2]) + b4.z; f[4 * q + 3] = __uint_as_float(r[4 * q + 3]) + b4.w;
@@ -136,7 +152,7 @@ __device__ __forceinline__ void pack32(const uint32_t* r, const float* sb, const
     }
   }
 #pragma unroll
-  for (int q = 0; q < 4; ++q) {
+  for (int q = 0; q < N / 8; ++q) {
     __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&packed[q]);
 #pragma unroll
     for (int e = 0; e < 4; ++e) h2[e] = __floats2bfloat162_rn(f[8 * q + 2 * e], f[8 * q + 2 * e + 1]);
@@ -146,9 +162,9 @@ __device__ __forceinline__ void pack32(const uint32_t* r, const float* sb, const
 // ACT: the gate activation as a compile-time constant (ACT_ELU, the model default) or -1 = read p.gate_act.  A runtime switch
 // inside the unrolled gate pass compiled to one jump table (LDC + BRX) per element: 34 indirect branches per tile-thread that
 // also kept the 16 iterations from overlapping (ncu, B = 1000: 1950 instructions per tile-thread, IPC 0.35 per scheduler).
-template <int ACT>
+template <int ACT, int EW>
 #define CG_STAMP(slot) do { if (p.dbg && blockIdx.x == 0 && lane == 0) p.dbg[it * 16 + (slot)] = clock64(); } while (0)
-__global__ void __launch_bounds__(CG_THREADS, 1)
+__global__ void __launch_bounds__(64 + 32 * EW, 1)
 conv_gate_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW2,
                     const __grid_constant__ CUtensorMap tmWg, const __grid_constant__ CUtensorMap tmC2,
                     const __grid_constant__ CUtensorMap tmH, const __grid_constant__ CUtensorMap tmOut, const CgParams p) {
@@ -161,16 +177,27 @@ conv_gate_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   uint8_t* sC2 = sA + p.n_stages * stage_bytes;          // staged c2 tile = A operand of the gate GEMM; later the staged out tile
   uint8_t* sH = sC2 + CG_TILE_BYTES;                     // staged h tile: [a | g], two 64-channel blocks
   uint64_t* bars = (uint64_t*)(sH + 2 * CG_TILE_BYTES);
-  // barriers: [0..S) full, [S..2S) empty, 2S weights, 2S+1..2 acc1_full[2], 2S+3..4 acc1_empty[2], 2S+5 c2_staged,
-  //           2S+6 acc2_full, 2S+7 acc2_empty
+  // barriers: [0..S) full, [S..2S) empty, 2S weights, 2S+1..2 acc1_full[2], 2S+3..4 acc1_empty[2], 2S+5..6 c2_staged[2],
+  //           2S+7..8 acc2_full[2], 2S+9..10 acc2_empty[2]  (the second of each gate-side pair: eval mode with two epilogue groups)
   const int S = p.n_stages;
-  uint32_t* tmem_slot = (uint32_t*)(bars + 2 * S + 8);
+  uint32_t* tmem_slot = (uint32_t*)(bars + 2 * S + 12);
   float* sbias = (float*)(bars + 32);                    // [0,64): bias2, [64,192): bias_g
   float* sred = sbias + 192;                             // 2 x 8 x 64 partial statistics
   const uint32_t bar0 = smem_u32(bars);
   auto BAR = [&](int i) { return bar0 + 8u * (uint32_t)i; };
-  const int B_W = 2 * S, B_A1F = 2 * S + 1, B_A1E = 2 * S + 3, B_C2 = 2 * S + 5, B_A2F = 2 * S + 6, B_A2E = 2 * S + 7;
+  const int B_W = 2 * S, B_A1F = 2 * S + 1, B_A1E = 2 * S + 3, B_C2 = 2 * S + 5, B_A2F = 2 * S + 7, B_A2E = 2 * S + 9;
+  // Eval mode (nothing but `out` leaves the SM) with 16 epilogue warps: TWO GROUPS of eight warps take alternate tiles, each
+  // with its own staging buffer, gate accumulator and barriers, so that two of the per-tile chains
+  //   acc1 -> c2 staged -> gate GEMM -> gate -> out staged -> TMA store      (~4500 cycles, all dependent latencies)
+  // are in flight against ~2300 cycles of MMAs per tile: the kernel becomes tensor-pipe-bound instead of chain-bound.
+  const bool fast = !p.store_c2h && !p.stats_acc;
+  const int G = (fast && EW == 16) ? 2 : 1;
+  const uint32_t tmem_cols = G == 2 ? 512u : 256u;
 
+  constexpr int CG_THREADS = 64 + 32 * EW;
+  constexpr int CPT = 256 / EW;              // accumulator columns per epilogue thread and 64-column block (32 / 16)
+  constexpr int RPW = 128 / EW;              // staged rows per epilogue warp in the channel-major gate pass (16 / 8)
+  constexpr int NQ = CPT / 8;                // 16-byte bf16 chunks per thread and block
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int gact = ACT >= 0 ? ACT : p.gate_act;
   const int n_tiles = p.halo ? (p.M_total / (p.H * p.W)) * p.tiles_per_img : (p.M_total + CG_BM - 1) / CG_BM;
@@ -187,11 +214,13 @@ conv_gate_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     mbar_init(BAR(B_W), 1);
     mbar_init(BAR(B_A1F), 1);
     mbar_init(BAR(B_A1F + 1), 1);
-    mbar_init(BAR(B_A1E), 8);          // one arrive per epilogue warp
-    mbar_init(BAR(B_A1E + 1), 8);
-    mbar_init(BAR(B_C2), 1);           // thread 64, after the staging barrier
-    mbar_init(BAR(B_A2F), 1);
-    mbar_init(BAR(B_A2E), 8);
+    mbar_init(BAR(B_A1E), EW / G);     // one arrive per epilogue warp (of the group that owns the tile)
+    mbar_init(BAR(B_A1E + 1), EW / G);
+    for (int g = 0; g < 2; ++g) {
+      mbar_init(BAR(B_C2 + g), 1);     // the group's elected thread, after the staging barrier
+      mbar_init(BAR(B_A2F + g), 1);
+      mbar_init(BAR(B_A2E + g), EW / G);
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 0) {
@@ -207,13 +236,13 @@ conv_gate_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   for (int i = threadIdx.x; i < 192; i += CG_THREADS)
     sbias[i] = i < 64 ? (p.bias2 ? p.bias2[i] : 0.f) : (p.bias_g ? p.bias_g[i - 64] : 0.f);
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(256) : "memory");
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(tmem_cols) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;      // columns [0,64) / [64,128): acc1[0] / acc1[1]; [128,256): acc2
+  const uint32_t tmem_base = *tmem_slot;      // columns [0,64) / [64,128): acc1[0] / acc1[1]; [128,256): acc2[0]; [256,384): acc2[1]
   pdl_wait();
   pdl_launch();
 
@@ -259,17 +288,19 @@ conv_gate_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     tc_fence_after();
     // gate GEMM of tile j (the j-th tile of this CTA): A = the staged c2 tile, B = the gate weights, D = acc2
     auto gate_phase = [&](int j) {
-      mbar_wait(BAR(B_A2E), (uint32_t)((j & 1) ^ 1));        // epilogue drained acc2 of tile j-1
-      mbar_wait(BAR(B_C2), (uint32_t)(j & 1));               // c2 of tile j is staged (and fenced for the async proxy)
+      const int g = G == 2 ? (j & 1) : 0;                    // epilogue group of tile j and its own tile count
+      const uint32_t par = (uint32_t)((G == 2 ? (j >> 1) : j) & 1);
+      mbar_wait(BAR(B_A2E + g), par ^ 1);                    // epilogue drained this gate accumulator
+      mbar_wait(BAR(B_C2 + g), par);                         // c2 of tile j is staged (and fenced for the async proxy)
       tc_fence_after();
       if (p.dbg && blockIdx.x == 0 && lane == 0) p.dbg[j * 16 + 10] = clock64();
       if (elect_one()) {
-        const uint64_t adesc = umma_desc_k_sw128(smem_u32(sC2));
+        const uint64_t adesc = umma_desc_k_sw128(smem_u32(sC2 + g * CG_TILE_BYTES));
         const uint64_t bdesc = umma_desc_k_sw128(smem_u32(sWg));
 #pragma unroll
         for (int k = 0; k < 4; ++k)
-          umma_bf16(tmem_u + 128u, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idescg, (uint32_t)(k != 0));
-        umma_commit(BAR(B_A2F));
+          umma_bf16(tmem_u + 128u + (uint32_t)(g * 128), adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idescg, (uint32_t)(k != 0));
+        umma_commit(BAR(B_A2F + g));
       }
       __syncwarp();
     };
@@ -325,27 +356,147 @@ conv_gate_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     }
     if (it > 0) gate_phase(it - 1);
   } else {
-    // ===================== epilogue (8 warps: TMEM lane quadrant x column half) =====================
+    // ===================== epilogue (EW warps: TMEM lane quadrant x column part) =====================
     const int quad = warp & 3;
-    const int half = (warp - 2) >> 2;
+    const int part = (warp - 2) >> 2;                          // which CPT columns of every 64-column block
     const int row = quad * 32 + lane;
     const int ew = warp - 2;
     float ra0 = 0.f, ra1 = 0.f, rb0 = 0.f, rb1 = 0.f;          // statistics of out, channels 2l and 2l+1
     const int rstep = p.halo ? p.W - 8 : 0;
+#define CG_EPI_BAR() asm volatile("bar.sync 1, %0;" ::"n"(32 * EW) : "memory")
+    if (fast) {
+      // ---------------- eval mode (the IW evaluator's sample passes) ----------------
+      // Group g = eight warps (TMEM lane quadrant x column half, 32 accumulator columns per thread) owns the CTA's tiles
+      // it = g, g + G, ...  The gate is evaluated straight from the accumulator registers -- a thread's loads are channels
+      // [32 half, 32 half + 32) of `a` and of `g` for its own pixel -- values rounded to bf16 exactly where the training path
+      // rounds them (so `out` is bit-identical to it), and `out` is staged in the buffer that held c2 (the gate GEMM is done).
+      const int g = G == 2 ? (ew >> 3) : 0;
+      const int half = (ew & 7) >> 2;
+      uint8_t* sStage = sC2 + g * CG_TILE_BYTES;
+      const bool elected = threadIdx.x == 64 + g * 256;
+      const float* ba = sbias + 64 + 32 * half;
+      const float* bg = sbias + 128 + 32 * half;
+      const uint32_t lane_addr = tmem_base + ((uint32_t)(quad * 32) << 16);
+      auto group_bar = [&]() {
+        if (G == 2) asm volatile("bar.sync %0, 256;" ::"r"(1 + g) : "memory");
+        else CG_EPI_BAR();
+      };
+      int it = 0;
+      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+        if (G == 2 && (it & 1) != g) continue;
+        const int buf = it & 1;
+        const uint32_t par1 = (uint32_t)((it >> 1) & 1);                       // this acc1 buffer's use count
+        const uint32_t par2 = (uint32_t)((G == 2 ? (it >> 1) : it) & 1);       // the group's own tile count
+        int m = tile * CG_BM + row;
+        int c1, c2, c3;
+        if (p.halo) {
+          const int n0 = tile >> p.lg_tpi;
+          const int r = tile & (p.tiles_per_img - 1);
+          const int ty = r >> p.lg_tx, tx = r & (p.tiles_x - 1);
+          m = (n0 * p.H + ty * 16 + (row >> 3)) * p.W + tx * 8 + (row & 7);
+          c3 = n0; c2 = ty * 16; c1 = tx * 8;
+        } else {
+          const int p0 = tile * CG_BM;
+          c3 = p0 >> p.lg_hw;
+          const int rem = p0 & (hw - 1);
+          c2 = rem >> p.lg_w; c1 = rem & (p.W - 1);
+        }
+        const bool valid = m < p.M_total;
+        const float* scale_row = p.scale2 ? p.scale2 + (long long)(valid ? (m >> p.lg_hw) : 0) * 64 : nullptr;
+        if (ew == 0 || ew == 8) CG_STAMP(0);
+        uint4 xr[4];                                              // this thread's half row of the residual: requested first
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+          xr[q] = valid ? __ldg(reinterpret_cast<const uint4*>(p.x_res + (long long)m * 64 + 32 * half) + q) : make_uint4(0u, 0u, 0u, 0u);
+        // phase 1: c2 = (acc1 + bias2) * mask2 -> bf16 -> the group's staging buffer
+        mbar_wait(BAR(B_A1F + buf), par1);
+        tc_fence_after();
+        if (ew == 0 || ew == 8) CG_STAMP(1);
+        {
+          uint4 pc[4];
+          uint32_t r[32];
+          tmem_ld32_nowait(lane_addr + (uint32_t)(buf * 64 + 32 * half), r);
+          tmem_wait_ld();
+          packN<32>(r, sbias, scale_row, 32 * half, pc);
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(BAR(B_A1E + buf));           // the 3x3 accumulator is free for the tile after next
+          if (elected) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // the group's previous `out` store has left the buffer
+          group_bar();
+          uint8_t* blk = sStage + row * 128;
+#pragma unroll
+          for (int q = 0; q < 4; ++q) *reinterpret_cast<uint4*>(blk + (((4 * half + q) ^ (row & 7)) << 4)) = pc[q];
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        group_bar();
+        if (ew == 0 || ew == 8) CG_STAMP(3);
+        if (elected) mbar_arrive(BAR(B_C2 + g));                  // the MMA warp may run the gate GEMM on the staged tile
+        // phase 2: out = act(a) * sigmoid(g) + x from the gate accumulator, 16 columns at a time
+        mbar_wait(BAR(B_A2F + g), par2);
+        tc_fence_after();
+        if (ew == 0 || ew == 8) CG_STAMP(4);
+        uint4 po[4];
+#pragma unroll
+        for (int hq = 0; hq < 2; ++hq) {
+          uint32_t ra[16], rg[16];
+          tmem_ld16_nowait(lane_addr + (uint32_t)(128 + g * 128 + 32 * half + 16 * hq), ra);
+          tmem_ld16_nowait(lane_addr + (uint32_t)(128 + g * 128 + 64 + 32 * half + 16 * hq), rg);
+          tmem_wait_ld();
+#pragma unroll
+          for (int q = 0; q < 2; ++q) {
+            const uint32_t* xw = reinterpret_cast<const uint32_t*>(&xr[2 * hq + q]);
+            uint32_t* ow = reinterpret_cast<uint32_t*>(&po[2 * hq + q]);
+            const float4 ba0 = *reinterpret_cast<const float4*>(ba + 16 * hq + 8 * q), ba1 = *reinterpret_cast<const float4*>(ba + 16 * hq + 8 * q + 4);
+            const float4 bg0 = *reinterpret_cast<const float4*>(bg + 16 * hq + 8 * q), bg1 = *reinterpret_cast<const float4*>(bg + 16 * hq + 8 * q + 4);
+            const float bav[8] = {ba0.x, ba0.y, ba0.z, ba0.w, ba1.x, ba1.y, ba1.z, ba1.w};
+            const float bgv[8] = {bg0.x, bg0.y, bg0.z, bg0.w, bg1.x, bg1.y, bg1.z, bg1.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const int c = 8 * q + 2 * e;
+              const __nv_bfloat162 ab = __floats2bfloat162_rn(__uint_as_float(ra[c]) + bav[2 * e], __uint_as_float(ra[c + 1]) + bav[2 * e + 1]);
+              const __nv_bfloat162 gb = __floats2bfloat162_rn(__uint_as_float(rg[c]) + bgv[2 * e], __uint_as_float(rg[c + 1]) + bgv[2 * e + 1]);
+              const float2 af = __bfloat1622float2(ab), gf = __bfloat1622float2(gb);
+              const float x0 = __uint_as_float(xw[e] << 16), x1 = __uint_as_float(xw[e] & 0xFFFF0000u);
+              const float o0 = fmaf(act_fwd_t<true>(af.x, gact), sigmoid_tanh_approx(gf.x), x0);
+              const float o1 = fmaf(act_fwd_t<true>(af.y, gact), sigmoid_tanh_approx(gf.y), x1);
+              const __nv_bfloat162 ob = __floats2bfloat162_rn(o0, o1);
+              ow[e] = *reinterpret_cast<const uint32_t*>(&ob);
+            }
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(BAR(B_A2E + g));               // the gate accumulator is free for the group's next tile
+        if (ew == 0 || ew == 8) CG_STAMP(5);
+        {
+          uint8_t* blk = sStage + row * 128;                      // c2 was consumed: acc2_full means the gate MMAs have completed
+#pragma unroll
+          for (int q = 0; q < 4; ++q) *reinterpret_cast<uint4*>(blk + (((4 * half + q) ^ (row & 7)) << 4)) = po[q];
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        group_bar();
+        if (elected) {
+          tma_store_4d(&tmOut, smem_u32(sStage), 0, c1, c2, c3);
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
+        if (ew == 0 || ew == 8) CG_STAMP(6);
+      }
+      if (elected) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    } else {
     int it = 0;
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
       const int buf = it & 1;
       const uint32_t use = (uint32_t)(it >> 1);
-      // pixel of this thread's accumulator row; first pixel of the 16 staged rows this warp owns in the gate pass
+      // pixel of this thread's accumulator row; first pixel of the RPW staged rows this warp owns in the gate pass
       int m = tile * CG_BM + row;                               // (M_total = B*H*W fits an int)
-      int rbase = tile * CG_BM + ew * 16;
+      int rbase = tile * CG_BM + ew * RPW;
       int c1, c2, c3;                                           // TMA-store coordinates of the tile
       if (p.halo) {
         const int n0 = tile >> p.lg_tpi;
         const int r = tile & (p.tiles_per_img - 1);
         const int ty = r >> p.lg_tx, tx = r & (p.tiles_x - 1);
         m = (n0 * p.H + ty * 16 + (row >> 3)) * p.W + tx * 8 + (row & 7);
-        rbase = (n0 * p.H + ty * 16 + ew * 2) * p.W + tx * 8;
+        rbase = (n0 * p.H + ty * 16 + ((ew * RPW) >> 3)) * p.W + tx * 8;
         c3 = n0; c2 = ty * 16; c1 = tx * 8;
       } else {
         const int p0 = tile * CG_BM;
@@ -358,45 +509,32 @@ conv_gate_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       const float* scale_row = p.scale2 ? p.scale2 + (long long)b * 64 : nullptr;
       const uint32_t lane_addr = tmem_base + ((uint32_t)(quad * 32) << 16);
 
-      // eval fast path: this thread's half row of the residual, requested before anything of the tile is waited for (ncu: the
-      // first use of these loads, issued after the gate GEMM, was the largest single stall of the epilogue -- 20 % of its samples)
-      uint4 xr[4];
       if (warp == 2) CG_STAMP(0);
-      if (!p.store_c2h && !p.stats_acc) {
-#pragma unroll
-        for (int q = 0; q < 4; ++q)
-          xr[q] = valid ? __ldg(reinterpret_cast<const uint4*>(p.x_res + (long long)m * 64 + 32 * half) + q) : make_uint4(0u, 0u, 0u, 0u);
-      }
       // ---------------- phase 1: c2 = (acc1 + bias2) * mask2 -> bf16 -> staged tile (+ TMA store) ----------------
       mbar_wait(BAR(B_A1F + buf), use & 1);
       tc_fence_after();
       if (warp == 2) CG_STAMP(1);
-      uint4 pc[4];
+      uint4 pc[NQ];
       {
-        uint32_t r[32];
-        tmem_ld32_nowait(lane_addr + (uint32_t)(buf * 64 + 32 * half), r);
+        uint32_t r[CPT];
+        tmem_ldN_nowait<CPT>(lane_addr + (uint32_t)(buf * 64 + CPT * part), r);
         tmem_wait_ld();
-        pack32(r, sbias, scale_row, 32 * half, pc);
+        packN<CPT>(r, sbias, scale_row, CPT * part, pc);
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(BAR(B_A1E + buf));             // the 3x3 accumulator is free for the tile after next
       if (warp == 2) CG_STAMP(2);
-      // every TMA store of the previous tile (c2, h, out) has finished reading the staging buffers.  Eval fast path: the only
-      // store is `out`, staged alternately in the two (otherwise unused) h buffers, so it is enough that the store of the
-      // tile BEFORE the previous one has been read: the previous tile's store stays in flight instead of stalling this one
-      if (threadIdx.x == 64) {
-        if (!p.store_c2h && !p.stats_acc) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
-        else asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-      }
-      asm volatile("bar.sync 1, 256;" ::: "memory");
+      // every TMA store of the previous tile (c2, h, out) has finished reading the staging buffers
+      if (threadIdx.x == 64) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+      CG_EPI_BAR();
       {
         uint8_t* blk = sC2 + row * 128;
 #pragma unroll
-        for (int q = 0; q < 4; ++q) *reinterpret_cast<uint4*>(blk + (((4 * half + q) ^ (row & 7)) << 4)) = pc[q];
+        for (int q = 0; q < NQ; ++q) *reinterpret_cast<uint4*>(blk + (((NQ * part + q) ^ (row & 7)) << 4)) = pc[q];
       }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic writes -> visible to TMA and tcgen05.mma
-      asm volatile("bar.sync 1, 256;" ::: "memory");
+      CG_EPI_BAR();
       if (warp == 2) CG_STAMP(3);
       if (threadIdx.x == 64) {
         mbar_arrive(BAR(B_C2));                                  // the MMA warp may run the gate GEMM on the staged tile
@@ -405,64 +543,12 @@ conv_gate_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           asm volatile("cp.async.bulk.commit_group;" ::: "memory");
         }
       }
-      if (!p.store_c2h && !p.stats_acc) {
-        // ---------------- eval fast path (IW evaluator): nothing but `out` leaves the SM, so the gate is evaluated straight
-        // from the accumulator registers -- a thread's two 32-column loads are channels [32 half, 32 half + 32) of `a` and of
-        // `g` for its own pixel -- instead of staging h (2 x 16 KB) and re-reading it in a second, channel-major pass: one
-        // barrier and ~50 KB of shared-memory traffic per tile less.  Values are rounded to bf16 exactly where the staged
-        // path rounds them, so `out` is bit-identical.
-        mbar_wait(BAR(B_A2F), (uint32_t)(it & 1));
-        tc_fence_after();
-        if (warp == 2) CG_STAMP(4);
-        uint32_t ra[32], rg[32];
-        tmem_ld32_nowait(lane_addr + (uint32_t)(128 + 32 * half), ra);
-        tmem_ld32_nowait(lane_addr + (uint32_t)(128 + 64 + 32 * half), rg);
-        tmem_wait_ld();
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(BAR(B_A2E));                  // acc2 is free for the next tile's gate GEMM
-        const float* ba = sbias + 64 + 32 * half;
-        const float* bg = sbias + 128 + 32 * half;
-        uint4 po[4];
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const uint32_t* xw = reinterpret_cast<const uint32_t*>(&xr[q]);
-          uint32_t* ow = reinterpret_cast<uint32_t*>(&po[q]);
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const int c = 8 * q + 2 * e;
-            const __nv_bfloat162 ab = __floats2bfloat162_rn(__uint_as_float(ra[c]) + ba[c], __uint_as_float(ra[c + 1]) + ba[c + 1]);
-            const __nv_bfloat162 gb = __floats2bfloat162_rn(__uint_as_float(rg[c]) + bg[c], __uint_as_float(rg[c + 1]) + bg[c + 1]);
-            const float2 af = __bfloat1622float2(ab), gf = __bfloat1622float2(gb);
-            const float x0 = __uint_as_float(xw[e] << 16), x1 = __uint_as_float(xw[e] & 0xFFFF0000u);
-            const float o0 = fmaf(act_fwd_t<true>(af.x, gact), sigmoid_tanh_approx(gf.x), x0);
-            const float o1 = fmaf(act_fwd_t<true>(af.y, gact), sigmoid_tanh_approx(gf.y), x1);
-            const __nv_bfloat162 ob = __floats2bfloat162_rn(o0, o1);
-            ow[e] = *reinterpret_cast<const uint32_t*>(&ob);
-          }
-        }
-        if (warp == 2) CG_STAMP(5);
-        uint8_t* sOutE = sH + (it & 1) * CG_TILE_BYTES;      // free since the store of tile it-2 was read (phase 1's wait)
-        {
-          uint8_t* blk = sOutE + row * 128;
-#pragma unroll
-          for (int q = 0; q < 4; ++q) *reinterpret_cast<uint4*>(blk + (((4 * half + q) ^ (row & 7)) << 4)) = po[q];
-        }
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        asm volatile("bar.sync 1, 256;" ::: "memory");
-        if (threadIdx.x == 64) {
-          tma_store_4d(&tmOut, smem_u32(sOutE), 0, c1, c2, c3);
-          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-        }
-        if (warp == 2) CG_STAMP(6);
-        continue;
-      }
       // residual rows for the gate pass: in flight while the gate GEMM runs
-      uint32_t xq[16];
+      uint32_t xq[RPW];
       {
         const uint32_t* xb = reinterpret_cast<const uint32_t*>(p.x_res + (long long)rbase * 64) + lane;
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
+        for (int i = 0; i < RPW; ++i) {
           const int off = i + (i >> 3) * rstep;
           xq[i] = rbase + off < p.M_total ? __ldg(xb + off * 32) : 0u;
         }
@@ -471,23 +557,24 @@ conv_gate_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       // ---------------- phase 2: h = acc2 + bias_g -> bf16 -> staged (+ TMA store); gate pass; out -> staged -> TMA store ------
       mbar_wait(BAR(B_A2F), (uint32_t)(it & 1));
       tc_fence_after();
+      if (warp == 2) CG_STAMP(4);
       // (sH is free: the previous tile's h store finished reading it before this tile's phase 1 passed its first barrier)
 #pragma unroll
       for (int nch = 0; nch < 2; ++nch) {
-        uint32_t r[32];
-        uint4 ph[4];
-        tmem_ld32_nowait(lane_addr + (uint32_t)(128 + 32 * half + 64 * nch), r);
+        uint32_t r[CPT];
+        uint4 ph[NQ];
+        tmem_ldN_nowait<CPT>(lane_addr + (uint32_t)(128 + CPT * part + 64 * nch), r);
         tmem_wait_ld();
-        pack32(r, sbias + 64, nullptr, 32 * half + 64 * nch, ph);
+        packN<CPT>(r, sbias + 64, nullptr, CPT * part + 64 * nch, ph);
         uint8_t* blk = sH + nch * CG_TILE_BYTES + row * 128;
 #pragma unroll
-        for (int q = 0; q < 4; ++q) *reinterpret_cast<uint4*>(blk + (((4 * half + q) ^ (row & 7)) << 4)) = ph[q];
+        for (int q = 0; q < NQ; ++q) *reinterpret_cast<uint4*>(blk + (((NQ * part + q) ^ (row & 7)) << 4)) = ph[q];
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(BAR(B_A2E));                    // acc2 is free for the next tile's gate GEMM
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-      asm volatile("bar.sync 1, 256;" ::: "memory");
+      CG_EPI_BAR();
       if (threadIdx.x == 64) {
         if (p.store_c2h) {
           tma_store_4d(&tmH, smem_u32(sH), 0, c1, c2, c3);
@@ -497,12 +584,12 @@ conv_gate_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
         }
       }
-      asm volatile("bar.sync 1, 256;" ::: "memory");
+      CG_EPI_BAR();
       {
-        const int nrows = p.halo ? 128 : (int)min((long long)128, p.M_total - (long long)tile * CG_BM);
+        const int nrows = p.halo ? 128 : min(128, p.M_total - tile * CG_BM);
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          const int r = ew * 16 + i;
+        for (int i = 0; i < RPW; ++i) {
+          const int r = ew * RPW + i;
           const int pos = r * 128 + ((((lane >> 2) ^ (r & 7))) << 4) + (lane & 3) * 4;
           const uint32_t ua = *reinterpret_cast<const uint32_t*>(sH + pos);
           const uint32_t ug = *reinterpret_cast<const uint32_t*>(sH + CG_TILE_BYTES + pos);
@@ -521,17 +608,31 @@ conv_gate_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           }
         }
       }
+      if (warp == 2) CG_STAMP(5);
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-      asm volatile("bar.sync 1, 256;" ::: "memory");
+      CG_EPI_BAR();
       if (threadIdx.x == 64) {
         tma_store_4d(&tmOut, smem_u32(sC2), 0, c1, c2, c3);
         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
       }
+      if (warp == 2) CG_STAMP(6);
     }
+    }   // training path
     if (p.stats_acc) {
-      sred[(0 * 8 + ew) * 64 + 2 * lane] = ra0; sred[(0 * 8 + ew) * 64 + 2 * lane + 1] = ra1;
-      sred[(1 * 8 + ew) * 64 + 2 * lane] = rb0; sred[(1 * 8 + ew) * 64 + 2 * lane + 1] = rb1;
-      asm volatile("bar.sync 1, 256;" ::: "memory");
+      // combine the EW row groups per channel in a fixed order (deterministic): eight slots, the warps beyond the eighth add
+      // into the slot of warp ew - 8 after the first eight have written theirs
+      if (ew < 8) {
+        sred[(0 * 8 + ew) * 64 + 2 * lane] = ra0; sred[(0 * 8 + ew) * 64 + 2 * lane + 1] = ra1;
+        sred[(1 * 8 + ew) * 64 + 2 * lane] = rb0; sred[(1 * 8 + ew) * 64 + 2 * lane + 1] = rb1;
+      }
+      CG_EPI_BAR();
+      if (EW > 8) {
+        if (ew >= 8) {
+          sred[(0 * 8 + ew - 8) * 64 + 2 * lane] += ra0; sred[(0 * 8 + ew - 8) * 64 + 2 * lane + 1] += ra1;
+          sred[(1 * 8 + ew - 8) * 64 + 2 * lane] += rb0; sred[(1 * 8 + ew - 8) * 64 + 2 * lane + 1] += rb1;
+        }
+        CG_EPI_BAR();
+      }
       const int t = threadIdx.x - 64;
       if (t < 128) {
         const int st = t >> 6, c = t & 63;
@@ -541,12 +642,13 @@ conv_gate_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         atomicAdd(p.stats_acc + (blockIdx.x & 7) * 128 + st * 64 + c, (double)sum);    // 8-way striped (see elementwise.cu)
       }
     }
+#undef CG_EPI_BAR
   }
   if (threadIdx.x == 64) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   tc_fence_before();
   __syncthreads();
   if (warp == 1) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols) : "memory");
   }
 }
 
@@ -651,15 +753,19 @@ LVAE_API int lvae_conv_gate_tc(const void* a2, const void* w2p, const float* bia
   }
   static bool attr = false;
   if (!attr) {
-    cudaError_t e = cudaFuncSetAttribute(conv_gate_tc_kernel<ACT_ELU>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024));
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_gate_tc_kernel<-1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024));
+    cudaError_t e = cudaFuncSetAttribute(conv_gate_tc_kernel<ACT_ELU, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024));
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_gate_tc_kernel<ACT_ELU, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024));
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_gate_tc_kernel<-1, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024));
     if (e != cudaSuccess) { lvae_set_error("conv_gate_tc: cannot raise dynamic smem: %s", cudaGetErrorString(e)); return LVAE_ERR_CUDA; }
     attr = true;
   }
   const int n_tiles = p.halo ? B * p.tiles_per_img : (p.M_total + CG_BM - 1) / CG_BM;
   const int grid = n_tiles < lvae_num_sms() ? n_tiles : lvae_num_sms();
-  if (gate_act == ACT_ELU) lvae_launch(conv_gate_tc_kernel<ACT_ELU>, grid, CG_THREADS, smem, stream, tmA, tmW2, tmWg, tmC2, tmH, tmOut, p);
-  else lvae_launch(conv_gate_tc_kernel<-1>, grid, CG_THREADS, smem, stream, tmA, tmW2, tmWg, tmC2, tmH, tmOut, p);
+  static int ew_env = -1;
+  if (ew_env < 0) { const char* e = getenv("LVAE_CONV_GATE_EW"); ew_env = e ? atoi(e) : CG_EW_DEFAULT; }     // A/B aid: 8 or 16 epilogue warps
+  if (gate_act == ACT_ELU && ew_env == 16) lvae_launch(conv_gate_tc_kernel<ACT_ELU, 16>, grid, 64 + 32 * 16, smem, stream, tmA, tmW2, tmWg, tmC2, tmH, tmOut, p);
+  else if (gate_act == ACT_ELU) lvae_launch(conv_gate_tc_kernel<ACT_ELU, 8>, grid, 64 + 32 * 8, smem, stream, tmA, tmW2, tmWg, tmC2, tmH, tmOut, p);
+  else lvae_launch(conv_gate_tc_kernel<-1, 8>, grid, 64 + 32 * 8, smem, stream, tmA, tmW2, tmWg, tmC2, tmH, tmOut, p);
   LVAE_COUNT_LAUNCH();
   LVAE_CHECK_LAUNCH("conv_gate_tc");
   return LVAE_OK;
