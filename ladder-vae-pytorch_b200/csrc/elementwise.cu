@@ -446,22 +446,23 @@ __global__ void gate_bwd_kernel(const T* __restrict__ dout, const T* __restrict_
   pdl_wait();
   pdl_launch();
   const int act = ACT >= 0 ? ACT : act_rt;
-  const int CV = C / V;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (long long)gridDim.x * blockDim.x) {
-    long long row = i / CV;
-    int c = (int)(i - row * CV) * V;
+  const unsigned CV = (unsigned)(C / V);
+  // 32-bit index arithmetic (lvae_gate_bwd checks that the element count fits): a 64-bit i / CV per iteration is ~100 instructions
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < (unsigned)nvec; i += gridDim.x * blockDim.x) {
+    const unsigned row = i / CV;
+    const int c = (int)(i - row * CV) * V;
     float av[V], gv[V], dv[V], da[V], dg[V];
-    ldv<T, V>(h + row * 2 * C + c, av);
-    ldv<T, V>(h + row * 2 * C + C + c, gv);
-    ldv<T, V>(dout + i * V, dv);
+    ldv<T, V>(h + (size_t)row * 2 * C + c, av);
+    ldv<T, V>(h + (size_t)row * 2 * C + C + c, gv);
+    ldv<T, V>(dout + (size_t)i * V, dv);
 #pragma unroll
     for (int j = 0; j < V; ++j) {
       float s = sigmoid_t<sizeof(T) == 2>(gv[j]);
       da[j] = dv[j] * s * act_bwd_t<sizeof(T) == 2>(av[j], act);
       dg[j] = dv[j] * act_fwd_t<sizeof(T) == 2>(av[j], act) * s * (1.f - s);
     }
-    stv<T, V>(dh + row * 2 * C + c, da);
-    stv<T, V>(dh + row * 2 * C + C + c, dg);
+    stv<T, V>(dh + (size_t)row * 2 * C + c, da);
+    stv<T, V>(dh + (size_t)row * 2 * C + C + c, dg);
   }
 }
 
@@ -478,6 +479,7 @@ LVAE_API int lvae_gate_fwd(const void* h, const void* res, void* out, long long 
 
 LVAE_API int lvae_gate_bwd(const void* dout, const void* h, void* dh, long long P, int C, int act, int dtype, cudaStream_t stream) {
   LVAE_REQUIRE(dout && h && dh && P > 0 && C % 4 == 0, "gate_bwd: bad args");
+  LVAE_REQUIRE(P * (long long)C < (1LL << 32), "gate_bwd: more than 2^32 elements");
   if (dtype == 1 && C % 8 == 0) {
     long long nv = P * (C / 8);
     if (act == ACT_ELU) lvae_launch(gate_bwd_kernel<__nv_bfloat16, 8, ACT_ELU>, ew_grid(nv, 256), 256, 0, stream, (const __nv_bfloat16*)dout, (const __nv_bfloat16*)h, (__nv_bfloat16*)dh, nv, C, act);
@@ -924,7 +926,7 @@ __global__ void __launch_bounds__(256, 3) bn_act_bwd2_kernel(const T* __restrict
       }
     }
     if (post_scale) {
-      const unsigned bidx = (unsigned)(i / CV) / (unsigned)hw;      // pixel and image indices fit 32 bits
+      const unsigned bidx = ((unsigned)i / (unsigned)CV) / (unsigned)hw;      // vector, pixel and image indices fit 32 bits (checked by the launcher)
       const float* ps = post_scale + (size_t)bidx * C + c;
 #pragma unroll
       for (int j = 0; j < V; ++j) o[j] *= ps[j];
@@ -947,9 +949,16 @@ static inline int bn_grid_cap() {
   if (!cap) { const char* e = getenv("LVAE_BN_CTAS_PER_SM"); cap = e ? atoi(e) : 4; if (cap < 1) cap = 1; }
   return cap * lvae_num_sms();
 }
-static inline int ew_grid_aligned(long long n, int threads, int CV) {
+// resident CTAs per SM of a kernel at 256 threads (a grid of 4 CTAs per SM for a kernel that fits 3 runs as 1.33 waves)
+template <typename K> static inline int resident_ctas(K kernel) {
+  int occ = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, 256, 0) != cudaSuccess || occ < 1) occ = 1;
+  return occ;
+}
+static inline int ew_grid_aligned(long long n, int threads, int CV, int max_resident = 1 << 20) {
   int g = ew_grid(n, threads);
   if (g > bn_grid_cap()) g = bn_grid_cap();
+  if (g > max_resident * lvae_num_sms()) g = max_resident * lvae_num_sms();
   while (((long long)g * threads) % CV != 0) ++g;
   return g;
 }
@@ -990,6 +999,7 @@ LVAE_API int lvae_bn_act_bwd2(const void* dy, const void* x, void* dx, const flo
                               const void* add, long long P, int hw, int C, int act, int training, int dtype,
                               int skip_reduce, cudaStream_t stream) {
   LVAE_REQUIRE(dy && x && dx && save && gamma && beta && acc && P > 0 && bn_c_ok(C), "bn_act_bwd2: bad args");
+  LVAE_REQUIRE(P * (long long)C < (1LL << 32), "bn_act_bwd2: more than 2^32 elements");
   long long nq = P * (C / 4);
   if (!skip_reduce) {            // the producer of dy (tcgen05 dgrad epilogue) may already have accumulated the sums
     launch_bwd_reduce(dy, x, save, save + C, gamma, beta, acc, P, C, act, dtype, stream);
@@ -998,7 +1008,9 @@ LVAE_API int lvae_bn_act_bwd2(const void* dy, const void* x, void* dx, const flo
   }
   if (use_v8(dtype, C)) {
     long long nv = P * (C / 8);
-    int g = ew_grid_aligned(nv, 256, C / 8);
+    static const int occ_elu = resident_ctas(bn_act_bwd2_kernel<__nv_bfloat16, 8, ACT_ELU>);
+    static const int occ_any = resident_ctas(bn_act_bwd2_kernel<__nv_bfloat16, 8>);
+    int g = ew_grid_aligned(nv, 256, C / 8, act == ACT_ELU ? occ_elu : occ_any);
     if (act == ACT_ELU)
       lvae_launch(bn_act_bwd2_kernel<__nv_bfloat16, 8, ACT_ELU>, g, 256, 0, stream, (const __nv_bfloat16*)dy, (const __nv_bfloat16*)x, (__nv_bfloat16*)dx, save,
           gamma, beta, acc, dgamma, dbeta, post_scale, (const __nv_bfloat16*)add, nv, P, hw, C, act, training);

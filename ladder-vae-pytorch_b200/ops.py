@@ -368,6 +368,7 @@ class WeightPack:
 
 _tc_enabled = [True]
 _s2_enabled = [os.environ.get("LVAE_CONV_S2_TC", "1") != "0"]
+_debug_skip_wgrad = [os.environ.get("LVAE_DEBUG_SKIP_WGRAD", "0") == "1"]   # measurement aid: main-chain time without weight gradients
 _s2_wgrad_enabled = [os.environ.get("LVAE_WGRAD_S2_TC", "1") != "0"]     # A/B aid: stride-2 weight gradients on tcgen05
 
 
@@ -666,7 +667,9 @@ def conv_backward_raw(spec: ConvSpec, xn, x2n, weight, bias, out_scale, gyn, nee
             _side["keep"].append((xn, x2n, gyn, out_scale))                  # keep operands alive until the join
             ctx_mgr = torch.cuda.stream(side)
             ctx_mgr.__enter__()
-        if use_tc and out_scale is None and C1 == 64 and C2 in (0, 64) and N in (64, 128) and gyn.dtype == torch.bfloat16 \
+        if _debug_skip_wgrad[0]:
+            pass          # timing experiment only (LVAE_DEBUG_SKIP_WGRAD=1): no weight gradients, results are wrong
+        elif use_tc and out_scale is None and C1 == 64 and C2 in (0, 64) and N in (64, 128) and gyn.dtype == torch.bfloat16 \
                 and spec.k * spec.k * (2 if C2 else 1) <= 9:
             stats["tc_wgrad"] += 1
             gp = getattr(weight, "_lvae_gp", None) if (sunk and bsunk) else None
