@@ -816,12 +816,14 @@ __global__ void bn_act_fwd2_kernel(const TI* __restrict__ x, TO* __restrict__ y,
   bool has = i < nvec;
   RawV<TI, V> rx;
   if (has) rx = ldraw<TI, V>(x + i * V);                           // in flight during the statistics prologue
-  // one thread per channel derives the statistics (the only double-precision math in the kernel)
+  // one thread per channel derives the statistics (the only double-precision math in the kernel; the reciprocal of P is
+  // taken while the accumulator loads are in flight -- two double divisions behind them cost ~0.4 us per launch)
+  const double invP = 1.0 / (double)P;
   for (int ch = threadIdx.x; ch < C; ch += blockDim.x) {
     float mean, rstd;
     if (training) {
-      double m = acc_sum(acc, ch, C) / (double)P;
-      double var = acc_sum(acc, C + ch, C) / (double)P - m * m;
+      double m = acc_sum(acc, ch, C) * invP;
+      double var = acc_sum(acc, C + ch, C) * invP - m * m;
       if (var < 0.0) var = 0.0;
       mean = (float)m;
       rstd = rsqrtf((float)var + eps);
