@@ -120,6 +120,14 @@ typedef struct {
   const float* fold_var;
   float fold_eps;
   int fold_act;
+  /* with fold_*: the eval-mode BatchNorm2d + activation in FRONT of the conv (lib/nn.py:78-81 in eval mode) applied to the
+   * operand tile in shared memory on its way to the tensor cores (same activation as fold_act): x may then be the raw block
+   * input.  Single 64-channel input, 3x3, W % 8 == 0, H % 16 == 0.  pre_gamma NULL = off. */
+  const float* pre_gamma;
+  const float* pre_beta;
+  const float* pre_mean;
+  const float* pre_var;
+  float pre_eps;
 } LvaeConvFuse;
 int lvae_conv2d_tc_ex(const void* x, const void* x2, const void* wp, const float* bias, const float* out_scale,
                       const void* res, void* y, void* y2, int nsplit, int B, int H, int W, int Cin, int N, int ksize,

@@ -89,7 +89,8 @@ class ConvFuse(ctypes.Structure):
                 ("bnb_beta", c_void_p), ("bnb_acc", c_void_p), ("bnb_act", c_int), ("gate_x", c_void_p),
                 ("gate_out", c_void_p), ("gate_act", c_int), ("gate_skip_h", c_int), ("fold_gamma", c_void_p),
                 ("fold_beta", c_void_p), ("fold_mean", c_void_p), ("fold_var", c_void_p), ("fold_eps", ctypes.c_float),
-                ("fold_act", c_int)]
+                ("fold_act", c_int), ("pre_gamma", c_void_p), ("pre_beta", c_void_p), ("pre_mean", c_void_p), ("pre_var", c_void_p),
+                ("pre_eps", ctypes.c_float)]
 
 
 def exported_symbols():

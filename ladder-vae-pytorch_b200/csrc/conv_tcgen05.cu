@@ -67,6 +67,12 @@ struct TcParams {
   const float* fold_gamma; const float* fold_beta; const float* fold_mean; const float* fold_var;
   float fold_eps;
   int fold_act;
+  // ... and the eval-mode BatchNorm + activation in FRONT of this conv applied to its operand on the way in (FUSE 4, halo tiles):
+  // five transform warps rewrite every landed halo tile in place, x -> act(x * s + t), before the MMA warp may read it, and leave
+  // the zero fill of the out-of-image pixels alone (it is the convolution's padding of the ACTIVATED tensor).  The separate
+  // BatchNorm-apply pass of the block input disappears: one launch and one read + write of the tensor less (lib/nn.py:78-81).
+  const float* pre_gamma; const float* pre_beta; const float* pre_mean; const float* pre_var;
+  float pre_eps;
   long long* dbg;           // optional per-tile clock64 trace of CTA 0 (profiling aid, normally null)
   int8_t dx[TC_MAX_KB], dy[TC_MAX_KB], src[TC_MAX_KB], coff[TC_MAX_KB];   // coff: channel offset / 64 inside the tensor
   // stride-2 convolutions (lvae_conv2d_tc_s2): the tile's pixel coordinates are multiplied by in_stride before the tap
@@ -264,7 +270,7 @@ __device__ __forceinline__ void epilogue16(const uint32_t* __restrict__ r, const
 // ACT (FUSE 2 / 3 only): the activation of the fused BatchNorm-backward / gate pass as a compile-time constant (ACT_ELU, the
 // model default) or -1 = runtime value; a switch inside the unrolled second pass costs one jump table per element.
 template <int FUSE, int ACT = -1>
-__global__ void __launch_bounds__(TC_THREADS, 1)
+__global__ void __launch_bounds__(FUSE == 4 ? TC_THREADS + 160 : TC_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmY,
                const __grid_constant__ CUtensorMap tmY2, const TcParams p) {
@@ -280,7 +286,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
   uint64_t* bars = (uint64_t*)(sOut + (p.tma_store ? (p.Npad / 64 + (FUSE == 3 ? 1 : 0)) * TC_STAGE_BYTES : 0));
   // barrier layout: [0..S) full, [S..2S) empty, 2S: weights, 2S+1..2S+2: tmem_full[2], 2S+3..2S+4: tmem_empty[2]
   const int S = p.n_stages;
-  uint32_t* tmem_slot = (uint32_t*)(bars + 2 * S + 5);
+  // FUSE 4: [2S+5 .. 3S+5) "stage transformed" (operand-path BatchNorm), tmem slot behind them (S <= 8: still below bars + 32)
+  uint32_t* tmem_slot = (uint32_t*)(bars + (FUSE == 4 ? 3 * S + 5 : 2 * S + 5));
+  const bool pre_bn = FUSE == 4 && p.pre_gamma != nullptr && p.halo;
   float* sbias = (float*)(bars + 32);                         // Npad floats (<= 256), zero beyond N / when bias == null
   float* sred = sbias + 256;                                  // 2 statistics x 8 warps x 64 channels (fused reductions)
   const uint32_t bar0 = smem_u32(bars);
@@ -302,6 +310,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     mbar_init(BAR(2 * S + 2), 1);
     mbar_init(BAR(2 * S + 3), 8);                  // one arrive per epilogue warp
     mbar_init(BAR(2 * S + 4), 8);
+    if (FUSE == 4) for (int i = 0; i < S; ++i) mbar_init(BAR(2 * S + 5 + i), 5);     // one arrive per transform warp
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 0) {
@@ -320,6 +329,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
       const float sc = p.fold_gamma[i] * rsqrtf(p.fold_var[i] + p.fold_eps);
       sred[i] = sc;
       sbias[i] = fmaf(p.bias ? p.bias[i] : 0.f, sc, p.fold_beta[i] - p.fold_mean[i] * sc);
+      if (pre_bn) {                                  // same arithmetic as bn_act_fwd2's eval prologue: bit-identical operand
+        const float rstd = rsqrtf(p.pre_var[i] + p.pre_eps);
+        const float ps = rstd * p.pre_gamma[i];
+        sred[64 + i] = ps;
+        sred[128 + i] = p.pre_beta[i] - p.pre_mean[i] * ps;
+      }
     }
   } else {
     for (int i = threadIdx.x; i < p.Npad; i += TC_THREADS) sbias[i] = (p.bias && i < p.N) ? p.bias[i] : 0.f;
@@ -394,7 +409,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         const uint32_t d_tmem = tmem_u + (uint32_t)(buf * p.Npad);
         if (p.halo) {
           if (p.dbg && blockIdx.x == 0 && lane == 0) p.dbg[it * 8 + 0] = clock64();
-          mbar_wait(BAR(stage), phase);
+          mbar_wait(BAR(pre_bn ? 2 * S + 5 + stage : stage), phase);     // landed (and, with the operand-path BatchNorm, transformed)
           tc_fence_after();
           if (p.dbg && blockIdx.x == 0 && lane == 0) p.dbg[it * 8 + 1] = clock64();
           const uint32_t a_base = smem_u32(sA + stage * stage_bytes);
@@ -435,6 +450,50 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         }
         if (elect_one()) umma_commit(BAR(2 * S + 1 + buf));    // accumulator ready for the epilogue
         __syncwarp();
+      }
+    }
+  } else if (FUSE == 4 && warp >= 10) {
+    // ===================== operand transform (5 warps): halo tile -> act(BatchNorm_eval(halo tile)) in place =====================
+    if (pre_bn) {
+      const int t = (int)threadIdx.x - TC_THREADS;               // 0..159
+      const int cphys = t & 7, slot = t >> 3;                    // 16-byte chunk of a 128-byte pixel row; 20 pixel slots
+      const int hx = slot % 10, hy0 = slot / 10;                 // the MMAs read halo columns 0..9 only; rows hy0, hy0 + 2, ...
+      const int clog = cphys ^ (hx & 7);                         // 128B swizzle: chunk index ^= (row & 7), row = 16 hy + hx
+      float ps[8], pt[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) { ps[e] = sred[64 + clog * 8 + e]; pt[e] = sred[128 + clog * 8 + e]; }
+      const int fact = ACT >= 0 ? ACT : p.fold_act;
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = (int)blockIdx.x; tile < n_tiles; tile += (int)gridDim.x) {
+        const int r = tile & (p.tiles_per_img - 1);
+        const int ty = r >> p.lg_tx, tx = r & (p.tiles_x - 1);
+        const int x = tx * 8 - 1 + hx;
+        const bool xin = x >= 0 && x < p.W;
+        mbar_wait(BAR(stage), phase);                            // TMA landed (async-proxy writes visible after the wait)
+        uint8_t* base = sA + stage * stage_bytes + hx * 128 + (cphys << 4);
+#pragma unroll
+        for (int j = 0; j < 9; ++j) {
+          const int hy = hy0 + 2 * j;
+          const int y = ty * 16 - 1 + hy;
+          if (xin && y >= 0 && y < p.H) {                        // out-of-image pixels stay zero: padding of the activated tensor
+            uint4* ptr = reinterpret_cast<uint4*>(base + hy * 2048);
+            uint4 v = *ptr;
+            uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const float a = act_fwd_t<true>(fmaf(__uint_as_float(w[q] << 16), ps[2 * q], pt[2 * q]), fact);
+              const float b = act_fwd_t<true>(fmaf(__uint_as_float(w[q] & 0xFFFF0000u), ps[2 * q + 1], pt[2 * q + 1]), fact);
+              const __nv_bfloat162 ob = __floats2bfloat162_rn(a, b);
+              w[q] = *reinterpret_cast<const uint32_t*>(&ob);
+            }
+            *ptr = make_uint4(w[0], w[1], w[2], w[3]);
+          }
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic writes -> visible to tcgen05.mma
+        __syncwarp();
+        if (lane == 0) mbar_arrive(BAR(2 * S + 5 + stage));
+        if (++stage == S) { stage = 0; phase ^= 1; }
       }
     }
   } else if (warp >= 2) {
@@ -751,6 +810,11 @@ struct LvaeConvFuse {
   const float* fold_var;
   float fold_eps;
   int fold_act;
+  const float* pre_gamma;
+  const float* pre_beta;
+  const float* pre_mean;
+  const float* pre_var;
+  float pre_eps;
 };
 
 LVAE_API int lvae_conv2d_tc_ex(const void* x, const void* x2, const void* wp, const float* bias, const float* out_scale,
@@ -802,6 +866,12 @@ LVAE_API int lvae_conv2d_tc_ex(const void* x, const void* x2, const void* wp, co
                    "conv2d_tc: the folded eval-mode BatchNorm needs N == 64, bf16 output and no other epilogue fusion");
       p.fold_gamma = fuse->fold_gamma; p.fold_beta = fuse->fold_beta; p.fold_mean = fuse->fold_mean; p.fold_var = fuse->fold_var;
       p.fold_eps = fuse->fold_eps; p.fold_act = fuse->fold_act;
+      if (fuse->pre_gamma) {
+        LVAE_REQUIRE(fuse->pre_beta && fuse->pre_mean && fuse->pre_var && !x2 && Cin == 64 && ksize == 3 && W % 8 == 0 && H % 16 == 0,
+                     "conv2d_tc: the operand-path BatchNorm needs a single 64-channel input, a 3x3 kernel and halo tiles (W % 8 == 0, H % 16 == 0)");
+        p.pre_gamma = fuse->pre_gamma; p.pre_beta = fuse->pre_beta; p.pre_mean = fuse->pre_mean; p.pre_var = fuse->pre_var;
+        p.pre_eps = fuse->pre_eps;
+      }
     }
   }
   const int inputs = x2 ? 2 : 1;
@@ -849,6 +919,7 @@ LVAE_API int lvae_conv2d_tc_ex(const void* x, const void* x2, const void* wp, co
   p.tiles_per_img = (W / 8) * (H / 16);
   set_shifts(p);
   p.bo_mode = bo_env;
+  LVAE_REQUIRE(!p.pre_gamma || p.halo, "conv2d_tc: the operand-path BatchNorm needs the halo-tile path (LVAE_CONV_HALO)");
   int stages = (max_smem - wbytes - out_stage) / (p.halo ? p.stage_bytes : TC_STAGE_BYTES);
   if (stages > 8) stages = 8;
   LVAE_REQUIRE(stages >= 2, "conv2d_tc: weights leave no room for the activation pipeline");
@@ -910,8 +981,8 @@ LVAE_API int lvae_conv2d_tc_ex(const void* x, const void* x2, const void* wp, co
   }
   const int n_tiles = p.halo ? B * p.tiles_per_img : (p.M_total + TC_BM - 1) / TC_BM;
   const int grid = n_tiles < lvae_num_sms() ? n_tiles : lvae_num_sms();
-  if (p.fold_gamma && p.fold_act == ACT_ELU) lvae_launch(conv_tc_kernel<4, ACT_ELU>, grid, TC_THREADS, smem, stream, tmA0, tmA1, tmW, tmY, tmY2, p);
-  else if (p.fold_gamma) lvae_launch(conv_tc_kernel<4>, grid, TC_THREADS, smem, stream, tmA0, tmA1, tmW, tmY, tmY2, p);
+  if (p.fold_gamma && p.fold_act == ACT_ELU) lvae_launch(conv_tc_kernel<4, ACT_ELU>, grid, TC_THREADS + 160, smem, stream, tmA0, tmA1, tmW, tmY, tmY2, p);
+  else if (p.fold_gamma) lvae_launch(conv_tc_kernel<4>, grid, TC_THREADS + 160, smem, stream, tmA0, tmA1, tmW, tmY, tmY2, p);
   else if (p.gate_x && p.gate_act == ACT_ELU) lvae_launch(conv_tc_kernel<3, ACT_ELU>, grid, TC_THREADS, smem, stream, tmA0, tmA1, tmW, tmY, tmY2, p);
   else if (p.gate_x) lvae_launch(conv_tc_kernel<3>, grid, TC_THREADS, smem, stream, tmA0, tmA1, tmW, tmY, tmY2, p);
   else if (p.stats_acc) lvae_launch(conv_tc_kernel<1>, grid, TC_THREADS, smem, stream, tmA0, tmA1, tmW, tmY, tmY2, p);

@@ -517,9 +517,13 @@ def _conv_tc(x, x2, wp, bias, out_scale, res, N, ksize, flip, out_f32, nsplit=0,
         f = _capi.ConvFuse()
         f.stats_acc = _p(stats_acc)
         if fold is not None:            # eval-mode BatchNorm + activation of the consumer: (gamma, beta, mean, var, eps, act)
-            fg, fb, fm, fv, feps, fact = fold
+            fg, fb, fm, fv, feps, fact = fold[:6]
             f.fold_gamma, f.fold_beta, f.fold_mean, f.fold_var = fg.data_ptr(), fb.data_ptr(), fm.data_ptr(), fv.data_ptr()
             f.fold_eps, f.fold_act = float(feps), int(fact)
+            if len(fold) > 6 and fold[6] is not None:     # + the eval-mode BatchNorm in front of the conv: (gamma, beta, mean, var, eps)
+                pg, pb, pm, pv, peps = fold[6]
+                f.pre_gamma, f.pre_beta, f.pre_mean, f.pre_var = pg.data_ptr(), pb.data_ptr(), pm.data_ptr(), pv.data_ptr()
+                f.pre_eps = float(peps)
         if gate is not None:            # (residual input (B,H,W,64) bf16, activation id): gated residual output in the epilogue
             gx, gact = gate
             gate_out = torch.empty_like(gx)
@@ -833,6 +837,7 @@ _gate_keep_h = [True]     # set per call by gated_block(): autograd.Function.for
 # conv2 + gate conv + gate as ONE launch, the 1x1 GEMM reading the staged conv2 tile (lvae_conv_gate_tc; validated and
 # timed on the B200 in round 2: bit-identical tensors, 17.41 -> 16.71 ms per CIFAR-15 step).  LVAE_CONV_GATE_CHAIN=0 = A/B.
 _gate_chain = [os.environ.get("LVAE_CONV_GATE_CHAIN", "1") != "0"]
+_eval_bn_pre = [os.environ.get("LVAE_EVAL_BN_PRE", "1") != "0"]      # A/B aid: eval-mode BatchNorm1 on conv1's operand path
 _eval_bn_fold = [os.environ.get("LVAE_EVAL_BN_FOLD", "1") != "0"]    # A/B aid: eval-mode BatchNorm2 folded into conv1's epilogue
 
 
@@ -920,19 +925,24 @@ class GatedBlockFn(Function):
                  dt, dt, _stream())
             return out
 
-        a1 = bn_fwd(xn, bn1, sc1, saves[0], g1, b1, x_stats)
         acc2 = None
         # eval mode under no_grad (the IW evaluator's sample passes): BatchNorm2 is a fixed per-channel affine map, so it rides
         # with the activation in conv1's epilogue -- one launch and one read + write of the tensor less per block
         fold2 = (_eval_bn_fold[0] and not training and not _gate_keep_h[0] and C == 64 and m1 is None
                  and xn.dtype == torch.bfloat16 and bn2.running_mean is not None and conv1.spec.cout == 64
-                 and not conv1.spec.out_fp32 and conv1.spec.tc_forward_ok(a1, None))
+                 and not conv1.spec.out_fp32 and conv1.spec.tc_forward_ok(xn, None))
+        # ... and BatchNorm1 + activation on conv1's operand tile as it lands in shared memory (halo tiles: 16x16 and larger)
+        pre1 = fold2 and _eval_bn_pre[0] and conv1.spec.k == 3 and H % 16 == 0 and W % 8 == 0 and bn1.running_mean is not None
+        a1 = None if pre1 else bn_fwd(xn, bn1, sc1, saves[0], g1, b1, x_stats)
         if fold2:
             stats["tc_fwd"] += 1
             stats["bn_fold"] = stats.get("bn_fold", 0) + 1
+            stats["bn_pre"] = stats.get("bn_pre", 0) + (1 if pre1 else 0)
             y1 = None
-            a2 = _conv_tc(a1, None, conv1.spec.pack_tc_fwd.get(w1, torch.bfloat16), cb1, None, None, 64, conv1.spec.k, False,
-                          False, fold=(g2, b2, bn2.running_mean, bn2.running_var, bn2.eps, act))
+            a2 = _conv_tc(xn if pre1 else a1, None, conv1.spec.pack_tc_fwd.get(w1, torch.bfloat16), cb1, None, None, 64,
+                          conv1.spec.k, False, False,
+                          fold=(g2, b2, bn2.running_mean, bn2.running_var, bn2.eps, act,
+                                (g1, b1, bn1.running_mean, bn1.running_var, bn1.eps) if pre1 else None))
         elif training and C == 64:
             acc2 = sc2[0]
             _bn_clean(bn2, acc2, "fwd")

@@ -145,12 +145,13 @@ def test_eval_block_with_folded_batchnorm_matches_unfolded(monkeypatch):
     blk.eval()
     x = torch.randn(6, 16, 16, 64, device="cuda").to(torch.bfloat16).permute(0, 3, 1, 2)
     outs = []
-    for fold in (False, True):
+    for fold, pre in ((False, False), (True, False), (True, True)):
         monkeypatch.setattr(ops, "_eval_bn_fold", [fold])
-        ops.stats["bn_fold"] = 0
+        monkeypatch.setattr(ops, "_eval_bn_pre", [pre])
+        ops.stats["bn_fold"] = ops.stats["bn_pre"] = 0
         with torch.no_grad():
             outs.append(blk(x).float())
-        assert (ops.stats.get("bn_fold", 0) > 0) == fold
+        assert (ops.stats.get("bn_fold", 0) > 0) == fold and (ops.stats.get("bn_pre", 0) > 0) == pre
     # with grad enabled (a backward may follow) the fold must stay off: the pre-BatchNorm tensor is needed
     ops.stats["bn_fold"] = 0
     blk(x)
@@ -158,3 +159,34 @@ def test_eval_block_with_folded_batchnorm_matches_unfolded(monkeypatch):
     torch.cuda.synchronize()
     d = (outs[0] - outs[1]).abs().max().item()
     assert d <= 3e-2 * outs[0].abs().max().item(), d
+    assert torch.equal(outs[1], outs[2])           # BatchNorm1 on the operand path: same operand bits as the separate pass
+
+
+@pytest.mark.parametrize("case", [(3, 16, 16, 3), (2, 32, 32, 3), (2, 16, 32, 1), (5, 32, 16, 4), (150, 16, 16, 3)])
+def test_eval_batchnorm_on_the_operand_path(case):
+    """conv_tc_kernel<4> with pre_*: y = act(BN2(conv(act(BN1(x))))) in ONE launch, BatchNorm1 + activation applied to the halo
+    tile in shared memory before the MMAs read it (out-of-image pixels stay zero = padding of the activated tensor).  Against
+    the BatchNorm-apply kernel followed by the folded conv: the operand is computed with the same arithmetic, so the results
+    must be bit-identical."""
+    import lvae_b200  # noqa: F401
+    from lvae_b200 import ops
+    from lvae_b200._capi import call
+    B, H, W, act = case
+    g = torch.Generator().manual_seed(B * 100 + H + W)
+    bf = torch.bfloat16
+    x = torch.randn(B, H, W, 64, generator=g).to(bf).cuda()
+    w = (torch.randn(64, 64, 3, 3, generator=g) / 24).cuda()
+    bias = torch.randn(64, generator=g).cuda()
+    bn = [((torch.rand(64, generator=g) + 0.5).cuda(), torch.randn(64, generator=g).cuda(), torch.randn(64, generator=g).cuda(),
+           (torch.rand(64, generator=g) + 0.3).cuda()) for _ in range(2)]
+    eps = 1e-5
+    wp = ops.WeightPack(64, 64, 9, 2).get(w, bf)
+    a1 = torch.empty_like(x)
+    save = torch.empty(2, 64, device="cuda")
+    call("lvae_bn_act_fwd2", x.data_ptr(), a1.data_ptr(), None, bn[0][0].data_ptr(), bn[0][1].data_ptr(), save.data_ptr(),
+         bn[0][2].data_ptr(), bn[0][3].data_ptr(), None, B * H * W, 64, act, 0, 0.1, eps, 1, 1, ops._stream())
+    ref = ops._conv_tc(a1, None, wp, bias, None, None, 64, 3, False, False, fold=(bn[1][0], bn[1][1], bn[1][2], bn[1][3], eps, act))
+    y = ops._conv_tc(x, None, wp, bias, None, None, 64, 3, False, False,
+                     fold=(bn[1][0], bn[1][1], bn[1][2], bn[1][3], eps, act, (bn[0][0], bn[0][1], bn[0][2], bn[0][3], eps)))
+    torch.cuda.synchronize()
+    assert torch.equal(y, ref), (y.float() - ref.float()).abs().max().item()
