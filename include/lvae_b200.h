@@ -157,6 +157,11 @@ int lvae_conv2d_tc_s2(const void* x, const void* wp, const float* bias, const fl
  * lib/likelihoods.py:61: 64 -> 1): bandwidth-bound, 8 lanes per pixel.  w: torch (N,64,3,3) fp32; y (B,H,W,N) fp32 / bf16. */
 int lvae_conv3x3_narrow(const void* x, const float* w, const float* bias, void* y, int B, int H, int W, int N, int out_f32,
                         lvae_stream_t stream);
+/* The same with the input given as a WINDOW of a larger (B,Hs,Ws,64) bf16 tensor (N == 1 only): x points at the window's first
+ * pixel, row_pitch / img_pitch are the elements between consecutive rows / images (0 = dense).  The centred crop in front of the
+ * likelihood (models/lvae.py:143, boilr crop_img_tensor) then needs no pass of its own. */
+int lvae_conv3x3_narrow_ex(const void* x, const float* w, const float* bias, void* y, int B, int H, int W, int N, int out_f32,
+                           int row_pitch, long long img_pitch, lvae_stream_t stream);
 /* profiling aid: CTA 0 of subsequent lvae_conv2d_tc launches records clock64 stamps per tile into dev_buf (NULL = off) */
 void lvae_conv2d_tc_debug(long long* dev_buf);
 /* the same for lvae_conv_gate_tc (16 stamps per tile: epilogue phases in slots 0..6, MMA warp in 8..10) */

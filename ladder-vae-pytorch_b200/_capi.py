@@ -26,6 +26,7 @@ _SIGNATURES = {
     "lvae_conv2d_tc_s2": [P, P, P, P, P, I, I, I, I, I, P],
     "lvae_conv_gate_tc": [P, P, P, P, P, P, P, P, P, P, P, I, I, I, I, P],
     "lvae_conv3x3_narrow": [P, P, P, P, I, I, I, I, I, P],
+    "lvae_conv3x3_narrow_ex": [P, P, P, P, I, I, I, I, I, I, L, P],
     "lvae_channel_scale": [P, P, P, I, I, I, I, P],
     "lvae_conv2d_wgrad_tc": [P, P, P, P, P, P, I, I, I, I, I, I, I, I, I, P],
     "lvae_conv2d_wgrad_tc_acc": [P, P, P, P, I, I, I, I, I, I, I, P],

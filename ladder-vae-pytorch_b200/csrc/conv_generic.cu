@@ -639,9 +639,111 @@ __global__ void __launch_bounds__(256) conv3x3_narrow_kernel(const __nv_bfloat16
   }
 }
 
+// N = 1 (the Bernoulli head): row-segment formulation.  A group of 8 lanes (8 channels each) owns 8 consecutive output pixels of
+// one image row: it reads the 3 x 10 input pixels under them ONCE (30 coalesced 128-byte rows instead of 8 x 9 = 72), keeps
+// the 9 x 8 weights of its channel slice in registers, and finishes with a 7-shuffle transposing reduction that leaves one
+// pixel's sum in every lane.  ~115 instructions per output and lane against ~370 of the per-pixel kernel above (which spent a
+// third of them on 64-bit index divisions).  The input may be a WINDOW of a larger NHWC tensor (row / image pitch in elements):
+// the centred crop in front of the likelihood (models/lvae.py:143) then costs no pass of its own.
+template <typename TO>
+__global__ void __launch_bounds__(256) conv3x3_narrow1_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ w,
+                                                              const float* __restrict__ bias, TO* __restrict__ y, int B, int H,
+                                                              int W, int row_pitch, long long img_pitch) {
+  pdl_wait();
+  pdl_launch();
+  const int sub = threadIdx.x & 7;                          // which 8 channels of a pixel
+  float wr[9][8];                                           // torch layout (1, 64, 3, 3): w[ci * 9 + t]
+#pragma unroll
+  for (int t = 0; t < 9; ++t)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) wr[t][j] = __ldg(w + (sub * 8 + j) * 9 + t);
+  const float b0 = bias ? __ldg(bias) : 0.f;
+  const int segs_per_row = (W + 7) >> 3;
+  const int n_seg = B * H * segs_per_row;
+  const int group = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 3), n_groups = (int)((gridDim.x * blockDim.x) >> 3);
+  // all 32 lanes of a warp run the same number of iterations (the shuffles below are warp-wide)
+  const int iters = (n_seg + n_groups - 1) / n_groups;
+  for (int itn = 0; itn < iters; ++itn) {
+    const int seg = group + itn * n_groups;
+    const bool live = seg < n_seg;
+    const int sg = live ? seg : 0;
+    const int row_id = sg / segs_per_row;                   // b * H + y
+    const int x0 = (sg - row_id * segs_per_row) << 3;
+    const int b = row_id / H, py = row_id - b * H;
+    float acc[8];
+#pragma unroll
+    for (int o = 0; o < 8; ++o) acc[o] = 0.f;
+#pragma unroll
+    for (int dy = 0; dy < 3; ++dy) {
+      const int iy = py + dy - 1;
+      const bool rowin = live && iy >= 0 && iy < H;
+      const __nv_bfloat16* rp = x + (long long)b * img_pitch + (long long)iy * row_pitch + sub * 8;
+#pragma unroll
+      for (int hx = 0; hx < 10; ++hx) {
+        const int ix = x0 + hx - 1;
+        if (rowin && ix >= 0 && ix < W) {
+          const uint4 u = *reinterpret_cast<const uint4*>(rp + (long long)ix * 64);
+          const uint32_t wd[4] = {u.x, u.y, u.z, u.w};
+          float v[8];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) { v[2 * j] = __uint_as_float(wd[j] << 16); v[2 * j + 1] = __uint_as_float(wd[j] & 0xFFFF0000u); }
+#pragma unroll
+          for (int dx = 0; dx < 3; ++dx) {
+            const int o = hx - dx;                           // output pixel x0 + o reads input x0 + o + dx - 1 = x0 + hx - 1
+            if (o >= 0 && o < 8) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) acc[o] = fmaf(v[j], wr[dy * 3 + dx][j], acc[o]);
+            }
+          }
+        }
+      }
+    }
+    // transposing reduction over the 8 lanes of the group: lane `sub` ends with the sum of output pixel `sub`
+#pragma unroll
+    for (int o = 0; o < 4; ++o) {
+      const float keep = (sub & 4) ? acc[o + 4] : acc[o], give = (sub & 4) ? acc[o] : acc[o + 4];
+      acc[o] = keep + __shfl_xor_sync(0xffffffffu, give, 4);
+    }
+#pragma unroll
+    for (int o = 0; o < 2; ++o) {
+      const float keep = (sub & 2) ? acc[o + 2] : acc[o], give = (sub & 2) ? acc[o] : acc[o + 2];
+      acc[o] = keep + __shfl_xor_sync(0xffffffffu, give, 2);
+    }
+    {
+      const float keep = (sub & 1) ? acc[1] : acc[0], give = (sub & 1) ? acc[0] : acc[1];
+      acc[0] = keep + __shfl_xor_sync(0xffffffffu, give, 1);
+    }
+    if (live && x0 + sub < W) st1<TO>(y + (long long)row_id * W + x0 + sub, acc[0] + b0);
+  }
+}
+
+// x may be a window of a larger (B, Hs, Ws, 64) tensor: row_pitch / img_pitch = elements between consecutive rows / images of
+// the window (0 = dense: W * 64 and H * W * 64); x points at the window's first pixel.
+LVAE_API int lvae_conv3x3_narrow_ex(const void* x, const float* w, const float* bias, void* y, int B, int H, int W, int N,
+                                    int out_f32, int row_pitch, long long img_pitch, cudaStream_t stream);
+
 LVAE_API int lvae_conv3x3_narrow(const void* x, const float* w, const float* bias, void* y, int B, int H, int W, int N,
                                  int out_f32, cudaStream_t stream) {
+  return lvae_conv3x3_narrow_ex(x, w, bias, y, B, H, W, N, out_f32, 0, 0, stream);
+}
+
+LVAE_API int lvae_conv3x3_narrow_ex(const void* x, const float* w, const float* bias, void* y, int B, int H, int W, int N,
+                                    int out_f32, int row_pitch, long long img_pitch, cudaStream_t stream) {
   LVAE_REQUIRE(x && w && y && B > 0 && H > 0 && W > 0 && N >= 1 && N <= 4, "conv3x3_narrow: bad args (1 <= N <= 4)");
+  if (!row_pitch) row_pitch = W * 64;
+  if (!img_pitch) img_pitch = (long long)H * W * 64;
+  const bool dense = row_pitch == W * 64 && img_pitch == (long long)H * W * 64;
+  LVAE_REQUIRE(dense || N == 1, "conv3x3_narrow: a windowed input needs N == 1");
+  LVAE_REQUIRE(row_pitch % 8 == 0 && img_pitch % 8 == 0 && ((size_t)x & 15) == 0, "conv3x3_narrow: the window must keep 16-byte alignment");
+  if (N == 1 && (long long)B * H * ((W + 7) / 8) < (1LL << 30)) {
+    const long long groups = (long long)B * H * ((W + 7) / 8);
+    const int grid = (int)min((long long)8 * lvae_num_sms(), (groups * 8 + 255) / 256);
+    if (out_f32) lvae_launch(conv3x3_narrow1_kernel<float>, grid, 256, 0, stream, (const __nv_bfloat16*)x, w, bias, (float*)y, B, H, W, row_pitch, img_pitch);
+    else lvae_launch(conv3x3_narrow1_kernel<__nv_bfloat16>, grid, 256, 0, stream, (const __nv_bfloat16*)x, w, bias, (__nv_bfloat16*)y, B, H, W, row_pitch, img_pitch);
+    LVAE_COUNT_LAUNCH();
+    LVAE_CHECK_LAUNCH("conv3x3_narrow");
+    return LVAE_OK;
+  }
   const long long M = (long long)B * H * W;
   const int grid = (int)min((long long)8 * lvae_num_sms(), (M * 8 + 255) / 256);
   if (out_f32) lvae_launch(conv3x3_narrow_kernel<float>, grid, 256, 0, stream, (const __nv_bfloat16*)x, w, bias, (float*)y, M, H, W, N);

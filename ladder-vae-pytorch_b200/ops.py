@@ -548,7 +548,7 @@ def _gather(x, x2, wp, ld, bias, in_scale, out_scale, res, B, Hi, Wi, C1, C2, Ho
     return y
 
 
-def conv_forward_raw(spec: ConvSpec, xn, x2n, weight, bias, out_scale, resn, stats_acc=None):
+def conv_forward_raw(spec: ConvSpec, xn, x2n, weight, bias, out_scale, resn, stats_acc=None, window=None):
     """(conv(cat(xn, x2n)) + bias) * out_scale + resn on NHWC tensors.  bf16 activations on eligible shapes run on
     the tensor cores (lvae_conv2d_tc), everything else on the CUDA-core implicit GEMM (lvae_conv2d_gather)."""
     B, Hi, Wi, C1 = xn.shape
@@ -571,9 +571,11 @@ def conv_forward_raw(spec: ConvSpec, xn, x2n, weight, bias, out_scale, resn, sta
         # narrow head (Bernoulli parameter_net, 64 -> 1): a GEMM tile would be 63/64 padding
         stats["narrow_fwd"] = stats.get("narrow_fwd", 0) + 1
         y = torch.empty((B, Ho, Wo, spec.cout), dtype=torch.float32 if want_f32 else torch.bfloat16, device=xn.device)
-        call("lvae_conv3x3_narrow", xn.data_ptr(), weight.data_ptr(), _p(bias), y.data_ptr(), B, Hi, Wi, spec.cout,
-             1 if want_f32 else 0, _stream())
+        rp, ip = window if window is not None else (0, 0)     # xn may be a window of a larger NHWC tensor (zero-copy crop)
+        call("lvae_conv3x3_narrow_ex", xn.data_ptr(), weight.data_ptr(), _p(bias), y.data_ptr(), B, Hi, Wi, spec.cout,
+             1 if want_f32 else 0, int(rp), int(ip), _stream())
         return (y, False) if stats_acc is not None else y
+    assert window is None, "only the narrow head convolution reads a windowed input"
     if padded and not spec.tc_forward_ok(xn, x2n):
         xn, C1 = xn[..., :spec.cin].contiguous(), spec.cin
     if spec.tc_forward_ok(xn, x2n) and (resn is None or resn.dtype == (torch.float32 if want_f32 else torch.bfloat16)):
@@ -726,7 +728,16 @@ class Conv2dFn(Function):
         # x_lowp: the kernel's actual operand when the caller already holds a bf16, channel-padded copy of x (the stochastic
         # kernel writes z both as fp32 and as the 64-channel bf16 operand of conv_out); x itself then only carries the autograd
         # edge, and the data gradient comes back in x's own shape and dtype (fp32 epilogue): no pad / slice / cast passes
-        xn = nhwc(x_lowp) if x_lowp is not None else nhwc(x)
+        window = None
+        xv = x.permute(0, 2, 3, 1)
+        if (x_lowp is None and x2 is None and res is None and out_scale is None and not torch.is_grad_enabled()
+                and not xv.is_contiguous() and spec.cout == 1 and spec.k == 3 and spec.stride == 1 and spec.pad == 1
+                and not spec.transposed and xv.dtype == torch.bfloat16 and xv.shape[3] == 64 == spec.cin
+                and xv.stride(3) == 1 and xv.stride(2) == 64):
+            # a cropped view of an NHWC activation (ops.crop under no_grad): the narrow head conv reads the window in place
+            xn, window = xv, (xv.stride(1), xv.stride(0))
+        else:
+            xn = nhwc(x_lowp) if x_lowp is not None else nhwc(x)
         x2n = nhwc(x2) if x2 is not None else None
         resn = nhwc(res) if res is not None else None
         if out_scale is not None:
@@ -740,7 +751,7 @@ class Conv2dFn(Function):
             if fused:
                 spec._last_stats = (acc, y.shape[0] * y.shape[1] * y.shape[2], _bn_epoch[0])
         else:
-            y = conv_forward_raw(spec, xn, x2n, weight, bias, out_scale, resn)
+            y = conv_forward_raw(spec, xn, x2n, weight, bias, out_scale, resn, window=window)
         ctx.spec = spec
         ctx.save_for_backward(xn, x2n, weight, bias, out_scale)
         ctx.has_res = res is not None
@@ -1158,9 +1169,22 @@ class CropFn(Function):
         return as_nchw(dx), None
 
 
+_crop_view = [os.environ.get("LVAE_CROP_VIEW", "1") != "0"]      # A/B aid
+
+
 def crop(x, size):
     if tuple(x.shape[2:]) == tuple(int(s) for s in size):
         return x
+    if _crop_view[0] and not torch.is_grad_enabled() and x.is_cuda:
+        # nothing runs backward (IW evaluator, sampling): the centred crop is a strided view of the NHWC buffer -- the Bernoulli
+        # head's narrow conv reads the window in place, any other consumer makes it contiguous itself (ops.nhwc)
+        xn = x.permute(0, 2, 3, 1)
+        h, w = int(size[0]), int(size[1])
+        dr, dc = xn.shape[1] - h, xn.shape[2] - w
+        if dr < 0 or dc < 0:
+            raise ValueError("trying to crop to a larger size")
+        if xn.is_contiguous():
+            return xn[:, dr // 2:dr // 2 + h, dc // 2:dc // 2 + w, :].permute(0, 3, 1, 2)
     return CropFn.apply(x, size)
 
 

@@ -192,3 +192,33 @@ def test_narrow_head_conv(cout, H, W, B, out_fp32):
     torch.cuda.synchronize()
     assert rel_err(xd.grad.float(), xr.grad) < 8e-3
     assert rel_err(mod.weight.grad, wr.grad) < 8e-3
+
+
+@pytest.mark.parametrize("B,Hs,Ws,h,w", [(5, 32, 32, 28, 28), (3, 16, 16, 13, 9), (2, 32, 32, 32, 30), (65, 32, 32, 28, 28)])
+def test_narrow_head_conv_reads_a_cropped_view_in_place(B, Hs, Ws, h, w):
+    """Under no_grad ops.crop returns a strided view of the NHWC buffer and the 64 -> 1 head conv (row-segment kernel) reads the
+    window in place: same result as the copying crop followed by the conv on a dense tensor, and as the fp64 reference; the
+    zero padding is that of the WINDOW, not of the surrounding tensor."""
+    import lvae_b200  # noqa: F401
+    from lvae_b200.lib.nn import Conv2d
+    from lvae_b200 import ops
+    g = torch.Generator().manual_seed(B + Hs + h)
+    x = torch.randn(B, 64, Hs, Ws, generator=g).to(torch.bfloat16)
+    mod = Conv2d(64, 1, 3, padding=1).cuda()
+    mod.spec.out_fp32 = True
+    xd = phys_nhwc(x.cuda())
+    y0, x0 = (Hs - h) // 2, (Ws - w) // 2
+    ref = F.conv2d(x.double()[:, :, y0:y0 + h, x0:x0 + w], mod.weight.detach().double().cpu(), mod.bias.detach().double().cpu(), padding=1)
+    with torch.no_grad():
+        v = ops.crop(xd, (h, w))
+        assert v.data_ptr() != xd.data_ptr() or (y0 == 0 and x0 == 0)
+        assert v.permute(0, 2, 3, 1).untyped_storage().data_ptr() == xd.permute(0, 2, 3, 1).untyped_storage().data_ptr()   # a view
+        y_view = mod(v)
+        dense = phys_nhwc(x[:, :, y0:y0 + h, x0:x0 + w].contiguous().cuda())
+        y_dense = mod(dense)
+    torch.cuda.synchronize()
+    assert torch.equal(y_view, y_dense)
+    assert rel_err(y_view.float(), ref) < 1e-5
+    # with grad enabled the crop is the copying autograd node
+    c = ops.crop(xd.requires_grad_(True), (h, w))
+    assert c.permute(0, 2, 3, 1).is_contiguous()
