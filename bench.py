@@ -336,7 +336,7 @@ def kernel_shares(torch, engine):
         return {"error": repr(e)[:200]}
 
 
-def time_train(cx, cfg_name, batch, dtype, steps, warmup, graph=True, side_streams=2, with_e2e=True, sampler=None,
+def time_train(cx, cfg_name, batch, dtype, steps, warmup, graph=True, side_streams=3, with_e2e=True, sampler=None,
                shares=False, dp_check=False):
     """Build the model, warm up, time `steps` steps device-resident (`value`) and through TrainEngine.step(x_host) (`e2e`)."""
     torch = cx.torch
@@ -526,7 +526,7 @@ def main():
     ap.add_argument("--iw-full-forward", action="store_true",
                     help="IW: recompute the bottom-up pass for every sample like the reference's loop (default: once per batch)")
     ap.add_argument("--no-side-stream", action="store_true", help="keep weight-gradient kernels on the main stream")
-    ap.add_argument("--side-streams", type=int, default=2, help="number of side streams the weight-gradient kernels rotate over")
+    ap.add_argument("--side-streams", type=int, default=3, help="number of side streams the weight-gradient kernels rotate over")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-hbm-rooflines", action="store_true", help="skip the stochastic / likelihood kernel microbenchmarks")

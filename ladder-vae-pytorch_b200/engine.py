@@ -267,7 +267,7 @@ class TrainEngine:
         self._unpacked = set()
         self.x = torch.zeros((batch_size, model.color_ch) + tuple(model.img_shape), dtype=torch.float32, device=dev)
         self.use_graph = use_graph
-        n_side = int(wgrad_side_stream) if not isinstance(wgrad_side_stream, bool) else (2 if wgrad_side_stream else 0)
+        n_side = int(wgrad_side_stream) if not isinstance(wgrad_side_stream, bool) else (3 if wgrad_side_stream else 0)
         # Side streams run at the lowest priority and the step is captured on a high-priority stream: when SMs free up the
         # block scheduler serves the dependent main chain (fwd / dgrad / BatchNorm) first, the weight gradients fill the rest.
         lo, hi = torch.cuda.Stream.priority_range() if hasattr(torch.cuda.Stream, "priority_range") else (0, -1)

@@ -119,7 +119,7 @@ def _run_engine(cfg_name, dtype, use_graph, steps, batch, seed=7, side=True):
 @pytest.mark.parametrize("cfg_name,dtype", [("mnist3", torch.float32), ("mnist3", torch.bfloat16),
                                             ("cifar15", torch.bfloat16)])
 def test_graph_replay_equals_eager_steps(cfg_name, dtype):
-    """The benched path (CUDA-graph replay, weight gradients on two side streams, packed TMA reduce-adds, batched unpack,
+    """The benched path (CUDA-graph replay, weight gradients on three side streams, packed TMA reduce-adds, batched unpack,
     graph-advanced Philox) against the same engine run eagerly on ONE stream, from the same seed.  Same kernels and the same
     noise, so the only legitimate difference is the summation order of floating-point atomics / reduce-adds; a race
     between the side-stream weight gradients, the unpack and the optimizer, a stale packed weight or a capture bug shows up
