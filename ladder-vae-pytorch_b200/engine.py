@@ -271,7 +271,9 @@ class TrainEngine:
         # Side streams run at the lowest priority and the step is captured on a high-priority stream: when SMs free up the
         # block scheduler serves the dependent main chain (fwd / dgrad / BatchNorm) first, the weight gradients fill the rest.
         lo, hi = torch.cuda.Stream.priority_range() if hasattr(torch.cuda.Stream, "priority_range") else (0, -1)
-        prio = os.environ.get("LVAE_STREAM_PRIORITY", "0") != "0"       # measured: 19.25 ms with priorities vs 18.83 ms without
+        # measured: round 1 (two side streams, 18.8 ms step) 19.25 ms with priorities vs 18.83 without; end of round 2 (three side
+        # streams) 14.41-14.44 ms with vs 14.50 without -> on by default; LVAE_STREAM_PRIORITY=0 is the A/B switch
+        prio = os.environ.get("LVAE_STREAM_PRIORITY", "1") != "0"
         self.side_stream = [torch.cuda.Stream(device=dev, priority=lo if prio else 0) for _ in range(n_side)] if n_side else None
         self.main_stream = torch.cuda.Stream(device=dev, priority=hi if prio else 0)
         self.graph_fb: Optional[torch.cuda.CUDAGraph] = None
