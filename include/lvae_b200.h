@@ -209,6 +209,13 @@ int lvae_bn_act_bwd2(const void* dy, const void* x, void* dx, const float* save,
                      const float* beta, double* acc, float* dgamma, float* dbeta, const float* post_scale,
                      const void* add, long long P, int hw, int C, int act, int training, int dtype,
                      int skip_reduce, lvae_stream_t stream);
+/* The same apply pass (statistics sums already in acc) that also runs the gate backward (lib/nn.py:121-126) of the residual block
+ * that PRODUCED x -- the next block of the backward pass, whose output gradient is exactly this dx: gate_dh (P,2C) =
+ * gate'(dx, gate_h).  bf16 only.  One launch and one re-read of dx less per pair of adjacent gated blocks. */
+int lvae_bn_act_bwd2_gate(const void* dy, const void* x, void* dx, const float* save, const float* gamma, const float* beta,
+                          double* acc, float* dgamma, float* dbeta, const float* post_scale, const void* add,
+                          const void* gate_h, void* gate_dh, long long P, int hw, int C, int act, int gate_act, int training,
+                          lvae_stream_t stream);
 
 /* ---- GateLayer2d product + residual: lib/nn.py:121-126 and :99 ----
  * h (P,2C): out = act(h[:, :C]) * sigmoid(h[:, C:]) + res */

@@ -42,6 +42,7 @@ _SIGNATURES = {
     "lvae_bn_act_bwd": [P, P, P, P, P, P, P, P, P, P, L, I, I, I, I, P],
     "lvae_bn_act_fwd2": [P, P, P, P, P, P, P, P, P, L, I, I, I, F, F, I, I, P],
     "lvae_bn_act_bwd2": [P, P, P, P, P, P, P, P, P, P, P, L, I, I, I, I, I, I, P],
+    "lvae_bn_act_bwd2_gate": [P, P, P, P, P, P, P, P, P, P, P, P, P, L, I, I, I, I, I, P],
     "lvae_gate_fwd_stats": [P, P, P, P, L, I, I, I, P],
     "lvae_gate_fwd": [P, P, P, L, I, I, I, P],
     "lvae_gate_bwd": [P, P, P, L, I, I, I, P],

@@ -864,16 +864,21 @@ __global__ void bn_act_fwd2_kernel(const TI* __restrict__ x, TO* __restrict__ y,
   }
 }
 
-template <typename T, int V, int ACT = -1>
-__global__ void __launch_bounds__(256, 3) bn_act_bwd2_kernel(const T* __restrict__ dy, const T* __restrict__ x, T* __restrict__ dx,
+// GATE: the gate backward of the residual block that PRODUCED x (the next block of the backward pass) rides in the same pass --
+// dx of this BatchNorm (+ residual gradient) is exactly that block's output gradient: dh = gate'(dx, gh) is written next to dx,
+// one launch and one re-read of dx less per pair of adjacent blocks (ops.GatedBlockFn hands the pending apply over).
+template <typename T, int V, int ACT = -1, bool GATE = false>
+__global__ void __launch_bounds__(256, GATE ? 2 : 3) bn_act_bwd2_kernel(const T* __restrict__ dy, const T* __restrict__ x, T* __restrict__ dx,
                                    const float* __restrict__ save, const float* __restrict__ gamma,
                                    const float* __restrict__ beta, const double* __restrict__ acc,
                                    float* dgamma, float* dbeta, const float* __restrict__ post_scale,
                                    const T* __restrict__ add, long long nvec, long long P, int hw, int C, int act_rt,
-                                   int training) {
+                                   int training, const T* __restrict__ gh = nullptr, T* __restrict__ gdh = nullptr,
+                                   int gate_act_rt = 0) {
   pdl_wait();
   pdl_launch();
   const int act = ACT >= 0 ? ACT : act_rt;
+  const int gact = ACT >= 0 ? ACT : gate_act_rt;          // (the ELU instantiation serves blocks whose gate is ELU as well)
   // per-channel constants live in shared memory (two float4 per channel), not in 6 x V registers per thread
   __shared__ __align__(16) float s_t[6][256];                     // mean, rstd, gamma, beta, m1, m2 (SoA: conflict-free V-wide reads)
   const int CV = C / V;
@@ -881,11 +886,16 @@ __global__ void __launch_bounds__(256, 3) bn_act_bwd2_kernel(const T* __restrict
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const int c = (int)(i % CV) * V;
   bool has = i < nvec;
-  RawV<T, V> rx, rd, ra;
+  RawV<T, V> rx, rd, ra, rha, rhg;
   if (has) {                                                       // in flight during the prologue
     rx = ldraw<T, V>(x + i * V);
     rd = ldraw<T, V>(dy + i * V);
     if (add) ra = ldraw<T, V>(add + i * V);
+    if (GATE) {
+      const size_t hrow = (size_t)((unsigned)i / (unsigned)CV) * 2 * C + c;
+      rha = ldraw<T, V>(gh + hrow);
+      rhg = ldraw<T, V>(gh + hrow + C);
+    }
   }
   const double invP = 1.0 / (double)P;
   for (int ch = threadIdx.x; ch < C; ch += blockDim.x) {
@@ -901,16 +911,22 @@ __global__ void __launch_bounds__(256, 3) bn_act_bwd2_kernel(const T* __restrict
   }
   __syncthreads();
   while (has) {
-    float xs[V], ds[V], av[V], o[V];
+    float xs[V], ds[V], av[V], o[V], ha[V], hg[V];
     unraw(rx, xs);
     unraw(rd, ds);
     if (add) unraw(ra, av);
+    if (GATE) { unraw(rha, ha); unraw(rhg, hg); }
     const long long inext = i + stride;
     const bool hn = inext < nvec;
     if (hn) {
       rx = ldraw<T, V>(x + inext * V);
       rd = ldraw<T, V>(dy + inext * V);
       if (add) ra = ldraw<T, V>(add + inext * V);
+      if (GATE) {
+        const size_t hrow = (size_t)((unsigned)inext / (unsigned)CV) * 2 * C + c;
+        rha = ldraw<T, V>(gh + hrow);
+        rhg = ldraw<T, V>(gh + hrow + C);
+      }
     }
     int cc = c;
     asm volatile("" : "+r"(cc));                                  // keep the table reads inside the loop (not hoisted into 6 x V registers)
@@ -938,6 +954,20 @@ __global__ void __launch_bounds__(256, 3) bn_act_bwd2_kernel(const T* __restrict
       for (int j = 0; j < V; ++j) o[j] += av[j];
     }
     stv<T, V>(dx + i * V, o);
+    if (GATE) {
+      // same arithmetic as gate_bwd_kernel on dx AS STORED (rounded to T): bit-identical to the two-launch route
+      float da[V], dg[V];
+#pragma unroll
+      for (int j = 0; j < V; ++j) {
+        const float dv = round_to<T>(o[j]);
+        const float sg = sigmoid_t<sizeof(T) == 2>(hg[j]);
+        da[j] = dv * sg * act_bwd_t<sizeof(T) == 2>(ha[j], gact);
+        dg[j] = dv * act_fwd_t<sizeof(T) == 2>(ha[j], gact) * sg * (1.f - sg);
+      }
+      const size_t hrow = (size_t)((unsigned)i / (unsigned)CV) * 2 * C + c;
+      stv<T, V>(gdh + hrow, da);
+      stv<T, V>(gdh + hrow + C, dg);
+    }
     i = inext;
     has = hn;
   }
@@ -1015,19 +1045,48 @@ LVAE_API int lvae_bn_act_bwd2(const void* dy, const void* x, void* dx, const flo
     int g = ew_grid_aligned(nv, 256, C / 8, act == ACT_ELU ? occ_elu : occ_any);
     if (act == ACT_ELU)
       lvae_launch(bn_act_bwd2_kernel<__nv_bfloat16, 8, ACT_ELU>, g, 256, 0, stream, (const __nv_bfloat16*)dy, (const __nv_bfloat16*)x, (__nv_bfloat16*)dx, save,
-          gamma, beta, acc, dgamma, dbeta, post_scale, (const __nv_bfloat16*)add, nv, P, hw, C, act, training);
+          gamma, beta, acc, dgamma, dbeta, post_scale, (const __nv_bfloat16*)add, nv, P, hw, C, act, training,
+          (const __nv_bfloat16*)nullptr, (__nv_bfloat16*)nullptr, 0);
     else
       lvae_launch(bn_act_bwd2_kernel<__nv_bfloat16, 8>, g, 256, 0, stream, (const __nv_bfloat16*)dy, (const __nv_bfloat16*)x, (__nv_bfloat16*)dx, save,
-          gamma, beta, acc, dgamma, dbeta, post_scale, (const __nv_bfloat16*)add, nv, P, hw, C, act, training);
+          gamma, beta, acc, dgamma, dbeta, post_scale, (const __nv_bfloat16*)add, nv, P, hw, C, act, training,
+          (const __nv_bfloat16*)nullptr, (__nv_bfloat16*)nullptr, 0);
   } else {
     int g = ew_grid_aligned(nq, 256, C / 4);
     if (dtype == 0)
-      lvae_launch(bn_act_bwd2_kernel<float, 4>, g, 256, 0, stream, (const float*)dy, (const float*)x, (float*)dx, save, gamma, beta, acc, dgamma, dbeta, post_scale, (const float*)add, nq, P, hw, C, act, training);
+      lvae_launch(bn_act_bwd2_kernel<float, 4>, g, 256, 0, stream, (const float*)dy, (const float*)x, (float*)dx, save, gamma, beta, acc, dgamma, dbeta, post_scale, (const float*)add, nq, P, hw, C, act, training, (const float*)nullptr, (float*)nullptr, 0);
     else
-      lvae_launch(bn_act_bwd2_kernel<__nv_bfloat16, 4>, g, 256, 0, stream, (const __nv_bfloat16*)dy, (const __nv_bfloat16*)x, (__nv_bfloat16*)dx, save, gamma, beta, acc, dgamma, dbeta, post_scale, (const __nv_bfloat16*)add, nq, P, hw, C, act, training);
+      lvae_launch(bn_act_bwd2_kernel<__nv_bfloat16, 4>, g, 256, 0, stream, (const __nv_bfloat16*)dy, (const __nv_bfloat16*)x, (__nv_bfloat16*)dx, save, gamma, beta, acc, dgamma, dbeta, post_scale, (const __nv_bfloat16*)add, nq, P, hw, C, act, training, (const __nv_bfloat16*)nullptr, (__nv_bfloat16*)nullptr, 0);
   }
   LVAE_COUNT_LAUNCH();
   LVAE_CHECK_LAUNCH("bn_act_bwd2");
+  return LVAE_OK;
+}
+
+// BatchNorm-backward apply of one residual block (dx = BN'(dy, x) + add) and the gate backward of the block that produced x
+// (dh = gate'(dx, gh), gh / dh: (P, 2C)) in one pass.  bf16, C % 8 == 0, C <= 256; the statistics sums are already in acc.
+LVAE_API int lvae_bn_act_bwd2_gate(const void* dy, const void* x, void* dx, const float* save, const float* gamma,
+                                   const float* beta, double* acc, float* dgamma, float* dbeta, const float* post_scale,
+                                   const void* add, const void* gate_h, void* gate_dh, long long P, int hw, int C, int act,
+                                   int gate_act, int training, cudaStream_t stream) {
+  LVAE_REQUIRE(dy && x && dx && save && gamma && beta && acc && gate_h && gate_dh && P > 0 && bn_c_ok(C) && C % 8 == 0,
+               "bn_act_bwd2_gate: bad args");
+  LVAE_REQUIRE(P * (long long)C < (1LL << 32), "bn_act_bwd2_gate: more than 2^32 elements");
+  typedef __nv_bfloat16 bf;
+  const long long nv = P * (C / 8);
+  if (act == ACT_ELU && gate_act == ACT_ELU) {
+    static const int occ = resident_ctas(bn_act_bwd2_kernel<bf, 8, ACT_ELU, true>);
+    const int g = ew_grid_aligned(nv, 256, C / 8, occ);
+    lvae_launch(bn_act_bwd2_kernel<bf, 8, ACT_ELU, true>, g, 256, 0, stream, (const bf*)dy, (const bf*)x, (bf*)dx, save, gamma, beta,
+                acc, dgamma, dbeta, post_scale, (const bf*)add, nv, P, hw, C, act, training, (const bf*)gate_h, (bf*)gate_dh, gate_act);
+  } else {
+    static const int occ = resident_ctas(bn_act_bwd2_kernel<bf, 8, -1, true>);
+    const int g = ew_grid_aligned(nv, 256, C / 8, occ);
+    lvae_launch(bn_act_bwd2_kernel<bf, 8, -1, true>, g, 256, 0, stream, (const bf*)dy, (const bf*)x, (bf*)dx, save, gamma, beta,
+                acc, dgamma, dbeta, post_scale, (const bf*)add, nv, P, hw, C, act, training, (const bf*)gate_h, (bf*)gate_dh, gate_act);
+  }
+  LVAE_COUNT_LAUNCH();
+  LVAE_CHECK_LAUNCH("bn_act_bwd2_gate");
   return LVAE_OK;
 }
 

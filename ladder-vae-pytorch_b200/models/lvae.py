@@ -15,7 +15,7 @@ from lvae_b200.boilr_compat import BaseGenerativeModel
 from lvae_b200.lib.likelihoods import (BernoulliLikelihood, DiscretizedLogisticLikelihood,
                                        DiscretizedLogisticMixLikelihood, GaussianLikelihood)
 from lvae_b200.lib.nn import Conv2d, Dropout2d, Interpolate, NONLIN
-from .lvae_layers import BottomUpDeterministicResBlock, BottomUpLayer, TopDownDeterministicResBlock, TopDownLayer
+from .lvae_layers import BottomUpDeterministicResBlock, BottomUpLayer, TopDownDeterministicResBlock, TopDownLayer, _BlockStack
 
 
 class LadderVAE(BaseGenerativeModel):
@@ -70,7 +70,7 @@ class LadderVAE(BaseGenerativeModel):
         final = [] if no_initial_downscaling else [Interpolate(scale=2)]
         final += [TopDownDeterministicResBlock(c_in=n_filters, c_out=n_filters, gated=gated, **block_kw)
                   for _ in range(blocks_per_layer)]
-        self.final_top_down = nn.Sequential(*final)
+        self.final_top_down = _BlockStack(*final)
 
         if likelihood_form == "bernoulli":
             self.likelihood = BernoulliLikelihood(n_filters, color_ch)

@@ -7,6 +7,7 @@ from __future__ import annotations
 import torch
 from torch import nn
 
+from lvae_b200 import ops
 from lvae_b200.lib.nn import Conv2d, ConvTranspose2d, LeakyReLU, ResidualBlock, ResidualGatedBlock, _hooked
 from lvae_b200.lib.stochastic import NormalStochasticBlock2d
 
@@ -56,6 +57,24 @@ class BottomUpDeterministicResBlock(ResBlockWithResampling):
         super().__init__("bottom-up", *args, **kwargs)
 
 
+class _BlockStack(nn.Sequential):
+    """nn.Sequential of residual blocks (same child indices, hence the same state_dict keys) that tells the kernel layer when
+    a block's output is consumed by the next gated block of the stack and by nothing else -- no resampling / 1x1 conv in
+    between, no hooks: the two blocks' adjacent elementwise backward passes then run as one launch (ops._pending_bn1)."""
+
+    def forward(self, x):
+        mods = list(self)
+        for i, m in enumerate(mods):
+            nxt = mods[i + 1] if i + 1 < len(mods) else None
+            ops.mark_block_output_private(
+                nxt is not None and isinstance(m, ResBlockWithResampling) and isinstance(nxt, ResBlockWithResampling)
+                and m.post_conv is None and nxt.pre_conv is None and not _hooked(m) and not _hooked(nxt)
+                and not self._forward_hooks)
+            x = m(x)
+            ops.mark_block_output_private(False)
+        return x
+
+
 def _resampling_stack(block_cls, n_blocks, n_filters, n_resample, flag, **kw):
     """n_blocks residual blocks, the first n_resample of which change resolution."""
     return [block_cls(n_filters, n_filters, **{flag: i < n_resample}, **kw) for i in range(n_blocks)]
@@ -67,7 +86,7 @@ class BottomUpLayer(nn.Module):
     def __init__(self, n_res_blocks, n_filters, downsampling_steps=0, nonlin=None, batchnorm=True, dropout=None,
                  res_block_type=None, gated=None):
         super().__init__()
-        self.net = nn.Sequential(*_resampling_stack(
+        self.net = _BlockStack(*_resampling_stack(
             BottomUpDeterministicResBlock, n_res_blocks, n_filters, downsampling_steps, "downsample",
             nonlin=nonlin, batchnorm=batchnorm, dropout=dropout, res_block_type=res_block_type, gated=gated))
 
@@ -135,7 +154,7 @@ class TopDownLayer(nn.Module):
         self.analytical_kl = analytical_kl
         if is_top_layer:
             self.top_prior_params = nn.Parameter(torch.zeros(top_prior_param_shape), requires_grad=learn_top_prior)
-        self.deterministic_block = nn.Sequential(*_resampling_stack(
+        self.deterministic_block = _BlockStack(*_resampling_stack(
             TopDownDeterministicResBlock, n_res_blocks, n_filters, downsampling_steps or 0, "upsample",
             nonlin=nonlin, batchnorm=batchnorm, dropout=dropout, res_block_type=res_block_type, gated=gated))
         self.stochastic = NormalStochasticBlock2d(c_in=n_filters, c_vars=z_dim, c_out=n_filters,

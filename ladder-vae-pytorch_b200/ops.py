@@ -242,6 +242,7 @@ def grad_track_begin(bucket_of, counts, flush, record=None) -> None:
 
 def grad_track_end() -> None:
     """Flush whatever became ready at the last gradient site and stop tracking."""
+    check_no_pending_bn1()
     t = _grad_track
     if t["on"]:
         for k in t["pending"]:
@@ -875,8 +876,34 @@ def whole_block_enabled() -> bool:
 
 def new_forward_epoch() -> int:
     """A model zeroed its BatchNorm scratch arena: accumulators stamped with an older epoch are clean again."""
+    check_no_pending_bn1()
     _bn_epoch[0] += 1
     return _bn_epoch[0]
+
+
+# Cross-block fusion of the backward pass: inside a stack of directly adjacent gated residual blocks (models/lvae_layers.py
+# _BlockStack) the LAST launch of block k's backward (BatchNorm1-backward apply + residual gradient -> dx) and the FIRST launch
+# of block k-1's backward (gate backward on that very dx) are two elementwise passes over the same pixels.  Block k hands its
+# apply over instead of launching it (keyed by the storage of the dx tensor it returns); block k-1 runs both as one kernel
+# (lvae_bn_act_bwd2_gate).  Only when the stack guarantees that block k is the sole consumer of block k-1's output -- the
+# gradient then reaches block k-1 unaccumulated, as the same tensor -- and only with engine-owned gradient sinks.
+_stack_fusion = [os.environ.get("LVAE_BLOCK_STACK_FUSION", "1") != "0"]
+_private_out = [False]
+_defer_bn1_next = [False]
+_pending_bn1 = {}
+
+
+def mark_block_output_private(flag: bool = True) -> None:
+    """Called by the block stack right before it runs a block whose output is consumed by the next gated block only."""
+    _private_out[0] = bool(flag) and _stack_fusion[0]
+
+
+def check_no_pending_bn1() -> None:
+    if _pending_bn1:
+        n = len(_pending_bn1)
+        _pending_bn1.clear()
+        raise RuntimeError("lvae_b200: %d deferred BatchNorm-backward apply pass(es) were never picked up by the preceding "
+                           "block's backward: their input gradients were not computed (set LVAE_BLOCK_STACK_FUSION=0)" % n)
 
 
 def bn_scratch(bn, device):
@@ -996,6 +1023,8 @@ class GatedBlockFn(Function):
                 call("lvae_gate_fwd", h.data_ptr(), xn.data_ptr(), out.data_ptr(), Pn, C, gact, dt, _stream())
         ctx.save_for_backward(xn, a1, y1, a2, y2, h, saves, g1, b1, w1, cb1, g2, b2, w2, cb2, wg, gbias, m1, m2)
         ctx.blk, ctx.training = blk, training
+        ctx.defer_bn1 = bool(_defer_bn1_next[0])
+        _defer_bn1_next[0] = False
         blk[0]._lvae_last_out_stats = (out_stats, Pn, _bn_epoch[0]) if out_stats is not None else None
         return as_nchw(out)
 
@@ -1013,7 +1042,21 @@ class GatedBlockFn(Function):
         gsp = gconv.spec
         # gate
         dh = torch.empty_like(h)
-        call("lvae_gate_bwd", gn.data_ptr(), h.data_ptr(), dh.data_ptr(), Pn, C, gact, dt, _stream())
+        pend = _pending_bn1.pop(gn.data_ptr(), None)
+        if pend is not None:
+            # the consumer block deferred its BatchNorm1-backward apply: gn is its (still uncomputed) dx -- one pass writes
+            # dx into gn and this block's gate gradient dh
+            assert pend["shape"] == tuple(gn.shape) and gn.dtype == torch.bfloat16 and h.dtype == torch.bfloat16
+            grad_site()
+            pdg, _ = _param_grad_buffer(pend["gamma"])
+            pdb, _ = _param_grad_buffer(pend["beta"])
+            stats["bn1_gate_fused"] = stats.get("bn1_gate_fused", 0) + 1
+            call("lvae_bn_act_bwd2_gate", pend["dy"].data_ptr(), pend["x"].data_ptr(), gn.data_ptr(), pend["save"].data_ptr(),
+                 pend["gamma"].data_ptr(), pend["beta"].data_ptr(), pend["acc"].data_ptr(), pdg.data_ptr(), pdb.data_ptr(), None,
+                 pend["add"].data_ptr(), h.data_ptr(), dh.data_ptr(), Pn, H * W, C, pend["act"], gact,
+                 1 if pend["training"] else 0, _stream())
+        else:
+            call("lvae_gate_bwd", gn.data_ptr(), h.data_ptr(), dh.data_ptr(), Pn, C, gact, dt, _stream())
         # 1x1 gate conv: dgrad carries conv2's Dropout2d mask in its epilogue -> gradient wrt conv2's raw output
         dy2, _, gwg, ggb = conv_backward_raw(gsp, y2, None, wg, gbias, None, dh, True, ng[9], ng[10], dx_scale=m2)
         sc1b, sc2b = bn_scratch(bn1, dev), bn_scratch(bn2, dev)
@@ -1041,6 +1084,13 @@ class GatedBlockFn(Function):
                                               bnb=(xn, saves[0], g1, b1, acc1b, act) if C == 64 else None)
         fused1 = conv_backward_raw.last_fused
         # BN1 + act backward, residual gradient fused
+        if (ctx.defer_bn1 and fused1 and xn.dtype == torch.bfloat16 and C % 8 == 0 and grad_sink(g1) is not None
+                and grad_sink(b1) is not None and gn.dtype == torch.bfloat16):
+            # handed over to the backward of the block that produced xn (see _pending_bn1): dx is returned uncomputed
+            dx = torch.empty_like(xn)
+            _pending_bn1[dx.data_ptr()] = dict(dy=da1, x=xn, add=gn, save=saves[0], gamma=g1, beta=b1, acc=acc1b, act=act,
+                                               training=training, shape=tuple(xn.shape), keep=dx)
+            return (as_nchw(dx), None, None, gw1, gcb1, gg2, gb2, gw2, gcb2, gwg, ggb, None, None, None, None, None)
         dx, gg1, gb1 = bn_bwd(da1, xn, bn1, acc1b, saves[0], g1, b1, None, gn, fused1)
         return (as_nchw(dx), gg1, gb1, gw1, gcb1, gg2, gb2, gw2, gcb2, gwg, ggb, None, None, None, None, None)
 
@@ -1060,10 +1110,16 @@ def gated_block(x, bn1, conv1, drop1, bn2, conv2, drop2, gate_layer, act_id):
         m2 = m2.reshape(x.shape[0], -1)
     blk = (bn1, bn2, conv1, conv2, gate_layer.conv, act_id, getattr(gate_layer.nonlin, "act_id", 0))
     _gate_keep_h[0] = torch.is_grad_enabled()
+    private = _private_out[0]             # this block's output goes to the next gated block of the stack and nowhere else
+    _private_out[0] = False
+    # x is such a private output of the previous block: this block's BatchNorm1-backward apply may be handed over to it
+    _defer_bn1_next[0] = bool(getattr(x, "_lvae_private", False)) and training and torch.is_grad_enabled() and x.requires_grad
     out = GatedBlockFn.apply(x, bn1.weight, bn1.bias, conv1.weight, conv1.bias, bn2.weight, bn2.bias, conv2.weight,
                              conv2.bias, gate_layer.conv.weight, gate_layer.conv.bias, m1, m2, blk, x_stats, training)
     if training and bn1._lvae_last_out_stats is not None:
         out._lvae_stats = bn1._lvae_last_out_stats
+    if private and training and out.dtype == torch.bfloat16:
+        out._lvae_private = True
     return out
 
 
