@@ -70,10 +70,12 @@ template <> __device__ __forceinline__ float round_to<__nv_bfloat16>(float v) { 
 // (blockIdx.x % BN_STRIPES), consumers sum the stripes.
 constexpr int BN_STRIPES = 8;
 __device__ __forceinline__ double acc_sum(const double* acc, int idx, int C) {
-  double s = 0.0;
+  // pairwise tree: three dependent FP64 additions instead of eight (each costs ~40 cycles of latency on this part, and the
+  // sum sits on the critical path of every BatchNorm-apply launch)
+  double v[BN_STRIPES];
 #pragma unroll
-  for (int k = 0; k < BN_STRIPES; ++k) s += acc[k * 2 * C + idx];
-  return s;
+  for (int k = 0; k < BN_STRIPES; ++k) v[k] = acc[k * 2 * C + idx];
+  return ((v[0] + v[1]) + (v[2] + v[3])) + ((v[4] + v[5]) + (v[6] + v[7]));
 }
 __device__ __forceinline__ void acc_clear(double* acc, int idx, int C) {
 #pragma unroll
@@ -818,19 +820,33 @@ __global__ void bn_act_fwd2_kernel(const TI* __restrict__ x, TO* __restrict__ y,
   if (has) rx = ldraw<TI, V>(x + i * V);                           // in flight during the statistics prologue
   // one thread per channel derives the statistics (the only double-precision math in the kernel; the reciprocal of P is
   // taken while the accumulator loads are in flight -- two double divisions behind them cost ~0.4 us per launch)
+  // block 0 also updates the running statistics: their old values are requested now, not behind the statistics (a second,
+  // dependent global round trip in the one block every launch has to wait for)
+  float rm_old = 0.f, rv_old = 0.f;
+  const bool upd = blockIdx.x == 0 && training && running_mean && (int)threadIdx.x < C;
+  if (upd) { rm_old = running_mean[threadIdx.x]; rv_old = running_var[threadIdx.x]; }
   const double invP = 1.0 / (double)P;
+  // FP64 issues at a fraction of the FP32 rate here, and the 2 x 7 stripe additions per channel were one dependent chain in two
+  // warps (~0.9 us per launch, profiles/bench_bn_prologue.py): one thread per (statistic, channel) sums the stripes -- four
+  // warps, one per scheduler for C = 64 -- and hands the two means over through shared memory
+  __shared__ double s_m[2][256];
+  if (training) {
+    for (int k = threadIdx.x; k < 2 * C; k += blockDim.x) s_m[k >= C ? 1 : 0][k >= C ? k - C : k] = acc_sum(acc, k, C) * invP;
+    __syncthreads();
+  }
   for (int ch = threadIdx.x; ch < C; ch += blockDim.x) {
     float mean, rstd;
     if (training) {
-      double m = acc_sum(acc, ch, C) * invP;
-      double var = acc_sum(acc, C + ch, C) * invP - m * m;
+      double m = s_m[0][ch];
+      double var = s_m[1][ch] - m * m;
       if (var < 0.0) var = 0.0;
       mean = (float)m;
       rstd = rsqrtf((float)var + eps);
       if (blockIdx.x == 0 && running_mean) {
         double unb = P > 1 ? var * (double)P / (double)(P - 1) : var;
-        running_mean[ch] = (float)((1.0 - momentum) * (double)running_mean[ch] + momentum * m);
-        running_var[ch] = (float)((1.0 - momentum) * (double)running_var[ch] + momentum * unb);
+        const float ro = ch == (int)threadIdx.x ? rm_old : running_mean[ch], vo = ch == (int)threadIdx.x ? rv_old : running_var[ch];
+        running_mean[ch] = (float)((1.0 - momentum) * (double)ro + momentum * m);
+        running_var[ch] = (float)((1.0 - momentum) * (double)vo + momentum * unb);
       }
     } else {
       mean = running_mean[ch];
@@ -905,8 +921,10 @@ __global__ void __launch_bounds__(256, GATE ? 2 : 3) bn_act_bwd2_kernel(const T*
     s_t[4][ch] = training ? (float)(a1 * invP) : 0.f;
     s_t[5][ch] = training ? (float)(a2 * invP) : 0.f;
     if (blockIdx.x == 0) {
-      if (dbeta) dbeta[ch] += (float)a1;
-      if (dgamma) dgamma[ch] += (float)a2;
+      // fire-and-forget reductions (RED): a load-add-store here is a dependent global round trip in the one block every
+      // launch waits for; nothing else touches these gradient entries concurrently
+      if (dbeta) atomicAdd(dbeta + ch, (float)a1);
+      if (dgamma) atomicAdd(dgamma + ch, (float)a2);
     }
   }
   __syncthreads();
