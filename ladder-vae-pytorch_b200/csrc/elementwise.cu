@@ -860,7 +860,8 @@ __global__ void bn_act_fwd2_kernel(const TI* __restrict__ x, TO* __restrict__ y,
     s_scale[ch] = sc;
     s_shift[ch] = beta[ch] - mean * sc;
   }
-  if (blockIdx.x == 0 && threadIdx.x == 0 && training && nbt) *nbt += 1;
+  // (a reduction, not load-add-store: thread 0 would wait a global round trip in front of the barrier below)
+  if (blockIdx.x == 0 && threadIdx.x == 0 && training && nbt) atomicAdd(reinterpret_cast<unsigned long long*>(nbt), 1ULL);
   __syncthreads();
   const int c = (int)(i % CV) * V;
   float sc[V], sh[V];
