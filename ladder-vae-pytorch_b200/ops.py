@@ -1114,8 +1114,11 @@ def gated_block(x, bn1, conv1, drop1, bn2, conv2, drop2, gate_layer, act_id):
     _private_out[0] = False
     # x is such a private output of the previous block: this block's BatchNorm1-backward apply may be handed over to it
     _defer_bn1_next[0] = bool(getattr(x, "_lvae_private", False)) and training and torch.is_grad_enabled() and x.requires_grad
-    out = GatedBlockFn.apply(x, bn1.weight, bn1.bias, conv1.weight, conv1.bias, bn2.weight, bn2.bias, conv2.weight,
-                             conv2.bias, gate_layer.conv.weight, gate_layer.conv.bias, m1, m2, blk, x_stats, training)
+    try:
+        out = GatedBlockFn.apply(x, bn1.weight, bn1.bias, conv1.weight, conv1.bias, bn2.weight, bn2.bias, conv2.weight,
+                                 conv2.bias, gate_layer.conv.weight, gate_layer.conv.bias, m1, m2, blk, x_stats, training)
+    finally:
+        _defer_bn1_next[0] = False            # never leaks into another block if the forward raised before reading it
     if training and bn1._lvae_last_out_stats is not None:
         out._lvae_stats = bn1._lvae_last_out_stats
     if private and training and out.dtype == torch.bfloat16:
