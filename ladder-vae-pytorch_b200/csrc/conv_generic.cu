@@ -245,6 +245,98 @@ __global__ void __launch_bounds__(CG_THREADS) conv_gather_kernel(ConvArgs a) {
   }
 }
 
+// ------------------------------------------------------------------------------------------
+// The stem: Conv2d(c -> 64, 5x5, stride 2, padding 2) on the c = 1 / 3 channel image (models/lvae.py:75).  K = 25 c is far too
+// short for the 128x64x32 tiling above, whose scalar gather (c is not a multiple of 4) decodes (tap, channel) per element:
+// 99 us for the (256,32,32,3) CIFAR batch, 6 TFLOP/s.  Here a CTA owns a 16x16 tile of output pixels of one image: the 35x35
+// input patch under it (zero-filled outside the image = the padding) and all 25 c x 64 weights sit in shared memory as fp32,
+// a thread owns two pixels (8 rows apart) x 32 output channels, and the weights reach the FMAs as warp-wide broadcasts
+// (one LDS.128 per 4 x 2 FMAs).  The products are summed in the same order as in conv_gather_kernel (tap-major, channel
+// inner, one fmaf each), so the result is the same to the bit.
+// ------------------------------------------------------------------------------------------
+constexpr int ST_TILE = 16, ST_PATCH = 2 * ST_TILE + 3;
+
+template <typename T, int C>
+__global__ void __launch_bounds__(256) conv_stem5x5s2_kernel(const T* __restrict__ x, const T* __restrict__ wp,
+                                                             const float* __restrict__ bias, T* __restrict__ y, int Hi, int Wi,
+                                                             int Ho, int Wo, int ldw, int tiles_x, int tiles_per_img) {
+  pdl_wait();
+  pdl_launch();
+  constexpr int K = 25 * C;
+  constexpr int XPITCH = ST_PATCH * C + 1;
+  __shared__ __align__(16) float ws[K][64];
+  __shared__ float xs[ST_PATCH][XPITCH];
+  const int t = threadIdx.x;
+  const int b = blockIdx.x / tiles_per_img;
+  const int tr = blockIdx.x - b * tiles_per_img;
+  const int oy0 = (tr / tiles_x) * ST_TILE, ox0 = (tr - (tr / tiles_x) * tiles_x) * ST_TILE;
+  for (int i = t; i < K * 64; i += 256) ws[i >> 6][i & 63] = ld1<T>(wp + (size_t)(i >> 6) * ldw + (i & 63));
+  const int iy0 = 2 * oy0 - 2, ix0 = 2 * ox0 - 2;
+  const T* xb = x + (size_t)b * Hi * Wi * C;
+  for (int i = t; i < ST_PATCH * ST_PATCH * C; i += 256) {
+    const int r = i / (ST_PATCH * C), e = i - r * (ST_PATCH * C);
+    const int iy = iy0 + r, ix = ix0 + e / C;
+    float v = 0.f;
+    if (iy >= 0 && iy < Hi && ix >= 0 && ix < Wi) v = ld1<T>(xb + ((size_t)iy * Wi + ix) * C + (e - (e / C) * C));
+    xs[r][e] = v;
+  }
+  __syncthreads();
+  const int pp = t & 127, n0 = (t >> 7) * 32;           // the channel half is warp-uniform: weight reads are broadcasts
+  const int ly = pp >> 4, lx = pp & 15;
+  float acc[2][32];
+#pragma unroll
+  for (int j = 0; j < 32; ++j) acc[0][j] = acc[1][j] = 0.f;
+#pragma unroll 1
+  for (int ky = 0; ky < 5; ++ky) {
+    const float* r0 = &xs[2 * ly + ky][2 * lx * C];
+    const float* r1 = &xs[2 * (ly + 8) + ky][2 * lx * C];
+#pragma unroll
+    for (int kc = 0; kc < 5 * C; ++kc) {                // kc = kx * C + ci: five consecutive input pixels of the row
+      const float a0 = r0[kc], a1 = r1[kc];
+      const float* wr = &ws[ky * 5 * C + kc][n0];
+#pragma unroll
+      for (int j4 = 0; j4 < 8; ++j4) {
+        const float4 w4 = *reinterpret_cast<const float4*>(wr + 4 * j4);
+        acc[0][4 * j4 + 0] = fmaf(a0, w4.x, acc[0][4 * j4 + 0]); acc[1][4 * j4 + 0] = fmaf(a1, w4.x, acc[1][4 * j4 + 0]);
+        acc[0][4 * j4 + 1] = fmaf(a0, w4.y, acc[0][4 * j4 + 1]); acc[1][4 * j4 + 1] = fmaf(a1, w4.y, acc[1][4 * j4 + 1]);
+        acc[0][4 * j4 + 2] = fmaf(a0, w4.z, acc[0][4 * j4 + 2]); acc[1][4 * j4 + 2] = fmaf(a1, w4.z, acc[1][4 * j4 + 2]);
+        acc[0][4 * j4 + 3] = fmaf(a0, w4.w, acc[0][4 * j4 + 3]); acc[1][4 * j4 + 3] = fmaf(a1, w4.w, acc[1][4 * j4 + 3]);
+      }
+    }
+  }
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const int oy = oy0 + ly + 8 * h, ox = ox0 + lx;
+    if (oy < Ho && ox < Wo) {
+      T* yp = y + (((size_t)b * Ho + oy) * Wo + ox) * 64 + n0;
+#pragma unroll
+      for (int j4 = 0; j4 < 8; ++j4) {
+        float4 o = make_float4(acc[h][4 * j4], acc[h][4 * j4 + 1], acc[h][4 * j4 + 2], acc[h][4 * j4 + 3]);
+        if (bias) {
+          const float4 bv = *reinterpret_cast<const float4*>(bias + n0 + 4 * j4);
+          o.x += bv.x; o.y += bv.y; o.z += bv.z; o.w += bv.w;
+        }
+        st4<T>(yp + 4 * j4, o);
+      }
+    }
+  }
+}
+
+template <typename T>
+static bool launch_stem(const void* x, const void* wp, const float* bias, void* y, int B, int Hi, int Wi, int C, int Ho, int Wo,
+                        int ldw, cudaStream_t stream) {
+  const int tiles_x = cdiv(Wo, ST_TILE), tiles_per_img = tiles_x * cdiv(Ho, ST_TILE);
+  const long long grid = (long long)B * tiles_per_img;
+  if (grid >= (1LL << 31)) return false;
+  if (C == 1)
+    lvae_launch(conv_stem5x5s2_kernel<T, 1>, (int)grid, 256, 0, stream, (const T*)x, (const T*)wp, bias, (T*)y, Hi, Wi, Ho, Wo, ldw, tiles_x, tiles_per_img);
+  else if (C == 3)
+    lvae_launch(conv_stem5x5s2_kernel<T, 3>, (int)grid, 256, 0, stream, (const T*)x, (const T*)wp, bias, (T*)y, Hi, Wi, Ho, Wo, ldw, tiles_x, tiles_per_img);
+  else
+    return false;
+  return true;
+}
+
 LVAE_API int lvae_conv2d_gather(const void* x, const void* x2, const void* wp, const float* bias,
                                 const float* in_scale, const float* out_scale, const void* res, void* y,
                                 int B, int Hi, int Wi, int C1, int C2, int Ho, int Wo, int N, int ldw,
@@ -257,6 +349,15 @@ LVAE_API int lvae_conv2d_gather(const void* x, const void* x2, const void* wp, c
   LVAE_REQUIRE(dtype == 0 || dtype == 1, "conv2d_gather: dtype must be 0 (f32) or 1 (bf16)");
   long long M = (long long)B * Ho * Wo;
   const int cls = (mode == 1 && stride == 2 && Ho % 2 == 0 && Wo % 2 == 0 && (M / 4) % CG_BM == 0 && (C1 + C2) % CG_BK == 0) ? 1 : 0;
+  if (mode == 0 && kh == 5 && kw == 5 && stride == 2 && pad == 2 && !x2 && N == 64 && !in_scale && !out_scale && !res) {
+    const bool done = dtype == 0 ? launch_stem<float>(x, wp, bias, y, B, Hi, Wi, C1, Ho, Wo, ldw, stream)
+                                 : launch_stem<__nv_bfloat16>(x, wp, bias, y, B, Hi, Wi, C1, Ho, Wo, ldw, stream);
+    if (done) {
+      LVAE_COUNT_LAUNCH();
+      LVAE_CHECK_LAUNCH("conv2d_gather (stem)");
+      return LVAE_OK;
+    }
+  }
   ConvArgs a{x, x2, wp, bias, in_scale, out_scale, res, y, B, Hi, Wi, C1, C2, Ho, Wo, N, ldw, kh, kw, stride, pad, mode, cls};
   dim3 grid(cdiv(M, CG_BM), cdiv(N, CG_BN));
   bool vec = (C1 % 4 == 0) && (C2 % 4 == 0);
@@ -446,6 +547,107 @@ __global__ void __launch_bounds__(WG_THREADS) conv_wgrad_kernel(WgradArgs a) {
   }
 }
 
+// ------------------------------------------------------------------------------------------
+// Weight gradient of the stem (Conv2d c -> 64, 5x5, stride 2, padding 2; c = 1 / 3): the LAST kernel of the backward pass,
+// nothing overlaps it, and the scalar path of conv_wgrad_kernel takes ~90-130 us for the CIFAR batch.  Same tiling as the
+// forward stem kernel: a CTA walks over 8x16 tiles of output pixels with the 19x35 input patch and the 128x64 dY tile in
+// shared memory; thread (ky, ci, o-quad) keeps dW[o..o+3][ci][ky][0..4] (20 accumulators) in registers over ALL its tiles,
+// reads a whole patch row once per output row (35 broadcast LDS for 16 pixels) and one LDS.128 of dY per pixel; 16 spare
+// threads sum dY for the bias gradient.  One pass of float atomics per CTA at the end (like conv_wgrad_kernel's K-splits).
+// ------------------------------------------------------------------------------------------
+constexpr int SW_ROWS = 8, SW_PR = 2 * SW_ROWS + 3;
+
+template <typename T, int C>
+__global__ void __launch_bounds__(256) wgrad_stem5x5s2_kernel(const T* __restrict__ u, const T* __restrict__ dz, float* __restrict__ dw,
+                                                              float* __restrict__ dbias, int Hi, int Wi, int Ho, int Wo, int tiles_x,
+                                                              int tiles_per_img, int n_tiles) {
+  pdl_wait();
+  pdl_launch();
+  constexpr int XPITCH = ST_PATCH * C + 1;
+  __shared__ float xs[SW_PR][XPITCH];
+  __shared__ __align__(16) float ds[SW_ROWS * ST_TILE][64];
+  const int t = threadIdx.x;
+  const int kyc = t >> 4, oq = t & 15;                  // kyc = ky * C + ci
+  const bool active = kyc < 5 * C, is_bias = kyc == 5 * C && dbias != nullptr;
+  const int ky = kyc / C, ci = kyc - ky * C;
+  float acc[5][4];
+#pragma unroll
+  for (int kx = 0; kx < 5; ++kx)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[kx][j] = 0.f;
+  float bsum[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const int b = tile / tiles_per_img;
+    const int tr = tile - b * tiles_per_img;
+    const int oy0 = (tr / tiles_x) * SW_ROWS, ox0 = (tr - (tr / tiles_x) * tiles_x) * ST_TILE;
+    const int iy0 = 2 * oy0 - 2, ix0 = 2 * ox0 - 2;
+    const T* ub = u + (size_t)b * Hi * Wi * C;
+    __syncthreads();                                    // the previous tile has been consumed
+    for (int i = t; i < SW_PR * ST_PATCH * C; i += 256) {
+      const int r = i / (ST_PATCH * C), e = i - r * (ST_PATCH * C);
+      const int iy = iy0 + r, ix = ix0 + e / C;
+      float v = 0.f;
+      if (iy >= 0 && iy < Hi && ix >= 0 && ix < Wi) v = ld1<T>(ub + ((size_t)iy * Wi + ix) * C + (e - (e / C) * C));
+      xs[r][e] = v;
+    }
+    for (int i = t; i < SW_ROWS * ST_TILE * 16; i += 256) {
+      const int p = i >> 4, c4 = (i & 15) * 4;
+      const int oy = oy0 + (p >> 4), ox = ox0 + (p & 15);
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (oy < Ho && ox < Wo) v = ld4<T>(dz + (((size_t)b * Ho + oy) * Wo + ox) * 64 + c4);
+      *reinterpret_cast<float4*>(&ds[p][c4]) = v;
+    }
+    __syncthreads();
+    if (active) {
+#pragma unroll 1
+      for (int r = 0; r < SW_ROWS; ++r) {
+        const float* xr = &xs[2 * r + ky][ci];
+        float xv[ST_PATCH];
+#pragma unroll
+        for (int i = 0; i < ST_PATCH; ++i) xv[i] = xr[i * C];
+#pragma unroll
+        for (int ox = 0; ox < ST_TILE; ++ox) {
+          const float4 d4 = *reinterpret_cast<const float4*>(&ds[r * ST_TILE + ox][4 * oq]);
+#pragma unroll
+          for (int kx = 0; kx < 5; ++kx) {
+            const float a = xv[2 * ox + kx];
+            acc[kx][0] = fmaf(a, d4.x, acc[kx][0]); acc[kx][1] = fmaf(a, d4.y, acc[kx][1]);
+            acc[kx][2] = fmaf(a, d4.z, acc[kx][2]); acc[kx][3] = fmaf(a, d4.w, acc[kx][3]);
+          }
+        }
+      }
+    } else if (is_bias) {
+      for (int p = 0; p < SW_ROWS * ST_TILE; ++p) {
+        const float4 d4 = *reinterpret_cast<const float4*>(&ds[p][4 * oq]);
+        bsum[0] += d4.x; bsum[1] += d4.y; bsum[2] += d4.z; bsum[3] += d4.w;
+      }
+    }
+  }
+  if (active) {
+#pragma unroll
+    for (int kx = 0; kx < 5; ++kx)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) atomicAdd(dw + ((size_t)(4 * oq + j) * C + ci) * 25 + ky * 5 + kx, acc[kx][j]);
+  } else if (is_bias) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) atomicAdd(dbias + 4 * oq + j, bsum[j]);
+  }
+}
+
+template <typename T>
+static bool launch_stem_wgrad(const void* u, const void* dz, float* dw, float* dbias, int B, int Hi, int Wi, int C, int Ho, int Wo,
+                              cudaStream_t stream) {
+  const int tiles_x = cdiv(Wo, ST_TILE), tiles_per_img = tiles_x * cdiv(Ho, SW_ROWS);
+  const long long n_tiles = (long long)B * tiles_per_img;
+  if (n_tiles >= (1LL << 31) || (C != 1 && C != 3)) return false;
+  const int grid = (int)min(n_tiles, (long long)lvae_num_sms());
+  if (C == 1)
+    lvae_launch(wgrad_stem5x5s2_kernel<T, 1>, grid, 256, 0, stream, (const T*)u, (const T*)dz, dw, dbias, Hi, Wi, Ho, Wo, tiles_x, tiles_per_img, (int)n_tiles);
+  else
+    lvae_launch(wgrad_stem5x5s2_kernel<T, 3>, grid, 256, 0, stream, (const T*)u, (const T*)dz, dw, dbias, Hi, Wi, Ho, Wo, tiles_x, tiles_per_img, (int)n_tiles);
+  return true;
+}
+
 LVAE_API int lvae_conv2d_wgrad(const void* u, const void* u2, const void* dz, const float* in_scale,
                                const float* out_scale, float* dw, float* dbias, int B, int Hi, int Wi,
                                int C1, int C2, int Ho, int Wo, int O, int kh, int kw, int stride, int pad,
@@ -453,6 +655,15 @@ LVAE_API int lvae_conv2d_wgrad(const void* u, const void* u2, const void* dz, co
   LVAE_REQUIRE(u && dz && dw, "conv2d_wgrad: null pointer");
   LVAE_REQUIRE((C2 == 0) == (u2 == nullptr), "conv2d_wgrad: u2/C2 mismatch");
   LVAE_REQUIRE(dtype == 0 || dtype == 1, "conv2d_wgrad: dtype must be 0 (f32) or 1 (bf16)");
+  if (kh == 5 && kw == 5 && stride == 2 && pad == 2 && !u2 && O == 64 && !in_scale && !out_scale) {
+    const bool done = dtype == 0 ? launch_stem_wgrad<float>(u, dz, dw, dbias, B, Hi, Wi, C1, Ho, Wo, stream)
+                                 : launch_stem_wgrad<__nv_bfloat16>(u, dz, dw, dbias, B, Hi, Wi, C1, Ho, Wo, stream);
+    if (done) {
+      LVAE_COUNT_LAUNCH();
+      LVAE_CHECK_LAUNCH("conv2d_wgrad (stem)");
+      return LVAE_OK;
+    }
+  }
   int I = C1 + C2, K = kh * kw * I;
   long long M = (long long)B * Ho * Wo;
   int ktiles = cdiv(K, WG_BK), ntiles = cdiv(O, WG_BN);
@@ -673,27 +884,34 @@ __global__ void __launch_bounds__(256) conv3x3_narrow1_kernel(const __nv_bfloat1
     float acc[8];
 #pragma unroll
     for (int o = 0; o < 8; ++o) acc[o] = 0.f;
+    // The ten loads of an input row are unconditional (clamped coordinates; pixels outside the image are zeroed after they
+    // land, which adds exact zeros) and issued back to back before their first use: with the loads inside the bounds branches
+    // every one of the 30 was a separate round trip to L2 (170 us for the (1000,28,28) head of the IW evaluator, i.e. 0.6 TB/s).
 #pragma unroll
     for (int dy = 0; dy < 3; ++dy) {
       const int iy = py + dy - 1;
       const bool rowin = live && iy >= 0 && iy < H;
-      const __nv_bfloat16* rp = x + (long long)b * img_pitch + (long long)iy * row_pitch + sub * 8;
+      const __nv_bfloat16* rp = x + (long long)b * img_pitch + (long long)min(max(iy, 0), H - 1) * row_pitch + sub * 8;
+      uint4 u[10];
 #pragma unroll
       for (int hx = 0; hx < 10; ++hx) {
         const int ix = x0 + hx - 1;
-        if (rowin && ix >= 0 && ix < W) {
-          const uint4 u = *reinterpret_cast<const uint4*>(rp + (long long)ix * 64);
-          const uint32_t wd[4] = {u.x, u.y, u.z, u.w};
-          float v[8];
+        u[hx] = *reinterpret_cast<const uint4*>(rp + (long long)min(max(ix, 0), W - 1) * 64);
+      }
 #pragma unroll
-          for (int j = 0; j < 4; ++j) { v[2 * j] = __uint_as_float(wd[j] << 16); v[2 * j + 1] = __uint_as_float(wd[j] & 0xFFFF0000u); }
+      for (int hx = 0; hx < 10; ++hx) {
+        const int ix = x0 + hx - 1;
+        const bool ok = rowin && ix >= 0 && ix < W;
+        const uint32_t wd[4] = {ok ? u[hx].x : 0u, ok ? u[hx].y : 0u, ok ? u[hx].z : 0u, ok ? u[hx].w : 0u};
+        float v[8];
 #pragma unroll
-          for (int dx = 0; dx < 3; ++dx) {
-            const int o = hx - dx;                           // output pixel x0 + o reads input x0 + o + dx - 1 = x0 + hx - 1
-            if (o >= 0 && o < 8) {
+        for (int j = 0; j < 4; ++j) { v[2 * j] = __uint_as_float(wd[j] << 16); v[2 * j + 1] = __uint_as_float(wd[j] & 0xFFFF0000u); }
 #pragma unroll
-              for (int j = 0; j < 8; ++j) acc[o] = fmaf(v[j], wr[dy * 3 + dx][j], acc[o]);
-            }
+        for (int dx = 0; dx < 3; ++dx) {
+          const int o = hx - dx;                           // output pixel x0 + o reads input x0 + o + dx - 1 = x0 + hx - 1
+          if (o >= 0 && o < 8) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[o] = fmaf(v[j], wr[dy * 3 + dx][j], acc[o]);
           }
         }
       }

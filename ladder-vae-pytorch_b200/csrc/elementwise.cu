@@ -247,21 +247,33 @@ __global__ void bn_act_bwd_apply_kernel(const T* __restrict__ dy, const T* __res
   pdl_launch();
   const int CV = C >> 2;
   const double invP = 1.0 / (double)P;
+  // The per-channel constants (16 striped double loads + 6 dependent FP64 additions per channel) are re-derived only when the
+  // thread's channel quad changes: with a grid stride that is a multiple of C / 4 (every C / 4 that divides 256) that is once
+  // per thread, not once per element (68 -> ~10 us for the stem block's (256,16,16,64) tensor).
+  int c_cur = -1;
+  float mj[4], rj[4], gj[4], bj[4], m1[4], m2[4];
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nquads; i += (long long)gridDim.x * blockDim.x) {
-    int c = (int)(i % CV) * 4;
+    const int c = (int)(i % CV) * 4;
     float4 xv = ld4<T>(x + i * 4), dv = ld4<T>(dy + i * 4);
+    if (c != c_cur) {
+      c_cur = c;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        mj[j] = mean[c + j]; rj[j] = rstd[c + j]; gj[j] = gamma[c + j]; bj[j] = beta[c + j];
+        m1[j] = m2[j] = 0.f;
+        if (training) {
+          m1[j] = (float)(acc_sum(acc, c + j, C) * invP);
+          m2[j] = (float)(acc_sum(acc, C + c + j, C) * invP);
+        }
+      }
+    }
     float xs[4] = {xv.x, xv.y, xv.z, xv.w}, ds[4] = {dv.x, dv.y, dv.z, dv.w}, o[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      float mj = mean[c + j], rj = rstd[c + j], gj = gamma[c + j], bj = beta[c + j];
-      float xh = (xs[j] - mj) * rj;
-      float gpre = ds[j] * act_bwd_t<sizeof(T) == 2>(xh * gj + bj, act);
-      if (training) {
-        float m1 = (float)(acc_sum(acc, c + j, C) * invP), m2 = (float)(acc_sum(acc, C + c + j, C) * invP);
-        o[j] = gj * rj * (gpre - m1 - xh * m2);
-      } else {
-        o[j] = gj * rj * gpre;
-      }
+      float xh = (xs[j] - mj[j]) * rj[j];
+      float gpre = ds[j] * act_bwd_t<sizeof(T) == 2>(xh * gj[j] + bj[j], act);
+      if (training) o[j] = gj[j] * rj[j] * (gpre - m1[j] - xh * m2[j]);
+      else o[j] = gj[j] * rj[j] * gpre;
     }
     st4<T>(dx + i * 4, make_float4(o[0], o[1], o[2], o[3]));
   }
@@ -614,6 +626,71 @@ __global__ void upsample2x_bwd_kernel(const T* __restrict__ dy, T* __restrict__ 
   }
 }
 
+// bf16, C % 8 == 0: the closed form of the same gather.  Along one axis input i collects
+//   0.25 dy[2i-1] + 0.75 dy[2i] + 0.75 dy[2i+1] + 0.25 dy[2i+2],
+// and the clamped borders fold the missing tap's weight onto its neighbour (i = 0: 1.0 dy[0]; i = n-1: 1.0 dy[2n-1]).
+// All 16 loads of a thread are unconditional (clamped coordinates) and issued before the first use, the taps are added in
+// the order of the generic kernel (so the result is the same to the bit), 16-byte transactions, 32-bit index arithmetic:
+// the generic kernel evaluates up2_src for 25 candidate taps per element and takes 64 us for the (256,32,32,64) gradient.
+__global__ void __launch_bounds__(256) upsample2x_bwd_bf16x8_kernel(const __nv_bfloat16* __restrict__ dy, __nv_bfloat16* __restrict__ dx,
+                                                                    int B, int H, int W, int C) {
+  pdl_wait();
+  pdl_launch();
+  const unsigned CV = (unsigned)C >> 3, W2 = 2u * W, H2 = 2u * H;
+  const unsigned total = (unsigned)B * H * W * CV;
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const unsigned cv = i % CV, p = i / CV;
+    const int ix = (int)(p % W);
+    const unsigned q = p / W;
+    const int iy = (int)(q % H);
+    const unsigned b = q / H;
+    float wy[4], wx[4];
+    int oy[4], ox[4];
+    bool vy[4], vx[4];
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      const int o_y = 2 * iy - 1 + t, o_x = 2 * ix - 1 + t;
+      vy[t] = o_y >= 0 && o_y < (int)H2;
+      vx[t] = o_x >= 0 && o_x < (int)W2;
+      oy[t] = min(max(o_y, 0), (int)H2 - 1);
+      ox[t] = min(max(o_x, 0), (int)W2 - 1);
+    }
+    wy[0] = 0.25f; wy[1] = iy > 0 ? 0.75f : 1.f; wy[2] = iy < H - 1 ? 0.75f : 1.f; wy[3] = 0.25f;
+    wx[0] = 0.25f; wx[1] = ix > 0 ? 0.75f : 1.f; wx[2] = ix < W - 1 ? 0.75f : 1.f; wx[3] = 0.25f;
+    const __nv_bfloat16* base = dy + ((size_t)b * H2 * W2) * C + cv * 8;
+    uint4 r[4][4];
+#pragma unroll
+    for (int ty = 0; ty < 4; ++ty)
+#pragma unroll
+      for (int tx = 0; tx < 4; ++tx)
+        r[ty][tx] = __ldg(reinterpret_cast<const uint4*>(base + (size_t)((unsigned)oy[ty] * W2 + (unsigned)ox[tx]) * C));
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+#pragma unroll
+    for (int ty = 0; ty < 4; ++ty)
+#pragma unroll
+      for (int tx = 0; tx < 4; ++tx)
+        if (vy[ty] && vx[tx]) {
+          const float w = wy[ty] * wx[tx];
+          const uint32_t* u = reinterpret_cast<const uint32_t*>(&r[ty][tx]);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            acc[2 * j] = fmaf(w, __uint_as_float(u[j] << 16), acc[2 * j]);
+            acc[2 * j + 1] = fmaf(w, __uint_as_float(u[j] & 0xFFFF0000u), acc[2 * j + 1]);
+          }
+        }
+    uint4 o;
+    uint32_t* op = reinterpret_cast<uint32_t*>(&o);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const __nv_bfloat162 h2 = __floats2bfloat162_rn(acc[2 * j], acc[2 * j + 1]);
+      op[j] = *reinterpret_cast<const uint32_t*>(&h2);
+    }
+    *reinterpret_cast<uint4*>(dx + (size_t)i * 8) = o;
+  }
+}
+
 LVAE_API int lvae_upsample2x_fwd(const void* x, void* y, int B, int H, int W, int C, int dtype, cudaStream_t stream) {
   LVAE_REQUIRE(x && y && C % 4 == 0, "upsample2x_fwd: bad args");
   long long n = (long long)B * 4 * H * W * (C / 4);
@@ -630,6 +707,8 @@ LVAE_API int lvae_upsample2x_bwd(const void* dy, void* dx, int B, int H, int W, 
   LVAE_REQUIRE(dy && dx && C % 4 == 0, "upsample2x_bwd: bad args");
   long long n = (long long)B * H * W * (C / 4);
   if (dtype == 0) lvae_launch(upsample2x_bwd_kernel<float>, ew_grid(n, 256), 256, 0, stream, (const float*)dy, (float*)dx, B, H, W, C);
+  else if (C % 8 == 0 && n * 2 < (1LL << 31))      // n * 2 = output pixels x (C / 8) of the larger tensor, the kernel's widest 32-bit index
+    lvae_launch(upsample2x_bwd_bf16x8_kernel, ew_grid(n / 2, 256), 256, 0, stream, (const __nv_bfloat16*)dy, (__nv_bfloat16*)dx, B, H, W, C);
   else lvae_launch(upsample2x_bwd_kernel<__nv_bfloat16>, ew_grid(n, 256), 256, 0, stream, (const __nv_bfloat16*)dy, (__nv_bfloat16*)dx, B, H, W, C);
   LVAE_COUNT_LAUNCH();
   LVAE_CHECK_LAUNCH("upsample2x_bwd");

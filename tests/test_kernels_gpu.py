@@ -189,6 +189,65 @@ def test_upsample_crop_pad(L):
     assert rel_err(c, cr.float()) == 0 and rel_err(ad.grad, ar.grad.float()) == 0
 
 
+@pytest.mark.parametrize("cin,H,W,B", [(3, 32, 32, 5), (1, 32, 32, 3), (3, 64, 64, 2), (3, 28, 20, 3), (1, 7, 9, 2), (3, 36, 70, 1)])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_stem_conv_kernels(L, cin, H, W, B, dtype):
+    """The stem (models/lvae.py:75: Conv2d c -> 64, 5x5, stride 2, padding 2) has its own forward and weight-gradient kernels
+    (16x16 / 8x16 output tiles with the input patch in shared memory): image sizes that are not multiples of the tiles, several
+    tiles per image, both channel counts, both activation types, against F.conv2d in float64."""
+    from lvae_b200 import _capi
+    from lvae_b200.lib.nn import Conv2d
+    g = torch.Generator().manual_seed(cin * 1000 + H * 10 + W)
+    x = torch.randn(B, cin, H, W, generator=g)
+    mod = Conv2d(cin, 64, 5, stride=2, padding=2)
+    w = torch.randn(mod.weight.shape, generator=g) / math.sqrt(cin * 25)
+    b = torch.randn(64, generator=g)
+    xq = x.to(dtype)
+    wq = w.to(dtype).double() if dtype == torch.bfloat16 else w.double()      # the bf16 path rounds the packed weights
+    wr, br = wq.clone().requires_grad_(True), b.double().requires_grad_(True)
+    yr = F.conv2d(xq.double(), wr, br, stride=2, padding=2)
+    gy = torch.randn(yr.shape, generator=g).to(dtype)
+    yr.backward(gy.double())
+    mod = mod.cuda()
+    with torch.no_grad():
+        mod.weight.copy_(w)
+        mod.bias.copy_(b)
+    n0 = _capi.launch_count()
+    xd = xq.cuda().permute(0, 2, 3, 1).contiguous().permute(0, 3, 1, 2)
+    out = mod(xd)
+    assert out.dtype == dtype and tuple(out.shape) == tuple(yr.shape)
+    out.backward(gy.cuda())
+    tol, gtol = (TOL, GTOL) if dtype == torch.float32 else (6e-3, 2e-3)   # bf16: output rounding; gradients accumulate in fp32
+    assert rel_err(out, yr) < tol
+    assert rel_err(mod.weight.grad, wr.grad) < gtol
+    assert rel_err(mod.bias.grad, br.grad) < gtol
+    assert _capi.launch_count() > n0
+
+
+@pytest.mark.parametrize("B,C,H,W", [(3, 64, 16, 16), (2, 64, 5, 7), (2, 8, 1, 1), (1, 16, 2, 9), (2, 4, 4, 4)])
+def test_upsample_bf16_matches_rounded_exact_result(L, B, C, H, W):
+    """bf16 activations: the x2 bilinear weights are exact binary fractions, so forward and backward must equal the fp64 result
+    rounded to bf16 (up to a tie: one bf16 ulp on a handful of elements).  C % 8 == 0 takes the 16-byte kernels (closed-form
+    backward stencil), C = 4 the generic ones: both are checked against the same reference, including the clamped borders."""
+    from lvae_b200 import ops
+    g = torch.Generator().manual_seed(B * 100 + H * 10 + W)
+    x = torch.randn(B, C, H, W, generator=g).bfloat16()
+    gy = torch.randn(B, C, 2 * H, 2 * W, generator=g).bfloat16()
+    xr = x.double().requires_grad_(True)
+    yr = F.interpolate(xr, scale_factor=2, mode="bilinear", align_corners=False)
+    yr.backward(gy.double())
+    xd = x.cuda().permute(0, 2, 3, 1).contiguous().permute(0, 3, 1, 2).requires_grad_(True)
+    y = ops.upsample2x(xd)
+    y.backward(gy.cuda().permute(0, 2, 3, 1).contiguous().permute(0, 3, 1, 2))
+    for ours, ref in ((y, yr.detach()), (xd.grad, xr.grad)):
+        assert ours.dtype == torch.bfloat16
+        want = ref.bfloat16().double()
+        d = (ours.double().cpu() - want).abs()
+        ulp = want.abs().clamp(min=2.0 ** -120) * 2.0 ** -7            # >= one bf16 ulp of the reference value
+        assert bool((d <= ulp).all()), float((d / ulp).max())
+        assert float((d > 0).double().mean()) < 5e-3
+
+
 @pytest.mark.parametrize("Z,hw,analytical,broadcast", [(32, (8, 8), False, False), (32, (2, 2), False, True),
                                                        (32, (4, 4), True, False), (6, (3, 5), False, False),
                                                        (8, (4, 4), False, True), (64, (4, 4), False, False),
