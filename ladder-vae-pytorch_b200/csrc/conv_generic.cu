@@ -713,18 +713,28 @@ __global__ void pack_weights_kernel(const LvaePackDesc* descs, int n) {
       //   mode 3 (dgrad):    row n = input channel i,  k = output channel o  -> w[o][i][tap]
       const int nreal = p.mode == 2 ? p.O : p.I, kreal = p.mode == 2 ? p.I : p.O;
       const int KB = (kreal + 63) / 64, Npad = (nreal + 15) / 16 * 16;
-      const int total = p.taps * KB * Npad * 64;
-      for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
-        int c = idx & 63, r = idx >> 6;
-        int nn = r % Npad, t2 = r / Npad;
-        int kb = t2 % KB, tap = t2 / KB;
-        int kk = kb * 64 + c;
+      // A thread keeps its column c and walks over rows (tap, k-block, n) with a fixed stride: the row is decoded once and
+      // then advanced with carries -- the two runtime divisions per element made this launch instruction-bound (~100 us for
+      // the 29 M elements of the CIFAR-15 model's 1118 packs, at the head of every step).
+      const int rows = p.taps * KB * Npad, rstep = gridDim.x * (blockDim.x >> 6);
+      const int c = threadIdx.x & 63;
+      int r = blockIdx.x * (blockDim.x >> 6) + (threadIdx.x >> 6);
+      int nn = r % Npad, t2 = r / Npad;
+      int kb = t2 % KB, tap = t2 / KB;
+      const int dn = rstep % Npad, dt = rstep / Npad;
+      __nv_bfloat16* dst = (__nv_bfloat16*)p.dst;
+      for (; r < rows; r += rstep) {
+        const int kk = kb * 64 + c;
         float v = 0.f;
         if (nn < nreal && kk < kreal) {
-          int o = p.mode == 2 ? nn : kk, i = p.mode == 2 ? kk : nn;
-          v = p.src[((long long)o * p.I + i) * p.taps + tap];
+          const int o = p.mode == 2 ? nn : kk, i = p.mode == 2 ? kk : nn;
+          v = p.src[(o * p.I + i) * p.taps + tap];
         }
-        ((__nv_bfloat16*)p.dst)[idx] = __float2bfloat16(v);
+        dst[r * 64 + c] = __float2bfloat16(v);
+        nn += dn;
+        kb += dt;
+        if (nn >= Npad) { nn -= Npad; ++kb; }
+        while (kb >= KB) { kb -= KB; ++tap; }
       }
       continue;
     }
