@@ -259,6 +259,12 @@ long long lvae_stoch_ws_bytes(int B);
 int lvae_stoch_bwd(const float* q, const float* p, int p_broadcast, const float* z, const float* g_z,
                    const float* g_kl, const float* g_logp, const float* g_logq, const float* g_kls, float* dq,
                    float* dp, int B, int hw, int Z, int analytical, int z_kind, lvae_stream_t stream);
+/* The same with optional bf16 copies of dq / dp ((B,hw,2Z), round to nearest even; NULL = none): the operands of the tensor-core
+ * data / weight gradients of conv_in_q / conv_in_p (lib/stochastic.py:25-26), which then need no conversion pass. */
+int lvae_stoch_bwd_ex(const float* q, const float* p, int p_broadcast, const float* z, const float* g_z,
+                      const float* g_kl, const float* g_logp, const float* g_logq, const float* g_kls, float* dq,
+                      float* dp, void* dq_bf16, void* dp_bf16, int B, int hw, int Z, int analytical, int z_kind,
+                      lvae_stream_t stream);
 /* Free bits + KL bookkeeping of LadderVAE.forward (models/lvae.py:192-198; boilr free_bits_kl) and the log p(z) total of
  * topdown_pass (:301-302) in one launch over the (L,B) matrices whose rows the L stochastic kernels wrote:
  * kl_sep (B), scalars[3] = {kl, kl_loss, logp}, kl_avg_layerwise (L), coef (L,B) = d kl_loss / d kl (kept for the backward). */

@@ -54,6 +54,7 @@ _SIGNATURES = {
     "lvae_sum_batch": [P, P, I, L, I, P],
     "lvae_stoch_fwd": [P, P, I, P, P, P, U, P, P, I, P, P, P, P, I, I, I, I, I, P, P],
     "lvae_stoch_bwd": [P, P, I, P, P, P, P, P, P, P, P, I, I, I, I, I, P],
+    "lvae_stoch_bwd_ex": [P, P, I, P, P, P, P, P, P, P, P, P, P, I, I, I, I, I, P],
     "lvae_kl_bookkeeping": [P, P, I, I, F, P, P, P, P, P],
     "lvae_kl_bookkeeping_bwd": [P, P, P, P, I, I, P, P, P],
     "lvae_bernoulli_fwd": [P, P, P, P, I, I, I, P],

@@ -860,16 +860,21 @@ __global__ void __launch_bounds__(256) conv3x3_narrow_kernel(const __nv_bfloat16
   }
 }
 
-// N = 1 (the Bernoulli head): row-segment formulation.  A group of 8 lanes (8 channels each) owns 8 consecutive output pixels of
-// one image row: it reads the 3 x 10 input pixels under them ONCE (30 coalesced 128-byte rows instead of 8 x 9 = 72), keeps
-// the 9 x 8 weights of its channel slice in registers, and finishes with a 7-shuffle transposing reduction that leaves one
-// pixel's sum in every lane.  ~115 instructions per output and lane against ~370 of the per-pixel kernel above (which spent a
-// third of them on 64-bit index divisions).  The input may be a WINDOW of a larger NHWC tensor (row / image pitch in elements):
-// the centred crop in front of the likelihood (models/lvae.py:143) then costs no pass of its own.
+// N = 1 (the Bernoulli head): column-strip formulation.  A group of 8 lanes (8 channels each) owns 8 consecutive output pixels
+// of up to NR_ROWS consecutive image rows.  It walks DOWN the strip: every input row (10 pixels = 10 coalesced 128-byte rows,
+// loaded unconditionally from clamped coordinates and zeroed afterwards, all ten in flight) feeds the three output rows it
+// touches, whose partial sums live in three rotating accumulator sets; the 9 x 8 weights of the lane's channel slice sit in
+// registers, and a finished output row leaves through a 7-shuffle transposing reduction (one pixel's sum per lane).  Each input
+// pixel is fetched (R + 2) / R x 10 / 8 = 1.6 times (R = 7) instead of 3.75 times with one output row per group, and the taps
+// of an output pixel are added in the same order as before (dy, then x, then channel), so results are unchanged to the bit.
+// The input may be a WINDOW of a larger NHWC tensor (row / image pitch in elements): the centred crop in front of the
+// likelihood (models/lvae.py:143) then costs no pass of its own.
+constexpr int NR_ROWS = 8;
+
 template <typename TO>
 __global__ void __launch_bounds__(256) conv3x3_narrow1_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ w,
                                                               const float* __restrict__ bias, TO* __restrict__ y, int B, int H,
-                                                              int W, int row_pitch, long long img_pitch) {
+                                                              int W, int row_pitch, long long img_pitch, int chunks, int R) {
   pdl_wait();
   pdl_launch();
   const int sub = threadIdx.x & 7;                          // which 8 channels of a pixel
@@ -880,68 +885,98 @@ __global__ void __launch_bounds__(256) conv3x3_narrow1_kernel(const __nv_bfloat1
     for (int j = 0; j < 8; ++j) wr[t][j] = __ldg(w + (sub * 8 + j) * 9 + t);
   const float b0 = bias ? __ldg(bias) : 0.f;
   const int segs_per_row = (W + 7) >> 3;
-  const int n_seg = B * H * segs_per_row;
+  const int n_unit = B * chunks * segs_per_row;             // unit = (image, row chunk, 8-pixel column segment), segment fastest
   const int group = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 3), n_groups = (int)((gridDim.x * blockDim.x) >> 3);
-  // all 32 lanes of a warp run the same number of iterations (the shuffles below are warp-wide)
-  const int iters = (n_seg + n_groups - 1) / n_groups;
+  // all 32 lanes of a warp run the same number of iterations and rows (the shuffles below are warp-wide)
+  const int iters = (n_unit + n_groups - 1) / n_groups;
   for (int itn = 0; itn < iters; ++itn) {
-    const int seg = group + itn * n_groups;
-    const bool live = seg < n_seg;
-    const int sg = live ? seg : 0;
-    const int row_id = sg / segs_per_row;                   // b * H + y
-    const int x0 = (sg - row_id * segs_per_row) << 3;
-    const int b = row_id / H, py = row_id - b * H;
-    float acc[8];
+    const int unit = group + itn * n_groups;
+    const bool live = unit < n_unit;
+    const int un = live ? unit : 0;
+    const int t1 = un / segs_per_row;
+    const int x0 = (un - t1 * segs_per_row) << 3;
+    const int b = t1 / chunks;
+    const int y0 = (t1 - b * chunks) * R, y1 = min(H, y0 + R);
+    const __nv_bfloat16* xb = x + (long long)b * img_pitch + sub * 8;
+    float a0[8], a1[8], a2[8];                              // output rows iy + 1, iy, iy - 1 while input row iy is processed
 #pragma unroll
-    for (int o = 0; o < 8; ++o) acc[o] = 0.f;
-    // The ten loads of an input row are unconditional (clamped coordinates; pixels outside the image are zeroed after they
-    // land, which adds exact zeros) and issued back to back before their first use: with the loads inside the bounds branches
-    // every one of the 30 was a separate round trip to L2 (170 us for the (1000,28,28) head of the IW evaluator, i.e. 0.6 TB/s).
+    for (int o = 0; o < 8; ++o) a0[o] = a1[o] = a2[o] = 0.f;
+    // the next input row is requested before the current one is consumed (rows outside the image or the chunk are fetched from
+    // the clamped row and ignored): with one CTA of 8 warps per SM (160+ registers) nothing else hides the load latency
+    uint4 u[10], nx[10];
+    int xoff[10];
 #pragma unroll
-    for (int dy = 0; dy < 3; ++dy) {
-      const int iy = py + dy - 1;
-      const bool rowin = live && iy >= 0 && iy < H;
-      const __nv_bfloat16* rp = x + (long long)b * img_pitch + (long long)min(max(iy, 0), H - 1) * row_pitch + sub * 8;
-      uint4 u[10];
+    for (int hx = 0; hx < 10; ++hx) xoff[hx] = min(max(x0 + hx - 1, 0), W - 1) * 64;
+    {
+      const __nv_bfloat16* rp = xb + (long long)min(max(y0 - 1, 0), H - 1) * row_pitch;
 #pragma unroll
-      for (int hx = 0; hx < 10; ++hx) {
-        const int ix = x0 + hx - 1;
-        u[hx] = *reinterpret_cast<const uint4*>(rp + (long long)min(max(ix, 0), W - 1) * 64);
+      for (int hx = 0; hx < 10; ++hx) u[hx] = *reinterpret_cast<const uint4*>(rp + xoff[hx]);
+    }
+#pragma unroll 1
+    for (int k = 0; k < R + 2; ++k) {
+      const int iy = y0 - 1 + k;
+      const bool rowin = live && iy >= 0 && iy < H && iy <= y1;
+      // which of the three output rows this input row feeds lie inside the chunk
+      const bool do0 = iy + 1 < y1, do1 = iy >= y0 && iy < y1, do2 = iy - 1 >= y0 && iy - 1 < y1;
+      {
+        const __nv_bfloat16* rp = xb + (long long)min(max(iy + 1, 0), H - 1) * row_pitch;
+#pragma unroll
+        for (int hx = 0; hx < 10; ++hx) nx[hx] = *reinterpret_cast<const uint4*>(rp + xoff[hx]);
       }
+      if (rowin) {
 #pragma unroll
-      for (int hx = 0; hx < 10; ++hx) {
-        const int ix = x0 + hx - 1;
-        const bool ok = rowin && ix >= 0 && ix < W;
-        const uint32_t wd[4] = {ok ? u[hx].x : 0u, ok ? u[hx].y : 0u, ok ? u[hx].z : 0u, ok ? u[hx].w : 0u};
-        float v[8];
+        for (int hx = 0; hx < 10; ++hx) {
+          const int ix = x0 + hx - 1;
+          const bool ok = ix >= 0 && ix < W;
+          const uint32_t wd[4] = {ok ? u[hx].x : 0u, ok ? u[hx].y : 0u, ok ? u[hx].z : 0u, ok ? u[hx].w : 0u};
+          float v[8];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) { v[2 * j] = __uint_as_float(wd[j] << 16); v[2 * j + 1] = __uint_as_float(wd[j] & 0xFFFF0000u); }
+          for (int j = 0; j < 4; ++j) { v[2 * j] = __uint_as_float(wd[j] << 16); v[2 * j + 1] = __uint_as_float(wd[j] & 0xFFFF0000u); }
 #pragma unroll
-        for (int dx = 0; dx < 3; ++dx) {
-          const int o = hx - dx;                           // output pixel x0 + o reads input x0 + o + dx - 1 = x0 + hx - 1
-          if (o >= 0 && o < 8) {
+          for (int dx = 0; dx < 3; ++dx) {
+            const int o = hx - dx;                           // output pixel x0 + o reads input x0 + o + dx - 1 = x0 + hx - 1
+            if (o >= 0 && o < 8) {
+              if (do0) {
 #pragma unroll
-            for (int j = 0; j < 8; ++j) acc[o] = fmaf(v[j], wr[dy * 3 + dx][j], acc[o]);
+                for (int j = 0; j < 8; ++j) a0[o] = fmaf(v[j], wr[dx][j], a0[o]);
+              }
+              if (do1) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) a1[o] = fmaf(v[j], wr[3 + dx][j], a1[o]);
+              }
+              if (do2) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) a2[o] = fmaf(v[j], wr[6 + dx][j], a2[o]);
+              }
+            }
           }
         }
       }
-    }
-    // transposing reduction over the 8 lanes of the group: lane `sub` ends with the sum of output pixel `sub`
+      // output row iy - 1 is complete: transposing reduction over the 8 lanes of the group (lane `sub` ends with the sum of
+      // output pixel `sub`), then the accumulator sets rotate
+      float r[8];
 #pragma unroll
-    for (int o = 0; o < 4; ++o) {
-      const float keep = (sub & 4) ? acc[o + 4] : acc[o], give = (sub & 4) ? acc[o] : acc[o + 4];
-      acc[o] = keep + __shfl_xor_sync(0xffffffffu, give, 4);
-    }
+      for (int o = 0; o < 8; ++o) r[o] = a2[o];
 #pragma unroll
-    for (int o = 0; o < 2; ++o) {
-      const float keep = (sub & 2) ? acc[o + 2] : acc[o], give = (sub & 2) ? acc[o] : acc[o + 2];
-      acc[o] = keep + __shfl_xor_sync(0xffffffffu, give, 2);
+      for (int o = 0; o < 4; ++o) {
+        const float keep = (sub & 4) ? r[o + 4] : r[o], give = (sub & 4) ? r[o] : r[o + 4];
+        r[o] = keep + __shfl_xor_sync(0xffffffffu, give, 4);
+      }
+#pragma unroll
+      for (int o = 0; o < 2; ++o) {
+        const float keep = (sub & 2) ? r[o + 2] : r[o], give = (sub & 2) ? r[o] : r[o + 2];
+        r[o] = keep + __shfl_xor_sync(0xffffffffu, give, 2);
+      }
+      {
+        const float keep = (sub & 1) ? r[1] : r[0], give = (sub & 1) ? r[0] : r[1];
+        r[0] = keep + __shfl_xor_sync(0xffffffffu, give, 1);
+      }
+      if (live && do2 && x0 + sub < W) st1<TO>(y + ((long long)b * H + (iy - 1)) * W + x0 + sub, r[0] + b0);
+#pragma unroll
+      for (int o = 0; o < 8; ++o) { a2[o] = a1[o]; a1[o] = a0[o]; a0[o] = 0.f; }
+#pragma unroll
+      for (int hx = 0; hx < 10; ++hx) u[hx] = nx[hx];
     }
-    {
-      const float keep = (sub & 1) ? acc[1] : acc[0], give = (sub & 1) ? acc[0] : acc[1];
-      acc[0] = keep + __shfl_xor_sync(0xffffffffu, give, 1);
-    }
-    if (live && x0 + sub < W) st1<TO>(y + (long long)row_id * W + x0 + sub, acc[0] + b0);
   }
 }
 
@@ -964,10 +999,11 @@ LVAE_API int lvae_conv3x3_narrow_ex(const void* x, const float* w, const float* 
   LVAE_REQUIRE(dense || N == 1, "conv3x3_narrow: a windowed input needs N == 1");
   LVAE_REQUIRE(row_pitch % 8 == 0 && img_pitch % 8 == 0 && ((size_t)x & 15) == 0, "conv3x3_narrow: the window must keep 16-byte alignment");
   if (N == 1 && (long long)B * H * ((W + 7) / 8) < (1LL << 30)) {
-    const long long groups = (long long)B * H * ((W + 7) / 8);
+    const int chunks = cdiv(H, NR_ROWS), R = cdiv(H, chunks);        // H = 28: four chunks of 7 rows
+    const long long groups = (long long)B * chunks * ((W + 7) / 8);
     const int grid = (int)min((long long)8 * lvae_num_sms(), (groups * 8 + 255) / 256);
-    if (out_f32) lvae_launch(conv3x3_narrow1_kernel<float>, grid, 256, 0, stream, (const __nv_bfloat16*)x, w, bias, (float*)y, B, H, W, row_pitch, img_pitch);
-    else lvae_launch(conv3x3_narrow1_kernel<__nv_bfloat16>, grid, 256, 0, stream, (const __nv_bfloat16*)x, w, bias, (__nv_bfloat16*)y, B, H, W, row_pitch, img_pitch);
+    if (out_f32) lvae_launch(conv3x3_narrow1_kernel<float>, grid, 256, 0, stream, (const __nv_bfloat16*)x, w, bias, (float*)y, B, H, W, row_pitch, img_pitch, chunks, R);
+    else lvae_launch(conv3x3_narrow1_kernel<__nv_bfloat16>, grid, 256, 0, stream, (const __nv_bfloat16*)x, w, bias, (__nv_bfloat16*)y, B, H, W, row_pitch, img_pitch, chunks, R);
     LVAE_COUNT_LAUNCH();
     LVAE_CHECK_LAUNCH("conv3x3_narrow");
     return LVAE_OK;

@@ -401,9 +401,15 @@ struct StochBwdArgs {
   const float* g_z;
   const float* g_kl; const float* g_logp; const float* g_logq; const float* g_kls;
   float* dq; float* dp;
+  __nv_bfloat16* dq_lp; __nv_bfloat16* dp_lp;   // optional bf16 copies (same layout): the operands of the tcgen05 dgrad / wgrad of conv_in_q / conv_in_p
   int B, hw, Z, analytical, z_is_sample;  // z_is_sample: 1 rsample, 0 forced latent (no dz/dq path), 2 mode (dz/dmu only)
   long long nvec;                          // B * hw * Z / VEC
 };
+
+__device__ __forceinline__ uint2 pack_bf16x4(float a, float b, float c, float d) {
+  const __nv_bfloat162 lo = __floats2bfloat162_rn(a, b), hi = __floats2bfloat162_rn(c, d);
+  return make_uint2(*reinterpret_cast<const uint32_t*>(&lo), *reinterpret_cast<const uint32_t*>(&hi));
+}
 
 template <int VEC>
 __global__ void __launch_bounds__(256) stoch_bwd_kernel(StochBwdArgs a) {
@@ -467,22 +473,48 @@ __global__ void __launch_bounds__(256) stoch_bwd_kernel(StochBwdArgs a) {
       *reinterpret_cast<float4*>(a.dq + rowq + a.Z + c) = make_float4(dlq[0], dlq[1], dlq[2], dlq[3]);
       *reinterpret_cast<float4*>(a.dp + rowq + c) = make_float4(dmp[0], dmp[1], dmp[2], dmp[3]);
       *reinterpret_cast<float4*>(a.dp + rowq + a.Z + c) = make_float4(dlp[0], dlp[1], dlp[2], dlp[3]);
+      if (a.dq_lp) {
+        *reinterpret_cast<uint2*>(a.dq_lp + rowq + c) = pack_bf16x4(dmq[0], dmq[1], dmq[2], dmq[3]);
+        *reinterpret_cast<uint2*>(a.dq_lp + rowq + a.Z + c) = pack_bf16x4(dlq[0], dlq[1], dlq[2], dlq[3]);
+      }
+      if (a.dp_lp) {
+        *reinterpret_cast<uint2*>(a.dp_lp + rowq + c) = pack_bf16x4(dmp[0], dmp[1], dmp[2], dmp[3]);
+        *reinterpret_cast<uint2*>(a.dp_lp + rowq + a.Z + c) = pack_bf16x4(dlp[0], dlp[1], dlp[2], dlp[3]);
+      }
     } else {
       a.dq[rowq + c] = dmq[0]; a.dq[rowq + a.Z + c] = dlq[0];
       a.dp[rowq + c] = dmp[0]; a.dp[rowq + a.Z + c] = dlp[0];
+      if (a.dq_lp) { a.dq_lp[rowq + c] = __float2bfloat16(dmq[0]); a.dq_lp[rowq + a.Z + c] = __float2bfloat16(dlq[0]); }
+      if (a.dp_lp) { a.dp_lp[rowq + c] = __float2bfloat16(dmp[0]); a.dp_lp[rowq + a.Z + c] = __float2bfloat16(dlp[0]); }
     }
   }
 }
 
 }  // namespace
 
+LVAE_API int lvae_stoch_bwd_ex(const float* q, const float* p, int p_broadcast, const float* z, const float* g_z,
+                               const float* g_kl, const float* g_logp, const float* g_logq, const float* g_kls, float* dq,
+                               float* dp, void* dq_bf16, void* dp_bf16, int B, int hw, int Z, int analytical, int z_kind,
+                               cudaStream_t stream);
+
 LVAE_API int lvae_stoch_bwd(const float* q, const float* p, int p_broadcast, const float* z, const float* g_z,
                             const float* g_kl, const float* g_logp, const float* g_logq, const float* g_kls, float* dq,
                             float* dp, int B, int hw, int Z, int analytical, int z_kind, cudaStream_t stream) {
+  return lvae_stoch_bwd_ex(q, p, p_broadcast, z, g_z, g_kl, g_logp, g_logq, g_kls, dq, dp, nullptr, nullptr, B, hw, Z, analytical,
+                           z_kind, stream);
+}
+
+// dq_bf16 / dp_bf16 (optional): bf16 copies of dq / dp in the same (B,hw,2Z) layout, rounded to nearest even like a cast of
+// the fp32 result -- the tcgen05 dgrad / wgrad of conv_in_q / conv_in_p then read them without a conversion pass.
+LVAE_API int lvae_stoch_bwd_ex(const float* q, const float* p, int p_broadcast, const float* z, const float* g_z,
+                               const float* g_kl, const float* g_logp, const float* g_logq, const float* g_kls, float* dq,
+                               float* dp, void* dq_bf16, void* dp_bf16, int B, int hw, int Z, int analytical, int z_kind,
+                               cudaStream_t stream) {
   LVAE_REQUIRE(q && p && z && dq && dp && B > 0, "stoch_bwd: bad args");
   const int vec = Z % 4 == 0 ? 4 : 1;
   StochBwdArgs a{q, p, p_broadcast ? 0LL : (long long)hw * 2 * Z, z, g_z,
-                 g_kl, g_logp, g_logq, g_kls, dq, dp, B, hw, Z, analytical, z_kind, (long long)B * hw * Z / vec};
+                 g_kl, g_logp, g_logq, g_kls, dq, dp, (__nv_bfloat16*)dq_bf16, (__nv_bfloat16*)dp_bf16,
+                 B, hw, Z, analytical, z_kind, (long long)B * hw * Z / vec};
   const int grid = (int)min((long long)lvae_num_sms() * 8, (a.nvec + 255) / 256);
   if (vec == 4) lvae_launch(stoch_bwd_kernel<4>, grid, 256, 0, stream, a);
   else lvae_launch(stoch_bwd_kernel<1>, grid, 256, 0, stream, a);

@@ -604,7 +604,8 @@ def conv_backward_raw(spec: ConvSpec, xn, x2n, weight, bias, out_scale, gyn, nee
     conv that produced xn).  Returns (gx, gx2, gw, gb); gw / gb are None when accumulated into a gradient sink."""
     grad_site()
     if gyn.dtype != xn.dtype:
-        gyn = gyn.to(xn.dtype)
+        lp = _lowp_grad_take(gyn, xn.dtype) if gyn.dtype == torch.float32 else None
+        gyn = lp if lp is not None else gyn.to(xn.dtype)
     B, Hi, Wi, C1 = xn.shape
     C2 = x2n.shape[3] if x2n is not None else 0
     _, Ho, Wo, N = gyn.shape
@@ -1261,6 +1262,29 @@ def _stoch_workspace(batch: int, device) -> torch.Tensor:
     return ws
 
 
+# fp32 gradient buffer (data_ptr) -> (the fp32 tensor itself, its bf16 copy written by the producing kernel).  The entry keeps the
+# fp32 tensor alive, so the address cannot be handed to another tensor while the entry exists (and autograd, seeing a second
+# reference, never accumulates into it in place); a gradient that autograd summed with another one is a new tensor and misses.
+_lowp_grads: dict = {}
+
+
+def _lowp_grad_put(g32: torch.Tensor, g16: torch.Tensor) -> None:
+    if len(_lowp_grads) > 256:           # entries nobody collected (a consumer that needed no gradient)
+        _lowp_grads.clear()
+    _lowp_grads[g32.data_ptr()] = (g32, g16)
+
+
+def _lowp_grad_take(g32: torch.Tensor, dtype: torch.dtype):
+    """The bf16 copy of this very gradient tensor, if its producer wrote one (else None)."""
+    ent = _lowp_grads.pop(g32.data_ptr(), None)
+    if ent is None:
+        return None
+    k, g16 = ent
+    if g16.dtype != dtype or tuple(g16.shape) != tuple(g32.shape) or k.data_ptr() != g32.data_ptr() or k._version != g32._version:
+        return None
+    return g16
+
+
 class StochasticFn(Function):
     """Everything between conv_in_* and conv_out of NormalStochasticBlock2d (lib/stochastic.py:45-96)."""
 
@@ -1296,6 +1320,7 @@ class StochasticFn(Function):
         ctx.meta = (B, hw, Z, p_broadcast, analytical, 0 if forced is not None else (2 if use_mode else 1))
         ctx.q_dtype = q_params.dtype if q_params is not None else None
         ctx.p_dtype = p_params.dtype
+        ctx.lowp = bool(lowp_copy)
         zo = as_nchw(z)
         zlo = as_nchw(z_lp) if z_lp is not None else None
         if zlo is not None:
@@ -1313,9 +1338,17 @@ class StochasticFn(Function):
         g_kl, g_kls, g_logp, g_logq = cg(g_kl), cg(g_kls), cg(g_logp), cg(g_logq)
         dq = torch.empty_like(qn)
         dp = torch.empty((B,) + tuple(qn.shape[1:]), dtype=torch.float32, device=qn.device)
-        call("lvae_stoch_bwd", qn.data_ptr(), pn.data_ptr(), 1 if p_broadcast else 0, z.data_ptr(), _p(gz), _p(g_kl),
-             _p(g_logp), _p(g_logq), _p(g_kls), dq.data_ptr(), dp.data_ptr(), B, hw, Z, 1 if analytical else 0,
-             z_kind, _stream())
+        # bf16 pipeline: the kernel also writes bf16 copies of dq / dp, which the tensor-core data / weight gradients of conv_in_q /
+        # conv_in_p pick up from _lowp_grads instead of casting the fp32 gradient autograd hands them (29 ATen launches per step)
+        dq_lp = torch.empty(qn.shape, dtype=torch.bfloat16, device=qn.device) if ctx.lowp and 2 * Z == 64 else None
+        dp_lp = torch.empty(qn.shape, dtype=torch.bfloat16, device=qn.device) if dq_lp is not None and not p_broadcast else None
+        call("lvae_stoch_bwd_ex", qn.data_ptr(), pn.data_ptr(), 1 if p_broadcast else 0, z.data_ptr(), _p(gz), _p(g_kl),
+             _p(g_logp), _p(g_logq), _p(g_kls), dq.data_ptr(), dp.data_ptr(), _p(dq_lp), _p(dp_lp), B, hw, Z,
+             1 if analytical else 0, z_kind, _stream())
+        if dq_lp is not None and ctx.q_dtype == torch.float32:
+            _lowp_grad_put(dq, dq_lp)
+        if dp_lp is not None and ctx.p_dtype == torch.float32:
+            _lowp_grad_put(dp, dp_lp)
         if p_broadcast:
             dps = torch.empty_like(pn)
             call("lvae_sum_batch", dp.data_ptr(), dps.data_ptr(), B, dps.numel(), 0, _stream())
