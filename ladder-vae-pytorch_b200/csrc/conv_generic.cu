@@ -270,15 +270,40 @@ __global__ void __launch_bounds__(256) conv_stem5x5s2_kernel(const T* __restrict
   const int b = blockIdx.x / tiles_per_img;
   const int tr = blockIdx.x - b * tiles_per_img;
   const int oy0 = (tr / tiles_x) * ST_TILE, ox0 = (tr - (tr / tiles_x) * tiles_x) * ST_TILE;
-  for (int i = t; i < K * 64; i += 256) ws[i >> 6][i & 63] = ld1<T>(wp + (size_t)(i >> 6) * ldw + (i & 63));
+  // staging: the loads of a thread are issued in batches of eight before the first shared-memory store (one round trip to L2
+  // per batch instead of one per element: the 19 + 15 dependent iterations of the plain loops were two thirds of the kernel)
   const int iy0 = 2 * oy0 - 2, ix0 = 2 * ox0 - 2;
   const T* xb = x + (size_t)b * Hi * Wi * C;
-  for (int i = t; i < ST_PATCH * ST_PATCH * C; i += 256) {
-    const int r = i / (ST_PATCH * C), e = i - r * (ST_PATCH * C);
-    const int iy = iy0 + r, ix = ix0 + e / C;
-    float v = 0.f;
-    if (iy >= 0 && iy < Hi && ix >= 0 && ix < Wi) v = ld1<T>(xb + ((size_t)iy * Wi + ix) * C + (e - (e / C) * C));
-    xs[r][e] = v;
+  for (int base = t; base < K * 64; base += 8 * 256) {
+    float v[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int i = base + u * 256;
+      v[u] = i < K * 64 ? ld1<T>(wp + (size_t)(i >> 6) * ldw + (i & 63)) : 0.f;
+    }
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int i = base + u * 256;
+      if (i < K * 64) ws[i >> 6][i & 63] = v[u];
+    }
+  }
+  for (int base = t; base < ST_PATCH * ST_PATCH * C; base += 8 * 256) {
+    float v[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int i = base + u * 256;
+      const int r = i / (ST_PATCH * C), e = i - r * (ST_PATCH * C);
+      const int iy = iy0 + r, ix = ix0 + e / C;
+      v[u] = 0.f;
+      if (i < ST_PATCH * ST_PATCH * C && iy >= 0 && iy < Hi && ix >= 0 && ix < Wi)
+        v[u] = ld1<T>(xb + ((size_t)iy * Wi + ix) * C + (e - (e / C) * C));
+    }
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int i = base + u * 256;
+      const int r = i / (ST_PATCH * C), e = i - r * (ST_PATCH * C);
+      if (i < ST_PATCH * ST_PATCH * C) xs[r][e] = v[u];
+    }
   }
   __syncthreads();
   const int pp = t & 127, n0 = (t >> 7) * 32;           // the channel half is warp-uniform: weight reads are broadcasts
@@ -583,19 +608,40 @@ __global__ void __launch_bounds__(256) wgrad_stem5x5s2_kernel(const T* __restric
     const int iy0 = 2 * oy0 - 2, ix0 = 2 * ox0 - 2;
     const T* ub = u + (size_t)b * Hi * Wi * C;
     __syncthreads();                                    // the previous tile has been consumed
-    for (int i = t; i < SW_PR * ST_PATCH * C; i += 256) {
-      const int r = i / (ST_PATCH * C), e = i - r * (ST_PATCH * C);
-      const int iy = iy0 + r, ix = ix0 + e / C;
-      float v = 0.f;
-      if (iy >= 0 && iy < Hi && ix >= 0 && ix < Wi) v = ld1<T>(ub + ((size_t)iy * Wi + ix) * C + (e - (e / C) * C));
-      xs[r][e] = v;
-    }
-    for (int i = t; i < SW_ROWS * ST_TILE * 16; i += 256) {
-      const int p = i >> 4, c4 = (i & 15) * 4;
-      const int oy = oy0 + (p >> 4), ox = ox0 + (p & 15);
-      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (oy < Ho && ox < Wo) v = ld4<T>(dz + (((size_t)b * Ho + oy) * Wo + ox) * 64 + c4);
-      *reinterpret_cast<float4*>(&ds[p][c4]) = v;
+    {
+      // all 8 + 8 staging loads of a thread are in flight before the first shared-memory store (SW_PR * ST_PATCH * C <= 8 * 256,
+      // SW_ROWS * ST_TILE * 16 = 8 * 256): one round trip per tile instead of sixteen dependent ones
+      static_assert(SW_PR * ST_PATCH * C <= 8 * 256 && SW_ROWS * ST_TILE * 16 == 8 * 256, "staging assumes eight items per thread");
+      float xv8[8];
+      float4 dv8[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int i = t + u * 256;
+        const int r = i / (ST_PATCH * C), e = i - r * (ST_PATCH * C);
+        const int iy = iy0 + r, ix = ix0 + e / C;
+        xv8[u] = 0.f;
+        if (i < SW_PR * ST_PATCH * C && iy >= 0 && iy < Hi && ix >= 0 && ix < Wi)
+          xv8[u] = ld1<T>(ub + ((size_t)iy * Wi + ix) * C + (e - (e / C) * C));
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int i = t + u * 256;
+        const int p = i >> 4, c4 = (i & 15) * 4;
+        const int oy = oy0 + (p >> 4), ox = ox0 + (p & 15);
+        dv8[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (oy < Ho && ox < Wo) dv8[u] = ld4<T>(dz + (((size_t)b * Ho + oy) * Wo + ox) * 64 + c4);
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int i = t + u * 256;
+        const int r = i / (ST_PATCH * C), e = i - r * (ST_PATCH * C);
+        if (i < SW_PR * ST_PATCH * C) xs[r][e] = xv8[u];
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int i = t + u * 256;
+        *reinterpret_cast<float4*>(&ds[i >> 4][(i & 15) * 4]) = dv8[u];
+      }
     }
     __syncthreads();
     if (active) {

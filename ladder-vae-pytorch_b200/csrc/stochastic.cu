@@ -538,13 +538,17 @@ __global__ void __launch_bounds__(256) kl_bookkeeping_kernel(const float* __rest
                                                              float* __restrict__ coef) {
   pdl_wait();
   pdl_launch();
-  __shared__ float red[32];
+  // One warp per layer (layers warp, warp + 8, ...): lane-strided partial sums over the batch and one shuffle tree per statistic,
+  // no block-wide barrier inside the layer loop (36-45 of them in a row made this one-CTA launch 25-60 us long); the eight
+  // warps' totals meet once at the end, in a fixed order.
+  __shared__ float tot[8][3];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const float invB = 1.f / (float)B;
   const bool clamp = free_bits >= 1e-6f;
-  float tot_kl = 0.f, tot_loss = 0.f, tot_lp = 0.f;        // valid in thread 0
-  for (int l = 0; l < L; ++l) {
+  float tot_kl = 0.f, tot_loss = 0.f, tot_lp = 0.f;
+  for (int l = warp; l < L; l += 8) {
     float s = 0.f, sf = 0.f, sp = 0.f;
-    for (int b = threadIdx.x; b < B; b += blockDim.x) {
+    for (int b = lane; b < B; b += 32) {
       const float v = kl[(long long)l * B + b];
       const bool pass = !clamp || v >= free_bits;          // torch.clamp(min): gradient 1 where kl >= free_bits
       s += v;
@@ -552,20 +556,28 @@ __global__ void __launch_bounds__(256) kl_bookkeeping_kernel(const float* __rest
       if (coef) coef[(long long)l * B + b] = pass ? invB : 0.f;
       if (lp) sp += lp[(long long)l * B + b];
     }
-    s = block_sum(s, red);
-    sf = block_sum(sf, red);
-    sp = block_sum(sp, red);
-    if (threadIdx.x == 0) {
-      kl_avg[l] = s * invB;
-      tot_kl += s * invB; tot_loss += sf * invB; tot_lp += sp * invB;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      s += __shfl_xor_sync(0xffffffffu, s, o);
+      sf += __shfl_xor_sync(0xffffffffu, sf, o);
+      sp += __shfl_xor_sync(0xffffffffu, sp, o);
     }
+    if (lane == 0) kl_avg[l] = s * invB;
+    tot_kl += s * invB; tot_loss += sf * invB; tot_lp += sp * invB;
   }
+  if (lane == 0) { tot[warp][0] = tot_kl; tot[warp][1] = tot_loss; tot[warp][2] = tot_lp; }
   for (int b = threadIdx.x; b < B; b += blockDim.x) {
     float s = 0.f;
     for (int l = 0; l < L; ++l) s += kl[(long long)l * B + b];
     kl_sep[b] = s;
   }
-  if (threadIdx.x == 0) { scalars[0] = tot_kl; scalars[1] = tot_loss; scalars[2] = tot_lp; }
+  __syncthreads();
+  if (threadIdx.x < 3) {
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) t += tot[w][threadIdx.x];
+    scalars[threadIdx.x] = t;
+  }
 }
 
 // scalars: float[3] = {kl, kl_loss, logp}; logp_rows / coef may be NULL
