@@ -299,6 +299,11 @@ int lvae_adamax_step(float* p, const float* g, float* exp_avg, float* exp_inf, l
                      float beta2, float eps, float weight_decay, long long* step_count_dev, float grad_scale,
                      const float* hyper_dev, lvae_stream_t stream);
 int lvae_l2_norm(const float* p, long long n, double* acc, float* out, lvae_stream_t stream);
+/* lvae_adamax_step followed by lvae_l2_norm of the updated parameters, in one pass over the arena (l2_acc: device double scratch,
+ * zero on entry, cleared on exit; l2_out[0] = sqrt(sum p^2)). */
+int lvae_adamax_step_l2(float* p, const float* g, float* exp_avg, float* exp_inf, long long n, float lr, float beta1,
+                        float beta2, float eps, float weight_decay, long long* step_count_dev, float grad_scale,
+                        const float* hyper_dev, double* l2_acc, float* l2_out, lvae_stream_t stream);
 
 /* ---- importance-weighted bound (boilr test_procedure, call site evaluate.py:30) ----
  * state (B,2) = running (max, sum exp) of elbo = ll - kl over samples; combine merges R ranks' states. */

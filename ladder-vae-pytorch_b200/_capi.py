@@ -64,6 +64,7 @@ _SIGNATURES = {
     "lvae_dmol_bwd": [P, P, P, P, P, I, I, P],
     "lvae_dmol_sample": [P, P, I, I, P, U, P],
     "lvae_adamax_step": [P, P, P, P, L, F, F, F, F, F, P, F, P, P],
+    "lvae_adamax_step_l2": [P, P, P, P, L, F, F, F, F, F, P, F, P, P, P, P],
     "lvae_l2_norm": [P, L, P, P, P],
     "lvae_iw_lse_update": [P, P, P, I, I, P],
     "lvae_iw_lse_combine": [P, P, I, I, I, P],

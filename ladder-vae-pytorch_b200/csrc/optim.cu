@@ -5,42 +5,96 @@
 
 // ---- Adamax over a flat parameter arena (torch.optim.Adamax semantics) ----
 // step_count: device int64, incremented here so the captured graph advances on replay.
-__global__ void adamax_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
-                              float* __restrict__ u, long long n, float lr, float b1, float b2, float eps, float wd,
-                              const long long* __restrict__ step_count, float grad_scale,
-                              const float* __restrict__ hyper) {
+// 16-byte accesses (four parameters per thread and iteration: the scalar version kept ~32 KB per SM in flight, short of what
+// HBM3e needs, 85-95 us for the 14.5 M parameters of the CIFAR-15 model) and, with L2, the sum of squares of the UPDATED
+// parameters for the global L2 norm of experiment_manager.py:346-350 in the same pass (it used to be a second read of the arena).
+template <bool L2>
+__global__ void __launch_bounds__(256) adamax_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                                                     float* __restrict__ u, long long n, float lr, float b1, float b2, float eps,
+                                                     float wd, const long long* __restrict__ step_count, float grad_scale,
+                                                     const float* __restrict__ hyper, double* __restrict__ l2_acc) {
   pdl_wait();
   pdl_launch();
+  __shared__ float red[32];
   if (hyper) { lr = hyper[0]; wd = hyper[1]; }     // device-resident learning rate / weight decay: a captured graph follows them
   const double t = (double)(*step_count);
   const float clr = lr / (float)(1.0 - pow((double)b1, t));
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-    float gi = g[i] * grad_scale;
-    float pi = p[i];
+  float ss = 0.f;
+  auto upd = [&](float gi, float pi, float& mi, float& ui) {
+    gi *= grad_scale;
     if (wd != 0.f) gi += wd * pi;
-    float mi = b1 * m[i] + (1.f - b1) * gi;
-    float ui = fmaxf(b2 * u[i], fabsf(gi) + eps);
+    mi = b1 * mi + (1.f - b1) * gi;
+    ui = fmaxf(b2 * ui, fabsf(gi) + eps);
+    const float pn = pi - clr * (mi / ui);
+    if (L2) ss += pn * pn;
+    return pn;
+  };
+  const long long n4 = n >> 2;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    const float4 g4 = reinterpret_cast<const float4*>(g)[i];
+    float4 p4 = reinterpret_cast<float4*>(p)[i], m4 = reinterpret_cast<float4*>(m)[i], u4 = reinterpret_cast<float4*>(u)[i];
+    p4.x = upd(g4.x, p4.x, m4.x, u4.x);
+    p4.y = upd(g4.y, p4.y, m4.y, u4.y);
+    p4.z = upd(g4.z, p4.z, m4.z, u4.z);
+    p4.w = upd(g4.w, p4.w, m4.w, u4.w);
+    reinterpret_cast<float4*>(m)[i] = m4;
+    reinterpret_cast<float4*>(u)[i] = u4;
+    reinterpret_cast<float4*>(p)[i] = p4;
+  }
+  for (long long i = (n4 << 2) + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    float mi = m[i], ui = u[i];
+    p[i] = upd(g[i], p[i], mi, ui);
     m[i] = mi;
     u[i] = ui;
-    p[i] = pi - clr * (mi / ui);
+  }
+  if (L2) {
+    ss = block_sum(ss, red);
+    if (threadIdx.x == 0) atomicAdd(l2_acc, (double)ss);
   }
 }
 __global__ void step_inc_kernel(long long* s) {
   pdl_wait();
   pdl_launch(); *s += 1; }
+__global__ void sqrt_finalize_kernel(double* acc, float* out);
+
+static int adamax_launch(float* p, const float* g, float* exp_avg, float* exp_inf, long long n, float lr, float beta1, float beta2,
+                         float eps, float weight_decay, long long* step_count_dev, float grad_scale, const float* hyper_dev,
+                         double* l2_acc, float* l2_out, cudaStream_t stream) {
+  LVAE_REQUIRE(p && g && exp_avg && exp_inf && step_count_dev && n > 0, "adamax_step: bad args");
+  LVAE_REQUIRE((((size_t)p | (size_t)g | (size_t)exp_avg | (size_t)exp_inf) & 15) == 0, "adamax_step: the arenas must be 16-byte aligned");
+  lvae_launch(step_inc_kernel, 1, 1, 0, stream, step_count_dev);
+  LVAE_COUNT_LAUNCH();
+  int grid = (int)min((long long)8 * lvae_num_sms(), ((n >> 2) + 255) / 256 + 1);
+  if (l2_acc)
+    lvae_launch(adamax_kernel<true>, grid, 256, 0, stream, p, g, exp_avg, exp_inf, n, lr, beta1, beta2, eps, weight_decay,
+                step_count_dev, grad_scale, hyper_dev, l2_acc);
+  else
+    lvae_launch(adamax_kernel<false>, grid, 256, 0, stream, p, g, exp_avg, exp_inf, n, lr, beta1, beta2, eps, weight_decay,
+                step_count_dev, grad_scale, hyper_dev, l2_acc);
+  LVAE_COUNT_LAUNCH();
+  if (l2_acc) {
+    lvae_launch(sqrt_finalize_kernel, 1, 1, 0, stream, l2_acc, l2_out);
+    LVAE_COUNT_LAUNCH();
+  }
+  LVAE_CHECK_LAUNCH("adamax_step");
+  return LVAE_OK;
+}
 
 LVAE_API int lvae_adamax_step(float* p, const float* g, float* exp_avg, float* exp_inf, long long n, float lr,
                               float beta1, float beta2, float eps, float weight_decay, long long* step_count_dev,
                               float grad_scale, const float* hyper_dev, cudaStream_t stream) {
-  LVAE_REQUIRE(p && g && exp_avg && exp_inf && step_count_dev && n > 0, "adamax_step: bad args");
-  lvae_launch(step_inc_kernel, 1, 1, 0, stream, step_count_dev);
-  LVAE_COUNT_LAUNCH();
-  int grid = (int)min((long long)8 * lvae_num_sms(), (n + 255) / 256);
-  lvae_launch(adamax_kernel, grid, 256, 0, stream, p, g, exp_avg, exp_inf, n, lr, beta1, beta2, eps, weight_decay,
-                                          step_count_dev, grad_scale, hyper_dev);
-  LVAE_COUNT_LAUNCH();
-  LVAE_CHECK_LAUNCH("adamax_step");
-  return LVAE_OK;
+  return adamax_launch(p, g, exp_avg, exp_inf, n, lr, beta1, beta2, eps, weight_decay, step_count_dev, grad_scale, hyper_dev,
+                       nullptr, nullptr, stream);
+}
+
+// The same step, and l2_out[0] = sqrt(sum p^2) of the updated parameters (what lvae_l2_norm would return right after it).
+// l2_acc: device double scratch, zero on entry, cleared again on exit.
+LVAE_API int lvae_adamax_step_l2(float* p, const float* g, float* exp_avg, float* exp_inf, long long n, float lr,
+                                 float beta1, float beta2, float eps, float weight_decay, long long* step_count_dev,
+                                 float grad_scale, const float* hyper_dev, double* l2_acc, float* l2_out, cudaStream_t stream) {
+  LVAE_REQUIRE(l2_acc && l2_out, "adamax_step_l2: null pointer");
+  return adamax_launch(p, g, exp_avg, exp_inf, n, lr, beta1, beta2, eps, weight_decay, step_count_dev, grad_scale, hyper_dev,
+                       l2_acc, l2_out, stream);
 }
 
 // ---- global L2 norm of a flat arena: out[0] = sqrt(sum p^2) ----

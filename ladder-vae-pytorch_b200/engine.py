@@ -425,11 +425,14 @@ class TrainEngine:
 
     def _optimizer(self):
         a = self.arena
-        call("lvae_adamax_step", a.flat.data_ptr(), a.grad.data_ptr(), self.exp_avg.data_ptr(), self.exp_inf.data_ptr(),
-             a.numel, self._lr, self.betas[0], self.betas[1], self.eps, self._wd, self.step_count.data_ptr(),
-             1.0 / self.world, self._hyper.data_ptr(), _stream())
-        if self.compute_l2:
-            call("lvae_l2_norm", a.flat.data_ptr(), a.numel, self.l2_acc.data_ptr(), self.l2.data_ptr(), _stream())
+        if self.compute_l2:        # the L2 norm of the updated parameters (experiment_manager.py:346-350) rides on the Adamax pass
+            call("lvae_adamax_step_l2", a.flat.data_ptr(), a.grad.data_ptr(), self.exp_avg.data_ptr(), self.exp_inf.data_ptr(),
+                 a.numel, self._lr, self.betas[0], self.betas[1], self.eps, self._wd, self.step_count.data_ptr(),
+                 1.0 / self.world, self._hyper.data_ptr(), self.l2_acc.data_ptr(), self.l2.data_ptr(), _stream())
+        else:
+            call("lvae_adamax_step", a.flat.data_ptr(), a.grad.data_ptr(), self.exp_avg.data_ptr(), self.exp_inf.data_ptr(),
+                 a.numel, self._lr, self.betas[0], self.betas[1], self.eps, self._wd, self.step_count.data_ptr(),
+                 1.0 / self.world, self._hyper.data_ptr(), _stream())
         self.out["l2"] = self.l2
 
     def _eager_step(self):

@@ -473,6 +473,13 @@ def test_adamax_l2_iw(L):
     out = torch.zeros((), device="cuda")
     _capi.call("lvae_l2_norm", pd.data_ptr(), n, acc.data_ptr(), out.data_ptr(), s)
     assert rel_err(out, pr.pow(2).sum().sqrt()) < 1e-6 and float(acc) == 0.0
+    # the fused form: one more step, with the norm of the updated parameters from the same pass
+    gr = torch.randn(n, generator=g, dtype=torch.float64)
+    O.adamax_step(pr, gr, ea, ei, 4)
+    _capi.call("lvae_adamax_step_l2", pd.data_ptr(), dev(gr).data_ptr(), m.data_ptr(), u.data_ptr(), n, 3e-4, 0.9, 0.999,
+               1e-8, 0.0, step.data_ptr(), 1.0, None, acc.data_ptr(), out.data_ptr(), s)
+    assert int(step) == 4 and rel_err(pd, pr) < 1e-6
+    assert rel_err(out, pr.pow(2).sum().sqrt()) < 1e-6 and float(acc) == 0.0
     # IW bound: streaming logsumexp over K samples split over R "ranks"
     B, K, R = 37, 12, 3
     ll = torch.randn(K, B, generator=g, dtype=torch.float64) * 50 - 800
