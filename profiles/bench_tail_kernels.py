@@ -94,3 +94,8 @@ hy = torch.empty(Bi, 28, 28, 1, device="cuda")
 timeit("conv3x3_narrow1 (1000,28,28,64) window -> 1, fp32 out",
        lambda i: _capi.call("lvae_conv3x3_narrow_ex", hx[i][:, 2:, 2:].data_ptr(), hw_.data_ptr(), hb.data_ptr(), hy.data_ptr(), Bi, 28, 28, 1,
                             1, 32 * 64, 32 * 32 * 64, S()), 3, nbytes=Bi * 28 * 28 * 64 * 2)
+
+# --- batch sum of the top prior's gradient: (256, 2x2x64) fp32 -> (2x2x64) ----------------------------------------------
+dpb = [torch.randn(256, 256, device="cuda") for _ in range(3)]
+dps = torch.empty(256, device="cuda")
+timeit("sum_batch (256, 256) -> (256)", lambda i: _capi.call("lvae_sum_batch", dpb[i].data_ptr(), dps.data_ptr(), 256, 256, 0, S()), 3)
