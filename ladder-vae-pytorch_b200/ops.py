@@ -1262,7 +1262,7 @@ def _stoch_workspace(batch: int, device) -> torch.Tensor:
     return ws
 
 
-# fp32 gradient buffer (data_ptr) -> (the fp32 tensor itself, its bf16 copy written by the producing kernel).  The entry keeps the
+# fp32 gradient buffer (data_ptr) -> (the fp32 tensor itself, its bf16 copy written by the producing kernel, the buffer's version).  The entry keeps the
 # fp32 tensor alive, so the address cannot be handed to another tensor while the entry exists (and autograd, seeing a second
 # reference, never accumulates into it in place); a gradient that autograd summed with another one is a new tensor and misses.
 _lowp_grads: dict = {}
@@ -1271,7 +1271,7 @@ _lowp_grads: dict = {}
 def _lowp_grad_put(g32: torch.Tensor, g16: torch.Tensor) -> None:
     if len(_lowp_grads) > 256:           # entries nobody collected (a consumer that needed no gradient)
         _lowp_grads.clear()
-    _lowp_grads[g32.data_ptr()] = (g32, g16)
+    _lowp_grads[g32.data_ptr()] = (g32, g16, g32._version)
 
 
 def _lowp_grad_take(g32: torch.Tensor, dtype: torch.dtype):
@@ -1279,8 +1279,9 @@ def _lowp_grad_take(g32: torch.Tensor, dtype: torch.dtype):
     ent = _lowp_grads.pop(g32.data_ptr(), None)
     if ent is None:
         return None
-    k, g16 = ent
-    if g16.dtype != dtype or tuple(g16.shape) != tuple(g32.shape) or k.data_ptr() != g32.data_ptr() or k._version != g32._version:
+    k, g16, version = ent
+    # (an in-place write to the fp32 buffer after the copy was taken moves its version counter: the copy is stale)
+    if g16.dtype != dtype or tuple(g16.shape) != tuple(g32.shape) or k.data_ptr() != g32.data_ptr() or g32._version != version:
         return None
     return g16
 

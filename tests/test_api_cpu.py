@@ -76,3 +76,38 @@ def test_free_bits_matches_loader_stub():
             assert torch.equal(free_bits_kl(kl, fb, batch_average=ba), stub(kl, fb, batch_average=ba))
     out = free_bits_kl(kl, 1.0)
     assert tuple(out.shape) == (4,) and float(out.min()) >= 1.0
+
+
+def test_low_precision_gradient_side_table():
+    """ops._lowp_grads hands the bf16 copy a producing kernel wrote to the consumer of the SAME fp32 gradient tensor and to
+    nobody else (host logic only: CPU tensors stand in for device buffers)."""
+    from lvae_b200 import ops
+    ops._lowp_grads.clear()
+    g32 = torch.randn(2, 4, 4, 64)
+    g16 = g32.bfloat16()
+    ops._lowp_grad_put(g32, g16)
+    view = g32.permute(0, 3, 1, 2).permute(0, 2, 3, 1)                 # what autograd hands on: a view of the same storage
+    assert ops._lowp_grad_take(view, torch.bfloat16) is g16
+    assert ops._lowp_grad_take(view, torch.bfloat16) is None           # collected once
+    # a gradient that autograd summed with another one is a new tensor: no entry
+    ops._lowp_grad_put(g32, g16)
+    assert ops._lowp_grad_take(g32 + 1.0, torch.bfloat16) is None
+    # the buffer was written after the copy was taken (version counter moved): the copy is stale
+    g32.add_(1.0)
+    assert ops._lowp_grad_take(g32, torch.bfloat16) is None
+    # wrong dtype / shape on the consumer side
+    ops._lowp_grad_put(g32, g16)
+    assert ops._lowp_grad_take(g32, torch.float16) is None
+    ops._lowp_grad_put(g32, g16[:1])
+    assert ops._lowp_grad_take(g32, torch.bfloat16) is None
+    # the entry keeps the fp32 tensor alive, so its address cannot be recycled while the entry exists
+    ops._lowp_grad_put(g32, g16)
+    ptr = g32.data_ptr()
+    del g32, view
+    assert ops._lowp_grads[ptr][0].data_ptr() == ptr and len(ops._lowp_grads[ptr]) == 3
+    # uncollected entries are dropped wholesale, not accumulated forever
+    keep = [torch.zeros(1) for _ in range(300)]
+    for t in keep:
+        ops._lowp_grad_put(t, t.bfloat16())
+    assert len(ops._lowp_grads) <= 257
+    ops._lowp_grads.clear()
