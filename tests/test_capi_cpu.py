@@ -41,6 +41,50 @@ def test_binding_covers_header(libpath):
     lvae_b200._capi.lib()       # loads and resolves every bound symbol
 
 
+def header_prototypes():
+    """name -> list of parameter kinds ('P' pointer, 'I' int, 'L' long long, 'U' unsigned long long, 'F' float) parsed from the header."""
+    text = open(os.path.join(ROOT, "include", "lvae_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    text = re.sub(r"//[^\n]*", "", text)
+    protos = {}
+    for m in re.finditer(r"\b(lvae_[a-z0-9_]+)\s*\(([^()]*)\)\s*;", text):
+        name, args = m.group(1), m.group(2).strip()
+        kinds = []
+        if args and args != "void":
+            for a in args.split(","):
+                a = " ".join(a.split())
+                if "*" in a or "lvae_stream_t" in a:
+                    kinds.append("P")
+                elif "unsigned long long" in a:
+                    kinds.append("U")
+                elif "long long" in a:
+                    kinds.append("L")
+                elif "float" in a:
+                    kinds.append("F")
+                elif "int" in a:
+                    kinds.append("I")
+                else:
+                    raise AssertionError("unparsed parameter %r of %s" % (a, name))
+        protos[name] = kinds
+    return protos
+
+
+def test_binding_signatures_match_header(libpath):
+    """Every ctypes argtypes list has the arity and the parameter kinds of the prototype in include/lvae_b200.h (a pointer passed
+    where the library expects a long long is silent corruption, not an exception)."""
+    import lvae_b200
+    capi = lvae_b200._capi
+    kind = {ctypes.c_void_p: "P", ctypes.c_char_p: "P", ctypes.c_int: "I", ctypes.c_longlong: "L", ctypes.c_ulonglong: "U",
+            ctypes.c_float: "F"}
+    protos = header_prototypes()
+    bound = dict(capi._SIGNATURES)
+    bound.update({k: v[0] for k, v in capi._SPECIAL.items()})
+    assert sorted(bound) == sorted(protos)
+    for name, argtypes in bound.items():
+        got = [kind[t] for t in argtypes]
+        assert got == protos[name], "%s: binding %s vs header %s" % (name, "".join(got), "".join(protos[name]))
+
+
 def test_no_cpu_fallback(libpath):
     import lvae_b200
     from oracle import lvae_oracle as O
