@@ -194,3 +194,51 @@ def test_grad_ready_order_and_iw_shard_offsets():
     seq = [first[g] for g in ("likelihood.", "final_top_down.", "top_down_layers.0.", "top_down_layers.2.",
                               "bottom_up_layers.2.", "bottom_up_layers.0.", "first_bottom_up.")]
     assert seq == sorted(seq)                       # the order LadderVAE's backward finishes them in
+
+
+def test_bucket_cuts_and_sample_shards_property():
+    """Randomised invariants of the two partitioners the multi-GPU paths rest on (hypothesis): gradient buckets tile the arena,
+    are cut on tensor boundaries only and close as soon as they reach the size target; sample shards tile [0, K) in rank order
+    with sizes that differ by at most one."""
+    import sys
+    sys.path.insert(0, ROOT)
+    from hypothesis import given, settings, strategies as st
+    from lvae_b200.engine import bucket_ranges_aligned, bucket_ranges, shard_samples
+
+    @settings(max_examples=200, deadline=None)
+    @given(st.lists(st.integers(min_value=1, max_value=5000), min_size=1, max_size=60), st.integers(min_value=4, max_value=40000))
+    def buckets(sizes, bucket_bytes):
+        starts, pos = [], 0
+        for n in sizes:
+            starts.append(pos)
+            pos += n
+        numel = pos
+        cuts = bucket_ranges_aligned(starts, numel, bucket_bytes)
+        per = max(1, bucket_bytes // 4)
+        assert cuts[0][0] == 0 and cuts[-1][1] == numel
+        for (a, b), (c, _) in zip(cuts, cuts[1:]):
+            assert b == c                                  # contiguous, no gap, no overlap
+        sset = set(starts)
+        for a, b in cuts:
+            assert a in sset and a < b                     # every cut is a tensor boundary; no empty bucket
+        for a, b in cuts[:-1]:
+            assert b - a >= per                            # a bucket closes only once it has reached the target ...
+            last_start = max(s for s in starts if s < b)
+            assert last_start - a < per                    # ... and does so at the first tensor boundary past it
+        plain = bucket_ranges(numel, bucket_bytes)
+        assert plain[0][0] == 0 and plain[-1][1] == numel and all(b - a <= per for a, b in plain)
+
+    @settings(max_examples=200, deadline=None)
+    @given(st.integers(min_value=0, max_value=5000), st.integers(min_value=1, max_value=64))
+    def shards(k, world):
+        parts = [shard_samples(k, r, world) for r in range(world)]
+        pos = 0
+        for s, c in parts:
+            assert s == pos and c >= 0
+            pos += c
+        assert pos == k
+        sizes = [c for _, c in parts]
+        assert max(sizes) - min(sizes) <= 1 and sizes == sorted(sizes, reverse=True)
+
+    buckets()
+    shards()
